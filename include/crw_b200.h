@@ -1,0 +1,148 @@
+/*
+ * crw_b200.h -- C ABI of libcrw_b200.so: the B200 (sm_100a) CRW hot path.
+ *
+ * The reference (jdalcorso/radar-sounder-crw) has no FFI of its own: its hot path is
+ * Python calling ATen.  The entry points below are what a maintainer would bind from
+ * the reference's call sites (ctypes stubs are shown in INTEGRATION.md); each one names
+ * the reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer (cudaMalloc'd / torch CUDA tensor
+ *     storage); the library never allocates, frees or synchronises;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); calls are re-entrant per stream, there is no global state;
+ *   - return value: CRW_OK, a negative CRW_ERR_* code, or -(1000 + cudaError_t) when
+ *     a launch failed; no exceptions cross the boundary;
+ *   - tensors are dense row-major fp32 unless said otherwise; shapes in brackets.
+ *
+ * Symbols:  B batch, T frames, N nodes per frame, C channels, M classes, R radargrams,
+ *           k top-k, ctx context frames, tau / temp temperature.
+ */
+#ifndef CRW_B200_H_
+#define CRW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRW_OK 0
+#define CRW_ERR_INVALID (-1)     /* bad shape / parameter / null pointer            */
+#define CRW_ERR_UNSUPPORTED (-2) /* valid request this build cannot serve (k > 32 ...) */
+#define CRW_ERR_ALIGN (-3)       /* pointer not 16-byte aligned or C % 4 != 0         */
+#define CRW_ERR_WORKSPACE (-4)   /* workspace too small                               */
+#define CRW_ERR_CUDA_BASE (-1000)
+
+/* precision selectors */
+#define CRW_PREC_FP32 0        /* fp32 FMA, pinned order: bit-comparable with oracle/crw_oracle.c */
+#define CRW_PREC_BF16X3 1      /* tcgen05 kind::f16, error-compensated bf16 hi/lo (3 MMAs), fp32 accumulate */
+#define CRW_PREC_TF32 2        /* tcgen05 kind::tf32 (walk GEMMs), fp32 accumulate */
+
+/* label-propagation gather modes */
+#define CRW_LP_REF_EXACT 0     /* reproduce the reference's context-trim gather quirk */
+#define CRW_LP_FIXED 1         /* gather from the frames the keys came from           */
+
+int crw_version(void);
+const char* crw_error_string(int code);
+/* compute capability the library was built for (100 = sm_100a) */
+int crw_built_arch(void);
+
+/* ------------------------------------------------------------------------------------
+ * L2 normalisation -- replaces F.normalize(emb, dim=-1): src/model.py:22, src/utils.py:115
+ *   x, out [rows, C]; out may alias x.
+ * ---------------------------------------------------------------------------------- */
+int crw_l2_normalize(const float* x, int64_t rows, int C, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Training walk -- replaces the tail of CRW.forward, src/model.py:22-46:
+ *   normalise, stride-1 affinities / tau (model.py:26), palindrome walk (model.py:31-44),
+ *   cycle cross-entropy (model.py:45), return loss/N (model.py:46).
+ *   x        [B,T,N,C]  raw encoder output (un-normalised)
+ *   loss     [1]        loss/N
+ *   A        [B,T-1,N,N] or NULL   the affinities the reference also returns (model.py:46)
+ *   saved    workspace of crw_walk_saved_bytes(): state kept for the backward pass
+ * T < 3 gives loss = 0 exactly as the reference's empty loop (model.py:33-35).
+ * ---------------------------------------------------------------------------------- */
+size_t crw_walk_saved_bytes(int B, int T, int N, int C);
+int crw_walk_forward(const float* x, int B, int T, int N, int C, float tau, int precision,
+                     float* loss, float* A_or_null, void* saved, size_t saved_bytes, void* stream);
+
+/* Reverse pass -- replaces autograd through src/model.py:22-46 (scripts/train.py:71).
+ *   x        [B,T,N,C] the same raw encoder output given to crw_walk_forward
+ *   saved    the workspace crw_walk_forward filled
+ *   dloss    [1] device scalar: upstream gradient of loss
+ *   dA       [B,T-1,N,N] or NULL: upstream gradient of the returned affinities
+ *   dx       [B,T,N,C] out: gradient w.r.t. the raw encoder output
+ *   scratch  workspace of crw_walk_backward_scratch_bytes()
+ * ---------------------------------------------------------------------------------- */
+size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C);
+int crw_walk_backward(const float* x, const void* saved, size_t saved_bytes, const float* dloss,
+                      const float* dA_or_null, int B, int T, int N, int C, float tau, int precision, float* dx,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Affinity + top-k + softmax -- replaces batched_affinity, src/imported/maskedatt.py:151-175,
+ * with the radius bias of maskedatt.py:232-245 / labelprop.py:89-96 applied to every key
+ * frame and the context trim of maskedatt.py:166-167 applied *before* any arithmetic.
+ *   keys     [n_keys,N,C]  normalised features of ALL previous frames (frame 0 first)
+ *   queries  [n_q,N,C]     normalised features of query frames; query i plays frame
+ *                          n = n_first + i and sees keys 0..n-1 (trimmed to frame 0 + last ctx)
+ *   W        [n_q,k,N] f32 softmax weights, sorted by descending logit
+ *   I        [n_q,k,N] i32 candidate ids into the trimmed key set (frame-slot * N + node)
+ * Ties: equal logits ordered by ascending id (torch.topk leaves this unspecified).
+ * Whole-sequence use: keys = emb, queries = emb + N*C, n_first = 1, n_q = T-1.
+ * ---------------------------------------------------------------------------------- */
+int crw_affinity_topk(const float* keys, const float* queries, int n_first, int n_q, int N, int C,
+                      int ctx, float radius, float temp, int k, int precision, float* W, int32_t* I,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Label gather + argmax -- replaces the tail of LabelPropVOS_CRW.predict
+ * (src/imported/labelprop.py:82,106-116) and the frame loop / argmax of propagate
+ * (src/utils.py:152-160) for R independent radargrams.
+ *   W, I     [R,T,k,N]  as written by crw_affinity_topk with n_first = 1 (row 0 unused)
+ *   mask0    [R,M,N]    one-hot reference mask of frame 0 (utils.py:143-147)
+ *   labels   [R,T,N] i32 out: argmax class per node (labels[:,0] = argmax of mask0)
+ *   masks    [R,T,M,N]  out: soft masks of every frame (the reference keeps them, utils.py:157)
+ * ---------------------------------------------------------------------------------- */
+int crw_label_gather(const float* W, const int32_t* I, const float* mask0, int R, int T, int N, int M,
+                     int ctx, int k, int mode, int32_t* labels, float* masks, void* stream);
+
+/* One stepwise predict call -- replaces src/imported/labelprop.py:106-116 for callers that keep
+ * the reference's per-frame API (LabelPropVOS_CRW.predict):
+ *   W, I [k,N] from crw_affinity_topk (n_q = 1); lbl [F,M,N] soft masks of the frames the ids
+ *   index into (frame-slot major); out_mask [M,N]; out_label [N] i32 or NULL.
+ */
+int crw_label_gather_step(const float* W, const int32_t* I, const float* lbl, int F, int N, int M, int k,
+                          float* out_mask, int32_t* out_label_or_null, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole label-propagation path for R radargrams -- replaces propagate's encode-side tail and
+ * frame loop, src/utils.py:115,134-161 (normalise, top-k, gather, argmax).
+ *   feats    [R,T,N,C]  raw encoder output (normalised here when do_normalize != 0)
+ *   mask0    [R,M,N]
+ *   labels   [R,T,N] i32 out
+ *   masks    [R,T,M,N] out (required: the recurrence reads it)
+ *   W_or_null, I_or_null [R,T,k,N]: top-k dumps; when NULL they live in `scratch`
+ *   scratch  workspace of crw_labelprop_scratch_bytes()
+ * ---------------------------------------------------------------------------------- */
+size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k, int precision, int do_normalize,
+                                   int have_topk_out);
+int crw_labelprop_forward(const float* feats, const float* mask0, int R, int T, int N, int C, int M,
+                          int ctx, float radius, float temp, int k, int mode, int precision,
+                          int do_normalize, int32_t* labels, float* masks, float* W_or_null,
+                          int32_t* I_or_null, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * "Horizontality" metric -- replaces src/utils.py:118-123 (channel-shifted intra-frame
+ * similarity / 0.1, cross-entropy against the identity, reduction='none').
+ *   emb [T,N,C] normalised  ->  xent [N,T-1]
+ * ---------------------------------------------------------------------------------- */
+int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRW_B200_H_ */

@@ -9,6 +9,7 @@
  *   label gather           imported/labelprop.py:82,106-109   (context-trim quirk)
  *   frame loop + argmax    utils.py:134-161
  *   L2 normalise           utils.py:115  (F.normalize, eps 1e-12)
+ *   norm     see crw_oracle_l2_normalize (per-lane strided fmaf + xor butterfly)
  *
  * The fp32 operation order is PINNED so that the CUDA fp32 path can be compared
  * bit for bit (the reference itself leaves GEMM summation order, exp and tie
@@ -66,15 +67,24 @@ int crw_oracle_num_threads(void) {
 #endif
 }
 
-/* x [rows, C] -> out [rows, C] = x / max(||x||_2, 1e-12).  Pinned order:
- * ss = sequential fmaf over c; nrm = sqrtf(ss); out = x / max(nrm, eps). */
+/* x [rows, C] -> out [rows, C] = x / max(||x||_2, 1e-12).  Pinned order (maps onto one warp per
+ * row): partial[l] = sequential fmaf over c = l, l+32, l+64, ...; then a 5-stage xor butterfly
+ * (offsets 16,8,4,2,1) of plain adds; nrm = sqrtf(total); out = x / max(nrm, eps). */
 void crw_oracle_l2_normalize(const float* x, int64_t rows, int C, float* out) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < rows; ++i) {
         const float* xi = x + i * C;
-        float ss = 0.0f;
-        for (int c = 0; c < C; ++c) ss = fmaf(xi[c], xi[c], ss);
-        float d = fmaxf(sqrtf(ss), 1e-12f);
+        float p[32], t[32];
+        for (int l = 0; l < 32; ++l) {
+            float ss = 0.0f;
+            for (int c = l; c < C; c += 32) ss = fmaf(xi[c], xi[c], ss);
+            p[l] = ss;
+        }
+        for (int off = 16; off >= 1; off >>= 1) {
+            for (int l = 0; l < 32; ++l) t[l] = p[l] + p[l ^ off];
+            for (int l = 0; l < 32; ++l) p[l] = t[l];
+        }
+        float d = fmaxf(sqrtf(p[0]), 1e-12f);
         for (int c = 0; c < C; ++c) out[i * C + c] = xi[c] / d;
     }
 }

@@ -1,0 +1,522 @@
+// labelprop_f32.cu -- fp32 (pinned-order) label-propagation kernels for sm_100a.
+//
+// Replaces, for the h = N, w = 1 node grid the reference always uses:
+//   F.normalize                     src/utils.py:115
+//   batched_affinity                src/imported/maskedatt.py:151-175   (einsum, +mask, /temp, trim, topk, softmax)
+//   radius mask                     src/imported/maskedatt.py:232-245, src/imported/labelprop.py:89-96
+//   label gather of predict         src/imported/labelprop.py:82,106-109
+//   frame loop + argmax             src/utils.py:152-160
+//
+// Arithmetic order is pinned (see oracle/crw_oracle.c header) so results are bit-identical
+// to the C oracle: dot = sequential fmaf over channels, logit = dot * (1/temp), ties by
+// ascending candidate id, pinned polynomial exp, sequential softmax sum, mul-then-add gather.
+#include "common.cuh"
+
+namespace crw {
+
+// ------------------------------------------------------------------------------------------
+// L2 normalise: one warp per row.  lane l sums c = l, l+32, ... with fmaf, xor-butterfly.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* x, int64_t rows, int C, float* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* xr = x + row * C;
+    float ss = 0.0f;
+    for (int c = lane; c < C; c += 32) { float v = xr[c]; ss = __fmaf_rn(v, v, ss); }
+    ss = warp_sum_butterfly_rn(ss);
+    const float d = fmaxf(__fsqrt_rn(ss), kNormEps);
+    float* o = out + row * C;
+    for (int c = lane; c < C; c += 32) o[c] = __fdiv_rn(xr[c], d);
+}
+
+// ------------------------------------------------------------------------------------------
+// Affinity + radius band + top-k + softmax, fp32.
+//
+// One CTA = one (query frame, chunk of 64 query nodes).  Frames are staged TRANSPOSED in
+// shared memory as [c][64 nodes] with the 16-byte node groups xor-swizzled by (c>>2), so
+// that (a) the transposing stores are bank-conflict free and (b) a thread computing a 4x4
+// (key x query) block reads one float4 of keys and one float4 of queries per channel.
+// Only 4x4 blocks that intersect the band |j - q| <= rb are computed (compact item list).
+// Scores go through shared memory to regroup them per query; each warp then keeps the
+// running top-k of its queries sorted across lanes (ballot + shuffle insertion).
+// ------------------------------------------------------------------------------------------
+constexpr int kChunk = 64;          // nodes per staged tile
+constexpr int kScoreLd = 68;        // padded row of the score tile (16-byte aligned rows)
+constexpr int kTopkThreads = 256;
+constexpr int kQPerWarp = kChunk / (kTopkThreads / 32);  // 8 queries per warp
+
+struct TopkParams {
+    const float* keys;     // [n_keys, N, C]
+    const float* queries;  // [n_q, N, C]
+    float* W;              // [n_q, k, N]
+    int32_t* I;            // [n_q, k, N]
+    int n_first, n_q, N, C, ctx, rb, k;
+    float inv_temp;
+};
+
+__device__ __forceinline__ int swz(int c, int j) { return c * kChunk + ((((j >> 2) ^ (c >> 2)) & 15) << 2) + (j & 3); }
+
+// stage nodes [j_base, j_base+64) of `frame` ([N][C] row-major) into dst ([C][64] swizzled)
+__device__ __forceinline__ void stage_frame_T(const float* __restrict__ frame, int N, int C, int j_base, float* dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int jl4 = lane & 3, c4 = lane >> 2;
+    for (int rg = warp; rg < kChunk / 4; rg += kTopkThreads / 32) {
+        const int jl = rg * 4 + jl4;
+        const int j = j_base + jl;
+        const bool ok = j < N;
+        const float4* src = reinterpret_cast<const float4*>(frame + (size_t)j * C);
+        for (int cb = 0; cb < C; cb += 32) {
+            const int c = cb + c4 * 4;
+            if (c < C) {
+                float4 v = ok ? __ldg(src + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[swz(c + 0, jl)] = v.x;
+                dst[swz(c + 1, jl)] = v.y;
+                dst[swz(c + 2, jl)] = v.z;
+                dst[swz(c + 3, jl)] = v.w;
+            }
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kTopkThreads, 1) lp_topk_f32_kernel(TopkParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int N = p.N, C = p.C, k = p.k, rb = p.rb;
+    float* Qt = smem;                              // [C][64]
+    float* Kt = Qt + C * kChunk;                   // [G][C][64]
+    float* score = Kt + G * C * kChunk;            // [G][64][kScoreLd]
+    unsigned short* items = reinterpret_cast<unsigned short*>(score + G * kChunk * kScoreLd);  // [G*256]
+    __shared__ int n_items;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_qchunks = ceil_div(N, kChunk);
+    const int job = blockIdx.x / n_qchunks, qc = blockIdx.x % n_qchunks;
+    const int n = p.n_first + job;                 // the frame index this query plays
+    const int F = n_key_frames(n, p.ctx);
+    const int q_base = qc * kChunk;
+    // key chunks that can intersect the band of this query chunk
+    const int jc_lo = max(0, q_base - rb) / kChunk;
+    const int jc_hi = min(N - 1, q_base + kChunk - 1 + rb) / kChunk;
+    const int njc = jc_hi - jc_lo + 1;
+    const int n_tiles = F * njc;
+
+    stage_frame_T(p.queries + (size_t)job * N * C, N, C, q_base, Qt);
+
+    // running top-k of this warp's queries: lane i holds the i-th best (value, id)
+    float tv[kQPerWarp];
+    int ti[kQPerWarp];
+#pragma unroll
+    for (int i = 0; i < kQPerWarp; ++i) { tv[i] = -INFINITY; ti[i] = 0; }
+
+    for (int t0 = 0; t0 < n_tiles; t0 += G) {
+        const int g_cnt = min(G, n_tiles - t0);
+        if (tid == 0) n_items = 0;
+        __syncthreads();   // previous scan done with `score`; previous FMA done with Kt
+        for (int g = 0; g < g_cnt; ++g) {
+            const int t = t0 + g, f = t / njc, jc = jc_lo + t % njc;
+            stage_frame_T(p.keys + (size_t)key_frame(n, p.ctx, f) * N * C, N, C, jc * kChunk, Kt + g * C * kChunk);
+            // in-band 4x4 blocks of this tile: thread <-> (qb, jb)
+            const int qb = tid >> 4, jb = tid & 15;
+            const int q0 = q_base + qb * 4, j0 = jc * kChunk + jb * 4;
+            if (q0 < N && j0 < N && (j0 - (q0 + 3)) <= rb && (q0 - (j0 + 3)) <= rb) {
+                const int slot = atomicAdd(&n_items, 1);
+                items[slot] = (unsigned short)((g << 8) | (qb << 4) | jb);
+            }
+        }
+        __syncthreads();
+        const int cnt = n_items;
+        for (int it = tid; it < cnt; it += kTopkThreads) {
+            const int code = items[it];
+            const int g = code >> 8, qb = (code >> 4) & 15, jb = code & 15;
+            const float* Kg = Kt + g * C * kChunk;
+            float acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+#pragma unroll 2
+            for (int c4 = 0; c4 < (C >> 2); ++c4) {
+                const int sk = ((jb ^ c4) & 15) << 2, sq = ((qb ^ c4) & 15) << 2;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = c4 * 4 + i;
+                    const float4 kv = *reinterpret_cast<const float4*>(Kg + c * kChunk + sk);
+                    const float4 qv = *reinterpret_cast<const float4*>(Qt + c * kChunk + sq);
+                    const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = __fmaf_rn(kk[b], qq[a], acc[a][b]);
+                }
+            }
+            float* sc = score + (g * kChunk + qb * 4) * kScoreLd + jb * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                float4 o;
+                o.x = __fmul_rn(acc[a][0], p.inv_temp);
+                o.y = __fmul_rn(acc[a][1], p.inv_temp);
+                o.z = __fmul_rn(acc[a][2], p.inv_temp);
+                o.w = __fmul_rn(acc[a][3], p.inv_temp);
+                *reinterpret_cast<float4*>(sc + a * kScoreLd) = o;
+            }
+        }
+        __syncthreads();
+        // scan: candidates in ascending id order (tile order = frame-major, then node)
+        const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+#pragma unroll
+        for (int qi = 0; qi < kQPerWarp; ++qi) {
+            const int ql = warp + qi * (kTopkThreads / 32);
+            const int q = q_base + ql;
+            if (q >= N) continue;                       // warp-uniform
+            float v = tv[qi];
+            int id = ti[qi];
+            float thr = __shfl_sync(0xffffffffu, v, k - 1);
+            for (int g = 0; g < g_cnt; ++g) {
+                const int t = t0 + g, f = t / njc, jc = jc_lo + t % njc;
+                const float* srow = score + (g * kChunk + ql) * kScoreLd;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int jl = half * 32 + lane;
+                    const int j = jc * kChunk + jl;
+                    const int dj = j - q;
+                    const bool ok = (j < N) && (dj <= rb) && (-dj <= rb);
+                    const float cand = ok ? srow[jl] : -INFINITY;
+                    const int cid = f * N + j;
+                    unsigned m = __ballot_sync(0xffffffffu, ok && cand > thr);
+                    while (m) {
+                        const int s = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float c = __shfl_sync(0xffffffffu, cand, s);
+                        const int ci = __shfl_sync(0xffffffffu, cid, s);
+                        if (c > thr) {                  // warp-uniform
+                            const int pos = __popc(__ballot_sync(0xffffffffu, v >= c) & kmask);
+                            const float vup = __shfl_up_sync(0xffffffffu, v, 1);
+                            const int iup = __shfl_up_sync(0xffffffffu, id, 1);
+                            if (lane > pos) { v = vup; id = iup; }
+                            else if (lane == pos) { v = c; id = ci; }
+                            if (lane >= k) v = -INFINITY;
+                            thr = __shfl_sync(0xffffffffu, v, k - 1);
+                        }
+                    }
+                }
+            }
+            tv[qi] = v;
+            ti[qi] = id;
+        }
+    }
+
+    // finalise: masked fill (fewer than k in-band candidates), softmax, store
+    const float masked = __fmul_rn(kMaskBias, p.inv_temp);
+#pragma unroll
+    for (int qi = 0; qi < kQPerWarp; ++qi) {
+        const int q = q_base + warp + qi * (kTopkThreads / 32);
+        if (q >= N) continue;
+        float v = tv[qi];
+        int id = ti[qi];
+        int live = __popc(__ballot_sync(0xffffffffu, v > -INFINITY) & ((k >= 32) ? 0xffffffffu : ((1u << k) - 1u)));
+        if (live < k) {
+            // out-of-band candidates all carry the same logit; ascending id order
+            for (int f = 0; f < F && live < k; ++f)
+                for (int j = 0; j < N && live < k; ++j) {
+                    const int dj = j - q;
+                    if (dj <= rb && -dj <= rb) continue;
+                    if (lane == live) { v = masked; id = f * N + j; }
+                    ++live;
+                }
+        }
+        const float v0 = __shfl_sync(0xffffffffu, v, 0);
+        const float e = (lane < k) ? pinned_expf(__fsub_rn(v, v0)) : 0.0f;
+        float s = __shfl_sync(0xffffffffu, e, 0);
+        for (int j = 1; j < k; ++j) s = __fadd_rn(s, __shfl_sync(0xffffffffu, e, j));
+        if (lane < k) {
+            const size_t o = ((size_t)job * k + lane) * N + q;
+            p.W[o] = __fdiv_rn(e, s);
+            p.I[o] = id;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Label gather + argmax.
+//   sequential kernel: one CTA per radargram walks frames [n_begin, n_end) in order (the
+//   recurrence: frame n reads soft masks written for earlier frames).
+//   parallel kernel: frames whose label frames are all final (ref_exact, n > ctx+1).
+// `masks` is deliberately NOT __restrict__/ldg: it is read after being written by this CTA.
+// ------------------------------------------------------------------------------------------
+struct GatherParams {
+    const float* W;      // [R,T,k,N]
+    const int32_t* I;    // [R,T,k,N]
+    const float* mask0;  // [R,M,N]
+    int32_t* labels;     // [R,T,N]
+    float* masks;        // [R,T,M,N]
+    int R, T, N, M, ctx, k, mode_fixed;
+};
+
+__device__ __forceinline__ void gather_one(const GatherParams& p, const float* W, const int32_t* I, float* masks,
+                                           int32_t* labels, int n, int q) {
+    const int N = p.N, M = p.M, k = p.k;
+    float best = 0.0f;
+    int best_m = 0;
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+        for (int j = 0; j < k; ++j) {
+            const size_t o = ((size_t)n * k + j) * N + q;
+            const int id = I[o];
+            const float w = W[o];
+            const int lf = label_frame(n, p.ctx, id / N, p.mode_fixed);
+            const float* src = masks + ((size_t)lf * M + m0) * N + (id % N);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (m0 + u < M) acc[u] = __fadd_rn(acc[u], __fmul_rn(src[(size_t)u * N], w));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (m0 + u < M) {
+                masks[((size_t)n * M + m0 + u) * N + q] = acc[u];
+                if ((m0 + u == 0) || acc[u] > best) { best = acc[u]; best_m = m0 + u; }
+            }
+    }
+    labels[(size_t)n * N + q] = best_m;
+}
+
+__global__ void __launch_bounds__(256) lp_gather_seq_kernel(GatherParams p, int n_begin, int n_end, int init_frame0) {
+    const int r = blockIdx.x;
+    const int N = p.N, M = p.M;
+    const float* W = p.W + (size_t)r * p.T * p.k * N;
+    const int32_t* I = p.I + (size_t)r * p.T * p.k * N;
+    float* masks = p.masks + (size_t)r * p.T * M * N;
+    int32_t* labels = p.labels + (size_t)r * p.T * N;
+    if (init_frame0) {
+        const float* m0 = p.mask0 + (size_t)r * M * N;
+        for (int q = threadIdx.x; q < N; q += blockDim.x) {
+            float best = 0.0f;
+            int bm = 0;
+            for (int m = 0; m < M; ++m) {
+                const float v = m0[(size_t)m * N + q];
+                masks[(size_t)m * N + q] = v;
+                if (m == 0 || v > best) { best = v; bm = m; }
+            }
+            labels[q] = bm;
+        }
+        __syncthreads();
+    }
+    for (int n = n_begin; n < n_end; ++n) {
+        for (int q = threadIdx.x; q < N; q += blockDim.x) gather_one(p, W, I, masks, labels, n, q);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) lp_gather_par_kernel(GatherParams p, int n_begin, int n_end) {
+    const int r = blockIdx.y;
+    const int N = p.N;
+    const float* W = p.W + (size_t)r * p.T * p.k * N;
+    const int32_t* I = p.I + (size_t)r * p.T * p.k * N;
+    float* masks = p.masks + (size_t)r * p.T * p.M * N;
+    int32_t* labels = p.labels + (size_t)r * p.T * N;
+    const long long total = (long long)(n_end - n_begin) * N;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int n = n_begin + (int)(idx / N), q = (int)(idx % N);
+        gather_one(p, W, I, masks, labels, n, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Horizontality metric (src/utils.py:118-123): A[t][c][n] = <emb[t,c,:-1], emb[t,n,1:]> / 0.1,
+// xent[n,t] = logsumexp_c A[t][c][n] - A[t][n][n].  One CTA per frame t < T-1, warp per column n.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xent_kernel(const float* __restrict__ emb, int T, int N, int C, float* xent) {
+    extern __shared__ float fr[];  // [N][C+1]
+    const int t = blockIdx.x, ld = C + 1;
+    const float* e = emb + (size_t)t * N * C;
+    for (int i = threadIdx.x; i < N * C; i += blockDim.x) fr[(i / C) * ld + (i % C)] = e[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int n = warp; n < N; n += blockDim.x >> 5) {
+        float mx = -INFINITY, se = 0.0f, diag = 0.0f;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            const int c = c0 + lane;
+            float a = -INFINITY;
+            if (c < N) {
+                float acc = 0.0f;
+                for (int ch = 0; ch < C - 1; ++ch) acc = fmaf(fr[c * ld + ch], fr[n * ld + ch + 1], acc);
+                a = acc / 0.1f;
+                if (c == n) diag = a;
+            }
+            const float cm = warp_max(a);
+            const float nm = fmaxf(mx, cm);
+            se = se * __expf(mx - nm) + warp_sum(c < N ? __expf(a - nm) : 0.0f);
+            mx = nm;
+        }
+        diag = warp_sum(diag);
+        if (lane == 0) xent[(size_t)n * (T - 1) + t] = logf(se) + mx - diag;
+    }
+}
+
+// one stepwise predict call (labelprop.py:106-116): lbl [F,M,N] are the soft masks the ids index into
+__global__ void __launch_bounds__(256) lp_gather_step_kernel(const float* __restrict__ W, const int32_t* __restrict__ I,
+                                                             const float* __restrict__ lbl, int F, int N, int M, int k,
+                                                             float* out_mask, int32_t* out_label) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    float best = 0.0f;
+    int best_m = 0;
+    for (int m = 0; m < M; ++m) {
+        float acc = 0.0f;
+        for (int j = 0; j < k; ++j) {
+            const int id = I[(size_t)j * N + q];
+            const int f = id / N;
+            const float v = (f < F) ? lbl[((size_t)f * M + m) * N + (id % N)] : 0.0f;
+            acc = __fadd_rn(acc, __fmul_rn(v, W[(size_t)j * N + q]));
+        }
+        out_mask[(size_t)m * N + q] = acc;
+        if (m == 0 || acc > best) { best = acc; best_m = m; }
+    }
+    if (out_label) out_label[q] = best_m;
+}
+
+}  // namespace crw
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace crw;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int crw_l2_normalize(const float* x, int64_t rows, int C, float* out, void* stream) {
+    if (!x || !out || rows < 0 || C < 1) return CRW_ERR_INVALID;
+    if (rows == 0) return CRW_OK;
+    const int64_t blocks = (rows + 7) / 8;
+    if (blocks > 0x7fffffffLL) return CRW_ERR_UNSUPPORTED;
+    l2_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, C, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+template <int G>
+static int launch_topk_f32(const TopkParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)(1 + G) * p.C * kChunk * sizeof(float) + (size_t)G * kChunk * kScoreLd * sizeof(float) +
+                        (size_t)G * 256 * sizeof(unsigned short);
+    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_f32_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = p.n_q * ceil_div(p.N, kChunk);
+    lp_topk_f32_kernel<G><<<grid, kTopkThreads, smem, st>>>(p);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+extern "C" int crw_affinity_topk(const float* keys, const float* queries, int n_first, int n_q, int N, int C, int ctx,
+                                 float radius, float temp, int k, int precision, float* W, int32_t* I, void* stream) {
+    if (!keys || !queries || !W || !I) return CRW_ERR_INVALID;
+    if (n_first < 1 || n_q < 0 || N < 1 || C < 1 || ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f))
+        return CRW_ERR_INVALID;
+    if ((int64_t)n_key_frames(n_first, ctx) * N < k) return CRW_ERR_INVALID;  // torch.topk would raise
+    if (n_q == 0) return CRW_OK;
+    if (k > 32) return CRW_ERR_UNSUPPORTED;
+    if ((C & 3) || !aligned16(keys) || !aligned16(queries)) return CRW_ERR_ALIGN;
+    if (precision == CRW_PREC_FP32) {
+        if (C > 128) return CRW_ERR_UNSUPPORTED;
+        TopkParams p;
+        p.keys = keys; p.queries = queries; p.W = W; p.I = I;
+        p.n_first = n_first; p.n_q = n_q; p.N = N; p.C = C; p.ctx = ctx; p.k = k;
+        const float rc = ceilf(radius);
+        p.rb = (rc - 1.0f >= (float)N) ? N : (int)rc - 1;   // |d| < radius  <=>  |d| <= ceil(radius)-1
+        p.inv_temp = 1.0f / temp;
+        return launch_topk_f32<3>(p, (cudaStream_t)stream);
+    }
+    return CRW_ERR_UNSUPPORTED;
+}
+
+extern "C" int crw_label_gather(const float* W, const int32_t* I, const float* mask0, int R, int T, int N, int M,
+                                int ctx, int k, int mode, int32_t* labels, float* masks, void* stream) {
+    if (!W || !I || !mask0 || !labels || !masks) return CRW_ERR_INVALID;
+    if (R < 0 || T < 1 || N < 1 || M < 1 || ctx < 1 || k < 1) return CRW_ERR_INVALID;
+    if (mode != CRW_LP_REF_EXACT && mode != CRW_LP_FIXED) return CRW_ERR_INVALID;
+    if (R == 0) return CRW_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    GatherParams p;
+    p.W = W; p.I = I; p.mask0 = mask0; p.labels = labels; p.masks = masks;
+    p.R = R; p.T = T; p.N = N; p.M = M; p.ctx = ctx; p.k = k; p.mode_fixed = (mode == CRW_LP_FIXED);
+    // frames that must run in order: all of them in fixed mode, the first ctx+1 in ref_exact mode
+    const int seq_end = p.mode_fixed ? T : min(T, ctx + 2);
+    lp_gather_seq_kernel<<<R, 256, 0, st>>>(p, 1, seq_end, 1);
+    CRW_LAUNCH_RET();
+    if (seq_end < T) {
+        const long long total = (long long)(T - seq_end) * N;
+        long long gx64 = (total + 255) / 256; int gx = (int)(gx64 < 148LL * 8 ? gx64 : 148LL * 8);
+        lp_gather_par_kernel<<<dim3(gx, R), 256, 0, st>>>(p, seq_end, T);
+        CRW_LAUNCH_RET();
+    }
+    return CRW_OK;
+}
+
+extern "C" int crw_label_gather_step(const float* W, const int32_t* I, const float* lbl, int F, int N, int M, int k,
+                                     float* out_mask, int32_t* out_label_or_null, void* stream) {
+    if (!W || !I || !lbl || !out_mask || F < 1 || N < 1 || M < 1 || k < 1) return CRW_ERR_INVALID;
+    lp_gather_step_kernel<<<ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(W, I, lbl, F, N, M, k, out_mask,
+                                                                            out_label_or_null);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+extern "C" size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k, int precision, int do_normalize,
+                                              int have_topk_out) {
+    (void)precision;
+    size_t b = 0;
+    if (do_normalize) b += align_up((size_t)R * T * N * C * sizeof(float), 256);
+    if (!have_topk_out) b += 2 * align_up((size_t)R * T * k * N * sizeof(float), 256);
+    return b + 256;
+}
+
+extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int R, int T, int N, int C, int M, int ctx,
+                                     float radius, float temp, int k, int mode, int precision, int do_normalize,
+                                     int32_t* labels, float* masks, float* W_or_null, int32_t* I_or_null,
+                                     void* scratch, size_t scratch_bytes, void* stream) {
+    if (!feats || !mask0 || !labels || !masks) return CRW_ERR_INVALID;
+    if (R < 0 || T < 1 || N < 1 || C < 1 || M < 1) return CRW_ERR_INVALID;
+    if ((W_or_null == nullptr) != (I_or_null == nullptr)) return CRW_ERR_INVALID;
+    if (R == 0) return CRW_OK;
+    const size_t need = crw_labelprop_scratch_bytes(R, T, N, C, k, precision, do_normalize, W_or_null != nullptr);
+    if (need > 256 && (!scratch || scratch_bytes < need)) return CRW_ERR_WORKSPACE;
+    char* sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+    const float* emb = feats;
+    if (do_normalize) {
+        float* e = reinterpret_cast<float*>(sp);
+        sp += align_up((size_t)R * T * N * C * sizeof(float), 256);
+        int rc = crw_l2_normalize(feats, (int64_t)R * T * N, C, e, stream);
+        if (rc != CRW_OK) return rc;
+        emb = e;
+    }
+    float* W = W_or_null;
+    int32_t* I = I_or_null;
+    if (!W) {
+        W = reinterpret_cast<float*>(sp);
+        sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+        I = reinterpret_cast<int32_t*>(sp);
+    }
+    if (T > 1) {
+        for (int r = 0; r < R; ++r) {
+            const float* er = emb + (size_t)r * T * N * C;
+            const size_t o = ((size_t)r * T + 1) * k * N;
+            int rc = crw_affinity_topk(er, er + (size_t)N * C, 1, T - 1, N, C, ctx, radius, temp, k, precision, W + o,
+                                       I + o, stream);
+            if (rc != CRW_OK) return rc;
+        }
+    }
+    return crw_label_gather(W, I, mask0, R, T, N, M, ctx, k, mode, labels, masks, stream);
+}
+
+extern "C" int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, void* stream) {
+    if (!emb || !xent || T < 1 || N < 1 || C < 2) return CRW_ERR_INVALID;
+    if (T == 1) return CRW_OK;
+    const size_t smem = (size_t)N * (C + 1) * sizeof(float);
+    if (smem > 200 * 1024) return CRW_ERR_UNSUPPORTED;
+    CRW_CUDA_RET(cudaFuncSetAttribute(xent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xent_kernel<<<T - 1, 256, smem, (cudaStream_t)stream>>>(emb, T, N, C, xent);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}

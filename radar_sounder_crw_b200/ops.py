@@ -1,0 +1,221 @@
+"""``torch.library`` custom ops (namespace ``crw_b200::``) over the C ABI of libcrw_b200.so.
+
+Each op validates on the Python side only what the C side cannot see (device, dtype,
+contiguity), passes raw device pointers + the current CUDA stream across the ABI, and
+raises ``RuntimeError`` on any non-zero return.  No op has a CPU implementation.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import PREC_FP32, PREC_BF16X3, PREC_TF32, LP_REF_EXACT, LP_FIXED  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Tensor, name: str, dtype=torch.float32) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"crw_b200: `{name}` must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"crw_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# l2_normalize  (model.py:22, utils.py:115)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::l2_normalize", mutates_args=())
+def l2_normalize(x: Tensor) -> Tensor:
+    x = _chk(x, "x")
+    out = torch.empty_like(x)
+    C = x.shape[-1]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().crw_l2_normalize(_p(x), x.numel() // max(C, 1), C, _p(out), _stream()), "crw_l2_normalize")
+    return out
+
+
+@l2_normalize.register_fake
+def _(x):
+    return torch.empty_like(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# walk_loss / walk_loss_backward  (model.py:22-46 and its autograd)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::walk_loss", mutates_args=())
+def walk_loss(x: Tensor, tau: float, need_A: bool, precision: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """x [B,T,N,C] raw encoder output -> (loss/N scalar, A [B,T-1,N,N] or empty, saved workspace)."""
+    x = _chk(x, "x")
+    B, T, N, C = x.shape
+    L = _lib.lib()
+    loss = torch.empty((), device=x.device, dtype=torch.float32)
+    A = torch.empty((B, T - 1, N, N) if need_A else (0,), device=x.device, dtype=torch.float32)
+    nbytes = L.crw_walk_saved_bytes(B, T, N, C)
+    saved = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        _lib.check(L.crw_walk_forward(_p(x), B, T, N, C, float(tau), int(precision), _p(loss), _p(A), _p(saved),
+                                      nbytes, _stream()), "crw_walk_forward")
+    return loss, A, saved
+
+
+@walk_loss.register_fake
+def _(x, tau, need_A, precision):
+    B, T, N, C = x.shape
+    return (x.new_empty(()), x.new_empty((B, T - 1, N, N) if need_A else (0,)),
+            torch.empty(0, device=x.device, dtype=torch.uint8))
+
+
+@torch.library.custom_op("crw_b200::walk_loss_backward", mutates_args=())
+def walk_loss_backward(x: Tensor, saved: Tensor, dloss: Tensor, dA: Tensor, tau: float, precision: int) -> Tensor:
+    x = _chk(x, "x")
+    B, T, N, C = x.shape
+    L = _lib.lib()
+    dloss = _chk(dloss.reshape(1), "dloss")
+    dA_c = _chk(dA, "dA") if dA.numel() else None
+    dx = torch.empty_like(x)
+    sbytes = L.crw_walk_backward_scratch_bytes(B, T, N, C)
+    scratch = torch.empty(sbytes, device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        _lib.check(L.crw_walk_backward(_p(x), _p(saved), saved.numel(), _p(dloss), _p(dA_c), B, T, N, C, float(tau),
+                                       int(precision), _p(dx), _p(scratch), sbytes, _stream()), "crw_walk_backward")
+    return dx
+
+
+@walk_loss_backward.register_fake
+def _(x, saved, dloss, dA, tau, precision):
+    return torch.empty_like(x)
+
+
+def _walk_setup(ctx, inputs, output):
+    x, tau, need_A, precision = inputs
+    _, _, saved = output
+    ctx.save_for_backward(x, saved)
+    ctx.tau, ctx.need_A, ctx.precision = tau, need_A, precision
+
+
+def _walk_bwd(ctx, g_loss, g_A, _g_saved):
+    x, saved = ctx.saved_tensors
+    if g_loss is None:
+        g_loss = torch.zeros((), device=x.device, dtype=torch.float32)
+    if g_A is None or not ctx.need_A:
+        g_A = torch.empty(0, device=x.device, dtype=torch.float32)
+    dx = walk_loss_backward(x, saved, g_loss.to(torch.float32), g_A, ctx.tau, ctx.precision)
+    return dx, None, None, None
+
+
+walk_loss.register_autograd(_walk_bwd, setup_context=_walk_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# affinity_topk  (maskedatt.py:151-175)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::affinity_topk", mutates_args=())
+def affinity_topk(keys: Tensor, queries: Tensor, n_first: int, ctx: int, radius: float, temp: float, k: int,
+                  precision: int) -> Tuple[Tensor, Tensor]:
+    """keys [n_keys,N,C], queries [Q,N,C] (normalised) -> W [Q,k,N] f32, I [Q,k,N] i32."""
+    keys, queries = _chk(keys, "keys"), _chk(queries, "queries")
+    Q, N, C = queries.shape
+    if keys.shape[0] < n_first + Q - 1:
+        raise RuntimeError("crw_b200::affinity_topk: query n needs keys 0..n-1")
+    W = torch.empty((Q, k, N), device=keys.device, dtype=torch.float32)
+    I = torch.empty((Q, k, N), device=keys.device, dtype=torch.int32)
+    with torch.cuda.device(keys.device):
+        _lib.check(_lib.lib().crw_affinity_topk(_p(keys), _p(queries), n_first, Q, N, C, ctx, float(radius), float(temp),
+                                                k, int(precision), _p(W), _p(I), _stream()), "crw_affinity_topk")
+    return W, I
+
+
+@affinity_topk.register_fake
+def _(keys, queries, n_first, ctx, radius, temp, k, precision):
+    Q, N, _ = queries.shape
+    return keys.new_empty((Q, k, N)), torch.empty((Q, k, N), device=keys.device, dtype=torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# label_gather_step  (labelprop.py:106-116)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::label_gather_step", mutates_args=())
+def label_gather_step(W: Tensor, I: Tensor, lbl: Tensor) -> Tensor:
+    """W,I [k,N]; lbl [F,M,N] -> soft mask [M,N]."""
+    W, I, lbl = _chk(W, "W"), _chk(I, "I", torch.int32), _chk(lbl, "lbl")
+    k, N = W.shape
+    F, M, _ = lbl.shape
+    out = torch.empty((M, N), device=W.device, dtype=torch.float32)
+    with torch.cuda.device(W.device):
+        _lib.check(_lib.lib().crw_label_gather_step(_p(W), _p(I), _p(lbl), F, N, M, k, _p(out), None, _stream()),
+                   "crw_label_gather_step")
+    return out
+
+
+@label_gather_step.register_fake
+def _(W, I, lbl):
+    return W.new_empty((lbl.shape[1], W.shape[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# labelprop  (utils.py:115,134-161 + labelprop.py:67-116 + maskedatt.py:151-175)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::labelprop", mutates_args=())
+def labelprop(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: float, k: int, mode: int, precision: int,
+              normalize: bool, return_topk: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """feats [R,T,N,C], mask0 [R,M,N] -> labels [R,T,N] i32, masks [R,T,M,N], W/I [R,T,k,N] (or empty)."""
+    feats, mask0 = _chk(feats, "feats"), _chk(mask0, "mask0")
+    R, T, N, C = feats.shape
+    M = mask0.shape[1]
+    L = _lib.lib()
+    dev = feats.device
+    labels = torch.empty((R, T, N), device=dev, dtype=torch.int32)
+    masks = torch.empty((R, T, M, N), device=dev, dtype=torch.float32)
+    if return_topk:
+        W = torch.zeros((R, T, k, N), device=dev, dtype=torch.float32)
+        I = torch.zeros((R, T, k, N), device=dev, dtype=torch.int32)
+    else:
+        W = torch.empty(0, device=dev, dtype=torch.float32)
+        I = torch.empty(0, device=dev, dtype=torch.int32)
+    sbytes = L.crw_labelprop_scratch_bytes(R, T, N, C, k, int(precision), int(normalize), int(return_topk))
+    scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.crw_labelprop_forward(_p(feats), _p(mask0), R, T, N, C, M, ctx, float(radius), float(temp), k,
+                                           int(mode), int(precision), int(normalize), _p(labels), _p(masks), _p(W),
+                                           _p(I), _p(scratch), sbytes, _stream()), "crw_labelprop_forward")
+    return labels, masks, W, I
+
+
+@labelprop.register_fake
+def _(feats, mask0, ctx, radius, temp, k, mode, precision, normalize, return_topk):
+    R, T, N, _ = feats.shape
+    M = mask0.shape[1]
+    dev = feats.device
+    tk = (R, T, k, N) if return_topk else (0,)
+    return (torch.empty((R, T, N), device=dev, dtype=torch.int32), feats.new_empty((R, T, M, N)),
+            feats.new_empty(tk), torch.empty(tk, device=dev, dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# horizontality_xent  (utils.py:118-123)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::horizontality_xent", mutates_args=())
+def horizontality_xent(emb: Tensor) -> Tensor:
+    """emb [T,N,C] normalised -> xent [N,T-1]."""
+    emb = _chk(emb, "emb")
+    T, N, C = emb.shape
+    out = torch.empty((N, max(T - 1, 0)), device=emb.device, dtype=torch.float32)
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.lib().crw_horizontality_xent(_p(emb), T, N, C, _p(out), _stream()), "crw_horizontality_xent")
+    return out
+
+
+@horizontality_xent.register_fake
+def _(emb):
+    T, N, _ = emb.shape
+    return emb.new_empty((N, max(T - 1, 0)))
