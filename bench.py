@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- CRW hot-path benchmark (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 20 --warmup 5
+    python bench.py --impl reference --steps 3 --warmup 1       # CPU arm (oracle port) on the host cores
+
+Prints ONE JSON line on rank 0.  Primary workload = BASELINE config 2: CRW train step, B=32 per GPU,
+T=10 frames, N=47 nodes (400 rows, 32x32 patches, overlap 24), ResNet encoder (PyTorch), fused CUDA
+walk fwd+bwd, Adam step.  The same line carries a "labelprop" object = BASELINE config 3: label
+propagation over one 400 x 20k-column radargram per GPU (T=1250, N=49, 4 classes, ctx 20, k 10, r 12).
+
+value      whole-job radargrams/s (columns/s for labelprop) with inputs resident in HBM
+e2e        same, through the public API from pinned HOST buffers, H2D + D2H inside the timed region
+roofline   the path's own CUDA kernels: algorithmic FLOPs (walk; tensor bound) or bytes (labelprop; hbm
+           bound) over CUDA-event time, against MEASURED_PEAKS.json
+cpu_baseline  oracle port on the box's host cores, bounded sample (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+TRAIN = dict(B=32, T=10, H=400, patch=(32, 32), overlap=(24, 0), tau=0.07, lr=1e-3)       # config 2
+TRAIN_CPU_SAMPLE_B = 2
+LP = dict(R=1, rows=400, cols=20000, patch=(16, 16), overlap=(8, 0), M=4, ctx=20, k=10, radius=12, temp=0.07, C=128)
+COLS_PER_FRAME = 16
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            log("nvml unavailable:", e)
+            self.nv = None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop_flag = True
+        if self.nv:
+            self.t.join()
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def barrier_sync(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    import torch.distributed as dist
+    if world == 1:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed iterations (outside the CUDA-event brackets)."""
+
+    def __init__(self, mb=256):
+        self.buf = torch.empty(mb * 1024 * 1024 // 4, device="cuda", dtype=torch.float32)
+
+    def __call__(self):
+        self.buf.add_(1.0)
+
+
+def timed_loop(step_fn, steps, warmup, world, flush=None, sampler=None):
+    """W untimed warm-ups, then K steps, each bracketed by CUDA events on the launching stream; the whole loop
+    is bracketed by barrier + synchronize.  Returns mean ms/step (max over ranks)."""
+    for i in range(warmup):
+        step_fn(i)
+    barrier_sync(world)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx = sampler if sampler is not None else _Null()
+    with ctx:
+        for i in range(steps):
+            if flush is not None:
+                flush()
+            ev[i][0].record()
+            step_fn(warmup + i)
+            ev[i][1].record()
+        barrier_sync(world)
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    return max_over_ranks(ms, world)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def synth_train_batch(B, T, seed):
+    """randn radargrams [B, 400, T*32] cut exactly as the reference dataset does (src/dataset.py:34-39)."""
+    g = torch.Generator().manual_seed(seed)
+    (h, w), (oh, ow) = TRAIN["patch"], TRAIN["overlap"]
+    n = (TRAIN["H"] - oh) // (h - oh)                                   # dataset.py:22
+    rg = torch.randn(B, TRAIN["H"], T * w - ow * (T - 1), generator=g)
+    item = rg[:, : n * h - oh * (n - 1)].unfold(1, h, h - oh).unfold(2, w, w - ow)   # [B,N,T,h,w]
+    return item.permute(0, 2, 1, 3, 4).contiguous().float()
+
+
+def walk_flops(B, T, N, C):
+    f_aff = B * (T - 1) * 2 * N * N * C
+    f_walk = B * max(3 * T - 10, 0) * 2 * N ** 3
+    return 3 * (f_aff + f_walk)       # fwd + bwd
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def bench_train(crw, args, rank, world, local, pk):
+    """BASELINE config 2: full train step (PyTorch encoder + fused CUDA walk fwd/bwd + Adam)."""
+    import torch.distributed as dist  # noqa: F401
+    B, T, tau = TRAIN["B"], TRAIN["T"], TRAIN["tau"]
+    n_rot = 4   # rotate 4 distinct input batches: 4 x 61.6 MB > 126 MB L2
+    batches_host = [synth_train_batch(B, T, 1000 * rank + i).pin_memory() for i in range(n_rot)]
+    batches_dev = [b.cuda() for b in batches_host]
+    N = batches_dev[0].shape[2]
+    torch.manual_seed(11)
+    encoder = crw.Resnet(pos_embed=False).cuda().train()
+    model = crw.CRW(encoder, tau, False, need_A=False)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                          bucket_cap_mb=32)
+    opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"])
+    last_loss = [None]
+
+    def train_step(i, src=batches_dev):
+        seq = src[i % n_rot]
+        if not seq.is_cuda:
+            seq = seq.cuda(non_blocking=True)
+        loss, _ = model(seq)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        last_loss[0] = loss
+
+    sampler = ClockSampler(local)
+    ms = timed_loop(train_step, args.steps, args.warmup, world, sampler=sampler)
+
+    def train_step_e2e(i):
+        train_step(i, batches_host)
+        last_loss[0] = last_loss[0].item()      # D2H read of the step's result
+
+    ms_e2e = timed_loop(train_step_e2e, args.steps, 3, world)
+    return dict(ms_per_step=ms, value=B * world / (ms * 1e-3), N=N, clocks=sampler.summary(), loss=float(last_loss[0]),
+                e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="radargrams/s",
+                         h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
+
+
+def bench_walk(crw, args, world, pk, N=47):
+    """The hot path alone: fused walk fwd + bwd on resident embeddings (config-2 shape)."""
+    B, T, tau = TRAIN["B"], TRAIN["T"], TRAIN["tau"]
+    emb = torch.randn(B, T, N, 128, device="cuda", requires_grad=True)
+
+    def walk_step(i):
+        loss, _, _ = crw.ops.walk_loss(emb, tau, False, crw.ops.PREC_FP32)
+        emb.grad = None
+        loss.backward()
+
+    ms = timed_loop(walk_step, max(args.steps, 20), 5, world)
+    fl = walk_flops(B, T, N, 128)
+    tf = fl / (ms * 1e-3) / 1e12
+    return dict(ms=ms, launches=8,
+                roofline=dict(bound="tensor", achieved=tf, peak=pk["bf16"], unit="TFLOP/s", frac=tf / pk["bf16"],
+                              traffic=None, kernel="walk fwd+bwd kernels (fp32 FMA path), 8 launches",
+                              algorithmic_flops=fl, peak_source=pk["src"] + " bf16 burst",
+                              note="N=47: launch/latency bound; tensor-pipe ceiling at this N is <= ~36% (SURVEY 7.3.1)"))
+
+
+def bench_labelprop(crw, args, rank, world, pk):
+    """BASELINE config 3: one 400 x 20k-column radargram per GPU, features -> labels."""
+    Tl = LP["cols"] // COLS_PER_FRAME
+    Nl = (LP["rows"] - LP["overlap"][0]) // (LP["patch"][0] - LP["overlap"][0])
+    R, C, M = LP["R"], LP["C"], LP["M"]
+    g = torch.Generator().manual_seed(77 + rank)
+    feats_host = torch.randn(R, Tl, Nl, C, generator=g).pin_memory()
+    label0 = torch.randint(0, M, (R, Nl), generator=g)
+    mask0 = torch.stack([crw.utils.one_hot_mask(label0[r], M) for r in range(R)]).cuda()
+    feats_dev = feats_host.cuda()
+    res = [None]
+
+    def lp_step(i, src=feats_dev):
+        f = src if src.is_cuda else src.cuda(non_blocking=True)
+        labels, _, _, _ = crw.ops.labelprop(f, mask0, LP["ctx"], float(LP["radius"]), LP["temp"], LP["k"],
+                                            crw.ops.LP_REF_EXACT, crw.ops.PREC_FP32, True, False)
+        res[0] = labels
+
+    flush = L2Flusher()
+    ms = timed_loop(lp_step, args.steps, args.warmup, world, flush=flush)
+
+    def lp_step_e2e(i):
+        lp_step(i, feats_host)
+        res[0] = res[0].cpu()                   # D2H of the labels
+
+    ms_e2e = timed_loop(lp_step_e2e, args.steps, 3, world, flush=flush)
+    cols = R * Tl * COLS_PER_FRAME
+    lp_bytes = R * Tl * (Nl * C * 4 + Nl * 4)   # read features once + write labels
+    gbs = lp_bytes / (ms * 1e-3) / 1e9
+    dense = R * Tl * (LP["ctx"] + 1) * Nl * Nl * C * 2
+    return dict(
+        metric="labelprop_columns_per_sec", unit="columns/s", value=cols * world / (ms * 1e-3), ms_per_step=ms,
+        e2e=dict(value=cols * world / (ms_e2e * 1e-3), unit="columns/s",
+                 h2d_bytes_per_step=int(feats_host.numel() * 4), d2h_bytes_per_step=int(R * Tl * Nl * 4)),
+        roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=None,
+                      kernel="lp_topk_f32_kernel (+ normalise, gather)", algorithmic_bytes=lp_bytes,
+                      peak_source=pk["src"],
+                      tensor_bound_note=f"dense {dense / 1e9:.1f} GFLOP: AI ~514 FLOP/B > ridge, see DESIGN.md"),
+        gpu_launches=4 * args.steps, dtype="f32", frames=Tl,
+        config=dict(workload="BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
+                             "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact, precision=fp32",
+                    l2="flushed between iterations (256 MB write)"))
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import radar_sounder_crw_b200 as crw
+    pk = peaks()
+    torch.manual_seed(11 + rank)
+    only = args.only
+    tr = bench_train(crw, args, rank, world, local, pk) if only in ("all", "train") else None
+    wk = bench_walk(crw, args, world, pk) if only in ("all", "walk") else None
+    lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and only == "all":
+        cpu = cpu_baselines(steps_train=1, lp_frames=lp["frames"])
+        lp["cpu_baseline"] = cpu["labelprop"]
+
+    if rank == 0:
+        if only != "all":
+            print(json.dumps(dict(only=only, train=tr, walk=wk, labelprop=lp)), flush=True)
+        else:
+            B, T = TRAIN["B"], TRAIN["T"]
+            hot = dict(what="fused walk fwd+bwd (crw_b200::walk_loss + backward), embeddings resident", ms=wk["ms"],
+                       launches=wk["launches"], share_of_step=wk["ms"] / tr["ms_per_step"])
+            line = dict(
+                metric="crw_train_radargrams_per_sec", value=tr["value"], unit="radargrams/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=tr["ms_per_step"], higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="BASELINE config 2: CRW train step, B=32 per GPU, T=10 frames, 400-row radargram, "
+                                     "32x32 patches overlap (24,0) -> N=47 nodes, ResNet[1,1,1,1] encoder (PyTorch fp32), "
+                                     "fused CUDA walk fwd+bwd (fp32), Adam; random-init weights",
+                            global_batch=B * world, frames=T, nodes=tr["N"], tau=TRAIN["tau"],
+                            parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of encoder grads)" if world > 1 else ""),
+                            l2="4 rotating input batches (246 MB) > L2"),
+                clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=wk["launches"] * args.steps,
+                roofline=wk["roofline"], hot_path=hot, loss=tr["loss"],
+                cpu_baseline=(cpu["train"] if cpu else None), labelprop=lp)
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port) -- the only place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_train_port(steps, warmup, B):
+    from oracle.walk_torch_port import make_resnet_encoder, train_step
+    torch.manual_seed(11)
+    encoder = make_resnet_encoder().train()
+    opt = torch.optim.Adam(encoder.parameters(), lr=TRAIN["lr"])
+    seq = synth_train_batch(B, TRAIN["T"], 5)
+    best = None
+    for threads in sorted({1, os.cpu_count() or 1}):
+        torch.set_num_threads(threads)
+        for _ in range(warmup):
+            train_step(encoder, opt, seq, TRAIN["tau"])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            train_step(encoder, opt, seq, TRAIN["tau"])
+        dt = (time.perf_counter() - t0) / steps
+        log(f"cpu train port: B={B} threads={threads} {dt:.2f} s/step")
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    return best
+
+
+def cpu_baselines(steps_train, lp_frames):
+    from oracle import c_oracle
+    dt, threads = cpu_train_port(steps_train, 1, TRAIN_CPU_SAMPLE_B)
+    train = dict(value=TRAIN_CPU_SAMPLE_B / dt, unit="radargrams/s", cores=threads, kind="port",
+                 sample=f"B={TRAIN_CPU_SAMPLE_B} of the B=32 batch (same T=10, N=47, ResNet encoder, reference-order "
+                        f"(T-2)^2 walk with autograd, Adam), torch CPU, faster of 1 and {os.cpu_count()} threads")
+    rs = np.random.RandomState(3)
+    Nl = 49
+    feats = rs.randn(1, lp_frames, Nl, LP["C"]).astype(np.float32)
+    l0 = rs.randint(0, LP["M"], (1, Nl)).astype(np.int32)
+    c_oracle.labelprop(feats[:, :64], l0, LP["M"], LP["ctx"], LP["radius"], LP["temp"], LP["k"], want_masks=False, want_topk=False)
+    t0 = time.perf_counter()
+    c_oracle.labelprop(feats, l0, LP["M"], LP["ctx"], LP["radius"], LP["temp"], LP["k"], want_masks=False, want_topk=False)
+    dt_lp = time.perf_counter() - t0
+    lp = dict(value=lp_frames * COLS_PER_FRAME / dt_lp, unit="columns/s", cores=c_oracle.num_threads(), kind="port",
+              sample=f"full config-3 radargram ({lp_frames} frames), linear-time C port (oracle/crw_oracle.c, OpenMP); the "
+                     "reference's own O(T^2) torch loop measured 264-325 columns/s on 8 cores (BASELINE.md)")
+    return dict(train=train, labelprop=lp)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    B = TRAIN_CPU_SAMPLE_B
+    dt, threads = cpu_train_port(max(1, args.steps), max(1, min(args.warmup, 1)), B)
+    Tl = LP["cols"] // COLS_PER_FRAME
+    rs = np.random.RandomState(3)
+    feats = rs.randn(1, Tl, 49, LP["C"]).astype(np.float32)
+    l0 = rs.randint(0, LP["M"], (1, 49)).astype(np.int32)
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        c_oracle.labelprop(feats, l0, LP["M"], LP["ctx"], LP["radius"], LP["temp"], LP["k"], want_masks=False, want_topk=False)
+    dt_lp = (time.perf_counter() - t0) / max(1, args.steps)
+    value = B / dt
+    sample = (f"each step = B={B} radargrams of the B=32 config-2 batch (T=10, N=47, ResNet encoder, reference-order walk, "
+              f"autograd, Adam) on torch CPU, {threads} threads")
+    line = dict(impl="reference", metric="crw_train_radargrams_per_sec", value=value, unit="radargrams/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="BASELINE config 2 (bounded CPU sample): " + sample),
+                cpu_baseline=dict(value=value, unit="radargrams/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit="radargrams/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                labelprop=dict(metric="labelprop_columns_per_sec", unit="columns/s", value=Tl * COLS_PER_FRAME / dt_lp,
+                               ms_per_step=dt_lp * 1e3,
+                               cpu_baseline=dict(value=Tl * COLS_PER_FRAME / dt_lp, unit="columns/s",
+                                                 cores=c_oracle.num_threads(), kind="port",
+                                                 sample="full config-3 radargram, linear-time C port (OpenMP)"),
+                               e2e=dict(value=Tl * COLS_PER_FRAME / dt_lp, unit="columns/s", h2d_bytes_per_step=0,
+                                        d2h_bytes_per_step=0)))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop"],
+                    help="profiling aid: run one section only (the JSON line is then not the contract line)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,14 @@ def crw_loss_reference_order(emb: torch.Tensor, tau: float):
     return loss / N, A
 
 
+def make_resnet_encoder(in_ch: int = 1) -> torch.nn.Module:
+    """Same architecture as the reference's ``Resnet`` (src/encoder.py:62-89): 1x1 conv with padding=1,
+    BN, ReLU, then torchvision's ResNet(BasicBlock, [1,1,1,1], num_classes=128).  CPU-baseline use only."""
+    from torchvision.models.resnet import BasicBlock, ResNet
+    return torch.nn.Sequential(torch.nn.Conv2d(in_ch, 3, kernel_size=1, padding=1), torch.nn.BatchNorm2d(3),
+                               torch.nn.ReLU(inplace=True), ResNet(BasicBlock, [1, 1, 1, 1], num_classes=128))
+
+
 def train_step(encoder, optimizer, seq: torch.Tensor, tau: float):
     """One reference-shaped optimisation step (scripts/train.py:66-72) on whatever device ``seq`` is on."""
     B, T, N, H, W = seq.shape

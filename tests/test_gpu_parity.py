@@ -261,6 +261,9 @@ def test_crw_module_dropin_with_encoder(pkg):
     match a plain-torch fp64 restatement of model.py:22-46 driven by the same encoder weights."""
     from oracle.walk_torch_port import crw_loss_reference_order
     torch.manual_seed(11)
+    # the encoder is plain PyTorch on both sides; keep cuDNN/cuBLAS out of TF32 so the comparison sees the walk only
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     B, T, N, H, W = 2, 6, 12, 16, 16
     seq = torch.randn(B, T, N, H, W)
     enc = pkg.CNN(False).cuda().double()
