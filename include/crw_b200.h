@@ -142,6 +142,13 @@ int crw_labelprop_forward(const float* feats, const float* mask0, int R, int T, 
  * ---------------------------------------------------------------------------------- */
 int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Self-test of the tensor-core plumbing (TMA SWIZZLE_128B tiles -> tcgen05.mma -> TMEM -> tcgen05.ld):
+ *   out[128,BN] = A[128,128] * B[BN,128]^T, A/B bf16 row-major, out fp32; BN multiple of 16, <= 256.
+ * No reference counterpart; it pins the descriptor encodings the tensor-core kernels rely on.
+ * ---------------------------------------------------------------------------------- */
+int crw_debug_umma_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

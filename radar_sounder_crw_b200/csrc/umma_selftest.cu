@@ -1,0 +1,109 @@
+// umma_selftest.cu -- one-tile tcgen05 GEMM through exactly the TMA / descriptor / TMEM plumbing the
+// tensor-core kernels use: out[128 x BN] = A[128 x 128] * B[BN x 128]^T (bf16 in, fp32 out).
+// Exposed as crw_debug_umma_gemm so the GPU test-suite can pin the descriptor encodings against torch.
+#include "tc_common.cuh"
+
+namespace crw {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_k64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRW_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (cols * 2) % 16 || box_rows < 1 || box_rows > 256) return CRW_ERR_ALIGN;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
+}
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                     // [2 kblocks][128 rows][128 B]
+    uint8_t* sB = smem + 2 * 128 * 128;     // [2 kblocks][BN rows][128 B]
+    __shared__ uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(&bar_full, (uint32_t)((128 + BN) * 256));
+        for (int kb = 0; kb < 2; ++kb) {
+            tc::tma_load_2d(sA + kb * 128 * 128, &mapA, kb * 64, 0, &bar_full);
+            tc::tma_load_2d(sB + kb * BN * 128, &mapB, kb * 64, 0, &bar_full);
+        }
+        tc::mbar_wait(&bar_full, 0);
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::umma_idesc_bf16(128, BN);
+        for (int kb = 0; kb < 2; ++kb)
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = tc::umma_smem_desc_k128(tc::smem_u32(sA + kb * 128 * 128) + k * 32);
+                const uint64_t bd = tc::umma_smem_desc_k128(tc::smem_u32(sB + kb * BN * 128) + k * 32);
+                tc::umma_bf16_ss(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
+        tc::umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar_mma, 0);
+    tc::tc_fence_after();
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        float* o = out + (size_t)(warp * 32 + lane) * BN + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (c + i < BN) o[i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace crw
+
+using namespace crw;
+
+extern "C" int crw_debug_umma_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream) {
+    if (!A_bf16 || !B_bf16 || !out || BN < 16 || BN > 256 || (BN % 16)) return CRW_ERR_INVALID;
+    CUtensorMap mA, mB;
+    int rc = make_tmap_bf16_k64(&mA, A_bf16, 128, 128, 128);
+    if (rc != CRW_OK) return rc;
+    rc = make_tmap_bf16_k64(&mB, B_bf16, (uint64_t)BN, 128, (uint32_t)BN);
+    if (rc != CRW_OK) return rc;
+    const size_t smem = 1024 + 2 * 128 * 128 + 2 * (size_t)BN * 128;
+    CRW_CUDA_RET(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mA, mB, BN, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
