@@ -463,11 +463,16 @@ extern "C" int crw_label_gather_step(const float* W, const int32_t* I, const flo
     return CRW_OK;
 }
 
+namespace crw {
+int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
+               float* W, int32_t* I, void* scratch, cudaStream_t st);
+}
+
 extern "C" size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k, int precision, int do_normalize,
                                               int have_topk_out) {
-    (void)precision;
     size_t b = 0;
-    if (do_normalize) b += align_up((size_t)R * T * N * C * sizeof(float), 256);
+    if (precision == CRW_PREC_BF16X3) b += align_up((size_t)R * T * N * C * 2 * 2, 256);   // bf16 hi + lo
+    else if (do_normalize) b += align_up((size_t)R * T * N * C * sizeof(float), 256);
     if (!have_topk_out) b += 2 * align_up((size_t)R * T * k * N * sizeof(float), 256);
     return b + 256;
 }
@@ -483,6 +488,22 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
     const size_t need = crw_labelprop_scratch_bytes(R, T, N, C, k, precision, do_normalize, W_or_null != nullptr);
     if (need > 256 && (!scratch || scratch_bytes < need)) return CRW_ERR_WORKSPACE;
     char* sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+    if (precision == CRW_PREC_BF16X3) {
+        if (ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f) || (int64_t)N < k) return CRW_ERR_INVALID;
+        void* hilo = sp;
+        sp += align_up((size_t)R * T * N * C * 2 * 2, 256);
+        float* Wt = W_or_null;
+        int32_t* It = I_or_null;
+        if (!Wt) {
+            Wt = reinterpret_cast<float*>(sp);
+            sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+            It = reinterpret_cast<int32_t*>(sp);
+        }
+        int rc = lp_topk_tc(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, (cudaStream_t)stream);
+        if (rc != CRW_OK) return rc;
+        return crw_label_gather(Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks, stream);
+    }
+    if (precision != CRW_PREC_FP32) return CRW_ERR_UNSUPPORTED;
     const float* emb = feats;
     if (do_normalize) {
         float* e = reinterpret_cast<float*>(sp);

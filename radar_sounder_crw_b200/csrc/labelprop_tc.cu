@@ -1,0 +1,374 @@
+// labelprop_tc.cu -- tensor-core label-propagation affinity + top-k for sm_100a (tcgen05 / TMEM / TMA).
+//
+// Replaces the same reference code as labelprop_f32.cu (src/imported/maskedatt.py:151-175 with the radius
+// mask of :232-245), for the "bf16 path" of BASELINE.json: operands are error-compensated bf16 pairs
+// (x = hi + lo, dot ~ hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM), which keeps >= 99.9 % label
+// agreement on near-collinear embeddings where plain bf16 does not.
+//
+//   lp_prep_bf16_kernel   F.normalize (pinned order, bit-identical to the fp32 path) + hi/lo split
+//   lp_topk_tc_kernel     persistent, warp-specialised:
+//       warp 8      TMA producer: query tile (128 consecutive node rows) + 128-row key tiles, SWIZZLE_128B
+//       warp 9      tcgen05.mma issuer: 24 MMAs (3 passes x 8 k-steps) per key tile into one of 4 TMEM buffers
+//       warps 0-7   epilogue: tcgen05.ld a row per thread (thread = query node), frame-window + radius-band
+//                   predicate, running top-k in registers; the two column halves are merged through smem,
+//                   then softmax and the W / I stores.
+// A query tile is 128 consecutive rows of the [T*N, C] feature matrix, so tiles are dense even though
+// frames (N = 47..49 rows) straddle them; each thread derives its own frame / window from its row index.
+#include "tc_common.cuh"
+
+namespace crw {
+
+// ------------------------------------------------------------------------------------------
+// prep: normalise (optional) + split into bf16 hi / lo.  One warp per row, C == 128.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lp_prep_bf16_kernel(const float* __restrict__ x, int64_t rows, int do_normalize,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* xr = x + row * 128;
+    float v[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = xr[lane + 32 * m];
+    if (do_normalize) {
+        float ss = 0.0f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) ss = __fmaf_rn(v[m], v[m], ss);
+        ss = warp_sum_butterfly_rn(ss);
+        const float d = fmaxf(__fsqrt_rn(ss), kNormEps);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) v[m] = __fdiv_rn(v[m], d);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v[m]);
+        hi[row * 128 + lane + 32 * m] = h;
+        lo[row * 128 + lane + 32 * m] = __float2bfloat16_rn(v[m] - __bfloat162float(h));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------
+constexpr int kBM = 128;            // query rows per tile (TMEM lanes)
+constexpr int kBN = 128;            // key rows per stage (TMEM columns per accumulator buffer)
+constexpr int kStages = 2;          // key smem stages
+constexpr int kAcc = 4;             // TMEM accumulator buffers (4 x 128 columns = all 512)
+constexpr int kTileBytes = 4 * kBM * 128;   // [hi,lo][kblock 0,1][128 rows][128 B] = 64 KB
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = (kEpiWarps + 2) * 32;
+
+struct TcParams {
+    float* W;        // [R, T, k, N]  (row n of radargram r at ((r*T + n)*k + j)*N + q)
+    int32_t* I;
+    int R, T, N, ctx, rb, k;
+    float inv_temp;
+    int tiles_per_rg, total_tiles;
+};
+
+struct TileInfo {
+    int rg, r0;          // radargram, first (radargram-relative) query row
+    int n_lo, n_hi;      // first / last valid query frame in the tile (n_lo > n_hi: nothing to do)
+    int f_lo;            // first key frame of the contiguous key range [f_lo*N, n_hi*N)
+    int has_f0;          // separate frame-0 tile precedes the contiguous range
+    int n_ktiles;        // key tiles including the frame-0 tile
+};
+
+__device__ __forceinline__ TileInfo tile_info(const TcParams& p, int tile) {
+    TileInfo t;
+    t.rg = tile / p.tiles_per_rg;
+    t.r0 = (tile % p.tiles_per_rg) * kBM;
+    t.n_lo = max(1, t.r0 / p.N);
+    t.n_hi = min(p.T - 1, (t.r0 + kBM - 1) / p.N);
+    t.f_lo = max(0, t.n_lo - p.ctx);
+    t.has_f0 = t.f_lo > 0;
+    t.n_ktiles = (t.n_lo > t.n_hi) ? 0 : t.has_f0 + ceil_div((t.n_hi - t.f_lo) * p.N, kBN);
+    return t;
+}
+// first key row (radargram-relative) and number of valid key rows of key tile kt
+__device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t, int kt, int& row0, int& nrows) {
+    if (t.has_f0 && kt == 0) { row0 = 0; nrows = p.N; return; }
+    const int c = kt - t.has_f0;
+    row0 = t.f_lo * p.N + c * kBN;
+    nrows = min(kBN, t.n_hi * p.N - row0);
+}
+
+template <int KT>
+struct TopList {
+    float v[KT];
+    int id[KT];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < KT; ++s) { v[s] = -INFINITY; id[s] = 0x7fffffff; }
+    }
+    // insert keeping (value desc); a later candidate never displaces an equal value
+    __device__ __forceinline__ void insert(float x, int xid) {
+        bool g[KT];
+#pragma unroll
+        for (int s = 0; s < KT; ++s) g[s] = x > v[s];
+#pragma unroll
+        for (int s = KT - 1; s > 0; --s) {
+            v[s] = g[s - 1] ? v[s - 1] : (g[s] ? x : v[s]);
+            id[s] = g[s - 1] ? id[s - 1] : (g[s] ? xid : id[s]);
+        }
+        v[0] = g[0] ? x : v[0];
+        id[0] = g[0] ? xid : id[0];
+    }
+    // full comparator (value desc, id asc) for merging lists whose ids interleave
+    __device__ __forceinline__ void insert_tie(float x, int xid) {
+        bool g[KT];
+#pragma unroll
+        for (int s = 0; s < KT; ++s) g[s] = (x > v[s]) || (x == v[s] && xid < id[s]);
+#pragma unroll
+        for (int s = KT - 1; s > 0; --s) {
+            v[s] = g[s - 1] ? v[s - 1] : (g[s] ? x : v[s]);
+            id[s] = g[s - 1] ? id[s - 1] : (g[s] ? xid : id[s]);
+        }
+        v[0] = g[0] ? x : v[0];
+        id[0] = g[0] ? xid : id[0];
+    }
+};
+
+template <int KT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                  // 64 KB
+    uint8_t* sK = smem + kTileBytes;                     // kStages x 64 KB
+    float* mv = reinterpret_cast<float*>(sK + kStages * kTileBytes);   // merge scratch [128][KT] values
+    int* mi = reinterpret_cast<int*>(mv + kBM * KT);                   //               [128][KT] ids
+    __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N;
+
+    if (warp == 9) tc::tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&q_full, 1);
+        tc::mbar_init(&q_empty, 1);
+        for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
+        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], kEpiWarps); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 8 && lane == 0) { tc::prefetch_tmap(&map_hi); tc::prefetch_tmap(&map_lo); }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 8) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t kcnt = 0, tcnt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileInfo t = tile_info(p, tile);
+                if (t.n_ktiles == 0) continue;
+                const int grow = t.rg * p.T * N;   // first global row of this radargram
+                tc::mbar_wait(&q_empty, (tcnt & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&q_full, kTileBytes);
+                for (int part = 0; part < 2; ++part)
+                    for (int kb = 0; kb < 2; ++kb)
+                        tc::tma_load_2d(sQ + (part * 2 + kb) * (kBM * 128), part ? &map_lo : &map_hi, kb * 64, grow + t.r0, &q_full);
+                for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                    const int s = kcnt % kStages;
+                    int row0, nrows;
+                    ktile_rows(p, t, kt, row0, nrows);
+                    tc::mbar_wait(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+                    tc::mbar_arrive_expect_tx(&k_full[s], kTileBytes);
+                    uint8_t* dst = sK + s * kTileBytes;
+                    for (int part = 0; part < 2; ++part)
+                        for (int kb = 0; kb < 2; ++kb)
+                            tc::tma_load_2d(dst + (part * 2 + kb) * (kBN * 128), part ? &map_lo : &map_hi, kb * 64, grow + row0,
+                                            &k_full[s]);
+                }
+                ++tcnt;
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t kcnt = 0, tcnt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileInfo t = tile_info(p, tile);
+                if (t.n_ktiles == 0) continue;
+                tc::mbar_wait(&q_full, tcnt & 1);
+                for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                    const int s = kcnt % kStages, a = kcnt % kAcc;
+                    int row0, nrows;
+                    ktile_rows(p, t, kt, row0, nrows);
+                    const int ncols = min(kBN, (nrows + 15) & ~15);
+                    tc::mbar_wait(&k_full[s], (kcnt / kStages) & 1);
+                    tc::mbar_wait(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
+                    const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK + s * kTileBytes);
+                    const uint32_t d = tmem_base + (uint32_t)(a * kBN);
+                    uint32_t acc = 0;
+                    // pass 0: q_hi.k_hi   pass 1: q_hi.k_lo   pass 2: q_lo.k_hi
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t qpart = (pass == 2) ? 2u : 0u, kpart = (pass == 1) ? 2u : 0u;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = tc::umma_smem_desc_k128(q0 + (qpart + kb) * (kBM * 128) + ks * 32);
+                                const uint64_t bd = tc::umma_smem_desc_k128(k0 + (kpart + kb) * (kBN * 128) + ks * 32);
+                                tc::umma_bf16_ss(d, ad, bd, idesc, acc);
+                                acc = 1;
+                            }
+                    }
+                    tc::umma_commit(&k_empty[s]);     // smem stage may be refilled once these MMAs retire
+                    tc::umma_commit(&acc_full[a]);    // accumulator ready for the epilogue
+                }
+                tc::umma_commit(&q_empty);            // query tile may be overwritten
+                ++tcnt;
+            }
+        }
+    } else {
+        // ================= epilogue: 8 warps, thread = query row, warp/4 = column half =================
+        const int g = warp & 3, half = warp >> 2;
+        const int lrow = g * 32 + lane;
+        const int rb = p.rb, ctx = p.ctx, k = p.k;
+        uint32_t kcnt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileInfo t = tile_info(p, tile);
+            if (t.n_ktiles == 0) continue;
+            const int row = t.r0 + lrow;
+            const int n = row / N, q = row - n * N;
+            const bool qvalid = (n >= 1) && (n < p.T);
+            const int win_lo = (n > ctx + 1) ? n - ctx : 1;     // non-zero key frames allowed: [win_lo, n)
+            TopList<KT> top;
+            top.init();
+            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                const int a = kcnt % kAcc;
+                int row0, nrows;
+                ktile_rows(p, t, kt, row0, nrows);
+                tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + half * 64);
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int c0 = half * 64 + ch * 32;
+                    if (c0 >= nrows) break;                       // warp-uniform
+                    float v[32];
+                    tc::tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                    tc::tmem_ld_wait();
+                    int kr = row0 + c0;
+                    int kf = kr / N, j = kr - kf * N;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const bool fr_ok = (kf < n) && (kf == 0 || kf >= win_lo);
+                        const int dj = j - q;
+                        const bool ok = qvalid && fr_ok && (c0 + i < nrows) && (dj <= rb) && (-dj <= rb);
+                        if (ok && v[i] > top.v[KT - 1]) {
+                            const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
+                            top.insert(v[i], slot * N + j);
+                        }
+                        if (++j == N) { j = 0; ++kf; }
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+            }
+            // ---- merge the two column halves (warps 4-7 -> smem -> warps 0-3) ----
+            if (half == 1) {
+#pragma unroll
+                for (int s = 0; s < KT; ++s) { mv[lrow * KT + s] = top.v[s]; mi[lrow * KT + s] = top.id[s]; }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (half == 0) {
+                for (int s = 0; s < KT; ++s) {
+                    const float x = mv[lrow * KT + s];
+                    if (x > -INFINITY) top.insert_tie(x, mi[lrow * KT + s]);
+                }
+                if (qvalid) {
+                    // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
+                    const int F = n_key_frames(n, ctx);
+                    int live = 0;
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) live += (s < k && top.v[s] > -INFINITY) ? 1 : 0;
+                    const float masked = kMaskBias;   // raw-dot domain stand-in: exp() of it is exactly 0
+                    if (live < k) {
+                        int need = k - live, fill = live;
+                        for (int f = 0; f < F && need > 0; ++f)
+                            for (int jj = 0; jj < N && need > 0; ++jj) {
+                                const int dj = jj - q;
+                                if (dj <= rb && -dj <= rb) continue;
+#pragma unroll
+                                for (int s = 0; s < KT; ++s)
+                                    if (s == fill) { top.v[s] = masked; top.id[s] = f * N + jj; }
+                                ++fill; --need;
+                            }
+                    }
+                    const float l0 = top.v[0] * p.inv_temp;
+                    float e[KT], sum = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) {
+                        e[s] = (s < k) ? pinned_expf(top.v[s] * p.inv_temp - l0) : 0.0f;
+                        sum += e[s];
+                    }
+                    const float inv = 1.0f / sum;
+                    const size_t base = ((size_t)(t.rg * p.T + n) * k) * N + q;
+#pragma unroll
+                    for (int s = 0; s < KT; ++s)
+                        if (s < k) {
+                            p.W[base + (size_t)s * N] = e[s] * inv;
+                            p.I[base + (size_t)s * N] = top.id[s];
+                        }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // scratch free for the next tile
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tc::tmem_dealloc<512>(tmem_base);
+}
+
+template <int KT>
+static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)(1 + kStages) * kTileBytes + (size_t)kBM * KT * 8;
+    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    lp_topk_tc_kernel<KT><<<grid, kTcThreads, smem, st>>>(mh, ml, p);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+// Host entry used by crw_labelprop_forward: feats [R,T,N,128] fp32 -> W, I [R,T,k,N].
+// scratch must hold 2 * R*T*N*128 bf16.
+int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
+               float* W, int32_t* I, void* scratch, cudaStream_t st) {
+    if (C != 128 || N > 128 || N < 8 || k > 32) return CRW_ERR_UNSUPPORTED;
+    const int64_t rows = (int64_t)R * T * N;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
+    __nv_bfloat16* lo = hi + rows * 128;
+    lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
+    CRW_LAUNCH_RET();
+    if (T < 2) return CRW_OK;
+    CUtensorMap mh, ml;
+    int rc = make_tmap_bf16_k64(&mh, hi, (uint64_t)rows, 128, kBM);
+    if (rc != CRW_OK) return rc;
+    rc = make_tmap_bf16_k64(&ml, lo, (uint64_t)rows, 128, kBM);
+    if (rc != CRW_OK) return rc;
+    TcParams p;
+    p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
+    const float rc_ = ceilf(radius);
+    p.rb = (rc_ - 1.0f >= (float)N) ? N : (int)rc_ - 1;
+    p.inv_temp = 1.0f / temp;
+    p.tiles_per_rg = ceil_div(T * N, kBM);
+    p.total_tiles = R * p.tiles_per_rg;
+    if (k <= 10) return launch_tc<10>(mh, ml, p, st);
+    if (k <= 16) return launch_tc<16>(mh, ml, p, st);
+    if (k <= 20) return launch_tc<20>(mh, ml, p, st);
+    return launch_tc<32>(mh, ml, p, st);
+}
+
+}  // namespace crw

@@ -26,3 +26,76 @@ def test_umma_selftest_matches_torch(pkg, BN):
     ref = A.float() @ B.float().t()
     err = (out - ref).abs().max().item()
     assert err < 1e-3, err   # bf16 products are exact in fp32; only the accumulation order differs
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core label propagation (bf16 hi/lo x3, tcgen05): the "bf16 path" of BASELINE.json
+# bar: >= 99.9 % pixel agreement with the fp32 path; top-k sets identical except across near-ties
+# ----------------------------------------------------------------------------------------------
+from helpers import lp_case, topk_sets_equal  # noqa: E402
+from oracle import c_oracle, labelprop_oracle as lo  # noqa: E402
+
+TC_CASES = [
+    # R, T, N, M, ctx, k, radius, clustered
+    (1, 3, 49, 4, 20, 10, 12, False),       # one key tile
+    (1, 60, 49, 4, 20, 10, 12, False),      # config-3 parameters, frame-0 tile appears (n > ctx+1)
+    (2, 40, 47, 4, 20, 20, 24, True),       # config-5 parameters, clustered (near-collinear) features, 2 radargrams
+    (1, 30, 49, 4, 5, 10, 12, False),       # small ctx: trim active almost everywhere
+    (1, 20, 113, 5, 4, 10, 12, True),       # SHARAD node count (N > 64)
+    (1, 400, 49, 4, 20, 10, 12, True),      # > 148 query tiles: persistent loop, barrier phase wrap
+    (1, 12, 25, 3, 20, 20, 10, False),      # fewer than k in-band keys -> masked fill
+    (3, 9, 16, 9, 2, 16, 5, False),         # tiny N, several frames per tile, KT=16
+    (1, 8, 64, 2, 3, 32, 100, False),       # k = 32, radius >= N
+]
+
+
+def _dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_lp_tensorcore_vs_fp32_oracle(pkg, case):
+    R, T, N, M, ctx, k, radius, clustered = case
+    rs = np.random.RandomState(200 + TC_CASES.index(case))
+    feats = rs.randn(R, T, N, 128).astype(np.float32)
+    if clustered:
+        feats += 3.0 * rs.randn(R, 1, 1, 128).astype(np.float32)
+    label0 = rs.randint(0, M, (R, N)).astype(np.int32)
+    mask0 = np.stack([lo.one_hot_mask(label0[r], M, np.float32) for r in range(R)])
+    labels, masks, W, I = pkg.ops.labelprop(_dev(feats), _dev(mask0), ctx, float(radius), 0.07, k, 0,
+                                            pkg.ops.PREC_BF16X3, True, True)
+    torch.cuda.synchronize()
+    labels, masks, W, I = labels.cpu().numpy(), masks.cpu().numpy(), W.cpu().numpy(), I.cpu().numpy()
+    o = c_oracle.labelprop(feats, label0, M, ctx, radius, 0.07, k)
+    agree = (labels == o["labels"]).mean()
+    frac, same = topk_sets_equal(I[:, 1:], W[:, 1:], o["I"][:, 1:], o["W"][:, 1:])
+    assert agree >= 0.999, f"label agreement {agree:.5f}"
+    assert frac >= 0.995, f"top-k set agreement {frac:.5f}"
+    # where the id lists coincide exactly, the weights agree to bf16x3 accuracy
+    eq = (I[:, 1:] == o["I"][:, 1:]).all(2, keepdims=True)
+    assert np.abs(np.where(eq, W[:, 1:] - o["W"][:, 1:], 0)).max() < 2e-4
+    assert np.abs(W[:, 1:].sum(2) - 1).max() < 1e-5
+
+
+def test_lp_tensorcore_golden_reference_labels(pkg):
+    """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
+    for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
+        g = lp_case(name)
+        mask0 = lo.one_hot_mask(g["label0"], g["M"], np.float32)[None]
+        labels, _, _, _ = pkg.ops.labelprop(_dev(g["feats"][None]), _dev(mask0), g["ctx"], g["radius"], g["temp"], g["k"], 0,
+                                            pkg.ops.PREC_BF16X3, True, False)
+        agree = (labels[0].t().cpu().numpy() == g["labels"]).mean()
+        assert agree >= 0.999, (name, agree)
+
+
+def test_lp_tensorcore_config3_full_size(pkg):
+    T, N, M = 1250, 49, 4
+    rs = np.random.RandomState(11)
+    feats = (rs.randn(1, T, N, 128) + 2.0 * rs.randn(1, 1, 1, 128)).astype(np.float32)
+    label0 = rs.randint(0, M, (1, N)).astype(np.int32)
+    mask0 = lo.one_hot_mask(label0[0], M, np.float32)[None]
+    labels, masks, W, I = pkg.ops.labelprop(_dev(feats), _dev(mask0), 20, 12.0, 0.07, 10, 0, pkg.ops.PREC_BF16X3, True, True)
+    o = c_oracle.labelprop(feats, label0, M, 20, 12, 0.07, 10)
+    assert (labels.cpu().numpy() == o["labels"]).mean() >= 0.999
+    frac, _ = topk_sets_equal(I.cpu().numpy()[:, 1:], W.cpu().numpy()[:, 1:], o["I"][:, 1:], o["W"][:, 1:])
+    assert frac >= 0.995
