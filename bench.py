@@ -257,14 +257,26 @@ def bench_labelprop(crw, args, rank, world, pk):
     feats_dev = feats_host.cuda()
     res = [None]
 
+    prec = [crw.ops.PREC_BF16X3]
+
     def lp_step(i, src=feats_dev):
         f = src if src.is_cuda else src.cuda(non_blocking=True)
         labels, _, _, _ = crw.ops.labelprop(f, mask0, LP["ctx"], float(LP["radius"]), LP["temp"], LP["k"],
-                                            crw.ops.LP_REF_EXACT, crw.ops.PREC_FP32, True, False)
+                                            crw.ops.LP_REF_EXACT, prec[0], True, False)
         res[0] = labels
 
     flush = L2Flusher()
+    fp32_path = None
+    if args.lp_precision in ("both", "fp32"):
+        prec[0] = crw.ops.PREC_FP32
+        ms32 = timed_loop(lp_step, args.steps, args.warmup, world, flush=flush)
+        labels32 = res[0].clone()
+        fp32_path = dict(ms_per_step=ms32, value=R * Tl * COLS_PER_FRAME * world / (ms32 * 1e-3), unit="columns/s",
+                         note="fp32 FMA path, pinned order, bit-exact against oracle/crw_oracle.c")
+    prec[0] = crw.ops.PREC_BF16X3 if args.lp_precision != "fp32" else crw.ops.PREC_FP32
     ms = timed_loop(lp_step, args.steps, args.warmup, world, flush=flush)
+    if fp32_path is not None and args.lp_precision == "both":
+        fp32_path["label_agreement_with_primary"] = float((labels32 == res[0]).float().mean().item())
 
     def lp_step_e2e(i):
         lp_step(i, feats_host)
@@ -280,12 +292,14 @@ def bench_labelprop(crw, args, rank, world, pk):
         e2e=dict(value=cols * world / (ms_e2e * 1e-3), unit="columns/s",
                  h2d_bytes_per_step=int(feats_host.numel() * 4), d2h_bytes_per_step=int(R * Tl * Nl * 4)),
         roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"], traffic=None,
-                      kernel="lp_topk_f32_kernel (+ normalise, gather)", algorithmic_bytes=lp_bytes,
+                      kernel="lp_prep_bf16 + lp_topk_tc_kernel (tcgen05 bf16x3) + gather kernels" if args.lp_precision != "fp32"
+                      else "l2_normalize + lp_topk_f32_kernel + gather kernels", algorithmic_bytes=lp_bytes,
                       peak_source=pk["src"],
                       tensor_bound_note=f"dense {dense / 1e9:.1f} GFLOP: AI ~514 FLOP/B > ridge, see DESIGN.md"),
-        gpu_launches=4 * args.steps, dtype="f32", frames=Tl,
+        gpu_launches=4 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
+        frames=Tl, fp32_path=fp32_path,
         config=dict(workload="BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
-                             "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact, precision=fp32",
+                             "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact",
                     l2="flushed between iterations (256 MB write)"))
 
 
@@ -419,6 +433,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lp-precision", default="both", choices=["both", "bf16x3", "fp32"])
     ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()

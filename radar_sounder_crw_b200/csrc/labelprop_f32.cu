@@ -310,6 +310,77 @@ __global__ void __launch_bounds__(256) lp_gather_seq_kernel(GatherParams p, int 
     }
 }
 
+// Shared-memory version of the sequential gather: the soft masks of frame 0 and of the last ctx+1 frames
+// live in a ring in shared memory (slot(f) = f == 0 ? 0 : 1 + (f-1) % (ctx+1); identical to f while
+// f <= ctx+1), and each frame's W / I rows are prefetched with cp.async one frame ahead.
+__device__ __forceinline__ int ring_slot(int f, int ctx) { return f == 0 ? 0 : 1 + (f - 1) % (ctx + 1); }
+
+__global__ void __launch_bounds__(256) lp_gather_seq_smem_kernel(GatherParams p, int n_end) {
+    extern __shared__ __align__(16) float gsm[];
+    const int r = blockIdx.x, N = p.N, M = p.M, k = p.k, ctx = p.ctx;
+    const int kn = k * N, mn = M * N;
+    float* ring = gsm;                                     // [ctx+2][M][N]
+    float* wbuf = ring + (size_t)(ctx + 2) * mn;           // [2][k*N]
+    int* ibuf = reinterpret_cast<int*>(wbuf + 2 * kn);     // [2][k*N]
+    const float* W = p.W + (size_t)r * p.T * kn;
+    const int32_t* I = p.I + (size_t)r * p.T * kn;
+    float* masks = p.masks + (size_t)r * p.T * mn;
+    int32_t* labels = p.labels + (size_t)r * p.T * N;
+    const float* m0 = p.mask0 + (size_t)r * mn;
+
+    auto prefetch = [&](int n) {
+        const uint32_t wdst = (uint32_t)__cvta_generic_to_shared(wbuf + (n & 1) * kn);
+        const uint32_t idst = (uint32_t)__cvta_generic_to_shared(ibuf + (n & 1) * kn);
+        for (int i = threadIdx.x; i < kn; i += blockDim.x) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wdst + 4 * i), "l"(W + (size_t)n * kn + i));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(idst + 4 * i), "l"(I + (size_t)n * kn + i));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (n_end > 1) prefetch(1);
+    for (int i = threadIdx.x; i < mn; i += blockDim.x) { const float v = m0[i]; ring[i] = v; masks[i] = v; }
+    for (int q = threadIdx.x; q < N; q += blockDim.x) {
+        float best = 0.0f;
+        int bm = 0;
+        for (int m = 0; m < M; ++m) { const float v = m0[(size_t)m * N + q]; if (m == 0 || v > best) { best = v; bm = m; } }
+        labels[q] = bm;
+    }
+    for (int n = 1; n < n_end; ++n) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                       // W/I of frame n landed; ring writes of frame n-1 visible
+        if (n + 1 < n_end) prefetch(n + 1);
+        const float* wn = wbuf + (n & 1) * kn;
+        const int* in = ibuf + (n & 1) * kn;
+        float* out = ring + (size_t)ring_slot(n, ctx) * mn;
+        for (int q = threadIdx.x; q < N; q += blockDim.x) {
+            float best = 0.0f;
+            int best_m = 0;
+            for (int mb = 0; mb < M; mb += 8) {
+                float acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
+                for (int j = 0; j < k; ++j) {
+                    const int id = in[j * N + q];
+                    const float w = wn[j * N + q];
+                    const int lf = label_frame(n, ctx, id / N, p.mode_fixed);
+                    const float* src = ring + (size_t)ring_slot(lf, ctx) * mn + (size_t)mb * N + (id % N);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (mb + u < M) acc[u] = __fadd_rn(acc[u], __fmul_rn(src[u * N], w));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (mb + u < M) {
+                        out[(size_t)(mb + u) * N + q] = acc[u];
+                        masks[((size_t)n * M + mb + u) * N + q] = acc[u];
+                        if ((mb + u == 0) || acc[u] > best) { best = acc[u]; best_m = mb + u; }
+                    }
+            }
+            labels[(size_t)n * N + q] = best_m;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) lp_gather_par_kernel(GatherParams p, int n_begin, int n_end) {
     const int r = blockIdx.y;
     const int N = p.N;
@@ -443,7 +514,13 @@ extern "C" int crw_label_gather(const float* W, const int32_t* I, const float* m
     p.R = R; p.T = T; p.N = N; p.M = M; p.ctx = ctx; p.k = k; p.mode_fixed = (mode == CRW_LP_FIXED);
     // frames that must run in order: all of them in fixed mode, the first ctx+1 in ref_exact mode
     const int seq_end = p.mode_fixed ? T : min(T, ctx + 2);
-    lp_gather_seq_kernel<<<R, 256, 0, st>>>(p, 1, seq_end, 1);
+    const size_t gsmem = ((size_t)(ctx + 2) * M * N + 4 * (size_t)k * N) * sizeof(float);
+    if (gsmem <= 200 * 1024) {
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        lp_gather_seq_smem_kernel<<<R, 256, gsmem, st>>>(p, seq_end);
+    } else {
+        lp_gather_seq_kernel<<<R, 256, 0, st>>>(p, 1, seq_end, 1);
+    }
     CRW_LAUNCH_RET();
     if (seq_end < T) {
         const long long total = (long long)(T - seq_end) * N;
