@@ -345,39 +345,49 @@ __global__ void __launch_bounds__(256) lp_gather_seq_smem_kernel(GatherParams p,
         for (int m = 0; m < M; ++m) { const float v = m0[(size_t)m * N + q]; if (m == 0 || v > best) { best = v; bm = m; } }
         labels[q] = bm;
     }
+    // three short phases per frame: (A) k*N threads form the products label * weight, (B) M*N threads add
+    // them in top-k order (the pinned sequential sum), (C) N threads take the argmax.
+    float* prod = reinterpret_cast<float*>(ibuf + 2 * kn);          // [k][M][N]
+    const unsigned magic_n = (unsigned)(0x100000000ull / (unsigned)N) + 1u;
+    int nm = 0;                                                      // (n-1) % (ctx+1)
     for (int n = 1; n < n_end; ++n) {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();                       // W/I of frame n landed; ring writes of frame n-1 visible
         if (n + 1 < n_end) prefetch(n + 1);
         const float* wn = wbuf + (n & 1) * kn;
         const int* in = ibuf + (n & 1) * kn;
-        float* out = ring + (size_t)ring_slot(n, ctx) * mn;
+        const bool trimmed = (n > ctx + 1);
+        for (int idx = threadIdx.x; idx < kn; idx += blockDim.x) {
+            const int j = (int)__umulhi((unsigned)idx, magic_n), q = idx - j * N;
+            const int id = in[idx];
+            const float w = wn[idx];
+            const int f = (int)__umulhi((unsigned)id, magic_n), jj = id - f * N;
+            // frame the slot f gathers from (labelprop.py:82,106) and its ring slot
+            int slot;
+            if (!trimmed) slot = f;                                   // frames 0..n-1, slot == frame
+            else if (!p.mode_fixed) slot = f;                         // quirk: untrimmed list, frames 0..ctx
+            else if (f == 0) slot = 0;
+            else { const int d = ctx - f + 1; int s2 = nm - d; if (s2 < 0) s2 += ctx + 1; slot = 1 + s2; }
+            const float* src = ring + (size_t)slot * mn + jj;
+            float* dst = prod + (size_t)j * mn + q;
+            for (int m = 0; m < M; ++m) dst[m * N] = __fmul_rn(src[m * N], w);
+        }
+        __syncthreads();
+        float* out = ring + (size_t)(1 + nm) * mn;
+        for (int idx = threadIdx.x; idx < mn; idx += blockDim.x) {
+            float acc = 0.0f;
+            for (int j = 0; j < k; ++j) acc = __fadd_rn(acc, prod[(size_t)j * mn + idx]);
+            out[idx] = acc;
+            masks[(size_t)n * mn + idx] = acc;
+        }
+        __syncthreads();
         for (int q = threadIdx.x; q < N; q += blockDim.x) {
-            float best = 0.0f;
+            float best = out[q];
             int best_m = 0;
-            for (int mb = 0; mb < M; mb += 8) {
-                float acc[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] = 0.0f;
-                for (int j = 0; j < k; ++j) {
-                    const int id = in[j * N + q];
-                    const float w = wn[j * N + q];
-                    const int lf = label_frame(n, ctx, id / N, p.mode_fixed);
-                    const float* src = ring + (size_t)ring_slot(lf, ctx) * mn + (size_t)mb * N + (id % N);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (mb + u < M) acc[u] = __fadd_rn(acc[u], __fmul_rn(src[u * N], w));
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (mb + u < M) {
-                        out[(size_t)(mb + u) * N + q] = acc[u];
-                        masks[((size_t)n * M + mb + u) * N + q] = acc[u];
-                        if ((mb + u == 0) || acc[u] > best) { best = acc[u]; best_m = mb + u; }
-                    }
-            }
+            for (int m = 1; m < M; ++m) { const float v = out[(size_t)m * N + q]; if (v > best) { best = v; best_m = m; } }
             labels[(size_t)n * N + q] = best_m;
         }
+        if (++nm == ctx + 1) nm = 0;
     }
 }
 
@@ -514,7 +524,7 @@ extern "C" int crw_label_gather(const float* W, const int32_t* I, const float* m
     p.R = R; p.T = T; p.N = N; p.M = M; p.ctx = ctx; p.k = k; p.mode_fixed = (mode == CRW_LP_FIXED);
     // frames that must run in order: all of them in fixed mode, the first ctx+1 in ref_exact mode
     const int seq_end = p.mode_fixed ? T : min(T, ctx + 2);
-    const size_t gsmem = ((size_t)(ctx + 2) * M * N + 4 * (size_t)k * N) * sizeof(float);
+    const size_t gsmem = ((size_t)(ctx + 2) * M * N + 4 * (size_t)k * N + (size_t)k * M * N) * sizeof(float);
     if (gsmem <= 200 * 1024) {
         CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         lp_gather_seq_smem_kernel<<<R, 256, gsmem, st>>>(p, seq_end);

@@ -64,6 +64,7 @@ struct TcParams {
     int R, T, N, ctx, rb, k;
     float inv_temp;
     int tiles_per_rg, total_tiles;
+    unsigned magic_n;   // floor(2^32 / N) + 1: x / N == __umulhi(x, magic_n) for x * N < 2^32
 };
 
 struct TileInfo {
@@ -136,8 +137,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                  // 64 KB
     uint8_t* sK = smem + kTileBytes;                     // kStages x 64 KB
-    float* mv = reinterpret_cast<float*>(sK + kStages * kTileBytes);   // merge scratch [128][KT] values
-    int* mi = reinterpret_cast<int*>(mv + kBM * KT);                   //               [128][KT] ids
+    float* stage_buf = reinterpret_cast<float*>(sK + kStages * kTileBytes);   // 8 warps x [32][32] floats (32 KB)
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
     __shared__ uint32_t tmem_base_s;
 
@@ -229,9 +229,15 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
     } else {
         // ================= epilogue: 8 warps, thread = query row, warp/4 = column half =================
+        // Per 32-column block: (1) tcgen05.ld the thread's row, (2) park it in a thread-private smem column
+        // ([i][lane]: bank = lane, conflict-free) so that candidates can be fetched by dynamic index,
+        // (3) build a "beats the current k-th best" bitmask (2 instr / element) and a validity bitmask
+        // (frame window x radius band, a few bit ops per block), (4) run ONE rolled insertion loop over the
+        // set bits.  Keeping the insertion code in a single place keeps the hot loop inside the I-cache.
         const int g = warp & 3, half = warp >> 2;
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
+        float* park = stage_buf + warp * 1024;          // [32][32] floats, private to this warp
         uint32_t kcnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
@@ -249,25 +255,50 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + half * 64);
-#pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const int c0 = half * 64 + ch * 32;
                     if (c0 >= nrows) break;                       // warp-uniform
                     float v[32];
                     tc::tmem_ld_32x32b_x32(taddr + ch * 32, v);
                     tc::tmem_ld_wait();
-                    int kr = row0 + c0;
-                    int kf = kr / N, j = kr - kf * N;
+                    const float thr = top.v[KT - 1];
+                    uint32_t pm = 0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const bool fr_ok = (kf < n) && (kf == 0 || kf >= win_lo);
-                        const int dj = j - q;
-                        const bool ok = qvalid && fr_ok && (c0 + i < nrows) && (dj <= rb) && (-dj <= rb);
-                        if (ok && v[i] > top.v[KT - 1]) {
-                            const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
-                            top.insert(v[i], slot * N + j);
+                        park[i * 32 + lane] = v[i];
+                        pm |= (v[i] > thr) ? (1u << i) : 0u;
+                    }
+                    // validity mask of this thread over the block's 32 key rows (segments = key frames)
+                    const int kr0 = row0 + c0;
+                    const int kf0 = (int)__umulhi((unsigned)kr0, p.magic_n);
+                    uint32_t vm = 0;
+                    {
+                        int c = 0, kf = kf0, j = kr0 - kf0 * N;
+                        const int cend = min(32, nrows - c0);
+                        while (c < cend) {                          // warp-uniform trip count
+                            const int seg = min(cend - c, N - j);
+                            if ((kf < n) && (kf == 0 || kf >= win_lo)) {
+                                const int lo = max(j, q - rb), hi = min(j + seg - 1, q + rb);
+                                if (lo <= hi) {
+                                    const int b0 = c + lo - j, nb = hi - lo + 1;
+                                    vm |= ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u)) << b0;
+                                }
+                            }
+                            c += seg; j = 0; ++kf;
                         }
-                        if (++j == N) { j = 0; ++kf; }
+                    }
+                    uint32_t cand = qvalid ? (pm & vm) : 0u;
+                    while (cand) {
+                        const int i = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        const float x = park[i * 32 + lane];
+                        if (x > top.v[KT - 1]) {
+                            const int kr = kr0 + i;
+                            const int kf = (int)__umulhi((unsigned)kr, p.magic_n);
+                            const int j = kr - kf * N;
+                            const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
+                            top.insert(x, slot * N + j);
+                        }
                     }
                 }
                 tc::tc_fence_before();
@@ -275,15 +306,18 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
             }
             // ---- merge the two column halves (warps 4-7 -> smem -> warps 0-3) ----
+            float* mv = stage_buf + (4 + g) * 1024;                       // values: half-1 warp's own buffer
+            int* mi = reinterpret_cast<int*>(stage_buf + g * 1024);       // ids: the partner (half-0) warp's buffer
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue warp is done with its park buffer
             if (half == 1) {
 #pragma unroll
-                for (int s = 0; s < KT; ++s) { mv[lrow * KT + s] = top.v[s]; mi[lrow * KT + s] = top.id[s]; }
+                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (half == 0) {
                 for (int s = 0; s < KT; ++s) {
-                    const float x = mv[lrow * KT + s];
-                    if (x > -INFINITY) top.insert_tie(x, mi[lrow * KT + s]);
+                    const float x = mv[s * 32 + lane];
+                    if (x > -INFINITY) top.insert_tie(x, mi[s * 32 + lane]);
                 }
                 if (qvalid) {
                     // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
@@ -331,7 +365,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 
 template <int KT>
 static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)(1 + kStages) * kTileBytes + (size_t)kBM * KT * 8;
+    const size_t smem = 1024 + (size_t)(1 + kStages) * kTileBytes + (size_t)kEpiWarps * 4096;
     CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -363,6 +397,8 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     const float rc_ = ceilf(radius);
     p.rb = (rc_ - 1.0f >= (float)N) ? N : (int)rc_ - 1;
     p.inv_temp = 1.0f / temp;
+    if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
+    p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     p.tiles_per_rg = ceil_div(T * N, kBM);
     p.total_tiles = R * p.tiles_per_rg;
     if (k <= 10) return launch_tc<10>(mh, ml, p, st);
