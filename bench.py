@@ -36,6 +36,7 @@ import torch  # noqa: E402
 TRAIN = dict(B=32, T=10, H=400, patch=(32, 32), overlap=(24, 0), tau=0.07, lr=1e-3)       # config 2
 TRAIN_CPU_SAMPLE_B = 2
 LP = dict(R=1, rows=400, cols=20000, patch=(16, 16), overlap=(8, 0), M=4, ctx=20, k=10, radius=12, temp=0.07, C=128)
+LP5 = dict(R_total=64, rows=400, cols=50000, patch=(16, 16), overlap=(8, 0), M=4, ctx=20, k=20, radius=24, temp=0.07, C=128)
 COLS_PER_FRAME = 16
 
 
@@ -194,7 +195,9 @@ def bench_train(crw, args, rank, world, local, pk):
     batches_dev = [b.cuda() for b in batches_host]
     N = batches_dev[0].shape[2]
     torch.manual_seed(11)
-    encoder = crw.Resnet(pos_embed=False).cuda().train()
+    # the encoder is plain PyTorch (out of scope as a kernel); channels_last + TF32 are host-side settings
+    torch.backends.cudnn.benchmark = True
+    encoder = crw.Resnet(pos_embed=False).cuda().train().to(memory_format=torch.channels_last)
     model = crw.CRW(encoder, tau, False, need_A=False)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
@@ -246,7 +249,14 @@ def bench_walk(crw, args, world, pk, N=47):
 
 
 def bench_labelprop(crw, args, rank, world, pk):
-    """BASELINE config 3: one 400 x 20k-column radargram per GPU, features -> labels."""
+    """BASELINE config 3: one 400 x 20k-column radargram per GPU, features -> labels (weak scaling).
+    --lp-config 5: BASELINE config 5, 64 radargrams of 400 x 50k columns sharded over the ranks (strong scaling)."""
+    global LP
+    cfg5 = args.lp_config == 5
+    if cfg5:
+        from radar_sounder_crw_b200.parallel import shard_range
+        b, e = shard_range(LP5["R_total"], rank, world)
+        LP = dict(LP5, R=e - b)
     Tl = LP["cols"] // COLS_PER_FRAME
     Nl = (LP["rows"] - LP["overlap"][0]) // (LP["patch"][0] - LP["overlap"][0])
     R, C, M = LP["R"], LP["C"], LP["M"]
@@ -284,6 +294,8 @@ def bench_labelprop(crw, args, rank, world, pk):
 
     ms_e2e = timed_loop(lp_step_e2e, args.steps, 3, world, flush=flush)
     cols = R * Tl * COLS_PER_FRAME
+    if cfg5:
+        cols = LP5["R_total"] * Tl * COLS_PER_FRAME / world     # value below multiplies by world
     lp_bytes = R * Tl * (Nl * C * 4 + Nl * 4)   # read features once + write labels
     gbs = lp_bytes / (ms * 1e-3) / 1e9
     dense = R * Tl * (LP["ctx"] + 1) * Nl * Nl * C * 2
@@ -298,8 +310,11 @@ def bench_labelprop(crw, args, rank, world, pk):
                       tensor_bound_note=f"dense {dense / 1e9:.1f} GFLOP: AI ~514 FLOP/B > ridge, see DESIGN.md"),
         gpu_launches=4 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
         frames=Tl, fp32_path=fp32_path,
-        config=dict(workload="BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
-                             "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact",
+        scaling="strong" if cfg5 else "weak",
+        config=dict(workload=(f"BASELINE config 5: 64 radargrams of 400x50000 columns sharded over {world} GPU(s) "
+                              f"({R} on this rank) -> T=3125 x N=49 x C=128, M=4, ctx=20, k=20, radius=24, temp=0.07" if cfg5 else
+                              "BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
+                              "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact"),
                     l2="flushed between iterations (256 MB write)"))
 
 
@@ -434,6 +449,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lp-precision", default="both", choices=["both", "bf16x3", "fp32"])
+    ap.add_argument("--lp-config", type=int, default=3, choices=[3, 5])
     ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()

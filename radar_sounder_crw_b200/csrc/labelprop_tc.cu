@@ -166,7 +166,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 const TileInfo t = tile_info(p, tile);
                 if (t.n_ktiles == 0) continue;
                 const int grow = t.rg * p.T * N;   // first global row of this radargram
-                tc::mbar_wait(&q_empty, (tcnt & 1) ^ 1);
+                tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(&q_full, kTileBytes);
                 for (int part = 0; part < 2; ++part)
                     for (int kb = 0; kb < 2; ++kb)
@@ -175,7 +175,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     const int s = kcnt % kStages;
                     int row0, nrows;
                     ktile_rows(p, t, kt, row0, nrows);
-                    tc::mbar_wait(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+                    tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
                     tc::mbar_arrive_expect_tx(&k_full[s], kTileBytes);
                     uint8_t* dst = sK + s * kTileBytes;
                     for (int part = 0; part < 2; ++part)
@@ -193,14 +193,14 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileInfo t = tile_info(p, tile);
                 if (t.n_ktiles == 0) continue;
-                tc::mbar_wait(&q_full, tcnt & 1);
+                tc::mbar_wait_backoff(&q_full, tcnt & 1);
                 for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
                     const int s = kcnt % kStages, a = kcnt % kAcc;
                     int row0, nrows;
                     ktile_rows(p, t, kt, row0, nrows);
                     const int ncols = min(kBN, (nrows + 15) & ~15);
-                    tc::mbar_wait(&k_full[s], (kcnt / kStages) & 1);
-                    tc::mbar_wait(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
+                    tc::mbar_wait_backoff(&k_full[s], (kcnt / kStages) & 1);
+                    tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
                     tc::tc_fence_after();
                     const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
                     const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK + s * kTileBytes);
@@ -237,7 +237,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int g = warp & 3, half = warp >> 2;
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
-        float* park = stage_buf + warp * 1024;          // [32][32] floats, private to this warp
+        const uint32_t park = tc::smem_u32(stage_buf + warp * 1024) + lane * 4;   // [32][32] floats, private to this warp
         uint32_t kcnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
@@ -265,7 +265,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     uint32_t pm = 0;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        park[i * 32 + lane] = v[i];
+                        tc::sts_f32(park + i * 128, v[i]);
                         pm |= (v[i] > thr) ? (1u << i) : 0u;
                     }
                     // validity mask of this thread over the block's 32 key rows (segments = key frames)
@@ -291,7 +291,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     while (cand) {
                         const int i = __ffs(cand) - 1;
                         cand &= cand - 1;
-                        const float x = park[i * 32 + lane];
+                        const float x = tc::lds_f32(park + i * 128);
                         if (x > top.v[KT - 1]) {
                             const int kr = kr0 + i;
                             const int kf = (int)__umulhi((unsigned)kr, p.magic_n);
