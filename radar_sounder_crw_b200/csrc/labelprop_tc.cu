@@ -51,12 +51,12 @@ __global__ void __launch_bounds__(256) lp_prep_bf16_kernel(const float* __restri
 // main kernel
 // ------------------------------------------------------------------------------------------
 constexpr int kBM = 128;            // query rows per tile (TMEM lanes)
-constexpr int kBN = 128;            // key rows per stage (TMEM columns per accumulator buffer)
-constexpr int kStages = 2;          // key smem stages
-constexpr int kAcc = 4;             // TMEM accumulator buffers (4 x 128 columns = all 512)
-constexpr int kTileBytes = 4 * kBM * 128;   // [hi,lo][kblock 0,1][128 rows][128 B] = 64 KB
-constexpr int kEpiWarps = 8;
-constexpr int kTcThreads = (kEpiWarps + 2) * 32;
+constexpr int kBN = 64;             // key rows per stage (TMEM columns per accumulator buffer)
+constexpr int kStages = 3;          // key smem stages
+constexpr int kAcc = 8;             // TMEM accumulator buffers (8 x 64 columns = all 512)
+constexpr int kQBytes = 4 * kBM * 128;   // [hi,lo][kblock 0,1][128 rows][128 B] = 64 KB
+constexpr int kKBytes = 4 * kBN * 128;   // [hi,lo][kblock 0,1][ 64 rows][128 B] = 32 KB
+constexpr int kParkBytes = 64 * 1024;    // epilogue scratch, split evenly between the epilogue warps
 
 struct TcParams {
     float* W;        // [R, T, k, N]  (row n of radargram r at ((r*T + n)*k + j)*N + q)
@@ -71,8 +71,8 @@ struct TileInfo {
     int rg, r0;          // radargram, first (radargram-relative) query row
     int n_lo, n_hi;      // first / last valid query frame in the tile (n_lo > n_hi: nothing to do)
     int f_lo;            // first key frame of the contiguous key range [f_lo*N, n_hi*N)
-    int has_f0;          // separate frame-0 tile precedes the contiguous range
-    int n_ktiles;        // key tiles including the frame-0 tile
+    int has_f0;          // number of separate frame-0 tiles preceding the contiguous range
+    int n_ktiles;        // key tiles including the frame-0 tiles
 };
 
 __device__ __forceinline__ TileInfo tile_info(const TcParams& p, int tile) {
@@ -82,13 +82,13 @@ __device__ __forceinline__ TileInfo tile_info(const TcParams& p, int tile) {
     t.n_lo = max(1, t.r0 / p.N);
     t.n_hi = min(p.T - 1, (t.r0 + kBM - 1) / p.N);
     t.f_lo = max(0, t.n_lo - p.ctx);
-    t.has_f0 = t.f_lo > 0;
+    t.has_f0 = (t.f_lo > 0) ? ceil_div(p.N, kBN) : 0;
     t.n_ktiles = (t.n_lo > t.n_hi) ? 0 : t.has_f0 + ceil_div((t.n_hi - t.f_lo) * p.N, kBN);
     return t;
 }
 // first key row (radargram-relative) and number of valid key rows of key tile kt
 __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t, int kt, int& row0, int& nrows) {
-    if (t.has_f0 && kt == 0) { row0 = 0; nrows = p.N; return; }
+    if (kt < t.has_f0) { row0 = kt * kBN; nrows = min(kBN, p.N - row0); return; }
     const int c = kt - t.has_f0;
     row0 = t.f_lo * p.N + c * kBN;
     nrows = min(kBN, t.n_hi * p.N - row0);
@@ -130,35 +130,42 @@ struct TopList {
     }
 };
 
-template <int KT>
-__global__ void __launch_bounds__(kTcThreads, 1)
-lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, TcParams p) {
+template <int KT, int NEPI>
+__global__ void __launch_bounds__((NEPI + 2) * 32, 1)
+lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_constant__ CUtensorMap qmap_lo,
+                  const __grid_constant__ CUtensorMap kmap_hi, const __grid_constant__ CUtensorMap kmap_lo, TcParams p) {
+    constexpr int kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
+    constexpr int kParts = NEPI / 4;          // top-k lists per query (merged at the end of a tile)
+    constexpr int kTileGroups = NEPI / 8;     // key tiles are dealt round-robin to this many warp groups
+    constexpr int kParkWarp = kParkBytes / NEPI;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                  // 64 KB
-    uint8_t* sK = smem + kTileBytes;                     // kStages x 64 KB
-    float* stage_buf = reinterpret_cast<float*>(sK + kStages * kTileBytes);   // 8 warps x [32][32] floats (32 KB)
+    uint8_t* sK = smem + kQBytes;                        // kStages x 32 KB
+    uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
 
-    if (warp == 9) tc::tmem_alloc<512>(&tmem_base_s);
+    if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_base_s);
     if (tid == 0) {
         tc::mbar_init(&q_full, 1);
         tc::mbar_init(&q_empty, 1);
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
-        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], kEpiWarps); }
+        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 8); }
         tc::fence_barrier_init();
     }
-    if (warp == 8 && lane == 0) { tc::prefetch_tmap(&map_hi); tc::prefetch_tmap(&map_lo); }
+    if (warp == kProducerWarp && lane == 0) {
+        tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 8) {
+    if (warp == kProducerWarp) {
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t kcnt = 0, tcnt = 0;
@@ -167,26 +174,26 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 if (t.n_ktiles == 0) continue;
                 const int grow = t.rg * p.T * N;   // first global row of this radargram
                 tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&q_full, kTileBytes);
+                tc::mbar_arrive_expect_tx(&q_full, kQBytes);
                 for (int part = 0; part < 2; ++part)
                     for (int kb = 0; kb < 2; ++kb)
-                        tc::tma_load_2d(sQ + (part * 2 + kb) * (kBM * 128), part ? &map_lo : &map_hi, kb * 64, grow + t.r0, &q_full);
+                        tc::tma_load_2d(sQ + (part * 2 + kb) * (kBM * 128), part ? &qmap_lo : &qmap_hi, kb * 64, grow + t.r0, &q_full);
                 for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
                     const int s = kcnt % kStages;
                     int row0, nrows;
                     ktile_rows(p, t, kt, row0, nrows);
                     tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
-                    tc::mbar_arrive_expect_tx(&k_full[s], kTileBytes);
-                    uint8_t* dst = sK + s * kTileBytes;
+                    tc::mbar_arrive_expect_tx(&k_full[s], kKBytes);
+                    uint8_t* dst = sK + s * kKBytes;
                     for (int part = 0; part < 2; ++part)
                         for (int kb = 0; kb < 2; ++kb)
-                            tc::tma_load_2d(dst + (part * 2 + kb) * (kBN * 128), part ? &map_lo : &map_hi, kb * 64, grow + row0,
+                            tc::tma_load_2d(dst + (part * 2 + kb) * (kBN * 128), part ? &kmap_lo : &kmap_hi, kb * 64, grow + row0,
                                             &k_full[s]);
                 }
                 ++tcnt;
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t kcnt = 0, tcnt = 0;
@@ -203,7 +210,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
                     tc::tc_fence_after();
                     const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
-                    const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK + s * kTileBytes);
+                    const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK + s * kKBytes);
                     const uint32_t d = tmem_base + (uint32_t)(a * kBN);
                     uint32_t acc = 0;
                     // pass 0: q_hi.k_hi   pass 1: q_hi.k_lo   pass 2: q_lo.k_hi
@@ -228,16 +235,16 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             }
         }
     } else {
-        // ================= epilogue: 8 warps, thread = query row, warp/4 = column half =================
-        // Per 32-column block: (1) tcgen05.ld the thread's row, (2) park it in a thread-private smem column
-        // ([i][lane]: bank = lane, conflict-free) so that candidates can be fetched by dynamic index,
-        // (3) build a "beats the current k-th best" bitmask (2 instr / element) and a validity bitmask
-        // (frame window x radius band, a few bit ops per block), (4) run ONE rolled insertion loop over the
-        // set bits.  Keeping the insertion code in a single place keeps the hot loop inside the I-cache.
-        const int g = warp & 3, half = warp >> 2;
+        // ================= epilogue: NEPI warps; thread = query row (TMEM lane) =================
+        // warp = 4*part + lane-group.  part&1 selects the 32-column half of a key tile, part>>1 which key tiles
+        // (round-robin) this warp looks at.  Per block: (1) tcgen05.ld the thread's 32 columns, (2) park them in a
+        // thread-private smem column ([i][lane]: bank = lane, conflict-free) so candidates can be fetched by dynamic
+        // index, (3) "beats the current k-th best" bitmask & validity bitmask (frame window x radius band),
+        // (4) ONE rolled insertion loop over the set bits (keeps the hot loop inside the I-cache).
+        const int g = warp & 3, part = warp >> 2, half = part & 1, tgroup = part >> 1;
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
-        const uint32_t park = tc::smem_u32(stage_buf + warp * 1024) + lane * 4;   // [32][32] floats, private to this warp
+        const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
         uint32_t kcnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
@@ -246,20 +253,19 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const int n = row / N, q = row - n * N;
             const bool qvalid = (n >= 1) && (n < p.T);
             const int win_lo = (n > ctx + 1) ? n - ctx : 1;     // non-zero key frames allowed: [win_lo, n)
-            TopList<KT> top;
+            TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                if (kTileGroups > 1 && (kt % kTileGroups) != tgroup) continue;
                 const int a = kcnt % kAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
                 tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
                 tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + half * 64);
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int c0 = half * 64 + ch * 32;
-                    if (c0 >= nrows) break;                       // warp-uniform
+                const int c0 = half * 32;
+                if (c0 < nrows) {                                 // warp-uniform
                     float v[32];
-                    tc::tmem_ld_32x32b_x32(taddr + ch * 32, v);
+                    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + c0), v);
                     tc::tmem_ld_wait();
                     const float thr = top.v[KT - 1];
                     uint32_t pm = 0;
@@ -292,34 +298,41 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         const int i = __ffs(cand) - 1;
                         cand &= cand - 1;
                         const float x = tc::lds_f32(park + i * 128);
-                        if (x > top.v[KT - 1]) {
-                            const int kr = kr0 + i;
-                            const int kf = (int)__umulhi((unsigned)kr, p.magic_n);
-                            const int j = kr - kf * N;
-                            const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
-                            top.insert(x, slot * N + j);
-                        }
+                        if (x > top.v[KT - 1]) top.insert(x, kr0 + i);
                     }
                 }
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
             }
-            // ---- merge the two column halves (warps 4-7 -> smem -> warps 0-3) ----
-            float* mv = stage_buf + (4 + g) * 1024;                       // values: half-1 warp's own buffer
-            int* mi = reinterpret_cast<int*>(stage_buf + g * 1024);       // ids: the partner (half-0) warp's buffer
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue warp is done with its park buffer
-            if (half == 1) {
+            // ---- merge the kParts lists of every query (warps part>0 -> smem -> warp part 0) ----
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");   // every epilogue warp is done with its park buffer
+            float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
+            int* mi = reinterpret_cast<int*>(mv + KT * 32);
+            static_assert(KT * 32 * 8 <= kParkWarp, "merge scratch must fit the warp's park buffer");
+            if (part != 0) {
 #pragma unroll
                 for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (half == 0) {
-                for (int s = 0; s < KT; ++s) {
-                    const float x = mv[s * 32 + lane];
-                    if (x > -INFINITY) top.insert_tie(x, mi[s * 32 + lane]);
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (part == 0) {
+                for (int pp = 1; pp < kParts; ++pp) {
+                    const float* pv = reinterpret_cast<const float*>(park_base + (pp * 4 + g) * kParkWarp);
+                    const int* pi = reinterpret_cast<const int*>(pv + KT * 32);
+                    for (int s = 0; s < KT; ++s) {
+                        const float x = pv[s * 32 + lane];
+                        if (x > -INFINITY) top.insert_tie(x, pi[s * 32 + lane]);
+                    }
                 }
                 if (qvalid) {
+                    // key row -> candidate id (slot in the trimmed key set * N + node)
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) {
+                        const int kr = top.id[s];
+                        const int kf = (int)__umulhi((unsigned)kr, p.magic_n), j = kr - kf * N;
+                        const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
+                        top.id[s] = slot * N + j;
+                    }
                     // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
                     const int F = n_key_frames(n, ctx);
                     int live = 0;
@@ -355,23 +368,23 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         }
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // scratch free for the next tile
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");   // scratch free for the next tile
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc<512>(tmem_base);
+    if (warp == kMmaWarp) tc::tmem_dealloc<512>(tmem_base);
 }
 
-template <int KT>
-static int launch_tc(const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& p, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)(1 + kStages) * kTileBytes + (size_t)kEpiWarps * 4096;
-    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int KT, int NEPI>
+static int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
+    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-    lp_topk_tc_kernel<KT><<<grid, kTcThreads, smem, st>>>(mh, ml, p);
+    lp_topk_tc_kernel<KT, NEPI><<<grid, (NEPI + 2) * 32, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -387,10 +400,11 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
     CRW_LAUNCH_RET();
     if (T < 2) return CRW_OK;
-    CUtensorMap mh, ml;
-    int rc = make_tmap_bf16_k64(&mh, hi, (uint64_t)rows, 128, kBM);
-    if (rc != CRW_OK) return rc;
-    rc = make_tmap_bf16_k64(&ml, lo, (uint64_t)rows, 128, kBM);
+    CUtensorMap maps[4];
+    int rc = make_tmap_bf16_k64(&maps[0], hi, (uint64_t)rows, 128, kBM);
+    if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[1], lo, (uint64_t)rows, 128, kBM);
+    if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[2], hi, (uint64_t)rows, 128, kBN);
+    if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[3], lo, (uint64_t)rows, 128, kBN);
     if (rc != CRW_OK) return rc;
     TcParams p;
     p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
@@ -401,10 +415,10 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     p.tiles_per_rg = ceil_div(T * N, kBM);
     p.total_tiles = R * p.tiles_per_rg;
-    if (k <= 10) return launch_tc<10>(mh, ml, p, st);
-    if (k <= 16) return launch_tc<16>(mh, ml, p, st);
-    if (k <= 20) return launch_tc<20>(mh, ml, p, st);
-    return launch_tc<32>(mh, ml, p, st);
+    if (k <= 10) return launch_tc<10, 8>(maps, p, st);
+    if (k <= 16) return launch_tc<16, 8>(maps, p, st);
+    if (k <= 20) return launch_tc<20, 8>(maps, p, st);
+    return launch_tc<32, 8>(maps, p, st);
 }
 
 }  // namespace crw
