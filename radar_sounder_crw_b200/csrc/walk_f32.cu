@@ -14,6 +14,7 @@
 // All N x N state lives in the `saved` workspace (L2-resident at the reference's sizes); every
 // stage is built from one CTA-wide tiled fp32 GEMM (64x64 tile, 4x4 per thread).
 #include "common.cuh"
+#include "walk_layout.cuh"
 
 namespace crw {
 
@@ -87,26 +88,6 @@ __device__ __forceinline__ void cta_gemm(const float* A, int lda, const float* B
         }
     __syncthreads();
 }
-
-// layout of the `saved` workspace (floats)
-struct WalkLayout {
-    size_t invn, A, S, Sp, L, R, G, part, total;
-    int B, T, N, C;
-    __host__ __device__ WalkLayout(int B_, int T_, int N_, int C_) : B(B_), T(T_), N(N_), C(C_) {
-        const size_t nn = (size_t)N * N, bt1 = (size_t)B * (T - 1);
-        size_t o = 0;
-        invn = o; o += align_up((size_t)B * T * N, 64);
-        A = o;    o += align_up(bt1 * nn, 64);
-        S = o;    o += align_up(bt1 * nn, 64);
-        Sp = o;   o += align_up(bt1 * nn, 64);
-        L = o;    o += align_up(bt1 * nn, 64);   // L_k, k = 0..T-2
-        R = o;    o += align_up(bt1 * nn, 64);   // R_k, k = 0..T-2 (k = 0 unused)
-        G = o;    o += align_up(bt1 * nn, 64);   // G_k = rowsoftmax(M_k) - I, k = 1..T-2
-        part = o; o += align_up(bt1, 64);        // loss partials [B][T-1]
-        total = o;
-    }
-    __host__ __device__ size_t mat(size_t base, int b, int t) const { return base + ((size_t)b * (T - 1) + t) * N * N; }
-};
 
 // ------------------------------------------------------------------------------------------
 // forward stage 1: grid (T-1, B).  inverse norms, A_t, S_t = rowsoftmax(A_t), S'_t = rowsoftmax(A_t^T)
@@ -244,17 +225,6 @@ __global__ void walk_loss_reduce_kernel(const float* ws, float* loss, int B, int
 
 __global__ void walk_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 
-// ------------------------------------------------------------------------------------------
-// backward scratch layout (floats): dL, dR [B][T-1][N][N] (index k), dS, dSp [B][T-1][N][N] (index t)
-// ------------------------------------------------------------------------------------------
-struct BwdLayout {
-    size_t dL, dR, dS, dSp, dAw, total;
-    __host__ __device__ BwdLayout(int B, int T, int N) {
-        const size_t m = align_up((size_t)B * (T - 1) * N * N, 64);
-        dL = 0; dR = m; dS = 2 * m; dSp = 3 * m; dAw = 4 * m; total = 5 * m;
-    }
-};
-
 // bwd stage 1: grid (T-2, B, 2).  z=0: dL_k = s * G_k R_k^T ;  z=1: dR_k = s * L_k^T G_k
 __global__ void __launch_bounds__(kWT) walk_bwd_own_kernel(const float* ws, float* sc, const float* dloss, int B, int T,
                                                            int N, int C) {
@@ -391,7 +361,17 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restric
 
 }  // namespace crw
 
+namespace crw {
+bool walk_small_supported(int N, int C);
+int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
+                       cudaStream_t st);
+int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
+                        float tau, float* dx, float* sc, cudaStream_t st);
+}  // namespace crw
+
 using namespace crw;
+
+static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C) {
     if (B < 1 || T < 2 || N < 1 || C < 1) return 0;
@@ -416,6 +396,7 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = align256(saved);
     const float inv_tau = 1.0f / tau;
+    if (walk_small_supported(N, C) && aligned16p(x)) return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
     walk_affinity_kernel<<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     if (T < 3) {   // model.py:33-35: empty loop, loss = 0
@@ -443,6 +424,8 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     const float* ws = align256(const_cast<void*>(saved));
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
+    if (walk_small_supported(N, C) && aligned16p(x))
+        return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
     if (T >= 3) {
         walk_bwd_own_kernel<<<dim3(T - 2, B, 2), kWT, 0, st>>>(ws, sc, dloss, B, T, N, C);
         CRW_LAUNCH_RET();

@@ -1,0 +1,560 @@
+// walk_small.cu -- shared-memory-resident fp32 walk kernels for the reference's own sizes (N <= 64, C <= 128).
+//
+// Same algorithm, workspace layout and reference mapping as walk_f32.cu (src/model.py:22-46 and its autograd);
+// the difference is where the operands live.  At N = 47..49 every stage is latency bound, so each CTA pulls its
+// operands into shared memory ONCE with cp.async (zero-padded to 64 x 64), runs the GEMM from shared memory with
+// no barrier inside the k-loop, keeps intermediates (A_t, M_k, the running chain product) on chip, and the two
+// sequential chains prefetch the next step's operand while the current product is being formed.
+#include "common.cuh"
+#include "walk_layout.cuh"
+
+namespace crw {
+
+constexpr int kST = 256;      // threads per CTA (16 x 16 grid of 4x4 register blocks = one 64 x 64 tile)
+constexpr int kLD = 68;       // row pitch of a 64 x 64 matrix in smem (floats)
+constexpr int kLDX = 132;     // row pitch of a 64 x 128 feature tile in smem
+constexpr int kMat = 64 * kLD;
+constexpr int kMatX = 64 * kLDX;
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void zero_fill(float* p, int n) {
+    for (int i = threadIdx.x; i < n; i += kST) p[i] = 0.0f;
+}
+// N x N matrix (global, dense) -> smem pitch kLD.  Rows are not 16-byte aligned for odd N: 4-byte cp.async.
+__device__ __forceinline__ void load_nn(float* dst, const float* src, int N) {
+    for (int i = threadIdx.x; i < N * N; i += kST) {
+        const int r = i / N, c = i - r * N;
+        cp_async4(dst + r * kLD + c, src + i);
+    }
+}
+// N x C feature tile (global rows are 16-byte aligned since C % 4 == 0) -> smem pitch kLDX
+__device__ __forceinline__ void load_nc(float* dst, const float* src, int N, int C) {
+    const int c4 = C >> 2;
+    for (int i = threadIdx.x; i < N * c4; i += kST) {
+        const int r = i / c4, c = (i - r * c4) * 4;
+        cp_async16(dst + r * kLDX + c, src + (size_t)r * C + c);
+    }
+}
+
+// acc[i][j] += sum_k opA[row(i)][k] * opB[k][col(j)], all operands in smem, K4 = K rounded up to 4 (padding is zero).
+//   !TA: A[m*lda + k], rows owned: ty + 16 i      TA: A[k*lda + m], rows owned: 4 ty + i
+//   !TB: B[k*ldb + n], cols owned: 4 tx + j        TB: B[n*ldb + k], cols owned: tx + 16 j
+template <bool TA> __device__ __forceinline__ int own_row(int i) { return TA ? (threadIdx.x >> 4) * 4 + i : (threadIdx.x >> 4) + 16 * i; }
+template <bool TB> __device__ __forceinline__ int own_col(int j) { return TB ? (threadIdx.x & 15) + 16 * j : (threadIdx.x & 15) * 4 + j; }
+
+template <bool TA, bool TB>
+__device__ __forceinline__ void sgemm_tile(const float* A, int lda, const float* B, int ldb, int K4, int n0, float (&acc)[4][4]) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll 2
+    for (int k = 0; k < K4; k += 4) {
+        float a[4][4], b[4][4];   // a[i][kk], b[kk][j]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!TA) {
+                const float4 v = *reinterpret_cast<const float4*>(A + (ty + 16 * u) * lda + k);
+                a[u][0] = v.x; a[u][1] = v.y; a[u][2] = v.z; a[u][3] = v.w;
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(A + (k + u) * lda + ty * 4);
+                a[0][u] = v.x; a[1][u] = v.y; a[2][u] = v.z; a[3][u] = v.w;
+            }
+            if (!TB) {
+                const float4 v = *reinterpret_cast<const float4*>(B + (k + u) * ldb + n0 + tx * 4);
+                b[u][0] = v.x; b[u][1] = v.y; b[u][2] = v.z; b[u][3] = v.w;
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(B + (n0 + tx + 16 * u) * ldb + k);
+                b[0][u] = v.x; b[1][u] = v.y; b[2][u] = v.z; b[3][u] = v.w;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[kk][j], acc[i][j]);
+    }
+}
+__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward 1: grid (T-1, B).  A_t = E_t E_{t+1}^T / tau, S_t, S'_t   (model.py:22,26 + the softmaxes of :44)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __restrict__ x, float* ws, float* A_out, int B, int T,
+                                                             int N, int C, float inv_tau) {
+    extern __shared__ __align__(16) float sm[];
+    float* X0 = sm;
+    float* X1 = X0 + kMatX;
+    float* At = X1 + kMatX;
+    float* inv0 = At + kMat;
+    float* inv1 = inv0 + 64;
+    const WalkLayout lay(B, T, N, C);
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* x0 = x + ((size_t)b * T + t) * N * C;
+    load_nc(X0, x0, N, C);
+    load_nc(X1, x0 + (size_t)N * C, N, C);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int r = warp; r < 2 * N; r += kST / 32) {
+        const float* xr = (r < N) ? X0 + r * kLDX : X1 + (r - N) * kLDX;
+        float ss = 0.0f;
+        for (int c = lane; c < C; c += 32) ss = fmaf(xr[c], xr[c], ss);
+        ss = warp_sum(ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+        if (lane == 0) {
+            inv0[r < N ? r : 64 + (r - N)] = inv;
+            if (r < N) ws[lay.invn + ((size_t)b * T + t) * N + r] = inv;
+            else if (t == T - 2) ws[lay.invn + ((size_t)b * T + t + 1) * N + (r - N)] = inv;
+        }
+    }
+    __syncthreads();
+    float acc[4][4];
+    zero_acc(acc);
+    sgemm_tile<false, true>(X0, kLDX, X1, kLDX, C, 0, acc);
+    float* Ao = A_out ? A_out + ((size_t)b * (T - 1) + t) * N * N : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = own_row<false>(i), n = own_col<true>(j);
+            if (m < N && n < N) {
+                const float a = acc[i][j] * inv0[m] * inv1[n] * inv_tau;
+                At[m * kLD + n] = a;
+                if (Ao) Ao[(size_t)m * N + n] = a;
+            }
+        }
+    __syncthreads();
+    float* S = ws + lay.mat(lay.S, b, t);
+    float* Sp = ws + lay.mat(lay.Sp, b, t);
+    for (int r = warp; r < 2 * N; r += kST / 32) {
+        const bool col = r >= N;
+        const int i = col ? r - N : r;
+        const int step = col ? kLD : 1, base = col ? i : i * kLD;
+        float mx = -INFINITY;
+        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, At[base + j * step]);
+        mx = warp_max(mx);
+        float se = 0.0f;
+        for (int j = lane; j < N; j += 32) se += __expf(At[base + j * step] - mx);
+        se = warp_sum(se);
+        const float inv = 1.0f / se;
+        float* dst = (col ? Sp : S) + (size_t)i * N;
+        for (int j = lane; j < N; j += 32) dst[j] = __expf(At[base + j * step] - mx) * inv;
+    }
+}
+
+// store the thread's 4x4 block of a 64 x 64 result into smem (pitch kLD) and/or a dense N x N global matrix
+template <bool TA, bool TB, class F>
+__device__ __forceinline__ void for_each_out(const float (&acc)[4][4], int N, F f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = own_row<TA>(i), n = own_col<TB>(j);
+            if (m < N && n < N) f(m, n, acc[i][j]);
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward 2: grid (2, B).  x = 0: L_k = L_{k-1} S'_{k-1};  x = 1: R_k = S_{k-1} R_{k-1}   (sequential in k)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_chain_kernel(float* ws, int B, int T, int N, int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;                 // running product
+    float* Op = P + kMat;          // [2] next operand
+    const WalkLayout lay(B, T, N, C);
+    const int b = blockIdx.y, K = T - 2, N4 = (N + 3) & ~3;
+    const bool isL = blockIdx.x == 0;
+    const size_t chain = isL ? lay.L : lay.R, opnd = isL ? lay.Sp : lay.S;
+    const int k_first = isL ? 1 : 2;
+    zero_fill(sm, 3 * kMat);
+    __syncthreads();
+    if (k_first <= K) load_nn(Op, ws + lay.mat(opnd, b, k_first - 1), N);
+    float* first = ws + lay.mat(chain, b, k_first - 1);    // L_0 = I, R_1 = I
+    for (int i = threadIdx.x; i < N * N; i += kST) {
+        const int r = i / N, c = i - r * N;
+        const float v = (r == c) ? 1.0f : 0.0f;
+        P[r * kLD + c] = v;
+        first[i] = v;
+    }
+    for (int k = k_first; k <= K; ++k) {
+        const float* cur = Op + ((k - k_first) & 1) * kMat;
+        cp_async_wait_all();
+        __syncthreads();
+        if (k + 1 <= K) load_nn(Op + ((k + 1 - k_first) & 1) * kMat, ws + lay.mat(opnd, b, k), N);
+        float acc[4][4];
+        zero_acc(acc);
+        if (isL) sgemm_tile<false, false>(P, kLD, cur, kLD, N4, 0, acc);
+        else sgemm_tile<false, false>(cur, kLD, P, kLD, N4, 0, acc);
+        __syncthreads();
+        float* out = ws + lay.mat(chain, b, k);
+        for_each_out<false, false>(acc, N, [&](int m, int n, float v) { P[m * kLD + n] = v; out[(size_t)m * N + n] = v; });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward 3: grid (T-2, B).  M_k = L_k R_k; loss partial; G_k = rowsoftmax(M_k) - I   (model.py:45)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_cycle_kernel(float* ws, int B, int T, int N, int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* Lk = sm;
+    float* Rk = Lk + kMat;
+    float* M = Rk + kMat;
+    __shared__ float red[kST / 32];
+    const WalkLayout lay(B, T, N, C);
+    const int k = blockIdx.x + 1, b = blockIdx.y, N4 = (N + 3) & ~3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    zero_fill(sm, 2 * kMat);
+    __syncthreads();
+    load_nn(Lk, ws + lay.mat(lay.L, b, k), N);
+    load_nn(Rk, ws + lay.mat(lay.R, b, k), N);
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[4][4];
+    zero_acc(acc);
+    sgemm_tile<false, false>(Lk, kLD, Rk, kLD, N4, 0, acc);
+    for_each_out<false, false>(acc, N, [&](int m, int n, float v) { M[m * kLD + n] = v; });
+    __syncthreads();
+    float* Gk = ws + lay.mat(lay.G, b, k);
+    float part = 0.0f;
+    for (int d = warp; d < N; d += kST / 32) {
+        const float* row = M + d * kLD;
+        float mx = -INFINITY;
+        for (int c = lane; c < N; c += 32) mx = fmaxf(mx, row[c]);
+        mx = warp_max(mx);
+        float se = 0.0f;
+        for (int c = lane; c < N; c += 32) se += __expf(row[c] - mx);
+        se = warp_sum(se);
+        const float inv = 1.0f / se;
+        for (int c = lane; c < N; c += 32) Gk[(size_t)d * N + c] = __expf(row[c] - mx) * inv - (c == d ? 1.0f : 0.0f);
+        part += (logf(se) + mx) - row[d];
+    }
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < kST / 32; ++w) s += red[w];
+        ws[lay.part + (size_t)b * (T - 1) + k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward 1: grid (T-2, B, 2).  z = 0: dL_k = s G_k R_k^T;  z = 1: dR_k = s L_k^T G_k
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_bwd_own_kernel(const float* ws, float* sc, const float* dloss, int B, int T, int N,
+                                                            int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* G = sm;
+    float* O = G + kMat;
+    const WalkLayout lay(B, T, N, C);
+    const BwdLayout bl(B, T, N);
+    const int k = blockIdx.x + 1, b = blockIdx.y, N4 = (N + 3) & ~3;
+    const float s = *dloss / ((float)B * (float)N * (float)N);
+    zero_fill(sm, 2 * kMat);
+    __syncthreads();
+    load_nn(G, ws + lay.mat(lay.G, b, k), N);
+    load_nn(O, ws + lay.mat(blockIdx.z == 0 ? lay.R : lay.L, b, k), N);
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[4][4];
+    zero_acc(acc);
+    if (blockIdx.z == 0) {
+        sgemm_tile<false, true>(G, kLD, O, kLD, N4, 0, acc);
+        float* o = sc + lay.mat(bl.dL, b, k);
+        for_each_out<false, true>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
+    } else {
+        sgemm_tile<true, false>(O, kLD, G, kLD, N4, 0, acc);
+        float* o = sc + lay.mat(bl.dR, b, k);
+        for_each_out<true, false>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward 2: grid (2, B).  x = 0: dL_j += dL_{j+1} S'_j^T (j = K-1..1);  x = 1: dR_j += S_j^T dR_{j+1} (j = K-1..2)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_bwd_chain_kernel(const float* ws, float* sc, int B, int T, int N, int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* P = sm;                  // running adjoint dL_{j+1} / dR_{j+1}
+    float* Op = P + kMat;           // [2] S'_j or S_j
+    float* Own = Op + 2 * kMat;     // [2] own term of step j
+    const WalkLayout lay(B, T, N, C);
+    const BwdLayout bl(B, T, N);
+    const int b = blockIdx.y, K = T - 2, N4 = (N + 3) & ~3;
+    const bool isL = blockIdx.x == 0;
+    const size_t adj = isL ? bl.dL : bl.dR, opnd = isL ? lay.Sp : lay.S;
+    const int j_last = isL ? 1 : 2;
+    zero_fill(sm, 5 * kMat);
+    __syncthreads();
+    load_nn(P, sc + lay.mat(adj, b, K), N);
+    if (K - 1 >= j_last) {
+        load_nn(Op, ws + lay.mat(opnd, b, K - 1), N);
+        load_nn(Own, sc + lay.mat(adj, b, K - 1), N);
+    }
+    for (int j = K - 1, it = 0; j >= j_last; --j, ++it) {
+        const float* cur = Op + (it & 1) * kMat;
+        const float* own = Own + (it & 1) * kMat;
+        cp_async_wait_all();
+        __syncthreads();
+        if (j - 1 >= j_last) {
+            load_nn(Op + ((it + 1) & 1) * kMat, ws + lay.mat(opnd, b, j - 1), N);
+            load_nn(Own + ((it + 1) & 1) * kMat, sc + lay.mat(adj, b, j - 1), N);
+        }
+        float acc[4][4];
+        zero_acc(acc);
+        float* out = sc + lay.mat(adj, b, j);
+        if (isL) {
+            sgemm_tile<false, true>(P, kLD, cur, kLD, N4, 0, acc);
+            __syncthreads();
+            for_each_out<false, true>(acc, N, [&](int m, int n, float v) {
+                const float r = v + own[m * kLD + n];
+                P[m * kLD + n] = r;
+                out[(size_t)m * N + n] = r;
+            });
+        } else {
+            sgemm_tile<true, false>(cur, kLD, P, kLD, N4, 0, acc);
+            __syncthreads();
+            for_each_out<true, false>(acc, N, [&](int m, int n, float v) {
+                const float r = v + own[m * kLD + n];
+                P[m * kLD + n] = r;
+                out[(size_t)m * N + n] = r;
+            });
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward 3: grid (T-1, B).  dS'_t = L_t^T dL_{t+1};  dS_t = dR_{t+1} R_t^T;  softmax backward;  dA_t
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, float* sc, const float* dA_ext, int B, int T, int N,
+                                                           int C) {
+    extern __shared__ __align__(16) float sm[];
+    float* Lt = sm;
+    float* dLn = Lt + kMat;
+    float* Rt = dLn + kMat;
+    float* dRn = Rt + kMat;
+    float* Ss = dRn + kMat;
+    float* Sps = Ss + kMat;
+    float* dSs = Sps + kMat;
+    float* dSps = dSs + kMat;
+    float* rS = dSps + kMat;
+    float* rSp = rS + 64;
+    const WalkLayout lay(B, T, N, C);
+    const BwdLayout bl(B, T, N);
+    const int t = blockIdx.x, b = blockIdx.y, K = T - 2, N4 = (N + 3) & ~3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool hasSp = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
+    float* dA = sc + lay.mat(bl.dAw, b, t);
+    const float* ext = dA_ext ? dA_ext + ((size_t)b * (T - 1) + t) * N * N : nullptr;
+    if (!hasSp && !hasS) {
+        for (int e = threadIdx.x; e < N * N; e += kST) dA[e] = ext ? ext[e] : 0.0f;
+        return;
+    }
+    zero_fill(sm, 8 * kMat);
+    __syncthreads();
+    if (hasSp) {
+        load_nn(Lt, ws + lay.mat(lay.L, b, t), N);
+        load_nn(dLn, sc + lay.mat(bl.dL, b, t + 1), N);
+        load_nn(Sps, ws + lay.mat(lay.Sp, b, t), N);
+    }
+    if (hasS) {
+        load_nn(Rt, ws + lay.mat(lay.R, b, t), N);
+        load_nn(dRn, sc + lay.mat(bl.dR, b, t + 1), N);
+        load_nn(Ss, ws + lay.mat(lay.S, b, t), N);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float acc[4][4];
+    if (hasSp) {
+        zero_acc(acc);
+        sgemm_tile<true, false>(Lt, kLD, dLn, kLD, N4, 0, acc);
+        for_each_out<true, false>(acc, N, [&](int m, int n, float v) { dSps[m * kLD + n] = v; });
+    }
+    if (hasS) {
+        zero_acc(acc);
+        sgemm_tile<false, true>(dRn, kLD, Rt, kLD, N4, 0, acc);
+        for_each_out<false, true>(acc, N, [&](int m, int n, float v) { dSs[m * kLD + n] = v; });
+    }
+    __syncthreads();
+    for (int r = warp; r < 2 * N; r += kST / 32) {
+        const bool second = r >= N;
+        const int i = second ? r - N : r;
+        const float* P = (second ? Sps : Ss) + i * kLD;
+        const float* dP = (second ? dSps : dSs) + i * kLD;
+        float a = 0.0f;
+        for (int j = lane; j < N; j += 32) a = fmaf(P[j], dP[j], a);   // zero when the term is absent (buffers zero-filled)
+        a = warp_sum(a);
+        if (lane == 0) (second ? rSp : rS)[i] = a;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += kST) {
+        const int i = e / N, j = e - i * N;
+        float g = ext ? ext[e] : 0.0f;
+        g += Ss[i * kLD + j] * (dSs[i * kLD + j] - rS[i]);
+        g += Sps[j * kLD + i] * (dSps[j * kLD + i] - rSp[j]);
+        dA[e] = g;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward 4: grid (T, B).  dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau, then the normalise backward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restrict__ x, const float* ws, const float* sc, float* dx,
+                                                           int B, int T, int N, int C, float inv_tau) {
+    extern __shared__ __align__(16) float sm[];
+    float* dAt = sm;
+    float* dAp = dAt + kMat;
+    float* En = dAp + kMat;
+    float* Ep = En + kMatX;
+    float* Out = Ep + kMatX;
+    const WalkLayout lay(B, T, N, C);
+    const BwdLayout bl(B, T, N);
+    const int t = blockIdx.x, b = blockIdx.y, N4 = (N + 3) & ~3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* invn = ws + lay.invn + (size_t)b * T * N;
+    const bool hasN = t <= T - 2, hasP = t >= 1;
+    zero_fill(sm, 2 * kMat + 2 * kMatX);
+    __syncthreads();
+    if (hasN) {
+        load_nn(dAt, sc + lay.mat(bl.dAw, b, t), N);
+        load_nc(En, x + ((size_t)b * T + t + 1) * N * C, N, C);
+    }
+    if (hasP) {
+        load_nn(dAp, sc + lay.mat(bl.dAw, b, t - 1), N);
+        load_nc(Ep, x + ((size_t)b * T + t - 1) * N * C, N, C);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // E = x * invn (rows)
+    for (int i = threadIdx.x; i < N * C; i += kST) {
+        const int r = i / C, c = i - r * C;
+        if (hasN) En[r * kLDX + c] *= invn[(size_t)(t + 1) * N + r];
+        if (hasP) Ep[r * kLDX + c] *= invn[(size_t)(t - 1) * N + r];
+    }
+    __syncthreads();
+    for (int n0 = 0; n0 < C; n0 += 64) {
+        float acc[4][4];
+        zero_acc(acc);
+        if (hasN) sgemm_tile<false, false>(dAt, kLD, En, kLDX, N4, n0, acc);
+        float acc2[4][4];
+        zero_acc(acc2);
+        if (hasP) sgemm_tile<true, false>(dAp, kLD, Ep, kLDX, N4, n0, acc2);
+        // the two products own different rows per thread (row mapping depends on TA): go through smem
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = own_row<false>(i), n = n0 + own_col<false>(j);
+                if (m < N && n < C) Out[m * kLDX + n] = acc[i][j] * inv_tau;
+            }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = own_row<true>(i), n = n0 + own_col<false>(j);
+                if (m < N && n < C) Out[m * kLDX + n] += acc2[i][j] * inv_tau;
+            }
+        __syncthreads();
+    }
+    const float* xt = x + ((size_t)b * T + t) * N * C;
+    float* o = dx + ((size_t)b * T + t) * N * C;
+    for (int i = warp; i < N; i += kST / 32) {
+        const float inv = invn[(size_t)t * N + i];
+        const float* dr = Out + i * kLDX;
+        const float* xr = xt + (size_t)i * C;
+        float* orow = o + (size_t)i * C;
+        if (inv >= 1.0f / kNormEps) {   // ||x|| <= eps: F.normalize divides by the constant eps
+            for (int c = lane; c < C; c += 32) orow[c] = dr[c] * inv;
+            continue;
+        }
+        float dot = 0.0f;
+        for (int c = lane; c < C; c += 32) dot = fmaf(xr[c] * inv, dr[c], dot);
+        dot = warp_sum(dot);
+        for (int c = lane; c < C; c += 32) orow[c] = (dr[c] - xr[c] * inv * dot) * inv;
+    }
+}
+
+__global__ void walk_s_loss_reduce_kernel(const float* ws, float* loss, int B, int T, int N, int C) {
+    const WalkLayout lay(B, T, N, C);
+    const int lane = threadIdx.x;
+    float s = 0.0f;
+    for (int i = lane; i < B * (T - 2); i += 32) {
+        const int b = i / (T - 2), k = i % (T - 2) + 1;
+        s += ws[lay.part + (size_t)b * (T - 1) + k];
+    }
+    s = warp_sum(s);
+    if (lane == 0) *loss = s / ((float)B * (float)N) / (float)N;
+}
+__global__ void walk_s_zero_loss_kernel(float* loss) { *loss = 0.0f; }
+
+// opt in to > 48 KB dynamic shared memory (idempotent; cheap enough to repeat per launch, never inside the kernels)
+template <class Kern>
+static int set_smem(Kern kern, size_t bytes) {
+    CRW_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return CRW_OK;
+}
+
+bool walk_small_supported(int N, int C) { return N <= 64 && C <= 128 && (C % 4) == 0; }
+
+int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
+                       cudaStream_t st) {
+    const float inv_tau = 1.0f / tau;
+    const size_t sm1 = (2 * kMatX + kMat + 128) * sizeof(float), sm2 = 3 * kMat * sizeof(float);
+    int rc = set_smem(walk_s_affinity_kernel, sm1);
+    if (rc) return rc;
+    walk_s_affinity_kernel<<<dim3(T - 1, B), kST, sm1, st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
+    CRW_LAUNCH_RET();
+    if (T < 3) {
+        walk_s_zero_loss_kernel<<<1, 1, 0, st>>>(loss);
+        CRW_LAUNCH_RET();
+        return CRW_OK;
+    }
+    if ((rc = set_smem(walk_s_chain_kernel, sm2))) return rc;
+    walk_s_chain_kernel<<<dim3(2, B), kST, sm2, st>>>(ws, B, T, N, C);
+    CRW_LAUNCH_RET();
+    if ((rc = set_smem(walk_s_cycle_kernel, sm2))) return rc;
+    walk_s_cycle_kernel<<<dim3(T - 2, B), kST, sm2, st>>>(ws, B, T, N, C);
+    CRW_LAUNCH_RET();
+    walk_s_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, B, T, N, C);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
+                        float tau, float* dx, float* sc, cudaStream_t st) {
+    const float inv_tau = 1.0f / tau;
+    int rc;
+    if (T >= 3) {
+        const size_t sm = 2 * kMat * sizeof(float);
+        if ((rc = set_smem(walk_s_bwd_own_kernel, sm))) return rc;
+        walk_s_bwd_own_kernel<<<dim3(T - 2, B, 2), kST, sm, st>>>(ws, sc, dloss, B, T, N, C);
+        CRW_LAUNCH_RET();
+        if (T >= 4) {
+            const size_t smc = 5 * kMat * sizeof(float);
+            if ((rc = set_smem(walk_s_bwd_chain_kernel, smc))) return rc;
+            walk_s_bwd_chain_kernel<<<dim3(2, B), kST, smc, st>>>(ws, sc, B, T, N, C);
+            CRW_LAUNCH_RET();
+        }
+    }
+    const size_t smA = (8 * kMat + 128) * sizeof(float);
+    if ((rc = set_smem(walk_s_bwd_dA_kernel, smA))) return rc;
+    walk_s_bwd_dA_kernel<<<dim3(T - 1, B), kST, smA, st>>>(ws, sc, dA_or_null, B, T, N, C);
+    CRW_LAUNCH_RET();
+    const size_t smX = (2 * kMat + 3 * kMatX) * sizeof(float);
+    if ((rc = set_smem(walk_s_bwd_dx_kernel, smX))) return rc;
+    walk_s_bwd_dx_kernel<<<dim3(T, B), kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+}  // namespace crw
