@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
     float* dRn = Rt + kMat;
     float* Ss = dRn + kMat;
     float* Sps = Ss + kMat;
-    float* dSs = Sps + kMat;
-    float* dSps = dSs + kMat;
-    float* rS = dSps + kMat;
+    float* dSs = Rt;               // results overwrite an operand that is dead by then (6 buffers -> 2 CTAs per SM)
+    float* dSps = Lt;
+    float* rS = Sps + kMat;
     float* rSp = rS + 64;
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
         for (int e = threadIdx.x; e < N * N; e += kST) dA[e] = ext ? ext[e] : 0.0f;
         return;
     }
-    zero_fill(sm, 8 * kMat);
+    zero_fill(sm, 6 * kMat);
     __syncthreads();
     if (hasSp) {
         load_nn(Lt, ws + lay.mat(lay.L, b, t), N);
@@ -373,17 +373,14 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
     }
     cp_async_wait_all();
     __syncthreads();
-    float acc[4][4];
-    if (hasSp) {
-        zero_acc(acc);
-        sgemm_tile<true, false>(Lt, kLD, dLn, kLD, N4, 0, acc);
-        for_each_out<true, false>(acc, N, [&](int m, int n, float v) { dSps[m * kLD + n] = v; });
-    }
-    if (hasS) {
-        zero_acc(acc);
-        sgemm_tile<false, true>(dRn, kLD, Rt, kLD, N4, 0, acc);
-        for_each_out<false, true>(acc, N, [&](int m, int n, float v) { dSs[m * kLD + n] = v; });
-    }
+    float acc[4][4], acc2[4][4];
+    zero_acc(acc);
+    zero_acc(acc2);
+    if (hasSp) sgemm_tile<true, false>(Lt, kLD, dLn, kLD, N4, 0, acc);
+    if (hasS) sgemm_tile<false, true>(dRn, kLD, Rt, kLD, N4, 0, acc2);
+    __syncthreads();               // every read of Lt / Rt is done: overwrite them with the products
+    for_each_out<true, false>(acc, N, [&](int m, int n, float v) { dSps[m * kLD + n] = v; });
+    for_each_out<false, true>(acc2, N, [&](int m, int n, float v) { dSs[m * kLD + n] = v; });
     __syncthreads();
     for (int r = warp; r < 2 * N; r += kST / 32) {
         const bool second = r >= N;
@@ -415,7 +412,7 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
     float* dAp = dAt + kMat;
     float* En = dAp + kMat;
     float* Ep = En + kMatX;
-    float* Out = Ep + kMatX;
+    float* Out = En;               // written only after both products are in registers (4 buffers -> 2 CTAs per SM)
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
     const int t = blockIdx.x, b = blockIdx.y, N4 = (N + 3) & ~3;
@@ -441,31 +438,38 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
         if (hasP) Ep[r * kLDX + c] *= invn[(size_t)(t - 1) * N + r];
     }
     __syncthreads();
-    for (int n0 = 0; n0 < C; n0 += 64) {
-        float acc[4][4];
-        zero_acc(acc);
-        if (hasN) sgemm_tile<false, false>(dAt, kLD, En, kLDX, N4, n0, acc);
-        float acc2[4][4];
-        zero_acc(acc2);
-        if (hasP) sgemm_tile<true, false>(dAp, kLD, Ep, kLDX, N4, n0, acc2);
-        // the two products own different rows per thread (row mapping depends on TA): go through smem
+    float acc[2][4][4], acc2[2][4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = own_row<false>(i), n = n0 + own_col<false>(j);
-                if (m < N && n < C) Out[m * kLDX + n] = acc[i][j] * inv_tau;
-            }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = own_row<true>(i), n = n0 + own_col<false>(j);
-                if (m < N && n < C) Out[m * kLDX + n] += acc2[i][j] * inv_tau;
-            }
-        __syncthreads();
+    for (int h = 0; h < 2; ++h) {
+        zero_acc(acc[h]);
+        zero_acc(acc2[h]);
+        if (h * 64 < C) {
+            if (hasN) sgemm_tile<false, false>(dAt, kLD, En, kLDX, N4, h * 64, acc[h]);
+            if (hasP) sgemm_tile<true, false>(dAp, kLD, Ep, kLDX, N4, h * 64, acc2[h]);
+        }
     }
+    __syncthreads();               // En is dead: reuse it as the output tile
+    // the two products own different rows per thread (row mapping depends on TA): combine through smem
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = own_row<false>(i), n = h * 64 + own_col<false>(j);
+                if (m < N && n < C) Out[m * kLDX + n] = acc[h][i][j] * inv_tau;
+            }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = own_row<true>(i), n = h * 64 + own_col<false>(j);
+                if (m < N && n < C) Out[m * kLDX + n] += acc2[h][i][j] * inv_tau;
+            }
+    __syncthreads();
     const float* xt = x + ((size_t)b * T + t) * N * C;
     float* o = dx + ((size_t)b * T + t) * N * C;
     for (int i = warp; i < N; i += kST / 32) {
@@ -501,6 +505,8 @@ __global__ void walk_s_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 template <class Kern>
 static int set_smem(Kern kern, size_t bytes) {
     CRW_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // one carveout for every kernel of the sequence: a different L1/shared split per launch forces an SM drain between them
+    CRW_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return CRW_OK;
 }
 
@@ -525,6 +531,7 @@ int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, fl
     if ((rc = set_smem(walk_s_cycle_kernel, sm2))) return rc;
     walk_s_cycle_kernel<<<dim3(T - 2, B), kST, sm2, st>>>(ws, B, T, N, C);
     CRW_LAUNCH_RET();
+    if ((rc = set_smem(walk_s_loss_reduce_kernel, 0))) return rc;
     walk_s_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, B, T, N, C);
     CRW_LAUNCH_RET();
     return CRW_OK;
@@ -546,11 +553,11 @@ int walk_small_backward(const float* x, const float* ws, const float* dloss, con
             CRW_LAUNCH_RET();
         }
     }
-    const size_t smA = (8 * kMat + 128) * sizeof(float);
+    const size_t smA = (6 * kMat + 128) * sizeof(float);
     if ((rc = set_smem(walk_s_bwd_dA_kernel, smA))) return rc;
     walk_s_bwd_dA_kernel<<<dim3(T - 1, B), kST, smA, st>>>(ws, sc, dA_or_null, B, T, N, C);
     CRW_LAUNCH_RET();
-    const size_t smX = (2 * kMat + 3 * kMatX) * sizeof(float);
+    const size_t smX = (2 * kMat + 2 * kMatX) * sizeof(float);
     if ((rc = set_smem(walk_s_bwd_dx_kernel, smX))) return rc;
     walk_s_bwd_dx_kernel<<<dim3(T, B), kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
