@@ -99,3 +99,48 @@ def test_lp_tensorcore_config3_full_size(pkg):
     assert (labels.cpu().numpy() == o["labels"]).mean() >= 0.999
     frac, _ = topk_sets_equal(I.cpu().numpy()[:, 1:], W.cpu().numpy()[:, 1:], o["I"][:, 1:], o["W"][:, 1:])
     assert frac >= 0.995
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core walk (tcgen05 bf16x3 GEMMs, fp32 accumulate in TMEM): loss / gradients within 1e-3 relative
+# ----------------------------------------------------------------------------------------------
+from helpers import load_golden, rel_err  # noqa: E402
+from oracle import walk_oracle as wo  # noqa: E402
+
+WALK_TC_CASES = [
+    # B, T, N, C, tau
+    (4, 10, 47, 128, 0.07),    # config 2 geometry on the tensor path
+    (2, 20, 47, 128, 0.07),    # config 4 geometry
+    (2, 6, 100, 128, 0.07),    # one 128-tile, K = 100 (two k-chunks)
+    (1, 5, 185, 128, 0.07),    # scaled geometry: 2 x 2 output tiles, three k-chunks
+    (2, 4, 12, 32, 0.07),      # K = 32 (half a chunk), K = 12
+    (2, 3, 9, 16, 0.05),       # T = 3
+    (2, 7, 24, 128, 0.01),     # the reference's train default tau
+]
+
+
+@pytest.mark.parametrize("case", WALK_TC_CASES)
+def test_walk_tensorcore_vs_f64_oracle(pkg, case):
+    B, T, N, C, tau = case
+    rs = np.random.RandomState(B * 1000 + T * 100 + N)
+    x = (rs.randn(B, T, N, C) + 1.0 * rs.randn(B, 1, 1, C)).astype(np.float32)
+    xt = _dev(x).requires_grad_(True)
+    loss, A, _ = pkg.ops.walk_loss(xt, float(tau), True, pkg.ops.PREC_BF16X3)
+    loss.backward()
+    torch.cuda.synchronize()
+    l64, _, _, dx64 = wo.walk_backward_chain(x.astype(np.float64), tau)
+    assert abs(loss.item() - l64) <= 1e-4 * abs(l64), (loss.item(), l64)
+    assert rel_err(A.detach().cpu().numpy(), wo.affinities(wo.l2_normalize(x.astype(np.float64)), tau)) < 1e-4
+    err = rel_err(xt.grad.cpu().numpy(), dx64)
+    assert err < 1e-3, err
+
+
+def test_walk_tensorcore_golden_reference(pkg):
+    for name in ["walk_cfg1_f32.npz", "walk_tau001_f32.npz"]:
+        g = load_golden(name)
+        xt = _dev(g["x"].astype(np.float32)).requires_grad_(True)
+        loss, _, _ = pkg.ops.walk_loss(xt, float(g["tau"]), False, pkg.ops.PREC_BF16X3)
+        loss.backward()
+        assert abs(loss.item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+        _, _, _, dx64 = wo.walk_backward_chain(g["x"].astype(np.float64), float(g["tau"]))
+        assert rel_err(xt.grad.cpu().numpy(), dx64) < 1e-3
