@@ -228,13 +228,16 @@ def bench_train(crw, args, rank, world, local, pk):
                          h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
 
 
-def bench_walk(crw, args, world, pk, N=47):
-    """The hot path alone: fused walk fwd + bwd on resident embeddings (config-2 shape)."""
-    B, T, tau = TRAIN["B"], TRAIN["T"], TRAIN["tau"]
+def bench_walk(crw, args, world, pk, N=47, T=None, B=None, precision=None, kernel_note=None):
+    """The hot path alone: fused walk fwd + bwd on resident embeddings (config-2 shape by default)."""
+    B = TRAIN["B"] if B is None else B
+    T = TRAIN["T"] if T is None else T
+    tau = TRAIN["tau"]
+    PREC = crw.ops.PREC_FP32 if precision is None else precision
     emb = torch.randn(B, T, N, 128, device="cuda", requires_grad=True)
 
     def walk_step(i):
-        loss, _, _ = crw.ops.walk_loss(emb, tau, False, crw.ops.PREC_FP32)
+        loss, _, _ = crw.ops.walk_loss(emb, tau, False, PREC)
         emb.grad = None
         loss.backward()
 
@@ -244,21 +247,36 @@ def bench_walk(crw, args, world, pk, N=47):
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         for _ in range(3):
-            loss, _, _ = crw.ops.walk_loss(emb, tau, False, crw.ops.PREC_FP32)
+            loss, _, _ = crw.ops.walk_loss(emb, tau, False, PREC)
             torch.autograd.grad(loss, emb)
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        loss, _, _ = crw.ops.walk_loss(emb, tau, False, crw.ops.PREC_FP32)
+        loss, _, _ = crw.ops.walk_loss(emb, tau, False, PREC)
         gemb, = torch.autograd.grad(loss, emb)
     ms = timed_loop(lambda i: graph.replay(), max(args.steps, 20), 5, world)
     fl = walk_flops(B, T, N, 128)
     tf = fl / (ms * 1e-3) / 1e12
-    return dict(ms=ms, ms_eager=ms_eager, launches=8,
+    kernel = kernel_note or ("walk fwd+bwd kernels (fp32, shared-memory-resident small-N path), 8 launches" if N <= 64 else
+                             "walk fwd+bwd kernels (fp32 FMA tiles), 8 launches")
+    return dict(ms=ms, ms_eager=ms_eager, launches=8, shape=dict(B=B, T=T, N=N, C=128),
                 roofline=dict(bound="tensor", achieved=tf, peak=pk["bf16"], unit="TFLOP/s", frac=tf / pk["bf16"],
-                              traffic=None, kernel="walk fwd+bwd kernels (fp32 FMA path), 8 launches",
-                              algorithmic_flops=fl, peak_source=pk["src"] + " bf16 burst",
-                              note="N=47: launch/latency bound; tensor-pipe ceiling at this N is <= ~36% (SURVEY 7.3.1)"))
+                              traffic=None, kernel=kernel, algorithmic_flops=fl, peak_source=pk["src"] + " bf16 burst",
+                              note=("N=47: launch/latency bound; tensor-pipe ceiling at this N is <= ~36% (SURVEY 7.3.1)"
+                                    if N <= 64 else "scaled geometry (SURVEY appendix D), not a reference-size figure")))
+
+
+def bench_walk_sweep(crw, args, world, pk):
+    """Walk fwd+bwd on both engines at the reference size and at the scaled geometries of SURVEY appendix D."""
+    out = []
+    tcn = "walk fwd+bwd kernels, tcgen05 bf16x3 GEMMs (3 passes; algorithmic FLOPs counted once), 8 launches"
+    for (B, T, N) in [(32, 10, 47), (32, 20, 47), (32, 20, 185), (32, 20, 369)]:
+        for prec, note in [(crw.ops.PREC_FP32, None), (crw.ops.PREC_BF16X3, tcn)]:
+            r = bench_walk(crw, args, world, pk, N=N, T=T, B=B, precision=prec, kernel_note=note)
+            r["precision"] = "fp32" if prec == crw.ops.PREC_FP32 else "bf16x3"
+            out.append(r)
+            log(f"walk B={B} T={T} N={N} {r['precision']}: {r['ms']:.3f} ms  {r['roofline']['achieved']:.2f} TFLOP/s")
+    return out
 
 
 def bench_labelprop(crw, args, rank, world, pk):
@@ -345,6 +363,11 @@ def run_b200(args):
     tr = bench_train(crw, args, rank, world, local, pk) if only in ("all", "train") else None
     wk = bench_walk(crw, args, world, pk) if only in ("all", "walk") else None
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
+    if only == "walk_sweep":
+        sweep = bench_walk_sweep(crw, args, world, pk)
+        if rank == 0:
+            print(json.dumps(dict(only=only, walk_sweep=sweep)), flush=True)
+        return
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and only == "all":
@@ -464,7 +487,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lp-precision", default="both", choices=["both", "bf16x3", "fp32"])
     ap.add_argument("--lp-config", type=int, default=3, choices=[3, 5])
-    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop"],
+    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()
     if args.impl == "reference":

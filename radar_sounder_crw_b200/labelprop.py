@@ -45,7 +45,8 @@ class LabelPropVOS_CRW(object):
         lbl = torch.stack([masks[f][0, :, :, 0] for f in lf]).contiguous().float()            # [F,M,N]
         query = curr_feat[0, :, :, 0].t().contiguous().float()[None]                          # [1,N,C]
         F = len(kf)
+        # the stepwise API always runs the fp32 kernel (the tensor-core kernel works on whole sequences: propagate())
         W, I = ops.affinity_topk(keys, query, F, max(F, 1), float(self.radius), float(self.temperature),
-                                 int(self.topk), self.precision)
+                                 int(self.topk), ops.PREC_FP32)
         pred = ops.label_gather_step(W[0], I[0], lbl)                                          # [M,N]
         return pred[None, :, :, None]

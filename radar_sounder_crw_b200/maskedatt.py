@@ -54,7 +54,7 @@ def _band_radius_from_bias(mask: torch.Tensor) -> int:
     return r
 
 
-def batched_affinity(query, keys, mask, temperature, topk, long_mem, ctx, device=None, precision=ops.PREC_FP32):
+def batched_affinity(query, keys, mask, temperature, topk, long_mem, ctx, device=None):
     """Same call contract as the reference (maskedatt.py:151):
 
     query [1,C,1,hw], keys [1,C,1,n,hw], mask [1,1,hw,hw] bias (0 / -1e10) or an int/float radius,
@@ -69,5 +69,5 @@ def batched_affinity(query, keys, mask, temperature, topk, long_mem, ctx, device
         kk = torch.cat([kk[:1], kk[n - ctx:]], 0)
     kk = kk.contiguous()
     F = kk.shape[0]
-    W, I = ops.affinity_topk(kk, q, F, max(F, 1), float(radius), float(temperature), int(topk), precision)
+    W, I = ops.affinity_topk(kk, q, F, max(F, 1), float(radius), float(temperature), int(topk), ops.PREC_FP32)
     return [W[0]], [I[0].long()]
