@@ -14,6 +14,7 @@
 //                   then softmax and the W / I stores.
 // A query tile is 128 consecutive rows of the [T*N, C] feature matrix, so tiles are dense even though
 // frames (N = 47..49 rows) straddle them; each thread derives its own frame / window from its row index.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace crw {
@@ -65,6 +66,7 @@ struct TcParams {
     float inv_temp;
     int tiles_per_rg, total_tiles;
     unsigned magic_n;   // floor(2^32 / N) + 1: x / N == __umulhi(x, magic_n) for x * N < 2^32
+    int debug;          // profiling aid (env CRW_TC_DEBUG): 1 = skip insertions, 2 = also skip filter/park; results invalid
 };
 
 struct TileInfo {
@@ -136,8 +138,8 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap kmap_hi, const __grid_constant__ CUtensorMap kmap_lo, TcParams p) {
     constexpr int kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
     constexpr int kParts = NEPI / 4;          // top-k lists per query (merged at the end of a tile)
-    constexpr int kTileGroups = NEPI / 8;     // key tiles are dealt round-robin to this many warp groups
     constexpr int kParkWarp = kParkBytes / NEPI;
+    static_assert(kParkWarp >= kBN * 32 * 4, "park buffer must hold one 64-column tile per lane");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                  // 64 KB
@@ -154,7 +156,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         tc::mbar_init(&q_full, 1);
         tc::mbar_init(&q_empty, 1);
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
-        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 8); }
+        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
         tc::fence_barrier_init();
     }
     if (warp == kProducerWarp && lane == 0) {
@@ -166,82 +168,89 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == kProducerWarp) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            uint32_t kcnt = 0, tcnt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileInfo t = tile_info(p, tile);
-                if (t.n_ktiles == 0) continue;
-                const int grow = t.rg * p.T * N;   // first global row of this radargram
-                tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
+        // ================= TMA producer (whole warp runs the loop; one elected lane issues) =================
+        const bool leader = tc::elect_one();
+        uint32_t kcnt = 0, tcnt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileInfo t = tile_info(p, tile);
+            if (t.n_ktiles == 0) continue;
+            const int grow = t.rg * p.T * N;   // first global row of this radargram
+            tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
+            if (leader) {
                 tc::mbar_arrive_expect_tx(&q_full, kQBytes);
-                for (int part = 0; part < 2; ++part)
-                    for (int kb = 0; kb < 2; ++kb)
-                        tc::tma_load_2d(sQ + (part * 2 + kb) * (kBM * 128), part ? &qmap_lo : &qmap_hi, kb * 64, grow + t.r0, &q_full);
-                for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                    const int s = kcnt % kStages;
-                    int row0, nrows;
-                    ktile_rows(p, t, kt, row0, nrows);
-                    tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub)
+                    tc::tma_load_2d(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64, grow + t.r0, &q_full);
+            }
+            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                const int s = kcnt % kStages;
+                int row0, nrows;
+                ktile_rows(p, t, kt, row0, nrows);
+                tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+                if (leader) {
                     tc::mbar_arrive_expect_tx(&k_full[s], kKBytes);
                     uint8_t* dst = sK + s * kKBytes;
-                    for (int part = 0; part < 2; ++part)
-                        for (int kb = 0; kb < 2; ++kb)
-                            tc::tma_load_2d(dst + (part * 2 + kb) * (kBN * 128), part ? &kmap_lo : &kmap_hi, kb * 64, grow + row0,
-                                            &k_full[s]);
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub)
+                        tc::tma_load_2d(dst + sub * (kBN * 128), (sub & 2) ? &kmap_lo : &kmap_hi, (sub & 1) * 64, grow + row0, &k_full[s]);
                 }
-                ++tcnt;
             }
+            ++tcnt;
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t kcnt = 0, tcnt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileInfo t = tile_info(p, tile);
-                if (t.n_ktiles == 0) continue;
-                tc::mbar_wait_backoff(&q_full, tcnt & 1);
-                for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                    const int s = kcnt % kStages, a = kcnt % kAcc;
-                    int row0, nrows;
-                    ktile_rows(p, t, kt, row0, nrows);
-                    const int ncols = min(kBN, (nrows + 15) & ~15);
-                    tc::mbar_wait_backoff(&k_full[s], (kcnt / kStages) & 1);
-                    tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
-                    tc::tc_fence_after();
-                    const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
-                    const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK + s * kKBytes);
-                    const uint32_t d = tmem_base + (uint32_t)(a * kBN);
-                    uint32_t acc = 0;
-                    // pass 0: q_hi.k_hi   pass 1: q_hi.k_lo   pass 2: q_lo.k_hi
+        // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+        const bool leader = tc::elect_one();
+        const uint64_t qdesc = tc::umma_smem_desc_k128(tc::smem_u32(sQ));     // descriptor of sub-tile 0, k-step 0
+        const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
+        uint32_t kcnt = 0, tcnt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileInfo t = tile_info(p, tile);
+            if (t.n_ktiles == 0) continue;
+            tc::mbar_wait_backoff(&q_full, tcnt & 1);
+            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                const int s = kcnt % kStages, a = kcnt % kAcc;
+                int row0, nrows;
+                ktile_rows(p, t, kt, row0, nrows);
+                const int ncols = min(kBN, (nrows + 15) & ~15);
+                tc::mbar_wait(&k_full[s], (kcnt / kStages) & 1);            // latency critical: no backoff
+                tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
+                const uint64_t kdesc = kdesc0 + (uint64_t)((s * kKBytes) >> 4);   // start-address field counts 16-byte units
+                const uint32_t d = tmem_base + (uint32_t)(a * kBN);
+                if (leader) {
+                    // pass 0: q_hi.k_hi   pass 1: q_hi.k_lo   pass 2: q_lo.k_hi ; sub-tile = part*2 + kblock, k-step = 32 bytes
+                    if (!(p.debug & 4))
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t qpart = (pass == 2) ? 2u : 0u, kpart = (pass == 1) ? 2u : 0u;
+                        const int qpart = (pass == 2) ? 2 : 0, kpart = (pass == 1) ? 2 : 0;
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = tc::umma_smem_desc_k128(q0 + (qpart + kb) * (kBM * 128) + ks * 32);
-                                const uint64_t bd = tc::umma_smem_desc_k128(k0 + (kpart + kb) * (kBN * 128) + ks * 32);
-                                tc::umma_bf16_ss(d, ad, bd, idesc, acc);
-                                acc = 1;
+                                const uint64_t ad = qdesc + (uint64_t)((((qpart + kb) * (kBM * 128)) + ks * 32) >> 4);
+                                const uint64_t bd = kdesc + (uint64_t)((((kpart + kb) * (kBN * 128)) + ks * 32) >> 4);
+                                tc::umma_bf16_ss(d, ad, bd, idesc, (pass | kb | ks) ? 1u : 0u);
                             }
                     }
                     tc::umma_commit(&k_empty[s]);     // smem stage may be refilled once these MMAs retire
                     tc::umma_commit(&acc_full[a]);    // accumulator ready for the epilogue
                 }
-                tc::umma_commit(&q_empty);            // query tile may be overwritten
-                ++tcnt;
+                __syncwarp();
             }
+            if (leader) tc::umma_commit(&q_empty);    // query tile may be overwritten
+            __syncwarp();
+            ++tcnt;
         }
     } else {
         // ================= epilogue: NEPI warps; thread = query row (TMEM lane) =================
-        // warp = 4*part + lane-group.  part&1 selects the 32-column half of a key tile, part>>1 which key tiles
-        // (round-robin) this warp looks at.  Per block: (1) tcgen05.ld the thread's 32 columns, (2) park them in a
+        // warp = 4*part + lane-group; key tiles (64 columns) are dealt round-robin to the parts, so every query has
+        // kParts partial top-k lists that are merged at the end of the query tile.  Per key tile: (1) tcgen05.ld the
+        // thread's 2 x 32 columns, (2) park them in a
         // thread-private smem column ([i][lane]: bank = lane, conflict-free) so candidates can be fetched by dynamic
         // index, (3) "beats the current k-th best" bitmask & validity bitmask (frame window x radius band),
         // (4) ONE rolled insertion loop over the set bits (keeps the hot loop inside the I-cache).
-        const int g = warp & 3, part = warp >> 2, half = part & 1, tgroup = part >> 1;
+        const int g = warp & 3, part = warp >> 2;
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
@@ -256,50 +265,53 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                if (kTileGroups > 1 && (kt % kTileGroups) != tgroup) continue;
+                if ((kt % kParts) != part) continue;              // whole 64-column key tiles are dealt round-robin
                 const int a = kcnt % kAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
                 tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
                 tc::tc_fence_after();
-                const int c0 = half * 32;
-                if (c0 < nrows) {                                 // warp-uniform
-                    float v[32];
-                    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + c0), v);
-                    tc::tmem_ld_wait();
-                    const float thr = top.v[KT - 1];
-                    uint32_t pm = 0;
+                const float thr = top.v[KT - 1];
+                uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        tc::sts_f32(park + i * 128, v[i]);
-                        pm |= (v[i] > thr) ? (1u << i) : 0u;
-                    }
-                    // validity mask of this thread over the block's 32 key rows (segments = key frames)
-                    const int kr0 = row0 + c0;
-                    const int kf0 = (int)__umulhi((unsigned)kr0, p.magic_n);
-                    uint32_t vm = 0;
-                    {
-                        int c = 0, kf = kf0, j = kr0 - kf0 * N;
-                        const int cend = min(32, nrows - c0);
-                        while (c < cend) {                          // warp-uniform trip count
-                            const int seg = min(cend - c, N - j);
-                            if ((kf < n) && (kf == 0 || kf >= win_lo)) {
-                                const int lo = max(j, q - rb), hi = min(j + seg - 1, q + rb);
-                                if (lo <= hi) {
-                                    const int b0 = c + lo - j, nb = hi - lo + 1;
-                                    vm |= ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1u)) << b0;
-                                }
-                            }
-                            c += seg; j = 0; ++kf;
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (ch * 32 < nrows && !(p.debug & 2)) {                        // warp-uniform
+                        float v[32];
+                        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + ch * 32), v);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            tc::sts_f32(park + (ch * 32 + i) * 128, v[i]);
+                            pm[ch] |= (v[i] > thr) ? (1u << i) : 0u;
                         }
                     }
-                    uint32_t cand = qvalid ? (pm & vm) : 0u;
-                    while (cand) {
-                        const int i = __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        const float x = tc::lds_f32(park + i * 128);
-                        if (x > top.v[KT - 1]) top.insert(x, kr0 + i);
+                }
+                // validity mask of this thread over the tile's key rows (segments = key frames)
+                {
+                    const int kf0 = (int)__umulhi((unsigned)row0, p.magic_n);
+                    int c = 0, kf = kf0, j = row0 - kf0 * N;
+                    while (c < nrows) {                           // warp-uniform trip count
+                        const int seg = min(nrows - c, N - j);
+                        if ((kf < n) && (kf == 0 || kf >= win_lo)) {
+                            const int lo = max(j, q - rb), hi = min(j + seg - 1, q + rb);
+                            if (lo <= hi) {
+                                const int b0 = c + lo - j, nb = hi - lo + 1;
+                                const unsigned long long m64 = ((nb >= 64) ? ~0ull : ((1ull << nb) - 1ull)) << b0;
+                                vm[0] |= (uint32_t)m64;
+                                vm[1] |= (uint32_t)(m64 >> 32);
+                            }
+                        }
+                        c += seg; j = 0; ++kf;
                     }
+                }
+                uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
+                if (p.debug & 3) { c0 = 0; c1 = 0; }
+                while (c0 | c1) {
+                    int i;
+                    if (c0) { i = __ffs(c0) - 1; c0 &= c0 - 1; }
+                    else { i = 32 + __ffs(c1) - 1; c1 &= c1 - 1; }
+                    const float x = tc::lds_f32(park + i * 128);
+                    if (x > top.v[KT - 1]) top.insert(x, row0 + i);
                 }
                 tc::tc_fence_before();
                 __syncwarp();
@@ -413,6 +425,7 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     p.inv_temp = 1.0f / temp;
     if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
     p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
+    { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.tiles_per_rg = ceil_div(T * N, kBM);
     p.total_tiles = R * p.tiles_per_rg;
     if (k <= 10) return launch_tc<10, 8>(maps, p, st);
