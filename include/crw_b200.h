@@ -143,6 +143,13 @@ int crw_labelprop_forward(const float* feats, const float* mask0, int R, int T, 
 int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Nearest-neighbour upsample of the propagated label map to pixel resolution -- replaces
+ * `up = Resize((seg_h, rg_len), NEAREST)` applied to final_prediction, scripts/test/test_all.py:79,96.
+ *   labels [R,T,N] i32  ->  out [R,H,W] f32  (out[r,y,x] = labels[r, floor(x*T/W), floor(y*N/H)])
+ * ---------------------------------------------------------------------------------- */
+int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Self-test of the tensor-core plumbing (TMA SWIZZLE_128B tiles -> tcgen05.mma -> TMEM -> tcgen05.ld):
  *   out[128,BN] = A[128,128] * B[BN,128]^T, A/B bf16 row-major, out fp32; BN multiple of 16, <= 256.
  * No reference counterpart; it pins the descriptor encodings the tensor-core kernels rely on.

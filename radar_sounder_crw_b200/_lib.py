@@ -34,6 +34,7 @@ SIGNATURES = {
     "crw_labelprop_forward": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_int,
                                        _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_sz, _vp]),
     "crw_horizontality_xent": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "crw_labels_upsample": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_debug_umma_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
 }
 

@@ -516,6 +516,20 @@ __global__ void __launch_bounds__(256) lp_gather_step_kernel(const float* __rest
     if (out_label) out_label[q] = best_m;
 }
 
+// Nearest-neighbour upsample of a label map (reference: `up = Resize((seg_h, rg_len), NEAREST)` applied to
+// final_prediction[N,T], scripts/test/test_all.py:79,96).  labels [R,T,N] i32 -> out [R,H,W] f32 with torch's
+// rule src = min(floor(dst * float(in/out)), in-1) on both axes.
+__global__ void __launch_bounds__(256) lp_upsample_kernel(const int32_t* __restrict__ labels, int R, int T, int N, int H, int W,
+                                                          float* __restrict__ out) {
+    const float sy = (float)N / (float)H, sx = (float)T / (float)W;
+    const long long total = (long long)R * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H), r = (int)(i / ((long long)W * H));
+        const int n = min((int)floorf((float)y * sy), N - 1), t = min((int)floorf((float)x * sx), T - 1);
+        out[i] = (float)labels[((size_t)r * T + t) * N + n];
+    }
+}
+
 }  // namespace crw
 
 // ==========================================================================================
@@ -679,6 +693,16 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         }
     }
     return crw_label_gather(W, I, mask0, R, T, N, M, ctx, k, mode, labels, masks, stream);
+}
+
+extern "C" int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W, float* out, void* stream) {
+    if (!labels || !out || R < 0 || T < 1 || N < 1 || H < 1 || W < 1) return CRW_ERR_INVALID;
+    const long long total = (long long)R * H * W;
+    if (total == 0) return CRW_OK;
+    const long long blocks = (total + 255) / 256;
+    lp_upsample_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(labels, R, T, N, H, W, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
 }
 
 extern "C" int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, void* stream) {

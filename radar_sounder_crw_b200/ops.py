@@ -219,3 +219,22 @@ def horizontality_xent(emb: Tensor) -> Tensor:
 def _(emb):
     T, N, _ = emb.shape
     return emb.new_empty((N, max(T - 1, 0)))
+
+
+# ------------------------------------------------------------------------------------------------
+# labels_upsample  (scripts/test/test_all.py:79,96: Resize((seg_h, rg_len), NEAREST) of final_prediction)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::labels_upsample", mutates_args=())
+def labels_upsample(labels: Tensor, H: int, W: int) -> Tensor:
+    """labels [R,T,N] i32 -> [R,H,W] f32 nearest-neighbour upsample (rows <- nodes, columns <- frames)."""
+    labels = _chk(labels, "labels", torch.int32)
+    R, T, N = labels.shape
+    out = torch.empty((R, H, W), device=labels.device, dtype=torch.float32)
+    with torch.cuda.device(labels.device):
+        _lib.check(_lib.lib().crw_labels_upsample(_p(labels), R, T, N, H, W, _p(out), _stream()), "crw_labels_upsample")
+    return out
+
+
+@labels_upsample.register_fake
+def _(labels, H, W):
+    return labels.new_empty((labels.shape[0], H, W), dtype=torch.float32)

@@ -304,3 +304,16 @@ def test_propagate_dropin_end_to_end(pkg):
 def test_no_cpu_fallback(pkg):
     with pytest.raises(RuntimeError):
         pkg.ops.l2_normalize(torch.randn(4, 8))
+
+
+def test_labels_upsample_matches_torchvision_nearest(pkg):
+    """Post-processing row: Resize((seg_h, rg_len), NEAREST) of final_prediction[N,T] (test_all.py:79,96)."""
+    from torchvision import transforms
+    from torchvision.transforms import InterpolationMode
+    for (T, N, H, W) in [(100, 49, 400, 1600), (37, 47, 410, 1184), (8, 113, 912, 128)]:
+        labels = torch.randint(0, 5, (2, T, N), dtype=torch.int32)
+        got = pkg.ops.labels_upsample(labels.cuda(), H, W).cpu()
+        up = transforms.Resize((H, W), interpolation=InterpolationMode.NEAREST)
+        for r in range(2):
+            ref = up(labels[r].t().float()[None]).squeeze(0)       # final_prediction is [N,T]
+            assert torch.equal(got[r], ref), (T, N, H, W)
