@@ -202,7 +202,7 @@ def bench_train(crw, args, rank, world, local, pk):
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=32)
-    opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"])
+    opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"], fused=True)   # train-loop glue
     last_loss = [None]
 
     def train_step(i, src=batches_dev):

@@ -57,23 +57,35 @@ struct TopkParams {
 
 __device__ __forceinline__ int swz(int c, int j) { return c * kChunk + ((((j >> 2) ^ (c >> 2)) & 15) << 2) + (j & 3); }
 
-// stage nodes [j_base, j_base+64) of `frame` ([N][C] row-major) into dst ([C][64] swizzled)
+// stage nodes [j_base, j_base+64) of `frame` ([N][C] row-major) into dst ([C][64] swizzled).
+// All global loads of a thread are issued before the first shared store so their latencies overlap.
 __device__ __forceinline__ void stage_frame_T(const float* __restrict__ frame, int N, int C, int j_base, float* dst) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int jl4 = lane & 3, c4 = lane >> 2;
-    for (int rg = warp; rg < kChunk / 4; rg += kTopkThreads / 32) {
-        const int jl = rg * 4 + jl4;
+    constexpr int kRg = (kChunk / 4) / (kTopkThreads / 32);   // row groups per warp (2)
+    float4 v[kRg][4];                                          // C <= 128: at most 4 column blocks of 32
+#pragma unroll
+    for (int u = 0; u < kRg; ++u) {
+        const int jl = (warp + u * (kTopkThreads / 32)) * 4 + jl4;
         const int j = j_base + jl;
-        const bool ok = j < N;
         const float4* src = reinterpret_cast<const float4*>(frame + (size_t)j * C);
-        for (int cb = 0; cb < C; cb += 32) {
-            const int c = cb + c4 * 4;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int c = b * 32 + c4 * 4;
+            v[u][b] = (j < N && c < C) ? __ldg(src + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kRg; ++u) {
+        const int jl = (warp + u * (kTopkThreads / 32)) * 4 + jl4;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int c = b * 32 + c4 * 4;
             if (c < C) {
-                float4 v = ok ? __ldg(src + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                dst[swz(c + 0, jl)] = v.x;
-                dst[swz(c + 1, jl)] = v.y;
-                dst[swz(c + 2, jl)] = v.z;
-                dst[swz(c + 3, jl)] = v.w;
+                dst[swz(c + 0, jl)] = v[u][b].x;
+                dst[swz(c + 1, jl)] = v[u][b].y;
+                dst[swz(c + 2, jl)] = v[u][b].z;
+                dst[swz(c + 3, jl)] = v[u][b].w;
             }
         }
     }
