@@ -155,6 +155,8 @@ int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W
  * No reference counterpart; it pins the descriptor encodings the tensor-core kernels rely on.
  * ---------------------------------------------------------------------------------- */
 int crw_debug_umma_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
+/* same product with A parked in TMEM by the threads (tcgen05.st) and read by the "TS" form of tcgen05.mma */
+int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,21 @@ def test_umma_selftest_matches_torch(pkg, BN):
     assert err < 1e-3, err   # bf16 products are exact in fp32; only the accumulation order differs
 
 
+@pytest.mark.parametrize("BN", [16, 64, 256])
+def test_umma_ts_selftest_matches_torch(pkg, BN):
+    """A operand parked in TMEM with tcgen05.st and read by the TS form of tcgen05.mma: pins the A-in-TMEM layout."""
+    torch.manual_seed(100 + BN)
+    A = torch.randn(128, 128, device="cuda").bfloat16()
+    B = torch.randn(BN, 128, device="cuda").bfloat16()
+    out = torch.full((128, BN), float("nan"), device="cuda")
+    L = pkg._lib.lib()
+    pkg._lib.check(L.crw_debug_umma_ts_gemm(A.data_ptr(), B.data_ptr(), BN, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "crw_debug_umma_ts_gemm")
+    torch.cuda.synchronize()
+    err = (out - A.float() @ B.float().t()).abs().max().item()
+    assert err < 1e-3, err
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core label propagation (bf16 hi/lo x3, tcgen05): the "bf16 path" of BASELINE.json
 # bar: >= 99.9 % pixel agreement with the fp32 path; top-k sets identical except across near-ties
