@@ -317,3 +317,27 @@ def test_labels_upsample_matches_torchvision_nearest(pkg):
         for r in range(2):
             ref = up(labels[r].t().float()[None]).squeeze(0)       # final_prediction is [N,T]
             assert torch.equal(got[r], ref), (T, N, H, W)
+
+
+def test_encoder_few_channel_batchnorm_is_equivalent(pkg):
+    """The 3-channel bn0 of the encoder is evaluated with tensor reductions (cuDNN parallelises BN over channels);
+    same parameters, running statistics and results as nn.BatchNorm2d."""
+    import torch.nn as nn
+    from radar_sounder_crw_b200.encoder import batchnorm_few_channels
+    torch.manual_seed(3)
+    x = torch.randn(200, 3, 18, 18, device="cuda", requires_grad=True)
+    x2 = x.detach().clone().requires_grad_(True)
+    bn_a, bn_b = nn.BatchNorm2d(3).cuda(), nn.BatchNorm2d(3).cuda()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-1, 1)
+    bn_b.load_state_dict(bn_a.state_dict())
+    ya, yb = bn_a(x), batchnorm_few_channels(x2, bn_b)
+    g = torch.randn_like(ya)
+    ya.backward(g)
+    yb.backward(g)
+    assert torch.allclose(ya, yb, atol=1e-5) and torch.allclose(x.grad, x2.grad, atol=1e-5)
+    assert torch.allclose(bn_a.weight.grad, bn_b.weight.grad, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(bn_a.running_var, bn_b.running_var, atol=1e-6) and bn_b.num_batches_tracked.item() == 1
+    bn_a.eval(), bn_b.eval()
+    assert torch.allclose(bn_a(x), batchnorm_few_channels(x2, bn_b), atol=1e-5)
