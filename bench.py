@@ -366,6 +366,12 @@ def run_b200(args):
     tr = bench_train(crw, args, rank, world, local, pk) if only in ("all", "train") else None
     wk = bench_walk(crw, args, world, pk) if only in ("all", "walk") else None
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
+    if only == "walk_tc_large":     # profiling aid: the tcgen05 walk engine at the scaled geometry N=369
+        r = bench_walk(crw, args, world, pk, N=369, T=20, B=32, precision=crw.ops.PREC_BF16X3,
+                       kernel_note="walk fwd+bwd kernels, tcgen05 bf16x3 GEMMs, 8 launches")
+        if rank == 0:
+            print(json.dumps(dict(only=only, walk=r)), flush=True)
+        return
     if only == "walk_sweep":
         sweep = bench_walk_sweep(crw, args, world, pk)
         if rank == 0:
@@ -490,7 +496,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lp-precision", default="both", choices=["both", "bf16x3", "fp32"])
     ap.add_argument("--lp-config", type=int, default=3, choices=[3, 5])
-    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep"],
+    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep", "walk_tc_large"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()
     if args.impl == "reference":

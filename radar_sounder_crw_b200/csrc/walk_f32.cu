@@ -15,7 +15,6 @@
 // stage is built from one CTA-wide tiled fp32 GEMM (64x64 tile, 4x4 per thread).
 #include "common.cuh"
 #include "walk_layout.cuh"
-#include "walk_tc.cuh"
 
 namespace crw {
 
@@ -90,33 +89,12 @@ __device__ __forceinline__ void cta_gemm(const float* A, int lda, const float* B
     __syncthreads();
 }
 
-// one call site for both GEMM engines: TC = tcgen05 bf16x3 (walk_tc.cuh), !TC = fp32 FMA (cta_gemm above)
-template <bool TC, bool TA, bool TB, class Epi>
-__device__ __forceinline__ void gemm_any(const float* A, int lda, const float* B, int ldb, int M, int Nn, int K,
-                                         const float* kscale, GemmSmem& sm, TcGemmCtx& cx, Epi epi) {
-    if constexpr (TC) cta_gemm_tc<TA, TB>(A, lda, B, ldb, M, Nn, K, kscale, cx, epi);
-    else cta_gemm<TA, TB>(A, lda, B, ldb, M, Nn, K, kscale, sm, epi);
-}
-#define CRW_TC_BEGIN(dyn_floats)                                                                       \
-    TcGemmCtx cx;                                                                                      \
-    __shared__ uint64_t tc_bars[2];                                                                    \
-    __shared__ uint32_t tc_slot;                                                                       \
-    if (TC) {                                                                                          \
-        extern __shared__ float dyn_all[];                                                             \
-        tc_ctx_init(cx, reinterpret_cast<uint8_t*>(dyn_all + (dyn_floats)), tc_bars, &tc_slot);        \
-    }
-#define CRW_TC_END() \
-    if (TC) tc_ctx_fini(cx);
-
 // ------------------------------------------------------------------------------------------
 // forward stage 1: grid (T-1, B).  inverse norms, A_t, S_t = rowsoftmax(A_t), S'_t = rowsoftmax(A_t^T)
 // ------------------------------------------------------------------------------------------
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_affinity_kernel(const float* __restrict__ x, float* ws, float* A_out,
                                                             int B, int T, int N, int C, float inv_tau) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(2 * N)
     extern __shared__ float dyn[];   // inv norms of frame t and t+1: [2][N]
     const WalkLayout lay(B, T, N, C);
     const int t = blockIdx.x, b = blockIdx.y;
@@ -140,7 +118,7 @@ __global__ void __launch_bounds__(kWT) walk_affinity_kernel(const float* __restr
     __syncthreads();
     float* At = ws + lay.mat(lay.A, b, t);
     float* Ao = A_out ? A_out + ((size_t)b * (T - 1) + t) * N * N : nullptr;
-    gemm_any<TC, false, true>(x0, C, x1, C, N, N, C, nullptr, sm, cx, [&](int i, int j, float v) {
+    cta_gemm<false, true>(x0, C, x1, C, N, N, C, nullptr, sm, [&](int i, int j, float v) {
         const float a = v * inv0[i] * inv1[j] * inv_tau;
         At[(size_t)i * N + j] = a;
         if (Ao) Ao[(size_t)i * N + j] = a;
@@ -162,17 +140,13 @@ __global__ void __launch_bounds__(kWT) walk_affinity_kernel(const float* __restr
         float* dst = (col ? Sp : S) + (size_t)i * N;
         for (int j = lane; j < N; j += 32) dst[j] = __expf(At[base + j * step] - mx) * inv;
     }
-    CRW_TC_END()
 }
 
 // ------------------------------------------------------------------------------------------
 // forward stage 2: grid (2, B).  x = 0: L chain, x = 1: R chain (sequential in k)
 // ------------------------------------------------------------------------------------------
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_chain_kernel(float* ws, int B, int T, int N, int C) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(0)
     const WalkLayout lay(B, T, N, C);
     const int b = blockIdx.y, K = T - 2;
     const size_t nn = (size_t)N * N;
@@ -184,7 +158,7 @@ __global__ void __launch_bounds__(kWT) walk_chain_kernel(float* ws, int B, int T
             const float* Lp = ws + lay.mat(lay.L, b, k - 1);
             const float* Sp = ws + lay.mat(lay.Sp, b, k - 1);
             float* Lk = ws + lay.mat(lay.L, b, k);
-            gemm_any<TC, false, false>(Lp, N, Sp, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { Lk[(size_t)i * N + j] = v; });
+            cta_gemm<false, false>(Lp, N, Sp, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { Lk[(size_t)i * N + j] = v; });
         }
     } else {
         float* R1 = ws + lay.mat(lay.R, b, 1);
@@ -194,20 +168,16 @@ __global__ void __launch_bounds__(kWT) walk_chain_kernel(float* ws, int B, int T
             const float* Rp = ws + lay.mat(lay.R, b, k - 1);
             const float* S = ws + lay.mat(lay.S, b, k - 1);
             float* Rk = ws + lay.mat(lay.R, b, k);
-            gemm_any<TC, false, false>(S, N, Rp, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { Rk[(size_t)i * N + j] = v; });
+            cta_gemm<false, false>(S, N, Rp, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { Rk[(size_t)i * N + j] = v; });
         }
     }
-    CRW_TC_END()
 }
 
 // ------------------------------------------------------------------------------------------
 // forward stage 3: grid (T-2, B).  M_k = L_k R_k, loss partial, G_k = rowsoftmax(M_k) - I
 // ------------------------------------------------------------------------------------------
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_cycle_kernel(float* ws, int B, int T, int N, int C) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(0)
     __shared__ float red[kWT / 32];
     const WalkLayout lay(B, T, N, C);
     const int k = blockIdx.x + 1, b = blockIdx.y;
@@ -215,7 +185,7 @@ __global__ void __launch_bounds__(kWT) walk_cycle_kernel(float* ws, int B, int T
     const float* Lk = ws + lay.mat(lay.L, b, k);
     const float* Rk = ws + lay.mat(lay.R, b, k);
     float* Gk = ws + lay.mat(lay.G, b, k);
-    gemm_any<TC, false, false>(Lk, N, Rk, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { Gk[(size_t)i * N + j] = v; });
+    cta_gemm<false, false>(Lk, N, Rk, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { Gk[(size_t)i * N + j] = v; });
     float part = 0.0f;
     for (int d = warp; d < N; d += kWT / 32) {
         float* row = Gk + (size_t)d * N;
@@ -238,7 +208,6 @@ __global__ void __launch_bounds__(kWT) walk_cycle_kernel(float* ws, int B, int T
         for (int w = 0; w < kWT / 32; ++w) s += red[w];
         ws[lay.part + (size_t)b * (T - 1) + k] = s;
     }
-    CRW_TC_END()
 }
 
 // forward stage 4: one warp, fixed summation order.  loss = sum_{b,k} part / (B*N) / N
@@ -257,12 +226,9 @@ __global__ void walk_loss_reduce_kernel(const float* ws, float* loss, int B, int
 __global__ void walk_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 
 // bwd stage 1: grid (T-2, B, 2).  z=0: dL_k = s * G_k R_k^T ;  z=1: dR_k = s * L_k^T G_k
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_bwd_own_kernel(const float* ws, float* sc, const float* dloss, int B, int T,
                                                            int N, int C) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(0)
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
     const int k = blockIdx.x + 1, b = blockIdx.y;
@@ -271,21 +237,17 @@ __global__ void __launch_bounds__(kWT) walk_bwd_own_kernel(const float* ws, floa
     if (blockIdx.z == 0) {
         const float* Rk = ws + lay.mat(lay.R, b, k);
         float* o = sc + lay.mat(bl.dL, b, k);
-        gemm_any<TC, false, true>(Gk, N, Rk, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { o[(size_t)i * N + j] = v * s; });
+        cta_gemm<false, true>(Gk, N, Rk, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { o[(size_t)i * N + j] = v * s; });
     } else {
         const float* Lk = ws + lay.mat(lay.L, b, k);
         float* o = sc + lay.mat(bl.dR, b, k);
-        gemm_any<TC, true, false>(Lk, N, Gk, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { o[(size_t)i * N + j] = v * s; });
+        cta_gemm<true, false>(Lk, N, Gk, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { o[(size_t)i * N + j] = v * s; });
     }
-    CRW_TC_END()
 }
 
 // bwd stage 2: grid (2, B).  x=0: dL_j += dL_{j+1} S'_j^T (j = K-1..1);  x=1: dR_j += S_j^T dR_{j+1} (j = K-1..2)
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_bwd_chain_kernel(const float* ws, float* sc, int B, int T, int N, int C) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(0)
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
     const int b = blockIdx.y, K = T - 2;
@@ -294,26 +256,22 @@ __global__ void __launch_bounds__(kWT) walk_bwd_chain_kernel(const float* ws, fl
             const float* dLn = sc + lay.mat(bl.dL, b, j + 1);
             const float* Sp = ws + lay.mat(lay.Sp, b, j);
             float* o = sc + lay.mat(bl.dL, b, j);
-            gemm_any<TC, false, true>(dLn, N, Sp, N, N, N, N, nullptr, sm, cx, [&](int i, int c, float v) { o[(size_t)i * N + c] += v; });
+            cta_gemm<false, true>(dLn, N, Sp, N, N, N, N, nullptr, sm, [&](int i, int c, float v) { o[(size_t)i * N + c] += v; });
         }
     } else {
         for (int j = K - 1; j >= 2; --j) {
             const float* dRn = sc + lay.mat(bl.dR, b, j + 1);
             const float* S = ws + lay.mat(lay.S, b, j);
             float* o = sc + lay.mat(bl.dR, b, j);
-            gemm_any<TC, true, false>(S, N, dRn, N, N, N, N, nullptr, sm, cx, [&](int i, int c, float v) { o[(size_t)i * N + c] += v; });
+            cta_gemm<true, false>(S, N, dRn, N, N, N, N, nullptr, sm, [&](int i, int c, float v) { o[(size_t)i * N + c] += v; });
         }
     }
-    CRW_TC_END()
 }
 
 // bwd stage 3: grid (T-1, B).  dS'_t = L_t^T dL_{t+1}; dS_t = dR_{t+1} R_t^T; softmax backward; dA_t
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_bwd_dA_kernel(const float* ws, float* sc, const float* dA_ext, int B, int T,
                                                           int N, int C) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(2 * N)
     extern __shared__ float dyn[];   // rS[N], rSp[N]
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
@@ -329,12 +287,12 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dA_kernel(const float* ws, float
     if (hasSp) {
         const float* Lt = ws + lay.mat(lay.L, b, t);
         const float* dLn = sc + lay.mat(bl.dL, b, t + 1);
-        gemm_any<TC, true, false>(Lt, N, dLn, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { dSp[(size_t)i * N + j] = v; });
+        cta_gemm<true, false>(Lt, N, dLn, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { dSp[(size_t)i * N + j] = v; });
     }
     if (hasS) {
         const float* Rt = ws + lay.mat(lay.R, b, t);
         const float* dRn = sc + lay.mat(bl.dR, b, t + 1);
-        gemm_any<TC, false, true>(dRn, N, Rt, N, N, N, N, nullptr, sm, cx, [&](int i, int j, float v) { dS[(size_t)i * N + j] = v; });
+        cta_gemm<false, true>(dRn, N, Rt, N, N, N, N, nullptr, sm, [&](int i, int j, float v) { dS[(size_t)i * N + j] = v; });
     }
     float* rS = dyn;
     float* rSp = dyn + N;
@@ -358,16 +316,12 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dA_kernel(const float* ws, float
         if (hasSp) g += Sp[(size_t)j * N + i] * (dSp[(size_t)j * N + i] - rSp[j]);
         dA[e] = g;
     }
-    CRW_TC_END()
 }
 
 // bwd stage 4: grid (T, B).  dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau, then normalise backward
-template <bool TC>
 __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restrict__ x, const float* ws, const float* sc,
                                                           float* dx, int B, int T, int N, int C, float inv_tau) {
     __shared__ GemmSmem sm;
-    const int N_for_dyn = N; (void)N_for_dyn;
-    CRW_TC_BEGIN(0)
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
     const int t = blockIdx.x, b = blockIdx.y;
@@ -377,7 +331,7 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restric
     if (t <= T - 2) {
         const float* dA = sc + lay.mat(bl.dAw, b, t);
         const float* xn = x + ((size_t)b * T + t + 1) * N * C;
-        gemm_any<TC, false, false>(dA, N, xn, C, N, C, N, invn + (size_t)(t + 1) * N, sm, cx,
+        cta_gemm<false, false>(dA, N, xn, C, N, C, N, invn + (size_t)(t + 1) * N, sm,
                                [&](int i, int c, float v) { o[(size_t)i * C + c] = v * inv_tau; });
     } else {
         for (size_t e = threadIdx.x; e < (size_t)N * C; e += kWT) o[e] = 0.0f;
@@ -386,7 +340,7 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restric
     if (t >= 1) {
         const float* dAp = sc + lay.mat(bl.dAw, b, t - 1);
         const float* xp = x + ((size_t)b * T + t - 1) * N * C;
-        gemm_any<TC, true, false>(dAp, N, xp, C, N, C, N, invn + (size_t)(t - 1) * N, sm, cx,
+        cta_gemm<true, false>(dAp, N, xp, C, N, C, N, invn + (size_t)(t - 1) * N, sm,
                               [&](int i, int c, float v) { o[(size_t)i * C + c] += v * inv_tau; });
     }
     const float* xt = x + ((size_t)b * T + t) * N * C;
@@ -403,7 +357,6 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restric
         dot = warp_sum(dot);
         for (int c = lane; c < C; c += 32) orow[c] = (orow[c] - xr[c] * inv * dot) * inv;
     }
-    CRW_TC_END()
 }
 
 }  // namespace crw
@@ -414,24 +367,16 @@ int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, fl
                        cudaStream_t st);
 int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
                         float tau, float* dx, float* sc, cudaStream_t st);
+// walk_tc_tiles.cu: tile-parallel tcgen05 bf16x3 path
+int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
+                       cudaStream_t st);
+int walk_tiles_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
+                        float tau, float* dx, float* sc, cudaStream_t st);
 }  // namespace crw
 
 using namespace crw;
 
 static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-// the tensor-core variants need > 48 KB of dynamic shared memory (two 64 KB operand stages)
-static int walk_tc_opt_in() {
-    const int bytes = kTcSmemBytes + 2 * 1024 * (int)sizeof(float);   // + the per-kernel 2N-float prefix (N <= 1024)
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_affinity_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_cycle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_bwd_own_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_bwd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_bwd_dA_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CRW_CUDA_RET(cudaFuncSetAttribute(walk_bwd_dx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return CRW_OK;
-}
 
 extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C) {
     if (B < 1 || T < 2 || N < 1 || C < 1) return 0;
@@ -456,26 +401,19 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = align256(saved);
     const float inv_tau = 1.0f / tau;
-    const bool tc = precision == CRW_PREC_BF16X3;     // tcgen05 bf16x3 GEMMs (any N); fp32: smem path for N <= 64, FMA tiles beyond
-    if (!tc && walk_small_supported(N, C) && aligned16p(x))
-        return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
-    if (tc) {
-        int rc = walk_tc_opt_in();
-        if (rc != CRW_OK) return rc;
-    }
-    if (tc) walk_affinity_kernel<true><<<dim3(T - 1, B), kWT, 2 * N * sizeof(float) + kTcSmemBytes, st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
-    else walk_affinity_kernel<false><<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
+    // BF16X3: tile-parallel tcgen05 GEMMs (any N).  FP32: shared-memory path for N <= 64, FMA tiles beyond.
+    if (precision == CRW_PREC_BF16X3) return walk_tiles_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
+    if (walk_small_supported(N, C) && aligned16p(x)) return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
+    walk_affinity_kernel<<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     if (T < 3) {   // model.py:33-35: empty loop, loss = 0
         walk_zero_loss_kernel<<<1, 1, 0, st>>>(loss);
         CRW_LAUNCH_RET();
         return CRW_OK;
     }
-    if (tc) walk_chain_kernel<true><<<dim3(2, B), kWT, kTcSmemBytes, st>>>(ws, B, T, N, C);
-    else walk_chain_kernel<false><<<dim3(2, B), kWT, 0, st>>>(ws, B, T, N, C);
+    walk_chain_kernel<<<dim3(2, B), kWT, 0, st>>>(ws, B, T, N, C);
     CRW_LAUNCH_RET();
-    if (tc) walk_cycle_kernel<true><<<dim3(T - 2, B), kWT, kTcSmemBytes, st>>>(ws, B, T, N, C);
-    else walk_cycle_kernel<false><<<dim3(T - 2, B), kWT, 0, st>>>(ws, B, T, N, C);
+    walk_cycle_kernel<<<dim3(T - 2, B), kWT, 0, st>>>(ws, B, T, N, C);
     CRW_LAUNCH_RET();
     walk_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, B, T, N, C);
     CRW_LAUNCH_RET();
@@ -493,28 +431,20 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     const float* ws = align256(const_cast<void*>(saved));
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
-    const bool tc = precision == CRW_PREC_BF16X3;
-    if (!tc && walk_small_supported(N, C) && aligned16p(x))
+    if (precision == CRW_PREC_BF16X3) return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
+    if (walk_small_supported(N, C) && aligned16p(x))
         return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
-    if (tc) {
-        int rc = walk_tc_opt_in();
-        if (rc != CRW_OK) return rc;
-    }
     if (T >= 3) {
-        if (tc) walk_bwd_own_kernel<true><<<dim3(T - 2, B, 2), kWT, kTcSmemBytes, st>>>(ws, sc, dloss, B, T, N, C);
-        else walk_bwd_own_kernel<false><<<dim3(T - 2, B, 2), kWT, 0, st>>>(ws, sc, dloss, B, T, N, C);
+        walk_bwd_own_kernel<<<dim3(T - 2, B, 2), kWT, 0, st>>>(ws, sc, dloss, B, T, N, C);
         CRW_LAUNCH_RET();
         if (T >= 4) {
-            if (tc) walk_bwd_chain_kernel<true><<<dim3(2, B), kWT, kTcSmemBytes, st>>>(ws, sc, B, T, N, C);
-            else walk_bwd_chain_kernel<false><<<dim3(2, B), kWT, 0, st>>>(ws, sc, B, T, N, C);
+            walk_bwd_chain_kernel<<<dim3(2, B), kWT, 0, st>>>(ws, sc, B, T, N, C);
             CRW_LAUNCH_RET();
         }
     }
-    if (tc) walk_bwd_dA_kernel<true><<<dim3(T - 1, B), kWT, 2 * N * sizeof(float) + kTcSmemBytes, st>>>(ws, sc, dA_or_null, B, T, N, C);
-    else walk_bwd_dA_kernel<false><<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(ws, sc, dA_or_null, B, T, N, C);
+    walk_bwd_dA_kernel<<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(ws, sc, dA_or_null, B, T, N, C);
     CRW_LAUNCH_RET();
-    if (tc) walk_bwd_dx_kernel<true><<<dim3(T, B), kWT, kTcSmemBytes, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
-    else walk_bwd_dx_kernel<false><<<dim3(T, B), kWT, 0, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
+    walk_bwd_dx_kernel<<<dim3(T, B), kWT, 0, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }

@@ -1,4 +1,4 @@
-// walk_tc.cuh -- CTA-wide tensor-core GEMM for the generic walk path (any N): tcgen05.mma, TMEM accumulator.
+// walk_tc.cuh -- CTA-wide tensor-core GEMM tile for the walk (any N): tcgen05.mma, TMEM accumulator.
 //
 // C[128 x 128 tile] = op(A) * op(B) with fp32 operands in global memory.  The operands of the walk are produced in
 // fp32 by the previous stage's epilogue (softmax, chain products, adjoints), some of them consumed transposed, so
@@ -6,7 +6,7 @@
 // 16-byte chunks written straight into the UMMA K-major SWIZZLE_128B layout (chunk index xor row%8), double
 // buffered so that staging chunk c+1 overlaps the 12 MMAs (3 passes hi.hi, hi.lo, lo.hi x 4 k-steps) of chunk c.
 // The accumulator stays in TMEM across the whole K loop and is read back once with tcgen05.ld for the epilogue
-// (scale / softmax inputs / accumulate), which is the same lambda the fp32 FMA path uses.
+// (scale / accumulate).  Used by walk_tc_tiles.cu, one CTA per 128 x 128 output tile.
 #pragma once
 #include "tc_common.cuh"
 
@@ -92,61 +92,67 @@ __device__ __forceinline__ void tc_stage_operand(uint8_t* hi_base, uint8_t* lo_b
     }
 }
 
-// C = op(A) op(B):  !TA: A[m*lda+k], TA: A[k*lda+m];  !TB: B[k*ldb+n], TB: B[n*ldb+k].   epi(m, n, value).
+// One 128 x 128 output tile at (m0, n0):  C = op(A) op(B),  !TA: A[m*lda+k], TA: A[k*lda+m];  !TB: B[k*ldb+n], TB: B[n*ldb+k].
+// epi(m, n, value) is called once per valid element by the thread that owns TMEM lane m.
 template <bool TA, bool TB, class Epi>
-__device__ __forceinline__ void cta_gemm_tc(const float* A, int lda, const float* B, int ldb, int M, int Nn, int K,
-                                            const float* kscale, TcGemmCtx& cx, Epi epi) {
+__device__ __forceinline__ void cta_gemm_tc_tile(const float* A, int lda, const float* B, int ldb, int M, int Nn, int K,
+                                                 const float* kscale, int m0, int n0, TcGemmCtx& cx, Epi epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t idesc = tc::umma_idesc_bf16(kTcTile, kTcTile);
     const int nchunks = (K + kTcKChunk - 1) / kTcKChunk;
-    for (int m0 = 0; m0 < M; m0 += kTcTile)
-        for (int n0 = 0; n0 < Nn; n0 += kTcTile) {
-            int last_stage = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c & 1;
-                if (cx.uses[s] > 0) tc::mbar_wait(&cx.bar[s], (cx.uses[s] - 1) & 1);   // stage free again
-                uint8_t* st = cx.buf + s * kTcStageBytes;
-                tc_stage_operand<!TA>(st, st + kTcOperandBytes, A, lda, m0, M, c * kTcKChunk, K, nullptr);
-                tc_stage_operand<TB>(st + 2 * kTcOperandBytes, st + 3 * kTcOperandBytes, B, ldb, n0, Nn, c * kTcKChunk, K, kscale);
-                tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    tc::tc_fence_after();
-                    const uint32_t a0 = tc::smem_u32(st), b0 = a0 + 2 * kTcOperandBytes;
-#pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t ap = a0 + ((pass == 2) ? kTcOperandBytes : 0), bp = b0 + ((pass == 1) ? kTcOperandBytes : 0);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            tc::umma_bf16_ss(cx.tmem, tc::umma_smem_desc_k128(ap + ks * 32), tc::umma_smem_desc_k128(bp + ks * 32),
-                                             idesc, (c | pass | ks) ? 1u : 0u);
-                    }
-                    tc::umma_commit(&cx.bar[s]);
-                }
-                cx.uses[s]++;
-                last_stage = s;
-            }
-            tc::mbar_wait(&cx.bar[last_stage], (cx.uses[last_stage] - 1) & 1);   // commit tracks every earlier MMA too
+    int last_stage = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c & 1;
+        if (cx.uses[s] > 0) tc::mbar_wait(&cx.bar[s], (cx.uses[s] - 1) & 1);   // stage free again
+        uint8_t* st = cx.buf + s * kTcStageBytes;
+        tc_stage_operand<!TA>(st, st + kTcOperandBytes, A, lda, m0, M, c * kTcKChunk, K, nullptr);
+        tc_stage_operand<TB>(st + 2 * kTcOperandBytes, st + 3 * kTcOperandBytes, B, ldb, n0, Nn, c * kTcKChunk, K, kscale);
+        tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (threadIdx.x == 0) {
             tc::tc_fence_after();
-            const int g = warp & 3, half = warp >> 2;
-            const int m = m0 + g * 32 + lane;
+            const uint32_t a0 = tc::smem_u32(st), b0 = a0 + 2 * kTcOperandBytes;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float v[32];
-                const int cb = half * 64 + ch * 32;
-                tc::tmem_ld_32x32b_x32(cx.tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)cb, v);
-                tc::tmem_ld_wait();
-                if (m < M) {
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ap = a0 + ((pass == 2) ? kTcOperandBytes : 0), bp = b0 + ((pass == 1) ? kTcOperandBytes : 0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = n0 + cb + i;
-                        if (n < Nn) epi(m, n, v[i]);
-                    }
-                }
+                for (int ks = 0; ks < 4; ++ks)
+                    tc::umma_bf16_ss(cx.tmem, tc::umma_smem_desc_k128(ap + ks * 32), tc::umma_smem_desc_k128(bp + ks * 32),
+                                     idesc, (c | pass | ks) ? 1u : 0u);
             }
-            tc::tc_fence_before();
-            __syncthreads();     // TMEM may be overwritten by the next tile's first MMA; epilogue stores visible CTA-wide
+            tc::umma_commit(&cx.bar[s]);
         }
+        cx.uses[s]++;
+        last_stage = s;
+    }
+    tc::mbar_wait(&cx.bar[last_stage], (cx.uses[last_stage] - 1) & 1);   // commit tracks every earlier MMA too
+    tc::tc_fence_after();
+    const int g = warp & 3, half = warp >> 2;
+    const int m = m0 + g * 32 + lane;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        float v[32];
+        const int cb = half * 64 + ch * 32;
+        tc::tmem_ld_32x32b_x32(cx.tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)cb, v);
+        tc::tmem_ld_wait();
+        if (m < M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = n0 + cb + i;
+                if (n < Nn) epi(m, n, v[i]);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();     // TMEM may be overwritten by the next tile's first MMA; epilogue stores visible CTA-wide
+}
+
+// whole matrix, tiles walked by this one CTA (monolithic kernels)
+template <bool TA, bool TB, class Epi>
+__device__ __forceinline__ void cta_gemm_tc(const float* A, int lda, const float* B, int ldb, int M, int Nn, int K,
+                                            const float* kscale, TcGemmCtx& cx, Epi epi) {
+    for (int m0 = 0; m0 < M; m0 += kTcTile)
+        for (int n0 = 0; n0 < Nn; n0 += kTcTile) cta_gemm_tc_tile<TA, TB>(A, lda, B, ldb, M, Nn, K, kscale, m0, n0, cx, epi);
 }
 
 }  // namespace crw
