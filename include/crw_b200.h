@@ -65,7 +65,7 @@ int crw_l2_normalize(const float* x, int64_t rows, int C, float* out, void* stre
  *   saved    workspace of crw_walk_saved_bytes(): state kept for the backward pass
  * T < 3 gives loss = 0 exactly as the reference's empty loop (model.py:33-35).
  * ---------------------------------------------------------------------------------- */
-size_t crw_walk_saved_bytes(int B, int T, int N, int C);
+size_t crw_walk_saved_bytes(int B, int T, int N, int C, int precision);
 int crw_walk_forward(const float* x, int B, int T, int N, int C, float tau, int precision,
                      float* loss, float* A_or_null, void* saved, size_t saved_bytes, void* stream);
 
@@ -77,7 +77,7 @@ int crw_walk_forward(const float* x, int B, int T, int N, int C, float tau, int 
  *   dx       [B,T,N,C] out: gradient w.r.t. the raw encoder output
  *   scratch  workspace of crw_walk_backward_scratch_bytes()
  * ---------------------------------------------------------------------------------- */
-size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C);
+size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C, int precision);
 int crw_walk_backward(const float* x, const void* saved, size_t saved_bytes, const float* dloss,
                       const float* dA_or_null, int B, int T, int N, int C, float tau, int precision, float* dx,
                       void* scratch, size_t scratch_bytes, void* stream);

@@ -21,9 +21,9 @@ SIGNATURES = {
     "crw_built_arch": (_c_int, []),
     "crw_error_string": (ctypes.c_char_p, [_c_int]),
     "crw_l2_normalize": (_c_int, [_vp, ctypes.c_int64, _c_int, _vp, _vp]),
-    "crw_walk_saved_bytes": (_c_sz, [_c_int] * 4),
+    "crw_walk_saved_bytes": (_c_sz, [_c_int] * 5),
     "crw_walk_forward": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int, _vp, _vp, _vp, _c_sz, _vp]),
-    "crw_walk_backward_scratch_bytes": (_c_sz, [_c_int] * 4),
+    "crw_walk_backward_scratch_bytes": (_c_sz, [_c_int] * 5),
     "crw_walk_backward": (_c_int, [_vp, _vp, _c_sz, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int, _vp, _vp,
                                    _c_sz, _vp]),
     "crw_affinity_topk": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_int, _c_int, _vp,

@@ -372,21 +372,26 @@ int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, fl
                        cudaStream_t st);
 int walk_tiles_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
                         float tau, float* dx, float* sc, cudaStream_t st);
+size_t walk_tiles_saved_extra_bytes(int B, int T, int N, int C);     // bf16 operand planes kept next to the fp32 state
+size_t walk_tiles_scratch_extra_bytes(int B, int T, int N, int C);
 }  // namespace crw
 
 using namespace crw;
 
 static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C) {
+extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C, int precision) {
     if (B < 1 || T < 2 || N < 1 || C < 1) return 0;
-    return WalkLayout(B, T, N, C).total * sizeof(float) + 256;
+    size_t b = WalkLayout(B, T, N, C).total * sizeof(float) + 256;
+    if (precision == CRW_PREC_BF16X3) b += walk_tiles_saved_extra_bytes(B, T, N, C) + 256;
+    return b;
 }
 
-extern "C" size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C) {
-    (void)C;
+extern "C" size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C, int precision) {
     if (B < 1 || T < 2 || N < 1) return 0;
-    return BwdLayout(B, T, N).total * sizeof(float) + 256;
+    size_t b = BwdLayout(B, T, N).total * sizeof(float) + 256;
+    if (precision == CRW_PREC_BF16X3) b += walk_tiles_scratch_extra_bytes(B, T, N, C) + 256;
+    return b;
 }
 
 static inline float* align256(void* p) {
@@ -397,7 +402,7 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
                                 float* A_or_null, void* saved, size_t saved_bytes, void* stream) {
     if (!x || !loss || B < 1 || T < 2 || N < 1 || C < 1 || !(tau > 0.0f)) return CRW_ERR_INVALID;
     if (precision != CRW_PREC_FP32 && precision != CRW_PREC_BF16X3) return CRW_ERR_UNSUPPORTED;
-    if (!saved || saved_bytes < crw_walk_saved_bytes(B, T, N, C)) return CRW_ERR_WORKSPACE;
+    if (!saved || saved_bytes < crw_walk_saved_bytes(B, T, N, C, precision)) return CRW_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = align256(saved);
     const float inv_tau = 1.0f / tau;
@@ -425,8 +430,8 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
                                  float* dx, void* scratch, size_t scratch_bytes, void* stream) {
     if (!x || !saved || !dloss || !dx || B < 1 || T < 2 || N < 1 || C < 1 || !(tau > 0.0f)) return CRW_ERR_INVALID;
     if (precision != CRW_PREC_FP32 && precision != CRW_PREC_BF16X3) return CRW_ERR_UNSUPPORTED;
-    if (saved_bytes < crw_walk_saved_bytes(B, T, N, C)) return CRW_ERR_WORKSPACE;
-    if (!scratch || scratch_bytes < crw_walk_backward_scratch_bytes(B, T, N, C)) return CRW_ERR_WORKSPACE;
+    if (saved_bytes < crw_walk_saved_bytes(B, T, N, C, precision)) return CRW_ERR_WORKSPACE;
+    if (!scratch || scratch_bytes < crw_walk_backward_scratch_bytes(B, T, N, C, precision)) return CRW_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const float* ws = align256(const_cast<void*>(saved));
     float* sc = align256(scratch);

@@ -69,26 +69,38 @@ __device__ __forceinline__ void tc_store_chunk(uint8_t* hi_base, uint8_t* lo_bas
 // Stage rows [r0, r0+128) x k in [k0, k0+64) of the logical matrix X(r,k):
 //   KCONTIG: X(r,k) = P[r*ld + k]   (k contiguous in memory)      else: X(r,k) = P[k*ld + r]   (r contiguous)
 // rows >= R and k >= K are zero; kscale (optional) multiplies X(r,k) by kscale[k].
+// Split in a load half and a store half so that a caller can put ALL global loads of a k-chunk (both operands, 64
+// per thread) in flight before the first conversion / shared store: the staging is latency bound otherwise.
 template <bool KCONTIG>
-__device__ __forceinline__ void tc_stage_operand(uint8_t* hi_base, uint8_t* lo_base, const float* P, int ld, int r0, int R, int k0,
-                                                 int K, const float* kscale) {
+__device__ __forceinline__ void tc_stage_load(float (&v)[4][8], const float* __restrict__ P, int ld, int r0, int R, int k0, int K,
+                                              const float* __restrict__ kscale) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int id = threadIdx.x + it * 256;            // 1024 chunks of 8 elements
         const int r = KCONTIG ? (id >> 3) : (id & 127);
         const int c = KCONTIG ? (id & 7) : (id >> 7);
         const int gr = r0 + r, gk = k0 + c * 8;
-        float v[8];
+        const float* src = KCONTIG ? P + (size_t)gr * ld + gk : P + (size_t)gk * ld + gr;
+        const size_t estride = KCONTIG ? 1 : (size_t)ld;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float x = 0.0f;
             if (gr < R && gk + e < K) {
-                x = KCONTIG ? P[(size_t)gr * ld + gk + e] : P[(size_t)(gk + e) * ld + gr];
-                if (kscale) x *= kscale[gk + e];
+                x = __ldg(src + e * estride);
+                if (kscale) x *= __ldg(kscale + gk + e);
             }
-            v[e] = x;
+            v[it][e] = x;
         }
-        tc_store_chunk(hi_base, lo_base, r, c, v);
+    }
+}
+template <bool KCONTIG>
+__device__ __forceinline__ void tc_stage_store(uint8_t* hi_base, uint8_t* lo_base, const float (&v)[4][8]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int id = threadIdx.x + it * 256;
+        const int r = KCONTIG ? (id >> 3) : (id & 127);
+        const int c = KCONTIG ? (id & 7) : (id >> 7);
+        tc_store_chunk(hi_base, lo_base, r, c, v[it]);
     }
 }
 
@@ -105,8 +117,13 @@ __device__ __forceinline__ void cta_gemm_tc_tile(const float* A, int lda, const 
         const int s = c & 1;
         if (cx.uses[s] > 0) tc::mbar_wait(&cx.bar[s], (cx.uses[s] - 1) & 1);   // stage free again
         uint8_t* st = cx.buf + s * kTcStageBytes;
-        tc_stage_operand<!TA>(st, st + kTcOperandBytes, A, lda, m0, M, c * kTcKChunk, K, nullptr);
-        tc_stage_operand<TB>(st + 2 * kTcOperandBytes, st + 3 * kTcOperandBytes, B, ldb, n0, Nn, c * kTcKChunk, K, kscale);
+        {
+            float va[4][8], vb[4][8];
+            tc_stage_load<!TA>(va, A, lda, m0, M, c * kTcKChunk, K, nullptr);
+            tc_stage_load<TB>(vb, B, ldb, n0, Nn, c * kTcKChunk, K, kscale);
+            tc_stage_store<!TA>(st, st + kTcOperandBytes, va);
+            tc_stage_store<TB>(st + 2 * kTcOperandBytes, st + 3 * kTcOperandBytes, vb);
+        }
         tc::fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (threadIdx.x == 0) {

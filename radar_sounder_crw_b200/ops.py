@@ -60,7 +60,7 @@ def walk_loss(x: Tensor, tau: float, need_A: bool, precision: int) -> Tuple[Tens
     L = _lib.lib()
     loss = torch.empty((), device=x.device, dtype=torch.float32)
     A = torch.empty((B, T - 1, N, N) if need_A else (0,), device=x.device, dtype=torch.float32)
-    nbytes = L.crw_walk_saved_bytes(B, T, N, C)
+    nbytes = L.crw_walk_saved_bytes(B, T, N, C, int(precision))
     saved = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
     with torch.cuda.device(x.device):
         _lib.check(L.crw_walk_forward(_p(x), B, T, N, C, float(tau), int(precision), _p(loss), _p(A), _p(saved),
@@ -83,7 +83,7 @@ def walk_loss_backward(x: Tensor, saved: Tensor, dloss: Tensor, dA: Tensor, tau:
     dloss = _chk(dloss.reshape(1), "dloss")
     dA_c = _chk(dA, "dA") if dA.numel() else None
     dx = torch.empty_like(x)
-    sbytes = L.crw_walk_backward_scratch_bytes(B, T, N, C)
+    sbytes = L.crw_walk_backward_scratch_bytes(B, T, N, C, int(precision))
     scratch = torch.empty(sbytes, device=x.device, dtype=torch.uint8)
     with torch.cuda.device(x.device):
         _lib.check(L.crw_walk_backward(_p(x), _p(saved), saved.numel(), _p(dloss), _p(dA_c), B, T, N, C, float(tau),
