@@ -48,7 +48,7 @@ def test_version_and_error_strings(pkg):
     assert "workspace" in pkg._lib.error_string(-4)
     # size queries are pure host functions
     assert L.crw_walk_saved_bytes(32, 10, 47, 128, 0) > 32 * 9 * 47 * 47 * 4 * 6
-    assert L.crw_walk_saved_bytes(32, 10, 47, 128, 1) > L.crw_walk_saved_bytes(32, 10, 47, 128, 0)   # + bf16 operand planes
+    assert L.crw_walk_saved_bytes(32, 10, 47, 128, 1) >= L.crw_walk_saved_bytes(32, 10, 47, 128, 0)
     assert L.crw_walk_saved_bytes(0, 10, 47, 128, 0) == 0
     assert L.crw_labelprop_scratch_bytes(1, 1250, 49, 128, 10, 0, 1, 0) > 1250 * 49 * 128 * 4
 
