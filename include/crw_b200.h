@@ -157,6 +157,9 @@ int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W
 int crw_debug_umma_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 /* same product with A parked in TMEM by the threads (tcgen05.st) and read by the "TS" form of tcgen05.mma */
 int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
+/* K = 64 product with MN-major operands: A is At[64][128] when a_mn else A[128][64]; B is Bkn[64][BN] when b_mn else
+ * Bt[BN][64]; BN in {64, 128}.  Pins the MN-major shared-memory descriptors (transposed operands without a copy). */
+int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a_mn, int b_mn, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,9 +106,26 @@ __device__ __forceinline__ uint64_t umma_smem_desc_k128(uint32_t smem_addr_bytes
     d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
+// MN-major operand tile: stored as [k rows][64 MN-elements] (128-byte rows, the element index along M or N is the
+// contiguous one), TMA SWIZZLE_128B.  lbo = byte distance between consecutive groups of 64 MN-elements, sbo = byte
+// distance between consecutive groups of 8 k-rows (1024 when the k-rows of one MN-group are contiguous).
+__device__ __forceinline__ uint64_t umma_smem_desc_mn128(uint32_t smem_addr_bytes, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr_bytes & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // kind::f16, A/B = bf16 K-major, D = fp32, shape M x N (K = 16 per instruction)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// same with per-operand majorness: bit 15 = A is MN-major, bit 16 = B is MN-major
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_major(int M, int N, bool a_mn, bool b_mn) {
+    return umma_idesc_bf16(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread

@@ -35,6 +35,22 @@ int make_tmap_bf16_k64(CUtensorMap* out, const void* base, uint64_t rows, uint64
     return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
 }
 
+// 2-D bf16 row-major matrix [rows][cols], box = [box_rows][box_cols elements] (box_cols * 2 bytes <= 128), SWIZZLE_128B
+int make_tmap_bf16_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRW_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (cols * 2) % 16 || box_rows < 1 || box_rows > 256 || box_cols * 2 > 128)
+        return CRW_ERR_ALIGN;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
+}
+
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, float* out) {
     extern __shared__ uint8_t smem_raw[];
@@ -155,9 +171,84 @@ umma_ts_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __grid_consta
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
+// MN-major operands: out[128 x BN] = A * B with A given as At[K=64][128] (M contiguous) when a_mn, else A[128][64];
+// and B given as Bkn[64][BN] (N contiguous) when b_mn, else Bt[BN][64].  Pins the MN-major descriptors (LBO / SBO /
+// major bits) so that transposed operands need no second copy.
+int make_tmap_bf16_box(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+
+__global__ void __launch_bounds__(128, 1)
+umma_mn_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, int a_mn, int b_mn,
+                        float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;               // K-major: [128 rows][128 B] = 16 KB ; MN-major: 2 groups x [64 k][128 B] = 16 KB
+    uint8_t* sB = smem + 16384;       // K-major: [BN rows][128 B]          ; MN-major: BN/64 groups x [64 k][128 B]
+    __shared__ uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(&bar_full, (uint32_t)((128 + BN) * 128));
+        if (a_mn) { for (int g = 0; g < 2; ++g) tc::tma_load_2d(sA + g * 8192, &mapA, g * 64, 0, &bar_full); }   // box: 64 m x 64 k
+        else tc::tma_load_2d(sA, &mapA, 0, 0, &bar_full);                                                        // box: 64 k x 128 m
+        if (b_mn) { for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(sB + g * 8192, &mapB, g * 64, 0, &bar_full); }
+        else tc::tma_load_2d(sB, &mapB, 0, 0, &bar_full);
+        tc::mbar_wait(&bar_full, 0);
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::umma_idesc_bf16_major(128, BN, a_mn != 0, b_mn != 0);
+        for (int k = 0; k < 4; ++k) {       // K = 64 = 4 k-steps of 16
+            const uint64_t ad = a_mn ? tc::umma_smem_desc_mn128(tc::smem_u32(sA) + k * 2048, 8192, 1024)
+                                     : tc::umma_smem_desc_k128(tc::smem_u32(sA) + k * 32);
+            const uint64_t bd = b_mn ? tc::umma_smem_desc_mn128(tc::smem_u32(sB) + k * 2048, 8192, 1024)
+                                     : tc::umma_smem_desc_k128(tc::smem_u32(sB) + k * 32);
+            tc::umma_bf16_ss(tmem_base, ad, bd, idesc, k ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar_mma, 0);
+    tc::tc_fence_after();
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        float* o = out + (size_t)(warp * 32 + lane) * BN + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (c + i < BN) o[i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
 }  // namespace crw
 
 using namespace crw;
+
+extern "C" int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a_mn, int b_mn, float* out, void* stream) {
+    if (!A_bf16 || !B_bf16 || !out || (BN != 64 && BN != 128)) return CRW_ERR_INVALID;
+    CUtensorMap mA, mB;
+    // K-major: matrix [rows][64 k], box 64 k x rows.  MN-major: matrix [64 k][mn], box 64 mn x 64 k.
+    int rc = a_mn ? make_tmap_bf16_box(&mA, A_bf16, 64, 128, 64, 64) : make_tmap_bf16_box(&mA, A_bf16, 128, 64, 128, 64);
+    if (rc != CRW_OK) return rc;
+    rc = b_mn ? make_tmap_bf16_box(&mB, B_bf16, 64, (uint64_t)BN, 64, 64) : make_tmap_bf16_box(&mB, B_bf16, (uint64_t)BN, 64, (uint32_t)BN, 64);
+    if (rc != CRW_OK) return rc;
+    const size_t smem = 1024 + 16384 + (size_t)BN * 128;
+    CRW_CUDA_RET(cudaFuncSetAttribute(umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_mn_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mA, mB, BN, a_mn, b_mn, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
 
 extern "C" int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream) {
     if (!A_bf16 || !B_bf16 || !out || BN < 16 || BN > 256 || (BN % 16)) return CRW_ERR_INVALID;

@@ -28,6 +28,23 @@ def test_umma_selftest_matches_torch(pkg, BN):
     assert err < 1e-3, err   # bf16 products are exact in fp32; only the accumulation order differs
 
 
+@pytest.mark.parametrize("BN,a_mn,b_mn", [(64, 0, 0), (128, 0, 1), (64, 1, 0), (128, 1, 1)])
+def test_umma_mn_major_selftest_matches_torch(pkg, BN, a_mn, b_mn):
+    """MN-major (transposed) operands straight from a row-major [K][MN] matrix: pins LBO / SBO / the major bits."""
+    torch.manual_seed(7 * BN + a_mn + 2 * b_mn)
+    A = torch.randn(128, 64, device="cuda").bfloat16()          # logical A [M=128][K=64]
+    B = torch.randn(64, BN, device="cuda").bfloat16()           # logical B [K=64][N=BN]
+    A_in = A.t().contiguous() if a_mn else A                    # At [64][128]  vs  A [128][64]
+    B_in = B if b_mn else B.t().contiguous()                    # Bkn [64][BN]  vs  Bt [BN][64]
+    out = torch.full((128, BN), float("nan"), device="cuda")
+    L = pkg._lib.lib()
+    pkg._lib.check(L.crw_debug_umma_mn_gemm(A_in.data_ptr(), B_in.data_ptr(), BN, a_mn, b_mn, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "crw_debug_umma_mn_gemm")
+    torch.cuda.synchronize()
+    err = (out - A.float() @ B.float()).abs().max().item()
+    assert err < 1e-3, err
+
+
 @pytest.mark.parametrize("BN", [16, 64, 256])
 def test_umma_ts_selftest_matches_torch(pkg, BN):
     """A operand parked in TMEM with tcgen05.st and read by the TS form of tcgen05.mma: pins the A-in-TMEM layout."""
