@@ -1,192 +1,424 @@
 // walk_tc_tiles.cu -- tile-parallel tensor-core walk (precision = CRW_PREC_BF16X3), any N.
 //
-// Same algorithm, workspace layout and reference mapping as walk_f32.cu (src/model.py:22-46 and its autograd), but
-// every GEMM is a grid of independent 128 x 128 output tiles (one CTA each: tcgen05.mma bf16x3, TMEM accumulator,
-// walk_tc.cuh) and the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in
-// separate small kernels.  The L / R chains and their adjoints are one launch per step (both chains in one grid),
-// so the only serialisation left is the algorithm's own: 2(T-3) dependent products forward and backward.
+// Same algorithm and reference mapping as walk_f32.cu (src/model.py:22-46 and its autograd).  Here
+//   * every GEMM is a grid of independent 128 x 128 output tiles, one CTA each: tcgen05.mma kind::f16 on
+//     error-compensated bf16 pairs (x = hi + lo; passes hi.hi, hi.lo, lo.hi), fp32 accumulator in TMEM;
+//   * every matrix that is ever a GEMM operand is kept, next to its fp32 copy, as two ROW-MAJOR bf16 planes (hi, lo;
+//     row pitch padded to 8 elements, pads zero), written by the epilogue that produces it with 16-byte stores;
+//   * an operand used as stored is a K-major tile, an operand used transposed is an MN-major tile of the SAME plane
+//     (UMMA majorness bits + LBO/SBO descriptors, pinned by crw_debug_umma_mn_gemm) -- no transposed copies;
+//   * staging is sixteen 16-byte cp.async per thread per 64-wide k-chunk straight into the SWIZZLE_128B layout, three
+//     stages deep; the MMAs of chunk c are queued before the CTA waits for the stage of chunk c-1 to drain;
+//   * the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in small kernels;
+//   * the L / R chains and their adjoints are one launch per step (both chains in one grid): the only serialisation
+//     left is the algorithm's own 2(T-3) dependent products forward and backward.
 #include "common.cuh"
 #include "walk_layout.cuh"
-#include "walk_tc.cuh"
+#include "tc_common.cuh"
 
 namespace crw {
 
 constexpr int kTT = 256;
+typedef __nv_bfloat16 bf16;
+
+constexpr int kWTile = 128;                       // output tile
+constexpr int kWChunk = 64;                       // k elements per stage
+constexpr int kWOperand = kWTile * 128;           // one operand plane of one stage: 16 KB (K-major and MN-major alike)
+constexpr int kWStage = 4 * kWOperand;            // A_hi, A_lo, B_hi, B_lo
+constexpr int kWStages = 3;
+constexpr int kWSmem = kWStages * kWStage + 1024;
+
+struct Dims { int B, T, N, C; };
+
+// ---- bf16 arenas ------------------------------------------------------------------------------------------
+enum { kFamS = 0, kFamSp, kFamL, kFamR, kFamG, kNumSavedFam };      // saved arena (forward state)
+enum { kFamDL = 0, kFamDR, kFamDA, kNumBwdFam };                    // scratch arena (backward state)
+
+struct TcArena {
+    int P;                       // row pitch of N x N planes (N rounded up to 8 elements = 16 bytes)
+    int CP;                      // row pitch of the E planes (C rounded up likewise)
+    size_t plane;                // B*(T-1)*N*P elements: one plane of one family
+    size_t E, fam0, total;       // offsets in bf16 elements
+    __host__ __device__ TcArena(const Dims& d, int nfam, bool with_E) {
+        P = (d.N + 7) & ~7;
+        CP = (d.C + 7) & ~7;
+        plane = (size_t)d.B * (d.T - 1) * d.N * P;
+        size_t o = 0;
+        E = o; if (with_E) o += 2 * (size_t)d.B * d.T * d.N * CP;            // hi, lo   [B*T*N][CP]
+        o = (o + 63) & ~size_t(63);
+        fam0 = o; o += (size_t)nfam * 2 * plane;                             // hi, lo per family
+        total = o;
+    }
+};
+struct Mat2 { bf16 *hi, *lo; int P; };
+__device__ __forceinline__ Mat2 mat2(bf16* arena, const TcArena& a, const Dims& d, int fam, int b, int t) {
+    bf16* base = arena + a.fam0 + (size_t)fam * 2 * a.plane + ((size_t)b * (d.T - 1) + t) * d.N * a.P;
+    return Mat2{base, base + a.plane, a.P};
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void emit_one(const Mat2& mt, int r, int c, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    mt.hi[(size_t)r * mt.P + c] = h;
+    mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+// value for n < N, zero for the pad columns N <= n < pitch
+__device__ __forceinline__ void emit_pad(const Mat2& mt, int r, int n, float v, int N) {
+    if (n < mt.P) emit_one(mt, r, n, n < N ? v : 0.0f);
+}
+__device__ __forceinline__ void zero_row_pad(const Mat2& mt, int r, int N, int lane) {
+    for (int c = N + lane; c < mt.P; c += 32) { mt.hi[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); }
+}
+
+// ---- one 128 x 128 tile from bf16 planes -----------------------------------------------------------------
+// K-major use: logical X(r,k) = plane[r*pitch + k]; MN-major use: X(r,k) = plane[k*pitch + r].  `rows` = valid r extent.
+struct OpSrc { const bf16 *hi, *lo; int pitch, rows; };
+
+struct TcCtx3 { uint8_t* buf; uint64_t* bar; uint32_t tmem; uint32_t uses[kWStages]; };
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+template <bool MN>
+__device__ __forceinline__ void stage_operand_async(uint32_t dst_hi, uint32_t dst_lo, const OpSrc& S, int r0, int k0, int K) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int id = threadIdx.x + it * kTT;          // 1024 chunks of 8 elements
+        size_t so;
+        uint32_t off;
+        bool valid;
+        if (!MN) {
+            const int r = id >> 3, c = id & 7, kk = k0 + c * 8;
+            valid = (r0 + r) < S.rows && kk < K;
+            so = (size_t)(r0 + r) * S.pitch + kk;
+            off = (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ (r & 7)) & 7) << 4));
+        } else {
+            const int g = id >> 9, kk = (id >> 3) & 63, c = id & 7, r = r0 + g * 64 + c * 8;
+            valid = (k0 + kk) < K && r < ((S.rows + 7) & ~7);
+            so = (size_t)(k0 + kk) * S.pitch + r;
+            off = (uint32_t)((g << 13) + (kk << 7) + (((c ^ (kk & 7)) & 7) << 4));
+        }
+        if (!valid) so = 0;
+        cp_async16_zfill(dst_hi + off, S.hi + so, valid);
+        cp_async16_zfill(dst_lo + off, S.lo + so, valid);
+    }
+}
+
+// epi(m, n, value) is called for every row m < Mvalid of the tile and every column n of the tile (the caller clips n
+// against its own extents and pitch).  The accumulator goes TMEM -> registers (thread = row) -> shared memory ->
+// registers (warp = row, lane = column) so that every global access of the epilogue is coalesced.
+constexpr int kEpPitch = 132;      // floats; 528-byte rows: 16-byte aligned, conflict-free for the v4 stores of phase 1
+template <bool A_MN, bool B_MN, class Epi>
+__device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t idesc = tc::umma_idesc_bf16_major(kWTile, kWTile, A_MN, B_MN);
+    const int nchunks = (K + kWChunk - 1) / kWChunk;
+    auto issue = [&](int c) {
+        const int s = c % kWStages;
+        if (cx.uses[s] > 0) tc::mbar_wait(&cx.bar[s], (cx.uses[s] - 1) & 1);      // MMAs that read this stage retired
+        const uint32_t base = tc::smem_u32(cx.buf + s * kWStage);
+        stage_operand_async<A_MN>(base, base + kWOperand, A, m0, c * kWChunk, K);
+        stage_operand_async<B_MN>(base + 2 * kWOperand, base + 3 * kWOperand, B, n0, c * kWChunk, K);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    if (nchunks > 1) issue(1);
+    int last_stage = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % kWStages;
+        if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        tc::fence_proxy_async();       // cp.async (generic proxy) writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tc::tc_fence_after();
+            const uint32_t a0 = tc::smem_u32(cx.buf + s * kWStage), b0 = a0 + 2 * kWOperand;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ap = a0 + ((pass == 2) ? kWOperand : 0), bp = b0 + ((pass == 1) ? kWOperand : 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
+                    const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
+                    tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (c | pass | ks) ? 1u : 0u);
+                }
+            }
+            tc::umma_commit(&cx.bar[s]);
+        }
+        cx.uses[s]++;
+        last_stage = s;
+        if (c + 2 < nchunks) issue(c + 2);     // its stage held chunk c-1: the wait overlaps the MMAs just queued
+    }
+    tc::mbar_wait(&cx.bar[last_stage], (cx.uses[last_stage] - 1) & 1);   // commit tracks every earlier MMA too: all stages idle
+    tc::tc_fence_after();
+    float* ep = reinterpret_cast<float*>(cx.buf);
+    {
+        const int g = warp & 3, half = warp >> 2;
+        float* row = ep + (g * 32 + lane) * kEpPitch + half * 64;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            float v[32];
+            tc::tmem_ld_32x32b_x32(cx.tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(half * 64 + ch * 32), v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(row + ch * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    for (int r = warp; r < kWTile && m0 + r < Mvalid; r += 8) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) epi(m0 + r, n0 + lane + 32 * q, ep[r * kEpPitch + lane + 32 * q]);
+    }
+    __syncthreads();     // the staging buffer and TMEM are reused by the next tile
+}
 
 template <class P>
 __global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(P p) {
     extern __shared__ uint8_t tc_raw[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[kWStages];
     __shared__ uint32_t slot;
-    TcGemmCtx cx;
-    tc_ctx_init(cx, tc_raw, bars, &slot);
-    p.run((int)blockIdx.z, (int)blockIdx.y * kTcTile, (int)blockIdx.x * kTcTile, cx);
-    tc_ctx_fini(cx);
+    TcCtx3 cx;
+    cx.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+    cx.bar = bars;
+#pragma unroll
+    for (int s = 0; s < kWStages; ++s) cx.uses[s] = 0;
+    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<128>(&slot);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWStages; ++s) tc::mbar_init(&bars[s], 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    cx.tmem = slot;
+    p.run((int)blockIdx.z, (int)blockIdx.y * kWTile, (int)blockIdx.x * kWTile, cx);
+    tc::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<128>(cx.tmem);
 }
 
-struct Dims { int B, T, N, C; };
+// pointers every problem needs
+struct Ctx {
+    Dims d;
+    float* ws;        // fp32 saved workspace (WalkLayout)
+    bf16* wa;         // bf16 saved arena
+    float* sc;        // fp32 backward scratch (BwdLayout)
+    bf16* sa;         // bf16 backward arena
+};
+__device__ __forceinline__ OpSrc src_of(const Mat2& m, int rows) { return OpSrc{m.hi, m.lo, m.P, rows}; }
 
 // ---- forward problems -----------------------------------------------------------------------------------
-struct AffinityProb {       // batch = b*(T-1) + t
-    Dims d; const float* x; float* ws; float* A_out; float inv_tau;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct AffinityProb {       // batch = b*(T-1) + t :  A_t = E_t E_{t+1}^T / tau
+    Ctx c; float* A_out; float inv_tau;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
+        const TcArena ar(d, kNumSavedFam, true);
         const int b = z / (d.T - 1), t = z % (d.T - 1), N = d.N;
-        const float* x0 = x + ((size_t)b * d.T + t) * N * d.C;
-        const float* i0 = ws + lay.invn + ((size_t)b * d.T + t) * N;
-        float* At = ws + lay.mat(lay.A, b, t);
+        const size_t rows = (size_t)d.B * d.T * N, r0 = ((size_t)b * d.T + t) * N;
+        const bf16* Ehi = c.wa + ar.E;
+        const bf16* Elo = Ehi + rows * ar.CP;
+        const OpSrc A{Ehi + r0 * ar.CP, Elo + r0 * ar.CP, ar.CP, N}, Bm{Ehi + (r0 + N) * ar.CP, Elo + (r0 + N) * ar.CP, ar.CP, N};
+        float* At = c.ws + lay.mat(lay.A, b, t);
         float* Ao = A_out ? A_out + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
         const float it = inv_tau;
-        cta_gemm_tc_tile<false, true>(x0, d.C, x0 + (size_t)N * d.C, d.C, N, N, d.C, nullptr, m0, n0, cx, [&](int m, int n, float v) {
-            const float a = v * i0[m] * i0[N + n] * it;     // invn of frame t+1 follows frame t
-            At[(size_t)m * N + n] = a;
-            if (Ao) Ao[(size_t)m * N + n] = a;
+        bf_gemm_tile<false, false>(A, Bm, d.C, m0, n0, N, cx, [&](int m, int n, float v) {
+            if (n >= N) return;
+            At[(size_t)m * N + n] = v * it;
+            if (Ao) Ao[(size_t)m * N + n] = v * it;
         });
     }
 };
 
-struct ChainProb {          // batch = role*B + b ; step k
-    Dims d; float* ws; int k;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} ;  R_k = S_{k-1} R_{k-1}
+    Ctx c; int k;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
+        const TcArena ar(d, kNumSavedFam, true);
         const int role = z / d.B, b = z % d.B, N = d.N;
         if (role == 1 && k < 2) return;
-        const float* A = role == 0 ? ws + lay.mat(lay.L, b, k - 1) : ws + lay.mat(lay.S, b, k - 1);
-        const float* Bm = role == 0 ? ws + lay.mat(lay.Sp, b, k - 1) : ws + lay.mat(lay.R, b, k - 1);
-        float* out = ws + lay.mat(role == 0 ? lay.L : lay.R, b, k);
-        cta_gemm_tc_tile<false, false>(A, N, Bm, N, N, N, N, nullptr, m0, n0, cx, [&](int m, int n, float v) { out[(size_t)m * N + n] = v; });
+        const OpSrc A = src_of(mat2(c.wa, ar, d, role == 0 ? kFamL : kFamS, b, k - 1), N);      // as stored (K-major)
+        const OpSrc Bm = src_of(mat2(c.wa, ar, d, role == 0 ? kFamSp : kFamR, b, k - 1), N);    // B(k,n) = X[k][n]: MN-major
+        float* out = c.ws + lay.mat(role == 0 ? lay.L : lay.R, b, k);
+        const Mat2 om = mat2(c.wa, ar, d, role == 0 ? kFamL : kFamR, b, k);
+        bf_gemm_tile<false, true>(A, Bm, N, m0, n0, N, cx, [&](int m, int n, float v) {
+            if (n < N) out[(size_t)m * N + n] = v;
+            emit_pad(om, m, n, v, N);
+        });
     }
 };
 
-struct CycleProb {          // batch = b*K + (k-1)
-    Dims d; float* ws;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct CycleProb {          // batch = b*K + (k-1) :  M_k = L_k R_k  (raw, into the G slot)
+    Ctx c;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
+        const TcArena ar(d, kNumSavedFam, true);
         const int K = d.T - 2, b = z / K, k = z % K + 1, N = d.N;
-        float* G = ws + lay.mat(lay.G, b, k);
-        cta_gemm_tc_tile<false, false>(ws + lay.mat(lay.L, b, k), N, ws + lay.mat(lay.R, b, k), N, N, N, N, nullptr, m0, n0, cx,
-                                       [&](int m, int n, float v) { G[(size_t)m * N + n] = v; });
+        float* G = c.ws + lay.mat(lay.G, b, k);
+        bf_gemm_tile<false, true>(src_of(mat2(c.wa, ar, d, kFamL, b, k), N), src_of(mat2(c.wa, ar, d, kFamR, b, k), N), N, m0, n0, N, cx,
+                                  [&](int m, int n, float v) { if (n < N) G[(size_t)m * N + n] = v; });
     }
 };
 
 // ---- backward problems ----------------------------------------------------------------------------------
-struct OwnProb {            // batch = role*B*K + b*K + (k-1)
-    Dims d; const float* ws; float* sc; const float* dloss;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct OwnProb {            // batch = role*B*K + b*K + (k-1) :  dL_k = s G_k R_k^T ;  dR_k = s L_k^T G_k
+    Ctx c; const float* dloss;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const BwdLayout bl(d.B, d.T, d.N);
+        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int K = d.T - 2, N = d.N, role = z / (d.B * K), r = z % (d.B * K), b = r / K, k = r % K + 1;
         const float s = *dloss / ((float)d.B * (float)N * (float)N);
-        const float* G = ws + lay.mat(lay.G, b, k);
-        if (role == 0) {
-            float* o = sc + lay.mat(bl.dL, b, k);
-            cta_gemm_tc_tile<false, true>(G, N, ws + lay.mat(lay.R, b, k), N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
-        } else {
-            float* o = sc + lay.mat(bl.dR, b, k);
-            cta_gemm_tc_tile<true, false>(ws + lay.mat(lay.L, b, k), N, G, N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
-        }
+        const OpSrc G = src_of(mat2(c.wa, ar, d, kFamG, b, k), N);
+        float* o = c.sc + lay.mat(role == 0 ? bl.dL : bl.dR, b, k);
+        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, k);
+        auto epi = [&](int m, int n, float v) {
+            v *= s;
+            if (n < N) o[(size_t)m * N + n] = v;
+            emit_pad(om, m, n, v, N);
+        };
+        if (role == 0) bf_gemm_tile<false, false>(G, src_of(mat2(c.wa, ar, d, kFamR, b, k), N), N, m0, n0, N, cx, epi);   // B^T(n,k) = R[n][k]
+        else bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, k), N), G, N, m0, n0, N, cx, epi);             // A(m,k) = L[k][m], B(k,n) = G[k][n]
     }
 };
 
-struct BwdChainProb {       // batch = role*B + b ; step j: dL_j += dL_{j+1} S'_j^T ; dR_j += S_j^T dR_{j+1}
-    Dims d; const float* ws; float* sc; int j;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct BwdChainProb {       // batch = role*B + b ; dL_j += dL_{j+1} S'_j^T ; dR_j += S_j^T dR_{j+1}
+    Ctx c; int j;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const BwdLayout bl(d.B, d.T, d.N);
+        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int role = z / d.B, b = z % d.B, N = d.N;
         if (role == 1 && j < 2) return;
-        if (role == 0) {
-            float* o = sc + lay.mat(bl.dL, b, j);
-            cta_gemm_tc_tile<false, true>(sc + lay.mat(bl.dL, b, j + 1), N, ws + lay.mat(lay.Sp, b, j), N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] += v; });
-        } else {
-            float* o = sc + lay.mat(bl.dR, b, j);
-            cta_gemm_tc_tile<true, false>(ws + lay.mat(lay.S, b, j), N, sc + lay.mat(bl.dR, b, j + 1), N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] += v; });
-        }
+        float* o = c.sc + lay.mat(role == 0 ? bl.dL : bl.dR, b, j);
+        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j);
+        auto epi = [&](int m, int n, float v) {
+            if (n < N) {
+                v += o[(size_t)m * N + n];
+                o[(size_t)m * N + n] = v;
+            }
+            emit_pad(om, m, n, v, N);
+        };
+        if (role == 0)
+            bf_gemm_tile<false, false>(src_of(mat2(c.sa, ab, d, kFamDL, b, j + 1), N), src_of(mat2(c.wa, ar, d, kFamSp, b, j), N), N, m0, n0, N, cx, epi);
+        else
+            bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamS, b, j), N), src_of(mat2(c.sa, ab, d, kFamDR, b, j + 1), N), N, m0, n0, N, cx, epi);
     }
 };
 
-struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; role 0: dS'_t = L_t^T dL_{t+1} ; role 1: dS_t = dR_{t+1} R_t^T
-    Dims d; const float* ws; float* sc;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
+struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; dS'_t = L_t^T dL_{t+1} ; dS_t = dR_{t+1} R_t^T
+    Ctx c;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const BwdLayout bl(d.B, d.T, d.N);
+        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int K = d.T - 2, N = d.N, nt = d.T - 1, role = z / (d.B * nt), r = z % (d.B * nt), b = r / nt, t = r % nt;
         if (role == 0) {
             if (t + 1 > K) return;
-            float* o = sc + lay.mat(bl.dSp, b, t);
-            cta_gemm_tc_tile<true, false>(ws + lay.mat(lay.L, b, t), N, sc + lay.mat(bl.dL, b, t + 1), N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] = v; });
+            float* o = c.sc + lay.mat(bl.dSp, b, t);
+            bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, t), N), src_of(mat2(c.sa, ab, d, kFamDL, b, t + 1), N), N, m0, n0, N, cx,
+                                     [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v; });
         } else {
             if (t < 1 || t + 1 > K) return;
-            float* o = sc + lay.mat(bl.dS, b, t);
-            cta_gemm_tc_tile<false, true>(sc + lay.mat(bl.dR, b, t + 1), N, ws + lay.mat(lay.R, b, t), N, N, N, N, nullptr, m0, n0, cx,
-                                          [&](int m, int n, float v) { o[(size_t)m * N + n] = v; });
+            float* o = c.sc + lay.mat(bl.dS, b, t);
+            bf_gemm_tile<false, false>(src_of(mat2(c.sa, ab, d, kFamDR, b, t + 1), N), src_of(mat2(c.wa, ar, d, kFamR, b, t), N), N, m0, n0, N, cx,
+                                       [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v; });
         }
     }
 };
 
-struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau   (E = x * invn)
-    Dims d; const float* x; const float* ws; const float* sc; float* dx; float inv_tau;
-    __device__ void run(int z, int m0, int n0, TcGemmCtx& cx) const {
-        const WalkLayout lay(d.B, d.T, d.N, d.C);
-        const BwdLayout bl(d.B, d.T, d.N);
+struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau
+    Ctx c; float* dx; float inv_tau;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
+        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int b = z / d.T, t = z % d.T, N = d.N, C = d.C;
         float* o = dx + ((size_t)b * d.T + t) * N * C;
-        const float* invn = ws + lay.invn + (size_t)b * d.T * N;
+        const size_t rows = (size_t)d.B * d.T * N;
+        const bf16* Ehi = c.wa + ar.E;
+        const bf16* Elo = Ehi + rows * ar.CP;
         const float it = inv_tau;
         if (t <= d.T - 2) {
-            cta_gemm_tc_tile<false, false>(sc + lay.mat(bl.dAw, b, t), N, x + ((size_t)b * d.T + t + 1) * N * C, C, N, C, N,
-                                           invn + (size_t)(t + 1) * N, m0, n0, cx,
-                                           [&](int m, int c, float v) { o[(size_t)m * C + c] = v * it; });
+            const size_t eo = ((size_t)b * d.T + t + 1) * N * ar.CP;      // B(k=j, n=ch) = E_{t+1}[j][ch]: MN-major, MN extent C
+            bf_gemm_tile<false, true>(src_of(mat2(c.sa, ab, d, kFamDA, b, t), N), OpSrc{Ehi + eo, Elo + eo, ar.CP, C}, N, m0, n0, N, cx,
+                                      [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] = v * it; });
         } else {
-            for (int e = threadIdx.x; e < kTcTile * kTcTile; e += kTT) {
-                const int m = m0 + e / kTcTile, c = n0 + e % kTcTile;
-                if (m < N && c < C) o[(size_t)m * C + c] = 0.0f;
+            for (int e = threadIdx.x; e < kWTile * kWTile; e += kTT) {
+                const int m = m0 + e / kWTile, ch = n0 + e % kWTile;
+                if (m < N && ch < C) o[(size_t)m * C + ch] = 0.0f;
             }
             __syncthreads();
         }
-        if (t >= 1)
-            cta_gemm_tc_tile<true, false>(sc + lay.mat(bl.dAw, b, t - 1), N, x + ((size_t)b * d.T + t - 1) * N * C, C, N, C, N,
-                                          invn + (size_t)(t - 1) * N, m0, n0, cx,
-                                          [&](int m, int c, float v) { o[(size_t)m * C + c] += v * it; });
+        if (t >= 1) {
+            const size_t eo = ((size_t)b * d.T + t - 1) * N * ar.CP;
+            bf_gemm_tile<true, true>(src_of(mat2(c.sa, ab, d, kFamDA, b, t - 1), N), OpSrc{Ehi + eo, Elo + eo, ar.CP, C}, N, m0, n0, N, cx,
+                                     [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] += v * it; });
+        }
     }
 };
 
 // ---- row-wise kernels -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) t_rownorm_kernel(const float* __restrict__ x, float* ws, Dims d) {
+// inverse norms and E = x / ||x|| as bf16 hi/lo [rows][C]
+__global__ void __launch_bounds__(256) t_rownorm_kernel(const float* __restrict__ x, Ctx c) {
+    const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const TcArena ar(d, kNumSavedFam, true);
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), rows = (long long)d.B * d.T * d.N;
     if (row >= rows) return;
     const float* xr = x + row * d.C;
     float ss = 0.0f;
-    for (int c = lane; c < d.C; c += 32) ss = fmaf(xr[c], xr[c], ss);
+    for (int ch = lane; ch < d.C; ch += 32) ss = fmaf(xr[ch], xr[ch], ss);
     ss = warp_sum(ss);
-    if (lane == 0) ws[lay.invn + row] = 1.0f / fmaxf(sqrtf(ss), kNormEps);
-}
-
-__global__ void __launch_bounds__(256) t_identity_kernel(float* ws, Dims d) {   // L_0 = I, R_1 = I
-    const WalkLayout lay(d.B, d.T, d.N, d.C);
-    const int b = blockIdx.x, N = d.N;
-    float* L0 = ws + lay.mat(lay.L, b, 0);
-    float* R1 = (d.T >= 3) ? ws + lay.mat(lay.R, b, 1) : nullptr;
-    for (size_t i = threadIdx.x; i < (size_t)N * N; i += blockDim.x) {
-        const float v = (i / N == i % N) ? 1.0f : 0.0f;
-        L0[i] = v;
-        if (R1) R1[i] = v;
+    const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+    if (lane == 0) c.ws[lay.invn + row] = inv;
+    bf16* Ehi = c.wa + ar.E;
+    bf16* Elo = Ehi + (size_t)rows * ar.CP;
+    for (int ch = lane; ch < ar.CP; ch += 32) {
+        const float e = ch < d.C ? xr[ch] * inv : 0.0f;
+        const bf16 h = __float2bfloat16_rn(e);
+        Ehi[row * ar.CP + ch] = h;
+        Elo[row * ar.CP + ch] = __float2bfloat16_rn(e - __bfloat162float(h));
     }
 }
 
-__global__ void __launch_bounds__(256) t_softmax_kernel(float* ws, Dims d) {    // grid (T-1, B): S_t, S'_t from A_t
+__global__ void __launch_bounds__(256) t_identity_kernel(Ctx c) {   // L_0 = I, R_1 = I
+    const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const TcArena ar(d, kNumSavedFam, true);
+    const int b = blockIdx.x, N = d.N;
+    float* L0 = c.ws + lay.mat(lay.L, b, 0);
+    float* R1 = c.ws + lay.mat(lay.R, b, 1);
+    const Mat2 l0 = mat2(c.wa, ar, d, kFamL, b, 0), r1 = mat2(c.wa, ar, d, kFamR, b, 1);
+    for (size_t i = threadIdx.x; i < (size_t)N * l0.P; i += blockDim.x) {
+        const int r = (int)(i / l0.P), cc = (int)(i % l0.P);
+        const float v = (r == cc) ? 1.0f : 0.0f;
+        if (cc < N) { L0[(size_t)r * N + cc] = v; R1[(size_t)r * N + cc] = v; }
+        const bf16 h = __float2bfloat16_rn(v), zz = __float2bfloat16_rn(0.0f);
+        l0.hi[i] = h; l0.lo[i] = zz;
+        r1.hi[i] = h; r1.lo[i] = zz;
+    }
+}
+
+__global__ void __launch_bounds__(256) t_softmax_kernel(Ctx c) {    // grid (T-1, B): S_t, S'_t from A_t
+    const Dims& d = c.d;
+    const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const TcArena ar(d, kNumSavedFam, true);
     const int t = blockIdx.x, b = blockIdx.y, N = d.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* At = ws + lay.mat(lay.A, b, t);
-    float* S = ws + lay.mat(lay.S, b, t);
-    float* Sp = ws + lay.mat(lay.Sp, b, t);
+    const float* At = c.ws + lay.mat(lay.A, b, t);
+    float* S = c.ws + lay.mat(lay.S, b, t);
+    float* Sp = c.ws + lay.mat(lay.Sp, b, t);
+    const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mp = mat2(c.wa, ar, d, kFamSp, b, t);
     for (int r = warp; r < 2 * N; r += 8) {
         const bool col = r >= N;
         const int i = col ? r - N : r;
@@ -199,28 +431,42 @@ __global__ void __launch_bounds__(256) t_softmax_kernel(float* ws, Dims d) {    
         se = warp_sum(se);
         const float inv = 1.0f / se;
         float* dst = (col ? Sp : S) + (size_t)i * N;
-        for (int j = lane; j < N; j += 32) dst[j] = __expf(At[base + j * step] - mx) * inv;
+        const Mat2& mm = col ? mp : ms;
+        for (int j = lane; j < N; j += 32) {
+            const float v = __expf(At[base + j * step] - mx) * inv;
+            dst[j] = v;
+            emit_one(mm, i, j, v);
+        }
+        zero_row_pad(mm, i, N, lane);
     }
 }
 
-__global__ void __launch_bounds__(256) t_cycle_epi_kernel(float* ws, Dims d) {  // grid (T-2, B): G_k = softmax(M_k) - I, loss partial
+__global__ void __launch_bounds__(256) t_cycle_epi_kernel(Ctx c) {  // grid (T-2, B): G_k = softmax(M_k) - I, loss partial
     __shared__ float red[8];
+    const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const TcArena ar(d, kNumSavedFam, true);
     const int k = blockIdx.x + 1, b = blockIdx.y, N = d.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* Gk = ws + lay.mat(lay.G, b, k);
+    float* Gk = c.ws + lay.mat(lay.G, b, k);
+    const Mat2 mg = mat2(c.wa, ar, d, kFamG, b, k);
     float part = 0.0f;
     for (int r = warp; r < N; r += 8) {
         float* row = Gk + (size_t)r * N;
         float mx = -INFINITY;
-        for (int c = lane; c < N; c += 32) mx = fmaxf(mx, row[c]);
+        for (int cc = lane; cc < N; cc += 32) mx = fmaxf(mx, row[cc]);
         mx = warp_max(mx);
         float se = 0.0f;
-        for (int c = lane; c < N; c += 32) se += __expf(row[c] - mx);
+        for (int cc = lane; cc < N; cc += 32) se += __expf(row[cc] - mx);
         se = warp_sum(se);
         const float diag = row[r];
         __syncwarp();
         const float inv = 1.0f / se;
-        for (int c = lane; c < N; c += 32) row[c] = __expf(row[c] - mx) * inv - (c == r ? 1.0f : 0.0f);
+        for (int cc = lane; cc < N; cc += 32) {
+            const float v = __expf(row[cc] - mx) * inv - (cc == r ? 1.0f : 0.0f);
+            row[cc] = v;
+            emit_one(mg, r, cc, v);
+        }
+        zero_row_pad(mg, r, N, lane);
         part += (logf(se) + mx) - diag;
     }
     if (lane == 0) red[warp] = part;
@@ -228,7 +474,7 @@ __global__ void __launch_bounds__(256) t_cycle_epi_kernel(float* ws, Dims d) {  
     if (threadIdx.x == 0) {
         float s = 0.0f;
         for (int w = 0; w < 8; ++w) s += red[w];
-        ws[lay.part + (size_t)b * (d.T - 1) + k] = s;
+        c.ws[lay.part + (size_t)b * (d.T - 1) + k] = s;
     }
 }
 
@@ -242,37 +488,45 @@ __global__ void t_loss_reduce_kernel(const float* ws, float* loss, Dims d) {
 }
 __global__ void t_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 
-__global__ void __launch_bounds__(256) t_dA_epi_kernel(const float* ws, float* sc, const float* dA_ext, Dims d) {   // grid (T-1, B)
+__global__ void __launch_bounds__(256) t_dA_epi_kernel(Ctx c, const float* dA_ext) {   // grid (T-1, B)
     extern __shared__ float rdot[];   // rS[N], rSp[N]
+    const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const BwdLayout bl(d.B, d.T, d.N);
+    const TcArena ab(d, kNumBwdFam, false);
     const int t = blockIdx.x, b = blockIdx.y, N = d.N, K = d.T - 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool hasSp = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
-    const float* S = ws + lay.mat(lay.S, b, t);
-    const float* Sp = ws + lay.mat(lay.Sp, b, t);
-    const float* dS = sc + lay.mat(bl.dS, b, t);
-    const float* dSp = sc + lay.mat(bl.dSp, b, t);
-    float* dA = sc + lay.mat(bl.dAw, b, t);
+    const float* S = c.ws + lay.mat(lay.S, b, t);
+    const float* Sp = c.ws + lay.mat(lay.Sp, b, t);
+    const float* dS = c.sc + lay.mat(bl.dS, b, t);
+    const float* dSp = c.sc + lay.mat(bl.dSp, b, t);
+    const Mat2 ma = mat2(c.sa, ab, d, kFamDA, b, t);
     const float* ext = dA_ext ? dA_ext + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
     for (int r = warp; r < 2 * N; r += 8) {
         const bool second = r >= N;
         const int i = second ? r - N : r;
         float a = 0.0f;
         if (second ? hasSp : hasS) {
-            const float* P = (second ? Sp : S) + (size_t)i * N;
+            const float* Pm = (second ? Sp : S) + (size_t)i * N;
             const float* dP = (second ? dSp : dS) + (size_t)i * N;
-            for (int j = lane; j < N; j += 32) a = fmaf(P[j], dP[j], a);
+            for (int j = lane; j < N; j += 32) a = fmaf(Pm[j], dP[j], a);
             a = warp_sum(a);
         }
         if (lane == 0) rdot[r] = a;
     }
     __syncthreads();
-    for (size_t e = threadIdx.x; e < (size_t)N * N; e += blockDim.x) {
-        const int i = (int)(e / N), j = (int)(e % N);
-        float g = ext ? ext[e] : 0.0f;
-        if (hasS) g += S[e] * (dS[e] - rdot[i]);
-        if (hasSp) g += Sp[(size_t)j * N + i] * (dSp[(size_t)j * N + i] - rdot[N + j]);
-        dA[e] = g;
+    for (size_t e = threadIdx.x; e < (size_t)N * ma.P; e += blockDim.x) {
+        const int i = (int)(e / ma.P), j = (int)(e % ma.P);
+        float g = 0.0f;
+        if (j < N) {
+            const size_t en = (size_t)i * N + j;
+            g = ext ? ext[en] : 0.0f;
+            if (hasS) g += S[en] * (dS[en] - rdot[i]);
+            if (hasSp) g += Sp[(size_t)j * N + i] * (dSp[(size_t)j * N + i] - rdot[N + j]);
+        }
+        const bf16 h = __float2bfloat16_rn(g);
+        ma.hi[e] = h;
+        ma.lo[e] = __float2bfloat16_rn(g - __bfloat162float(h));
     }
 }
 
@@ -287,13 +541,13 @@ __global__ void __launch_bounds__(256) t_dx_epi_kernel(const float* __restrict__
         float* orow = o + (size_t)i * C;
         const float* xr = xt + (size_t)i * C;
         if (inv >= 1.0f / kNormEps) {
-            for (int c = lane; c < C; c += 32) orow[c] *= inv;
+            for (int ch = lane; ch < C; ch += 32) orow[ch] *= inv;
             continue;
         }
         float dot = 0.0f;
-        for (int c = lane; c < C; c += 32) dot = fmaf(xr[c] * inv, orow[c], dot);
+        for (int ch = lane; ch < C; ch += 32) dot = fmaf(xr[ch] * inv, orow[ch], dot);
         dot = warp_sum(dot);
-        for (int c = lane; c < C; c += 32) orow[c] = (orow[c] - xr[c] * inv * dot) * inv;
+        for (int ch = lane; ch < C; ch += 32) orow[ch] = (orow[ch] - xr[ch] * inv * dot) * inv;
     }
 }
 
@@ -302,62 +556,75 @@ template <class P>
 static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_t st) {
     static bool opted = false;   // per instantiation; idempotent
     if (!opted) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(tc_tiles_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        CRW_CUDA_RET(cudaFuncSetAttribute(tc_tiles_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
         opted = true;
     }
     if (batch <= 0) return CRW_OK;
-    dim3 grid(ceil_div(Ncols, kTcTile), ceil_div(Mrows, kTcTile), batch);
-    tc_tiles_kernel<P><<<grid, kTT, kTcSmemBytes, st>>>(p);
+    dim3 grid(ceil_div(Ncols, kWTile), ceil_div(Mrows, kWTile), batch);
+    tc_tiles_kernel<P><<<grid, kTT, kWSmem, st>>>(p);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
 
-// No extra state beyond the fp32 workspaces: operands are converted to bf16 hi/lo while they are staged.
-size_t walk_tiles_saved_extra_bytes(int, int, int, int) { return 0; }
-size_t walk_tiles_scratch_extra_bytes(int, int, int, int) { return 0; }
+// bf16 operand planes kept next to the fp32 state
+size_t walk_tiles_saved_extra_bytes(int B, int T, int N, int C) {
+    return TcArena(Dims{B, T, N, C}, kNumSavedFam, true).total * sizeof(bf16) + 256;
+}
+size_t walk_tiles_scratch_extra_bytes(int B, int T, int N, int C) {
+    return TcArena(Dims{B, T, N, C}, kNumBwdFam, false).total * sizeof(bf16) + 256;
+}
+static bf16* arena_after(float* f32_base, size_t f32_floats) {
+    return reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(f32_base + f32_floats) + 255) & ~uintptr_t(255));
+}
 
 int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
                        cudaStream_t st) {
     const Dims d{B, T, N, C};
+    const WalkLayout lay(B, T, N, C);
+    Ctx c{d, ws, arena_after(ws, lay.total), nullptr, nullptr};
+    int rc;
     const long long rows = (long long)B * T * N;
-    t_rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, ws, d);
+    t_rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, c);
     CRW_LAUNCH_RET();
-    int rc = launch_tiles(AffinityProb{d, x, ws, A_or_null, 1.0f / tau}, N, N, B * (T - 1), st);
-    if (rc) return rc;
+    if ((rc = launch_tiles(AffinityProb{c, A_or_null, 1.0f / tau}, N, N, B * (T - 1), st))) return rc;
     if (T < 3) {
         t_zero_loss_kernel<<<1, 1, 0, st>>>(loss);
         CRW_LAUNCH_RET();
         return CRW_OK;
     }
-    t_softmax_kernel<<<dim3(T - 1, B), 256, 0, st>>>(ws, d);
+    t_softmax_kernel<<<dim3(T - 1, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
-    t_identity_kernel<<<B, 256, 0, st>>>(ws, d);
+    t_identity_kernel<<<B, 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
     const int K = T - 2;
     for (int k = 1; k <= K; ++k)
-        if ((rc = launch_tiles(ChainProb{d, ws, k}, N, N, k >= 2 ? 2 * B : B, st))) return rc;
-    if ((rc = launch_tiles(CycleProb{d, ws}, N, N, B * K, st))) return rc;
-    t_cycle_epi_kernel<<<dim3(K, B), 256, 0, st>>>(ws, d);
+        if ((rc = launch_tiles(ChainProb{c, k}, N, N, k >= 2 ? 2 * B : B, st))) return rc;
+    if ((rc = launch_tiles(CycleProb{c}, N, N, B * K, st))) return rc;
+    t_cycle_epi_kernel<<<dim3(K, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
     t_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, d);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
 
-int walk_tiles_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
+int walk_tiles_backward(const float* x, const float* ws_c, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
                         float tau, float* dx, float* sc, cudaStream_t st) {
     const Dims d{B, T, N, C};
-    const int K = T - 2;
+    const WalkLayout lay(B, T, N, C);
+    const BwdLayout bl(B, T, N);
+    float* ws = const_cast<float*>(ws_c);
+    Ctx c{d, ws, arena_after(ws, lay.total), sc, arena_after(sc, bl.total)};
     int rc;
+    const int K = T - 2;
     if (T >= 3) {
-        if ((rc = launch_tiles(OwnProb{d, ws, sc, dloss}, N, N, 2 * B * K, st))) return rc;
+        if ((rc = launch_tiles(OwnProb{c, dloss}, N, N, 2 * B * K, st))) return rc;
         for (int j = K - 1; j >= 1; --j)
-            if ((rc = launch_tiles(BwdChainProb{d, ws, sc, j}, N, N, j >= 2 ? 2 * B : B, st))) return rc;
-        if ((rc = launch_tiles(DsProb{d, ws, sc}, N, N, 2 * B * (T - 1), st))) return rc;
+            if ((rc = launch_tiles(BwdChainProb{c, j}, N, N, j >= 2 ? 2 * B : B, st))) return rc;
+        if ((rc = launch_tiles(DsProb{c}, N, N, 2 * B * (T - 1), st))) return rc;
     }
-    t_dA_epi_kernel<<<dim3(T - 1, B), 256, 2 * N * sizeof(float), st>>>(ws, sc, dA_or_null, d);
+    t_dA_epi_kernel<<<dim3(T - 1, B), 256, 2 * N * sizeof(float), st>>>(c, dA_or_null);
     CRW_LAUNCH_RET();
-    if ((rc = launch_tiles(DxProb{d, x, ws, sc, dx, 1.0f / tau}, N, C, B * T, st))) return rc;
+    if ((rc = launch_tiles(DxProb{c, dx, 1.0f / tau}, N, C, B * T, st))) return rc;
     t_dx_epi_kernel<<<dim3(T, B), 256, 0, st>>>(x, ws, dx, d);
     CRW_LAUNCH_RET();
     return CRW_OK;
