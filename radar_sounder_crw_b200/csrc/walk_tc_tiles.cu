@@ -9,6 +9,8 @@
 //     (UMMA majorness bits + LBO/SBO descriptors, pinned by crw_debug_umma_mn_gemm) -- no transposed copies;
 //   * staging is sixteen 16-byte cp.async per thread per 64-wide k-chunk straight into the SWIZZLE_128B layout, three
 //     stages deep; the MMAs of chunk c are queued before the CTA waits for the stage of chunk c-1 to drain;
+//   * S'_t = softmax(A_t^T) is never materialised: the path keeps Q_t = S'_t^T = column-softmax(A_t) (same orientation
+//     as A_t, so softmax forward / backward are transposition-free and coalesced) and uses it through the other majorness;
 //   * the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in small kernels;
 //   * the L / R chains and their adjoints are one launch per step (both chains in one grid): the only serialisation
 //     left is the algorithm's own 2(T-3) dependent products forward and backward.
@@ -31,7 +33,7 @@ constexpr int kWSmem = kWStages * kWStage + 1024;
 struct Dims { int B, T, N, C; };
 
 // ---- bf16 arenas ------------------------------------------------------------------------------------------
-enum { kFamS = 0, kFamSp, kFamL, kFamR, kFamG, kNumSavedFam };      // saved arena (forward state)
+enum { kFamS = 0, kFamQ, kFamL, kFamR, kFamG, kNumSavedFam };       // saved arena (forward state); Q = S'^T
 enum { kFamDL = 0, kFamDR, kFamDA, kNumBwdFam };                    // scratch arena (backward state)
 
 struct TcArena {
@@ -76,7 +78,7 @@ __device__ __forceinline__ void zero_row_pad(const Mat2& mt, int r, int N, int l
 // K-major use: logical X(r,k) = plane[r*pitch + k]; MN-major use: X(r,k) = plane[k*pitch + r].  `rows` = valid r extent.
 struct OpSrc { const bf16 *hi, *lo; int pitch, rows; };
 
-struct TcCtx3 { uint8_t* buf; uint64_t* bar; uint32_t tmem; uint32_t uses[kWStages]; };
+struct TcCtx3 { uint8_t* buf; uint64_t* bar; uint32_t tmem; uint32_t uses[kWStages]; int last_stage; };
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
     const int n = valid ? 16 : 0;
@@ -111,9 +113,9 @@ __device__ __forceinline__ void stage_operand_async(uint32_t dst_hi, uint32_t ds
 // against its own extents and pitch).  The accumulator goes TMEM -> registers (thread = row) -> shared memory ->
 // registers (warp = row, lane = column) so that every global access of the epilogue is coalesced.
 constexpr int kEpPitch = 132;      // floats; 528-byte rows: 16-byte aligned, conflict-free for the v4 stores of phase 1
-template <bool A_MN, bool B_MN, class Epi>
-__device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// acc (TMEM) = (fresh ? 0 : acc) + A B over the whole K extent; several calls may accumulate into one tile
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void bf_gemm_accumulate(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, TcCtx3& cx, bool fresh) {
     const uint32_t idesc = tc::umma_idesc_bf16_major(kWTile, kWTile, A_MN, B_MN);
     const int nchunks = (K + kWChunk - 1) / kWChunk;
     auto issue = [&](int c) {
@@ -126,7 +128,6 @@ __device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int
     };
     issue(0);
     if (nchunks > 1) issue(1);
-    int last_stage = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int s = c % kWStages;
         if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -143,16 +144,20 @@ __device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int
                 for (int ks = 0; ks < 4; ++ks) {
                     const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
                     const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
-                    tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (c | pass | ks) ? 1u : 0u);
+                    tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (!fresh || (c | pass | ks)) ? 1u : 0u);
                 }
             }
             tc::umma_commit(&cx.bar[s]);
         }
         cx.uses[s]++;
-        last_stage = s;
+        cx.last_stage = s;
         if (c + 2 < nchunks) issue(c + 2);     // its stage held chunk c-1: the wait overlaps the MMAs just queued
     }
-    tc::mbar_wait(&cx.bar[last_stage], (cx.uses[last_stage] - 1) & 1);   // commit tracks every earlier MMA too: all stages idle
+}
+template <class Epi>
+__device__ __forceinline__ void bf_gemm_epilogue(int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    tc::mbar_wait(&cx.bar[cx.last_stage], (cx.uses[cx.last_stage] - 1) & 1);   // commit tracks every earlier MMA too: all stages idle
     tc::tc_fence_after();
     float* ep = reinterpret_cast<float*>(cx.buf);
     {
@@ -176,6 +181,11 @@ __device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int
     }
     __syncthreads();     // the staging buffer and TMEM are reused by the next tile
 }
+template <bool A_MN, bool B_MN, class Epi>
+__device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
+    bf_gemm_accumulate<A_MN, B_MN>(A, B, K, m0, n0, cx, true);
+    bf_gemm_epilogue(m0, n0, Mvalid, cx, epi);
+}
 
 template <class P>
 __global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(P p) {
@@ -185,6 +195,7 @@ __global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(P p) {
     TcCtx3 cx;
     cx.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
     cx.bar = bars;
+    cx.last_stage = 0;
 #pragma unroll
     for (int s = 0; s < kWStages; ++s) cx.uses[s] = 0;
     if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<128>(&slot);
@@ -235,7 +246,7 @@ struct AffinityProb {       // batch = b*(T-1) + t :  A_t = E_t E_{t+1}^T / tau
     }
 };
 
-struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} ;  R_k = S_{k-1} R_{k-1}
+struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} = L_{k-1} Q_{k-1}^T ;  R_k = S_{k-1} R_{k-1}
     Ctx c; int k;
     __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
         const Dims& d = c.d;
@@ -244,13 +255,15 @@ struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} ;  R_
         const int role = z / d.B, b = z % d.B, N = d.N;
         if (role == 1 && k < 2) return;
         const OpSrc A = src_of(mat2(c.wa, ar, d, role == 0 ? kFamL : kFamS, b, k - 1), N);      // as stored (K-major)
-        const OpSrc Bm = src_of(mat2(c.wa, ar, d, role == 0 ? kFamSp : kFamR, b, k - 1), N);    // B(k,n) = X[k][n]: MN-major
+        const OpSrc Bm = src_of(mat2(c.wa, ar, d, role == 0 ? kFamQ : kFamR, b, k - 1), N);
         float* out = c.ws + lay.mat(role == 0 ? lay.L : lay.R, b, k);
         const Mat2 om = mat2(c.wa, ar, d, role == 0 ? kFamL : kFamR, b, k);
-        bf_gemm_tile<false, true>(A, Bm, N, m0, n0, N, cx, [&](int m, int n, float v) {
+        auto epi = [&](int m, int n, float v) {
             if (n < N) out[(size_t)m * N + n] = v;
             emit_pad(om, m, n, v, N);
-        });
+        };
+        if (role == 0) bf_gemm_tile<false, false>(A, Bm, N, m0, n0, N, cx, epi);    // B(k,n) = Q[n][k]: K-major
+        else bf_gemm_tile<false, true>(A, Bm, N, m0, n0, N, cx, epi);               // B(k,n) = R[k][n]: MN-major
     }
 };
 
@@ -268,71 +281,50 @@ struct CycleProb {          // batch = b*K + (k-1) :  M_k = L_k R_k  (raw, into 
 };
 
 // ---- backward problems ----------------------------------------------------------------------------------
-struct OwnProb {            // batch = role*B*K + b*K + (k-1) :  dL_k = s G_k R_k^T ;  dR_k = s L_k^T G_k
+// The adjoints of the chain are carried UNSCALED (dL~ = dL / s, dR~ = dR / s with s = dloss / (B N^2)): every product
+// below is linear in s, which is applied once in DsProb's epilogue.  That lets one accumulator take both the step's own
+// term and the propagated term, and only the bf16 planes of dL~ / dR~ are ever written.
+struct BwdChainProb {       // batch = role*B + b ; dL~_j = G_j R_j^T + dL~_{j+1} Q_j ;  dR~_j = L_j^T G_j + S_j^T dR~_{j+1}
+    Ctx c; int j;
+    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+        const Dims& d = c.d;
+        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
+        const int role = z / d.B, b = z % d.B, N = d.N, K = d.T - 2;
+        if (role == 1 && j < 2) return;
+        const OpSrc G = src_of(mat2(c.wa, ar, d, kFamG, b, j), N);
+        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j);
+        if (role == 0) {
+            bf_gemm_accumulate<false, false>(G, src_of(mat2(c.wa, ar, d, kFamR, b, j), N), N, m0, n0, cx, true);      // B^T(n,k) = R[n][k]
+            if (j < K)
+                bf_gemm_accumulate<false, true>(src_of(mat2(c.sa, ab, d, kFamDL, b, j + 1), N), src_of(mat2(c.wa, ar, d, kFamQ, b, j), N), N, m0, n0, cx, false);
+        } else {
+            bf_gemm_accumulate<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, j), N), G, N, m0, n0, cx, true);        // A(m,k) = L[k][m]
+            if (j < K)
+                bf_gemm_accumulate<true, true>(src_of(mat2(c.wa, ar, d, kFamS, b, j), N), src_of(mat2(c.sa, ab, d, kFamDR, b, j + 1), N), N, m0, n0, cx, false);
+        }
+        bf_gemm_epilogue(m0, n0, N, cx, [&](int m, int n, float v) { emit_pad(om, m, n, v, N); });
+    }
+};
+
+struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; dQ_t = s dL~_{t+1}^T L_t  (= (L_t^T dL_{t+1})^T) ; dS_t = s dR~_{t+1} R_t^T
     Ctx c; const float* dloss;
     __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
         const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const BwdLayout bl(d.B, d.T, d.N);
         const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
-        const int K = d.T - 2, N = d.N, role = z / (d.B * K), r = z % (d.B * K), b = r / K, k = r % K + 1;
-        const float s = *dloss / ((float)d.B * (float)N * (float)N);
-        const OpSrc G = src_of(mat2(c.wa, ar, d, kFamG, b, k), N);
-        float* o = c.sc + lay.mat(role == 0 ? bl.dL : bl.dR, b, k);
-        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, k);
-        auto epi = [&](int m, int n, float v) {
-            v *= s;
-            if (n < N) o[(size_t)m * N + n] = v;
-            emit_pad(om, m, n, v, N);
-        };
-        if (role == 0) bf_gemm_tile<false, false>(G, src_of(mat2(c.wa, ar, d, kFamR, b, k), N), N, m0, n0, N, cx, epi);   // B^T(n,k) = R[n][k]
-        else bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, k), N), G, N, m0, n0, N, cx, epi);             // A(m,k) = L[k][m], B(k,n) = G[k][n]
-    }
-};
-
-struct BwdChainProb {       // batch = role*B + b ; dL_j += dL_{j+1} S'_j^T ; dR_j += S_j^T dR_{j+1}
-    Ctx c; int j;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
-        const Dims& d = c.d;
-        const WalkLayout lay(d.B, d.T, d.N, d.C);
-        const BwdLayout bl(d.B, d.T, d.N);
-        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
-        const int role = z / d.B, b = z % d.B, N = d.N;
-        if (role == 1 && j < 2) return;
-        float* o = c.sc + lay.mat(role == 0 ? bl.dL : bl.dR, b, j);
-        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j);
-        auto epi = [&](int m, int n, float v) {
-            if (n < N) {
-                v += o[(size_t)m * N + n];
-                o[(size_t)m * N + n] = v;
-            }
-            emit_pad(om, m, n, v, N);
-        };
-        if (role == 0)
-            bf_gemm_tile<false, false>(src_of(mat2(c.sa, ab, d, kFamDL, b, j + 1), N), src_of(mat2(c.wa, ar, d, kFamSp, b, j), N), N, m0, n0, N, cx, epi);
-        else
-            bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamS, b, j), N), src_of(mat2(c.sa, ab, d, kFamDR, b, j + 1), N), N, m0, n0, N, cx, epi);
-    }
-};
-
-struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; dS'_t = L_t^T dL_{t+1} ; dS_t = dR_{t+1} R_t^T
-    Ctx c;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
-        const Dims& d = c.d;
-        const WalkLayout lay(d.B, d.T, d.N, d.C);
-        const BwdLayout bl(d.B, d.T, d.N);
-        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int K = d.T - 2, N = d.N, nt = d.T - 1, role = z / (d.B * nt), r = z % (d.B * nt), b = r / nt, t = r % nt;
+        const float s = *dloss / ((float)d.B * (float)N * (float)N);
         if (role == 0) {
             if (t + 1 > K) return;
             float* o = c.sc + lay.mat(bl.dSp, b, t);
-            bf_gemm_tile<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, t), N), src_of(mat2(c.sa, ab, d, kFamDL, b, t + 1), N), N, m0, n0, N, cx,
-                                     [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v; });
+            bf_gemm_tile<true, true>(src_of(mat2(c.sa, ab, d, kFamDL, b, t + 1), N), src_of(mat2(c.wa, ar, d, kFamL, b, t), N), N, m0, n0, N, cx,
+                                     [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
         } else {
             if (t < 1 || t + 1 > K) return;
             float* o = c.sc + lay.mat(bl.dS, b, t);
             bf_gemm_tile<false, false>(src_of(mat2(c.sa, ab, d, kFamDR, b, t + 1), N), src_of(mat2(c.wa, ar, d, kFamR, b, t), N), N, m0, n0, N, cx,
-                                       [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v; });
+                                       [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
         }
     }
 };
@@ -410,34 +402,77 @@ __global__ void __launch_bounds__(256) t_identity_kernel(Ctx c) {   // L_0 = I, 
     }
 }
 
-__global__ void __launch_bounds__(256) t_softmax_kernel(Ctx c) {    // grid (T-1, B): S_t, S'_t from A_t
+// column statistics helper: every warp scans its rows (warp, warp+8, ...) with lanes on consecutive columns (coalesced),
+// the 8 partials per column meet in shared memory.  f(i, j) is the value at row i, column j.
+template <class F>
+__device__ __forceinline__ void column_max(float* out, float* part, int N, F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = lane; j < N; j += 32) {
+        float m = -INFINITY;
+        for (int i = warp; i < N; i += 8) m = fmaxf(m, f(i, j));
+        part[warp * N + j] = m;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float m = part[j];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, part[w * N + j]);
+        out[j] = m;
+    }
+    __syncthreads();
+}
+template <class F>
+__device__ __forceinline__ void column_sum(float* out, float* part, int N, F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = lane; j < N; j += 32) {
+        float a = 0.0f;
+        for (int i = warp; i < N; i += 8) a += f(i, j);
+        part[warp * N + j] = a;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        float a = part[j];
+        for (int w = 1; w < 8; ++w) a += part[w * N + j];
+        out[j] = a;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) t_softmax_kernel(Ctx c) {    // grid (T-1, B): S_t = rowsoftmax(A_t), Q_t = colsoftmax(A_t)
+    extern __shared__ float sm_soft[];      // part[8][N], cmax[N], cinv[N]
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const TcArena ar(d, kNumSavedFam, true);
     const int t = blockIdx.x, b = blockIdx.y, N = d.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* At = c.ws + lay.mat(lay.A, b, t);
     float* S = c.ws + lay.mat(lay.S, b, t);
-    float* Sp = c.ws + lay.mat(lay.Sp, b, t);
-    const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mp = mat2(c.wa, ar, d, kFamSp, b, t);
-    for (int r = warp; r < 2 * N; r += 8) {
-        const bool col = r >= N;
-        const int i = col ? r - N : r;
-        const size_t step = col ? (size_t)N : 1, base = col ? (size_t)i : (size_t)i * N;
+    float* Q = c.ws + lay.mat(lay.Sp, b, t);
+    const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mq = mat2(c.wa, ar, d, kFamQ, b, t);
+    float* part = sm_soft;
+    float* cmax = part + 8 * N;
+    float* cinv = cmax + N;
+    column_max(cmax, part, N, [&](int i, int j) { return At[(size_t)i * N + j]; });
+    column_sum(cinv, part, N, [&](int i, int j) { return __expf(At[(size_t)i * N + j] - cmax[j]); });
+    for (int j = threadIdx.x; j < N; j += blockDim.x) cinv[j] = 1.0f / cinv[j];
+    __syncthreads();
+    for (int i = warp; i < N; i += 8) {
+        const float* row = At + (size_t)i * N;
         float mx = -INFINITY;
-        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, At[base + j * step]);
+        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
         mx = warp_max(mx);
         float se = 0.0f;
-        for (int j = lane; j < N; j += 32) se += __expf(At[base + j * step] - mx);
+        for (int j = lane; j < N; j += 32) se += __expf(row[j] - mx);
         se = warp_sum(se);
         const float inv = 1.0f / se;
-        float* dst = (col ? Sp : S) + (size_t)i * N;
-        const Mat2& mm = col ? mp : ms;
         for (int j = lane; j < N; j += 32) {
-            const float v = __expf(At[base + j * step] - mx) * inv;
-            dst[j] = v;
-            emit_one(mm, i, j, v);
+            const float a = row[j];
+            const float sv = __expf(a - mx) * inv, qv = __expf(a - cmax[j]) * cinv[j];
+            S[(size_t)i * N + j] = sv;
+            Q[(size_t)i * N + j] = qv;
+            emit_one(ms, i, j, sv);
+            emit_one(mq, i, j, qv);
         }
-        zero_row_pad(mm, i, N, lane);
+        zero_row_pad(ms, i, N, lane);
+        zero_row_pad(mq, i, N, lane);
     }
 }
 
@@ -489,44 +524,44 @@ __global__ void t_loss_reduce_kernel(const float* ws, float* loss, Dims d) {
 __global__ void t_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 
 __global__ void __launch_bounds__(256) t_dA_epi_kernel(Ctx c, const float* dA_ext) {   // grid (T-1, B)
-    extern __shared__ float rdot[];   // rS[N], rSp[N]
+    extern __shared__ float sm_da[];   // part[8][N], rS[N], rQ[N]
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const BwdLayout bl(d.B, d.T, d.N);
     const TcArena ab(d, kNumBwdFam, false);
     const int t = blockIdx.x, b = blockIdx.y, N = d.N, K = d.T - 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool hasSp = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
+    const bool hasQ = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
     const float* S = c.ws + lay.mat(lay.S, b, t);
-    const float* Sp = c.ws + lay.mat(lay.Sp, b, t);
+    const float* Q = c.ws + lay.mat(lay.Sp, b, t);
     const float* dS = c.sc + lay.mat(bl.dS, b, t);
-    const float* dSp = c.sc + lay.mat(bl.dSp, b, t);
+    const float* dQ = c.sc + lay.mat(bl.dSp, b, t);
     const Mat2 ma = mat2(c.sa, ab, d, kFamDA, b, t);
     const float* ext = dA_ext ? dA_ext + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
-    for (int r = warp; r < 2 * N; r += 8) {
-        const bool second = r >= N;
-        const int i = second ? r - N : r;
+    float* part = sm_da;
+    float* rS = part + 8 * N;
+    float* rQ = rS + N;
+    if (hasQ) column_sum(rQ, part, N, [&](int i, int j) { return Q[(size_t)i * N + j] * dQ[(size_t)i * N + j]; });
+    for (int i = warp; i < N; i += 8) {
         float a = 0.0f;
-        if (second ? hasSp : hasS) {
-            const float* Pm = (second ? Sp : S) + (size_t)i * N;
-            const float* dP = (second ? dSp : dS) + (size_t)i * N;
-            for (int j = lane; j < N; j += 32) a = fmaf(Pm[j], dP[j], a);
+        if (hasS) {
+            for (int j = lane; j < N; j += 32) a = fmaf(S[(size_t)i * N + j], dS[(size_t)i * N + j], a);
             a = warp_sum(a);
         }
-        if (lane == 0) rdot[r] = a;
+        if (lane == 0) rS[i] = a;
     }
     __syncthreads();
-    for (size_t e = threadIdx.x; e < (size_t)N * ma.P; e += blockDim.x) {
-        const int i = (int)(e / ma.P), j = (int)(e % ma.P);
-        float g = 0.0f;
-        if (j < N) {
-            const size_t en = (size_t)i * N + j;
-            g = ext ? ext[en] : 0.0f;
-            if (hasS) g += S[en] * (dS[en] - rdot[i]);
-            if (hasSp) g += Sp[(size_t)j * N + i] * (dSp[(size_t)j * N + i] - rdot[N + j]);
+    for (int i = warp; i < N; i += 8) {
+        const float ri = rS[i];
+        for (int j = lane; j < ma.P; j += 32) {
+            float g = 0.0f;
+            if (j < N) {
+                const size_t e = (size_t)i * N + j;
+                g = ext ? ext[e] : 0.0f;
+                if (hasS) g += S[e] * (dS[e] - ri);
+                if (hasQ) g += Q[e] * (dQ[e] - rQ[j]);
+            }
+            emit_one(ma, i, j, g);
         }
-        const bf16 h = __float2bfloat16_rn(g);
-        ma.hi[e] = h;
-        ma.lo[e] = __float2bfloat16_rn(g - __bfloat162float(h));
     }
 }
 
@@ -566,6 +601,15 @@ static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_
     return CRW_OK;
 }
 
+// the column-statistics kernels keep 10 N floats in shared memory
+template <class Kern>
+static int opt_in_rowwise_smem(Kern kern, int N) {
+    const size_t need = 10 * (size_t)N * sizeof(float);
+    if (need > 227 * 1024) return CRW_ERR_UNSUPPORTED;
+    if (need > 48 * 1024) CRW_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    return CRW_OK;
+}
+
 // bf16 operand planes kept next to the fp32 state
 size_t walk_tiles_saved_extra_bytes(int B, int T, int N, int C) {
     return TcArena(Dims{B, T, N, C}, kNumSavedFam, true).total * sizeof(bf16) + 256;
@@ -592,7 +636,8 @@ int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, fl
         CRW_LAUNCH_RET();
         return CRW_OK;
     }
-    t_softmax_kernel<<<dim3(T - 1, B), 256, 0, st>>>(c);
+    if ((rc = opt_in_rowwise_smem(t_softmax_kernel, N))) return rc;
+    t_softmax_kernel<<<dim3(T - 1, B), 256, 10 * N * sizeof(float), st>>>(c);
     CRW_LAUNCH_RET();
     t_identity_kernel<<<B, 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
@@ -617,12 +662,12 @@ int walk_tiles_backward(const float* x, const float* ws_c, const float* dloss, c
     int rc;
     const int K = T - 2;
     if (T >= 3) {
-        if ((rc = launch_tiles(OwnProb{c, dloss}, N, N, 2 * B * K, st))) return rc;
-        for (int j = K - 1; j >= 1; --j)
+        for (int j = K; j >= 1; --j)
             if ((rc = launch_tiles(BwdChainProb{c, j}, N, N, j >= 2 ? 2 * B : B, st))) return rc;
-        if ((rc = launch_tiles(DsProb{c}, N, N, 2 * B * (T - 1), st))) return rc;
+        if ((rc = launch_tiles(DsProb{c, dloss}, N, N, 2 * B * (T - 1), st))) return rc;
     }
-    t_dA_epi_kernel<<<dim3(T - 1, B), 256, 2 * N * sizeof(float), st>>>(c, dA_or_null);
+    if ((rc = opt_in_rowwise_smem(t_dA_epi_kernel, N))) return rc;
+    t_dA_epi_kernel<<<dim3(T - 1, B), 256, 10 * N * sizeof(float), st>>>(c, dA_or_null);
     CRW_LAUNCH_RET();
     if ((rc = launch_tiles(DxProb{c, dx, 1.0f / tau}, N, C, B * T, st))) return rc;
     t_dx_epi_kernel<<<dim3(T, B), 256, 0, st>>>(x, ws, dx, d);

@@ -101,6 +101,9 @@ def _walk_setup(ctx, inputs, output):
     _, _, saved = output
     ctx.save_for_backward(x, saved)
     ctx.tau, ctx.need_A, ctx.precision = tau, need_A, precision
+    # no zero-filled stand-ins for the gradients of `A` (when unused) and of the `saved` workspace: at scaled
+    # geometries those are GB-sized fills (measured: 2 x 0.48 ms per step at N=369)
+    ctx.set_materialize_grads(False)
 
 
 def _walk_bwd(ctx, g_loss, g_A, _g_saved):
