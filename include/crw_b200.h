@@ -150,6 +150,40 @@ int crw_horizontality_xent(const float* emb, int T, int N, int C, float* xent, v
 int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Radargram -> frame sequences -- replaces RGDataset.__getitem__ / get_smaller_item, src/dataset.py:34-47
+ * (slice, unfold rows, unfold columns, permute) and the `use_last` frame flip of src/utils.py:108.
+ *   rg  [H, ld] f32, device resident (the `.pt` radargram of src/utils.py:32-38 copied once)
+ *   item r starts at column col_start + r*col_stride (dataset index i: col_start = (w-ow)*i, dataset.py:35)
+ *   out [R,T,N,h,w]:  out[r,t,n,y,x] = rg[n*(h-oh)+y][col_start + r*col_stride + t'*(w-ow) + x],
+ *                     t' = T-1-t when `reverse`, else t.   N*h - oh*(N-1) <= H is required (dataset.py:27).
+ * ---------------------------------------------------------------------------------- */
+int crw_patch_unfold(const float* rg, int H, int64_t ld, int64_t col_start, int64_t col_stride, int R, int T, int N,
+                     int h, int w, int oh, int ow, int reverse, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * First-column label seeding -- replaces `down = Resize((N,1), NEAREST)`, the label read and the
+ * one-hot mask loop of src/utils.py:139-147 (seg_ref = seg[:rows, col : col+W], scripts/test/test_all.py:94).
+ *   seg [rows.., ld] f32 class ids; radargram r reads column col_start + r*col_stride
+ *   label0_or_null [R,N] i32:  seg[min(floor(i * float(rows)/float(N)), rows-1)][col]
+ *   mask0_or_null  [R,M,N] f32 one-hot (the `mask0` input of crw_labelprop_forward)
+ * ---------------------------------------------------------------------------------- */
+int crw_seed_labels(const float* seg, int rows, int64_t ld, int64_t col_start, int64_t col_stride, int R, int N, int M,
+                    int32_t* label0_or_null, float* mask0_or_null, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Reversed-pass mask fusion -- replaces scripts/test/test_all.py:146-158: the reversed pass's map is un-flipped per
+ * radargram (unfold / flip / view) and its class-2 (bedrock) pixels overwrite the forward map.
+ *   fwd, rev, out [H, W] f32 class ids, W a multiple of rg_len; `rev` in the reversed pass's own column order;
+ *   out may alias fwd.   rule = the reference's dataset id:
+ *     0: mask = rev' == 2                         1: ... && fwd != 3 && no class 4 anywhere in that column of rev'
+ *     3: mask = rev' == 2, second half of the flattened map only
+ *   scratch: crw_fuse_reversed_scratch_bytes(W) bytes (used by rule 1).
+ * ---------------------------------------------------------------------------------- */
+size_t crw_fuse_reversed_scratch_bytes(int64_t W);
+int crw_fuse_reversed(const float* fwd, const float* rev, int H, int64_t W, int rg_len, int rule, float* out,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Self-test of the tensor-core plumbing (TMA SWIZZLE_128B tiles -> tcgen05.mma -> TMEM -> tcgen05.ld):
  *   out[128,BN] = A[128,128] * B[BN,128]^T, A/B bf16 row-major, out fp32; BN multiple of 16, <= 256.
  * No reference counterpart; it pins the descriptor encodings the tensor-core kernels rely on.

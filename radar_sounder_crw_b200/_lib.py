@@ -14,6 +14,7 @@ PREC_FP32, PREC_BF16X3, PREC_TF32 = 0, 1, 2
 LP_REF_EXACT, LP_FIXED = 0, 1
 
 _c_int, _c_f, _c_sz, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
+_c_i64 = ctypes.c_int64
 
 # name -> (restype, argtypes); mirrors include/crw_b200.h one to one
 SIGNATURES = {
@@ -35,6 +36,11 @@ SIGNATURES = {
                                        _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_sz, _vp]),
     "crw_horizontality_xent": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_labels_upsample": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "crw_patch_unfold": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                  _c_int, _c_int, _vp, _vp]),
+    "crw_seed_labels": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "crw_fuse_reversed_scratch_bytes": (_c_sz, [_c_i64]),
+    "crw_fuse_reversed": (_c_int, [_vp, _vp, _c_int, _c_i64, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
     "crw_debug_umma_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_umma_ts_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_umma_mn_gemm": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),

@@ -241,3 +241,72 @@ def labels_upsample(labels: Tensor, H: int, W: int) -> Tensor:
 @labels_upsample.register_fake
 def _(labels, H, W):
     return labels.new_empty((labels.shape[0], H, W), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# patch_unfold  (dataset.py:34-47 RGDataset.__getitem__ + the use_last flip of utils.py:108)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::patch_unfold", mutates_args=())
+def patch_unfold(rg: Tensor, col_start: int, col_stride: int, R: int, T: int, h: int, w: int, oh: int, ow: int,
+                 reverse: bool) -> Tensor:
+    """rg [H,W] f32 (device) -> frames [R,T,N,h,w]; item r starts at column col_start + r*col_stride."""
+    rg = _chk(rg, "rg")
+    H, ld = rg.shape
+    N = (H - oh) // (h - oh)                                            # dataset.py:22
+    out = torch.empty((R, T, N, h, w), device=rg.device, dtype=torch.float32)
+    with torch.cuda.device(rg.device):
+        _lib.check(_lib.lib().crw_patch_unfold(_p(rg), H, ld, col_start, col_stride, R, T, N, h, w, oh, ow, int(reverse),
+                                               _p(out), _stream()), "crw_patch_unfold")
+    return out
+
+
+@patch_unfold.register_fake
+def _(rg, col_start, col_stride, R, T, h, w, oh, ow, reverse):
+    return rg.new_empty((R, T, (rg.shape[0] - oh) // (h - oh), h, w))
+
+
+# ------------------------------------------------------------------------------------------------
+# seed_labels  (utils.py:139-147)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::seed_labels", mutates_args=())
+def seed_labels(seg: Tensor, rows: int, col_start: int, col_stride: int, R: int, N: int, M: int) -> Tuple[Tensor, Tensor]:
+    """seg [H,W] f32 class ids (device) -> (label0 [R,N] i32, mask0 [R,M,N] f32) from rows [0,rows) of one column each."""
+    seg = _chk(seg, "seg")
+    if rows > seg.shape[0]:
+        raise RuntimeError("crw_b200::seed_labels: rows exceeds the segmentation height")
+    label0 = torch.empty((R, N), device=seg.device, dtype=torch.int32)
+    mask0 = torch.empty((R, M, N), device=seg.device, dtype=torch.float32)
+    with torch.cuda.device(seg.device):
+        _lib.check(_lib.lib().crw_seed_labels(_p(seg), rows, seg.shape[1], col_start, col_stride, R, N, M, _p(label0),
+                                              _p(mask0), _stream()), "crw_seed_labels")
+    return label0, mask0
+
+
+@seed_labels.register_fake
+def _(seg, rows, col_start, col_stride, R, N, M):
+    return (torch.empty((R, N), device=seg.device, dtype=torch.int32), seg.new_empty((R, M, N)))
+
+
+# ------------------------------------------------------------------------------------------------
+# fuse_reversed  (scripts/test/test_all.py:146-158)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::fuse_reversed", mutates_args=())
+def fuse_reversed(fwd: Tensor, rev: Tensor, rg_len: int, rule: int) -> Tensor:
+    """fwd, rev [H,W] f32 class maps (rev in the reversed pass's column order) -> fused map [H,W]."""
+    fwd, rev = _chk(fwd, "fwd"), _chk(rev, "rev")
+    if fwd.shape != rev.shape or fwd.dim() != 2:
+        raise RuntimeError("crw_b200::fuse_reversed: fwd and rev must both be [H,W]")
+    H, W = fwd.shape
+    L = _lib.lib()
+    out = torch.empty_like(fwd)
+    nb = L.crw_fuse_reversed_scratch_bytes(W)
+    scratch = torch.empty(max(nb, 1), device=fwd.device, dtype=torch.uint8)
+    with torch.cuda.device(fwd.device):
+        _lib.check(L.crw_fuse_reversed(_p(fwd), _p(rev), H, W, rg_len, rule, _p(out), _p(scratch), nb, _stream()),
+                   "crw_fuse_reversed")
+    return out
+
+
+@fuse_reversed.register_fake
+def _(fwd, rev, rg_len, rule):
+    return torch.empty_like(fwd)

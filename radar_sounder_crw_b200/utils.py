@@ -56,6 +56,18 @@ def one_hot_mask(label0: torch.Tensor, nclasses: int) -> torch.Tensor:
     return (label0.view(1, -1) == cls).float()
 
 
+def seed_labels(seg: torch.Tensor, rows: int, col_start: int, col_stride: int, R: int, N: int, nclasses: int):
+    """Device-side label seeding for R radargrams at once (reference utils.py:139-147 per radargram, with
+    ``seg_ref = seg[:rows, col:col+W]`` of scripts/test/test_all.py:94): -> (label0 [R,N] i32, mask0 [R,M,N] f32)."""
+    return ops.seed_labels(seg.float(), rows, col_start, col_stride, R, N, nclasses)
+
+
+def fuse_reversed(final_pred: torch.Tensor, pred_rev: torch.Tensor, rg_len: int, dataset: int) -> torch.Tensor:
+    """Reversed-pass fusion (scripts/test/test_all.py:146-158): ``pred_rev`` is the concatenated map of the
+    ``use_last=True`` pass in its own (flipped) column order; returns the fused [H,W] map."""
+    return ops.fuse_reversed(final_pred.float(), pred_rev.float(), rg_len, dataset)
+
+
 def _change_point(xent: torch.Tensor):
     """PELT change point on the horizontality metric (reference utils.py:125-132); None without ruptures."""
     try:
@@ -95,8 +107,12 @@ def propagate(seq, seg_ref, model, lp, nclasses, do_pos_embed, use_last):
     emb = ops.l2_normalize(model(x).view(T, N, -1).float())               # utils.py:114-115
     xent = ops.horizontality_xent(emb).cpu()                              # utils.py:118-123
     change_idx = _change_point(xent)
-    label0 = first_column_labels(seg_ref, N).to(emb.device).long()        # utils.py:139-142
-    mask0 = one_hot_mask(label0, nclasses)[None]                          # utils.py:143-147
+    if seg_ref.is_cuda:                                                   # utils.py:139-147 on the device
+        label0, mask0 = ops.seed_labels(seg_ref.float(), seg_ref.shape[0], 0, 0, 1, N, nclasses)
+        label0 = label0[0].long()
+    else:
+        label0 = first_column_labels(seg_ref, N).to(emb.device).long()
+        mask0 = one_hot_mask(label0, nclasses)[None]
     labels, _, _, _ = ops.labelprop(emb[None], mask0, int(lp.cxt_size), float(lp.radius), float(lp.temperature),
                                     int(lp.topk), int(lp.mode), int(lp.precision), False, False)
     final_prediction = labels[0].t().float()                              # [N,T]
