@@ -194,6 +194,9 @@ int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, int BN, float
 /* K = 64 product with MN-major operands: A is At[64][128] when a_mn else A[128][64]; B is Bkn[64][BN] when b_mn else
  * Bt[BN][64]; BN in {64, 128}.  Pins the MN-major shared-memory descriptors (transposed operands without a copy). */
 int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a_mn, int b_mn, float* out, void* stream);
+/* CTA-pair form (tcgen05 cta_group::2 on a 2-CTA cluster): out[256,BN] = A[256,128] * B[BN,128]^T, BN multiple of 32,
+ * 32..256.  Pins the pair plumbing (leader-credited TMA, M=256 MMA, multicast commit) of the label-propagation kernel. */
+int crw_debug_umma_pair_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -231,9 +231,87 @@ umma_mn_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
 }
 
+// CTA-pair form (cta_group::2): out[256 x BN] = A[256 x 128] * B[BN x 128]^T on a cluster of two CTAs.  CTA r loads A rows
+// [128 r, 128 r + 128) and B rows [BN/2 r, BN/2 r + BN/2) into its own smem (the TMA credits the leader's mbarrier), the
+// leader issues M = 256 MMAs, the commit is multicast to both CTAs, and each CTA reads its 128 accumulator rows from its
+// own TMEM.  Pins the pair plumbing lp_topk_pair_kernel relies on.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_pair_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int half = BN / 2;
+    uint8_t* sA = smem;                     // [2 kblocks][128 rows][128 B]
+    uint8_t* sB = smem + 2 * 128 * 128;     // [2 kblocks][BN/2 rows][128 B]
+    __shared__ uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+
+    if (warp == 0) tc::tmem_alloc_pair<256>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();                     // both CTAs' barriers exist before any remote traffic
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (tid == 0) {
+        const uint32_t leader_full = tc::mapa_u32(tc::smem_u32(&bar_full), 0);
+        if (rank == 0) tc::mbar_arrive_expect_tx(&bar_full, (uint32_t)(2 * (128 + half) * 256));    // bytes of BOTH CTAs
+        for (int kb = 0; kb < 2; ++kb) {
+            tc::tma_load_2d_pair(sA + kb * 128 * 128, &mapA, kb * 64, (int)rank * 128, leader_full);
+            tc::tma_load_2d_pair(sB + kb * half * 128, &mapB, kb * 64, (int)rank * half, leader_full);
+        }
+        if (rank == 0) {
+            tc::mbar_wait(&bar_full, 0);
+            tc::tc_fence_after();
+            const uint32_t idesc = tc::umma_idesc_bf16(256, BN);
+            for (int kb = 0; kb < 2; ++kb)
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ad = tc::umma_smem_desc_k128(tc::smem_u32(sA + kb * 128 * 128) + k * 32);
+                    const uint64_t bd = tc::umma_smem_desc_k128(tc::smem_u32(sB + kb * half * 128) + k * 32);
+                    tc::umma_bf16_ss_pair(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                }
+            tc::umma_commit_pair(&bar_mma, 0b11);
+        }
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar_mma, 0);
+    tc::tc_fence_after();
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        float* o = out + (size_t)(rank * 128 + warp * 32 + lane) * BN + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (c + i < BN) o[i] = v[i];
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();                     // neither CTA may exit (or free TMEM) while the peer still uses the pair
+    if (warp == 0) tc::tmem_dealloc_pair<256>(tmem_base);
+}
+
 }  // namespace crw
 
 using namespace crw;
+
+extern "C" int crw_debug_umma_pair_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream) {
+    if (!A_bf16 || !B_bf16 || !out || BN < 32 || BN > 256 || (BN % 32)) return CRW_ERR_INVALID;
+    CUtensorMap mA, mB;
+    int rc = make_tmap_bf16_k64(&mA, A_bf16, 256, 128, 128);
+    if (rc != CRW_OK) return rc;
+    rc = make_tmap_bf16_k64(&mB, B_bf16, (uint64_t)BN, 128, (uint32_t)(BN / 2));
+    if (rc != CRW_OK) return rc;
+    const size_t smem = 1024 + 2 * 128 * 128 + (size_t)BN * 128;
+    CRW_CUDA_RET(cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_pair_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(mA, mB, BN, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
 
 extern "C" int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a_mn, int b_mn, float* out, void* stream) {
     if (!A_bf16 || !B_bf16 || !out || (BN != 64 && BN != 128)) return CRW_ERR_INVALID;
