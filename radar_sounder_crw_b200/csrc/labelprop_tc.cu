@@ -132,6 +132,53 @@ struct TopList {
     }
 };
 
+// key rows -> candidate ids, fill with out-of-band candidates when fewer than k are in band, softmax, W / I stores
+template <int KT>
+__device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& top, int rg, int n, int q, int win_lo) {
+    const int N = p.N, ctx = p.ctx, k = p.k, rb = p.rb;
+    // key row -> candidate id (slot in the trimmed key set * N + node)
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        const int kr = top.id[s];
+        const int kf = (int)__umulhi((unsigned)kr, p.magic_n), j = kr - kf * N;
+        const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
+        top.id[s] = slot * N + j;
+    }
+    // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
+    const int F = n_key_frames(n, ctx);
+    int live = 0;
+#pragma unroll
+    for (int s = 0; s < KT; ++s) live += (s < k && top.v[s] > -INFINITY) ? 1 : 0;
+    const float masked = kMaskBias;   // raw-dot domain stand-in: exp() of it is exactly 0
+    if (live < k) {
+        int need = k - live, fill = live;
+        for (int f = 0; f < F && need > 0; ++f)
+            for (int jj = 0; jj < N && need > 0; ++jj) {
+                const int dj = jj - q;
+                if (dj <= rb && -dj <= rb) continue;
+#pragma unroll
+                for (int s = 0; s < KT; ++s)
+                    if (s == fill) { top.v[s] = masked; top.id[s] = f * N + jj; }
+                ++fill; --need;
+            }
+    }
+    const float l0 = top.v[0] * p.inv_temp;
+    float e[KT], sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        e[s] = (s < k) ? pinned_expf(top.v[s] * p.inv_temp - l0) : 0.0f;
+        sum += e[s];
+    }
+    const float inv = 1.0f / sum;
+    const size_t base = ((size_t)(rg * p.T + n) * k) * N + q;
+#pragma unroll
+    for (int s = 0; s < KT; ++s)
+        if (s < k) {
+            p.W[base + (size_t)s * N] = e[s] * inv;
+            p.I[base + (size_t)s * N] = top.id[s];
+        }
+}
+
 template <int KT, int NEPI>
 __global__ void __launch_bounds__((NEPI + 2) * 32, 1)
 lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_constant__ CUtensorMap qmap_lo,
@@ -336,49 +383,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         if (x > -INFINITY) top.insert_tie(x, pi[s * 32 + lane]);
                     }
                 }
-                if (qvalid) {
-                    // key row -> candidate id (slot in the trimmed key set * N + node)
-#pragma unroll
-                    for (int s = 0; s < KT; ++s) {
-                        const int kr = top.id[s];
-                        const int kf = (int)__umulhi((unsigned)kr, p.magic_n), j = kr - kf * N;
-                        const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
-                        top.id[s] = slot * N + j;
-                    }
-                    // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
-                    const int F = n_key_frames(n, ctx);
-                    int live = 0;
-#pragma unroll
-                    for (int s = 0; s < KT; ++s) live += (s < k && top.v[s] > -INFINITY) ? 1 : 0;
-                    const float masked = kMaskBias;   // raw-dot domain stand-in: exp() of it is exactly 0
-                    if (live < k) {
-                        int need = k - live, fill = live;
-                        for (int f = 0; f < F && need > 0; ++f)
-                            for (int jj = 0; jj < N && need > 0; ++jj) {
-                                const int dj = jj - q;
-                                if (dj <= rb && -dj <= rb) continue;
-#pragma unroll
-                                for (int s = 0; s < KT; ++s)
-                                    if (s == fill) { top.v[s] = masked; top.id[s] = f * N + jj; }
-                                ++fill; --need;
-                            }
-                    }
-                    const float l0 = top.v[0] * p.inv_temp;
-                    float e[KT], sum = 0.0f;
-#pragma unroll
-                    for (int s = 0; s < KT; ++s) {
-                        e[s] = (s < k) ? pinned_expf(top.v[s] * p.inv_temp - l0) : 0.0f;
-                        sum += e[s];
-                    }
-                    const float inv = 1.0f / sum;
-                    const size_t base = ((size_t)(t.rg * p.T + n) * k) * N + q;
-#pragma unroll
-                    for (int s = 0; s < KT; ++s)
-                        if (s < k) {
-                            p.W[base + (size_t)s * N] = e[s] * inv;
-                            p.I[base + (size_t)s * N] = top.id[s];
-                        }
-                }
+                if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");   // scratch free for the next tile
         }
@@ -386,6 +391,260 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     tc::tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) tc::tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2 on 2-CTA clusters): one pair owns 256 consecutive query rows (128 per CTA) and
+// walks the union key window in 128-row key tiles, 64 rows loaded by each CTA.  Per key row streamed from L2 the pair
+// serves twice as many queries, and each SM reads only its own half of the B operand from shared memory, which is what
+// bounded the single-CTA kernel (profiles/r01_lp_tc_anatomy.txt).  Roles per CTA as above; only the leader's warp 9
+// issues MMAs, its commits are multicast to both CTAs' barriers, and the peer's epilogue warps release accumulator
+// buffers on the leader's barriers.
+// ------------------------------------------------------------------------------------------
+constexpr int kPairM = 256;         // query rows per pair tile
+constexpr int kPairN = 128;         // key rows per pair key tile (TMEM columns per accumulator buffer)
+constexpr int kPairAcc = 4;         // 4 x 128 columns = all 512
+
+__device__ __forceinline__ TileInfo pair_tile_info(const TcParams& p, int tile) {
+    TileInfo t;
+    t.rg = tile / p.tiles_per_rg;
+    t.r0 = (tile % p.tiles_per_rg) * kPairM;
+    t.n_lo = max(1, t.r0 / p.N);
+    t.n_hi = min(p.T - 1, (t.r0 + kPairM - 1) / p.N);
+    t.f_lo = max(0, t.n_lo - p.ctx);
+    t.has_f0 = (t.f_lo > 0) ? ceil_div(p.N, kPairN) : 0;
+    t.n_ktiles = (t.n_lo > t.n_hi) ? 0 : t.has_f0 + ceil_div((t.n_hi - t.f_lo) * p.N, kPairN);
+    return t;
+}
+__device__ __forceinline__ void pair_ktile_rows(const TcParams& p, const TileInfo& t, int kt, int& row0, int& nrows) {
+    if (kt < t.has_f0) { row0 = kt * kPairN; nrows = min(kPairN, p.N - row0); return; }
+    const int c = kt - t.has_f0;
+    row0 = t.f_lo * p.N + c * kPairN;
+    nrows = min(kPairN, t.n_hi * p.N - row0);
+}
+
+template <int KT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_constant__ CUtensorMap qmap_lo,
+                    const __grid_constant__ CUtensorMap kmap_hi, const __grid_constant__ CUtensorMap kmap_lo, TcParams p) {
+    constexpr int NEPI = 8, kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
+    constexpr int kParkWarp = kParkBytes / NEPI;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                  // 64 KB: this CTA's 128 query rows
+    uint8_t* sK = smem + kQBytes;                        // kStages x 32 KB: this CTA's 64 rows of each key tile
+    uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
+    __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kPairAcc], acc_empty[kPairAcc];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == kMmaWarp) tc::tmem_alloc_pair<512>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&q_full, 1);
+        tc::mbar_init(&q_empty, 1);
+        for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
+        for (int a = 0; a < kPairAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 2 * NEPI); }
+        tc::fence_barrier_init();
+    }
+    if (warp == kProducerWarp && lane == 0) {
+        tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == kProducerWarp) {
+        // ================= TMA producer (both CTAs; the leader also arms the barriers with both CTAs' bytes) =================
+        const bool leader_lane = tc::elect_one();
+        const uint32_t q_full_l = tc::mapa_u32(tc::smem_u32(&q_full), 0);
+        uint32_t kcnt = 0, tcnt = 0;
+        for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+            const TileInfo t = pair_tile_info(p, tile);
+            if (t.n_ktiles == 0) continue;
+            const int grow = t.rg * p.T * N;
+            tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
+            if (leader_lane) {
+                if (rank == 0) tc::mbar_arrive_expect_tx(&q_full, 2 * kQBytes);
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub)
+                    tc::tma_load_2d_pair(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64,
+                                         grow + t.r0 + (int)rank * kBM, q_full_l);
+            }
+            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                const int s = kcnt % kStages;
+                int row0, nrows;
+                pair_ktile_rows(p, t, kt, row0, nrows);
+                tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+                if (leader_lane) {
+                    const uint32_t k_full_l = tc::mapa_u32(tc::smem_u32(&k_full[s]), 0);
+                    if (rank == 0) tc::mbar_arrive_expect_tx(&k_full[s], 2 * kKBytes);
+                    uint8_t* dst = sK + s * kKBytes;
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub)
+                        tc::tma_load_2d_pair(dst + sub * (kBN * 128), (sub & 2) ? &kmap_lo : &kmap_hi, (sub & 1) * 64,
+                                             grow + row0 + (int)rank * kBN, k_full_l);
+                }
+            }
+            ++tcnt;
+        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer: leader CTA only =================
+        if (rank == 0) {
+            const bool leader_lane = tc::elect_one();
+            const uint64_t qdesc = tc::umma_smem_desc_k128(tc::smem_u32(sQ));
+            const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
+            const uint32_t idesc = tc::umma_idesc_bf16(kPairM, kPairN);
+            uint32_t kcnt = 0, tcnt = 0;
+            for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+                const TileInfo t = pair_tile_info(p, tile);
+                if (t.n_ktiles == 0) continue;
+                tc::mbar_wait_backoff(&q_full, tcnt & 1);
+                for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                    const int s = kcnt % kStages, a = kcnt % kPairAcc;
+                    tc::mbar_wait(&k_full[s], (kcnt / kStages) & 1);
+                    tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kPairAcc) & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint64_t kdesc = kdesc0 + (uint64_t)((s * kKBytes) >> 4);
+                    const uint32_t d = tmem_base + (uint32_t)(a * kPairN);
+                    if (leader_lane) {
+                        if (!(p.debug & 4))
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const int qpart = (pass == 2) ? 2 : 0, kpart = (pass == 1) ? 2 : 0;
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t ad = qdesc + (uint64_t)((((qpart + kb) * (kBM * 128)) + ks * 32) >> 4);
+                                    const uint64_t bd = kdesc + (uint64_t)((((kpart + kb) * (kBN * 128)) + ks * 32) >> 4);
+                                    tc::umma_bf16_ss_pair(d, ad, bd, idesc, (pass | kb | ks) ? 1u : 0u);
+                                }
+                        }
+                        tc::umma_commit_pair(&k_empty[s], 0b11);
+                        tc::umma_commit_pair(&acc_full[a], 0b11);
+                    }
+                    __syncwarp();
+                }
+                if (leader_lane) tc::umma_commit_pair(&q_empty, 0b11);
+                __syncwarp();
+                ++tcnt;
+            }
+        }
+    } else {
+        // ================= epilogue: 8 warps; thread = query row (TMEM lane); part p = columns [64p, 64p+64) of every key tile =====
+        const int g = warp & 3, part = warp >> 2;
+        const int lrow = (int)rank * kBM + g * 32 + lane;
+        const int rb = p.rb, ctx = p.ctx, k = p.k;
+        const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
+        uint32_t kcnt = 0;
+        for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+            const TileInfo t = pair_tile_info(p, tile);
+            if (t.n_ktiles == 0) continue;
+            const int row = t.r0 + lrow;
+            const int n = row / N, q = row - n * N;
+            const bool qvalid = (n >= 1) && (n < p.T);
+            const int win_lo = (n > ctx + 1) ? n - ctx : 1;
+            TopList<KT> top;
+            top.init();
+            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+                const int a = kcnt % kPairAcc;
+                int row0, nrows;
+                pair_ktile_rows(p, t, kt, row0, nrows);
+                row0 += part * kBN;                                   // this part's 64-column half
+                nrows = min(kBN, nrows - part * kBN);
+                tc::mbar_wait(&acc_full[a], (kcnt / kPairAcc) & 1);
+                tc::tc_fence_after();
+                if (nrows > 0) {
+                    const float thr = top.v[KT - 1];
+                    uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (ch * 32 < nrows && !(p.debug & 2)) {
+                            float v[32];
+                            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kPairN + part * kBN + ch * 32), v);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                tc::sts_f32(park + (ch * 32 + i) * 128, v[i]);
+                                pm[ch] |= (v[i] > thr) ? (1u << i) : 0u;
+                            }
+                        }
+                    }
+                    {
+                        const int kf0 = (int)__umulhi((unsigned)row0, p.magic_n);
+                        int c = 0, kf = kf0, j = row0 - kf0 * N;
+                        while (c < nrows) {
+                            const int seg = min(nrows - c, N - j);
+                            if ((kf < n) && (kf == 0 || kf >= win_lo)) {
+                                const int lo = max(j, q - rb), hi = min(j + seg - 1, q + rb);
+                                if (lo <= hi) {
+                                    const int b0 = c + lo - j, nb = hi - lo + 1;
+                                    const unsigned long long m64 = ((nb >= 64) ? ~0ull : ((1ull << nb) - 1ull)) << b0;
+                                    vm[0] |= (uint32_t)m64;
+                                    vm[1] |= (uint32_t)(m64 >> 32);
+                                }
+                            }
+                            c += seg; j = 0; ++kf;
+                        }
+                    }
+                    uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
+                    if (p.debug & 3) { c0 = 0; c1 = 0; }
+                    while (c0 | c1) {
+                        int i;
+                        if (c0) { i = __ffs(c0) - 1; c0 &= c0 - 1; }
+                        else { i = 32 + __ffs(c1) - 1; c1 &= c1 - 1; }
+                        const float x = tc::lds_f32(park + i * 128);
+                        if (x > top.v[KT - 1]) top.insert(x, row0 + i);
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&acc_empty[a]), 0));
+            }
+            // ---- merge the two column-half lists of every query (warps 4-7 -> smem -> warps 0-3) ----
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
+            int* mi = reinterpret_cast<int*>(mv + KT * 32);
+            if (part != 0) {
+#pragma unroll
+                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            if (part == 0) {
+                const float* pv = reinterpret_cast<const float*>(park_base + (4 + g) * kParkWarp);
+                const int* pi = reinterpret_cast<const int*>(pv + KT * 32);
+                for (int s = 0; s < KT; ++s) {
+                    const float x = pv[s * 32 + lane];
+                    if (x > -INFINITY) top.insert_tie(x, pi[s * 32 + lane]);
+                }
+                if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+        }
+    }
+    tc::tc_fence_before();
+    tc::cluster_sync();
+    if (warp == kMmaWarp) tc::tmem_dealloc_pair<512>(tmem_base);
+}
+
+template <int KT>
+static int launch_pair(const CUtensorMap* maps, TcParams p, cudaStream_t st) {
+    const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
+    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_pair_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p.tiles_per_rg = ceil_div(p.T * p.N, kPairM);
+    p.total_tiles = p.R * p.tiles_per_rg;
+    const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+    lp_topk_pair_kernel<KT><<<2 * clusters, 320, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
 }
 
 template <int KT, int NEPI>
@@ -428,6 +687,15 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.tiles_per_rg = ceil_div(T * N, kBM);
     p.total_tiles = R * p.tiles_per_rg;
+    // The CTA-pair kernel is correct (tests run it) and has the cheaper MMA side (68 vs 78 us with the selection switched
+    // off), but at BASELINE config 3 the selection epilogue bounds both kernels and the pair form pays more per-tile
+    // overhead there (153 vs 143 us, profiles/r01_lp_pair_anatomy.txt): opt-in until the epilogue is the smaller half.
+    { const char* e = getenv("CRW_LP_PAIR"); if (e && atoi(e) != 0) {
+        if (k <= 10) return launch_pair<10>(maps, p, st);
+        if (k <= 16) return launch_pair<16>(maps, p, st);
+        if (k <= 20) return launch_pair<20>(maps, p, st);
+        return launch_pair<32>(maps, p, st);
+    } }
     if (k <= 10) return launch_tc<10, 8>(maps, p, st);
     if (k <= 16) return launch_tc<16, 8>(maps, p, st);
     if (k <= 20) return launch_tc<20, 8>(maps, p, st);

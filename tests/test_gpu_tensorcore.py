@@ -100,8 +100,15 @@ def _dev(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
 
 
+@pytest.fixture(params=["single", "pair"])
+def lp_kernel(request, monkeypatch):
+    """Both tensor-path kernels: the single-CTA one (default) and the CTA-pair one (cta_group::2, env CRW_LP_PAIR=1)."""
+    monkeypatch.setenv("CRW_LP_PAIR", "1" if request.param == "pair" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("case", TC_CASES)
-def test_lp_tensorcore_vs_fp32_oracle(pkg, case):
+def test_lp_tensorcore_vs_fp32_oracle(pkg, case, lp_kernel):
     R, T, N, M, ctx, k, radius, clustered = case
     rs = np.random.RandomState(200 + TC_CASES.index(case))
     feats = rs.randn(R, T, N, 128).astype(np.float32)
@@ -124,7 +131,7 @@ def test_lp_tensorcore_vs_fp32_oracle(pkg, case):
     assert np.abs(W[:, 1:].sum(2) - 1).max() < 1e-5
 
 
-def test_lp_tensorcore_golden_reference_labels(pkg):
+def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
     for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
         g = lp_case(name)
