@@ -197,6 +197,9 @@ int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a
 /* CTA-pair form (tcgen05 cta_group::2 on a 2-CTA cluster): out[256,BN] = A[256,128] * B[BN,128]^T, BN multiple of 32,
  * 32..256.  Pins the pair plumbing (leader-credited TMA, M=256 MMA, multicast commit) of the label-propagation kernel. */
 int crw_debug_umma_pair_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
+/* Profiling aid for the tensor-path top-k kernel: with env CRW_TC_DEBUG bit 3 set the epilogue warps accumulate cycles per
+ * phase; this copies the 160 x 8 x 6 uint64 counters to HOST memory (synchronising) and clears them when `reset`. */
+int crw_debug_lp_profile(unsigned long long* host_out, int reset);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,11 @@ __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t,
     nrows = min(kBN, t.n_hi * p.N - row0);
 }
 
+// profiling aid (CRW_TC_DEBUG bit 3): cycles each epilogue warp spends per phase, summed over the launch
+//   [0] waiting for an accumulator  [1] tcgen05.ld + park + threshold mask  [2] validity mask  [3] insertion loop
+//   [4] merge + finish + stores     [5] insertion-loop iterations (count, not cycles)
+__device__ unsigned long long g_lp_prof[160 * 8 * 6];
+
 template <int KT>
 struct TopList {
     float v[KT];
@@ -131,6 +136,21 @@ struct TopList {
         id[0] = g[0] ? xid : id[0];
     }
 };
+
+// Filter threshold of one partial list.  The lists of the other parts of the same query (same lane, warps 4 apart) cover
+// disjoint key columns, so their k-th best values are lower bounds on the query's final k-th best as well: a candidate
+// strictly below any of them cannot survive the merge.  Equal values may still win the merge on the id tie rule, hence
+// the partner bound is taken one ulp down and the comparison stays strict.  Stale (smaller) published values are safe.
+template <int NEPI>
+__device__ __forceinline__ float shared_threshold(const float* thr_pub, int warp, int lane, float own) {
+    float t = own;
+#pragma unroll
+    for (int pp = 1; pp < NEPI / 4; ++pp) {
+        const float o = *reinterpret_cast<const volatile float*>(&thr_pub[((warp + 4 * pp) % NEPI) * 32 + lane]);
+        t = fmaxf(t, nextafterf(o, -INFINITY));
+    }
+    return t;
+}
 
 // key rows -> candidate ids, fill with out-of-band candidates when fewer than k are in band, softmax, W / I stores
 template <int KT>
@@ -194,6 +214,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float thr_pub[NEPI * 32];     // every list's current k-th best, read by the other part(s) of the same query
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
@@ -206,6 +227,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
         tc::fence_barrier_init();
     }
+    if (tid < NEPI * 32) thr_pub[tid] = -INFINITY;
     if (warp == kProducerWarp && lane == 0) {
         tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
     }
@@ -316,9 +338,12 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 const int a = kcnt % kAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
+                const bool prof = (p.debug & 8) != 0;
+                long long c_0 = prof ? clock64() : 0;
                 tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
                 tc::tc_fence_after();
-                const float thr = top.v[KT - 1];
+                long long c_1 = prof ? clock64() : 0;
+                const float thr = shared_threshold<NEPI>(thr_pub, warp, lane, top.v[KT - 1]);
                 uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
@@ -333,6 +358,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         }
                     }
                 }
+                long long c_2 = prof ? clock64() : 0;
                 // validity mask of this thread over the tile's key rows (segments = key frames)
                 {
                     const int kf0 = (int)__umulhi((unsigned)row0, p.magic_n);
@@ -353,19 +379,34 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
                 uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
                 if (p.debug & 3) { c0 = 0; c1 = 0; }
+                long long c_3 = prof ? clock64() : 0;
+                int iters = 0;
                 while (c0 | c1) {
-                    int i;
-                    if (c0) { i = __ffs(c0) - 1; c0 &= c0 - 1; }
-                    else { i = 32 + __ffs(c1) - 1; c1 &= c1 - 1; }
-                    const float x = tc::lds_f32(park + i * 128);
-                    if (x > top.v[KT - 1]) top.insert(x, row0 + i);
+                    // branch-free pop of the lowest set bit of (c1:c0); insert() is a no-op for x <= the k-th best
+                    const bool in_lo = c0 != 0u;
+                    const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
+                    const int i = __ffs(w) - 1 + (in_lo ? 0 : 32);
+                    c0 = in_lo ? nw : c0;
+                    c1 = in_lo ? c1 : nw;
+                    top.insert(tc::lds_f32(park + i * 128), row0 + i);
+                    if (prof) ++iters;
                 }
+                thr_pub[warp * 32 + lane] = top.v[KT - 1];
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+                if (prof) {
+                    const long long c_4 = clock64();
+                    iters = __reduce_max_sync(0xffffffffu, iters);
+                    if (lane == 0) {
+                        unsigned long long* g = g_lp_prof + ((size_t)blockIdx.x * 8 + warp) * 6;
+                        g[0] += c_1 - c_0; g[1] += c_2 - c_1; g[2] += c_3 - c_2; g[3] += c_4 - c_3; g[5] += iters;
+                    }
+                }
             }
             // ---- merge the kParts lists of every query (warps part>0 -> smem -> warp part 0) ----
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");   // every epilogue warp is done with its park buffer
+            const long long c_m = (p.debug & 8) ? clock64() : 0;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // every epilogue warp is done with its park buffer
             float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
             int* mi = reinterpret_cast<int*>(mv + KT * 32);
             static_assert(KT * 32 * 8 <= kParkWarp, "merge scratch must fit the warp's park buffer");
@@ -373,7 +414,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
 #pragma unroll
                 for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             if (part == 0) {
                 for (int pp = 1; pp < kParts; ++pp) {
                     const float* pv = reinterpret_cast<const float*>(park_base + (pp * 4 + g) * kParkWarp);
@@ -385,7 +426,9 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");   // scratch free for the next tile
+            thr_pub[warp * 32 + lane] = -INFINITY;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // scratch free for the next tile
+            if ((p.debug & 8) && lane == 0) g_lp_prof[((size_t)blockIdx.x * 8 + warp) * 6 + 4] += clock64() - c_m;
         }
     }
     tc::tc_fence_before();
@@ -436,6 +479,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
     uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kPairAcc], acc_empty[kPairAcc];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float thr_pub[NEPI * 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
@@ -450,6 +494,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
         for (int a = 0; a < kPairAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 2 * NEPI); }
         tc::fence_barrier_init();
     }
+    if (tid < NEPI * 32) thr_pub[tid] = -INFINITY;
     if (warp == kProducerWarp && lane == 0) {
         tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
     }
@@ -560,7 +605,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                 tc::mbar_wait(&acc_full[a], (kcnt / kPairAcc) & 1);
                 tc::tc_fence_after();
                 if (nrows > 0) {
-                    const float thr = top.v[KT - 1];
+                    const float thr = shared_threshold<NEPI>(thr_pub, warp, lane, top.v[KT - 1]);
                     uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
@@ -595,26 +640,28 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                     uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
                     if (p.debug & 3) { c0 = 0; c1 = 0; }
                     while (c0 | c1) {
-                        int i;
-                        if (c0) { i = __ffs(c0) - 1; c0 &= c0 - 1; }
-                        else { i = 32 + __ffs(c1) - 1; c1 &= c1 - 1; }
-                        const float x = tc::lds_f32(park + i * 128);
-                        if (x > top.v[KT - 1]) top.insert(x, row0 + i);
+                        const bool in_lo = c0 != 0u;
+                        const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
+                        const int i = __ffs(w) - 1 + (in_lo ? 0 : 32);
+                        c0 = in_lo ? nw : c0;
+                        c1 = in_lo ? c1 : nw;
+                        top.insert(tc::lds_f32(park + i * 128), row0 + i);
                     }
                 }
+                thr_pub[warp * 32 + lane] = top.v[KT - 1];
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&acc_empty[a]), 0));
             }
             // ---- merge the two column-half lists of every query (warps 4-7 -> smem -> warps 0-3) ----
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
             int* mi = reinterpret_cast<int*>(mv + KT * 32);
             if (part != 0) {
 #pragma unroll
                 for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             if (part == 0) {
                 const float* pv = reinterpret_cast<const float*>(park_base + (4 + g) * kParkWarp);
                 const int* pi = reinterpret_cast<const int*>(pv + KT * 32);
@@ -624,7 +671,8 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                 }
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NEPI * 32) : "memory");
+            thr_pub[warp * 32 + lane] = -INFINITY;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
         }
     }
     tc::tc_fence_before();
@@ -702,4 +750,17 @@ int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float ra
     return launch_tc<32, 8>(maps, p, st);
 }
 
+int lp_profile_read(unsigned long long* host_out, int reset) {
+    if (host_out) CRW_CUDA_RET(cudaMemcpyFromSymbol(host_out, g_lp_prof, sizeof(g_lp_prof)));
+    if (reset) {
+        void* ptr = nullptr;
+        CRW_CUDA_RET(cudaGetSymbolAddress(&ptr, g_lp_prof));
+        CRW_CUDA_RET(cudaMemset(ptr, 0, sizeof(g_lp_prof)));
+    }
+    return CRW_OK;
+}
+
 }  // namespace crw
+
+// profiling aid: copies the per-warp phase counters (160 x 8 x 6 uint64) to host memory and optionally clears them
+extern "C" int crw_debug_lp_profile(unsigned long long* host_out, int reset) { return crw::lp_profile_read(host_out, reset); }

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Profiling aid: per-phase cycle counters of the tensor-path top-k epilogue (CRW_TC_DEBUG=8) at BASELINE config 3."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import radar_sounder_crw_b200 as crw  # noqa: E402
+
+T, N, C, M = 1250, 49, 128, 4
+torch.manual_seed(11)
+feats = torch.randn(1, T, N, C, device="cuda")
+mask0 = torch.nn.functional.one_hot(torch.randint(0, M, (1, N), device="cuda"), M).permute(0, 2, 1).float().contiguous()
+os.environ["CRW_LP_PAIR"] = "0"
+os.environ["CRW_TC_DEBUG"] = "8"
+L = crw._lib.lib()
+buf = np.zeros(160 * 8 * 6, dtype=np.uint64)
+crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, crw.ops.PREC_BF16X3, True, False)
+torch.cuda.synchronize()
+L.crw_debug_lp_profile(None, 1)
+crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, crw.ops.PREC_BF16X3, True, False)
+torch.cuda.synchronize()
+L.crw_debug_lp_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
+p = buf.reshape(160, 8, 6).astype(np.float64)[:148]
+names = ["wait acc_full", "ld+park+mask", "validity", "insert loop", "merge+finish", "iterations"]
+print("per-warp totals over the launch (cycles; mean / max over the 148 x 8 epilogue warps):")
+for i, nm in enumerate(names):
+    print(f"  {nm:14s} mean {p[:, :, i].mean():10.0f}   max {p[:, :, i].max():10.0f}")
+tot = p[:, :, :5].sum(2)
+print(f"  sum of phases  mean {tot.mean():10.0f}   max {tot.max():10.0f}   (1 us = ~1965 cycles)")
+print("  part 0 vs part 1 insert-loop cycles:", p[:, :4, 3].mean(), p[:, 4:, 3].mean())
+print("  cycles per insertion-loop iteration:", p[:, :, 3].sum() / max(p[:, :, 5].sum(), 1))
