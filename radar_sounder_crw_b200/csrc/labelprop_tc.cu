@@ -137,6 +137,20 @@ struct TopList {
     }
 };
 
+// Branch-free pop of the lowest set bit of the candidate mask (c1:c0) and fetch of that column from the lane's park
+// slots.  Returns false (x = -inf, a no-op for insert()) when the mask is empty; the fetch then reads slot 31, in range.
+__device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32_t park, int row0, float& x, int& xid) {
+    const bool any = (c0 | c1) != 0u, in_lo = c0 != 0u;
+    const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
+    const int i = (__ffs(w) - 1 + (in_lo ? 0 : 32)) & 63;
+    c0 = in_lo ? nw : c0;
+    c1 = in_lo ? c1 : nw;
+    const float v = tc::lds_f32(park + i * 128);
+    x = any ? v : -INFINITY;
+    xid = row0 + i;
+    return any;
+}
+
 // Filter threshold of one partial list.  The lists of the other parts of the same query (same lane, warps 4 apart) cover
 // disjoint key columns, so their k-th best values are lower bounds on the query's final k-th best as well: a candidate
 // strictly below any of them cannot survive the merge.  Equal values may still win the merge on the id tie rule, hence
@@ -381,15 +395,17 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 if (p.debug & 3) { c0 = 0; c1 = 0; }
                 long long c_3 = prof ? clock64() : 0;
                 int iters = 0;
-                while (c0 | c1) {
-                    // branch-free pop of the lowest set bit of (c1:c0); insert() is a no-op for x <= the k-th best
-                    const bool in_lo = c0 != 0u;
-                    const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
-                    const int i = __ffs(w) - 1 + (in_lo ? 0 : 32);
-                    c0 = in_lo ? nw : c0;
-                    c1 = in_lo ? c1 : nw;
-                    top.insert(tc::lds_f32(park + i * 128), row0 + i);
-                    if (prof) ++iters;
+                {
+                    // software-pipelined: the next candidate is popped and fetched while the current one is inserted
+                    float x; int xid;
+                    bool have = pop_candidate(c0, c1, park, row0, x, xid);
+                    while (have) {
+                        float xn; int xidn;
+                        const bool have_n = pop_candidate(c0, c1, park, row0, xn, xidn);
+                        top.insert(x, xid);
+                        x = xn; xid = xidn; have = have_n;
+                        if (prof) ++iters;
+                    }
                 }
                 thr_pub[warp * 32 + lane] = top.v[KT - 1];
                 tc::tc_fence_before();
@@ -639,13 +655,15 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                     }
                     uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
                     if (p.debug & 3) { c0 = 0; c1 = 0; }
-                    while (c0 | c1) {
-                        const bool in_lo = c0 != 0u;
-                        const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
-                        const int i = __ffs(w) - 1 + (in_lo ? 0 : 32);
-                        c0 = in_lo ? nw : c0;
-                        c1 = in_lo ? c1 : nw;
-                        top.insert(tc::lds_f32(park + i * 128), row0 + i);
+                    {
+                        float x; int xid;
+                        bool have = pop_candidate(c0, c1, park, row0, x, xid);
+                        while (have) {
+                            float xn; int xidn;
+                            const bool have_n = pop_candidate(c0, c1, park, row0, xn, xidn);
+                            top.insert(x, xid);
+                            x = xn; xid = xidn; have = have_n;
+                        }
                     }
                 }
                 thr_pub[warp * 32 + lane] = top.v[KT - 1];
