@@ -594,40 +594,57 @@ extern "C" int crw_affinity_topk(const float* keys, const float* queries, int n_
     return CRW_ERR_UNSUPPORTED;
 }
 
-extern "C" int crw_label_gather(const float* W, const int32_t* I, const float* mask0, int R, int T, int N, int M,
-                                int ctx, int k, int mode, int32_t* labels, float* masks, void* stream) {
+// frames that must run in order: all of them in fixed mode, the first ctx+1 in ref_exact mode
+static int gather_seq_end(const GatherParams& p) { return p.mode_fixed ? p.T : min(p.T, p.ctx + 2); }
+
+static int gather_launch_seq(const GatherParams& p, cudaStream_t st) {
+    const int seq_end = gather_seq_end(p);
+    const size_t gsmem = ((size_t)(p.ctx + 2) * p.M * p.N + 4 * (size_t)p.k * p.N + (size_t)p.k * p.M * p.N) * sizeof(float);
+    if (gsmem <= 200 * 1024) {
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        lp_gather_seq_smem_kernel<<<p.R, 256, gsmem, st>>>(p, seq_end);
+    } else {
+        lp_gather_seq_kernel<<<p.R, 256, 0, st>>>(p, 1, seq_end, 1);
+    }
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+static int gather_launch_par(const GatherParams& p, cudaStream_t st) {
+    const int seq_end = gather_seq_end(p), T = p.T;
+    if (seq_end >= T) return CRW_OK;
+    const long long total = (long long)(T - seq_end) * p.N;
+    long long gx64 = (total + 255) / 256; int gx = (int)(gx64 < 148LL * 8 ? gx64 : 148LL * 8);
+    const size_t psmem = (size_t)(p.ctx + 1) * p.M * p.N * sizeof(float);
+    if (psmem <= 96 * 1024) {     // ref_exact only reaches here (fixed mode is sequential throughout)
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_par_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        if (gx > 148 * 2) gx = 148 * 2;
+        lp_gather_par_smem_kernel<<<dim3(gx, p.R), 256, psmem, st>>>(p, seq_end, T);
+    } else {
+        lp_gather_par_kernel<<<dim3(gx, p.R), 256, 0, st>>>(p, seq_end, T);
+    }
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+static int gather_params(GatherParams& p, const float* W, const int32_t* I, const float* mask0, int R, int T, int N, int M, int ctx,
+                         int k, int mode, int32_t* labels, float* masks) {
     if (!W || !I || !mask0 || !labels || !masks) return CRW_ERR_INVALID;
     if (R < 0 || T < 1 || N < 1 || M < 1 || ctx < 1 || k < 1) return CRW_ERR_INVALID;
     if (mode != CRW_LP_REF_EXACT && mode != CRW_LP_FIXED) return CRW_ERR_INVALID;
-    if (R == 0) return CRW_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    GatherParams p;
     p.W = W; p.I = I; p.mask0 = mask0; p.labels = labels; p.masks = masks;
     p.R = R; p.T = T; p.N = N; p.M = M; p.ctx = ctx; p.k = k; p.mode_fixed = (mode == CRW_LP_FIXED);
-    // frames that must run in order: all of them in fixed mode, the first ctx+1 in ref_exact mode
-    const int seq_end = p.mode_fixed ? T : min(T, ctx + 2);
-    const size_t gsmem = ((size_t)(ctx + 2) * M * N + 4 * (size_t)k * N + (size_t)k * M * N) * sizeof(float);
-    if (gsmem <= 200 * 1024) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        lp_gather_seq_smem_kernel<<<R, 256, gsmem, st>>>(p, seq_end);
-    } else {
-        lp_gather_seq_kernel<<<R, 256, 0, st>>>(p, 1, seq_end, 1);
-    }
-    CRW_LAUNCH_RET();
-    if (seq_end < T) {
-        const long long total = (long long)(T - seq_end) * N;
-        long long gx64 = (total + 255) / 256; int gx = (int)(gx64 < 148LL * 8 ? gx64 : 148LL * 8);
-        const size_t psmem = (size_t)(ctx + 1) * M * N * sizeof(float);
-        if (psmem <= 96 * 1024) {     // ref_exact only reaches here (fixed mode is sequential throughout)
-            CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_par_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            if (gx > 148 * 2) gx = 148 * 2;
-            lp_gather_par_smem_kernel<<<dim3(gx, R), 256, psmem, st>>>(p, seq_end, T);
-        } else {
-            lp_gather_par_kernel<<<dim3(gx, R), 256, 0, st>>>(p, seq_end, T);
-        }
-        CRW_LAUNCH_RET();
-    }
     return CRW_OK;
+}
+
+extern "C" int crw_label_gather(const float* W, const int32_t* I, const float* mask0, int R, int T, int N, int M,
+                                int ctx, int k, int mode, int32_t* labels, float* masks, void* stream) {
+    GatherParams p;
+    int rc = gather_params(p, W, I, mask0, R, T, N, M, ctx, k, mode, labels, masks);
+    if (rc != CRW_OK) return rc;
+    if (R == 0) return CRW_OK;
+    if ((rc = gather_launch_seq(p, (cudaStream_t)stream)) != CRW_OK) return rc;
+    return gather_launch_par(p, (cudaStream_t)stream);
 }
 
 extern "C" int crw_label_gather_step(const float* W, const int32_t* I, const float* lbl, int F, int N, int M, int k,
@@ -640,9 +657,37 @@ extern "C" int crw_label_gather_step(const float* W, const int32_t* I, const flo
 }
 
 namespace crw {
-int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
-               float* W, int32_t* I, void* scratch, cudaStream_t st);
+// tensor path (labelprop_tc.cu): prep kernel + plan, then top-k launches over ranges of schedule slots
+struct LpTcPlanStorage { alignas(64) unsigned char bytes[1024]; };
+int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
+                  float* W, int32_t* I, void* scratch, cudaStream_t st, void* plan_storage);
+int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st);
+int lp_tc_total_slots(const void* plan_storage);
+int lp_tc_early_slots(const void* plan_storage);
 }
+
+// A second, higher-priority stream and two events per device, created on first use: the tensor path forks the early query
+// tiles + the sequential label gather onto it so that they overlap the bulk of the top-k (fork / join by events only,
+// nothing synchronises with the host; the enqueue sequence is serialised by a mutex because the events are shared).
+#include <mutex>
+namespace {
+struct SideCtx { cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool ok = false; std::mutex mu; };
+SideCtx* side_ctx() {
+    static SideCtx ctx[64];
+    static std::once_flag once[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::call_once(once[dev], [dev]() {
+        SideCtx& c = ctx[dev];
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // hi = numerically lowest = greatest priority
+        c.ok = cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, hi) == cudaSuccess &&
+               cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) == cudaSuccess;
+    });
+    return ctx[dev].ok ? &ctx[dev] : nullptr;
+}
+}  // namespace
 
 extern "C" size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k, int precision, int do_normalize,
                                               int have_topk_out) {
@@ -675,9 +720,35 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
             sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
             It = reinterpret_cast<int32_t*>(sp);
         }
-        int rc = lp_topk_tc(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, (cudaStream_t)stream);
+        cudaStream_t st = (cudaStream_t)stream;
+        GatherParams gp;
+        int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
         if (rc != CRW_OK) return rc;
-        return crw_label_gather(Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks, stream);
+        LpTcPlanStorage plan;
+        if ((rc = lp_tc_prepare(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, st, plan.bytes)) != CRW_OK) return rc;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int total = lp_tc_total_slots(plan.bytes), early = lp_tc_early_slots(plan.bytes);
+        // fork only when there is something to overlap: ref_exact mode (later frames do not depend on each other), query
+        // tiles beyond the early ones, and few enough early tiles that they are a side job
+        const char* nofork = getenv("CRW_LP_NO_FORK");
+        SideCtx* sc = (gp.mode_fixed || early >= total || early > sms / 2 || (nofork && atoi(nofork))) ? nullptr : side_ctx();
+        if (!sc) {
+            if ((rc = lp_tc_launch(plan.bytes, 0, total, sms, st)) != CRW_OK) return rc;
+            if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
+            return gather_launch_par(gp, st);
+        }
+        std::lock_guard<std::mutex> lock(sc->mu);
+        CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));                       // prep done
+        CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
+        if ((rc = lp_tc_launch(plan.bytes, 0, early, sms, sc->s2)) != CRW_OK) return rc;            // frames 1..ctx+1 (and a few more)
+        if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;                              // the true recurrence
+        CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
+        const int bulk_ctas = (early <= sms / 8) ? sms - early : sms;         // leave the early tiles their SMs when they are few
+        if ((rc = lp_tc_launch(plan.bytes, early, total, bulk_ctas, st)) != CRW_OK) return rc;
+        CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
+        return gather_launch_par(gp, st);
     }
     if (precision != CRW_PREC_FP32) return CRW_ERR_UNSUPPORTED;
     const float* emb = feats;

@@ -65,8 +65,17 @@ struct TcParams {
     int R, T, N, ctx, rb, k;
     float inv_temp;
     int tiles_per_rg, total_tiles;
+    int early_per_rg;   // leading tiles of every radargram that hold the query rows of frames 0..ctx+1 (scheduled first)
+    int v_begin, v_end; // range of schedule slots this launch walks (slot -> tile: early tiles of all radargrams first)
     unsigned magic_n;   // floor(2^32 / N) + 1: x / N == __umulhi(x, magic_n) for x * N < 2^32
     int debug;          // profiling aid (env CRW_TC_DEBUG): 1 = skip insertions, 2 = also skip filter/park; results invalid
+};
+
+// host-side plan of one tensor-path call (opaque to labelprop_f32.cu: it only sees the size)
+struct LpTcPlan {
+    alignas(64) unsigned char maps[4 * sizeof(CUtensorMap)];
+    TcParams p;
+    int pair;
 };
 
 struct TileInfo {
@@ -77,10 +86,20 @@ struct TileInfo {
     int n_ktiles;        // key tiles including the frame-0 tiles
 };
 
+// schedule slot -> (radargram, tile within it): the early tiles of all radargrams occupy the first R * early_per_rg slots so
+// that the sequential part of the label gather (frames 1..ctx+1) can start while the rest of the top-k is still running
+__device__ __forceinline__ void slot_to_tile(const TcParams& p, int v, int& rg, int& tt) {
+    const int E = p.early_per_rg, early_total = p.R * E;
+    if (v < early_total) { rg = v / E; tt = v - rg * E; return; }
+    const int w = v - early_total, rest = p.tiles_per_rg - E;
+    rg = w / rest;
+    tt = E + (w - rg * rest);
+}
 __device__ __forceinline__ TileInfo tile_info(const TcParams& p, int tile) {
     TileInfo t;
-    t.rg = tile / p.tiles_per_rg;
-    t.r0 = (tile % p.tiles_per_rg) * kBM;
+    int tt;
+    slot_to_tile(p, tile, t.rg, tt);
+    t.r0 = tt * kBM;
     t.n_lo = max(1, t.r0 / p.N);
     t.n_hi = min(p.T - 1, (t.r0 + kBM - 1) / p.N);
     t.f_lo = max(0, t.n_lo - p.ctx);
@@ -254,7 +273,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         // ================= TMA producer (whole warp runs the loop; one elected lane issues) =================
         const bool leader = tc::elect_one();
         uint32_t kcnt = 0, tcnt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int grow = t.rg * p.T * N;   // first global row of this radargram
@@ -286,7 +305,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const uint64_t qdesc = tc::umma_smem_desc_k128(tc::smem_u32(sQ));     // descriptor of sub-tile 0, k-step 0
         const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
         uint32_t kcnt = 0, tcnt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             tc::mbar_wait_backoff(&q_full, tcnt & 1);
@@ -338,7 +357,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
         uint32_t kcnt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int row = t.r0 + lrow;
@@ -466,8 +485,9 @@ constexpr int kPairAcc = 4;         // 4 x 128 columns = all 512
 
 __device__ __forceinline__ TileInfo pair_tile_info(const TcParams& p, int tile) {
     TileInfo t;
-    t.rg = tile / p.tiles_per_rg;
-    t.r0 = (tile % p.tiles_per_rg) * kPairM;
+    int tt;
+    slot_to_tile(p, tile, t.rg, tt);
+    t.r0 = tt * kPairM;
     t.n_lo = max(1, t.r0 / p.N);
     t.n_hi = min(p.T - 1, (t.r0 + kPairM - 1) / p.N);
     t.f_lo = max(0, t.n_lo - p.ctx);
@@ -524,7 +544,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
         const bool leader_lane = tc::elect_one();
         const uint32_t q_full_l = tc::mapa_u32(tc::smem_u32(&q_full), 0);
         uint32_t kcnt = 0, tcnt = 0;
-        for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        for (int tile = p.v_begin + cluster_id; tile < p.v_end; tile += n_clusters) {
             const TileInfo t = pair_tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int grow = t.rg * p.T * N;
@@ -561,7 +581,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
             const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
             const uint32_t idesc = tc::umma_idesc_bf16(kPairM, kPairN);
             uint32_t kcnt = 0, tcnt = 0;
-            for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+            for (int tile = p.v_begin + cluster_id; tile < p.v_end; tile += n_clusters) {
                 const TileInfo t = pair_tile_info(p, tile);
                 if (t.n_ktiles == 0) continue;
                 tc::mbar_wait_backoff(&q_full, tcnt & 1);
@@ -603,7 +623,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
         uint32_t kcnt = 0;
-        for (int tile = cluster_id; tile < p.total_tiles; tile += n_clusters) {
+        for (int tile = p.v_begin + cluster_id; tile < p.v_end; tile += n_clusters) {
             const TileInfo t = pair_tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int row = t.r0 + lrow;
@@ -699,73 +719,93 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
 }
 
 template <int KT>
-static int launch_pair(const CUtensorMap* maps, TcParams p, cudaStream_t st) {
+static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
     CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_pair_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    p.tiles_per_rg = ceil_div(p.T * p.N, kPairM);
-    p.total_tiles = p.R * p.tiles_per_rg;
-    const int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+    const int items = p.v_end - p.v_begin;
+    int clusters = max_ctas / 2 < 1 ? 1 : max_ctas / 2;
+    if (items < clusters) clusters = items;
     lp_topk_pair_kernel<KT><<<2 * clusters, 320, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
 
 template <int KT, int NEPI>
-static int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
     CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const int items = p.v_end - p.v_begin;
+    const int grid = items < max_ctas ? items : max_ctas;
     lp_topk_tc_kernel<KT, NEPI><<<grid, (NEPI + 2) * 32, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
 
-// Host entry used by crw_labelprop_forward: feats [R,T,N,128] fp32 -> W, I [R,T,k,N].
-// scratch must hold 2 * R*T*N*128 bf16.
-int lp_topk_tc(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
-               float* W, int32_t* I, void* scratch, cudaStream_t st) {
+// Host side of the tensor path, in two steps so that crw_labelprop_forward can overlap the sequential label gather with
+// the bulk of the top-k: lp_tc_prepare launches the prep kernel and fills the plan (tensor maps, parameters, schedule);
+// lp_tc_launch runs the top-k kernel over a range of schedule slots on at most max_ctas CTAs.
+// feats [R,T,N,128] fp32 -> W, I [R,T,k,N]; scratch must hold 2 * R*T*N*128 bf16.
+int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
+                  float* W, int32_t* I, void* scratch, cudaStream_t st, void* plan_storage) {
+    static_assert(sizeof(LpTcPlan) <= 1024, "LpTcPlan must fit the caller's plan storage");
+    LpTcPlan* plan = reinterpret_cast<LpTcPlan*>(plan_storage);
     if (C != 128 || N > 128 || N < 8 || k > 32) return CRW_ERR_UNSUPPORTED;
     const int64_t rows = (int64_t)R * T * N;
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
     __nv_bfloat16* lo = hi + rows * 128;
     lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
     CRW_LAUNCH_RET();
+    TcParams& p = plan->p;
+    p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
+    p.total_tiles = 0; p.v_begin = p.v_end = 0; p.tiles_per_rg = 0; p.early_per_rg = 0;
     if (T < 2) return CRW_OK;
-    CUtensorMap maps[4];
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(plan->maps);
     int rc = make_tmap_bf16_k64(&maps[0], hi, (uint64_t)rows, 128, kBM);
     if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[1], lo, (uint64_t)rows, 128, kBM);
     if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[2], hi, (uint64_t)rows, 128, kBN);
     if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[3], lo, (uint64_t)rows, 128, kBN);
     if (rc != CRW_OK) return rc;
-    TcParams p;
-    p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
     const float rc_ = ceilf(radius);
     p.rb = (rc_ - 1.0f >= (float)N) ? N : (int)rc_ - 1;
     p.inv_temp = 1.0f / temp;
     if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
     p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    p.tiles_per_rg = ceil_div(T * N, kBM);
-    p.total_tiles = R * p.tiles_per_rg;
     // The CTA-pair kernel is correct (tests run it) and has the cheaper MMA side (68 vs 78 us with the selection switched
     // off), but at BASELINE config 3 the selection epilogue bounds both kernels and the pair form pays more per-tile
-    // overhead there (153 vs 143 us, profiles/r01_lp_pair_anatomy.txt): opt-in until the epilogue is the smaller half.
-    { const char* e = getenv("CRW_LP_PAIR"); if (e && atoi(e) != 0) {
-        if (k <= 10) return launch_pair<10>(maps, p, st);
-        if (k <= 16) return launch_pair<16>(maps, p, st);
-        if (k <= 20) return launch_pair<20>(maps, p, st);
-        return launch_pair<32>(maps, p, st);
-    } }
-    if (k <= 10) return launch_tc<10, 8>(maps, p, st);
-    if (k <= 16) return launch_tc<16, 8>(maps, p, st);
-    if (k <= 20) return launch_tc<20, 8>(maps, p, st);
-    return launch_tc<32, 8>(maps, p, st);
+    // overhead there (profiles/r01_lp_pair_anatomy.txt): opt-in until the epilogue is the smaller half.
+    { const char* e = getenv("CRW_LP_PAIR"); plan->pair = (e && atoi(e) != 0) ? 1 : 0; }
+    const int tile_rows = plan->pair ? kPairM : kBM;
+    p.tiles_per_rg = ceil_div(T * N, tile_rows);
+    p.total_tiles = R * p.tiles_per_rg;
+    const int early = ceil_div((ctx + 2) * N, tile_rows);
+    p.early_per_rg = early < p.tiles_per_rg ? early : p.tiles_per_rg;
+    return CRW_OK;
+}
+
+int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st) {
+    const LpTcPlan& plan = *reinterpret_cast<const LpTcPlan*>(plan_storage);
+    if (v_end <= v_begin) return CRW_OK;
+    TcParams p = plan.p;
+    p.v_begin = v_begin;
+    p.v_end = v_end;
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(plan.maps);
+    const int k = p.k;
+    if (plan.pair) {
+        if (k <= 10) return launch_pair<10>(maps, p, max_ctas, st);
+        if (k <= 16) return launch_pair<16>(maps, p, max_ctas, st);
+        if (k <= 20) return launch_pair<20>(maps, p, max_ctas, st);
+        return launch_pair<32>(maps, p, max_ctas, st);
+    }
+    if (k <= 10) return launch_tc<10, 8>(maps, p, max_ctas, st);
+    if (k <= 16) return launch_tc<16, 8>(maps, p, max_ctas, st);
+    if (k <= 20) return launch_tc<20, 8>(maps, p, max_ctas, st);
+    return launch_tc<32, 8>(maps, p, max_ctas, st);
+}
+int lp_tc_total_slots(const void* plan) { return reinterpret_cast<const LpTcPlan*>(plan)->p.total_tiles; }
+int lp_tc_early_slots(const void* plan) {
+    const LpTcPlan* pl = reinterpret_cast<const LpTcPlan*>(plan);
+    return pl->p.R * pl->p.early_per_rg;
 }
 
 int lp_profile_read(unsigned long long* host_out, int reset) {

@@ -131,6 +131,41 @@ def test_lp_tensorcore_vs_fp32_oracle(pkg, case, lp_kernel):
     assert np.abs(W[:, 1:].sum(2) - 1).max() < 1e-5
 
 
+def test_lp_tensorcore_fork_join_and_graph_capture(pkg, monkeypatch):
+    """The early query tiles + sequential gather run on a forked stream: same result as the single-stream order, also when
+    the call is captured into a CUDA graph and replayed on new inputs."""
+    rs = np.random.RandomState(77)
+    R, T, N, M = 2, 300, 49, 4
+    feats = _dev(rs.randn(R, T, N, 128).astype(np.float32))
+    mask0 = _dev(np.stack([lo.one_hot_mask(rs.randint(0, M, N), M, np.float32) for _ in range(R)]))
+
+    def run(f):
+        return pkg.ops.labelprop(f, mask0, 20, 12.0, 0.07, 10, 0, pkg.ops.PREC_BF16X3, True, True)
+
+    forked = [t.clone() for t in run(feats)]
+    monkeypatch.setenv("CRW_LP_NO_FORK", "1")
+    plain = run(feats)
+    monkeypatch.delenv("CRW_LP_NO_FORK")
+    for a_, b_ in zip(forked, plain):
+        assert torch.equal(a_, b_)
+    static_in = feats.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(static_in)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = run(static_in)
+    feats2 = _dev(rs.randn(R, T, N, 128).astype(np.float32))
+    static_in.copy_(feats2)
+    graph.replay()
+    torch.cuda.synchronize()
+    ref2 = run(feats2)
+    for a_, b_ in zip(out, ref2):
+        assert torch.equal(a_, b_)
+
+
 def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
     for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
