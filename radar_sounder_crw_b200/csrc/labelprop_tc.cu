@@ -239,12 +239,22 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     constexpr int kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
     constexpr int kParts = NEPI / 4;          // top-k lists per query (merged at the end of a tile)
     constexpr int kParkWarp = kParkBytes / NEPI;
-    static_assert(kParkWarp >= kBN * 32 * 4, "park buffer must hold one 64-column tile per lane");
+    // 8 epilogue warps: two parts, whole 64-column key tiles dealt round-robin.  16 warps: four parts = two tile groups x two
+    // 32-column halves (the park buffer of a warp then only has to hold 32 columns per lane).
+    constexpr int kColSplit = (NEPI > 8) ? 2 : 1;
+    constexpr int kTileGroups = kParts / kColSplit;
+    constexpr int kCols = kBN / kColSplit, kCh = kCols / 32;
+    static_assert(kParkWarp >= kCols * 32 * 4, "park buffer must hold this warp's columns of one key tile per lane");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                  // 64 KB
     uint8_t* sK = smem + kQBytes;                        // kStages x 32 KB
     uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
+    {
+        uint32_t dyn_bytes;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        if ((size_t)(park_base + kParkBytes - smem_raw) > dyn_bytes) __trap();    // the launch did not provide the carve-up
+    }
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
     __shared__ uint32_t tmem_base_s;
     __shared__ float thr_pub[NEPI * 32];     // every list's current k-th best, read by the other part(s) of the same query
@@ -257,7 +267,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         tc::mbar_init(&q_full, 1);
         tc::mbar_init(&q_empty, 1);
         for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
-        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4 * kColSplit); }
         tc::fence_barrier_init();
     }
     if (tid < NEPI * 32) thr_pub[tid] = -INFINITY;
@@ -367,10 +377,13 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                if ((kt % kParts) != part) continue;              // whole 64-column key tiles are dealt round-robin
+                if ((kt % kTileGroups) != part / kColSplit) continue;        // key tiles are dealt round-robin to the tile groups
                 const int a = kcnt % kAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
+                const int col0 = (part % kColSplit) * kCols;                 // this warp's columns of the tile
+                row0 += col0;
+                nrows = min(kCols, nrows - col0);                            // <= 0: nothing in this half, only release the buffer
                 const bool prof = (p.debug & 8) != 0;
                 long long c_0 = prof ? clock64() : 0;
                 tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
@@ -379,10 +392,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 const float thr = shared_threshold<NEPI>(thr_pub, warp, lane, top.v[KT - 1]);
                 uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
+                for (int ch = 0; ch < kCh; ++ch) {
                     if (ch * 32 < nrows && !(p.debug & 2)) {                        // warp-uniform
                         float v[32];
-                        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + ch * 32), v);
+                        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + col0 + ch * 32), v);
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
@@ -732,7 +745,12 @@ static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas,
 
 template <int KT, int NEPI>
 static int launch_tc(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
+    // dynamic shared memory starts right after the kernel's static part; only the gap up to the next 1024-byte boundary
+    // is needed as alignment slack (with 16 epilogue warps the kernel fills the 227 KB of an SM to the byte)
+    cudaFuncAttributes fa;
+    CRW_CUDA_RET(cudaFuncGetAttributes(&fa, lp_topk_tc_kernel<KT, NEPI>));
+    const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
+    const size_t smem = slack + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
     CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int items = p.v_end - p.v_begin;
     const int grid = items < max_ctas ? items : max_ctas;
@@ -797,6 +815,7 @@ int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas,
         if (k <= 20) return launch_pair<20>(maps, p, max_ctas, st);
         return launch_pair<32>(maps, p, max_ctas, st);
     }
+    // (a 16-epilogue-warp instantiation, launch_tc<10, 16>, is supported by the kernel but measured slower: 196 vs 125 us)
     if (k <= 10) return launch_tc<10, 8>(maps, p, max_ctas, st);
     if (k <= 16) return launch_tc<16, 8>(maps, p, max_ctas, st);
     if (k <= 20) return launch_tc<20, 8>(maps, p, max_ctas, st);
