@@ -218,11 +218,44 @@ def bench_train(crw, args, rank, world, local, pk):
     sampler = ClockSampler(local)
     ms = timed_loop(train_step, args.steps, args.warmup, world, sampler=sampler)
 
-    def train_step_e2e(i):
-        train_step(i, batches_host)
-        last_loss[0] = last_loss[0].item()      # D2H read of the step's result
+    # end to end from pinned HOST batches: a double-buffered input pipeline (what any data loader does) -- while step i
+    # computes, the H2D copy of batch i+1 runs on a copy stream into the other device buffer; every timed step still
+    # contains exactly one full batch copy and the D2H read of its loss.
+    copy_stream = torch.cuda.Stream()
+    dev_buf = [torch.empty_like(batches_dev[0]) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    ms_e2e = timed_loop(train_step_e2e, args.steps, 3, world)
+    def enqueue_copy(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])                 # the step that read this buffer has finished with it
+            dev_buf[slot].copy_(batches_host[i % n_rot], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    for ev in consumed:
+        ev.record()
+    enqueue_copy(0)
+
+    def train_step_e2e(i):
+        slot = i % 2
+        enqueue_copy(i + 1)                                        # next step's input, overlapped with this step
+        torch.cuda.current_stream().wait_event(ready[slot])
+        loss, _ = model(dev_buf[slot])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        consumed[slot].record()
+        opt.step()
+        last_loss[0] = loss.item()                                 # D2H read of the step's result
+
+    # timed_loop numbers its steps warmup + i: keep the slot sequence continuous across warm-up and timed steps
+    e2e_counter = [0]
+
+    def train_step_e2e_seq(_i):
+        train_step_e2e(e2e_counter[0])
+        e2e_counter[0] += 1
+
+    ms_e2e = timed_loop(train_step_e2e_seq, args.steps, 3, world)
     return dict(ms_per_step=ms, value=B * world / (ms * 1e-3), N=N, clocks=sampler.summary(), loss=float(last_loss[0]),
                 e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="radargrams/s",
                          h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
@@ -320,7 +353,14 @@ def bench_labelprop(crw, args, rank, world, pk):
         fp32_path["label_agreement_with_primary"] = float((labels32 == res[0]).float().mean().item())
 
     def lp_step_e2e(i):
-        lp_step(i, feats_host)
+        # the public host-buffer call: pinned host features streamed in chunks, the copy of chunk c+1 overlapping the
+        # top-k of chunk c (crw_labelprop_forward_host); the fp32 path has no such entry and copies first
+        if prec[0] == crw.ops.PREC_BF16X3:
+            labels, _, _, _ = crw.ops.labelprop_host(feats_host, mask0, LP["ctx"], float(LP["radius"]), LP["temp"], LP["k"],
+                                                     crw.ops.LP_REF_EXACT, True, False)
+            res[0] = labels
+        else:
+            lp_step(i, feats_host)
         res[0] = res[0].cpu()                   # D2H of the labels
 
     ms_e2e = timed_loop(lp_step_e2e, args.steps, 3, world, flush=flush)
@@ -342,7 +382,7 @@ def bench_labelprop(crw, args, rank, world, pk):
                       else "l2_normalize + lp_topk_f32_kernel + gather kernels", algorithmic_bytes=lp_bytes,
                       peak_source=pk["src"],
                       tensor_bound_note=f"dense {dense / 1e9:.1f} GFLOP: AI ~514 FLOP/B > ridge, see DESIGN.md"),
-        gpu_launches=4 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
+        gpu_launches=5 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
         frames=Tl, fp32_path=fp32_path,
         scaling="strong" if cfg5 else "weak",
         config=dict(workload=(f"BASELINE config 5: 64 radargrams of 400x50000 columns sharded over {world} GPU(s) "

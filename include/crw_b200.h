@@ -136,6 +136,20 @@ int crw_labelprop_forward(const float* feats, const float* mask0, int R, int T, 
                           int32_t* I_or_null, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Same as crw_labelprop_forward (tensor path, precision = CRW_PREC_BF16X3) with the features in PINNED HOST memory:
+ * every radargram is streamed to the device in chunks of whole query tiles on an internal copy stream while the previous
+ * chunk is normalised, split and searched on `stream` (a query tile only needs key rows that precede it).  This is the
+ * call for a caller whose encoder output / feature cache lives on the host; the host buffer must stay untouched until
+ * the work queued on `stream` has completed.  Returns CRW_ERR_INVALID for pageable memory.
+ *   scratch: crw_labelprop_host_scratch_bytes() bytes (adds a staging double buffer)
+ * ---------------------------------------------------------------------------------- */
+size_t crw_labelprop_host_scratch_bytes(int R, int T, int N, int C, int k, int have_topk_out);
+int crw_labelprop_forward_host(const float* feats_host, const float* mask0, int R, int T, int N, int C, int M,
+                               int ctx, float radius, float temp, int k, int mode, int do_normalize,
+                               int32_t* labels, float* masks, float* W_or_null, int32_t* I_or_null, void* scratch,
+                               size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * "Horizontality" metric -- replaces src/utils.py:118-123 (channel-shifted intra-frame
  * similarity / 0.1, cross-entropy against the identity, reduction='none').
  *   emb [T,N,C] normalised  ->  xent [N,T-1]

@@ -664,6 +664,11 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
 int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st);
 int lp_tc_total_slots(const void* plan_storage);
 int lp_tc_early_slots(const void* plan_storage);
+int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_t total_rows, int do_normalize, void* scratch,
+                    cudaStream_t st);
+int lp_tc_launch_tiles(const void* plan_storage, int rg, int ta, int tb, int max_ctas, cudaStream_t st);
+int lp_tc_tiles_per_rg(const void* plan_storage);
+int lp_tc_tile_rows(const void* plan_storage);
 }
 
 // A second, higher-priority stream and two events per device, created on first use: the tensor path forks the early query
@@ -671,7 +676,13 @@ int lp_tc_early_slots(const void* plan_storage);
 // nothing synchronises with the host; the enqueue sequence is serialised by a mutex because the events are shared).
 #include <mutex>
 namespace {
-struct SideCtx { cudaStream_t s2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool ok = false; std::mutex mu; };
+struct SideCtx {
+    cudaStream_t s2 = nullptr, s_copy = nullptr;                 // side compute stream (high priority), H2D copy stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};   // staging double buffer
+    bool ok = false;
+    std::mutex mu;
+};
 SideCtx* side_ctx() {
     static SideCtx ctx[64];
     static std::once_flag once[64];
@@ -683,7 +694,11 @@ SideCtx* side_ctx() {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);          // hi = numerically lowest = greatest priority
         c.ok = cudaStreamCreateWithPriority(&c.s2, cudaStreamNonBlocking, hi) == cudaSuccess &&
                cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-               cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) == cudaSuccess;
+               cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+               cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && c.ok; ++i)
+            c.ok = cudaEventCreateWithFlags(&c.ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&c.ev_free[i], cudaEventDisableTiming) == cudaSuccess;
     });
     return ctx[dev].ok ? &ctx[dev] : nullptr;
 }
@@ -776,6 +791,102 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         }
     }
     return crw_label_gather(W, I, mask0, R, T, N, M, ctx, k, mode, labels, masks, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-streamed tensor path: `feats` lives in PINNED HOST memory.  Each radargram is cut into chunks of whole query tiles;
+// chunk c+1 is copied into a staging double buffer on a copy stream while chunk c is normalised, split and searched
+// (a query tile only needs key rows that precede it, so the top-k of a chunk can run as soon as its rows are resident).
+// ------------------------------------------------------------------------------------------
+static int host_chunk_tiles(int tiles_per_rg, int tile_rows, int C) {
+    const size_t rg_bytes = (size_t)tiles_per_rg * tile_rows * C * sizeof(float);
+    int nch = rg_bytes >= (size_t)24 << 20 ? 4 : (rg_bytes >= (size_t)8 << 20 ? 2 : 1);
+    return ceil_div(tiles_per_rg, nch);
+}
+
+extern "C" size_t crw_labelprop_host_scratch_bytes(int R, int T, int N, int C, int k, int have_topk_out) {
+    const int tile_rows = 256;                                    // upper bound over both top-k kernels
+    const int tpr = ceil_div(T * N, 128);
+    const size_t stage = align_up((size_t)(host_chunk_tiles(tpr, 128, C) * 128 + tile_rows) * C * sizeof(float), 256);
+    return crw_labelprop_scratch_bytes(R, T, N, C, k, CRW_PREC_BF16X3, 1, have_topk_out) + 2 * stage;
+}
+
+extern "C" int crw_labelprop_forward_host(const float* feats_host, const float* mask0, int R, int T, int N, int C, int M, int ctx,
+                                          float radius, float temp, int k, int mode, int do_normalize, int32_t* labels,
+                                          float* masks, float* W_or_null, int32_t* I_or_null, void* scratch,
+                                          size_t scratch_bytes, void* stream) {
+    if (!feats_host || !mask0 || !labels || !masks) return CRW_ERR_INVALID;
+    if (R < 0 || T < 1 || N < 1 || C < 1 || M < 1) return CRW_ERR_INVALID;
+    if ((W_or_null == nullptr) != (I_or_null == nullptr)) return CRW_ERR_INVALID;
+    if (ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f) || (int64_t)N < k) return CRW_ERR_INVALID;
+    if (R == 0) return CRW_OK;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, feats_host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return CRW_ERR_INVALID;                                   // pageable memory would serialise the copies silently
+    }
+    const size_t need = crw_labelprop_host_scratch_bytes(R, T, N, C, k, W_or_null != nullptr);
+    if (!scratch || scratch_bytes < need) return CRW_ERR_WORKSPACE;
+    SideCtx* sc = side_ctx();
+    if (!sc) return CRW_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+    void* hilo = sp;
+    sp += align_up((size_t)R * T * N * C * 2 * 2, 256);
+    float* Wt = W_or_null;
+    int32_t* It = I_or_null;
+    if (!Wt) {
+        Wt = reinterpret_cast<float*>(sp);
+        sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+        It = reinterpret_cast<int32_t*>(sp);
+        sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+    }
+    GatherParams gp;
+    int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
+    if (rc != CRW_OK) return rc;
+    LpTcPlanStorage plan;
+    if ((rc = lp_tc_prepare(nullptr, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, st, plan.bytes)) != CRW_OK) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tpr = lp_tc_tiles_per_rg(plan.bytes), tile_rows = lp_tc_tile_rows(plan.bytes);
+    const int chunk_tiles = T < 2 ? 1 : host_chunk_tiles(tpr, tile_rows, C);
+    const int64_t rows_rg = (int64_t)T * N, total_rows = (int64_t)R * rows_rg;
+    const size_t stage_bytes = align_up((size_t)(host_chunk_tiles(ceil_div(T * N, 128), 128, C) * 128 + 256) * C * sizeof(float), 256);
+    float* stage[2] = {reinterpret_cast<float*>(sp), reinterpret_cast<float*>(sp + stage_bytes)};
+
+    std::lock_guard<std::mutex> lock(sc->mu);
+    CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));               // earlier work on `st` may still use the scratch
+    CRW_CUDA_RET(cudaStreamWaitEvent(sc->s_copy, sc->ev_fork, 0));
+    int g = 0;
+    bool forked = false;
+    for (int rg = 0; rg < R; ++rg) {
+        for (int ta = 0; ta * (int64_t)tile_rows < rows_rg; ta += chunk_tiles, ++g) {
+            const int slot = g & 1;
+            const int64_t r0 = (int64_t)ta * tile_rows;
+            const int64_t r1 = (r0 + (int64_t)chunk_tiles * tile_rows < rows_rg) ? r0 + (int64_t)chunk_tiles * tile_rows : rows_rg;
+            const int64_t grow = rg * rows_rg + r0;
+            if (g >= 2) CRW_CUDA_RET(cudaStreamWaitEvent(sc->s_copy, sc->ev_free[slot], 0));
+            CRW_CUDA_RET(cudaMemcpyAsync(stage[slot], feats_host + grow * C, (size_t)(r1 - r0) * C * sizeof(float),
+                                         cudaMemcpyHostToDevice, sc->s_copy));
+            CRW_CUDA_RET(cudaEventRecord(sc->ev_copied[slot], sc->s_copy));
+            CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_copied[slot], 0));
+            if ((rc = lp_tc_prep_rows(stage[slot], grow, r1 - r0, total_rows, do_normalize, hilo, st)) != CRW_OK) return rc;
+            CRW_CUDA_RET(cudaEventRecord(sc->ev_free[slot], st));
+            if (T >= 2 && (rc = lp_tc_launch_tiles(plan.bytes, rg, ta, ta + chunk_tiles, sms, st)) != CRW_OK) return rc;
+            // one radargram, first chunk holds frames 0..ctx+1: start the sequential gather beside the later chunks
+            if (R == 1 && ta == 0 && !gp.mode_fixed && r1 < rows_rg && r1 >= (int64_t)(ctx + 2) * N) {
+                CRW_CUDA_RET(cudaEventRecord(sc->ev_join, st));
+                CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_join, 0));
+                if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;
+                CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
+                forked = true;
+            }
+        }
+    }
+    if (forked) CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
+    else if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
+    return gather_launch_par(gp, st);
 }
 
 extern "C" int crw_labels_upsample(const int32_t* labels, int R, int T, int N, int H, int W, float* out, void* stream) {

@@ -771,11 +771,14 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     const int64_t rows = (int64_t)R * T * N;
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
     __nv_bfloat16* lo = hi + rows * 128;
-    lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
-    CRW_LAUNCH_RET();
+    if (feats) {       // null: the caller fills hi / lo itself with lp_tc_prep_rows (host-streamed features)
+        lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
+        CRW_LAUNCH_RET();
+    }
     TcParams& p = plan->p;
     p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
     p.total_tiles = 0; p.v_begin = p.v_end = 0; p.tiles_per_rg = 0; p.early_per_rg = 0;
+    plan->pair = 0;
     if (T < 2) return CRW_OK;
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(plan->maps);
     int rc = make_tmap_bf16_k64(&maps[0], hi, (uint64_t)rows, 128, kBM);
@@ -821,6 +824,30 @@ int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas,
     if (k <= 20) return launch_tc<20, 8>(maps, p, max_ctas, st);
     return launch_tc<32, 8>(maps, p, max_ctas, st);
 }
+// prep of `nrows` rows whose fp32 source sits in a staging buffer: writes hi / lo rows [row_begin, row_begin + nrows)
+int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_t total_rows, int do_normalize, void* scratch,
+                    cudaStream_t st) {
+    if (nrows <= 0) return CRW_OK;
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
+    __nv_bfloat16* lo = hi + total_rows * 128;
+    lp_prep_bf16_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(stage, nrows, do_normalize, hi + row_begin * 128, lo + row_begin * 128);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+// top-k over tiles [ta, tb) of radargram rg (at most two slot ranges: early tiles and the rest)
+int lp_tc_launch_tiles(const void* plan_storage, int rg, int ta, int tb, int max_ctas, cudaStream_t st) {
+    const LpTcPlan& plan = *reinterpret_cast<const LpTcPlan*>(plan_storage);
+    const int E = plan.p.early_per_rg, tpr = plan.p.tiles_per_rg, R = plan.p.R;
+    if (tb > tpr) tb = tpr;
+    int rc = CRW_OK;
+    const int ea = ta < E ? ta : E, eb = tb < E ? tb : E;
+    if (eb > ea) rc = lp_tc_launch(plan_storage, rg * E + ea, rg * E + eb, max_ctas, st);
+    const int ra = ta > E ? ta : E, rb = tb > E ? tb : E;
+    if (rc == CRW_OK && rb > ra) rc = lp_tc_launch(plan_storage, R * E + rg * (tpr - E) + (ra - E), R * E + rg * (tpr - E) + (rb - E), max_ctas, st);
+    return rc;
+}
+int lp_tc_tiles_per_rg(const void* plan) { return reinterpret_cast<const LpTcPlan*>(plan)->p.tiles_per_rg; }
+int lp_tc_tile_rows(const void* plan) { return reinterpret_cast<const LpTcPlan*>(plan)->pair ? kPairM : kBM; }
 int lp_tc_total_slots(const void* plan) { return reinterpret_cast<const LpTcPlan*>(plan)->p.total_tiles; }
 int lp_tc_early_slots(const void* plan) {
     const LpTcPlan* pl = reinterpret_cast<const LpTcPlan*>(plan);

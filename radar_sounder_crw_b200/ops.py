@@ -204,6 +204,48 @@ def _(feats, mask0, ctx, radius, temp, k, mode, precision, normalize, return_top
             feats.new_empty(tk), torch.empty(tk, device=dev, dtype=torch.int32))
 
 
+@torch.library.custom_op("crw_b200::labelprop_host", mutates_args=())
+def labelprop_host(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: float, k: int, mode: int,
+                   normalize: bool, return_topk: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``labelprop`` (tensor path) for features in PINNED HOST memory: the H2D copy is chunked and overlapped with the
+    top-k of the previous chunk.  ``feats`` must not be modified until the current stream has caught up."""
+    if feats.is_cuda or not feats.is_pinned():
+        raise RuntimeError("crw_b200::labelprop_host: `feats` must be a pinned host tensor (use labelprop for CUDA tensors)")
+    if feats.dtype != torch.float32:
+        raise RuntimeError("crw_b200::labelprop_host: `feats` must be float32")
+    feats = feats.contiguous()
+    mask0 = _chk(mask0, "mask0")
+    R, T, N, C = feats.shape
+    M = mask0.shape[1]
+    L = _lib.lib()
+    dev = mask0.device
+    labels = torch.empty((R, T, N), device=dev, dtype=torch.int32)
+    masks = torch.empty((R, T, M, N), device=dev, dtype=torch.float32)
+    if return_topk:
+        W = torch.zeros((R, T, k, N), device=dev, dtype=torch.float32)
+        I = torch.zeros((R, T, k, N), device=dev, dtype=torch.int32)
+    else:
+        W = torch.empty(0, device=dev, dtype=torch.float32)
+        I = torch.empty(0, device=dev, dtype=torch.int32)
+    sbytes = L.crw_labelprop_host_scratch_bytes(R, T, N, C, k, int(return_topk))
+    scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.check(L.crw_labelprop_forward_host(feats.data_ptr(), _p(mask0), R, T, N, C, M, ctx, float(radius), float(temp), k,
+                                                int(mode), int(normalize), _p(labels), _p(masks), _p(W), _p(I),
+                                                _p(scratch), sbytes, _stream()), "crw_labelprop_forward_host")
+    return labels, masks, W, I
+
+
+@labelprop_host.register_fake
+def _(feats, mask0, ctx, radius, temp, k, mode, normalize, return_topk):
+    R, T, N, _ = feats.shape
+    M = mask0.shape[1]
+    dev = mask0.device
+    tk = (R, T, k, N) if return_topk else (0,)
+    return (torch.empty((R, T, N), device=dev, dtype=torch.int32), torch.empty((R, T, M, N), device=dev),
+            torch.empty(tk, device=dev), torch.empty(tk, device=dev, dtype=torch.int32))
+
+
 # ------------------------------------------------------------------------------------------------
 # horizontality_xent  (utils.py:118-123)
 # ------------------------------------------------------------------------------------------------

@@ -166,6 +166,25 @@ def test_lp_tensorcore_fork_join_and_graph_capture(pkg, monkeypatch):
         assert torch.equal(a_, b_)
 
 
+@pytest.mark.parametrize("shape", [(1, 1250, 49), (3, 200, 47), (2, 1, 49), (1, 30, 49)])
+def test_lp_host_streamed_equals_device_path(pkg, shape, lp_kernel):
+    """Features in pinned host memory, chunked H2D overlapped with the top-k: bit-identical to the device-resident call."""
+    R, T, N = shape
+    rs = np.random.RandomState(T + N)
+    feats = torch.from_numpy(rs.randn(R, T, N, 128).astype(np.float32)).pin_memory()
+    M = 4
+    mask0 = _dev(np.stack([lo.one_hot_mask(rs.randint(0, M, N), M, np.float32) for _ in range(R)]))
+    a_ = pkg.ops.labelprop_host(feats, mask0, 20, 12.0, 0.07, 10, 0, True, True)
+    b_ = pkg.ops.labelprop(feats.cuda(), mask0, 20, 12.0, 0.07, 10, 0, pkg.ops.PREC_BF16X3, True, True)
+    torch.cuda.synchronize()
+    for x, y in zip(a_, b_):
+        assert torch.equal(x, y)
+    with pytest.raises(RuntimeError):
+        pkg.ops.labelprop_host(feats.cuda(), mask0, 20, 12.0, 0.07, 10, 0, True, True)
+    with pytest.raises(RuntimeError):
+        pkg.ops.labelprop_host(torch.zeros(1, 4, N, 128), mask0[:1], 20, 12.0, 0.07, 10, 0, True, True)     # pageable
+
+
 def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
     for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
