@@ -601,7 +601,8 @@ static int gather_launch_seq(const GatherParams& p, cudaStream_t st) {
     const int seq_end = gather_seq_end(p);
     const size_t gsmem = ((size_t)(p.ctx + 2) * p.M * p.N + 4 * (size_t)p.k * p.N + (size_t)p.k * p.M * p.N) * sizeof(float);
     if (gsmem <= 200 * 1024) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        if (gsmem > 48 * 1024)
+            CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_seq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
         lp_gather_seq_smem_kernel<<<p.R, 256, gsmem, st>>>(p, seq_end);
     } else {
         lp_gather_seq_kernel<<<p.R, 256, 0, st>>>(p, 1, seq_end, 1);
@@ -617,7 +618,8 @@ static int gather_launch_par(const GatherParams& p, cudaStream_t st) {
     long long gx64 = (total + 255) / 256; int gx = (int)(gx64 < 148LL * 8 ? gx64 : 148LL * 8);
     const size_t psmem = (size_t)(p.ctx + 1) * p.M * p.N * sizeof(float);
     if (psmem <= 96 * 1024) {     // ref_exact only reaches here (fixed mode is sequential throughout)
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_par_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        if (psmem > 48 * 1024)
+            CRW_CUDA_RET(cudaFuncSetAttribute(lp_gather_par_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         if (gx > 148 * 2) gx = 148 * 2;
         lp_gather_par_smem_kernel<<<dim3(gx, p.R), 256, psmem, st>>>(p, seq_end, T);
     } else {
@@ -756,12 +758,13 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         }
         std::lock_guard<std::mutex> lock(sc->mu);
         CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));                       // prep done
+        // the bulk is the critical path: enqueue it first (it leaves the early tiles their SMs when they are few)
+        const int bulk_ctas = (early <= sms / 8) ? sms - early : sms;
+        if ((rc = lp_tc_launch(plan.bytes, early, total, bulk_ctas, st)) != CRW_OK) return rc;
         CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
         if ((rc = lp_tc_launch(plan.bytes, 0, early, sms, sc->s2)) != CRW_OK) return rc;            // frames 1..ctx+1 (and a few more)
         if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;                              // the true recurrence
         CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
-        const int bulk_ctas = (early <= sms / 8) ? sms - early : sms;         // leave the early tiles their SMs when they are few
-        if ((rc = lp_tc_launch(plan.bytes, early, total, bulk_ctas, st)) != CRW_OK) return rc;
         CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
         return gather_launch_par(gp, st);
     }

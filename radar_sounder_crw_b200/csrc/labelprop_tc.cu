@@ -734,7 +734,13 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
 template <int KT>
 static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
     const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
-    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_pair_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool opted[64] = {};      // per device; the attribute calls cost microseconds on the launch path
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_pair_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
     const int items = p.v_end - p.v_begin;
     int clusters = max_ctas / 2 < 1 ? 1 : max_ctas / 2;
     if (items < clusters) clusters = items;
@@ -747,11 +753,18 @@ template <int KT, int NEPI>
 static int launch_tc(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
     // dynamic shared memory starts right after the kernel's static part; only the gap up to the next 1024-byte boundary
     // is needed as alignment slack (with 16 epilogue warps the kernel fills the 227 KB of an SM to the byte)
-    cudaFuncAttributes fa;
-    CRW_CUDA_RET(cudaFuncGetAttributes(&fa, lp_topk_tc_kernel<KT, NEPI>));
-    const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
-    const size_t smem = slack + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
-    CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_dev[64] = {};  // per device; the attribute calls cost microseconds on the launch path
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t smem = (dev >= 0 && dev < 64) ? smem_dev[dev] : 0;
+    if (smem == 0) {
+        cudaFuncAttributes fa;
+        CRW_CUDA_RET(cudaFuncGetAttributes(&fa, lp_topk_tc_kernel<KT, NEPI>));
+        const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
+        smem = slack + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) smem_dev[dev] = smem;
+    }
     const int items = p.v_end - p.v_begin;
     const int grid = items < max_ctas ? items : max_ctas;
     lp_topk_tc_kernel<KT, NEPI><<<grid, (NEPI + 2) * 32, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
