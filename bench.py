@@ -148,6 +148,7 @@ def timed_loop(step_fn, steps, warmup, world, flush=None, sampler=None):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ctx = sampler if sampler is not None else _Null()
     with ctx:
+        torch.cuda.nvtx.range_push("timed")       # lets `ncu --nvtx --nvtx-include "timed/"` list the timed launches only
         for i in range(steps):
             if flush is not None:
                 flush()
@@ -155,6 +156,7 @@ def timed_loop(step_fn, steps, warmup, world, flush=None, sampler=None):
             step_fn(warmup + i)
             ev[i][1].record()
         barrier_sync(world)
+        torch.cuda.nvtx.range_pop()
     ms = sum(a.elapsed_time(b) for a, b in ev) / steps
     return max_over_ranks(ms, world)
 
@@ -196,7 +198,7 @@ def bench_train(crw, args, rank, world, local, pk):
     N = batches_dev[0].shape[2]
     torch.manual_seed(11)
     # the encoder is plain PyTorch (out of scope as a kernel); channels_last + TF32 are host-side settings
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not os.environ.get("CRW_BENCH_NO_AUTOTUNE")    # off only to keep ncu launch lists short
     encoder = crw.Resnet(pos_embed=False).cuda().train().to(memory_format=torch.channels_last)
     model = crw.CRW(encoder, tau, False, need_A=False)
     if world > 1:
