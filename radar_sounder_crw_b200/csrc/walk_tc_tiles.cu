@@ -589,10 +589,12 @@ __global__ void __launch_bounds__(256) t_dx_epi_kernel(const float* __restrict__
 // ---- host orchestration -----------------------------------------------------------------------------------
 template <class P>
 static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_t st) {
-    static bool opted = false;   // per instantiation; idempotent
-    if (!opted) {
+    static bool opted[64] = {};   // per instantiation and device; the attribute is a per-device property of the function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
         CRW_CUDA_RET(cudaFuncSetAttribute(tc_tiles_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
-        opted = true;
+        if (dev >= 0 && dev < 64) opted[dev] = true;
     }
     if (batch <= 0) return CRW_OK;
     dim3 grid(ceil_div(Ncols, kWTile), ceil_div(Mrows, kWTile), batch);

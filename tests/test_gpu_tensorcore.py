@@ -185,6 +185,25 @@ def test_lp_host_streamed_equals_device_path(pkg, shape, lp_kernel):
         pkg.ops.labelprop_host(torch.zeros(1, 4, N, 128), mask0[:1], 20, 12.0, 0.07, 10, 0, True, True)     # pageable
 
 
+@pytest.mark.parametrize("host", [False, True])
+def test_lp_tensorcore_fixed_mode(pkg, host):
+    """mode = LP_FIXED (gather without the context-trim quirk: every frame is sequential, no fork) on the tensor path."""
+    rs = np.random.RandomState(5)
+    R, T, N, M, ctx, k = 2, 90, 49, 4, 6, 10
+    feats = rs.randn(R, T, N, 128).astype(np.float32)
+    label0 = rs.randint(0, M, (R, N)).astype(np.int32)
+    mask0 = _dev(np.stack([lo.one_hot_mask(label0[r], M, np.float32) for r in range(R)]))
+    if host:
+        labels, _, W, I = pkg.ops.labelprop_host(torch.from_numpy(feats).pin_memory(), mask0, ctx, 12.0, 0.07, k,
+                                                 pkg.ops.LP_FIXED, True, True)
+    else:
+        labels, _, W, I = pkg.ops.labelprop(_dev(feats), mask0, ctx, 12.0, 0.07, k, pkg.ops.LP_FIXED, pkg.ops.PREC_BF16X3, True, True)
+    o = c_oracle.labelprop(feats, label0, M, ctx, 12, 0.07, k, mode="fixed")
+    assert (labels.cpu().numpy() == o["labels"]).mean() >= 0.999
+    frac, _ = topk_sets_equal(I.cpu().numpy()[:, 1:], W.cpu().numpy()[:, 1:], o["I"][:, 1:], o["W"][:, 1:])
+    assert frac >= 0.995
+
+
 def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
     for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
