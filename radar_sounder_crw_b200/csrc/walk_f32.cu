@@ -13,6 +13,7 @@
 //
 // All N x N state lives in the `saved` workspace (L2-resident at the reference's sizes); every
 // stage is built from one CTA-wide tiled fp32 GEMM (64x64 tile, 4x4 per thread).
+#include <cstdlib>
 #include "common.cuh"
 #include "walk_layout.cuh"
 
@@ -363,10 +364,11 @@ __global__ void __launch_bounds__(kWT) walk_bwd_dx_kernel(const float* __restric
 
 namespace crw {
 bool walk_small_supported(int N, int C);
+bool walk_small_mma_supported(int N, int C);
 int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
-                       cudaStream_t st);
+                       cudaStream_t st, bool mma);
 int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
-                        float tau, float* dx, float* sc, cudaStream_t st);
+                        float tau, float* dx, float* sc, cudaStream_t st, bool mma);
 // walk_tc_tiles.cu: tile-parallel tcgen05 bf16x3 path
 int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
                        cudaStream_t st);
@@ -407,8 +409,13 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
     float* ws = align256(saved);
     const float inv_tau = 1.0f / tau;
     // BF16X3: tile-parallel tcgen05 GEMMs (any N).  FP32: shared-memory path for N <= 64, FMA tiles beyond.
-    if (precision == CRW_PREC_BF16X3) return walk_tiles_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
-    if (walk_small_supported(N, C) && aligned16p(x)) return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
+    // BF16X3: one-tile sizes run the shared-memory kernels with warp-level MMAs; beyond that the tile-parallel tcgen05 path
+    if (precision == CRW_PREC_BF16X3) {
+        if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
+            return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st, true);
+        return walk_tiles_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
+    }
+    if (walk_small_supported(N, C) && aligned16p(x)) return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st, false);
     walk_affinity_kernel<<<dim3(T - 1, B), kWT, 2 * N * sizeof(float), st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     if (T < 3) {   // model.py:33-35: empty loop, loss = 0
@@ -436,9 +443,13 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     const float* ws = align256(const_cast<void*>(saved));
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
-    if (precision == CRW_PREC_BF16X3) return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
+    if (precision == CRW_PREC_BF16X3) {
+        if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
+            return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st, true);
+        return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
+    }
     if (walk_small_supported(N, C) && aligned16p(x))
-        return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
+        return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st, false);
     if (T >= 3) {
         walk_bwd_own_kernel<<<dim3(T - 2, B, 2), kWT, 0, st>>>(ws, sc, dloss, B, T, N, C);
         CRW_LAUNCH_RET();

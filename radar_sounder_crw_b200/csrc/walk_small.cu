@@ -87,9 +87,79 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 }
 
+// ---- tensor-core variant of the same 64 x 64 tile (precision = CRW_PREC_BF16X3 at the reference's sizes) ----
+// mma.sync m16n8k16 on error-compensated bf16 pairs split on the fly from the fp32 operands in shared memory
+// (x = hi + lo; hi.hi + hi.lo + lo.hi, fp32 accumulate).  A dependent chain of 47 x 47 products is latency bound: the
+// warp-level MMA reads the operands where the previous step left them (no descriptor / TMEM round trip per step), which
+// is why this path does not use tcgen05 -- walk_tc_tiles.cu does, for N beyond one tile.
+// Warp w owns rows 16 (w & 3) .. +15 and columns 32 (w >> 2) .. +31; acc[nt][r] = n8-tile nt, fragment register r.
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));      // low half <- x0
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// same operand conventions as sgemm_tile; K4 is rounded up to 16 here (the padding of every operand is zero or unused)
+template <bool TA, bool TB>
+__device__ __forceinline__ void mma_tile(const float* A, int lda, const float* B, int ldb, int K4, int n0, float (&acc)[4][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const int m0 = 16 * (warp & 3), c0 = n0 + 32 * (warp >> 2);
+    for (int k0 = 0; k0 < K4; k0 += 16) {
+        uint32_t ah[4], al[4];                 // a0: (g, k..), a1: (g+8, k..), a2: (g, k+8..), a3: (g+8, k+8..)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int m = m0 + g + 8 * r, k = k0 + 2 * tig + 8 * h;
+                float x0, x1;
+                if (!TA) { const float2 v = *reinterpret_cast<const float2*>(A + m * lda + k); x0 = v.x; x1 = v.y; }
+                else { x0 = A[k * lda + m]; x1 = A[(k + 1) * lda + m]; }
+                split_pair(x0, x1, ah[2 * h + r], al[2 * h + r]);
+            }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int n = c0 + 8 * nt + g;
+            uint32_t bh[2], bl[2];             // b0: (k.., n), b1: (k+8.., n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + 2 * tig + 8 * h;
+                float x0, x1;
+                if (TB) { const float2 v = *reinterpret_cast<const float2*>(B + n * ldb + k); x0 = v.x; x1 = v.y; }
+                else { x0 = B[k * ldb + n]; x1 = B[(k + 1) * ldb + n]; }
+                split_pair(x0, x1, bh[h], bl[h]);
+            }
+            mma_bf16(acc[nt], ah, bh[0], bh[1]);
+            mma_bf16(acc[nt], ah, bl[0], bl[1]);
+            mma_bf16(acc[nt], al, bh[0], bh[1]);
+        }
+    }
+}
+template <bool MMA, bool TA, bool TB>
+__device__ __forceinline__ void gemm_tile(const float* A, int lda, const float* B, int ldb, int K4, int n0, float (&acc)[4][4]) {
+    if (MMA) mma_tile<TA, TB>(A, lda, B, ldb, K4, n0, acc);
+    else sgemm_tile<TA, TB>(A, lda, B, ldb, K4, n0, acc);
+}
+// (row, column) of acc[i][j] within the 64 x 64 tile
+template <bool MMA, bool TA, bool TB>
+__device__ __forceinline__ void out_rc(int i, int j, int& m, int& n) {
+    if (MMA) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        m = 16 * (warp & 3) + (lane >> 2) + 8 * (j >> 1);
+        n = 32 * (warp >> 2) + 8 * i + 2 * (lane & 3) + (j & 1);
+    } else {
+        m = own_row<TA>(i);
+        n = own_col<TB>(j);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward 1: grid (T-1, B).  A_t = E_t E_{t+1}^T / tau, S_t, S'_t   (model.py:22,26 + the softmaxes of :44)
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __restrict__ x, float* ws, float* A_out, int B, int T,
                                                              int N, int C, float inv_tau) {
     extern __shared__ __align__(16) float sm[];
@@ -121,13 +191,14 @@ __global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __res
     __syncthreads();
     float acc[4][4];
     zero_acc(acc);
-    sgemm_tile<false, true>(X0, kLDX, X1, kLDX, C, 0, acc);
+    gemm_tile<MMA, false, true>(X0, kLDX, X1, kLDX, C, 0, acc);
     float* Ao = A_out ? A_out + ((size_t)b * (T - 1) + t) * N * N : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int m = own_row<false>(i), n = own_col<true>(j);
+            int m, n;
+            out_rc<MMA, false, true>(i, j, m, n);
             if (m < N && n < N) {
                 const float a = acc[i][j] * inv0[m] * inv1[n] * inv_tau;
                 At[m * kLD + n] = a;
@@ -154,13 +225,14 @@ __global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __res
 }
 
 // store the thread's 4x4 block of a 64 x 64 result into smem (pitch kLD) and/or a dense N x N global matrix
-template <bool TA, bool TB, class F>
+template <bool MMA, bool TA, bool TB, class F>
 __device__ __forceinline__ void for_each_out(const float (&acc)[4][4], int N, F f) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int m = own_row<TA>(i), n = own_col<TB>(j);
+            int m, n;
+            out_rc<MMA, TA, TB>(i, j, m, n);
             if (m < N && n < N) f(m, n, acc[i][j]);
         }
 }
@@ -168,6 +240,7 @@ __device__ __forceinline__ void for_each_out(const float (&acc)[4][4], int N, F 
 // ------------------------------------------------------------------------------------------
 // forward 2: grid (2, B).  x = 0: L_k = L_{k-1} S'_{k-1};  x = 1: R_k = S_{k-1} R_{k-1}   (sequential in k)
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_chain_kernel(float* ws, int B, int T, int N, int C) {
     extern __shared__ __align__(16) float sm[];
     float* P = sm;                 // running product
@@ -194,17 +267,18 @@ __global__ void __launch_bounds__(kST) walk_s_chain_kernel(float* ws, int B, int
         if (k + 1 <= K) load_nn(Op + ((k + 1 - k_first) & 1) * kMat, ws + lay.mat(opnd, b, k), N);
         float acc[4][4];
         zero_acc(acc);
-        if (isL) sgemm_tile<false, false>(P, kLD, cur, kLD, N4, 0, acc);
-        else sgemm_tile<false, false>(cur, kLD, P, kLD, N4, 0, acc);
+        if (isL) gemm_tile<MMA, false, false>(P, kLD, cur, kLD, N4, 0, acc);
+        else gemm_tile<MMA, false, false>(cur, kLD, P, kLD, N4, 0, acc);
         __syncthreads();
         float* out = ws + lay.mat(chain, b, k);
-        for_each_out<false, false>(acc, N, [&](int m, int n, float v) { P[m * kLD + n] = v; out[(size_t)m * N + n] = v; });
+        for_each_out<MMA, false, false>(acc, N, [&](int m, int n, float v) { P[m * kLD + n] = v; out[(size_t)m * N + n] = v; });
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // forward 3: grid (T-2, B).  M_k = L_k R_k; loss partial; G_k = rowsoftmax(M_k) - I   (model.py:45)
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_cycle_kernel(float* ws, int B, int T, int N, int C) {
     extern __shared__ __align__(16) float sm[];
     float* Lk = sm;
@@ -222,8 +296,8 @@ __global__ void __launch_bounds__(kST) walk_s_cycle_kernel(float* ws, int B, int
     __syncthreads();
     float acc[4][4];
     zero_acc(acc);
-    sgemm_tile<false, false>(Lk, kLD, Rk, kLD, N4, 0, acc);
-    for_each_out<false, false>(acc, N, [&](int m, int n, float v) { M[m * kLD + n] = v; });
+    gemm_tile<MMA, false, false>(Lk, kLD, Rk, kLD, N4, 0, acc);
+    for_each_out<MMA, false, false>(acc, N, [&](int m, int n, float v) { M[m * kLD + n] = v; });
     __syncthreads();
     float* Gk = ws + lay.mat(lay.G, b, k);
     float part = 0.0f;
@@ -251,6 +325,7 @@ __global__ void __launch_bounds__(kST) walk_s_cycle_kernel(float* ws, int B, int
 // ------------------------------------------------------------------------------------------
 // backward 1: grid (T-2, B, 2).  z = 0: dL_k = s G_k R_k^T;  z = 1: dR_k = s L_k^T G_k
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_bwd_own_kernel(const float* ws, float* sc, const float* dloss, int B, int T, int N,
                                                             int C) {
     extern __shared__ __align__(16) float sm[];
@@ -269,19 +344,20 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_own_kernel(const float* ws, fl
     float acc[4][4];
     zero_acc(acc);
     if (blockIdx.z == 0) {
-        sgemm_tile<false, true>(G, kLD, O, kLD, N4, 0, acc);
+        gemm_tile<MMA, false, true>(G, kLD, O, kLD, N4, 0, acc);
         float* o = sc + lay.mat(bl.dL, b, k);
-        for_each_out<false, true>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
+        for_each_out<MMA, false, true>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
     } else {
-        sgemm_tile<true, false>(O, kLD, G, kLD, N4, 0, acc);
+        gemm_tile<MMA, true, false>(O, kLD, G, kLD, N4, 0, acc);
         float* o = sc + lay.mat(bl.dR, b, k);
-        for_each_out<true, false>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
+        for_each_out<MMA, true, false>(acc, N, [&](int m, int n, float v) { o[(size_t)m * N + n] = v * s; });
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // backward 2: grid (2, B).  x = 0: dL_j += dL_{j+1} S'_j^T (j = K-1..1);  x = 1: dR_j += S_j^T dR_{j+1} (j = K-1..2)
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_bwd_chain_kernel(const float* ws, float* sc, int B, int T, int N, int C) {
     extern __shared__ __align__(16) float sm[];
     float* P = sm;                  // running adjoint dL_{j+1} / dR_{j+1}
@@ -313,17 +389,17 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_chain_kernel(const float* ws, 
         zero_acc(acc);
         float* out = sc + lay.mat(adj, b, j);
         if (isL) {
-            sgemm_tile<false, true>(P, kLD, cur, kLD, N4, 0, acc);
+            gemm_tile<MMA, false, true>(P, kLD, cur, kLD, N4, 0, acc);
             __syncthreads();
-            for_each_out<false, true>(acc, N, [&](int m, int n, float v) {
+            for_each_out<MMA, false, true>(acc, N, [&](int m, int n, float v) {
                 const float r = v + own[m * kLD + n];
                 P[m * kLD + n] = r;
                 out[(size_t)m * N + n] = r;
             });
         } else {
-            sgemm_tile<true, false>(cur, kLD, P, kLD, N4, 0, acc);
+            gemm_tile<MMA, true, false>(cur, kLD, P, kLD, N4, 0, acc);
             __syncthreads();
-            for_each_out<true, false>(acc, N, [&](int m, int n, float v) {
+            for_each_out<MMA, true, false>(acc, N, [&](int m, int n, float v) {
                 const float r = v + own[m * kLD + n];
                 P[m * kLD + n] = r;
                 out[(size_t)m * N + n] = r;
@@ -335,6 +411,7 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_chain_kernel(const float* ws, 
 // ------------------------------------------------------------------------------------------
 // backward 3: grid (T-1, B).  dS'_t = L_t^T dL_{t+1};  dS_t = dR_{t+1} R_t^T;  softmax backward;  dA_t
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, float* sc, const float* dA_ext, int B, int T, int N,
                                                            int C) {
     extern __shared__ __align__(16) float sm[];
@@ -376,11 +453,11 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
     float acc[4][4], acc2[4][4];
     zero_acc(acc);
     zero_acc(acc2);
-    if (hasSp) sgemm_tile<true, false>(Lt, kLD, dLn, kLD, N4, 0, acc);
-    if (hasS) sgemm_tile<false, true>(dRn, kLD, Rt, kLD, N4, 0, acc2);
+    if (hasSp) gemm_tile<MMA, true, false>(Lt, kLD, dLn, kLD, N4, 0, acc);
+    if (hasS) gemm_tile<MMA, false, true>(dRn, kLD, Rt, kLD, N4, 0, acc2);
     __syncthreads();               // every read of Lt / Rt is done: overwrite them with the products
-    for_each_out<true, false>(acc, N, [&](int m, int n, float v) { dSps[m * kLD + n] = v; });
-    for_each_out<false, true>(acc2, N, [&](int m, int n, float v) { dSs[m * kLD + n] = v; });
+    for_each_out<MMA, true, false>(acc, N, [&](int m, int n, float v) { dSps[m * kLD + n] = v; });
+    for_each_out<MMA, false, true>(acc2, N, [&](int m, int n, float v) { dSs[m * kLD + n] = v; });
     __syncthreads();
     for (int r = warp; r < 2 * N; r += kST / 32) {
         const bool second = r >= N;
@@ -405,6 +482,7 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
 // ------------------------------------------------------------------------------------------
 // backward 4: grid (T, B).  dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau, then the normalise backward
 // ------------------------------------------------------------------------------------------
+template <bool MMA>
 __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restrict__ x, const float* ws, const float* sc, float* dx,
                                                            int B, int T, int N, int C, float inv_tau) {
     extern __shared__ __align__(16) float sm[];
@@ -444,8 +522,8 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
         zero_acc(acc[h]);
         zero_acc(acc2[h]);
         if (h * 64 < C) {
-            if (hasN) sgemm_tile<false, false>(dAt, kLD, En, kLDX, N4, h * 64, acc[h]);
-            if (hasP) sgemm_tile<true, false>(dAp, kLD, Ep, kLDX, N4, h * 64, acc2[h]);
+            if (hasN) gemm_tile<MMA, false, false>(dAt, kLD, En, kLDX, N4, h * 64, acc[h]);
+            if (hasP) gemm_tile<MMA, true, false>(dAp, kLD, Ep, kLDX, N4, h * 64, acc2[h]);
         }
     }
     __syncthreads();               // En is dead: reuse it as the output tile
@@ -456,7 +534,9 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int m = own_row<false>(i), n = h * 64 + own_col<false>(j);
+                int m, n;
+                out_rc<MMA, false, false>(i, j, m, n);
+                n += h * 64;
                 if (m < N && n < C) Out[m * kLDX + n] = acc[h][i][j] * inv_tau;
             }
     __syncthreads();
@@ -466,7 +546,9 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int m = own_row<true>(i), n = h * 64 + own_col<false>(j);
+                int m, n;
+                out_rc<MMA, true, false>(i, j, m, n);
+                n += h * 64;
                 if (m < N && n < C) Out[m * kLDX + n] += acc2[h][i][j] * inv_tau;
             }
     __syncthreads();
@@ -511,25 +593,27 @@ static int set_smem(Kern kern, size_t bytes) {
 }
 
 bool walk_small_supported(int N, int C) { return N <= 64 && C <= 128 && (C % 4) == 0; }
+bool walk_small_mma_supported(int N, int C) { return walk_small_supported(N, C) && (C % 16) == 0; }
 
-int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
-                       cudaStream_t st) {
+template <bool MMA>
+static int walk_small_forward_t(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
+                                cudaStream_t st) {
     const float inv_tau = 1.0f / tau;
     const size_t sm1 = (2 * kMatX + kMat + 128) * sizeof(float), sm2 = 3 * kMat * sizeof(float);
-    int rc = set_smem(walk_s_affinity_kernel, sm1);
+    int rc = set_smem(walk_s_affinity_kernel<MMA>, sm1);
     if (rc) return rc;
-    walk_s_affinity_kernel<<<dim3(T - 1, B), kST, sm1, st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
+    walk_s_affinity_kernel<MMA><<<dim3(T - 1, B), kST, sm1, st>>>(x, ws, A_or_null, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     if (T < 3) {
         walk_s_zero_loss_kernel<<<1, 1, 0, st>>>(loss);
         CRW_LAUNCH_RET();
         return CRW_OK;
     }
-    if ((rc = set_smem(walk_s_chain_kernel, sm2))) return rc;
-    walk_s_chain_kernel<<<dim3(2, B), kST, sm2, st>>>(ws, B, T, N, C);
+    if ((rc = set_smem(walk_s_chain_kernel<MMA>, sm2))) return rc;
+    walk_s_chain_kernel<MMA><<<dim3(2, B), kST, sm2, st>>>(ws, B, T, N, C);
     CRW_LAUNCH_RET();
-    if ((rc = set_smem(walk_s_cycle_kernel, sm2))) return rc;
-    walk_s_cycle_kernel<<<dim3(T - 2, B), kST, sm2, st>>>(ws, B, T, N, C);
+    if ((rc = set_smem(walk_s_cycle_kernel<MMA>, sm2))) return rc;
+    walk_s_cycle_kernel<MMA><<<dim3(T - 2, B), kST, sm2, st>>>(ws, B, T, N, C);
     CRW_LAUNCH_RET();
     if ((rc = set_smem(walk_s_loss_reduce_kernel, 0))) return rc;
     walk_s_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, B, T, N, C);
@@ -537,31 +621,44 @@ int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, fl
     return CRW_OK;
 }
 
-int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
-                        float tau, float* dx, float* sc, cudaStream_t st) {
+template <bool MMA>
+static int walk_small_backward_t(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N,
+                                 int C, float tau, float* dx, float* sc, cudaStream_t st) {
     const float inv_tau = 1.0f / tau;
     int rc;
     if (T >= 3) {
         const size_t sm = 2 * kMat * sizeof(float);
-        if ((rc = set_smem(walk_s_bwd_own_kernel, sm))) return rc;
-        walk_s_bwd_own_kernel<<<dim3(T - 2, B, 2), kST, sm, st>>>(ws, sc, dloss, B, T, N, C);
+        if ((rc = set_smem(walk_s_bwd_own_kernel<MMA>, sm))) return rc;
+        walk_s_bwd_own_kernel<MMA><<<dim3(T - 2, B, 2), kST, sm, st>>>(ws, sc, dloss, B, T, N, C);
         CRW_LAUNCH_RET();
         if (T >= 4) {
             const size_t smc = 5 * kMat * sizeof(float);
-            if ((rc = set_smem(walk_s_bwd_chain_kernel, smc))) return rc;
-            walk_s_bwd_chain_kernel<<<dim3(2, B), kST, smc, st>>>(ws, sc, B, T, N, C);
+            if ((rc = set_smem(walk_s_bwd_chain_kernel<MMA>, smc))) return rc;
+            walk_s_bwd_chain_kernel<MMA><<<dim3(2, B), kST, smc, st>>>(ws, sc, B, T, N, C);
             CRW_LAUNCH_RET();
         }
     }
     const size_t smA = (6 * kMat + 128) * sizeof(float);
-    if ((rc = set_smem(walk_s_bwd_dA_kernel, smA))) return rc;
-    walk_s_bwd_dA_kernel<<<dim3(T - 1, B), kST, smA, st>>>(ws, sc, dA_or_null, B, T, N, C);
+    if ((rc = set_smem(walk_s_bwd_dA_kernel<MMA>, smA))) return rc;
+    walk_s_bwd_dA_kernel<MMA><<<dim3(T - 1, B), kST, smA, st>>>(ws, sc, dA_or_null, B, T, N, C);
     CRW_LAUNCH_RET();
     const size_t smX = (2 * kMat + 2 * kMatX) * sizeof(float);
-    if ((rc = set_smem(walk_s_bwd_dx_kernel, smX))) return rc;
-    walk_s_bwd_dx_kernel<<<dim3(T, B), kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
+    if ((rc = set_smem(walk_s_bwd_dx_kernel<MMA>, smX))) return rc;
+    walk_s_bwd_dx_kernel<MMA><<<dim3(T, B), kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     return CRW_OK;
+}
+
+// mma = false: fp32 FMA (CRW_PREC_FP32);  mma = true: mma.sync on split bf16 pairs (CRW_PREC_BF16X3 at these sizes)
+int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
+                       cudaStream_t st, bool mma) {
+    return mma ? walk_small_forward_t<true>(x, B, T, N, C, tau, loss, A_or_null, ws, st)
+               : walk_small_forward_t<false>(x, B, T, N, C, tau, loss, A_or_null, ws, st);
+}
+int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
+                        float tau, float* dx, float* sc, cudaStream_t st, bool mma) {
+    return mma ? walk_small_backward_t<true>(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st)
+               : walk_small_backward_t<false>(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
 }
 
 }  // namespace crw

@@ -246,8 +246,19 @@ WALK_TC_CASES = [
 ]
 
 
+@pytest.fixture(params=["auto", "tiles"])
+def walk_engine(request, monkeypatch):
+    """BF16X3 engines: auto = warp-level MMA shared-memory kernels for one-tile sizes (N <= 64), tcgen05 tiles beyond;
+    tiles = the tcgen05 tile path at every size."""
+    if request.param == "tiles":
+        monkeypatch.setenv("CRW_WALK_FORCE_TILES", "1")
+    else:
+        monkeypatch.delenv("CRW_WALK_FORCE_TILES", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("case", WALK_TC_CASES)
-def test_walk_tensorcore_vs_f64_oracle(pkg, case):
+def test_walk_tensorcore_vs_f64_oracle(pkg, case, walk_engine):
     B, T, N, C, tau = case
     rs = np.random.RandomState(B * 1000 + T * 100 + N)
     x = (rs.randn(B, T, N, C) + 1.0 * rs.randn(B, 1, 1, C)).astype(np.float32)
@@ -262,7 +273,7 @@ def test_walk_tensorcore_vs_f64_oracle(pkg, case):
     assert err < 1e-3, err
 
 
-def test_walk_tensorcore_golden_reference(pkg):
+def test_walk_tensorcore_golden_reference(pkg, walk_engine):
     for name in ["walk_cfg1_f32.npz", "walk_tau001_f32.npz"]:
         g = load_golden(name)
         xt = _dev(g["x"].astype(np.float32)).requires_grad_(True)
