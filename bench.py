@@ -408,6 +408,9 @@ def run_b200(args):
     only = args.only
     tr = bench_train(crw, args, rank, world, local, pk) if only in ("all", "train") else None
     wk = bench_walk(crw, args, world, pk) if only in ("all", "walk") else None
+    # the same fwd+bwd with precision = BF16X3 (warp-level MMAs on split bf16 pairs at this size); reported beside the fp32 kernels
+    wk_tc = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3,
+                       kernel_note="walk fwd+bwd kernels (BF16X3: mma.sync on bf16 hi/lo pairs), 8 launches") if only in ("all", "walk") else None
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
     if only == "walk_tc_large":     # profiling aid: the tcgen05 walk engine at the scaled geometry N=369
         r = bench_walk(crw, args, world, pk, N=369, T=20, B=32, precision=crw.ops.PREC_BF16X3,
@@ -433,7 +436,10 @@ def run_b200(args):
             B, T = TRAIN["B"], TRAIN["T"]
             hot = dict(what="fused walk fwd+bwd (crw_b200::walk_loss + backward), embeddings resident, CUDA-graph replay",
                        ms=wk["ms"], ms_eager_dispatch=wk["ms_eager"],
-                       launches=wk["launches"], share_of_step=wk["ms"] / tr["ms_per_step"])
+                       launches=wk["launches"], share_of_step=wk["ms"] / tr["ms_per_step"],
+                       bf16x3=dict(ms=wk_tc["ms"], tflops=wk_tc["roofline"]["achieved"], frac=wk_tc["roofline"]["frac"],
+                                   note="precision=BF16X3 (error-compensated bf16 pairs, fp32 accumulate; gradients within 1e-4 "
+                                        "of fp64); the train step above runs the fp32 kernels"))
             line = dict(
                 metric="crw_train_radargrams_per_sec", value=tr["value"], unit="radargrams/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=tr["ms_per_step"], higher_is_better=True,
