@@ -204,6 +204,40 @@ def test_lp_tensorcore_fixed_mode(pkg, host):
     assert frac >= 0.995
 
 
+def test_lp_config5_per_gpu_size_properties(pkg):
+    """BASELINE config 5 as one GPU of eight sees it (8 radargrams x 400 x 50 000 columns -> R=8, T=3125, N=49, k=20, r=24):
+    size-independent properties of the result, radargram independence, the host-streamed path, and a window against the oracle."""
+    R, T, N, M, ctx, k, radius = 8, 3125, 49, 4, 20, 20, 24.0
+    g = torch.Generator().manual_seed(5)
+    feats_host = torch.randn(R, T, N, 128, generator=g).pin_memory()
+    label0 = torch.randint(0, M, (R, N), generator=g)
+    mask0 = torch.nn.functional.one_hot(label0, M).permute(0, 2, 1).float().contiguous().cuda()
+    feats = feats_host.cuda()
+    labels, masks, W, I = pkg.ops.labelprop(feats, mask0, ctx, radius, 0.07, k, 0, pkg.ops.PREC_BF16X3, True, True)
+    torch.cuda.synchronize()
+    W1, I1 = W[:, 1:], I[:, 1:]
+    assert torch.all(W1 >= 0) and (W1.sum(2) - 1).abs().max().item() < 1e-5            # softmax over the k neighbours
+    assert torch.all(W1[:, :, :-1] >= W1[:, :, 1:])                                     # sorted by descending weight
+    n = torch.arange(1, T, device="cuda").view(1, -1, 1, 1)
+    n_key = torch.clamp(n, max=ctx + 1)                                                 # frames in the (trimmed) key set
+    assert torch.all(I1 >= 0) and torch.all(I1 < n_key * N)
+    q = torch.arange(N, device="cuda").view(1, 1, 1, -1)
+    assert torch.all(((I1 % N) - q).abs() <= 23)                                        # inside the radius band (ceil(r) - 1)
+    srt = torch.sort(I1, dim=2).values
+    assert torch.all(srt[:, :, 1:] != srt[:, :, :-1])                                   # k distinct candidates
+    assert torch.all((labels >= 0) & (labels < M)) and torch.equal(labels[:, 0].cpu(), label0.int())
+    assert (masks.sum(2) - 1).abs().max().item() < 1e-4                                 # soft masks stay distributions
+    one = pkg.ops.labelprop(feats[3:4].contiguous(), mask0[3:4].contiguous(), ctx, radius, 0.07, k, 0, pkg.ops.PREC_BF16X3, True, True)
+    for a_, b_ in zip(one, (labels[3:4], masks[3:4], W[3:4], I[3:4])):                  # radargrams are independent
+        assert torch.equal(a_, b_)
+    host = pkg.ops.labelprop_host(feats_host, mask0, ctx, radius, 0.07, k, 0, True, True)   # 32 chunks through the staging buffers
+    torch.cuda.synchronize()
+    for a_, b_ in zip(host, (labels, masks, W, I)):
+        assert torch.equal(a_, b_)
+    o = c_oracle.labelprop(feats_host[5:6, :64].numpy(), label0[5:6].numpy().astype(np.int32), M, ctx, radius, 0.07, k)
+    assert (labels[5, :64].cpu().numpy() == o["labels"][0]).mean() >= 0.999
+
+
 def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
     for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
