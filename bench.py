@@ -385,6 +385,11 @@ def bench_labelprop(crw, args, rank, world, pk):
                       else "l2_normalize + lp_topk_f32_kernel + gather kernels", algorithmic_bytes=lp_bytes,
                       peak_source=pk["src"],
                       tensor_bound_note=f"dense {dense / 1e9:.1f} GFLOP: AI ~514 FLOP/B > ridge, see DESIGN.md"),
+        # the physically binding roofline (AI above the ridge): algorithmic dense FLOPs over the whole step; the error-compensated
+        # bf16 path executes three MMA passes, counted once here
+        roofline_tensor=dict(bound="tensor", achieved=dense / (ms * 1e-3) / 1e12, peak=pk["bf16"], unit="TFLOP/s",
+                             frac=dense / (ms * 1e-3) / 1e12 / pk["bf16"], algorithmic_flops=dense,
+                             note="dense (ctx+1) N^2 C 2 per query frame; 41 % of it lies inside the radius band; x3 executed"),
         gpu_launches=5 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
         frames=Tl, fp32_path=fp32_path,
         scaling="strong" if cfg5 else "weak",
