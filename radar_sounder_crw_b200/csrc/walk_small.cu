@@ -28,17 +28,21 @@ __device__ __forceinline__ void zero_fill(float* p, int n) {
     for (int i = threadIdx.x; i < n; i += kST) p[i] = 0.0f;
 }
 // N x N matrix (global, dense) -> smem pitch kLD.  Rows are not 16-byte aligned for odd N: 4-byte cp.async.
+// (x / d for x * d < 2^32 is __umulhi(x, 2^32 / d + 1): the index loops below would otherwise spend their time dividing)
+__device__ __forceinline__ unsigned div_magic(int d) { return (unsigned)(0x100000000ull / (unsigned)d) + 1u; }
 __device__ __forceinline__ void load_nn(float* dst, const float* src, int N) {
+    const unsigned mg = div_magic(N);
     for (int i = threadIdx.x; i < N * N; i += kST) {
-        const int r = i / N, c = i - r * N;
+        const int r = (int)__umulhi((unsigned)i, mg), c = i - r * N;
         cp_async4(dst + r * kLD + c, src + i);
     }
 }
 // N x C feature tile (global rows are 16-byte aligned since C % 4 == 0) -> smem pitch kLDX
 __device__ __forceinline__ void load_nc(float* dst, const float* src, int N, int C) {
     const int c4 = C >> 2;
+    const unsigned mg = div_magic(c4);
     for (int i = threadIdx.x; i < N * c4; i += kST) {
-        const int r = i / c4, c = (i - r * c4) * 4;
+        const int r = (int)__umulhi((unsigned)i, mg), c = (i - r * c4) * 4;
         cp_async16(dst + r * kLDX + c, src + (size_t)r * C + c);
     }
 }
@@ -212,15 +216,16 @@ __global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __res
         const bool col = r >= N;
         const int i = col ? r - N : r;
         const int step = col ? kLD : 1, base = col ? i : i * kLD;
-        float mx = -INFINITY;
-        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, At[base + j * step]);
-        mx = warp_max(mx);
-        float se = 0.0f;
-        for (int j = lane; j < N; j += 32) se += __expf(At[base + j * step] - mx);
-        se = warp_sum(se);
-        const float inv = 1.0f / se;
+        // N <= 64: a lane holds its (at most) two entries of the row / column in registers across the three passes
+        const bool has1 = lane + 32 < N;
+        const float a0 = (lane < N) ? At[base + lane * step] : -INFINITY;
+        const float a1 = has1 ? At[base + (lane + 32) * step] : -INFINITY;
+        const float mx = warp_max(fmaxf(a0, a1));
+        const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx);          // exp(-inf) = 0 for the absent entries
+        const float inv = 1.0f / warp_sum(e0 + e1);
         float* dst = (col ? Sp : S) + (size_t)i * N;
-        for (int j = lane; j < N; j += 32) dst[j] = __expf(At[base + j * step] - mx) * inv;
+        if (lane < N) dst[lane] = e0 * inv;
+        if (has1) dst[lane + 32] = e1 * inv;
     }
 }
 
@@ -254,8 +259,9 @@ __global__ void __launch_bounds__(kST) walk_s_chain_kernel(float* ws, int B, int
     __syncthreads();
     if (k_first <= K) load_nn(Op, ws + lay.mat(opnd, b, k_first - 1), N);
     float* first = ws + lay.mat(chain, b, k_first - 1);    // L_0 = I, R_1 = I
+    const unsigned mgN = div_magic(N);
     for (int i = threadIdx.x; i < N * N; i += kST) {
-        const int r = i / N, c = i - r * N;
+        const int r = (int)__umulhi((unsigned)i, mgN), c = i - r * N;
         const float v = (r == c) ? 1.0f : 0.0f;
         P[r * kLD + c] = v;
         first[i] = v;
@@ -303,14 +309,14 @@ __global__ void __launch_bounds__(kST) walk_s_cycle_kernel(float* ws, int B, int
     float part = 0.0f;
     for (int d = warp; d < N; d += kST / 32) {
         const float* row = M + d * kLD;
-        float mx = -INFINITY;
-        for (int c = lane; c < N; c += 32) mx = fmaxf(mx, row[c]);
-        mx = warp_max(mx);
-        float se = 0.0f;
-        for (int c = lane; c < N; c += 32) se += __expf(row[c] - mx);
-        se = warp_sum(se);
+        const bool has1 = lane + 32 < N;
+        const float a0 = (lane < N) ? row[lane] : -INFINITY, a1 = has1 ? row[lane + 32] : -INFINITY;
+        const float mx = warp_max(fmaxf(a0, a1));
+        const float e0 = __expf(a0 - mx), e1 = __expf(a1 - mx);
+        const float se = warp_sum(e0 + e1);
         const float inv = 1.0f / se;
-        for (int c = lane; c < N; c += 32) Gk[(size_t)d * N + c] = __expf(row[c] - mx) * inv - (c == d ? 1.0f : 0.0f);
+        if (lane < N) Gk[(size_t)d * N + lane] = e0 * inv - (lane == d ? 1.0f : 0.0f);
+        if (has1) Gk[(size_t)d * N + lane + 32] = e1 * inv - (lane + 32 == d ? 1.0f : 0.0f);
         part += (logf(se) + mx) - row[d];
     }
     if (lane == 0) red[warp] = part;
@@ -470,8 +476,9 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
         if (lane == 0) (second ? rSp : rS)[i] = a;
     }
     __syncthreads();
+    const unsigned mgN = div_magic(N);
     for (int e = threadIdx.x; e < N * N; e += kST) {
-        const int i = e / N, j = e - i * N;
+        const int i = (int)__umulhi((unsigned)e, mgN), j = e - i * N;
         float g = ext ? ext[e] : 0.0f;
         g += Ss[i * kLD + j] * (dSs[i * kLD + j] - rS[i]);
         g += Sps[j * kLD + i] * (dSps[j * kLD + i] - rSp[j]);
@@ -510,10 +517,12 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
     cp_async_wait_all();
     __syncthreads();
     // E = x * invn (rows)
-    for (int i = threadIdx.x; i < N * C; i += kST) {
-        const int r = i / C, c = i - r * C;
-        if (hasN) En[r * kLDX + c] *= invn[(size_t)(t + 1) * N + r];
-        if (hasP) Ep[r * kLDX + c] *= invn[(size_t)(t - 1) * N + r];
+    for (int r = warp; r < N; r += kST / 32) {
+        const float in = hasN ? invn[(size_t)(t + 1) * N + r] : 0.0f, ip = hasP ? invn[(size_t)(t - 1) * N + r] : 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            if (hasN) En[r * kLDX + c] *= in;
+            if (hasP) Ep[r * kLDX + c] *= ip;
+        }
     }
     __syncthreads();
     float acc[2][4][4], acc2[2][4][4];
