@@ -24,17 +24,18 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ void zero_fill(float* p, int n) {
-    for (int i = threadIdx.x; i < n; i += kST) p[i] = 0.0f;
+__device__ __forceinline__ void zero_fill(float* p, int n) {     // n % 4 == 0, p 16-byte aligned
+    float4* p4 = reinterpret_cast<float4*>(p);
+    for (int i = threadIdx.x; i < (n >> 2); i += kST) p4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 // N x N matrix (global, dense) -> smem pitch kLD.  Rows are not 16-byte aligned for odd N: 4-byte cp.async.
 // (x / d for x * d < 2^32 is __umulhi(x, 2^32 / d + 1): the index loops below would otherwise spend their time dividing)
 __device__ __forceinline__ unsigned div_magic(int d) { return (unsigned)(0x100000000ull / (unsigned)d) + 1u; }
 __device__ __forceinline__ void load_nn(float* dst, const float* src, int N) {
-    const unsigned mg = div_magic(N);
-    for (int i = threadIdx.x; i < N * N; i += kST) {
-        const int r = (int)__umulhi((unsigned)i, mg), c = i - r * N;
-        cp_async4(dst + r * kLD + c, src + i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < N; r += kST / 32) {           // N <= 64: at most two columns per lane
+        if (lane < N) cp_async4(dst + r * kLD + lane, src + r * N + lane);
+        if (lane + 32 < N) cp_async4(dst + r * kLD + lane + 32, src + r * N + lane + 32);
     }
 }
 // N x C feature tile (global rows are 16-byte aligned since C % 4 == 0) -> smem pitch kLDX
@@ -183,7 +184,10 @@ __global__ void __launch_bounds__(kST) walk_s_affinity_kernel(const float* __res
     for (int r = warp; r < 2 * N; r += kST / 32) {
         const float* xr = (r < N) ? X0 + r * kLDX : X1 + (r - N) * kLDX;
         float ss = 0.0f;
-        for (int c = lane; c < C; c += 32) ss = fmaf(xr[c], xr[c], ss);
+        for (int c = 4 * lane; c < C; c += 128) {          // C % 4 == 0, rows 16-byte aligned
+            const float4 v = *reinterpret_cast<const float4*>(xr + c);
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
         ss = warp_sum(ss);
         const float inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
         if (lane == 0) {
@@ -470,8 +474,8 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dA_kernel(const float* ws, flo
         const int i = second ? r - N : r;
         const float* P = (second ? Sps : Ss) + i * kLD;
         const float* dP = (second ? dSps : dSs) + i * kLD;
-        float a = 0.0f;
-        for (int j = lane; j < N; j += 32) a = fmaf(P[j], dP[j], a);   // zero when the term is absent (buffers zero-filled)
+        float a = (lane < N) ? P[lane] * dP[lane] : 0.0f;                  // zero when the term is absent (buffers zero-filled)
+        if (lane + 32 < N) a = fmaf(P[lane + 32], dP[lane + 32], a);
         a = warp_sum(a);
         if (lane == 0) (second ? rSp : rS)[i] = a;
     }
