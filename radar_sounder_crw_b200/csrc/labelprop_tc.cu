@@ -69,6 +69,9 @@ struct TcParams {
     int v_begin, v_end; // range of schedule slots this launch walks (slot -> tile: early tiles of all radargrams first)
     unsigned magic_n;   // floor(2^32 / N) + 1: x / N == __umulhi(x, magic_n) for x * N < 2^32
     int debug;          // profiling aid (env CRW_TC_DEBUG): 1 = skip insertions, 2 = also skip filter/park; results invalid
+    const __nv_bfloat16* hi;   // [R*T*N, 128] operand planes (the TS kernel reads its query rows straight from them)
+    const __nv_bfloat16* lo;
+    long long total_rows;
 };
 
 // host-side plan of one tensor-path call (opaque to labelprop_f32.cu: it only sees the size)
@@ -76,6 +79,7 @@ struct LpTcPlan {
     alignas(64) unsigned char maps[4 * sizeof(CUtensorMap)];
     TcParams p;
     int pair;
+    int ts;
 };
 
 struct TileInfo {
@@ -171,16 +175,28 @@ __device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32
 }
 
 // Filter threshold of one partial list.  The lists of the other parts of the same query (same lane, warps 4 apart) cover
-// disjoint key columns, so their k-th best values are lower bounds on the query's final k-th best as well: a candidate
-// strictly below any of them cannot survive the merge.  Equal values may still win the merge on the id tie rule, hence
-// the partner bound is taken one ulp down and the comparison stays strict.  Stale (smaller) published values are safe.
+// disjoint key columns, so lower bounds on the query's final k-th best follow from what they publish:
+//   (1) a partner's own k-th best (its list alone already holds k values that large);
+//   (2) with two parts, min(own[h-1], partner[h-1]) for h = ceil(KT / 2): the two lists together hold 2h >= k values at least
+//       that large.  For similar halves this is close to the k-th best of everything seen so far, where (1) is only the
+//       2k-th best -- it is what keeps the number of inserted candidates near k (1 + ln(n / k)) although the query has two lists.
+// A candidate strictly below a bound cannot survive the merge.  Equal values may still win the merge on the id tie rule,
+// hence the bounds are taken one ulp down and the comparison stays strict.  Stale (smaller) published values are safe.
+// a value strictly below x (within a few ulp); -inf stays -inf.  (nextafterf() is a ~20-instruction sequence.)
+__device__ __forceinline__ float strictly_below(float x) { return __fmaf_rn(-fabsf(x), 2.384185791015625e-07f, x) - 1.17549435e-38f; }
+
 template <int NEPI>
-__device__ __forceinline__ float shared_threshold(const float* thr_pub, int warp, int lane, float own) {
+__device__ __forceinline__ float shared_threshold(const float* thr_pub, const float* mid_pub, int warp, int lane, float own,
+                                                  float own_mid, bool use_mid = true) {
     float t = own;
 #pragma unroll
     for (int pp = 1; pp < NEPI / 4; ++pp) {
         const float o = *reinterpret_cast<const volatile float*>(&thr_pub[((warp + 4 * pp) % NEPI) * 32 + lane]);
-        t = fmaxf(t, nextafterf(o, -INFINITY));
+        t = fmaxf(t, strictly_below(o));
+    }
+    if (NEPI / 4 == 2 && use_mid) {
+        const float m = *reinterpret_cast<const volatile float*>(&mid_pub[((warp + 4) % NEPI) * 32 + lane]);
+        t = fmaxf(t, strictly_below(fminf(own_mid, m)));
     }
     return t;
 }
@@ -232,13 +248,22 @@ __device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& 
         }
 }
 
-template <int KT, int NEPI>
+// TS = true: the query tile is the A operand IN TENSOR MEMORY (tcgen05.mma "TS" form).  The epilogue threads (thread = query
+// row = TMEM lane) copy their own row of the hi / lo planes from global memory into one of two 128-column TMEM buffers, one
+// query tile ahead, so an MMA reads only its 2 KB of B from shared memory (64 B/clk) instead of 6 KB (192 B/clk against a
+// 128 B/clk port) and the freed 64 KB hold two more key stages.  TMEM: [0,256) two query buffers (hi 64 | lo 64 columns
+// each), [256,512) four 64-column accumulators.
+template <int KT, int NEPI, bool TS>
 __global__ void __launch_bounds__((NEPI + 2) * 32, 1)
 lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_constant__ CUtensorMap qmap_lo,
                   const __grid_constant__ CUtensorMap kmap_hi, const __grid_constant__ CUtensorMap kmap_lo, TcParams p) {
     constexpr int kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
     constexpr int kParts = NEPI / 4;          // top-k lists per query (merged at the end of a tile)
     constexpr int kParkWarp = kParkBytes / NEPI;
+    static_assert(!TS || NEPI == 8, "the TS form stages the hi plane with part 0 and the lo plane with part 1");
+    constexpr int kNStages = TS ? (kQBytes + kStages * kKBytes) / kKBytes : kStages;   // same carve-up size: 5 stages
+    constexpr int kNAcc = TS ? 4 : kAcc;
+    constexpr uint32_t kAccCol0 = TS ? 256u : 0u;
     // 8 epilogue warps: two parts, whole 64-column key tiles dealt round-robin.  16 warps: four parts = two tile groups x two
     // 32-column halves (the park buffer of a warp then only has to hold 32 columns per lane).
     constexpr int kColSplit = (NEPI > 8) ? 2 : 1;
@@ -247,32 +272,35 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     static_assert(kParkWarp >= kCols * 32 * 4, "park buffer must hold this warp's columns of one key tile per lane");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                  // 64 KB
-    uint8_t* sK = smem + kQBytes;                        // kStages x 32 KB
-    uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
+    uint8_t* sQ = smem;                                  // 64 KB (SS form only)
+    uint8_t* sK = TS ? smem : smem + kQBytes;            // kNStages x 32 KB
+    uint8_t* park_base = sK + kNStages * kKBytes;        // 64 KB
     {
         uint32_t dyn_bytes;
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
         if ((size_t)(park_base + kParkBytes - smem_raw) > dyn_bytes) __trap();    // the launch did not provide the carve-up
     }
-    __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kAcc], acc_empty[kAcc];
+    __shared__ uint64_t q_full[2], q_empty, k_full[kNStages], k_empty[kNStages], acc_full[kNAcc], acc_empty[kNAcc];
     __shared__ uint32_t tmem_base_s;
     __shared__ float thr_pub[NEPI * 32];     // every list's current k-th best, read by the other part(s) of the same query
+    __shared__ float mid_pub[NEPI * 32];     // ... and its current ceil(KT/2)-th best (see shared_threshold)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
 
     if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_base_s);
     if (tid == 0) {
-        tc::mbar_init(&q_full, 1);
+        tc::mbar_init(&q_full[0], TS ? NEPI : 1);
+        tc::mbar_init(&q_full[1], TS ? NEPI : 1);
         tc::mbar_init(&q_empty, 1);
-        for (int s = 0; s < kStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
-        for (int a = 0; a < kAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4 * kColSplit); }
+        for (int s = 0; s < kNStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
+        for (int a = 0; a < kNAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4 * kColSplit); }
         tc::fence_barrier_init();
     }
-    if (tid < NEPI * 32) thr_pub[tid] = -INFINITY;
+    if (tid < NEPI * 32) { thr_pub[tid] = -INFINITY; mid_pub[tid] = -INFINITY; }
     if (warp == kProducerWarp && lane == 0) {
-        tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
+        if (!TS) { tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); }
+        tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -287,18 +315,20 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int grow = t.rg * p.T * N;   // first global row of this radargram
-            tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
-            if (leader) {
-                tc::mbar_arrive_expect_tx(&q_full, kQBytes);
+            if (!TS) {
+                tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
+                if (leader) {
+                    tc::mbar_arrive_expect_tx(&q_full[0], kQBytes);
 #pragma unroll
-                for (int sub = 0; sub < 4; ++sub)
-                    tc::tma_load_2d(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64, grow + t.r0, &q_full);
+                    for (int sub = 0; sub < 4; ++sub)
+                        tc::tma_load_2d(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64, grow + t.r0, &q_full[0]);
+                }
             }
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                const int s = kcnt % kStages;
+                const int s = kcnt % kNStages;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
-                tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kStages) & 1) ^ 1);
+                tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kNStages) & 1) ^ 1);
                 if (leader) {
                     tc::mbar_arrive_expect_tx(&k_full[s], kKBytes);
                     uint8_t* dst = sK + s * kKBytes;
@@ -318,18 +348,20 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
-            tc::mbar_wait_backoff(&q_full, tcnt & 1);
+            if (TS) tc::mbar_wait_backoff(&q_full[tcnt & 1], (tcnt >> 1) & 1);
+            else tc::mbar_wait_backoff(&q_full[0], tcnt & 1);
+            const uint32_t qtmem = tmem_base + (uint32_t)((tcnt & 1) * 128);      // TS: this tile's query buffer
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                const int s = kcnt % kStages, a = kcnt % kAcc;
+                const int s = kcnt % kNStages, a = kcnt % kNAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
                 const int ncols = min(kBN, (nrows + 15) & ~15);
-                tc::mbar_wait(&k_full[s], (kcnt / kStages) & 1);            // latency critical: no backoff
-                tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kAcc) & 1) ^ 1);
+                tc::mbar_wait(&k_full[s], (kcnt / kNStages) & 1);           // latency critical: no backoff
+                tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kNAcc) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
                 const uint64_t kdesc = kdesc0 + (uint64_t)((s * kKBytes) >> 4);   // start-address field counts 16-byte units
-                const uint32_t d = tmem_base + (uint32_t)(a * kBN);
+                const uint32_t d = tmem_base + kAccCol0 + (uint32_t)(a * kBN);
                 if (leader) {
                     // pass 0: q_hi.k_hi   pass 1: q_hi.k_lo   pass 2: q_lo.k_hi ; sub-tile = part*2 + kblock, k-step = 32 bytes
                     if (!(p.debug & 4))
@@ -340,9 +372,14 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = qdesc + (uint64_t)((((qpart + kb) * (kBM * 128)) + ks * 32) >> 4);
                                 const uint64_t bd = kdesc + (uint64_t)((((kpart + kb) * (kBN * 128)) + ks * 32) >> 4);
-                                tc::umma_bf16_ss(d, ad, bd, idesc, (pass | kb | ks) ? 1u : 0u);
+                                if (TS) {
+                                    // 32-bit column c of a query buffer = K elements 2c, 2c+1: hi at [0,64), lo at [64,128)
+                                    tc::umma_bf16_ts(d, qtmem + (uint32_t)((qpart ? 64 : 0) + kb * 32 + ks * 8), bd, idesc, (pass | kb | ks) ? 1u : 0u);
+                                } else {
+                                    const uint64_t ad = qdesc + (uint64_t)((((qpart + kb) * (kBM * 128)) + ks * 32) >> 4);
+                                    tc::umma_bf16_ss(d, ad, bd, idesc, (pass | kb | ks) ? 1u : 0u);
+                                }
                             }
                     }
                     tc::umma_commit(&k_empty[s]);     // smem stage may be refilled once these MMAs retire
@@ -350,7 +387,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
                 __syncwarp();
             }
-            if (leader) tc::umma_commit(&q_empty);    // query tile may be overwritten
+            if (!TS && leader) tc::umma_commit(&q_empty);    // query tile may be overwritten
             __syncwarp();
             ++tcnt;
         }
@@ -366,10 +403,47 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
-        uint32_t kcnt = 0;
+        uint32_t kcnt = 0, tcnt = 0;
+        // TS: copy this thread's row of the hi (part 0) / lo (part 1) plane of query tile `tl` into query buffer `buf`
+        auto stage_query = [&](int tl, uint32_t buf) {
+            const TileInfo tq = tile_info(p, tl);
+            const long long grow_q = (long long)tq.rg * p.T * N + tq.r0 + lrow;
+            const uint4* src = reinterpret_cast<const uint4*>((part ? p.lo : p.hi) + grow_q * 128);
+            const bool in_range = grow_q < p.total_rows;
+            uint32_t r[64];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint4 v = in_range ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+                r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+            }
+            const uint32_t dst = tmem_base + ((uint32_t)(g * 32) << 16) + buf * 128u + (uint32_t)(part * 64);
+            tc::tmem_st_32x32b_x32(dst, r);
+            tc::tmem_st_32x32b_x32(dst + 32u, r + 32);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&q_full[buf]);
+        };
+        auto next_tile = [&](int tl) {       // next tile of this CTA that has work, or -1
+            for (tl += gridDim.x; tl < p.v_end; tl += gridDim.x)
+                if (tile_info(p, tl).n_ktiles != 0) return tl;
+            return -1;
+        };
+        if (TS) {
+            int first = p.v_begin + blockIdx.x;
+            if (first < p.v_end && tile_info(p, first).n_ktiles == 0) first = next_tile(first);
+            if (first >= 0 && first < p.v_end) stage_query(first, 0u);
+        }
         for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
+            if (TS) {
+                // one tile ahead: the other buffer was read by the previous tile, all of whose accumulators this warp pair has
+                // consumed (MMAs complete in order), so it is free
+                const int nx = next_tile(tile);
+                if (nx >= 0) stage_query(nx, (tcnt + 1) & 1u);
+                ++tcnt;
+            }
             const int row = t.r0 + lrow;
             const int n = row / N, q = row - n * N;
             const bool qvalid = (n >= 1) && (n < p.T);
@@ -377,8 +451,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                if ((kt % kTileGroups) != part / kColSplit) continue;        // key tiles are dealt round-robin to the tile groups
-                const int a = kcnt % kAcc;
+                // key tiles are dealt round-robin to the tile groups; the group that also merges and finishes the query (part 0)
+                // takes the later residue, i.e. the smaller share when the count does not divide
+                if ((kt % kTileGroups) != (((p.debug & 64) ? 0 : kTileGroups - 1) ^ (part / kColSplit)) % kTileGroups) continue;
+                const int a = kcnt % kNAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
                 const int col0 = (part % kColSplit) * kCols;                 // this warp's columns of the tile
@@ -386,23 +462,37 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 nrows = min(kCols, nrows - col0);                            // <= 0: nothing in this half, only release the buffer
                 const bool prof = (p.debug & 8) != 0;
                 long long c_0 = prof ? clock64() : 0;
-                tc::mbar_wait(&acc_full[a], (kcnt / kAcc) & 1);
+                tc::mbar_wait(&acc_full[a], (kcnt / kNAcc) & 1);
                 tc::tc_fence_after();
                 long long c_1 = prof ? clock64() : 0;
-                const float thr = shared_threshold<NEPI>(thr_pub, warp, lane, top.v[KT - 1]);
+                const float thr = shared_threshold<NEPI>(thr_pub, mid_pub, warp, lane, top.v[KT - 1], top.v[(KT + 1) / 2 - 1], !(p.debug & 16));
                 uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
+                {
+                    // both 32-column loads are in flight before the one wait; once the values sit in registers the TMEM
+                    // buffer is handed back to the MMA warp (the insertion loop below reads the parked copy only)
+                    const bool legacy = (p.debug & 32) != 0;      // A/B aid: wait per load, release after the insertions
+                    float v[kCh][32];
 #pragma unroll
-                for (int ch = 0; ch < kCh; ++ch) {
-                    if (ch * 32 < nrows && !(p.debug & 2)) {                        // warp-uniform
-                        float v[32];
-                        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kBN + col0 + ch * 32), v);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            tc::sts_f32(park + (ch * 32 + i) * 128, v[i]);
-                            pm[ch] |= (v[i] > thr) ? (1u << i) : 0u;
+                    for (int ch = 0; ch < kCh; ++ch)
+                        if (ch * 32 < nrows && !(p.debug & 2)) {                    // warp-uniform
+                            tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + kAccCol0 + (uint32_t)(a * kBN + col0 + ch * 32), v[ch]);
+                            if (legacy) tc::tmem_ld_wait();
                         }
+                    tc::tmem_ld_wait();
+                    if (!legacy) {
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
                     }
+#pragma unroll
+                    for (int ch = 0; ch < kCh; ++ch)
+                        if (ch * 32 < nrows && !(p.debug & 2)) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                tc::sts_f32(park + (ch * 32 + i) * 128, v[ch][i]);
+                                pm[ch] |= (v[ch][i] > thr) ? (1u << i) : 0u;
+                            }
+                        }
                 }
                 long long c_2 = prof ? clock64() : 0;
                 // validity mask of this thread over the tile's key rows (segments = key frames)
@@ -440,9 +530,12 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     }
                 }
                 thr_pub[warp * 32 + lane] = top.v[KT - 1];
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+                mid_pub[warp * 32 + lane] = top.v[(KT + 1) / 2 - 1];
+                if (p.debug & 32) {
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+                }
                 if (prof) {
                     const long long c_4 = clock64();
                     iters = __reduce_max_sync(0xffffffffu, iters);
@@ -475,6 +568,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
             thr_pub[warp * 32 + lane] = -INFINITY;
+            mid_pub[warp * 32 + lane] = -INFINITY;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // scratch free for the next tile
             if ((p.debug & 8) && lane == 0) g_lp_prof[((size_t)blockIdx.x * 8 + warp) * 6 + 4] += clock64() - c_m;
         }
@@ -526,9 +620,15 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
     uint8_t* sQ = smem;                                  // 64 KB: this CTA's 128 query rows
     uint8_t* sK = smem + kQBytes;                        // kStages x 32 KB: this CTA's 64 rows of each key tile
     uint8_t* park_base = sK + kStages * kKBytes;         // 64 KB
+    {
+        uint32_t dyn_bytes;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        if ((size_t)(park_base + kParkBytes - smem_raw) > dyn_bytes) __trap();    // the launch did not provide the carve-up
+    }
     __shared__ uint64_t q_full, q_empty, k_full[kStages], k_empty[kStages], acc_full[kPairAcc], acc_empty[kPairAcc];
     __shared__ uint32_t tmem_base_s;
     __shared__ float thr_pub[NEPI * 32];
+    __shared__ float mid_pub[NEPI * 32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N;
@@ -543,7 +643,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
         for (int a = 0; a < kPairAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 2 * NEPI); }
         tc::fence_barrier_init();
     }
-    if (tid < NEPI * 32) thr_pub[tid] = -INFINITY;
+    if (tid < NEPI * 32) { thr_pub[tid] = -INFINITY; mid_pub[tid] = -INFINITY; }
     if (warp == kProducerWarp && lane == 0) {
         tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
     }
@@ -654,7 +754,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                 tc::mbar_wait(&acc_full[a], (kcnt / kPairAcc) & 1);
                 tc::tc_fence_after();
                 if (nrows > 0) {
-                    const float thr = shared_threshold<NEPI>(thr_pub, warp, lane, top.v[KT - 1]);
+                    const float thr = shared_threshold<NEPI>(thr_pub, mid_pub, warp, lane, top.v[KT - 1], top.v[(KT + 1) / 2 - 1], !(p.debug & 16));
                     uint32_t pm[2] = {0u, 0u}, vm[2] = {0u, 0u};
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
@@ -700,6 +800,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                     }
                 }
                 thr_pub[warp * 32 + lane] = top.v[KT - 1];
+                mid_pub[warp * 32 + lane] = top.v[(KT + 1) / 2 - 1];
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&acc_empty[a]), 0));
@@ -723,6 +824,7 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
             thr_pub[warp * 32 + lane] = -INFINITY;
+            mid_pub[warp * 32 + lane] = -INFINITY;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
         }
     }
@@ -731,16 +833,31 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
     if (warp == kMmaWarp) tc::tmem_dealloc_pair<512>(tmem_base);
 }
 
-template <int KT>
-static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
-    const size_t smem = 1024 + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
-    static bool opted[64] = {};      // per device; the attribute calls cost microseconds on the launch path
+// dynamic shared memory starts right after the kernel's static part; only the gap up to the next 1024-byte boundary is
+// needed as alignment slack (static barriers + published thresholds + the carve-up fill the 227 KB of an SM to the byte)
+template <class Kernel>
+static int tc_dynamic_smem(Kernel kernel, size_t* smem_dev, size_t* smem_out) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !opted[dev]) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_pair_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) opted[dev] = true;
+    size_t smem = (dev >= 0 && dev < 64) ? smem_dev[dev] : 0;
+    if (smem == 0) {     // per device; the attribute calls cost microseconds on the launch path
+        cudaFuncAttributes fa;
+        CRW_CUDA_RET(cudaFuncGetAttributes(&fa, kernel));
+        const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
+        smem = slack + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
+        CRW_CUDA_RET(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) smem_dev[dev] = smem;
     }
+    *smem_out = smem;
+    return CRW_OK;
+}
+
+template <int KT>
+static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
+    static size_t smem_dev[64] = {};
+    size_t smem = 0;
+    const int rc = tc_dynamic_smem(lp_topk_pair_kernel<KT>, smem_dev, &smem);
+    if (rc != CRW_OK) return rc;
     const int items = p.v_end - p.v_begin;
     int clusters = max_ctas / 2 < 1 ? 1 : max_ctas / 2;
     if (items < clusters) clusters = items;
@@ -749,27 +866,21 @@ static int launch_pair(const CUtensorMap* maps, const TcParams& p, int max_ctas,
     return CRW_OK;
 }
 
-template <int KT, int NEPI>
+template <int KT, int NEPI, bool TS>
 static int launch_tc(const CUtensorMap* maps, const TcParams& p, int max_ctas, cudaStream_t st) {
-    // dynamic shared memory starts right after the kernel's static part; only the gap up to the next 1024-byte boundary
-    // is needed as alignment slack (with 16 epilogue warps the kernel fills the 227 KB of an SM to the byte)
-    static size_t smem_dev[64] = {};  // per device; the attribute calls cost microseconds on the launch path
-    int dev = 0;
-    cudaGetDevice(&dev);
-    size_t smem = (dev >= 0 && dev < 64) ? smem_dev[dev] : 0;
-    if (smem == 0) {
-        cudaFuncAttributes fa;
-        CRW_CUDA_RET(cudaFuncGetAttributes(&fa, lp_topk_tc_kernel<KT, NEPI>));
-        const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
-        smem = slack + (size_t)kQBytes + (size_t)kStages * kKBytes + (size_t)kParkBytes;
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_tc_kernel<KT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) smem_dev[dev] = smem;
-    }
+    static size_t smem_dev[64] = {};
+    size_t smem = 0;
+    const int rc = tc_dynamic_smem(lp_topk_tc_kernel<KT, NEPI, TS>, smem_dev, &smem);
+    if (rc != CRW_OK) return rc;
     const int items = p.v_end - p.v_begin;
     const int grid = items < max_ctas ? items : max_ctas;
-    lp_topk_tc_kernel<KT, NEPI><<<grid, (NEPI + 2) * 32, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    lp_topk_tc_kernel<KT, NEPI, TS><<<grid, (NEPI + 2) * 32, smem, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     CRW_LAUNCH_RET();
     return CRW_OK;
+}
+template <int KT>
+static int launch_tc_any(const CUtensorMap* maps, const TcParams& p, int ts, int max_ctas, cudaStream_t st) {
+    return ts ? launch_tc<KT, 8, true>(maps, p, max_ctas, st) : launch_tc<KT, 8, false>(maps, p, max_ctas, st);
 }
 
 // Host side of the tensor path, in two steps so that crw_labelprop_forward can overlap the sequential label gather with
@@ -791,7 +902,9 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     TcParams& p = plan->p;
     p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
     p.total_tiles = 0; p.v_begin = p.v_end = 0; p.tiles_per_rg = 0; p.early_per_rg = 0;
+    p.hi = hi; p.lo = lo; p.total_rows = rows;
     plan->pair = 0;
+    plan->ts = 0;
     if (T < 2) return CRW_OK;
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(plan->maps);
     int rc = make_tmap_bf16_k64(&maps[0], hi, (uint64_t)rows, 128, kBM);
@@ -809,6 +922,7 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     // off), but at BASELINE config 3 the selection epilogue bounds both kernels and the pair form pays more per-tile
     // overhead there (profiles/r01_lp_pair_anatomy.txt): opt-in until the epilogue is the smaller half.
     { const char* e = getenv("CRW_LP_PAIR"); plan->pair = (e && atoi(e) != 0) ? 1 : 0; }
+    { const char* e = getenv("CRW_LP_TS"); plan->ts = (e && atoi(e) != 0 && !plan->pair) ? 1 : 0; }
     const int tile_rows = plan->pair ? kPairM : kBM;
     p.tiles_per_rg = ceil_div(T * N, tile_rows);
     p.total_tiles = R * p.tiles_per_rg;
@@ -831,11 +945,11 @@ int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas,
         if (k <= 20) return launch_pair<20>(maps, p, max_ctas, st);
         return launch_pair<32>(maps, p, max_ctas, st);
     }
-    // (a 16-epilogue-warp instantiation, launch_tc<10, 16>, is supported by the kernel but measured slower: 196 vs 125 us)
-    if (k <= 10) return launch_tc<10, 8>(maps, p, max_ctas, st);
-    if (k <= 16) return launch_tc<16, 8>(maps, p, max_ctas, st);
-    if (k <= 20) return launch_tc<20, 8>(maps, p, max_ctas, st);
-    return launch_tc<32, 8>(maps, p, max_ctas, st);
+    // (a 16-epilogue-warp instantiation, launch_tc<10, 16, false>, is supported by the kernel but measured slower: 196 vs 125 us)
+    if (k <= 10) return launch_tc_any<10>(maps, p, plan.ts, max_ctas, st);
+    if (k <= 16) return launch_tc_any<16>(maps, p, plan.ts, max_ctas, st);
+    if (k <= 20) return launch_tc_any<20>(maps, p, plan.ts, max_ctas, st);
+    return launch_tc_any<32>(maps, p, plan.ts, max_ctas, st);
 }
 // prep of `nrows` rows whose fp32 source sits in a staging buffer: writes hi / lo rows [row_begin, row_begin + nrows)
 int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_t total_rows, int do_normalize, void* scratch,

@@ -100,10 +100,12 @@ def _dev(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
 
 
-@pytest.fixture(params=["single", "pair"])
+@pytest.fixture(params=["single", "pair", "ts"])
 def lp_kernel(request, monkeypatch):
-    """Both tensor-path kernels: the single-CTA one (default) and the CTA-pair one (cta_group::2, env CRW_LP_PAIR=1)."""
+    """The tensor-path kernels: single-CTA with the query tile in shared memory ("SS" MMAs), the CTA-pair one (cta_group::2,
+    env CRW_LP_PAIR=1) and single-CTA with the query tile in tensor memory ("TS" MMAs, env CRW_LP_TS)."""
     monkeypatch.setenv("CRW_LP_PAIR", "1" if request.param == "pair" else "0")
+    monkeypatch.setenv("CRW_LP_TS", "1" if request.param == "ts" else "0")
     return request.param
 
 
