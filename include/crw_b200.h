@@ -212,7 +212,7 @@ int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a
  * 32..256.  Pins the pair plumbing (leader-credited TMA, M=256 MMA, multicast commit) of the label-propagation kernel. */
 int crw_debug_umma_pair_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 /* Profiling aid for the tensor-path top-k kernel: with env CRW_TC_DEBUG bit 3 set the epilogue warps accumulate cycles per
- * phase; this copies the 160 x 8 x 6 uint64 counters to HOST memory (synchronising) and clears them when `reset`. */
+ * phase; this copies the 160 x 8 x 10 uint64 counters to HOST memory (synchronising) and clears them when `reset`. */
 int crw_debug_lp_profile(unsigned long long* host_out, int reset);
 
 #ifdef __cplusplus

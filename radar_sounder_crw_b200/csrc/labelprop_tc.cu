@@ -122,47 +122,39 @@ __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t,
 // profiling aid (CRW_TC_DEBUG bit 3): cycles each epilogue warp spends per phase, summed over the launch
 //   [0] waiting for an accumulator  [1] tcgen05.ld + park + threshold mask  [2] validity mask  [3] insertion loop
 //   [4] merge + finish + stores     [5] insertion-loop iterations (count, not cycles)
-__device__ unsigned long long g_lp_prof[160 * 8 * 6];
+//   inside [4]: [6] wait for the partner list (first barrier)  [7] list hand-over + merge  [8] finish (softmax, stores)
+//               [9] last barrier (scratch free)
+__device__ unsigned long long g_lp_prof[160 * 8 * 10];
+
+// Sorted insert of (x, xid) into a descending list, one inline-PTX block per list length (generated, see
+// tools/gen_toplist_insert.py): predicated FFMA moves on the FMA pipe instead of SEL / FSEL on the ALU pipe.
+template <int KT>
+__device__ __forceinline__ void toplist_insert_fma(float (&v)[KT], float (&idf)[KT], float x, float xid);
+template <int KT>
+__device__ __forceinline__ void toplist_insert_tie_fma(float (&v)[KT], float (&idf)[KT], float x, float xid);
+#include "toplist_insert.inc"
+
+constexpr float kIdNone = 16777216.0f;      // ids (key rows) travel as floats: exact below 2^24 (checked by lp_tc_prepare)
+constexpr float kNoValue = -3.402823466e+38f;   // empty list slot: finite (the insert multiplies slots by 0), below every dot product
 
 template <int KT>
 struct TopList {
     float v[KT];
-    int id[KT];
+    float idf[KT];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int s = 0; s < KT; ++s) { v[s] = -INFINITY; id[s] = 0x7fffffff; }
+        for (int s = 0; s < KT; ++s) { v[s] = kNoValue; idf[s] = kIdNone; }
     }
     // insert keeping (value desc); a later candidate never displaces an equal value
-    __device__ __forceinline__ void insert(float x, int xid) {
-        bool g[KT];
-#pragma unroll
-        for (int s = 0; s < KT; ++s) g[s] = x > v[s];
-#pragma unroll
-        for (int s = KT - 1; s > 0; --s) {
-            v[s] = g[s - 1] ? v[s - 1] : (g[s] ? x : v[s]);
-            id[s] = g[s - 1] ? id[s - 1] : (g[s] ? xid : id[s]);
-        }
-        v[0] = g[0] ? x : v[0];
-        id[0] = g[0] ? xid : id[0];
-    }
+    __device__ __forceinline__ void insert(float x, float xid) { toplist_insert_fma<KT>(v, idf, x, xid); }
     // full comparator (value desc, id asc) for merging lists whose ids interleave
-    __device__ __forceinline__ void insert_tie(float x, int xid) {
-        bool g[KT];
-#pragma unroll
-        for (int s = 0; s < KT; ++s) g[s] = (x > v[s]) || (x == v[s] && xid < id[s]);
-#pragma unroll
-        for (int s = KT - 1; s > 0; --s) {
-            v[s] = g[s - 1] ? v[s - 1] : (g[s] ? x : v[s]);
-            id[s] = g[s - 1] ? id[s - 1] : (g[s] ? xid : id[s]);
-        }
-        v[0] = g[0] ? x : v[0];
-        id[0] = g[0] ? xid : id[0];
-    }
+    __device__ __forceinline__ void insert_tie(float x, float xid) { toplist_insert_tie_fma<KT>(v, idf, x, xid); }
 };
 
 // Branch-free pop of the lowest set bit of the candidate mask (c1:c0) and fetch of that column from the lane's park
 // slots.  Returns false (x = -inf, a no-op for insert()) when the mask is empty; the fetch then reads slot 31, in range.
-__device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32_t park, int row0, float& x, int& xid) {
+// The id comes out as a float: (2^23 + i) + (row0 - 2^23), both terms and the sum exact.
+__device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32_t park, float row0_bias, float& x, float& xid) {
     const bool any = (c0 | c1) != 0u, in_lo = c0 != 0u;
     const uint32_t w = in_lo ? c0 : c1, nw = w & (w - 1u);
     const int i = (__ffs(w) - 1 + (in_lo ? 0 : 32)) & 63;
@@ -170,18 +162,11 @@ __device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32
     c1 = in_lo ? c1 : nw;
     const float v = tc::lds_f32(park + i * 128);
     x = any ? v : -INFINITY;
-    xid = row0 + i;
+    xid = __int_as_float(0x4B000000 | i) + row0_bias;
     return any;
 }
+__device__ __forceinline__ float row_bias(int row0) { return (float)row0 - 8388608.0f; }
 
-// Filter threshold of one partial list.  The lists of the other parts of the same query (same lane, warps 4 apart) cover
-// disjoint key columns, so lower bounds on the query's final k-th best follow from what they publish:
-//   (1) a partner's own k-th best (its list alone already holds k values that large);
-//   (2) with two parts, min(own[h-1], partner[h-1]) for h = ceil(KT / 2): the two lists together hold 2h >= k values at least
-//       that large.  For similar halves this is close to the k-th best of everything seen so far, where (1) is only the
-//       2k-th best -- it is what keeps the number of inserted candidates near k (1 + ln(n / k)) although the query has two lists.
-// A candidate strictly below a bound cannot survive the merge.  Equal values may still win the merge on the id tie rule,
-// hence the bounds are taken one ulp down and the comparison stays strict.  Stale (smaller) published values are safe.
 // a value strictly below x (within a few ulp); -inf stays -inf.  (nextafterf() is a ~20-instruction sequence.)
 __device__ __forceinline__ float strictly_below(float x) { return __fmaf_rn(-fabsf(x), 2.384185791015625e-07f, x) - 1.17549435e-38f; }
 
@@ -206,18 +191,19 @@ template <int KT>
 __device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& top, int rg, int n, int q, int win_lo) {
     const int N = p.N, ctx = p.ctx, k = p.k, rb = p.rb;
     // key row -> candidate id (slot in the trimmed key set * N + node)
+    int id[KT];
 #pragma unroll
     for (int s = 0; s < KT; ++s) {
-        const int kr = top.id[s];
+        const int kr = (int)top.idf[s];
         const int kf = (int)__umulhi((unsigned)kr, p.magic_n), j = kr - kf * N;
         const int slot = (n > ctx + 1 && kf != 0) ? kf - win_lo + 1 : kf;
-        top.id[s] = slot * N + j;
+        id[s] = slot * N + j;
     }
     // fewer than k in-band candidates: out-of-band ones share one logit; ascending id (pinned tie rule)
     const int F = n_key_frames(n, ctx);
     int live = 0;
 #pragma unroll
-    for (int s = 0; s < KT; ++s) live += (s < k && top.v[s] > -INFINITY) ? 1 : 0;
+    for (int s = 0; s < KT; ++s) live += (s < k && top.v[s] > kNoValue) ? 1 : 0;
     const float masked = kMaskBias;   // raw-dot domain stand-in: exp() of it is exactly 0
     if (live < k) {
         int need = k - live, fill = live;
@@ -227,7 +213,7 @@ __device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& 
                 if (dj <= rb && -dj <= rb) continue;
 #pragma unroll
                 for (int s = 0; s < KT; ++s)
-                    if (s == fill) { top.v[s] = masked; top.id[s] = f * N + jj; }
+                    if (s == fill) { top.v[s] = masked; id[s] = f * N + jj; }
                 ++fill; --need;
             }
     }
@@ -244,7 +230,7 @@ __device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& 
     for (int s = 0; s < KT; ++s)
         if (s < k) {
             p.W[base + (size_t)s * N] = e[s] * inv;
-            p.I[base + (size_t)s * N] = top.id[s];
+            p.I[base + (size_t)s * N] = id[s];
         }
 }
 
@@ -519,14 +505,16 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 int iters = 0;
                 {
                     // software-pipelined: the next candidate is popped and fetched while the current one is inserted
-                    float x; int xid;
-                    bool have = pop_candidate(c0, c1, park, row0, x, xid);
-                    while (have) {
-                        float xn; int xidn;
-                        const bool have_n = pop_candidate(c0, c1, park, row0, xn, xidn);
+                    const float rbias = row_bias(row0);
+                    float x, xid;
+                    bool have = pop_candidate(c0, c1, park, rbias, x, xid);
+                    while (have) {                   // two candidates per trip: no register rotation between trips
+                        float xn, xidn;
+                        pop_candidate(c0, c1, park, rbias, xn, xidn);
                         top.insert(x, xid);
-                        x = xn; xid = xidn; have = have_n;
-                        if (prof) ++iters;
+                        have = pop_candidate(c0, c1, park, rbias, x, xid);
+                        top.insert(xn, xidn);        // x = -inf (mask empty): a no-op
+                        if (prof) iters += 2;
                     }
                 }
                 thr_pub[warp * 32 + lane] = top.v[KT - 1];
@@ -540,37 +528,52 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     const long long c_4 = clock64();
                     iters = __reduce_max_sync(0xffffffffu, iters);
                     if (lane == 0) {
-                        unsigned long long* g = g_lp_prof + ((size_t)blockIdx.x * 8 + warp) * 6;
+                        unsigned long long* g = g_lp_prof + ((size_t)blockIdx.x * 8 + warp) * 10;
                         g[0] += c_1 - c_0; g[1] += c_2 - c_1; g[2] += c_3 - c_2; g[3] += c_4 - c_3; g[5] += iters;
                     }
                 }
             }
             // ---- merge the kParts lists of every query (warps part>0 -> smem -> warp part 0) ----
-            const long long c_m = (p.debug & 8) ? clock64() : 0;
+            const bool profm = (p.debug & 8) != 0;
+            const long long c_m = profm ? clock64() : 0;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // every epilogue warp is done with its park buffer
+            const long long c_m1 = profm ? clock64() : 0;
             float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
-            int* mi = reinterpret_cast<int*>(mv + KT * 32);
+            float* mi = mv + KT * 32;
             static_assert(KT * 32 * 8 <= kParkWarp, "merge scratch must fit the warp's park buffer");
             if (part != 0) {
 #pragma unroll
-                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
+                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.idf[s]; }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
+            long long c_m2 = c_m1;
             if (part == 0) {
                 for (int pp = 1; pp < kParts; ++pp) {
                     const float* pv = reinterpret_cast<const float*>(park_base + (pp * 4 + g) * kParkWarp);
-                    const int* pi = reinterpret_cast<const int*>(pv + KT * 32);
+                    const float* pi = pv + KT * 32;
+                    // (an empty slot, kNoValue / kIdNone, is a no-op for the comparator; lists are sorted, so once no lane's
+                    // entry reaches its current k-th best the rest cannot either)
+#pragma unroll 2
                     for (int s = 0; s < KT; ++s) {
                         const float x = pv[s * 32 + lane];
-                        if (x > -INFINITY) top.insert_tie(x, pi[s * 32 + lane]);
+                        if (!__any_sync(0xffffffffu, x >= top.v[KT - 1])) break;
+                        top.insert_tie(x, pi[s * 32 + lane]);
                     }
                 }
+                c_m2 = profm ? clock64() : 0;
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
+            } else {
+                c_m2 = profm ? clock64() : 0;
             }
+            const long long c_m3 = profm ? clock64() : 0;
             thr_pub[warp * 32 + lane] = -INFINITY;
             mid_pub[warp * 32 + lane] = -INFINITY;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // scratch free for the next tile
-            if ((p.debug & 8) && lane == 0) g_lp_prof[((size_t)blockIdx.x * 8 + warp) * 6 + 4] += clock64() - c_m;
+            if (profm && lane == 0) {
+                unsigned long long* gp = g_lp_prof + ((size_t)blockIdx.x * 8 + warp) * 10;
+                const long long c_e = clock64();
+                gp[4] += c_e - c_m; gp[6] += c_m1 - c_m; gp[7] += c_m2 - c_m1; gp[8] += c_m3 - c_m2; gp[9] += c_e - c_m3;
+            }
         }
     }
     tc::tc_fence_before();
@@ -789,13 +792,15 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                     uint32_t c0 = qvalid ? (pm[0] & vm[0]) : 0u, c1 = qvalid ? (pm[1] & vm[1]) : 0u;
                     if (p.debug & 3) { c0 = 0; c1 = 0; }
                     {
-                        float x; int xid;
-                        bool have = pop_candidate(c0, c1, park, row0, x, xid);
-                        while (have) {
-                            float xn; int xidn;
-                            const bool have_n = pop_candidate(c0, c1, park, row0, xn, xidn);
+                        const float rbias = row_bias(row0);
+                        float x, xid;
+                        bool have = pop_candidate(c0, c1, park, rbias, x, xid);
+                        while (have) {                   // two candidates per trip: no register rotation between trips
+                            float xn, xidn;
+                            pop_candidate(c0, c1, park, rbias, xn, xidn);
                             top.insert(x, xid);
-                            x = xn; xid = xidn; have = have_n;
+                            have = pop_candidate(c0, c1, park, rbias, x, xid);
+                            top.insert(xn, xidn);        // x = -inf (mask empty): a no-op
                         }
                     }
                 }
@@ -808,18 +813,20 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
             // ---- merge the two column-half lists of every query (warps 4-7 -> smem -> warps 0-3) ----
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
-            int* mi = reinterpret_cast<int*>(mv + KT * 32);
+            float* mi = mv + KT * 32;
             if (part != 0) {
 #pragma unroll
-                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.id[s]; }
+                for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.idf[s]; }
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             if (part == 0) {
                 const float* pv = reinterpret_cast<const float*>(park_base + (4 + g) * kParkWarp);
-                const int* pi = reinterpret_cast<const int*>(pv + KT * 32);
+                const float* pi = pv + KT * 32;
+#pragma unroll 2
                 for (int s = 0; s < KT; ++s) {
                     const float x = pv[s * 32 + lane];
-                    if (x > -INFINITY) top.insert_tie(x, pi[s * 32 + lane]);
+                    if (!__any_sync(0xffffffffu, x >= top.v[KT - 1])) break;
+                    top.insert_tie(x, pi[s * 32 + lane]);
                 }
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             }
@@ -916,6 +923,7 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     p.rb = (rc_ - 1.0f >= (float)N) ? N : (int)rc_ - 1;
     p.inv_temp = 1.0f / temp;
     if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
+    if ((uint64_t)T * N >= (1ull << 24)) return CRW_ERR_UNSUPPORTED;       // key rows travel as floats inside the top-k lists
     p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     // The CTA-pair kernel is correct (tests run it) and has the cheaper MMA side (68 vs 78 us with the selection switched
@@ -993,5 +1001,5 @@ int lp_profile_read(unsigned long long* host_out, int reset) {
 
 }  // namespace crw
 
-// profiling aid: copies the per-warp phase counters (160 x 8 x 6 uint64) to host memory and optionally clears them
+// profiling aid: copies the per-warp phase counters (160 x 8 x 10 uint64) to host memory and optionally clears them
 extern "C" int crw_debug_lp_profile(unsigned long long* host_out, int reset) { return crw::lp_profile_read(host_out, reset); }

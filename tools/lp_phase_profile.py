@@ -16,18 +16,19 @@ mask0 = torch.nn.functional.one_hot(torch.randint(0, M, (1, N), device="cuda"), 
 os.environ["CRW_LP_PAIR"] = "0"
 os.environ["CRW_TC_DEBUG"] = "8"
 L = crw._lib.lib()
-buf = np.zeros(160 * 8 * 6, dtype=np.uint64)
+buf = np.zeros(160 * 8 * 10, dtype=np.uint64)
 crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, crw.ops.PREC_BF16X3, True, False)
 torch.cuda.synchronize()
 L.crw_debug_lp_profile(None, 1)
 crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, crw.ops.PREC_BF16X3, True, False)
 torch.cuda.synchronize()
 L.crw_debug_lp_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
-p = buf.reshape(160, 8, 6).astype(np.float64)[:148]
-names = ["wait acc_full", "ld+park+mask", "validity", "insert loop", "merge+finish", "iterations"]
+p = buf.reshape(160, 8, 10).astype(np.float64)[:148]
+names = ["wait acc_full", "ld+park+mask", "validity", "insert loop", "merge+finish", "iterations",
+         "  m: partner", "  m: merge", "  m: finish", "  m: last bar"]
 print("per-warp totals over the launch (cycles; mean / max over the 148 x 8 epilogue warps):")
 for i, nm in enumerate(names):
-    print(f"  {nm:14s} mean {p[:, :, i].mean():10.0f}   max {p[:, :, i].max():10.0f}")
+    print(f"  {nm:14s} mean {p[:, :, i].mean():10.0f}   max {p[:, :, i].max():10.0f}   part0 {p[:, :4, i].mean():10.0f}   part1 {p[:, 4:, i].mean():10.0f}")
 tot = p[:, :, :5].sum(2)
 print(f"  sum of phases  mean {tot.mean():10.0f}   max {tot.max():10.0f}   (1 us = ~1965 cycles)")
 print("  part 0 vs part 1 insert-loop cycles:", p[:, :4, 3].mean(), p[:, 4:, 3].mean())
