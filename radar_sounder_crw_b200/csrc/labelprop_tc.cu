@@ -167,6 +167,49 @@ __device__ __forceinline__ bool pop_candidate(uint32_t& c0, uint32_t& c1, uint32
 }
 __device__ __forceinline__ float row_bias(int row0) { return (float)row0 - 8388608.0f; }
 
+// acc += 2^(i & 15) when v > thr: the "beats the threshold" bitmask of 32 parked values is collected as two exact float sums of
+// distinct powers of two (16 bits each) with predicated FADDs on the FMA pipe -- the SEL + IADD3 form of `mask |= p << i`
+// sits on the ALU pipe, which the selection epilogue saturates.
+template <int I>
+__device__ __forceinline__ void mask_acc(float& acc, float v, float thr) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.f32 %0, %0, %3;\n\t}" : "+f"(acc) : "f"(v), "f"(thr), "f"((float)(1u << (I & 15))));
+}
+__device__ __forceinline__ uint32_t mask_from_acc(float lo16, float hi16) {
+    return (uint32_t)__float2int_rz(lo16) | ((uint32_t)__float2int_rz(hi16) << 16);
+}
+template <int I>
+struct ParkLoop {
+    static __device__ __forceinline__ void run(const float (&v)[32], uint32_t park_ch, float thr, float& a0, float& a1) {
+        tc::sts_f32(park_ch + I * 128, v[I]);
+        if (I < 16) mask_acc<I>(a0, v[I], thr); else mask_acc<I>(a1, v[I], thr);
+        ParkLoop<I + 1>::run(v, park_ch, thr, a0, a1);
+    }
+};
+template <>
+struct ParkLoop<32> {
+    static __device__ __forceinline__ void run(const float (&)[32], uint32_t, float, float&, float&) {}
+};
+
+// Validity mask of one thread over the (<= 64) key rows [row0, row0 + nrows) of a key tile: bit c is set when key row row0 + c
+// lies in an allowed key frame (kf < n and kf == 0 or kf >= win_lo) and inside the radius band |node - q| <= rb.
+// The band of the thread's query node is one run of bits (mq, first node lo_q); per key frame it is shifted to where that
+// frame starts in the tile -- bits that leave the 64-bit word are exactly the nodes outside the tile.  Needs 2 rb + 1 <= 64.
+__device__ __forceinline__ void band_mask(int row0, int nrows, int N, unsigned magic_n, int n, int win_lo, int lo_q,
+                                          unsigned long long mq, uint32_t (&vm)[2]) {
+    if (nrows <= 0) return;
+    const int kf0 = (int)__umulhi((unsigned)row0, magic_n);
+    unsigned long long m = 0ull;
+    int kf = kf0;
+    for (int o = kf0 * N - row0; o < nrows; o += N, ++kf) {          // warp-uniform trip count; o = tile column of node 0
+        const int sh = o + lo_q;
+        const unsigned long long seg = (sh >= 0) ? ((sh < 64) ? (mq << sh) : 0ull) : ((sh > -64) ? (mq >> (-sh)) : 0ull);
+        m |= ((kf < n) && (kf == 0 || kf >= win_lo)) ? seg : 0ull;
+    }
+    if (nrows < 64) m &= (1ull << nrows) - 1ull;
+    vm[0] = (uint32_t)m;
+    vm[1] = (uint32_t)(m >> 32);
+}
+
 // a value strictly below x (within a few ulp); -inf stays -inf.  (nextafterf() is a ~20-instruction sequence.)
 __device__ __forceinline__ float strictly_below(float x) { return __fmaf_rn(-fabsf(x), 2.384185791015625e-07f, x) - 1.17549435e-38f; }
 
@@ -353,6 +396,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     if (!(p.debug & 4))
 #pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
+                        if ((p.debug & 128) && pass) break;      // timing aid: hi.hi pass only (results invalid)
                         const int qpart = (pass == 2) ? 2 : 0, kpart = (pass == 1) ? 2 : 0;
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb)
@@ -390,6 +434,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
         uint32_t kcnt = 0, tcnt = 0;
+        bool scratch_pending = false;     // part 1: part 0 may still be reading last tile's list out of this warp's park buffer
         // TS: copy this thread's row of the hi (part 0) / lo (part 1) plane of query tile `tl` into query buffer `buf`
         auto stage_query = [&](int tl, uint32_t buf) {
             const TileInfo tq = tile_info(p, tl);
@@ -434,12 +479,16 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             const int n = row / N, q = row - n * N;
             const bool qvalid = (n >= 1) && (n < p.T);
             const int win_lo = (n > ctx + 1) ? n - ctx : 1;     // non-zero key frames allowed: [win_lo, n)
+            const int lo_q = max(0, q - rb), w_q = min(N - 1, q + rb) - lo_q + 1;
+            const unsigned long long mq = (w_q >= 64) ? ~0ull : ((1ull << w_q) - 1ull);   // the band of this query node
+            const bool wide_band = 2 * rb + 1 > 64;             // (warp-uniform) band wider than a key tile: generic loop
             TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
                 // key tiles are dealt round-robin to the tile groups; the group that also merges and finishes the query (part 0)
-                // takes the later residue, i.e. the smaller share when the count does not divide
-                if ((kt % kTileGroups) != (((p.debug & 64) ? 0 : kTileGroups - 1) ^ (part / kColSplit)) % kTileGroups) continue;
+                // takes the later residue, i.e. the smaller share when the count does not divide.  (Giving part 1 a few key
+                // tiles more, to fill the time part 0 spends merging, measured slower: 114.0 / 114.6 / 115.3 / 116.8 us for 0-3.)
+                if ((kt % kTileGroups) != kTileGroups - 1 - part / kColSplit) continue;
                 const int a = kcnt % kNAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
@@ -470,19 +519,23 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
                     }
+                    if (scratch_pending) {          // (part 1 only, warp-uniform) once per query tile
+                        asm volatile("bar.sync %0, %1;" ::"r"(5 + g), "n"(64) : "memory");
+                        scratch_pending = false;
+                    }
 #pragma unroll
                     for (int ch = 0; ch < kCh; ++ch)
                         if (ch * 32 < nrows && !(p.debug & 2)) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                tc::sts_f32(park + (ch * 32 + i) * 128, v[ch][i]);
-                                pm[ch] |= (v[ch][i] > thr) ? (1u << i) : 0u;
-                            }
+                            float a0 = 0.0f, a1 = 0.0f;
+                            ParkLoop<0>::run(v[ch], park + ch * 32 * 128, thr, a0, a1);
+                            pm[ch] = mask_from_acc(a0, a1);
                         }
                 }
                 long long c_2 = prof ? clock64() : 0;
                 // validity mask of this thread over the tile's key rows (segments = key frames)
-                {
+                if (!wide_band) {
+                    band_mask(row0, nrows, N, p.magic_n, n, win_lo, lo_q, mq, vm);
+                } else {
                     const int kf0 = (int)__umulhi((unsigned)row0, p.magic_n);
                     int c = 0, kf = kf0, j = row0 - kf0 * N;
                     while (c < nrows) {                           // warp-uniform trip count
@@ -534,8 +587,15 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
             }
             // ---- merge the kParts lists of every query (warps part>0 -> smem -> warp part 0) ----
+            // Two parts: part 1 hands its list over and goes on to the next query tile at once; part 0 tells it through a second
+            // named barrier (arrive / sync) when the list has been read, which part 1 only needs before it parks values again.
+            constexpr bool kRunAhead = (kParts == 2);
             const bool profm = (p.debug & 8) != 0;
             const long long c_m = profm ? clock64() : 0;
+            if (kRunAhead && scratch_pending) {       // a query tile without key tiles for this part: settle the hand-shake now
+                asm volatile("bar.sync %0, %1;" ::"r"(5 + g), "n"(64) : "memory");
+                scratch_pending = false;
+            }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // every epilogue warp is done with its park buffer
             const long long c_m1 = profm ? clock64() : 0;
             float* mv = reinterpret_cast<float*>(park_base + warp * kParkWarp);
@@ -545,6 +605,9 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
 #pragma unroll
                 for (int s = 0; s < KT; ++s) { mv[s * 32 + lane] = top.v[s]; mi[s * 32 + lane] = top.idf[s]; }
             }
+            // published bounds belong to this query tile: cleared before anyone can start the next one
+            thr_pub[warp * 32 + lane] = -INFINITY;
+            mid_pub[warp * 32 + lane] = -INFINITY;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");
             long long c_m2 = c_m1;
             if (part == 0) {
@@ -560,21 +623,22 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         top.insert_tie(x, pi[s * 32 + lane]);
                     }
                 }
+                if (kRunAhead) asm volatile("bar.arrive %0, %1;" ::"r"(5 + g), "n"(64) : "memory");   // part 1's buffer is free again
                 c_m2 = profm ? clock64() : 0;
                 if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             } else {
+                if (kRunAhead) scratch_pending = true;
                 c_m2 = profm ? clock64() : 0;
             }
             const long long c_m3 = profm ? clock64() : 0;
-            thr_pub[warp * 32 + lane] = -INFINITY;
-            mid_pub[warp * 32 + lane] = -INFINITY;
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // scratch free for the next tile
+            if (!kRunAhead) asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"((NEPI / 4) * 32) : "memory");   // scratch free for the next tile
             if (profm && lane == 0) {
                 unsigned long long* gp = g_lp_prof + ((size_t)blockIdx.x * 8 + warp) * 10;
                 const long long c_e = clock64();
                 gp[4] += c_e - c_m; gp[6] += c_m1 - c_m; gp[7] += c_m2 - c_m1; gp[8] += c_m3 - c_m2; gp[9] += c_e - c_m3;
             }
         }
+        if (scratch_pending) asm volatile("bar.sync %0, %1;" ::"r"(5 + g), "n"(64) : "memory");   // leave no barrier half-armed
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -746,6 +810,9 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
             const int n = row / N, q = row - n * N;
             const bool qvalid = (n >= 1) && (n < p.T);
             const int win_lo = (n > ctx + 1) ? n - ctx : 1;
+            const int lo_q = max(0, q - rb), w_q = min(N - 1, q + rb) - lo_q + 1;
+            const unsigned long long mq = (w_q >= 64) ? ~0ull : ((1ull << w_q) - 1ull);
+            const bool wide_band = 2 * rb + 1 > 64;
             TopList<KT> top;
             top.init();
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
@@ -765,14 +832,14 @@ lp_topk_pair_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_co
                             float v[32];
                             tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(a * kPairN + part * kBN + ch * 32), v);
                             tc::tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                tc::sts_f32(park + (ch * 32 + i) * 128, v[i]);
-                                pm[ch] |= (v[i] > thr) ? (1u << i) : 0u;
-                            }
+                            float a0 = 0.0f, a1 = 0.0f;
+                            ParkLoop<0>::run(v, park + ch * 32 * 128, thr, a0, a1);
+                            pm[ch] = mask_from_acc(a0, a1);
                         }
                     }
-                    {
+                    if (!wide_band) {
+                        band_mask(row0, nrows, N, p.magic_n, n, win_lo, lo_q, mq, vm);
+                    } else {
                         const int kf0 = (int)__umulhi((unsigned)row0, p.magic_n);
                         int c = 0, kf = kf0, j = row0 - kf0 * N;
                         while (c < nrows) {
