@@ -33,3 +33,12 @@ tot = p[:, :, :5].sum(2)
 print(f"  sum of phases  mean {tot.mean():10.0f}   max {tot.max():10.0f}   (1 us = ~1965 cycles)")
 print("  part 0 vs part 1 insert-loop cycles:", p[:, :4, 3].mean(), p[:, 4:, 3].mean())
 print("  cycles per insertion-loop iteration:", p[:, :, 3].sum() / max(p[:, :, 5].sum(), 1))
+# load balance: per-CTA totals (slowest warp of the CTA bounds it), 4-tile vs 3-tile CTAs of the bulk launch (grid 139, 470 tiles)
+cta_max = tot.max(1)
+cta_mean = tot.mean(1)
+n4 = 470 - 3 * 139
+print(f"  CTAs with 4 tiles (0..{n4 - 1}): slowest warp mean {cta_max[9:n4].mean():9.0f}  warp mean {cta_mean[9:n4].mean():9.0f}")
+print(f"  CTAs with 3 tiles ({n4}..138): slowest warp mean {cta_max[n4:139].mean():9.0f}  warp mean {cta_mean[n4:139].mean():9.0f}")
+print(f"  slowest CTA {cta_max[:139].max():9.0f}; within-CTA (slowest warp / mean warp) {np.mean(cta_max[9:139] / cta_mean[9:139]):.3f}")
+by_g = tot[9:139].reshape(-1, 2, 4)          # [cta, part, quadrant]
+print("  mean by quadrant (part 0):", np.round(by_g[:, 0, :].mean(0)), " (part 1):", np.round(by_g[:, 1, :].mean(0)))
