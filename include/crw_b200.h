@@ -205,6 +205,9 @@ int crw_fuse_reversed(const float* fwd, const float* rev, int H, int64_t W, int 
 int crw_debug_umma_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 /* same product with A parked in TMEM by the threads (tcgen05.st) and read by the "TS" form of tcgen05.mma */
 int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
+/* same product with A brought in by TMA and copied shared memory -> TMEM by tcgen05.cp (128x256b per K = 16 step), then read
+ * by TS MMAs; BN multiple of 32, 32..256.  Pins the smem -> TMEM copy against the A-in-TMEM layout. */
+int crw_debug_umma_tscp_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream);
 /* K = 64 product with MN-major operands: A is At[64][128] when a_mn else A[128][64]; B is Bkn[64][BN] when b_mn else
  * Bt[BN][64]; BN in {64, 128}.  Pins the MN-major shared-memory descriptors (transposed operands without a copy). */
 int crw_debug_umma_mn_gemm(const void* A_bf16, const void* B_bf16, int BN, int a_mn, int b_mn, float* out, void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "crw_fuse_reversed": (_c_int, [_vp, _vp, _c_int, _c_i64, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
     "crw_debug_umma_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_umma_ts_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
+    "crw_debug_umma_tscp_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_umma_mn_gemm": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_debug_umma_pair_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_lp_profile": (_c_int, [_vp, _c_int]),

@@ -166,6 +166,12 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// shared memory -> TMEM, issued by ONE thread, asynchronous and ordered with the tcgen05.mma issued around it: 128 rows x 32 bytes
+// of the operand tile the descriptor points at (same descriptor as the K = 16 step of an SS MMA) land in lanes 0..127,
+// 8 consecutive 32-bit columns from taddr's column -- exactly the A-in-TMEM layout of the TS form
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

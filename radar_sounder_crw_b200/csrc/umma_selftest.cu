@@ -171,6 +171,60 @@ umma_ts_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __grid_consta
     if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
+// Same GEMM with A brought in by TMA (SWIZZLE_128B K-major tile, as the SS form reads it) and then copied into TMEM by
+// tcgen05.cp (128x256b per K = 16 step), consumed by TS MMAs.  Pins the smem -> TMEM copy against the A-in-TMEM layout.
+__global__ void __launch_bounds__(128, 1)
+umma_tscp_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sA = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));   // [kb 0,1][128][128 B]
+    uint8_t* sB = sA + 2 * 128 * 128;
+    __shared__ uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr uint32_t kACol = 256;
+
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_full, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(&bar_full, (uint32_t)(2 * 128 * 128 + BN * 256));
+        for (int kb = 0; kb < 2; ++kb) tc::tma_load_2d(sA + kb * 128 * 128, &mapA, kb * 64, 0, &bar_full);
+        for (int kb = 0; kb < 2; ++kb) tc::tma_load_2d(sB + kb * BN * 128, &mapB, kb * 64, 0, &bar_full);
+        tc::mbar_wait(&bar_full, 0);
+        tc::tc_fence_after();
+        for (int k8 = 0; k8 < 8; ++k8)
+            tc::tmem_cp_128x256b(tmem_base + kACol + k8 * 8, tc::umma_smem_desc_k128(tc::smem_u32(sA + (k8 >> 2) * 128 * 128) + (k8 & 3) * 32));
+        const uint32_t idesc = tc::umma_idesc_bf16(128, BN);
+        for (int k8 = 0; k8 < 8; ++k8) {
+            const uint64_t bd = tc::umma_smem_desc_k128(tc::smem_u32(sB + (k8 >> 2) * BN * 128) + (k8 & 3) * 32);
+            tc::umma_bf16_ts(tmem_base, tmem_base + kACol + k8 * 8, bd, idesc, k8 ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    tc::mbar_wait(&bar_mma, 0);
+    tc::tc_fence_after();
+    for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        float* o = out + (size_t)(warp * 32 + lane) * BN + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (c + i < BN) o[i] = v[i];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
 // MN-major operands: out[128 x BN] = A * B with A given as At[K=64][128] (M contiguous) when a_mn, else A[128][64];
 // and B given as Bkn[64][BN] (N contiguous) when b_mn, else Bt[BN][64].  Pins the MN-major descriptors (LBO / SBO /
 // major bits) so that transposed operands need no second copy.
@@ -336,6 +390,20 @@ extern "C" int crw_debug_umma_ts_gemm(const void* A_bf16, const void* B_bf16, in
     const size_t smem = 1024 + 2 * (size_t)BN * 128;
     CRW_CUDA_RET(cudaFuncSetAttribute(umma_ts_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_ts_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(A_bf16), mB, BN, out);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+extern "C" int crw_debug_umma_tscp_gemm(const void* A_bf16, const void* B_bf16, int BN, float* out, void* stream) {
+    if (!A_bf16 || !B_bf16 || !out || BN < 32 || BN > 256 || (BN % 32)) return CRW_ERR_INVALID;
+    CUtensorMap mA, mB;
+    int rc = make_tmap_bf16_k64(&mA, A_bf16, 128, 128, 128);
+    if (rc != CRW_OK) return rc;
+    rc = make_tmap_bf16_k64(&mB, B_bf16, (uint64_t)BN, 128, (uint32_t)BN);
+    if (rc != CRW_OK) return rc;
+    const size_t smem = 1024 + 2 * 128 * 128 + 2 * (size_t)BN * 128;
+    CRW_CUDA_RET(cudaFuncSetAttribute(umma_tscp_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_tscp_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mA, mB, BN, out);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }

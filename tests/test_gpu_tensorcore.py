@@ -60,6 +60,21 @@ def test_umma_ts_selftest_matches_torch(pkg, BN):
     assert err < 1e-3, err
 
 
+@pytest.mark.parametrize("BN", [32, 64, 256])
+def test_umma_tscp_selftest_matches_torch(pkg, BN):
+    """A operand: TMA -> shared memory -> tcgen05.cp -> TMEM -> TS MMAs: pins the smem -> TMEM copy."""
+    torch.manual_seed(300 + BN)
+    A = torch.randn(128, 128, device="cuda").bfloat16()
+    B = torch.randn(BN, 128, device="cuda").bfloat16()
+    out = torch.full((128, BN), float("nan"), device="cuda")
+    L = pkg._lib.lib()
+    pkg._lib.check(L.crw_debug_umma_tscp_gemm(A.data_ptr(), B.data_ptr(), BN, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "crw_debug_umma_tscp_gemm")
+    torch.cuda.synchronize()
+    err = (out - A.float() @ B.float().t()).abs().max().item()
+    assert err < 1e-3, err
+
+
 @pytest.mark.parametrize("BN", [32, 64, 128, 256])
 def test_umma_pair_selftest_matches_torch(pkg, BN):
     """cta_group::2 on a 2-CTA cluster: M = 256 MMA, leader-credited TMA, multicast commit."""
