@@ -119,6 +119,17 @@ __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t,
     nrows = min(kBN, t.n_hi * p.N - row0);
 }
 
+// next tile of a CTA's static schedule (stride tiles apart) that has work, or -1
+__device__ __forceinline__ int next_tile_with_work(const TcParams& p, int tile, int stride) {
+    for (tile += stride; tile < p.v_end; tile += stride)
+        if (tile_info(p, tile).n_ktiles != 0) return tile;
+    return -1;
+}
+__device__ __forceinline__ int first_tile_with_work(const TcParams& p, int tile, int stride) {
+    if (tile < p.v_end && tile_info(p, tile).n_ktiles != 0) return tile;
+    return next_tile_with_work(p, tile, stride);
+}
+
 // profiling aid (CRW_TC_DEBUG bit 3): cycles each epilogue warp spends per phase, summed over the launch
 //   [0] waiting for an accumulator  [1] tcgen05.ld + park + threshold mask  [2] validity mask  [3] insertion loop
 //   [4] merge + finish + stores     [5] insertion-loop iterations (count, not cycles)
@@ -277,11 +288,12 @@ __device__ __forceinline__ void lp_finish_query(const TcParams& p, TopList<KT>& 
         }
 }
 
-// TS = true: the query tile is the A operand IN TENSOR MEMORY (tcgen05.mma "TS" form).  The epilogue threads (thread = query
-// row = TMEM lane) copy their own row of the hi / lo planes from global memory into one of two 128-column TMEM buffers, one
-// query tile ahead, so an MMA reads only its 2 KB of B from shared memory (64 B/clk) instead of 6 KB (192 B/clk against a
-// 128 B/clk port) and the freed 64 KB hold two more key stages.  TMEM: [0,256) two query buffers (hi 64 | lo 64 columns
-// each), [256,512) four 64-column accumulators.
+// TS = true: the query tile is the A operand IN TENSOR MEMORY (tcgen05.mma "TS" form).  It travels through the key-stage ring:
+// the producer loads each 32 KB plane (hi, lo) of the NEXT query tile into a free stage right after the first key tile of the
+// current one, and the MMA warp, reaching those slots in the same order, copies them into one of two 128-column TMEM buffers
+// with tcgen05.cp (ordered with the MMAs around it) and hands the stage back.  An MMA then reads only its 2 KB of B from shared
+// memory instead of 6 KB, and the 64 KB of the shared-memory query tile hold two more key stages.  TMEM: [0,256) two query
+// buffers (hi 64 | lo 64 columns each), [256,512) four 64-column accumulators.
 template <int KT, int NEPI, bool TS>
 __global__ void __launch_bounds__((NEPI + 2) * 32, 1)
 lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_constant__ CUtensorMap qmap_lo,
@@ -289,7 +301,6 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     constexpr int kProducerWarp = NEPI, kMmaWarp = NEPI + 1;
     constexpr int kParts = NEPI / 4;          // top-k lists per query (merged at the end of a tile)
     constexpr int kParkWarp = kParkBytes / NEPI;
-    static_assert(!TS || NEPI == 8, "the TS form stages the hi plane with part 0 and the lo plane with part 1");
     constexpr int kNStages = TS ? (kQBytes + kStages * kKBytes) / kKBytes : kStages;   // same carve-up size: 5 stages
     constexpr int kNAcc = TS ? 4 : kAcc;
     constexpr uint32_t kAccCol0 = TS ? 256u : 0u;
@@ -319,8 +330,8 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
 
     if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_base_s);
     if (tid == 0) {
-        tc::mbar_init(&q_full[0], TS ? NEPI : 1);
-        tc::mbar_init(&q_full[1], TS ? NEPI : 1);
+        tc::mbar_init(&q_full[0], 1);
+        tc::mbar_init(&q_full[1], 1);
         tc::mbar_init(&q_empty, 1);
         for (int s = 0; s < kNStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
         for (int a = 0; a < kNAcc; ++a) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 4 * kColSplit); }
@@ -328,8 +339,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     }
     if (tid < NEPI * 32) { thr_pub[tid] = -INFINITY; mid_pub[tid] = -INFINITY; }
     if (warp == kProducerWarp && lane == 0) {
-        if (!TS) { tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); }
-        tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
+        tc::prefetch_tmap(&qmap_hi); tc::prefetch_tmap(&qmap_lo); tc::prefetch_tmap(&kmap_hi); tc::prefetch_tmap(&kmap_lo);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -339,11 +349,31 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
     if (warp == kProducerWarp) {
         // ================= TMA producer (whole warp runs the loop; one elected lane issues) =================
         const bool leader = tc::elect_one();
-        uint32_t kcnt = 0, tcnt = 0;
+        uint32_t scnt = 0, tcnt = 0;          // ring slots handed out so far (key tiles and, TS, query planes); tiles done
+        // TS: the two planes of query tile tl, one ring slot each ([kblock 0,1][128 rows][128 B])
+        auto push_query = [&](int tl) {
+            const TileInfo tq = tile_info(p, tl);
+            const int grow_q = tq.rg * p.T * N + tq.r0;
+            for (int plane = 0; plane < 2; ++plane, ++scnt) {
+                const int s = scnt % kNStages;
+                tc::mbar_wait_backoff(&k_empty[s], ((scnt / kNStages) & 1) ^ 1);
+                if (leader) {
+                    tc::mbar_arrive_expect_tx(&k_full[s], kKBytes);
+                    uint8_t* dst = sK + s * kKBytes;
+                    for (int kb = 0; kb < 2; ++kb)
+                        tc::tma_load_2d(dst + kb * (kBM * 128), plane ? &qmap_lo : &qmap_hi, kb * 64, grow_q, &k_full[s]);
+                }
+            }
+        };
+        if (TS) {
+            const int first = first_tile_with_work(p, p.v_begin + blockIdx.x, gridDim.x);
+            if (first >= 0) push_query(first);
+        }
         for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
             const int grow = t.rg * p.T * N;   // first global row of this radargram
+            const int nx = TS ? next_tile_with_work(p, tile, gridDim.x) : -1;
             if (!TS) {
                 tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
                 if (leader) {
@@ -353,11 +383,11 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         tc::tma_load_2d(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64, grow + t.r0, &q_full[0]);
                 }
             }
-            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                const int s = kcnt % kNStages;
+            for (int kt = 0; kt < t.n_ktiles; ++kt) {
+                const int s = scnt % kNStages;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
-                tc::mbar_wait_backoff(&k_empty[s], ((kcnt / kNStages) & 1) ^ 1);
+                tc::mbar_wait_backoff(&k_empty[s], ((scnt / kNStages) & 1) ^ 1);
                 if (leader) {
                     tc::mbar_arrive_expect_tx(&k_full[s], kKBytes);
                     uint8_t* dst = sK + s * kKBytes;
@@ -365,6 +395,8 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     for (int sub = 0; sub < 4; ++sub)
                         tc::tma_load_2d(dst + sub * (kBN * 128), (sub & 2) ? &kmap_lo : &kmap_hi, (sub & 1) * 64, grow + row0, &k_full[s]);
                 }
+                ++scnt;
+                if (TS && kt == 0 && nx >= 0) push_query(nx);
             }
             ++tcnt;
         }
@@ -373,19 +405,37 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const bool leader = tc::elect_one();
         const uint64_t qdesc = tc::umma_smem_desc_k128(tc::smem_u32(sQ));     // descriptor of sub-tile 0, k-step 0
         const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
-        uint32_t kcnt = 0, tcnt = 0;
+        uint32_t kcnt = 0, scnt = 0, tcnt = 0;      // key tiles (-> accumulator), ring slots, tiles
+        // TS: copy the two query planes waiting in the ring into TMEM query buffer buf (8 x 128x256b per plane)
+        auto copy_query = [&](uint32_t buf) {
+            for (int plane = 0; plane < 2; ++plane, ++scnt) {
+                const int s = scnt % kNStages;
+                tc::mbar_wait(&k_full[s], (scnt / kNStages) & 1);
+                tc::tc_fence_after();
+                if (leader) {
+                    const uint64_t sd = kdesc0 + (uint64_t)((s * kKBytes) >> 4);
+                    for (int kb = 0; kb < 2; ++kb)
+                        for (int ks = 0; ks < 4; ++ks)
+                            tc::tmem_cp_128x256b(tmem_base + buf * 128u + (uint32_t)(plane * 64 + kb * 32 + ks * 8),
+                                                 sd + (uint64_t)((kb * (kBM * 128) + ks * 32) >> 4));
+                    tc::umma_commit(&k_empty[s]);
+                }
+                __syncwarp();
+            }
+        };
+        if (TS && first_tile_with_work(p, p.v_begin + blockIdx.x, gridDim.x) >= 0) copy_query(0u);
         for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
-            if (TS) tc::mbar_wait_backoff(&q_full[tcnt & 1], (tcnt >> 1) & 1);
-            else tc::mbar_wait_backoff(&q_full[0], tcnt & 1);
+            const int nx = TS ? next_tile_with_work(p, tile, gridDim.x) : -1;
+            if (!TS) tc::mbar_wait_backoff(&q_full[0], tcnt & 1);
             const uint32_t qtmem = tmem_base + (uint32_t)((tcnt & 1) * 128);      // TS: this tile's query buffer
             for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
-                const int s = kcnt % kNStages, a = kcnt % kNAcc;
+                const int s = scnt % kNStages, a = kcnt % kNAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
                 const int ncols = min(kBN, (nrows + 15) & ~15);
-                tc::mbar_wait(&k_full[s], (kcnt / kNStages) & 1);           // latency critical: no backoff
+                tc::mbar_wait(&k_full[s], (scnt / kNStages) & 1);           // latency critical: no backoff
                 tc::mbar_wait_backoff(&acc_empty[a], ((kcnt / kNAcc) & 1) ^ 1);
                 tc::tc_fence_after();
                 const uint32_t idesc = tc::umma_idesc_bf16(kBM, ncols);
@@ -416,6 +466,8 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     tc::umma_commit(&acc_full[a]);    // accumulator ready for the epilogue
                 }
                 __syncwarp();
+                ++scnt;
+                if (TS && kt == 0 && nx >= 0) copy_query((tcnt + 1) & 1u);   // the next tile's query planes follow in the ring
             }
             if (!TS && leader) tc::umma_commit(&q_empty);    // query tile may be overwritten
             __syncwarp();
@@ -433,48 +485,11 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const int lrow = g * 32 + lane;
         const int rb = p.rb, ctx = p.ctx, k = p.k;
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
-        uint32_t kcnt = 0, tcnt = 0;
+        uint32_t kcnt = 0;
         bool scratch_pending = false;     // part 1: part 0 may still be reading last tile's list out of this warp's park buffer
-        // TS: copy this thread's row of the hi (part 0) / lo (part 1) plane of query tile `tl` into query buffer `buf`
-        auto stage_query = [&](int tl, uint32_t buf) {
-            const TileInfo tq = tile_info(p, tl);
-            const long long grow_q = (long long)tq.rg * p.T * N + tq.r0 + lrow;
-            const uint4* src = reinterpret_cast<const uint4*>((part ? p.lo : p.hi) + grow_q * 128);
-            const bool in_range = grow_q < p.total_rows;
-            uint32_t r[64];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint4 v = in_range ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
-                r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-            }
-            const uint32_t dst = tmem_base + ((uint32_t)(g * 32) << 16) + buf * 128u + (uint32_t)(part * 64);
-            tc::tmem_st_32x32b_x32(dst, r);
-            tc::tmem_st_32x32b_x32(dst + 32u, r + 32);
-            tc::tmem_st_wait();
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&q_full[buf]);
-        };
-        auto next_tile = [&](int tl) {       // next tile of this CTA that has work, or -1
-            for (tl += gridDim.x; tl < p.v_end; tl += gridDim.x)
-                if (tile_info(p, tl).n_ktiles != 0) return tl;
-            return -1;
-        };
-        if (TS) {
-            int first = p.v_begin + blockIdx.x;
-            if (first < p.v_end && tile_info(p, first).n_ktiles == 0) first = next_tile(first);
-            if (first >= 0 && first < p.v_end) stage_query(first, 0u);
-        }
         for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
             const TileInfo t = tile_info(p, tile);
             if (t.n_ktiles == 0) continue;
-            if (TS) {
-                // one tile ahead: the other buffer was read by the previous tile, all of whose accumulators this warp pair has
-                // consumed (MMAs complete in order), so it is free
-                const int nx = next_tile(tile);
-                if (nx >= 0) stage_query(nx, (tcnt + 1) & 1u);
-                ++tcnt;
-            }
             const int row = t.r0 + lrow;
             const int n = row / N, q = row - n * N;
             const bool qvalid = (n >= 1) && (n < p.T);
@@ -997,7 +1012,9 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     // off), but at BASELINE config 3 the selection epilogue bounds both kernels and the pair form pays more per-tile
     // overhead there (profiles/r01_lp_pair_anatomy.txt): opt-in until the epilogue is the smaller half.
     { const char* e = getenv("CRW_LP_PAIR"); plan->pair = (e && atoi(e) != 0) ? 1 : 0; }
-    { const char* e = getenv("CRW_LP_TS"); plan->ts = (e && atoi(e) != 0 && !plan->pair) ? 1 : 0; }
+    // query tile in tensor memory (TS MMAs, staged through the key ring by tcgen05.cp) is the default: MMA + TMA side 82 -> 75 us at
+    // config 3, whole kernel 91.3 -> 89.5 us; CRW_LP_TS=0 selects the shared-memory query tile (SS MMAs)
+    { const char* e = getenv("CRW_LP_TS"); plan->ts = ((!e || atoi(e) != 0) && !plan->pair) ? 1 : 0; }
     const int tile_rows = plan->pair ? kPairM : kBM;
     p.tiles_per_rg = ceil_div(T * N, tile_rows);
     p.total_tiles = R * p.tiles_per_rg;

@@ -115,12 +115,12 @@ def _dev(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
 
 
-@pytest.fixture(params=["single", "pair", "ts"])
+@pytest.fixture(params=["ts", "ss", "pair"])
 def lp_kernel(request, monkeypatch):
-    """The tensor-path kernels: single-CTA with the query tile in shared memory ("SS" MMAs), the CTA-pair one (cta_group::2,
-    env CRW_LP_PAIR=1) and single-CTA with the query tile in tensor memory ("TS" MMAs, env CRW_LP_TS)."""
+    """The tensor-path kernels: single-CTA with the query tile in tensor memory ("TS" MMAs, the default), single-CTA with
+    the query tile in shared memory ("SS" MMAs, env CRW_LP_TS=0) and the CTA-pair one (cta_group::2, env CRW_LP_PAIR=1)."""
     monkeypatch.setenv("CRW_LP_PAIR", "1" if request.param == "pair" else "0")
-    monkeypatch.setenv("CRW_LP_TS", "1" if request.param == "ts" else "0")
+    monkeypatch.setenv("CRW_LP_TS", "0" if request.param == "ss" else "1")
     return request.param
 
 
