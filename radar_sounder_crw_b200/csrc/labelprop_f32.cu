@@ -661,9 +661,10 @@ extern "C" int crw_label_gather_step(const float* W, const int32_t* I, const flo
 namespace crw {
 // tensor path (labelprop_tc.cu): prep kernel + plan, then top-k launches over ranges of schedule slots
 struct LpTcPlanStorage { alignas(64) unsigned char bytes[1024]; };
+size_t lp_tc_split_bytes();
 int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
-                  float* W, int32_t* I, void* scratch, cudaStream_t st, void* plan_storage);
-int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st);
+                  float* W, int32_t* I, void* scratch, void* split_ws, cudaStream_t st, void* plan_storage);
+int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st, bool split_tail);
 int lp_tc_total_slots(const void* plan_storage);
 int lp_tc_early_slots(const void* plan_storage);
 int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_t total_rows, int do_normalize, void* scratch,
@@ -709,7 +710,7 @@ SideCtx* side_ctx() {
 extern "C" size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k, int precision, int do_normalize,
                                               int have_topk_out) {
     size_t b = 0;
-    if (precision == CRW_PREC_BF16X3) b += align_up((size_t)R * T * N * C * 2 * 2, 256);   // bf16 hi + lo
+    if (precision == CRW_PREC_BF16X3) b += align_up((size_t)R * T * N * C * 2 * 2, 256) + align_up(crw::lp_tc_split_bytes(), 256);   // bf16 hi + lo, tail-split lists
     else if (do_normalize) b += align_up((size_t)R * T * N * C * sizeof(float), 256);
     if (!have_topk_out) b += 2 * align_up((size_t)R * T * k * N * sizeof(float), 256);
     return b + 256;
@@ -730,6 +731,8 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         if (ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f) || (int64_t)N < k) return CRW_ERR_INVALID;
         void* hilo = sp;
         sp += align_up((size_t)R * T * N * C * 2 * 2, 256);
+        void* split_ws = sp;
+        sp += align_up(lp_tc_split_bytes(), 256);
         float* Wt = W_or_null;
         int32_t* It = I_or_null;
         if (!Wt) {
@@ -742,7 +745,7 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
         if (rc != CRW_OK) return rc;
         LpTcPlanStorage plan;
-        if ((rc = lp_tc_prepare(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, st, plan.bytes)) != CRW_OK) return rc;
+        if ((rc = lp_tc_prepare(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, split_ws, st, plan.bytes)) != CRW_OK) return rc;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -752,7 +755,7 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         const char* nofork = getenv("CRW_LP_NO_FORK");
         SideCtx* sc = (gp.mode_fixed || early >= total || early > sms / 2 || (nofork && atoi(nofork))) ? nullptr : side_ctx();
         if (!sc) {
-            if ((rc = lp_tc_launch(plan.bytes, 0, total, sms, st)) != CRW_OK) return rc;
+            if ((rc = lp_tc_launch(plan.bytes, 0, total, sms, st, true)) != CRW_OK) return rc;
             if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
             return gather_launch_par(gp, st);
         }
@@ -760,9 +763,9 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));                       // prep done
         // the bulk is the critical path: enqueue it first (it leaves the early tiles their SMs when they are few)
         const int bulk_ctas = (early <= sms / 8) ? sms - early : sms;
-        if ((rc = lp_tc_launch(plan.bytes, early, total, bulk_ctas, st)) != CRW_OK) return rc;
+        if ((rc = lp_tc_launch(plan.bytes, early, total, bulk_ctas, st, true)) != CRW_OK) return rc;
         CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
-        if ((rc = lp_tc_launch(plan.bytes, 0, early, sms, sc->s2)) != CRW_OK) return rc;            // frames 1..ctx+1 (and a few more)
+        if ((rc = lp_tc_launch(plan.bytes, 0, early, sms, sc->s2, false)) != CRW_OK) return rc;     // frames 1..ctx+1 (and a few more)
         if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;                              // the true recurrence
         CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
         CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
@@ -848,7 +851,7 @@ extern "C" int crw_labelprop_forward_host(const float* feats_host, const float* 
     int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
     if (rc != CRW_OK) return rc;
     LpTcPlanStorage plan;
-    if ((rc = lp_tc_prepare(nullptr, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, st, plan.bytes)) != CRW_OK) return rc;
+    if ((rc = lp_tc_prepare(nullptr, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, hilo, nullptr, st, plan.bytes)) != CRW_OK) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -23,7 +23,10 @@ namespace crw {
 // prep: normalise (optional) + split into bf16 hi / lo.  One warp per row, C == 128.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lp_prep_bf16_kernel(const float* __restrict__ x, int64_t rows, int do_normalize,
-                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                           int* __restrict__ zero, int n_zero) {
+    if (blockIdx.x == 0)          // arrival counters of the top-k kernel's split tiles (same stream, runs before it)
+        for (int i = threadIdx.x; i < n_zero; i += 256) zero[i] = 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= rows) return;
@@ -69,10 +72,15 @@ struct TcParams {
     int v_begin, v_end; // range of schedule slots this launch walks (slot -> tile: early tiles of all radargrams first)
     unsigned magic_n;   // floor(2^32 / N) + 1: x / N == __umulhi(x, magic_n) for x * N < 2^32
     int debug;          // profiling aid (env CRW_TC_DEBUG): 1 = skip insertions, 2 = also skip filter/park; results invalid
-    const __nv_bfloat16* hi;   // [R*T*N, 128] operand planes (the TS kernel reads its query rows straight from them)
+    const __nv_bfloat16* hi;   // [R*T*N, 128] operand planes
     const __nv_bfloat16* lo;
     long long total_rows;
+    // tail split (see Sched): partial lists [tail tile][half][value s | id s][128 rows] and arrival counters [tail tile][quadrant]
+    float* pbuf;
+    int* pcnt;
+    int split_ok;
 };
+constexpr int kMaxSplitTiles = 74;       // at most half the SMs of a B200 own a tile in the last, partial round
 
 // host-side plan of one tensor-path call (opaque to labelprop_f32.cu: it only sees the size)
 struct LpTcPlan {
@@ -119,16 +127,56 @@ __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t,
     nrows = min(kBN, t.n_hi * p.N - row0);
 }
 
-// next tile of a CTA's static schedule (stride tiles apart) that has work, or -1
-__device__ __forceinline__ int next_tile_with_work(const TcParams& p, int tile, int stride) {
-    for (tile += stride; tile < p.v_end; tile += stride)
-        if (tile_info(p, tile).n_ktiles != 0) return tile;
-    return -1;
-}
-__device__ __forceinline__ int first_tile_with_work(const TcParams& p, int tile, int stride) {
-    if (tile < p.v_end && tile_info(p, tile).n_ktiles != 0) return tile;
-    return next_tile_with_work(p, tile, stride);
-}
+// Work items of one launch.  A CTA walks items blockIdx.x, blockIdx.x + G, ...  Items are whole query tiles, except that the tiles of
+// the last, partial round (tail = tiles mod G, when 2 tail <= G) are cut in two by KEY range: 2 tail items on 2 tail different CTAs,
+// each producing a partial top-k list per query; the half that arrives second (a counter per tile and lane quadrant) merges the
+// two lists and finishes the query.  470 tiles on 139 CTAs are 3 full rounds + 53 tiles = 106 half items instead of a 4th round.
+struct Sched {
+    int G, full, tail, n_items;
+    bool split;
+    __device__ __forceinline__ Sched(const TcParams& p, int grid) {
+        const int Tn = p.v_end - p.v_begin;
+        G = grid;
+        full = (Tn / G) * G;
+        tail = Tn - full;
+        split = p.split_ok && full > 0 && tail > 0 && 2 * tail <= G && tail <= kMaxSplitTiles;
+        n_items = full + (split ? 2 * tail : tail);
+    }
+    // item -> tile info, key-tile range [kt_lo, kt_hi), half (-1: whole tile) and index of the tile among the split ones.
+    // The halves are the FIRST items (one per CTA, 2 tail CTAs): the hand-over at the end of a half (global stores, counter,
+    // maybe the merge) then overlaps the start of the CTA's next item instead of sitting at the very end of the launch.
+    __device__ __forceinline__ TileInfo decode(const TcParams& p, int item, int& kt_lo, int& kt_hi, int& half, int& tidx) const {
+        int tile = p.v_begin + item;
+        half = -1; tidx = 0;
+        if (split) {
+            if (item < 2 * tail) {
+                half = (item >= tail) ? 1 : 0;
+                tidx = item - half * tail;
+                tile = p.v_begin + full + tidx;
+            } else {
+                tile = p.v_begin + item - 2 * tail;
+            }
+        }
+        const TileInfo t = tile_info(p, tile);
+        kt_lo = 0; kt_hi = t.n_ktiles;
+        if (half == 0) kt_hi = t.n_ktiles / 2;
+        if (half == 1) kt_lo = t.n_ktiles / 2;
+        return t;
+    }
+    __device__ __forceinline__ bool has_work(const TcParams& p, int item) const {
+        int a, b, h, x;
+        return decode(p, item, a, b, h, x).n_ktiles != 0;
+    }
+    __device__ __forceinline__ int next(const TcParams& p, int item) const {      // next item of this CTA with work, or -1
+        for (item += G; item < n_items; item += G)
+            if (has_work(p, item)) return item;
+        return -1;
+    }
+    __device__ __forceinline__ int first(const TcParams& p, int item) const {
+        if (item < n_items && has_work(p, item)) return item;
+        return next(p, item);
+    }
+};
 
 // profiling aid (CRW_TC_DEBUG bit 3): cycles each epilogue warp spends per phase, summed over the launch
 //   [0] waiting for an accumulator  [1] tcgen05.ld + park + threshold mask  [2] validity mask  [3] insertion loop
@@ -351,8 +399,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const bool leader = tc::elect_one();
         uint32_t scnt = 0, tcnt = 0;          // ring slots handed out so far (key tiles and, TS, query planes); tiles done
         // TS: the two planes of query tile tl, one ring slot each ([kblock 0,1][128 rows][128 B])
-        auto push_query = [&](int tl) {
-            const TileInfo tq = tile_info(p, tl);
+        const Sched sched(p, gridDim.x);
+        auto push_query = [&](int it) {
+            int a_, b_, h_, x_;
+            const TileInfo tq = sched.decode(p, it, a_, b_, h_, x_);
             const int grow_q = tq.rg * p.T * N + tq.r0;
             for (int plane = 0; plane < 2; ++plane, ++scnt) {
                 const int s = scnt % kNStages;
@@ -366,14 +416,15 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             }
         };
         if (TS) {
-            const int first = first_tile_with_work(p, p.v_begin + blockIdx.x, gridDim.x);
+            const int first = sched.first(p, blockIdx.x);
             if (first >= 0) push_query(first);
         }
-        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
-            const TileInfo t = tile_info(p, tile);
+        for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
+            int kt_lo, kt_hi, half, tidx;
+            const TileInfo t = sched.decode(p, item, kt_lo, kt_hi, half, tidx);
             if (t.n_ktiles == 0) continue;
             const int grow = t.rg * p.T * N;   // first global row of this radargram
-            const int nx = TS ? next_tile_with_work(p, tile, gridDim.x) : -1;
+            const int nx = TS ? sched.next(p, item) : -1;
             if (!TS) {
                 tc::mbar_wait_backoff(&q_empty, (tcnt & 1) ^ 1);
                 if (leader) {
@@ -383,7 +434,8 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         tc::tma_load_2d(sQ + sub * (kBM * 128), (sub & 2) ? &qmap_lo : &qmap_hi, (sub & 1) * 64, grow + t.r0, &q_full[0]);
                 }
             }
-            for (int kt = 0; kt < t.n_ktiles; ++kt) {
+            if (TS && kt_lo == kt_hi && nx >= 0) push_query(nx);      // (a half without key tiles still passes the next query on)
+            for (int kt = kt_lo; kt < kt_hi; ++kt) {
                 const int s = scnt % kNStages;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
@@ -396,7 +448,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                         tc::tma_load_2d(dst + sub * (kBN * 128), (sub & 2) ? &kmap_lo : &kmap_hi, (sub & 1) * 64, grow + row0, &k_full[s]);
                 }
                 ++scnt;
-                if (TS && kt == 0 && nx >= 0) push_query(nx);
+                if (TS && kt == kt_lo && nx >= 0) push_query(nx);
             }
             ++tcnt;
         }
@@ -423,14 +475,17 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 __syncwarp();
             }
         };
-        if (TS && first_tile_with_work(p, p.v_begin + blockIdx.x, gridDim.x) >= 0) copy_query(0u);
-        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
-            const TileInfo t = tile_info(p, tile);
+        const Sched sched(p, gridDim.x);
+        if (TS && sched.first(p, blockIdx.x) >= 0) copy_query(0u);
+        for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
+            int kt_lo, kt_hi, half, tidx;
+            const TileInfo t = sched.decode(p, item, kt_lo, kt_hi, half, tidx);
             if (t.n_ktiles == 0) continue;
-            const int nx = TS ? next_tile_with_work(p, tile, gridDim.x) : -1;
+            const int nx = TS ? sched.next(p, item) : -1;
             if (!TS) tc::mbar_wait_backoff(&q_full[0], tcnt & 1);
             const uint32_t qtmem = tmem_base + (uint32_t)((tcnt & 1) * 128);      // TS: this tile's query buffer
-            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+            if (TS && kt_lo == kt_hi && nx >= 0) copy_query((tcnt + 1) & 1u);
+            for (int kt = kt_lo; kt < kt_hi; ++kt, ++kcnt) {
                 const int s = scnt % kNStages, a = kcnt % kNAcc;
                 int row0, nrows;
                 ktile_rows(p, t, kt, row0, nrows);
@@ -467,7 +522,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
                 __syncwarp();
                 ++scnt;
-                if (TS && kt == 0 && nx >= 0) copy_query((tcnt + 1) & 1u);   // the next tile's query planes follow in the ring
+                if (TS && kt == kt_lo && nx >= 0) copy_query((tcnt + 1) & 1u);   // the next item's query planes follow in the ring
             }
             if (!TS && leader) tc::umma_commit(&q_empty);    // query tile may be overwritten
             __syncwarp();
@@ -487,8 +542,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
         const uint32_t park = tc::smem_u32(park_base + warp * kParkWarp) + lane * 4;
         uint32_t kcnt = 0;
         bool scratch_pending = false;     // part 1: part 0 may still be reading last tile's list out of this warp's park buffer
-        for (int tile = p.v_begin + blockIdx.x; tile < p.v_end; tile += gridDim.x) {
-            const TileInfo t = tile_info(p, tile);
+        const Sched sched(p, gridDim.x);
+        for (int item = blockIdx.x; item < sched.n_items; item += gridDim.x) {
+            int kt_lo, kt_hi, half, tidx;
+            const TileInfo t = sched.decode(p, item, kt_lo, kt_hi, half, tidx);
             if (t.n_ktiles == 0) continue;
             const int row = t.r0 + lrow;
             const int n = row / N, q = row - n * N;
@@ -499,7 +556,7 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
             const bool wide_band = 2 * rb + 1 > 64;             // (warp-uniform) band wider than a key tile: generic loop
             TopList<KT> top;                                    // ids hold the key ROW until the end of the tile
             top.init();
-            for (int kt = 0; kt < t.n_ktiles; ++kt, ++kcnt) {
+            for (int kt = kt_lo; kt < kt_hi; ++kt, ++kcnt) {
                 // key tiles are dealt round-robin to the tile groups; the group that also merges and finishes the query (part 0)
                 // takes the later residue, i.e. the smaller share when the count does not divide.  (Giving part 1 a few key
                 // tiles more, to fill the time part 0 spends merging, measured slower: 114.0 / 114.6 / 115.3 / 116.8 us for 0-3.)
@@ -640,7 +697,31 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                 }
                 if (kRunAhead) asm volatile("bar.arrive %0, %1;" ::"r"(5 + g), "n"(64) : "memory");   // part 1's buffer is free again
                 c_m2 = profm ? clock64() : 0;
-                if (qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
+                bool finish = true;
+                if (half >= 0) {
+                    // half of a split tile: publish this half's list, count the arrival; the second half to arrive merges both
+                    float* mine = p.pbuf + ((size_t)(tidx * 2 + half) * 2 * KT) * kBM + lrow;
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) { mine[s * kBM] = top.v[s]; mine[(KT + s) * kBM] = top.idf[s]; }
+                    // the lanes' stores happen before lane 0's release (ordered by the warp barrier); its acquire orders the
+                    // other half's list before the loads below (ordered by the shuffle)
+                    __syncwarp();
+                    int arrived = 0;
+                    if (lane == 0)
+                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(arrived) : "l"(&p.pcnt[tidx * 4 + g]) : "memory");
+                    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                    finish = arrived == 1;
+                    if (finish) {
+                        const float* other = p.pbuf + ((size_t)(tidx * 2 + (1 - half)) * 2 * KT) * kBM + lrow;
+#pragma unroll 2
+                        for (int s = 0; s < KT; ++s) {
+                            const float x = __ldcg(other + s * kBM);
+                            if (!__any_sync(0xffffffffu, x >= top.v[KT - 1])) break;
+                            top.insert_tie(x, __ldcg(other + (KT + s) * kBM));
+                        }
+                    }
+                }
+                if (finish && qvalid) lp_finish_query<KT>(p, top, t.rg, n, q, win_lo);
             } else {
                 if (kRunAhead) scratch_pending = true;
                 c_m2 = profm ? clock64() : 0;
@@ -976,19 +1057,25 @@ static int launch_tc_any(const CUtensorMap* maps, const TcParams& p, int ts, int
 // the bulk of the top-k: lp_tc_prepare launches the prep kernel and fills the plan (tensor maps, parameters, schedule);
 // lp_tc_launch runs the top-k kernel over a range of schedule slots on at most max_ctas CTAs.
 // feats [R,T,N,128] fp32 -> W, I [R,T,k,N]; scratch must hold 2 * R*T*N*128 bf16.
+size_t lp_tc_split_bytes() { return (size_t)kMaxSplitTiles * 2 * 2 * 32 * kBM * sizeof(float) + (size_t)kMaxSplitTiles * 4 * sizeof(int); }
+
+// split_ws: lp_tc_split_bytes() of scratch for the tail split (null: never split)
 int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize,
-                  float* W, int32_t* I, void* scratch, cudaStream_t st, void* plan_storage) {
+                  float* W, int32_t* I, void* scratch, void* split_ws, cudaStream_t st, void* plan_storage) {
     static_assert(sizeof(LpTcPlan) <= 1024, "LpTcPlan must fit the caller's plan storage");
     LpTcPlan* plan = reinterpret_cast<LpTcPlan*>(plan_storage);
     if (C != 128 || N > 128 || N < 8 || k > 32) return CRW_ERR_UNSUPPORTED;
     const int64_t rows = (int64_t)R * T * N;
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
     __nv_bfloat16* lo = hi + rows * 128;
+    TcParams& p = plan->p;
+    p.pbuf = reinterpret_cast<float*>(split_ws);
+    p.pcnt = split_ws ? reinterpret_cast<int*>(reinterpret_cast<char*>(split_ws) + (size_t)kMaxSplitTiles * 2 * 2 * 32 * kBM * sizeof(float)) : nullptr;
+    p.split_ok = 0;
     if (feats) {       // null: the caller fills hi / lo itself with lp_tc_prep_rows (host-streamed features)
-        lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo);
+        lp_prep_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(feats, rows, do_normalize, hi, lo, p.pcnt, p.pcnt ? kMaxSplitTiles * 4 : 0);
         CRW_LAUNCH_RET();
     }
-    TcParams& p = plan->p;
     p.W = W; p.I = I; p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
     p.total_tiles = 0; p.v_begin = p.v_end = 0; p.tiles_per_rg = 0; p.early_per_rg = 0;
     p.hi = hi; p.lo = lo; p.total_rows = rows;
@@ -1023,12 +1110,15 @@ int lp_tc_prepare(const float* feats, int R, int T, int N, int C, int ctx, float
     return CRW_OK;
 }
 
-int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st) {
+// split_tail: the tiles of the last, partial round may be cut in two (needs the split workspace and counters zeroed by the prep
+// kernel of this call, i.e. at most ONE splitting launch per lp_tc_prepare)
+int lp_tc_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st, bool split_tail) {
     const LpTcPlan& plan = *reinterpret_cast<const LpTcPlan*>(plan_storage);
     if (v_end <= v_begin) return CRW_OK;
     TcParams p = plan.p;
     p.v_begin = v_begin;
     p.v_end = v_end;
+    { const char* e = getenv("CRW_LP_NO_SPLIT"); p.split_ok = (split_tail && p.pbuf && !plan.pair && !(e && atoi(e))) ? 1 : 0; }
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(plan.maps);
     const int k = p.k;
     if (plan.pair) {
@@ -1049,7 +1139,7 @@ int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_
     if (nrows <= 0) return CRW_OK;
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(scratch);
     __nv_bfloat16* lo = hi + total_rows * 128;
-    lp_prep_bf16_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(stage, nrows, do_normalize, hi + row_begin * 128, lo + row_begin * 128);
+    lp_prep_bf16_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(stage, nrows, do_normalize, hi + row_begin * 128, lo + row_begin * 128, nullptr, 0);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -1060,9 +1150,9 @@ int lp_tc_launch_tiles(const void* plan_storage, int rg, int ta, int tb, int max
     if (tb > tpr) tb = tpr;
     int rc = CRW_OK;
     const int ea = ta < E ? ta : E, eb = tb < E ? tb : E;
-    if (eb > ea) rc = lp_tc_launch(plan_storage, rg * E + ea, rg * E + eb, max_ctas, st);
+    if (eb > ea) rc = lp_tc_launch(plan_storage, rg * E + ea, rg * E + eb, max_ctas, st, false);
     const int ra = ta > E ? ta : E, rb = tb > E ? tb : E;
-    if (rc == CRW_OK && rb > ra) rc = lp_tc_launch(plan_storage, R * E + rg * (tpr - E) + (ra - E), R * E + rg * (tpr - E) + (rb - E), max_ctas, st);
+    if (rc == CRW_OK && rb > ra) rc = lp_tc_launch(plan_storage, R * E + rg * (tpr - E) + (ra - E), R * E + rg * (tpr - E) + (rb - E), max_ctas, st, false);
     return rc;
 }
 int lp_tc_tiles_per_rg(const void* plan) { return reinterpret_cast<const LpTcPlan*>(plan)->p.tiles_per_rg; }

@@ -42,3 +42,7 @@ print(f"  CTAs with 3 tiles ({n4}..138): slowest warp mean {cta_max[n4:139].mean
 print(f"  slowest CTA {cta_max[:139].max():9.0f}; within-CTA (slowest warp / mean warp) {np.mean(cta_max[9:139] / cta_mean[9:139]):.3f}")
 by_g = tot[9:139].reshape(-1, 2, 4)          # [cta, part, quadrant]
 print("  mean by quadrant (part 0):", np.round(by_g[:, 0, :].mean(0)), " (part 1):", np.round(by_g[:, 1, :].mean(0)))
+# tail split (3 whole tiles + a half on CTAs 0..105, 3 whole tiles on the rest)
+print(f"  split view: CTAs 9..52 {cta_max[9:53].mean():9.0f}   53..105 {cta_max[53:106].mean():9.0f}   106..138 {cta_max[106:139].mean():9.0f}")
+for i, nm in enumerate(names):
+    print(f"    {nm:14s} 9..52 {p[9:53, :, i].mean():9.0f}   53..105 {p[53:106, :, i].mean():9.0f}   106..138 {p[106:139, :, i].mean():9.0f}")
