@@ -406,6 +406,8 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its debug lines ("NCCL version ...") to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import radar_sounder_crw_b200 as crw
     pk = peaks()
