@@ -44,6 +44,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def protect_stdout():
+    """Libraries print to stdout behind our back (NCCL: "NCCL version ..." at init).  Keep the original stdout for the ONE
+    JSON line and point fd 1 at stderr for everybody else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -406,8 +428,6 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL writes its debug lines ("NCCL version ...") to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import radar_sounder_crw_b200 as crw
     pk = peaks()
@@ -423,12 +443,12 @@ def run_b200(args):
         r = bench_walk(crw, args, world, pk, N=369, T=20, B=32, precision=crw.ops.PREC_BF16X3,
                        kernel_note="walk fwd+bwd kernels, tcgen05 bf16x3 GEMMs, 8 launches")
         if rank == 0:
-            print(json.dumps(dict(only=only, walk=r)), flush=True)
+            emit(dict(only=only, walk=r))
         return
     if only == "walk_sweep":
         sweep = bench_walk_sweep(crw, args, world, pk)
         if rank == 0:
-            print(json.dumps(dict(only=only, walk_sweep=sweep)), flush=True)
+            emit(dict(only=only, walk_sweep=sweep))
         return
 
     cpu = None
@@ -438,7 +458,7 @@ def run_b200(args):
 
     if rank == 0:
         if only != "all":
-            print(json.dumps(dict(only=only, train=tr, walk=wk, labelprop=lp)), flush=True)
+            emit(dict(only=only, train=tr, walk=wk, labelprop=lp))
         else:
             B, T = TRAIN["B"], TRAIN["T"]
             hot = dict(what="fused walk fwd+bwd (crw_b200::walk_loss + backward), embeddings resident, CUDA-graph replay",
@@ -460,7 +480,7 @@ def run_b200(args):
                 clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=wk["launches"] * args.steps,
                 roofline=wk["roofline"], hot_path=hot, loss=tr["loss"],
                 cpu_baseline=(cpu["train"] if cpu else None), labelprop=lp)
-            print(json.dumps(line), flush=True)
+            emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -540,7 +560,7 @@ def run_reference(args):
                                                  sample="full config-3 radargram, linear-time C port (OpenMP)"),
                                e2e=dict(value=Tl * COLS_PER_FRAME / dt_lp, unit="columns/s", h2d_bytes_per_step=0,
                                         d2h_bytes_per_step=0)))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -555,6 +575,7 @@ def main():
     ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep", "walk_tc_large"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
