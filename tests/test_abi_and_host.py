@@ -114,3 +114,13 @@ def test_encoder_state_dict_keys_are_reference_compatible(pkg):
     out = pkg.Resnet(pos_embed=False).eval()(torch.randn(2, 1, 16, 16))
     assert out.shape == (2, 128)
     assert pkg.CNN(False)(torch.randn(2, 1, 16, 16)).shape == (2, 128)
+
+
+def test_generated_toplist_insert_is_current():
+    """csrc/toplist_insert.inc is generated by tools/gen_toplist_insert.py: the committed file must be the generator's output."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_toplist_insert.py")], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(root, "radar_sounder_crw_b200", "csrc", "toplist_insert.inc")) as fh:
+        assert fh.read() == out

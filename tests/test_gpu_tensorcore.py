@@ -279,6 +279,31 @@ def test_lp_tensorcore_config3_full_size(pkg):
     assert frac >= 0.995
 
 
+@pytest.mark.parametrize("shape", [(1, 400, 49, 10, 12.0), (1, 1250, 49, 10, 12.0), (2, 600, 47, 20, 24.0)])
+def test_lp_tensorcore_variants_are_bit_identical(pkg, shape, monkeypatch):
+    """Every form of the tensor-path top-k computes each dot product with the same MMAs and orders ties the same way, so
+    the query tile in TMEM or shared memory, the tail split (partial lists merged through global memory) and the CTA-pair
+    kernel must agree to the bit: weights, ids, soft masks, labels.  Shapes: 6 / 53 / 34 tiles in the partial round (the last one over two radargrams, k = 20)."""
+    R, T, N, k, radius = shape
+    rs = np.random.RandomState(T + k)
+    feats = _dev((rs.randn(R, T, N, 128) + 1.5 * rs.randn(R, 1, 1, 128)).astype(np.float32))
+    M = 4
+    mask0 = _dev(np.stack([lo.one_hot_mask(rs.randint(0, M, N), M, np.float32) for _ in range(R)]))
+    outs = {}
+    for name, env in [("default", {}), ("no_split", {"CRW_LP_NO_SPLIT": "1"}), ("ss", {"CRW_LP_TS": "0"}),
+                      ("ss_no_split", {"CRW_LP_TS": "0", "CRW_LP_NO_SPLIT": "1"}), ("pair", {"CRW_LP_PAIR": "1"}),
+                      ("no_fork", {"CRW_LP_NO_FORK": "1"})]:
+        for key in ("CRW_LP_NO_SPLIT", "CRW_LP_TS", "CRW_LP_PAIR", "CRW_LP_NO_FORK"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        outs[name] = [x.clone() for x in pkg.ops.labelprop(feats, mask0, 20, radius, 0.07, k, 0, pkg.ops.PREC_BF16X3, True, True)]
+        torch.cuda.synchronize()
+    for name, o in outs.items():
+        for a, b in zip(outs["default"], o):
+            assert torch.equal(a[:, 1:], b[:, 1:]), name
+
+
 # ----------------------------------------------------------------------------------------------
 # tensor-core walk (tcgen05 bf16x3 GEMMs, fp32 accumulate in TMEM): loss / gradients within 1e-3 relative
 # ----------------------------------------------------------------------------------------------
