@@ -504,7 +504,16 @@ __global__ void __launch_bounds__(kST) walk_s_bwd_dx_kernel(const float* __restr
     float* Out = En;               // written only after both products are in registers (4 buffers -> 2 CTAs per SM)
     const WalkLayout lay(B, T, N, C);
     const BwdLayout bl(B, T, N);
-    const int t = blockIdx.x, b = blockIdx.y, N4 = (N + 3) & ~3;
+    // 1-D grid of B * T items, the B * (T - 2) inner frames first: they form two products each, frames 0 and T - 1 only one.
+    // B * T = 320 CTAs at config 2 are 1.08 waves of two CTAs per SM; with the light items last the second wave is short
+    // (and starts as soon as the first light items finish) instead of costing a whole heavy CTA time.
+    int t, b;
+    {
+        const int inner = B * (T - 2), idx = blockIdx.x;
+        if (idx < inner) { b = idx / (T - 2); t = 1 + idx - b * (T - 2); }
+        else { const int j = idx - inner; b = j >> 1; t = (j & 1) ? T - 1 : 0; }
+    }
+    const int N4 = (N + 3) & ~3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* invn = ws + lay.invn + (size_t)b * T * N;
     const bool hasN = t <= T - 2, hasP = t >= 1;
@@ -657,7 +666,7 @@ static int walk_small_backward_t(const float* x, const float* ws, const float* d
     CRW_LAUNCH_RET();
     const size_t smX = (2 * kMat + 2 * kMatX) * sizeof(float);
     if ((rc = set_smem(walk_s_bwd_dx_kernel<MMA>, smX))) return rc;
-    walk_s_bwd_dx_kernel<MMA><<<dim3(T, B), kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
+    walk_s_bwd_dx_kernel<MMA><<<B * T, kST, smX, st>>>(x, ws, sc, dx, B, T, N, C, inv_tau);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
