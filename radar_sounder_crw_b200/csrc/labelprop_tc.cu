@@ -134,29 +134,34 @@ __device__ __forceinline__ void ktile_rows(const TcParams& p, const TileInfo& t,
 struct Sched {
     int G, full, tail, n_items;
     bool split;
-    __device__ __forceinline__ Sched(const TcParams& p, int grid) {
-        const int Tn = p.v_end - p.v_begin;
+    __host__ __device__ __forceinline__ Sched(int n_tiles, int grid, bool split_ok) {
         G = grid;
-        full = (Tn / G) * G;
-        tail = Tn - full;
-        split = p.split_ok && full > 0 && tail > 0 && 2 * tail <= G && tail <= kMaxSplitTiles;
+        full = (n_tiles / G) * G;
+        tail = n_tiles - full;
+        split = split_ok && full > 0 && tail > 0 && 2 * tail <= G && tail <= kMaxSplitTiles;
         n_items = full + (split ? 2 * tail : tail);
+    }
+    __device__ __forceinline__ Sched(const TcParams& p, int grid) : Sched(p.v_end - p.v_begin, grid, p.split_ok != 0) {}
+    // item -> tile (relative to the launch's first slot), half (-1: whole tile), index among the split tiles
+    __host__ __device__ __forceinline__ void map(int item, int& tile_rel, int& half, int& tidx) const {
+        tile_rel = item; half = -1; tidx = 0;
+        if (split) {
+            if (item < 2 * tail) {
+                half = (item >= tail) ? 1 : 0;
+                tidx = item - half * tail;
+                tile_rel = full + tidx;
+            } else {
+                tile_rel = item - 2 * tail;
+            }
+        }
     }
     // item -> tile info, key-tile range [kt_lo, kt_hi), half (-1: whole tile) and index of the tile among the split ones.
     // The halves are the FIRST items (one per CTA, 2 tail CTAs): the hand-over at the end of a half (global stores, counter,
     // maybe the merge) then overlaps the start of the CTA's next item instead of sitting at the very end of the launch.
     __device__ __forceinline__ TileInfo decode(const TcParams& p, int item, int& kt_lo, int& kt_hi, int& half, int& tidx) const {
-        int tile = p.v_begin + item;
-        half = -1; tidx = 0;
-        if (split) {
-            if (item < 2 * tail) {
-                half = (item >= tail) ? 1 : 0;
-                tidx = item - half * tail;
-                tile = p.v_begin + full + tidx;
-            } else {
-                tile = p.v_begin + item - 2 * tail;
-            }
-        }
+        int tile;
+        map(item, tile, half, tidx);
+        tile += p.v_begin;
         const TileInfo t = tile_info(p, tile);
         kt_lo = 0; kt_hi = t.n_ktiles;
         if (half == 0) kt_hi = t.n_ktiles / 2;
@@ -1174,6 +1179,19 @@ int lp_profile_read(unsigned long long* host_out, int reset) {
 }
 
 }  // namespace crw
+
+// test aid (host only): the work items of a top-k launch over n_tiles tiles on grid CTAs, in item order: out[3 i] = tile,
+// out[3 i + 1] = half (-1 whole tile, 0 / 1 key-range half), out[3 i + 2] = index among the split tiles.  Returns the item count
+// (or, with out == null, only the count).
+extern "C" int crw_debug_lp_schedule(int n_tiles, int grid, int split_ok, int* out, int out_capacity_items) {
+    if (n_tiles < 0 || grid < 1) return CRW_ERR_INVALID;
+    const crw::Sched sc(n_tiles, grid, split_ok != 0);
+    if (out) {
+        if (out_capacity_items < sc.n_items) return CRW_ERR_INVALID;
+        for (int i = 0; i < sc.n_items; ++i) sc.map(i, out[3 * i], out[3 * i + 1], out[3 * i + 2]);
+    }
+    return sc.n_items;
+}
 
 // profiling aid: copies the per-warp phase counters (160 x 8 x 10 uint64) to host memory and optionally clears them
 extern "C" int crw_debug_lp_profile(unsigned long long* host_out, int reset) { return crw::lp_profile_read(host_out, reset); }

@@ -124,3 +124,32 @@ def test_generated_toplist_insert_is_current():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_toplist_insert.py")], capture_output=True, text=True, check=True).stdout
     with open(os.path.join(root, "radar_sounder_crw_b200", "csrc", "toplist_insert.inc")) as fh:
         assert fh.read() == out
+
+
+@pytest.mark.parametrize("n_tiles,grid", [(470, 139), (479, 148), (145, 139), (9, 9), (100, 148), (444, 148), (498, 130),
+                                          (9696, 148), (424, 130), (1, 1), (297, 148), (0, 148)])
+def test_lp_tail_split_schedule_covers_every_tile_once(pkg, n_tiles, grid):
+    """Host mirror of the device scheduler of the tensor-path top-k: every tile is one whole item or exactly two halves (0 and 1) on
+    different CTAs; halves come first, one per CTA; a CTA never owns more than ceil(items / grid) items."""
+    import ctypes
+    L = pkg._lib.lib()
+    for split_ok in (0, 1):
+        n = L.crw_debug_lp_schedule(n_tiles, grid, split_ok, None, 0)
+        assert n >= n_tiles
+        buf = (ctypes.c_int * (3 * max(n, 1)))()
+        assert L.crw_debug_lp_schedule(n_tiles, grid, split_ok, ctypes.cast(buf, ctypes.c_void_p), n) == n
+        items = np.frombuffer(buf, dtype=np.int32)[: 3 * n].reshape(n, 3)
+        whole = items[items[:, 1] < 0]
+        halves = items[items[:, 1] >= 0]
+        assert sorted(whole[:, 0].tolist() + sorted(set(halves[:, 0].tolist()))) == list(range(n_tiles))
+        if split_ok == 0:
+            assert len(halves) == 0 and n == n_tiles
+        for tile in set(halves[:, 0].tolist()):
+            rows = np.nonzero((items[:, 0] == tile) & (items[:, 1] >= 0))[0]
+            assert sorted(items[rows, 1].tolist()) == [0, 1]
+            assert len({int(r) % grid for r in rows}) == 2                 # the two halves run on different CTAs
+            assert len(set(items[rows, 2].tolist())) == 1 and 0 <= items[rows[0], 2] < 74
+        if len(halves):
+            assert n_tiles % grid != 0 and 2 * (n_tiles % grid) <= grid and n_tiles >= grid
+            assert (items[: len(halves), 1] >= 0).all() and len(halves) <= grid  # first items, at most one per CTA
+            assert len(set(halves[:, 2].tolist())) == len(halves) // 2
