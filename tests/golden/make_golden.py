@@ -191,6 +191,10 @@ def main():
         make_io_seed("io_seed.npz")
         make_io_fuse("io_fuse.npz")
         return
+    if "--round1b" in sys.argv:      # added later in round 1: BASELINE config 4 / config 5 parameters (the other fixtures stay byte-identical)
+        make_walk(ref, "walk_cfg4_f32.npz", 1, 20, 47, 128, 0.07, torch.float32, 15)
+        make_lp(ref, "lp_cfg5_short.npz", 45, 49, 128, 4, 20, 20, 24, 0.07, 16)
+        return
     make_walk(ref, "walk_small_f64.npz", 2, 6, 9, 16, 0.07, torch.float64, 11)
     make_walk(ref, "walk_t3_f64.npz", 2, 3, 7, 8, 0.07, torch.float64, 12)
     make_walk(ref, "walk_cfg1_f32.npz", 1, 10, 47, 128, 0.07, torch.float32, 11)

@@ -56,7 +56,7 @@ def _run_lp(pkg, feats, label0, M, ctx, radius, temp, k, mode="ref_exact", norma
     return labels.cpu().numpy(), masks.cpu().numpy(), W.cpu().numpy(), I.cpu().numpy()
 
 
-@pytest.mark.parametrize("name", ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_masked_ties.npz", "lp_clustered.npz"])
+@pytest.mark.parametrize("name", ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_masked_ties.npz", "lp_clustered.npz", "lp_cfg5_short.npz"])
 def test_lp_golden_reference_outputs(pkg, name):
     """CUDA fp32 path vs the outputs of the LIVE reference (golden) and vs the C oracle (bit-exact)."""
     g = lp_case(name)
@@ -191,7 +191,7 @@ def _walk_gpu(pkg, x, tau, need_A=True):
     return float(loss.item()), (A.detach().cpu().numpy() if need_A else None), g
 
 
-@pytest.mark.parametrize("name", ["walk_small_f64.npz", "walk_t3_f64.npz", "walk_cfg1_f32.npz", "walk_tau001_f32.npz"])
+@pytest.mark.parametrize("name", ["walk_small_f64.npz", "walk_t3_f64.npz", "walk_cfg1_f32.npz", "walk_tau001_f32.npz", "walk_cfg4_f32.npz"])
 def test_walk_golden_reference_outputs(pkg, name):
     g = load_golden(name)
     x = g["x"].astype(np.float32)

@@ -257,7 +257,7 @@ def test_lp_config5_per_gpu_size_properties(pkg):
 
 def test_lp_tensorcore_golden_reference_labels(pkg, lp_kernel):
     """bf16x3 path against the LIVE reference's outputs: >= 99.9 % of pixels."""
-    for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz"]:
+    for name in ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_clustered.npz", "lp_cfg5_short.npz"]:
         g = lp_case(name)
         mask0 = lo.one_hot_mask(g["label0"], g["M"], np.float32)[None]
         labels, _, _, _ = pkg.ops.labelprop(_dev(g["feats"][None]), _dev(mask0), g["ctx"], g["radius"], g["temp"], g["k"], 0,

@@ -8,8 +8,8 @@ import pytest
 from helpers import load_golden, lp_case, order_mismatches_are_ties, rel_err, topk_sets_equal
 from oracle import c_oracle, labelprop_oracle as lo, walk_oracle as wo
 
-WALK = ["walk_small_f64.npz", "walk_t3_f64.npz", "walk_cfg1_f32.npz", "walk_tau001_f32.npz"]
-LP = ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_masked_ties.npz", "lp_clustered.npz"]
+WALK = ["walk_small_f64.npz", "walk_t3_f64.npz", "walk_cfg1_f32.npz", "walk_tau001_f32.npz", "walk_cfg4_f32.npz"]
+LP = ["lp_quirk.npz", "lp_cfg3_short.npz", "lp_masked_ties.npz", "lp_clustered.npz", "lp_cfg5_short.npz"]
 
 
 @pytest.mark.parametrize("name", WALK)
