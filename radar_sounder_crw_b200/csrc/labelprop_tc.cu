@@ -7,11 +7,15 @@
 //
 //   lp_prep_bf16_kernel   F.normalize (pinned order, bit-identical to the fp32 path) + hi/lo split
 //   lp_topk_tc_kernel     persistent, warp-specialised:
-//       warp 8      TMA producer: query tile (128 consecutive node rows) + 128-row key tiles, SWIZZLE_128B
-//       warp 9      tcgen05.mma issuer: 24 MMAs (3 passes x 8 k-steps) per key tile into one of 4 TMEM buffers
+//       warp 8      TMA producer: a ring of 32 KB stages, SWIZZLE_128B -- 64-row key tiles and (TS form, the default) the two
+//                   planes of the next query tile (128 consecutive node rows)
+//       warp 9      tcgen05 issuer: 24 MMAs (3 passes x 8 k-steps) per key tile into one of 4 TMEM accumulators; query planes
+//                   are copied from their ring slot into a TMEM query buffer with tcgen05.cp, in ring order
 //       warps 0-7   epilogue: tcgen05.ld a row per thread (thread = query node), frame-window + radius-band
-//                   predicate, running top-k in registers; the two column halves are merged through smem,
-//                   then softmax and the W / I stores.
+//                   predicate, running top-k in registers (sorted inserts on the FMA pipe, toplist_insert.inc); the two lists of
+//                   a query (key tiles are dealt to two warp groups) are merged through smem, then softmax and the W / I stores
+//   Work items (Sched): whole query tiles, and the tiles of the last, partial round cut in two by key range (lists handed over
+//   through global memory).  lp_topk_pair_kernel: the same on 2-CTA clusters with cta_group::2 MMAs (opt-in).
 // A query tile is 128 consecutive rows of the [T*N, C] feature matrix, so tiles are dense even though
 // frames (N = 47..49 rows) straddle them; each thread derives its own frame / window from its row index.
 #include <cstdlib>
