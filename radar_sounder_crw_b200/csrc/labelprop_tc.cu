@@ -712,13 +712,14 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                     float* mine = p.pbuf + ((size_t)(tidx * 2 + half) * 2 * KT) * kBM + lrow;
 #pragma unroll
                     for (int s = 0; s < KT; ++s) { mine[s * kBM] = top.v[s]; mine[(KT + s) * kBM] = top.idf[s]; }
-                    // the lanes' stores happen before lane 0's release (ordered by the warp barrier); its acquire orders the
-                    // other half's list before the loads below (ordered by the shuffle)
+                    // the lanes' stores happen before lane 0's release (ordered by the warp barrier before it); its acquire orders the
+                    // other half's list before the loads below (ordered by the warp barrier after it)
                     __syncwarp();
                     int arrived = 0;
                     if (lane == 0)
                         asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(arrived) : "l"(&p.pcnt[tidx * 4 + g]) : "memory");
                     arrived = __shfl_sync(0xffffffffu, arrived, 0);
+                    __syncwarp();
                     finish = arrived == 1;
                     if (finish) {
                         const float* other = p.pbuf + ((size_t)(tidx * 2 + (1 - half)) * 2 * KT) * kBM + lrow;
