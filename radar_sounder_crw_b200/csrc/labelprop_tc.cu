@@ -526,7 +526,10 @@ lp_topk_tc_kernel(const __grid_constant__ CUtensorMap qmap_hi, const __grid_cons
                                 }
                             }
                     }
-                    tc::umma_commit(&k_empty[s]);     // smem stage may be refilled once these MMAs retire
+                    // (timing aid, debug bit 8 of the second byte = 256, results INVALID: hand the stage back at once, so the key
+                    // stream never waits for MMAs -- tells a dependency between the two apart from a shared resource)
+                    if (p.debug & 256) tc::mbar_arrive(&k_empty[s]);
+                    else tc::umma_commit(&k_empty[s]);     // smem stage may be refilled once these MMAs retire
                     tc::umma_commit(&acc_full[a]);    // accumulator ready for the epilogue
                 }
                 __syncwarp();
