@@ -400,9 +400,9 @@ def bench_labelprop(crw, args, rank, world, pk):
                  h2d_bytes_per_step=int(feats_host.numel() * 4), d2h_bytes_per_step=int(R * Tl * Nl * 4)),
         roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
                       # dram__bytes_read.sum + dram__bytes_write.sum of lp_topk_tc_kernel (the bulk launch, 470 of 479 tiles),
-                      # one `ncu --set full` capture at config 3 (profiles/r01_ncu_full_lp_topk_tc_final_raw.csv):
-                      # 31.37 MB read, 0 written back before exit
-                      traffic=(31370240 if (not cfg5 and args.lp_precision != "fp32") else None),
+                      # one `ncu --set full` capture at config 3 (profiles/r01_ncu_full_lp_topk_tc_final2_raw.csv):
+                      # 31.40 MB read, 0 written back before exit
+                      traffic=(31401216 if (not cfg5 and args.lp_precision != "fp32") else None),
                       kernel="lp_prep_bf16 + lp_topk_tc_kernel (tcgen05 bf16x3) + gather kernels" if args.lp_precision != "fp32"
                       else "l2_normalize + lp_topk_f32_kernel + gather kernels", algorithmic_bytes=lp_bytes,
                       peak_source=pk["src"],
