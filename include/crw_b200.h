@@ -39,6 +39,8 @@ extern "C" {
 #define CRW_PREC_FP32 0        /* fp32 FMA, pinned order: bit-comparable with oracle/crw_oracle.c */
 #define CRW_PREC_BF16X3 1      /* tcgen05 kind::f16, error-compensated bf16 hi/lo (3 MMAs), fp32 accumulate */
 #define CRW_PREC_TF32 2        /* tcgen05 kind::tf32 (walk GEMMs), fp32 accumulate */
+#define CRW_PREC_TC_EXACT 3    /* label propagation only: one tcgen05 fp16 pass FILTERS the candidates with a proven margin, the
+                                  survivors are re-scored in fp32 in the pinned order -- results bit-identical to CRW_PREC_FP32 */
 
 /* label-propagation gather modes */
 #define CRW_LP_REF_EXACT 0     /* reproduce the reference's context-trim gather quirk */

@@ -672,6 +672,16 @@ int lp_tc_prep_rows(const float* stage, int64_t row_begin, int64_t nrows, int64_
 int lp_tc_launch_tiles(const void* plan_storage, int rg, int ta, int tb, int max_ctas, cudaStream_t st);
 int lp_tc_tiles_per_rg(const void* plan_storage);
 int lp_tc_tile_rows(const void* plan_storage);
+// exact tensor path (labelprop_x.cu): prep + plan, then filter + refine launches over ranges of schedule slots
+struct LpXPlanStorage { alignas(64) unsigned char bytes[1024]; };
+size_t lp_x_plan_bytes();
+size_t lp_x_scratch_bytes(int R, int T, int N, int C, int k, int do_normalize);
+int lp_x_max_k();
+int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize, float* W,
+                 int32_t* I, void* scratch, int sms, cudaStream_t st, void* plan_storage, size_t plan_bytes);
+int lp_x_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st);
+int lp_x_total_slots(const void* plan_storage);
+int lp_x_early_slots(const void* plan_storage);
 }
 
 // A second, higher-priority stream and two events per device, created on first use: the tensor path forks the early query
@@ -686,6 +696,11 @@ struct SideCtx {
     bool ok = false;
     std::mutex mu;
 };
+// environment switches are read once per process
+bool env_no_fork() {
+    static const bool v = [] { const char* e = getenv("CRW_LP_NO_FORK"); return e && atoi(e) != 0; }();
+    return v;
+}
 SideCtx* side_ctx() {
     static SideCtx ctx[64];
     static std::once_flag once[64];
@@ -711,6 +726,7 @@ extern "C" size_t crw_labelprop_scratch_bytes(int R, int T, int N, int C, int k,
                                               int have_topk_out) {
     size_t b = 0;
     if (precision == CRW_PREC_BF16X3) b += align_up((size_t)R * T * N * C * 2 * 2, 256) + align_up(crw::lp_tc_split_bytes(), 256);   // bf16 hi + lo, tail-split lists
+    else if (precision == CRW_PREC_TC_EXACT) b += align_up(crw::lp_x_scratch_bytes(R, T, N, C, k, do_normalize), 256);
     else if (do_normalize) b += align_up((size_t)R * T * N * C * sizeof(float), 256);
     if (!have_topk_out) b += 2 * align_up((size_t)R * T * k * N * sizeof(float), 256);
     return b + 256;
@@ -752,8 +768,7 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         const int total = lp_tc_total_slots(plan.bytes), early = lp_tc_early_slots(plan.bytes);
         // fork only when there is something to overlap: ref_exact mode (later frames do not depend on each other), query
         // tiles beyond the early ones, and few enough early tiles that they are a side job
-        const char* nofork = getenv("CRW_LP_NO_FORK");
-        SideCtx* sc = (gp.mode_fixed || early >= total || early > sms / 2 || (nofork && atoi(nofork))) ? nullptr : side_ctx();
+        SideCtx* sc = (gp.mode_fixed || early >= total || early > sms / 2 || env_no_fork()) ? nullptr : side_ctx();
         if (!sc) {
             if ((rc = lp_tc_launch(plan.bytes, 0, total, sms, st, true)) != CRW_OK) return rc;
             if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
@@ -767,6 +782,44 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
         if ((rc = lp_tc_launch(plan.bytes, 0, early, sms, sc->s2, false)) != CRW_OK) return rc;     // frames 1..ctx+1 (and a few more)
         if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;                              // the true recurrence
+        CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
+        CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
+        return gather_launch_par(gp, st);
+    }
+    if (precision == CRW_PREC_TC_EXACT) {
+        if (ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f) || (int64_t)N < k) return CRW_ERR_INVALID;
+        void* xs = sp;
+        sp += align_up(lp_x_scratch_bytes(R, T, N, C, k, do_normalize), 256);
+        float* Wt = W_or_null;
+        int32_t* It = I_or_null;
+        if (!Wt) {
+            Wt = reinterpret_cast<float*>(sp);
+            sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+            It = reinterpret_cast<int32_t*>(sp);
+        }
+        cudaStream_t st = (cudaStream_t)stream;
+        GatherParams gp;
+        int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
+        if (rc != CRW_OK) return rc;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        LpXPlanStorage plan;
+        if ((rc = lp_x_prepare(feats, R, T, N, C, ctx, radius, temp, k, do_normalize, Wt, It, xs, sms, st, plan.bytes, sizeof(plan.bytes))) != CRW_OK) return rc;
+        const int total = lp_x_total_slots(plan.bytes), early = lp_x_early_slots(plan.bytes);
+        // the frames 1..ctx+1 (the only true recurrence) go to the side stream: their items, then the sequential gather
+        SideCtx* sc = (gp.mode_fixed || early >= total || early > sms / 2 || env_no_fork()) ? nullptr : side_ctx();
+        if (!sc) {
+            if ((rc = lp_x_launch(plan.bytes, 0, total, sms, st)) != CRW_OK) return rc;
+            if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
+            return gather_launch_par(gp, st);
+        }
+        std::lock_guard<std::mutex> lock(sc->mu);
+        CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));                       // prep done
+        if ((rc = lp_x_launch(plan.bytes, early, total, sms, st)) != CRW_OK) return rc;
+        CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
+        if ((rc = lp_x_launch(plan.bytes, 0, early, sms, sc->s2)) != CRW_OK) return rc;
+        if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;
         CRW_CUDA_RET(cudaEventRecord(sc->ev_join, sc->s2));
         CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_join, 0));
         return gather_launch_par(gp, st);

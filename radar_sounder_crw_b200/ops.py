@@ -12,7 +12,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import PREC_FP32, PREC_BF16X3, PREC_TF32, LP_REF_EXACT, LP_FIXED  # noqa: F401
+from ._lib import PREC_FP32, PREC_BF16X3, PREC_TF32, PREC_TC_EXACT, LP_REF_EXACT, LP_FIXED  # noqa: F401
 
 
 def _stream() -> int:

@@ -1,0 +1,131 @@
+// Profiling aid (standalone): L2 -> SM bandwidth on B200 for the access patterns the label-propagation refine step can use.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o l2_probe l2_probe.cu && ./l2_probe
+// A 31 MB buffer (config 3's fp32 features) stays L2 resident; every kernel reads `rows_per_thread_or_warp` rows of 512 B.
+//   stream   : coalesced LDG.128 grid-stride over the whole buffer (upper bound for LDG)
+//   warprow  : one warp reads one pseudo-random 512 B row per step (lane = 16 B)
+//   lanerow  : one LANE reads one pseudo-random 512 B row per step (32 x LDG.128, 32 different rows per warp instruction)
+//   bulk     : cp.async.bulk global -> shared of 16 KB chunks, 4 in flight per CTA (the TMA path)
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+
+__global__ void __launch_bounds__(256) k_stream(const float4* __restrict__ buf, size_t n4, int reps, float* out) {
+    float acc = 0.f;
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = __ldcg(buf + ((i + (size_t)r * 977) % n4));
+            acc += v.x + v.y + v.z + v.w;
+        }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_warprow(const float4* __restrict__ buf, uint32_t rows, int steps, float* out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < steps; ++s) {
+        const uint32_t row = hash32(gw * 7919u + s) % rows;
+        const float4 v = __ldcg(buf + (size_t)row * 32 + lane);
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+// window > 0: rows are drawn from a window of `window` rows that moves with the CTA (models the key window of one query frame)
+__global__ void __launch_bounds__(256) k_lanerow(const float4* __restrict__ buf, uint32_t rows, int steps, uint32_t window, float* out) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc = 0.f;
+    for (int s = 0; s < steps; ++s) {
+        uint32_t row;
+        if (window) row = ((uint32_t)(((uint64_t)blockIdx.x * rows) / gridDim.x) + hash32(gt * 7919u + s) % window) % rows;
+        else row = hash32(gt * 7919u + s) % rows;
+        const float4* p = buf + (size_t)row * 32;
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {            // the sequential chain of the exact dot product
+            const float4 v = __ldg(p + c);
+            a = fmaf(v.x, 1.0001f, a); a = fmaf(v.y, 1.0002f, a); a = fmaf(v.z, 1.0003f, a); a = fmaf(v.w, 1.0004f, a);
+        }
+        acc += a;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(128) k_bulk(const uint8_t* __restrict__ buf, size_t bytes, int chunks_per_cta, float* out) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    constexpr int kChunk = 16384, kDepth = 8;
+    __shared__ uint64_t bar[kDepth];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDepth; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t nchunks = bytes / kChunk;
+    if (threadIdx.x == 0) {
+        auto issue = [&](int c) {
+            const int s = c % kDepth;
+            const size_t ch = (hash32(blockIdx.x * 1000003u + c)) % nchunks;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(kChunk) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sm + s * kChunk)),
+                         "l"(buf + ch * kChunk), "r"(kChunk), "r"(smem_u32(&bar[s]))
+                         : "memory");
+        };
+        for (int c = 0; c < kDepth && c < chunks_per_cta; ++c) issue(c);
+        for (int c = 0; c < chunks_per_cta; ++c) {
+            const int s = c % kDepth;
+            const uint32_t parity = (c / kDepth) & 1;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}" ::"r"(
+                    smem_u32(&bar[s])),
+                "r"(parity)
+                : "memory");
+            if (c + kDepth < chunks_per_cta) issue(c + kDepth);
+        }
+        if (sm[5] == 77 && sm[9] == 78 && sm[100] == 3) out[0] = 1.f;
+    }
+}
+
+int main() {
+    const size_t bytes = 31360000;          // 1250 x 49 rows x 512 B
+    const uint32_t rows = bytes / 512;
+    uint8_t* buf; float* out;
+    CK(cudaMalloc(&buf, bytes)); CK(cudaMalloc(&out, 64));
+    CK(cudaMemset(buf, 1, bytes));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    auto report = [&](const char* name, double moved_bytes, float ms) { printf("%-28s %8.1f MB in %7.1f us  -> %7.2f TB/s\n", name, moved_bytes / 1e6, ms * 1e3, moved_bytes / (ms * 1e-3) / 1e12); };
+    float ms;
+    for (int occ : {4, 8}) {
+        const int reps = 10;
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_stream<<<sms * occ, 256>>>((const float4*)buf, bytes / 16, reps, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        char nm[64]; snprintf(nm, 64, "stream LDG.128 occ%d", occ); report(nm, (double)bytes * reps, ms);
+    }
+    for (int occ : {4, 8}) {
+        const int steps = 256;
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_warprow<<<sms * occ, 256>>>((const float4*)buf, rows, steps, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        char nm[64]; snprintf(nm, 64, "warp-per-row gather occ%d", occ); report(nm, (double)sms * occ * 8 * steps * 512, ms);
+    }
+    for (uint32_t window : {0u, 1100u}) for (int occ : {2, 4, 8}) {
+        const int steps = 12;
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_lanerow<<<sms * occ, 256>>>((const float4*)buf, rows, steps, window, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        char nm[64]; snprintf(nm, 64, "lane-per-row chain w%u occ%d", window, occ); report(nm, (double)sms * occ * 256 * steps * 512, ms);
+    }
+    {
+        const int chunks = 512;
+        CK(cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384));
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_bulk<<<sms, 128, 8 * 16384>>>(buf, bytes, chunks, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        report("cp.async.bulk 16 KB x8 deep", (double)sms * chunks * 16384, ms);
+    }
+    printf("done\n");
+    return 0;
+}
