@@ -22,10 +22,16 @@ import types
 import torch
 
 REF_ROOT = os.environ.get("CRW_REFERENCE_ROOT", "/root/reference")
+# bench.py's reference arm times the reference on the HOST cores of a GPU box: the 'cuda' literals are mapped to CPU there too
+FORCE_CPU = bool(os.environ.get("CRW_REFERENCE_FORCE_CPU"))
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "src", "model.py"))
+
+
+def _on_cpu() -> bool:
+    return FORCE_CPU or not torch.cuda.is_available()
 
 
 def _stub_modules():
@@ -67,7 +73,7 @@ def load():
         import dataset as ref_dataset
         from imported import labelprop as ref_labelprop
         from imported import maskedatt as ref_maskedatt
-    if not torch.cuda.is_available():
+    if _on_cpu():
         # model.py:36 -- zeros(..., device='cuda')
         ref_model.zeros = lambda *a, device=None, **k: torch.zeros(*a, **k)
     _loaded.update(model=ref_model, utils=ref_utils, encoder=ref_encoder, dataset=ref_dataset,
@@ -78,7 +84,7 @@ def load():
 @contextlib.contextmanager
 def cpu_device_patches():
     """Map every hard-coded 'cuda' in ``propagate``/``predict`` to CPU for the duration."""
-    if torch.cuda.is_available():
+    if not _on_cpu():
         yield
         return
     orig_zeros, orig_to, orig_cuda = torch.zeros, torch.Tensor.to, torch.Tensor.cuda

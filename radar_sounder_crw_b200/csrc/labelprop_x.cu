@@ -31,12 +31,15 @@ namespace crw {
 // ------------------------------------------------------------------------------------------
 constexpr float kXScale = 256.0f;            // fp16 plane holds 256 * xn: keeps small components out of the subnormal range
 
+constexpr int kXStatSlots = 32;           // the per-call maxima are spread over 32 slots (fewer same-address atomics), reduced by the filter
+
 __global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict__ x, int64_t rows, int do_normalize,
                                                         float* __restrict__ xn, __half* __restrict__ h, unsigned* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float max_n2 = 0.0f, max_e2 = 0.0f;
-    for (int64_t row = warp0; row < rows; row += nwarps) {
+    __shared__ float s_n2[8], s_e2[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    float n2 = 0.0f, e2 = 0.0f;
+    if (row < rows) {
         const float* xr = x + row * 128;
         float v[4];
 #pragma unroll
@@ -50,7 +53,6 @@ __global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict_
 #pragma unroll
             for (int m = 0; m < 4; ++m) v[m] = __fdiv_rn(v[m], d);
         }
-        float n2 = 0.0f, e2 = 0.0f;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const __half hv = __float2half_rn(v[m] * kXScale);
@@ -60,14 +62,20 @@ __global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict_
             h[row * 128 + lane + 32 * m] = hv;
             if (xn) xn[row * 128 + lane + 32 * m] = v[m];
         }
-        n2 = warp_sum(n2);
-        e2 = warp_sum(e2);
-        max_n2 = fmaxf(max_n2, n2);
-        max_e2 = fmaxf(max_e2, e2);
+        // one butterfly for both sums: the pair travels together
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
     }
-    if (lane == 0) {                 // non-negative floats order like their bit patterns
-        atomicMax(&stats[0], __float_as_uint(max_n2));
-        atomicMax(&stats[1], __float_as_uint(max_e2));
+    if (lane == 0) { s_n2[warp] = n2; s_e2[warp] = e2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {          // non-negative floats order like their bit patterns
+        float a = 0.0f, b2 = 0.0f;
+        for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_n2[w]); b2 = fmaxf(b2, s_e2[w]); }
+        atomicMax(&stats[2 * (blockIdx.x % kXStatSlots)], __float_as_uint(a));
+        atomicMax(&stats[2 * (blockIdx.x % kXStatSlots) + 1], __float_as_uint(b2));
     }
 }
 
@@ -78,10 +86,10 @@ constexpr int kXBM = 128;                    // query rows per tile (TMEM lanes)
 constexpr int kXBN = 64;                     // key rows per stage (TMEM columns per accumulator)
 constexpr int kXG = 4;                       // query tiles per item (share the key stream)
 constexpr int kXStageBytes = 16384;          // key tile [kblock 0,1][64 rows][128 B]  or  half a query tile [128 rows][128 B]
-constexpr int kXStages = 8;
+constexpr int kXStages = 5;
 constexpr int kXEpi = 16;                    // epilogue warps
 constexpr int kXCap = 32;                    // appended-survivor slots per thread between two flushes
-constexpr int kXThreads = (kXEpi + 2) * 32;
+constexpr int kXThreads = (kXEpi + 2) * 32;         // 16 epilogue warps, the TMA producer, the MMA issuer
 constexpr int kXColBits = 12;                // packed key: value << 12 | stream column (key tile * 64 + column)
 constexpr float kXFixBias = 278528.0f;       // (dot + 1.0625) * 2^18 with a = 65536 dot:  fix = 4 a + 278528
 constexpr float kXFixMagic = 12582912.0f;    // 1.5 * 2^23: float -> integer in the low mantissa bits
@@ -173,6 +181,24 @@ __device__ __forceinline__ unsigned long long x_band_mask(int row0, int nrows, i
     if (nrows < 64) m &= (1ull << nrows) - 1ull;
     return m;
 }
+// closed form for 32 <= N <= 64 (at most three frames meet a 64-row key tile): the band is the N-periodic pattern P (bits lo_q ..
+// lo_q + w_q - 1) read from phase row0 mod N; the window is frame 0 plus the run of rows [win_lo N, n N)
+__device__ __forceinline__ unsigned long long x_shl64(unsigned long long x, int s) { return (s >= 0 && s < 64) ? (x << s) : 0ull; }
+__device__ __forceinline__ unsigned long long x_run64(int lo, int hi) {      // bits [lo, hi) of a 64-bit word, any lo / hi
+    lo = max(lo, 0);
+    hi = min(hi, 64);
+    if (lo >= hi) return 0ull;
+    const unsigned long long upto = (hi >= 64) ? ~0ull : ((1ull << hi) - 1ull);
+    return upto & ~((1ull << lo) - 1ull);
+}
+__device__ __forceinline__ unsigned long long x_band_mask_fast(int row0, int nrows, int N, unsigned magic_n, int n, int win_lo, int lo_q,
+                                                               unsigned long long mq) {
+    const int kf0 = (int)__umulhi((unsigned)row0, magic_n), phi = row0 - kf0 * N;
+    const unsigned long long P = mq << lo_q;                                  // lo_q + w_q <= N <= 64
+    const unsigned long long band = (P >> phi) | x_shl64(P, N - phi) | x_shl64(P, 2 * N - phi);
+    const unsigned long long win = x_run64(-row0, N - row0) | x_run64(win_lo * N - row0, n * N - row0);
+    return band & win & x_run64(0, nrows);
+}
 // generic form (any band width)
 __device__ __forceinline__ unsigned long long x_band_mask_wide(int row0, int nrows, int N, unsigned magic_n, int n, int win_lo, int q, int rb) {
     unsigned long long m = 0ull;
@@ -192,6 +218,13 @@ __device__ __forceinline__ unsigned long long x_band_mask_wide(int row0, int nro
     return m;
 }
 
+// profiling aid (CRW_TC_DEBUG bit 3 = 8): cycles per phase, summed per (CTA, warp).  [kernel 0 = filter, 1 = refine][CTA][warp 0..17][8]
+//   filter epilogue: [0] wait for an accumulator [1] validity mask [2] TMEM loads + scan [3] flushes [4] final list -> global [5] item total
+//   refine:          [0] metadata staging [1] wait (producer: empty slot; consumer: full slot) [2] producer issue / consumer chain
+//                    [3] rank + finish [4] full rescans [5] chunk total
+__device__ unsigned long long g_x_prof[2 * 160 * 18 * 8];
+#define XPROF(kern, idx, cyc) do { if (prof && lane == 0) atomicAdd(&g_x_prof[(((kern) * 160 + (blockIdx.x % 160)) * 18 + warp) * 8 + (idx)], (unsigned long long)(cyc)); } while (0)
+
 template <int KL>
 __device__ __forceinline__ void x_list_insert(uint32_t (&L)[KL], uint32_t P) {
 #pragma unroll
@@ -206,20 +239,33 @@ __device__ __forceinline__ float x_threshold(uint32_t theta, int m_fix) {
     return ((float)max(X, 0) - kXFixBias) * 0.25f;
 }
 
-// 16 columns of a key tile: branch-free append of the values that beat the bound and are valid (window x band)
-template <int I0>
-__device__ __forceinline__ void x_scan16(const float (&val)[32], uint32_t vbits, uint32_t colbase, float thr, uint32_t app, int& cnt) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float a = val[I0 + i];
-        const bool ok = ((vbits >> (I0 + i)) & 1u) && (a >= thr);
-        const float tf = __fmaf_rn(a, 4.0f, kXFixBias + kXFixMagic);
-        const uint32_t P = (__float_as_uint(tf) << kXColBits) | (colbase + (uint32_t)(I0 + i));
-        if (ok) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(app + cnt * 128), "r"(P) : "memory");
-            ++cnt;
-        }
+// 16 columns of a key tile: branch-free append of the values that beat the bound and are valid (window x band).
+// Per value: validity bit -> predicate, compare, column id, predicated 8-byte store (raw value, column), predicated slot advance.
+// Written as PTX so that the per-value work stays at these five instructions (the fixed-point packing happens at flush time).
+template <int I, int END>
+struct XScan {
+    static __device__ __forceinline__ void run(const float (&val)[32], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
+        asm volatile(
+            "{\n\t.reg .pred p, v;\n\t.reg .b32 t, c;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 v, t, 0;\n\t"
+            "setp.ge.and.f32 p, %3, %4, v;\n\t"
+            "or.b32 c, %5, %6;\n\t"
+            "@p st.shared.v2.b32 [%0], {%7, c};\n\t"
+            "@p add.u32 %0, %0, 256;\n\t}"
+            : "+r"(ptr)
+            : "r"(vbits), "n"(1u << I), "f"(val[I]), "f"(thr), "r"(colbase), "n"(I), "r"(__float_as_uint(val[I]))
+            : "memory");
+        XScan<I + 1, END>::run(val, vbits, colbase, thr, ptr);
     }
+};
+template <int END>
+struct XScan<END, END> {
+    static __device__ __forceinline__ void run(const float (&)[32], uint32_t, uint32_t, float, uint32_t&) {}
+};
+template <int I0>
+__device__ __forceinline__ void x_scan16(const float (&val)[32], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
+    XScan<I0, I0 + 16>::run(val, vbits, colbase, thr, ptr);
 }
 
 template <int KT, int KL>
@@ -229,7 +275,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                                              // kXStages x 16 KB ring
-    uint32_t* sApp = reinterpret_cast<uint32_t*>(smem + kXStages * kXStageBytes);   // [16 warps][kXCap][32 lanes]
+    uint2* sApp = reinterpret_cast<uint2*>(smem + kXStages * kXStageBytes);         // [16 warps][kXCap][32 lanes] (value, column)
     __shared__ uint64_t k_full[kXStages], k_empty[kXStages], acc_full[kXG], acc_empty[kXG];
     __shared__ uint32_t tmem_base_s;
 
@@ -321,7 +367,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 #pragma unroll
                 for (int g = 0; g < kXG; ++g) {
                     if (!x_needs(p, qt[g], row0, nrows)) continue;
-                    tc::mbar_wait_backoff(&acc_empty[g], ((ucnt[g]) & 1) ^ 1);
+                    tc::mbar_wait(&acc_empty[g], ((ucnt[g]) & 1) ^ 1);
                     tc::tc_fence_after();
                     if (leader) {
                         const uint32_t d = tmem_base + 256u + (uint32_t)(g * kXBN);
@@ -345,9 +391,10 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
         // ================= epilogue: thread = query row =================
         const int g = warp >> 2, quarter = warp & 3;
         const int rb = p.rb, ctx = p.ctx;
-        const uint32_t app = tc::smem_u32(sApp + (size_t)warp * kXCap * 32) + lane * 4;
+        const uint32_t app = tc::smem_u32(sApp + (size_t)warp * kXCap * 32) + lane * 8;
         // margin from the call's maxima (see header): E = 2 eps |x| + accumulation slack, survivors within 2 E of the bound
-        const float n2 = __uint_as_float(p.stats[0]), e2 = __uint_as_float(p.stats[1]);
+        float n2 = 0.0f, e2 = 0.0f;
+        for (int i = 0; i < kXStatSlots; ++i) { n2 = fmaxf(n2, __uint_as_float(p.stats[2 * i])); e2 = fmaxf(e2, __uint_as_float(p.stats[2 * i + 1])); }
         const float nrm = sqrtf(n2) * 1.00001f, eps = sqrtf(e2) * 1.0001f + 1e-9f;
         const float E = (2.0f * eps * nrm + eps * eps + 2.5e-5f * nrm * nrm) * 1.02f;
         const int m_fix = (int)ceilf(2.0f * E * 262144.0f) + 2;
@@ -369,41 +416,46 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
             const int lo_q = max(0, q - rb), w_q = min(N - 1, q + rb) - lo_q + 1;
             const unsigned long long mq = (w_q >= 64) ? ~0ull : ((1ull << w_q) - 1ull);
             const bool wide_band = 2 * rb + 1 > 64;
+            const bool fast_mask = N >= 32 && N <= 64;
             uint32_t L[KL];
 #pragma unroll
             for (int s = 0; s < KL; ++s) L[s] = 0u;
-            int cnt = 0;
+            uint32_t ptr = app;                                   // next free append slot of this thread (slots are 256 B apart)
             float thr = -INFINITY;
             auto flush = [&]() {
+                const int cnt = (int)((ptr - app) >> 8);
                 const int maxc = __reduce_max_sync(0xffffffffu, cnt);
                 for (int i = 0; i < maxc; ++i) {
-                    uint32_t P;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(P) : "r"(app + i * 128) : "memory");
+                    uint32_t vb, col;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(vb), "=r"(col) : "r"(app + i * 256) : "memory");
+                    const float tf = __fmaf_rn(__uint_as_float(vb), 4.0f, kXFixBias + kXFixMagic);
+                    const uint32_t P = (__float_as_uint(tf) << kXColBits) | col;
                     x_list_insert<KL>(L, (i < cnt) ? P : 0u);
                 }
-                cnt = 0;
+                ptr = app;
                 thr = x_threshold(L[KT - 1], m_fix);
             };
-            auto maybe_flush = [&]() { if (__any_sync(0xffffffffu, cnt > kXCap - 16)) flush(); };
+            auto maybe_flush = [&]() { if (__any_sync(0xffffffffu, ptr > app + (kXCap - 16) * 256)) flush(); };
             for (int kt = 0; kt < t.n_kt; ++kt) {
                 int row0, nrows;
                 x_ktile_rows(p, t, kt, row0, nrows);
                 if (!x_needs(p, qt, row0, nrows)) continue;                      // warp-uniform (same test as the MMA warp)
+                unsigned long long vm = 0ull;
+                if (qvalid) vm = wide_band ? x_band_mask_wide(row0, nrows, N, p.magic_n, n, win_lo, q, rb)
+                                 : (fast_mask ? x_band_mask_fast(row0, nrows, N, p.magic_n, n, win_lo, lo_q, mq)
+                                              : x_band_mask(row0, nrows, N, p.magic_n, n, win_lo, lo_q, mq));
+                if (p.debug & 1) vm = 0ull;
                 tc::mbar_wait(&acc_full[g], ucnt & 1);
                 tc::tc_fence_after();
                 ++ucnt;
-                unsigned long long vm = 0ull;
-                if (qvalid) vm = wide_band ? x_band_mask_wide(row0, nrows, N, p.magic_n, n, win_lo, q, rb)
-                                           : x_band_mask(row0, nrows, N, p.magic_n, n, win_lo, lo_q, mq);
-                if (p.debug & 1) vm = 0ull;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u + (uint32_t)(g * kXBN);
                 float val[32];
                 if (!(p.debug & 2)) {
                     tc::tmem_ld_32x32b_x32(taddr, val);
                     tc::tmem_ld_wait();
-                    x_scan16<0>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, app, cnt);
+                    x_scan16<0>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
                     maybe_flush();
-                    x_scan16<16>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, app, cnt);
+                    x_scan16<16>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
                     maybe_flush();
                 }
                 if (nrows > 32 && !(p.debug & 2)) {
@@ -414,9 +466,9 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[g]);
                 if (nrows > 32 && !(p.debug & 2)) {
-                    x_scan16<0>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, app, cnt);
+                    x_scan16<0>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
                     maybe_flush();
-                    x_scan16<16>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, app, cnt);
+                    x_scan16<16>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
                     maybe_flush();
                 }
             }
@@ -454,12 +506,9 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // refine
 // ------------------------------------------------------------------------------------------
-constexpr int kRWarps = 8;                   // consumer warps
-constexpr int kRThreads = (kRWarps + 1) * 32;
 constexpr int kRRowBytes = 528;              // 128 floats + 16 B pad: float4 row reads of 32 lanes are conflict-free
-constexpr int kRBufRows = 34;                // 32 survivor rows + up to 2 query rows
-constexpr int kRBufBytes = kRBufRows * kRRowBytes;
-constexpr int kRBufs = 10;
+constexpr int kRChunk = 128;                 // queries per metadata chunk
+constexpr int kRMaxWarps = 16;
 
 struct RParams {
     const float* xn;         // [total_rows, 128] normalised features
@@ -472,13 +521,14 @@ struct RParams {
     long long total_rows;
     float inv_temp;
     unsigned magic_n;
+    int debug;               // timing aids (CRW_TC_DEBUG): 16 = no W / I stores, 32 = no row copies, 64 = no chains (results invalid)
 };
 
-__device__ __forceinline__ void bulk_row_copy(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
-                 "r"(bytes), "r"(tc::smem_u32(bar))
-                 : "memory");
+// one 512-byte feature row global -> shared by the whole warp (16 bytes per lane, asynchronous: cp.async / LDGSTS)
+__device__ __forceinline__ void warp_row_copy_async(uint32_t dst_row_smem, const float* src_row, int lane) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_row_smem + lane * 16), "l"(src_row + lane * 4) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 // candidate id (slot in the trimmed key set * N + node) of key row kr for query frame n
 __device__ __forceinline__ int x_cand_id(int kr, int n, int N, int ctx, unsigned magic_n) {
@@ -487,49 +537,71 @@ __device__ __forceinline__ int x_cand_id(int kr, int n, int N, int ctx, unsigned
     return slot * N + j;
 }
 
-// full exact scan of one query by one warp (list overflow: many candidates tie within the filter margin).  Candidates in ascending id
-// order, lane i holds the i-th best -- the insertion of lp_topk_f32_kernel.  Returns this lane's (logit, id); live = entries found.
-__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, int n, int q, int k, float& v_out, int& id_out) {
+// the oracle's dot product: sequential fmaf chain over the 128 channels of two staged rows
+__device__ __forceinline__ float x_chain_dot(const uint8_t* krow_smem, const uint8_t* qrow_smem) {
+    const float4* krow = reinterpret_cast<const float4*>(krow_smem);
+    const float4* qrow = reinterpret_cast<const float4*>(qrow_smem);
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 kv = krow[c4], qv = qrow[c4];
+        acc = __fmaf_rn(kv.x, qv.x, acc);
+        acc = __fmaf_rn(kv.y, qv.y, acc);
+        acc = __fmaf_rn(kv.z, qv.z, acc);
+        acc = __fmaf_rn(kv.w, qv.w, acc);
+    }
+    return acc;
+}
+
+// Full exact scan of one query by one warp (its survivor list overflowed: many candidates tie within the filter margin).  The
+// in-band candidates are visited in ascending id order, 32 at a time through the warp's staging buffer; lane i keeps the i-th
+// best (the insertion of lp_topk_f32_kernel).  Returns this lane's (logit, id).
+template <int CAP>
+__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, uint8_t* buf, int n, int q, int k, float& v_out, int& id_out) {
+    constexpr int kStep = CAP < 32 ? CAP : 32;      // candidates per round
     const int lane = threadIdx.x & 31;
     const int N = p.N, rb = p.rb;
-    const float* qrow = xr + ((size_t)n * N + q) * 128;
     const int F = n_key_frames(n, p.ctx);
     const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     float v = -INFINITY;
     int id = 0;
     float thr = -INFINITY;
     const int jlo = max(0, q - rb), jhi = min(N - 1, q + rb), bw = jhi - jlo + 1;
-    for (int f = 0; f < F; ++f) {
-        const float* kf = xr + (size_t)key_frame(n, p.ctx, f) * N * 128;
-        for (int j0 = 0; j0 < bw; j0 += 32) {
-            const int j = jlo + j0 + lane;
-            const bool ok = (j0 + lane) < bw;
-            float cand = -INFINITY;
-            if (ok) {
-                const float* kv = kf + (size_t)j * 128;
-                float acc = 0.0f;
-                for (int c = 0; c < 128; ++c) acc = __fmaf_rn(kv[c], qrow[c], acc);
-                cand = __fmul_rn(acc, p.inv_temp);
-            }
-            const int cid = f * N + j;
-            unsigned m = __ballot_sync(0xffffffffu, ok && cand > thr);
-            while (m) {
-                const int s = __ffs(m) - 1;
-                m &= m - 1;
-                const float c = __shfl_sync(0xffffffffu, cand, s);
-                const int ci = __shfl_sync(0xffffffffu, cid, s);
-                if (c > thr) {
-                    const int pos = __popc(__ballot_sync(0xffffffffu, v >= c) & kmask);
-                    const float vup = __shfl_up_sync(0xffffffffu, v, 1);
-                    const int iup = __shfl_up_sync(0xffffffffu, id, 1);
-                    if (lane > pos) { v = vup; id = iup; }
-                    else if (lane == pos) { v = c; id = ci; }
-                    if (lane >= k) v = -INFINITY;
-                    thr = __shfl_sync(0xffffffffu, v, k - 1);
-                }
+    const uint32_t sbuf = tc::smem_u32(buf);
+    warp_row_copy_async(sbuf + CAP * kRRowBytes, xr + ((size_t)n * N + q) * 128, lane);
+    const int total = F * bw;                          // in-band candidates, ascending id = (frame slot, node)
+    for (int c0 = 0; c0 < total; c0 += kStep) {
+        const int nrow = min(kStep, total - c0);
+        __syncwarp();
+        for (int r = 0; r < nrow; ++r) {
+            const int cc = c0 + r, f = cc / bw, jj = cc - f * bw;
+            warp_row_copy_async(sbuf + r * kRRowBytes, xr + ((size_t)key_frame(n, p.ctx, f) * N + jlo + jj) * 128, lane);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const bool ok = lane < nrow;
+        float cand = -INFINITY;
+        if (ok) cand = __fmul_rn(x_chain_dot(buf + lane * kRRowBytes, buf + CAP * kRRowBytes), p.inv_temp);
+        const int cc = c0 + lane, fl = cc / bw;
+        const int cid = fl * N + jlo + (cc - fl * bw);
+        unsigned m = __ballot_sync(0xffffffffu, ok && cand > thr);
+        while (m) {
+            const int s = __ffs(m) - 1;
+            m &= m - 1;
+            const float c = __shfl_sync(0xffffffffu, cand, s);
+            const int ci = __shfl_sync(0xffffffffu, cid, s);
+            if (c > thr) {
+                const int pos = __popc(__ballot_sync(0xffffffffu, v >= c) & kmask);
+                const float vup = __shfl_up_sync(0xffffffffu, v, 1);
+                const int iup = __shfl_up_sync(0xffffffffu, id, 1);
+                if (lane > pos) { v = vup; id = iup; }
+                else if (lane == pos) { v = c; id = ci; }
+                if (lane >= k) v = -INFINITY;
+                thr = __shfl_sync(0xffffffffu, v, k - 1);
             }
         }
     }
+    __syncwarp();
     v_out = v;
     id_out = id;
 }
@@ -559,129 +631,162 @@ __device__ __forceinline__ void x_finish_group(const RParams& p, float v, int id
         for (int j = 1; j < k; ++j) ssum = __fadd_rn(ssum, es[j]);
     }
     __syncwarp();
-    if (w) {
+    if (w && !(p.debug & 16)) {
         const size_t o = ((size_t)(rg * p.T + n) * k + sl) * N + q;
         p.W[o] = __fdiv_rn(e, ssum);
         p.I[o] = id;
     }
 }
 
-// SL = survivor slots per query handled by one lane group (16: two queries per buffer; 32: one query per buffer)
-template <int SL>
-__global__ void __launch_bounds__(kRThreads, 1) lp_refine_kernel(RParams p) {
-    constexpr int QPB = 32 / SL;             // queries per buffer
+// SL = survivor slots per query handled by one lane group (16: two queries per pass; 32: one query per pass); WARPS autonomous
+// warps per CTA, each with a staging buffer of SROWS feature rows (the last 32 / SL of them hold the query rows).
+// A CTA owns a contiguous range of query rows and walks it in chunks of kRChunk queries: all threads first stage the chunk's
+// survivor lists (counts + key rows) in shared memory with coalesced loads.  Then every warp works on its own passes: the fp32
+// rows of the survivors (and the query rows) are copied into the warp's staging buffer with cp.async, one coalesced 512-byte
+// row per instruction, packed in survivor order; each lane then runs the sequential chain for its own survivor slot from
+// shared memory.  The bytes in flight per SM (what bounds this gather) are WARPS x ~11 rows x 512 B.
+template <int SL, int WARPS, int SROWS>
+__global__ void __launch_bounds__(WARPS * 32, 1) lp_refine_kernel(RParams p) {
+    constexpr int QPB = 32 / SL;             // queries per pass
+    constexpr int kCapRows = SROWS - QPB;    // survivor rows one pass can stage
+    constexpr int kBufBytes = SROWS * kRRowBytes;
+    constexpr int kThreads = WARPS * 32;
     extern __shared__ __align__(128) uint8_t rsm[];
-    __shared__ uint64_t full[kRBufs], empty[kRBufs];
-    __shared__ float es_all[kRWarps][2][32];
-    __shared__ float sc_v[kRWarps][32];
-    __shared__ int sc_i[kRWarps][32];
+    __shared__ float es_all[WARPS][2][32];
+    __shared__ float sc_v[WARPS][32];
+    __shared__ int sc_i[WARPS][32];
+    __shared__ int s_cnt[kRChunk];
+    int* s_kr = reinterpret_cast<int*>(rsm + (size_t)WARPS * kBufBytes);      // [SL][kRChunk]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, k = p.k;
-    if (tid == 0) {
-        for (int b = 0; b < kRBufs; ++b) { tc::mbar_init(&full[b], 1); tc::mbar_init(&empty[b], 1); }
-        tc::fence_barrier_init();
-    }
-    __syncthreads();
+    // this CTA's share of the launch: rows [r_lo, r_hi) of the flattened (radargram, row in [row_begin, row_end)) space
     const int rows_launch = p.row_end - p.row_begin;
-    const int bufs_rg = ceil_div(rows_launch, QPB);
-    const long long total_bufs = (long long)p.R * bufs_rg;
-    // contiguous share of the buffers per CTA
-    const long long per = (total_bufs + gridDim.x - 1) / gridDim.x;
-    const long long b_lo = (long long)blockIdx.x * per, b_hi = min(total_bufs, b_lo + per);
+    const long long total_q = (long long)p.R * rows_launch;
+    long long per = (total_q + gridDim.x - 1) / gridDim.x;
+    per = (per + QPB - 1) / QPB * QPB;
+    const long long r_lo = (long long)blockIdx.x * per, r_hi = min(total_q, r_lo + per);
+    const int ql = lane / SL, s = lane % SL, sub_base = ql * SL;
+    const bool prof = (p.debug & 8) != 0;
+    uint8_t* buf = rsm + (size_t)warp * kBufBytes;
+    const uint32_t sbuf = tc::smem_u32(buf);
 
-    if (warp == kRWarps) {
-        // ================= producer: one bulk copy per survivor row (lane = slot) =================
-        const int ql = lane / SL, s = lane % SL;
-        for (long long i = b_lo; i < b_hi; ++i) {
-            const int slot = (int)((i - b_lo) % kRBufs);
-            const uint32_t par = (uint32_t)(((i - b_lo) / kRBufs) & 1);
-            tc::mbar_wait_backoff(&empty[slot], par ^ 1);
-            const int rg = (int)(i / bufs_rg), bi = (int)(i - (long long)rg * bufs_rg);
-            const int row = p.row_begin + bi * QPB + ql;
-            const size_t grow = (size_t)rg * p.rows_rg + row;
-            int c = 0;
-            if (row < p.row_end) c = p.cnt[grow];
-            const bool rescan = (c >> 30) & 1;
-            c = rescan ? 0 : (c & 0xffff);
-            const bool valid = s < c;
-            const int kr = valid ? p.surv[(size_t)s * p.total_rows + grow] : 0;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            const unsigned qmask = __ballot_sync(0xffffffffu, s == 0 && c > 0);
-            const uint32_t bytes = (uint32_t)(__popc(vmask) + __popc(qmask)) * 512u;
-            uint8_t* buf = rsm + (size_t)slot * kRBufBytes;
-            if (lane == 0) {
-                if (bytes) tc::mbar_arrive_expect_tx(&full[slot], bytes);
-                else tc::mbar_arrive(&full[slot]);
-            }
-            __syncwarp();
-            if (valid) bulk_row_copy(tc::smem_u32(buf + lane * kRRowBytes), p.xn + ((size_t)rg * p.rows_rg + kr) * 128, 512u, &full[slot]);
-            if (s == 0 && c > 0) bulk_row_copy(tc::smem_u32(buf + (32 + ql) * kRRowBytes), p.xn + grow * 128, 512u, &full[slot]);
-        }
-    } else {
-        // ================= consumers: lane = survivor slot; sequential fmaf chain, exact selection =================
-        const int ql = lane / SL, s = lane % SL, sub_base = ql * SL;
-        for (long long i = b_lo + warp; i < b_hi; i += kRWarps) {
-            const int slot = (int)((i - b_lo) % kRBufs);
-            const uint32_t par = (uint32_t)(((i - b_lo) / kRBufs) & 1);
-            const int rg = (int)(i / bufs_rg), bi = (int)(i - (long long)rg * bufs_rg);
-            const int row = p.row_begin + bi * QPB + ql;
-            const size_t grow = (size_t)rg * p.rows_rg + row;
-            const int n = row / N, q = row - n * N;
-            int c = 0;
-            if (row < p.row_end) c = p.cnt[grow];
-            const bool rescan = (c >> 30) & 1;
-            c = rescan ? 0 : (c & 0xffff);
-            const bool valid = s < c;
-            const int kr = valid ? p.surv[(size_t)s * p.total_rows + grow] : 0;
-            tc::mbar_wait(&full[slot], par);
-            const uint8_t* buf = rsm + (size_t)slot * kRBufBytes;
-            float acc = 0.0f;
-            if (valid) {
-                const float4* krow = reinterpret_cast<const float4*>(buf + lane * kRRowBytes);
-                const float4* qrow = reinterpret_cast<const float4*>(buf + (32 + ql) * kRRowBytes);
-#pragma unroll 8
-                for (int c4 = 0; c4 < 32; ++c4) {
-                    const float4 kv = krow[c4], qv = qrow[c4];
-                    acc = __fmaf_rn(kv.x, qv.x, acc);
-                    acc = __fmaf_rn(kv.y, qv.y, acc);
-                    acc = __fmaf_rn(kv.z, qv.z, acc);
-                    acc = __fmaf_rn(kv.w, qv.w, acc);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&empty[slot]);             // the buffer may be refilled
-            const float lg = valid ? __fmul_rn(acc, p.inv_temp) : -INFINITY;
-            const int id = valid ? x_cand_id(kr, n, N, p.ctx, p.magic_n) : 0x7fffffff;
-            // rank among the query's survivors: (logit desc, id asc)
-            int rank = 0;
+    for (long long c0 = r_lo; c0 < r_hi; c0 += kRChunk) {
+        const int nq = (int)min((long long)kRChunk, r_hi - c0);
+        const long long c_s0 = prof ? clock64() : 0;
+        // ---- stage the chunk's metadata: every thread issues its loads back to back (independent, coalesced along the rows) ----
+        const int rg0 = (int)(c0 / rows_launch);
+        const int row0 = p.row_begin + (int)(c0 - (long long)rg0 * rows_launch);        // chunk row i: row0 + i, wrapping into the next radargram
+        {
+            constexpr int kPer = (SL * kRChunk + kThreads - 1) / kThreads;
+            int vals[kPer];
 #pragma unroll
-            for (int o = 0; o < SL; ++o) {
-                const float lo_ = __shfl_sync(0xffffffffu, lg, sub_base + o);
-                const int io = __shfl_sync(0xffffffffu, id, sub_base + o);
-                rank += (lo_ > lg || (lo_ == lg && io < id)) ? 1 : 0;
+            for (int u = 0; u < kPer; ++u) {
+                const int j = tid + u * kThreads, sl = j / kRChunk, i = j - sl * kRChunk;
+                int rg = rg0, row = row0 + i;
+                while (row >= p.row_end) { row -= rows_launch; ++rg; }
+                vals[u] = (sl < SL && i < nq) ? __ldg(p.surv + (size_t)sl * p.total_rows + (size_t)rg * p.rows_rg + row) : 0;
             }
-            // move every survivor to the lane of its rank within the query's lane group (rank < c <= SL)
-            if (valid) { sc_v[warp][sub_base + rank] = lg; sc_i[warp][sub_base + rank] = id; }
-            __syncwarp();
-            float v = -INFINITY;
-            int idv = 0;
-            if (s < c) { v = sc_v[warp][lane]; idv = sc_i[warp][lane]; }
-            __syncwarp();
-            const bool is_query = row < p.row_end && n >= 1 && n < p.T;
-            x_finish_group(p, v, idv, is_query && !rescan, min(c, k), rg, n, q, k, sub_base, s, es_all[warp][ql]);
+            if (tid < nq) {
+                int rg = rg0, row = row0 + tid;
+                while (row >= p.row_end) { row -= rows_launch; ++rg; }
+                s_cnt[tid] = __ldg(p.cnt + (size_t)rg * p.rows_rg + row);
+            }
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int j = tid + u * kThreads;
+                if (j < SL * kRChunk) s_kr[j] = vals[u];
+            }
+        }
+        __syncthreads();
+        const long long c_s1 = prof ? clock64() : 0;
+        XPROF(1, 0, c_s1 - c_s0);
+        const int nbuf = (nq + QPB - 1) / QPB;
+        for (int b = warp; b < nbuf; b += WARPS) {
+            const int i = b * QPB + ql;
+            int rg = rg0, row = row0 + i;
+            while (row >= p.row_end) { row -= rows_launch; ++rg; }
+            const int n = row / N, q = row - n * N;
+            int c = (i < nq) ? s_cnt[i] : 0;
+            const bool rescan = (c >> 30) & 1;
+            c = rescan ? 0 : (c & 0xffff);
+            const bool valid = s < c;
+            const int kr = valid ? s_kr[s * kRChunk + i] : 0;
+            const bool is_query = i < nq && n >= 1 && n < p.T;
+            const unsigned vall = __ballot_sync(0xffffffffu, valid);
+            // the staging buffer holds kCapRows survivor rows: when the pass has more (two long lists), the lane groups go one by one
+            const int nsteps = (__popc(vall) > kCapRows) ? QPB : 1;
+            for (int step = 0; step < nsteps; ++step) {
+                const long long c_c0 = prof ? clock64() : 0;
+                const bool mine = valid && (nsteps == 1 || ql == step);
+                const unsigned vmask = __ballot_sync(0xffffffffu, mine);
+                const int srow = __popc(vmask & ((1u << lane) - 1u));          // this lane's row of the staging buffer
+                if (!(p.debug & 32)) {
+                    unsigned m = vmask;
+                    int r_stage = 0;
+                    while (m) {
+                        const int r = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int kr_r = __shfl_sync(0xffffffffu, kr, r);
+                        const int rg_r = __shfl_sync(0xffffffffu, rg, r);
+                        warp_row_copy_async(sbuf + r_stage * kRRowBytes, p.xn + ((size_t)rg_r * p.rows_rg + kr_r) * 128, lane);
+                        ++r_stage;
+                    }
+#pragma unroll
+                    for (int grp = 0; grp < QPB; ++grp) {
+                        if (nsteps > 1 && grp != step) continue;
+                        const int c_g = __shfl_sync(0xffffffffu, c, grp * SL);
+                        if (c_g > 0) {
+                            const int rg_g = __shfl_sync(0xffffffffu, rg, grp * SL), row_g = __shfl_sync(0xffffffffu, row, grp * SL);
+                            warp_row_copy_async(sbuf + (kCapRows + grp) * kRRowBytes, p.xn + ((size_t)rg_g * p.rows_rg + row_g) * 128, lane);
+                        }
+                    }
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                const long long c_c1 = prof ? clock64() : 0;
+                float acc = 0.0f;
+                if (mine && !(p.debug & 64)) acc = x_chain_dot(buf + srow * kRRowBytes, buf + (kCapRows + ql) * kRRowBytes);
+                __syncwarp();                                                 // the staging buffer may be refilled
+                const long long c_c2 = prof ? clock64() : 0;
+                const float lg = mine ? __fmul_rn(acc, p.inv_temp) : -INFINITY;
+                const int id = mine ? x_cand_id(kr, n, N, p.ctx, p.magic_n) : 0x7fffffff;
+                // rank among the query's survivors: (logit desc, id asc)
+                int rank = 0;
+#pragma unroll
+                for (int o = 0; o < SL; ++o) {
+                    const float lo_ = __shfl_sync(0xffffffffu, lg, sub_base + o);
+                    const int io = __shfl_sync(0xffffffffu, id, sub_base + o);
+                    rank += (lo_ > lg || (lo_ == lg && io < id)) ? 1 : 0;
+                }
+                // move every survivor to the lane of its rank within the query's lane group (rank < c <= SL)
+                if (mine) { sc_v[warp][sub_base + rank] = lg; sc_i[warp][sub_base + rank] = id; }
+                __syncwarp();
+                float v = -INFINITY;
+                int idv = 0;
+                const bool grp_on = nsteps == 1 || ql == step;
+                if (grp_on && s < c) { v = sc_v[warp][lane]; idv = sc_i[warp][lane]; }
+                __syncwarp();
+                x_finish_group(p, v, idv, grp_on && is_query && !rescan, min(c, k), rg, n, q, k, sub_base, s, es_all[warp][ql]);
+                if (prof) { const long long c_c3 = clock64(); XPROF(1, 1, c_c1 - c_c0); XPROF(1, 2, c_c2 - c_c1); XPROF(1, 3, c_c3 - c_c2); }
+            }
             // overflowed lists: full exact scan, one query at a time by the whole warp
+            const long long c_r0 = prof ? clock64() : 0;
 #pragma unroll
             for (int grp = 0; grp < QPB; ++grp) {
                 const int need = __shfl_sync(0xffffffffu, (rescan && is_query) ? 1 : 0, grp * SL);
                 if (!need) continue;                                         // warp-uniform
                 const int g_n = __shfl_sync(0xffffffffu, n, grp * SL), g_q = __shfl_sync(0xffffffffu, q, grp * SL);
+                const int g_rg = __shfl_sync(0xffffffffu, rg, grp * SL);
                 float fv;
                 int fid;
-                x_full_scan(p, p.xn + (size_t)rg * p.rows_rg * 128, g_n, g_q, k, fv, fid);
+                x_full_scan<kCapRows>(p, p.xn + (size_t)g_rg * p.rows_rg * 128, buf, g_n, g_q, k, fv, fid);
                 const int g_live = __popc(__ballot_sync(0xffffffffu, fv > -INFINITY) & ((k >= 32) ? 0xffffffffu : ((1u << k) - 1u)));
-                x_finish_group(p, fv, fid, true, g_live, rg, g_n, g_q, k, 0, lane, es_all[warp][0]);
+                x_finish_group(p, fv, fid, true, g_live, g_rg, g_n, g_q, k, 0, lane, es_all[warp][0]);
             }
+            if (prof) XPROF(1, 4, clock64() - c_r0);
         }
+        __syncthreads();                      // the metadata of this chunk is dead
+        if (prof) XPROF(1, 5, clock64() - c_s0);
     }
 }
 
@@ -725,7 +830,7 @@ static int launch_filter(const LpXPlan& plan, const XParams& p, int max_ctas, cu
         cudaFuncAttributes fa;
         CRW_CUDA_RET(cudaFuncGetAttributes(&fa, lp_filter_kernel<KT, KL>));
         const size_t slack = (1024 - (fa.sharedSizeBytes % 1024)) % 1024;
-        smem = slack + (size_t)kXStages * kXStageBytes + (size_t)kXEpi * kXCap * 32 * sizeof(uint32_t);
+        smem = slack + (size_t)kXStages * kXStageBytes + (size_t)kXEpi * kXCap * 32 * sizeof(uint2);
         CRW_CUDA_RET(cudaFuncSetAttribute(lp_filter_kernel<KT, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) smem_dev[dev] = smem;
     }
@@ -737,20 +842,20 @@ static int launch_filter(const LpXPlan& plan, const XParams& p, int max_ctas, cu
     return CRW_OK;
 }
 
-template <int SL>
+template <int SL, int WARPS, int SROWS>
 static int launch_refine(const RParams& r, int max_ctas, cudaStream_t st) {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = (size_t)kRBufs * kRBufBytes;
+    const size_t smem = (size_t)WARPS * SROWS * kRRowBytes + (size_t)SL * kRChunk * sizeof(int);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_refine_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRW_CUDA_RET(cudaFuncSetAttribute(lp_refine_kernel<SL, WARPS, SROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const long long bufs = (long long)r.R * ceil_div(r.row_end - r.row_begin, 32 / SL);
+    const long long bufs = ((long long)r.R * (r.row_end - r.row_begin) + 32 / SL - 1) / (32 / SL);
     if (bufs <= 0) return CRW_OK;
     const int grid = (int)(bufs < max_ctas ? bufs : max_ctas);
-    lp_refine_kernel<SL><<<grid, kRThreads, smem, st>>>(r);
+    lp_refine_kernel<SL, WARPS, SROWS><<<grid, WARPS * 32, smem, st>>>(r);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -778,11 +883,8 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
 
     CRW_CUDA_RET(cudaMemsetAsync(stats, 0, 256, st));
     {
-        const int64_t warps_needed = (int64_t)rows;
-        int64_t blocks = (warps_needed + 7) / 8;
-        const int64_t cap = (int64_t)sms * 16;
-        if (blocks > cap) blocks = cap;
-        if (blocks < 1) blocks = 1;
+        const int64_t blocks = ((int64_t)rows + 7) / 8;
+        if (blocks > 0x7fffffffLL) return CRW_ERR_UNSUPPORTED;
         lp_prep_x_kernel<<<(unsigned)blocks, 256, 0, st>>>(feats, (int64_t)rows, do_normalize, xn, h, stats);
         CRW_LAUNCH_RET();
     }
@@ -822,7 +924,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     r.surv = surv; r.cnt = cnt; r.W = W; r.I = I;
     r.R = R; r.T = T; r.N = N; r.ctx = ctx; r.rb = p.rb; r.k = k;
     r.rows_rg = p.rows_rg; r.row_begin = 0; r.row_end = 0;
-    r.total_rows = p.total_rows; r.inv_temp = p.inv_temp; r.magic_n = p.magic_n;
+    r.total_rows = p.total_rows; r.inv_temp = p.inv_temp; r.magic_n = p.magic_n; r.debug = p.debug;
     if (T < 2) return CRW_OK;
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(plan->maps);
     int rc = make_tmap_bf16_k64(&maps[0], h, (uint64_t)rows, 128, kXBM);      // 2-byte elements: the bf16 map type moves fp16 as well
@@ -854,8 +956,21 @@ int lp_x_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, 
     const int early_slots = p.R * p.early_items_rg, early_rows = lp_x_early_rows(plan_storage);
     r.row_begin = (v_begin >= early_slots) ? early_rows : 0;
     r.row_end = (v_end <= early_slots) ? early_rows : p.rows_rg;
-    return plan.kl <= 16 ? launch_refine<16>(r, max_ctas, st) : launch_refine<32>(r, max_ctas, st);
+    return plan.kl <= 16 ? launch_refine<16, 16, 24>(r, max_ctas, st) : launch_refine<32, 11, 33>(r, max_ctas, st);
 }
 size_t lp_x_plan_bytes() { return sizeof(LpXPlan); }
+int lp_x_profile_read(unsigned long long* host_out, int reset) {
+    if (host_out) CRW_CUDA_RET(cudaMemcpyFromSymbol(host_out, g_x_prof, sizeof(g_x_prof)));
+    if (reset) {
+        void* ptr = nullptr;
+        CRW_CUDA_RET(cudaGetSymbolAddress(&ptr, g_x_prof));
+        CRW_CUDA_RET(cudaMemset(ptr, 0, sizeof(g_x_prof)));
+    }
+    return CRW_OK;
+}
 
 }  // namespace crw
+
+// profiling aid: copies the per-warp phase counters of the exact tensor path ([2 kernels][160 CTAs][18 warps][8] uint64) to host
+// memory (synchronising) and clears them when `reset`
+extern "C" int crw_debug_lp_x_profile(unsigned long long* host_out, int reset) { return crw::lp_x_profile_read(host_out, reset); }

@@ -81,3 +81,76 @@ class CNN(nn.Module):
         x = self.pool2(self.relu2(self.conv2(x)))
         x = self.relu5(self.conv5(self.relu4(self.conv4(self.relu3(self.conv3(x))))))
         return self.fc(self.global_avg_pool(x).flatten(1))
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet-as-encoder adapter (BASELINE config 4).  NOT reference behaviour: in the reference, ``UNet`` (src/unet.py) is only a
+# supervised segmentation baseline (scripts/test/test_unet.py:27) and never feeds CRW.  BASELINE.json's config 4 names it as
+# the encoder, so this adapter builds the same 3-down / 3-up bilinear U-Net with ``n_classes = 128`` output channels (module
+# names as in src/unet.py:80-104, so a reference ``UNet(1,128)`` state dict loads) and reduces the per-pixel map to one
+# 128-d vector per patch with a global average pool.
+# ------------------------------------------------------------------------------------------------
+def _double_conv(cin, cout, cmid=None):
+    cmid = cmid or cout
+    m = nn.Module()
+    m.double_conv = nn.Sequential(nn.Conv2d(cin, cmid, 3, padding=1, bias=False), nn.BatchNorm2d(cmid), nn.ReLU(inplace=True),
+                                  nn.Conv2d(cmid, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+    return m
+
+
+class _Stage(nn.Module):
+    """One U-Net stage: ``down`` = maxpool + double conv; ``up`` = bilinear x2 + skip concat + double conv."""
+
+    def __init__(self, kind, cin, cout):
+        super().__init__()
+        self.kind = kind
+        if kind == "in":
+            self.double_conv = _double_conv(cin, cout).double_conv
+        elif kind == "down":
+            self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _double_conv(cin, cout))
+            self.maxpool_conv[1].forward = lambda x, m=self.maxpool_conv[1]: m.double_conv(x)
+        else:
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = _double_conv(cin, cout, cin // 2)
+
+    def forward(self, x, skip=None):
+        if self.kind == "in":
+            return self.double_conv(x)
+        if self.kind == "down":
+            return self.maxpool_conv(x)
+        x = self.up(x)
+        dy, dx = skip.shape[2] - x.shape[2], skip.shape[3] - x.shape[3]
+        if dy or dx:
+            x = F.pad(x, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+        return self.conv.double_conv(torch.cat([skip, x], dim=1))
+
+
+class UNetEncoder(nn.Module):
+    """``UNet(1 or 2, 128)`` + global average pool -> [patches, 128].  ``chunk`` patches at a time go through the network under
+    activation checkpointing (a B=32, T=20, N=47 step is 30 080 patches of 32x32: the full-resolution activations of the
+    whole batch would not fit next to each other); BatchNorm statistics are therefore per chunk."""
+
+    def __init__(self, pos_embed=False, out_dim=128, chunk=4096):
+        super().__init__()
+        self.chunk = chunk
+        self.inc = _Stage("in", 2 if pos_embed else 1, 64)
+        self.down1, self.down2, self.down3 = _Stage("down", 64, 128), _Stage("down", 128, 256), _Stage("down", 256, 256)
+        self.up1, self.up2, self.up3 = _Stage("up", 512, 128), _Stage("up", 256, 64), _Stage("up", 128, 64)
+        self.outc = nn.Module()
+        self.outc.conv = nn.Conv2d(64, out_dim, kernel_size=1)
+
+    def _net(self, x):
+        x1 = self.inc(x)
+        x2 = self.down1(x1)
+        x3 = self.down2(x2)
+        x4 = self.down3(x3)
+        y = self.up3(self.up2(self.up1(x4, x3), x2), x1)
+        return self.outc.conv(y).mean(dim=(2, 3))
+
+    def forward(self, x):
+        if x.shape[0] <= self.chunk:
+            return self._net(x)
+        from torch.utils.checkpoint import checkpoint
+        outs = [checkpoint(self._net, xc, use_reentrant=False) if torch.is_grad_enabled() else self._net(xc)
+                for xc in x.split(self.chunk)]
+        return torch.cat(outs)

@@ -11,6 +11,8 @@ import torch  # noqa: E402
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 import radar_sounder_crw_b200 as crw  # noqa: E402
 
+PREC = {"bf16x3": crw.ops.PREC_BF16X3, "tcx": crw.ops.PREC_TC_EXACT, "fp32": crw.ops.PREC_FP32}[os.environ.get("LP_PREC", "tcx")]
+
 cfg5 = os.environ.get("LP_CFG") == "5"
 R, T, N, C, M = (4, 3125, 49, 128, 4) if cfg5 else (1, 1250, 49, 128, 4)
 k, r = (20, 24.0) if cfg5 else (10, 12.0)
@@ -21,7 +23,7 @@ flush = torch.empty(64 * 1024 * 1024, device="cuda")
 
 
 def run():
-    return crw.ops.labelprop(feats, mask0, 20, r, 0.07, k, 0, crw.ops.PREC_BF16X3, True, False)
+    return crw.ops.labelprop(feats, mask0, 20, r, 0.07, k, 0, PREC, True, False)
 
 
 ref = None

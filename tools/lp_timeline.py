@@ -8,6 +8,8 @@ import torch  # noqa: E402
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 import radar_sounder_crw_b200 as crw  # noqa: E402
 
+PREC = {"bf16x3": crw.ops.PREC_BF16X3, "tcx": crw.ops.PREC_TC_EXACT, "fp32": crw.ops.PREC_FP32}[os.environ.get("LP_PREC", "tcx")]
+
 T, N, C, M = 1250, 49, 128, 4
 torch.manual_seed(11)
 feats = torch.randn(1, T, N, C, device="cuda")
@@ -15,7 +17,7 @@ mask0 = torch.nn.functional.one_hot(torch.randint(0, M, (1, N), device="cuda"), 
 
 
 def run():
-    return crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, crw.ops.PREC_BF16X3, True, False)
+    return crw.ops.labelprop(feats, mask0, 20, 12.0, 0.07, 10, 0, PREC, True, False)
 
 
 for _ in range(5):
