@@ -210,22 +210,29 @@ def walk_flops(B, T, N, C):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def bench_train(crw, args, rank, world, local, pk):
-    """BASELINE config 2: full train step (PyTorch encoder + fused CUDA walk fwd/bwd + Adam)."""
+def bench_train(crw, args, rank, world, local, pk, cfg4=False):
+    """BASELINE config 2: full train step (PyTorch encoder + fused CUDA walk fwd/bwd + Adam).
+    cfg4: BASELINE config 4 -- T=20 frames and the UNet-as-encoder adapter (UNet(1,128) + global average pool; NOT reference
+    behaviour, see encoder.UNetEncoder), B=32 per GPU, DDP all-reduce of the 17.2 MB of gradients."""
     import torch.distributed as dist  # noqa: F401
-    B, T, tau = TRAIN["B"], TRAIN["T"], TRAIN["tau"]
-    n_rot = 4   # rotate 4 distinct input batches: 4 x 61.6 MB > 126 MB L2
+    B, T, tau = TRAIN["B"], (20 if cfg4 else TRAIN["T"]), TRAIN["tau"]
+    steps = max(2, min(args.steps, 4)) if cfg4 else args.steps
+    warm = 2 if cfg4 else args.warmup
+    n_rot = 2 if cfg4 else 4   # rotate distinct input batches: 4 x 61.6 MB (2 x 123 MB) > 126 MB L2
     batches_host = [synth_train_batch(B, T, 1000 * rank + i).pin_memory() for i in range(n_rot)]
     batches_dev = [b.cuda() for b in batches_host]
     N = batches_dev[0].shape[2]
     torch.manual_seed(11)
     # the encoder is plain PyTorch (out of scope as a kernel); channels_last + TF32 are host-side settings
     torch.backends.cudnn.benchmark = not os.environ.get("CRW_BENCH_NO_AUTOTUNE")    # off only to keep ncu launch lists short
-    encoder = crw.Resnet(pos_embed=False).cuda().train().to(memory_format=torch.channels_last)
+    if cfg4:
+        encoder = crw.UNetEncoder(pos_embed=False, chunk=2048).cuda().train().to(memory_format=torch.channels_last)
+    else:
+        encoder = crw.Resnet(pos_embed=False).cuda().train().to(memory_format=torch.channels_last)
     model = crw.CRW(encoder, tau, False, need_A=False)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                          bucket_cap_mb=32)
+                                                          bucket_cap_mb=5)          # ~4 buckets of the 19.9 MB of gradients: the all-reduce overlaps backward
     opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"], fused=True)   # train-loop glue (SURVEY 8f-4)
     last_loss = [None]
 
@@ -240,7 +247,7 @@ def bench_train(crw, args, rank, world, local, pk):
         last_loss[0] = loss
 
     sampler = ClockSampler(local)
-    ms = timed_loop(train_step, args.steps, args.warmup, world, sampler=sampler)
+    ms = timed_loop(train_step, steps, warm, world, sampler=sampler)
 
     # end to end from pinned HOST batches: a double-buffered input pipeline (what any data loader does) -- while step i
     # computes, the H2D copy of batch i+1 runs on a copy stream into the other device buffer; every timed step still
@@ -279,8 +286,8 @@ def bench_train(crw, args, rank, world, local, pk):
         train_step_e2e(e2e_counter[0])
         e2e_counter[0] += 1
 
-    ms_e2e = timed_loop(train_step_e2e_seq, args.steps, 3, world)
-    return dict(ms_per_step=ms, value=B * world / (ms * 1e-3), N=N, clocks=sampler.summary(), loss=float(last_loss[0]),
+    ms_e2e = timed_loop(train_step_e2e_seq, steps, 2 if cfg4 else 3, world)
+    return dict(steps=steps, warmup=warm, frames=T, ms_per_step=ms, value=B * world / (ms * 1e-3), N=N, clocks=sampler.summary(), loss=float(last_loss[0]),
                 e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="radargrams/s",
                          h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
 
@@ -336,11 +343,13 @@ def bench_walk_sweep(crw, args, world, pk):
     return out
 
 
-def bench_labelprop(crw, args, rank, world, pk):
+def bench_labelprop(crw, args, rank, world, pk, lp_config=None):
     """BASELINE config 3: one 400 x 20k-column radargram per GPU, features -> labels (weak scaling).
-    --lp-config 5: BASELINE config 5, 64 radargrams of 400 x 50k columns sharded over the ranks (strong scaling)."""
+    lp_config 5: BASELINE config 5, 64 radargrams of 400 x 50k columns sharded over the ranks (strong scaling)."""
     global LP
-    cfg5 = args.lp_config == 5
+    cfg5 = (args.lp_config if lp_config is None else lp_config) == 5
+    lp_saved = LP
+    steps = max(2, min(args.steps, 5)) if cfg5 else args.steps
     if cfg5:
         from radar_sounder_crw_b200.parallel import shard_range
         b, e = shard_range(LP5["R_total"], rank, world)
@@ -365,16 +374,31 @@ def bench_labelprop(crw, args, rank, world, pk):
 
     flush = L2Flusher()
     fp32_path = None
-    if args.lp_precision in ("both", "fp32"):
+    labels32 = None
+    if args.lp_precision in ("both", "fp32") and not cfg5:
         prec[0] = crw.ops.PREC_FP32
-        ms32 = timed_loop(lp_step, args.steps, args.warmup, world, flush=flush)
+        ms32 = timed_loop(lp_step, steps, args.warmup, world, flush=flush)
         labels32 = res[0].clone()
         fp32_path = dict(ms_per_step=ms32, value=R * Tl * COLS_PER_FRAME * world / (ms32 * 1e-3), unit="columns/s",
                          note="fp32 FMA path, pinned order, bit-exact against oracle/crw_oracle.c")
+    # exact tensor path: one tcgen05 fp16 pass filters with a proven margin, survivors re-scored in fp32 in the pinned order
+    exact_path = None
+    if args.lp_precision != "fp32":
+        prec[0] = crw.ops.PREC_TC_EXACT
+        msx = timed_loop(lp_step, steps, args.warmup, world, flush=flush)
+        exact_path = dict(ms_per_step=msx, value=(LP5["R_total"] if cfg5 else R * world) * Tl * COLS_PER_FRAME / (msx * 1e-3), unit="columns/s",
+                          kernel="lp_prep_x + lp_filter_kernel (tcgen05 kind::f16, one pass) + lp_refine_kernel (fp32 chain) + gather kernels",
+                          note="precision=TC_EXACT: W / I / masks / labels bit-identical to the fp32 path and to oracle/crw_oracle.c "
+                               "(tests/test_gpu_tc_exact.py)")
+        if labels32 is not None:
+            exact_path["labels_identical_to_fp32_path"] = bool((labels32 == res[0]).all().item())
+        labels_x = res[0].clone()
     prec[0] = crw.ops.PREC_BF16X3 if args.lp_precision != "fp32" else crw.ops.PREC_FP32
-    ms = timed_loop(lp_step, args.steps, args.warmup, world, flush=flush)
+    ms = timed_loop(lp_step, steps, args.warmup, world, flush=flush)
     if fp32_path is not None and args.lp_precision == "both":
         fp32_path["label_agreement_with_primary"] = float((labels32 == res[0]).float().mean().item())
+    if exact_path is not None:
+        exact_path["label_agreement_of_bf16x3_path"] = float((labels_x == res[0]).float().mean().item())
 
     def lp_step_e2e(i):
         # the public host-buffer call: pinned host features streamed in chunks, the copy of chunk c+1 overlapping the
@@ -387,22 +411,24 @@ def bench_labelprop(crw, args, rank, world, pk):
             lp_step(i, feats_host)
         res[0] = res[0].cpu()                   # D2H of the labels
 
-    ms_e2e = timed_loop(lp_step_e2e, args.steps, 3, world, flush=flush)
+    ms_e2e = timed_loop(lp_step_e2e, steps, 3, world, flush=flush)
+    LP = lp_saved
     cols = R * Tl * COLS_PER_FRAME
     if cfg5:
         cols = LP5["R_total"] * Tl * COLS_PER_FRAME / world     # value below multiplies by world
     lp_bytes = R * Tl * (Nl * C * 4 + Nl * 4)   # read features once + write labels
     gbs = lp_bytes / (ms * 1e-3) / 1e9
-    dense = R * Tl * (LP["ctx"] + 1) * Nl * Nl * C * 2
+    cfgd = LP5 if cfg5 else lp_saved
+    dense = R * Tl * (cfgd["ctx"] + 1) * Nl * Nl * C * 2
+    traffic = lp_call_traffic(cfg5, args.lp_precision)
     return dict(
         metric="labelprop_columns_per_sec", unit="columns/s", value=cols * world / (ms * 1e-3), ms_per_step=ms,
         e2e=dict(value=cols * world / (ms_e2e * 1e-3), unit="columns/s",
                  h2d_bytes_per_step=int(feats_host.numel() * 4), d2h_bytes_per_step=int(R * Tl * Nl * 4)),
         roofline=dict(bound="hbm", achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
-                      # dram__bytes_read.sum + dram__bytes_write.sum of lp_topk_tc_kernel (the bulk launch, 470 of 479 tiles),
-                      # one `ncu --set full` capture at config 3 (profiles/r01_ncu_full_lp_topk_tc_final2_raw.csv):
-                      # 31.40 MB read, 0 written back before exit
-                      traffic=(31401216 if (not cfg5 and args.lp_precision != "fp32") else None),
+                      # dram__bytes_read.sum + dram__bytes_write.sum summed over ALL kernels of one call (ncu capture named in
+                      # traffic_source; see lp_call_traffic)
+                      traffic=traffic["bytes"], traffic_source=traffic["source"],
                       kernel="lp_prep_bf16 + lp_topk_tc_kernel (tcgen05 bf16x3) + gather kernels" if args.lp_precision != "fp32"
                       else "l2_normalize + lp_topk_f32_kernel + gather kernels", algorithmic_bytes=lp_bytes,
                       peak_source=pk["src"],
@@ -412,7 +438,7 @@ def bench_labelprop(crw, args, rank, world, pk):
         roofline_tensor=dict(bound="tensor", achieved=dense / (ms * 1e-3) / 1e12, peak=pk["bf16"], unit="TFLOP/s",
                              frac=dense / (ms * 1e-3) / 1e12 / pk["bf16"], algorithmic_flops=dense,
                              note="dense (ctx+1) N^2 C 2 per query frame; 41 % of it lies inside the radius band; x3 executed"),
-        gpu_launches=5 * args.steps, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
+        gpu_launches=5 * steps, steps=steps, exact_path=exact_path, dtype="bf16x3 operands (hi/lo split), fp32 accumulate" if args.lp_precision != "fp32" else "f32",
         frames=Tl, fp32_path=fp32_path,
         scaling="strong" if cfg5 else "weak",
         config=dict(workload=(f"BASELINE config 5: 64 radargrams of 400x50000 columns sharded over {world} GPU(s) "
@@ -420,6 +446,19 @@ def bench_labelprop(crw, args, rank, world, pk):
                               "BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
                               "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact"),
                     l2="flushed between iterations (256 MB write)"))
+
+
+def lp_call_traffic(cfg5, lp_precision):
+    """Whole-call DRAM traffic of one label-propagation call: dram__bytes_read.sum + dram__bytes_write.sum summed over every kernel
+    of the call, from the ncu capture summarised in profiles/r02_lp_call_dram.json (written by tools/summarize_dram.py from an
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` run of tools/lp_once.py).  None when no capture covers the case."""
+    path = os.path.join(ROOT, "profiles", "r02_lp_call_dram.json")
+    key = ("cfg5_" if cfg5 else "cfg3_") + ("fp32" if lp_precision == "fp32" else "bf16x3")
+    try:
+        d = json.load(open(path))[key]
+        return dict(bytes=int(d["bytes"]), source=f"profiles/r02_lp_call_dram.json[{key}] <- {d['capture']}")
+    except Exception:  # noqa: BLE001
+        return dict(bytes=None, source="no ncu capture for this case")
 
 
 def run_b200(args):
@@ -439,6 +478,12 @@ def run_b200(args):
     wk_tc = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3,
                        kernel_note="walk fwd+bwd kernels (BF16X3: mma.sync on bf16 hi/lo pairs), 8 launches") if only in ("all", "walk") else None
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
+    # the multi-GPU configurations BASELINE names (config 4: T=20 + UNet-as-encoder, data parallel; config 5: 64 radargrams of
+    # 50k columns sharded over the ranks, strong scaling) ride in the same line as objects of their own
+    tr4 = bench_train(crw, args, rank, world, local, pk, cfg4=True) if only in ("all", "train4") and not args.no_cfg45 else None
+    lp5 = bench_labelprop(crw, args, rank, world, pk, lp_config=5) if only in ("all", "labelprop5") and not args.no_cfg45 else None
+    if tr4 is not None:
+        torch.cuda.empty_cache()
     if only == "walk_tc_large":     # profiling aid: the tcgen05 walk engine at the scaled geometry N=369
         r = bench_walk(crw, args, world, pk, N=369, T=20, B=32, precision=crw.ops.PREC_BF16X3,
                        kernel_note="walk fwd+bwd kernels, tcgen05 bf16x3 GEMMs, 8 launches")
@@ -455,10 +500,12 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline and only == "all":
         cpu = cpu_baselines(steps_train=1, lp_frames=lp["frames"])
         lp["cpu_baseline"] = cpu["labelprop"]
+        if lp5 is not None:
+            lp5["cpu_baseline"] = cpu["labelprop5"]
 
     if rank == 0:
         if only != "all":
-            emit(dict(only=only, train=tr, walk=wk, labelprop=lp))
+            emit(dict(only=only, train=tr, walk=wk, labelprop=lp, train_cfg4=tr4, labelprop_cfg5=lp5))
         else:
             B, T = TRAIN["B"], TRAIN["T"]
             hot = dict(what="fused walk fwd+bwd (crw_b200::walk_loss + backward), embeddings resident, CUDA-graph replay",
@@ -480,6 +527,20 @@ def run_b200(args):
                 clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=wk["launches"] * args.steps,
                 roofline=wk["roofline"], hot_path=hot, loss=tr["loss"],
                 cpu_baseline=(cpu["train"] if cpu else None), labelprop=lp)
+            if cpu:
+                hot["cpu_baseline"] = cpu["walk"]
+            if tr4 is not None:
+                line["train_cfg4"] = dict(
+                    metric="crw_train_radargrams_per_sec", value=tr4["value"], unit="radargrams/s", ms_per_step=tr4["ms_per_step"],
+                    steps=tr4["steps"], warmup=tr4["warmup"], scaling="weak", e2e=tr4["e2e"], loss=tr4["loss"], clocks=tr4["clocks"],
+                    config=dict(workload="BASELINE config 4: data-parallel CRW train step, B=32 per GPU, T=20 frames, N=47 nodes, "
+                                         "UNet-as-encoder adapter (UNet(1,128) + global average pool, 2048-patch chunks under activation "
+                                         "checkpointing; NOT reference behaviour: the reference never feeds CRW from its UNet), fused CUDA "
+                                         "walk fwd+bwd (fp32), Adam",
+                                global_batch=B * world, frames=20, nodes=tr4["N"],
+                                parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of 17.2 MB of encoder grads, 5 MB buckets)" if world > 1 else "")))
+            if lp5 is not None:
+                line["labelprop_cfg5"] = lp5
             emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -511,10 +572,17 @@ def cpu_train_port(steps, warmup, B):
 
 def cpu_baselines(steps_train, lp_frames):
     from oracle import c_oracle
-    dt, threads = cpu_train_port(steps_train, 1, TRAIN_CPU_SAMPLE_B)
-    train = dict(value=TRAIN_CPU_SAMPLE_B / dt, unit="radargrams/s", cores=threads, kind="port",
-                 sample=f"B={TRAIN_CPU_SAMPLE_B} of the B=32 batch (same T=10, N=47, ResNet encoder, reference-order "
-                        f"(T-2)^2 walk with autograd, Adam), torch CPU, faster of 1 and {os.cpu_count()} threads")
+    loaded = load_reference()
+    if loaded is not None:
+        dt, threads, every = reference_train_step(loaded[1], TRAIN_CPU_SAMPLE_B, steps_train, 1)
+        train = dict(value=TRAIN_CPU_SAMPLE_B / dt, unit="radargrams/s", cores=threads, kind="reference",
+                     sample=f"B={TRAIN_CPU_SAMPLE_B} of the B=32 batch (same T=10, N=47): the reference's own CRW + Resnet + Adam "
+                            f"(baseline/_ref, scripts/train.py:56-72 verbatim) on the host cores; s/step by threads: {every}")
+    else:
+        dt, threads = cpu_train_port(steps_train, 1, TRAIN_CPU_SAMPLE_B)
+        train = dict(value=TRAIN_CPU_SAMPLE_B / dt, unit="radargrams/s", cores=threads, kind="port",
+                     sample=f"B={TRAIN_CPU_SAMPLE_B} of the B=32 batch (same T=10, N=47, ResNet encoder, reference-order "
+                            f"(T-2)^2 walk with autograd, Adam), torch CPU, faster of 1 and {os.cpu_count()} threads")
     rs = np.random.RandomState(3)
     Nl = 49
     feats = rs.randn(1, lp_frames, Nl, LP["C"]).astype(np.float32)
@@ -526,38 +594,167 @@ def cpu_baselines(steps_train, lp_frames):
     lp = dict(value=lp_frames * COLS_PER_FRAME / dt_lp, unit="columns/s", cores=c_oracle.num_threads(), kind="port",
               sample=f"full config-3 radargram ({lp_frames} frames), linear-time C port (oracle/crw_oracle.c, OpenMP); the "
                      "reference's own O(T^2) torch loop measured 264-325 columns/s on 8 cores (BASELINE.md)")
-    return dict(train=train, labelprop=lp)
+    # config 5: one of the 64 radargrams (400 x 50000 columns, k=20, r=24) on the C port, times 64
+    T5 = LP5["cols"] // COLS_PER_FRAME
+    feats5 = rs.randn(1, T5, Nl, LP5["C"]).astype(np.float32)
+    t0 = time.perf_counter()
+    c_oracle.labelprop(feats5, l0, LP5["M"], LP5["ctx"], LP5["radius"], LP5["temp"], LP5["k"], want_masks=False, want_topk=False)
+    dt5 = time.perf_counter() - t0
+    lp5 = dict(value=T5 * COLS_PER_FRAME / dt5, unit="columns/s", cores=c_oracle.num_threads(), kind="port",
+               sample=f"ONE of the 64 radargrams of config 5 ({T5} frames, k=20, r=24) on the linear-time C port (OpenMP), {dt5:.2f} s; "
+                      f"the 64 radargrams are independent, so the whole job is 64 x that ({64 * dt5:.1f} s) at the same columns/s")
+    # the hot path alone on the host: the reference's own walk (src/model.py:22-46 + autograd) when baseline/_ref is there
+    loaded = load_reference()
+    if loaded is not None:
+        wdt, wthreads, wevery = reference_walk_only(loaded[1], TRAIN["B"], TRAIN["T"], 47, 2, 1)
+        walk = dict(value=TRAIN["B"] / wdt, unit="radargrams/s", ms_per_step=wdt * 1e3, cores=wthreads, kind="reference",
+                    sample=f"walk only, reference code verbatim (baseline/_ref/src/model.py:22-46 + autograd, pre-computed embeddings), "
+                           f"full B={TRAIN['B']}, T={TRAIN['T']}, N=47; s/step by threads: {wevery}")
+    else:
+        walk = None
+    return dict(train=train, labelprop=lp, labelprop5=lp5, walk=walk)
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference():
+    """The UNMODIFIED reference (baseline/_ref/src, staged by __graft_entry__.build()) imported through oracle/ref_shim.py with the
+    'cuda' literals mapped to the host: returns the shim namespace, or None when the copy is absent."""
+    if not os.path.isfile(os.path.join(REF_DIR, "src", "model.py")):
+        return None
+    os.environ["CRW_REFERENCE_ROOT"] = REF_DIR
+    os.environ["CRW_REFERENCE_FORCE_CPU"] = "1"
+    from oracle import ref_shim
+    return ref_shim, ref_shim.load()
+
+
+class _Precomputed(torch.nn.Module):
+    """Stands in for the encoder in the walk-only leg: returns pre-computed per-patch features."""
+
+    def __init__(self, feats):
+        super().__init__()
+        self.feats = feats
+
+    def forward(self, _x):
+        return self.feats.reshape(-1, self.feats.shape[-1])
+
+
+def _best_over_threads(fn, steps, warmup):
+    """fn() timed at 1 thread and at all host threads (the hot path's many small ops are often faster on one): (s/step, threads, all)."""
+    best, every = None, {}
+    for threads in sorted({1, os.cpu_count() or 1}):
+        torch.set_num_threads(threads)
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+        every[threads] = dt
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    return best[0], best[1], every
+
+
+def reference_train_step(ref, B, steps, warmup):
+    """scripts/train.py:56-72 verbatim on the host cores: reference CRW + reference Resnet + Adam on a B-radargram sample."""
+    import contextlib
+    torch.manual_seed(11)
+    with open(os.devnull, "w") as dn, contextlib.redirect_stdout(dn):
+        enc = ref.encoder.Resnet(pos_embed=False)
+    model = ref.model.CRW(enc, TRAIN["tau"], False)
+    model.train(True)
+    opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"])
+    seq = synth_train_batch(B, TRAIN["T"], 5)
+
+    def step():
+        loss, _ = model(seq)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    return _best_over_threads(step, steps, warmup)
+
+
+def reference_walk_only(ref, B, T, N, steps, warmup):
+    """src/model.py:22-46 + autograd with pre-computed embeddings (no encoder): the hot path alone, reference code verbatim."""
+    torch.manual_seed(11)
+    x = torch.randn(B, T, N, 128, requires_grad=True)
+    model = ref.model.CRW(_Precomputed(x), TRAIN["tau"], False)
+    dummy = torch.zeros(B, T, N, 2, 2)
+
+    def step():
+        x.grad = None
+        loss, _ = model(dummy)
+        loss.backward()
+
+    return _best_over_threads(step, steps, warmup)
+
+
+def reference_propagate(shim, ref, T, steps):
+    """src/utils.py:94-161 verbatim (its own O(T^2) frame loop) on pre-computed features of T frames."""
+    torch.manual_seed(11)
+    N = 49
+    feats = torch.randn(T, N, LP["C"])
+    seg_ref = torch.randint(0, LP["M"], (400, 8))
+    lp = ref.labelprop.LabelPropVOS_CRW({"CXT_SIZE": LP["ctx"], "RADIUS": LP["radius"], "TEMP": LP["temp"], "KNN": LP["k"]})
+
+    def run():
+        with shim.cpu_device_patches():
+            ref.utils.propagate(torch.zeros(T, N, 2, 2), seg_ref, _Precomputed(feats), lp, LP["M"], False, False)
+
+    return _best_over_threads(run, steps, 0)
 
 
 def run_reference(args):
+    """CPU arm: the reference's own code (baseline/_ref, kind "reference") on the box's host cores; the oracle ports only where the
+    reference itself cannot finish in bounded time (label propagation at full config-3 length: the reference loop is O(T^2))."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     from oracle import c_oracle
     B = TRAIN_CPU_SAMPLE_B
-    dt, threads = cpu_train_port(max(1, args.steps), max(1, min(args.warmup, 1)), B)
+    loaded = load_reference()
+    steps = max(1, min(args.steps, 3))
+    if loaded is not None:
+        shim, ref = loaded
+        dt, threads, every = reference_train_step(ref, B, steps, 1)
+        kind = "reference"
+        wdt, wthreads, wevery = reference_walk_only(ref, TRAIN["B"], TRAIN["T"], 47, steps, 1)
+        pdt, pthreads, pevery = reference_propagate(shim, ref, 300, 1)
+        walk = dict(value=TRAIN["B"] / wdt, unit="radargrams/s", ms_per_step=wdt * 1e3, cores=wthreads, kind="reference",
+                    sample=f"walk only (src/model.py:22-46 + autograd, pre-computed embeddings), full B={TRAIN['B']}, T={TRAIN['T']}, N=47; "
+                           f"s/step by threads: {wevery}")
+        prop = dict(value=300 * COLS_PER_FRAME / pdt, unit="columns/s", cores=pthreads, kind="reference",
+                    sample=f"src/utils.py propagate verbatim (O(T^2) frame loop) on T=300 frames of pre-computed features; s by threads: {pevery}")
+    else:
+        dt, threads = cpu_train_port(steps, 1, B)
+        every, kind, walk, prop = {threads: dt}, "port", None, None
     Tl = LP["cols"] // COLS_PER_FRAME
     rs = np.random.RandomState(3)
     feats = rs.randn(1, Tl, 49, LP["C"]).astype(np.float32)
     l0 = rs.randint(0, LP["M"], (1, 49)).astype(np.int32)
     t0 = time.perf_counter()
-    for _ in range(max(1, args.steps)):
+    for _ in range(steps):
         c_oracle.labelprop(feats, l0, LP["M"], LP["ctx"], LP["radius"], LP["temp"], LP["k"], want_masks=False, want_topk=False)
-    dt_lp = (time.perf_counter() - t0) / max(1, args.steps)
+    dt_lp = (time.perf_counter() - t0) / steps
     value = B / dt
-    sample = (f"each step = B={B} radargrams of the B=32 config-2 batch (T=10, N=47, ResNet encoder, reference-order walk, "
-              f"autograd, Adam) on torch CPU, {threads} threads")
+    sample = (f"each step = B={B} radargrams of the B=32 config-2 batch (T=10, N=47, reference Resnet encoder, reference CRW loss, "
+              f"autograd, Adam: scripts/train.py:56-72 verbatim) on the host cores, {threads} threads; s/step by threads: {every}")
     line = dict(impl="reference", metric="crw_train_radargrams_per_sec", value=value, unit="radargrams/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="BASELINE config 2 (bounded CPU sample): " + sample),
-                cpu_baseline=dict(value=value, unit="radargrams/s", cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=value, unit="radargrams/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="radargrams/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                hot_path=walk,
                 labelprop=dict(metric="labelprop_columns_per_sec", unit="columns/s", value=Tl * COLS_PER_FRAME / dt_lp,
                                ms_per_step=dt_lp * 1e3,
                                cpu_baseline=dict(value=Tl * COLS_PER_FRAME / dt_lp, unit="columns/s",
                                                  cores=c_oracle.num_threads(), kind="port",
                                                  sample="full config-3 radargram, linear-time C port (OpenMP)"),
+                               reference_loop=prop,
                                e2e=dict(value=Tl * COLS_PER_FRAME / dt_lp, unit="columns/s", h2d_bytes_per_step=0,
                                         d2h_bytes_per_step=0)))
     emit(line)
@@ -572,7 +769,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lp-precision", default="both", choices=["both", "bf16x3", "fp32"])
     ap.add_argument("--lp-config", type=int, default=3, choices=[3, 5])
-    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep", "walk_tc_large"],
+    ap.add_argument("--no-cfg45", action="store_true", help="skip the config-4 / config-5 objects (quick runs)")
+    ap.add_argument("--only", default="all", choices=["all", "train", "walk", "labelprop", "walk_sweep", "walk_tc_large", "train4", "labelprop5"],
                     help="profiling aid: run one section only (the JSON line is then not the contract line)")
     args = ap.parse_args()
     protect_stdout()

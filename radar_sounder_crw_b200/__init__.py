@@ -18,6 +18,6 @@ from .labelprop import LabelPropVOS_CRW  # noqa: F401
 from .maskedatt import MaskedAttention, batched_affinity  # noqa: F401
 from .utils import propagate, propagate_batch, pos_embed, ndiag_matrix, create_model, seed_labels, fuse_reversed  # noqa: F401
 from .dataset import RGDataset, trim_miguel  # noqa: F401
-from .encoder import CNN, Resnet  # noqa: F401
+from .encoder import CNN, Resnet, UNetEncoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -556,8 +556,10 @@ __device__ __forceinline__ float x_chain_dot(const uint8_t* krow_smem, const uin
 // Full exact scan of one query by one warp (its survivor list overflowed: many candidates tie within the filter margin).  The
 // in-band candidates are visited in ascending id order, 32 at a time through the warp's staging buffer; lane i keeps the i-th
 // best (the insertion of lp_topk_f32_kernel).  Returns this lane's (logit, id).
+// round_begin / round_stride: this warp visits rounds round_begin, round_begin + round_stride, ... (0, 1 = all of them)
 template <int CAP>
-__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, uint8_t* buf, int n, int q, int k, float& v_out, int& id_out) {
+__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, uint8_t* buf, int n, int q, int k, int round_begin, int round_stride,
+                                            float& v_out, int& id_out) {
     constexpr int kStep = CAP < 32 ? CAP : 32;      // candidates per round
     const int lane = threadIdx.x & 31;
     const int N = p.N, rb = p.rb;
@@ -570,7 +572,7 @@ __device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, u
     const uint32_t sbuf = tc::smem_u32(buf);
     warp_row_copy_async(sbuf + CAP * kRRowBytes, xr + ((size_t)n * N + q) * 128, lane);
     const int total = F * bw;                          // in-band candidates, ascending id = (frame slot, node)
-    for (int c0 = 0; c0 < total; c0 += kStep) {
+    for (int c0 = round_begin * kStep; c0 < total; c0 += round_stride * kStep) {
         const int nrow = min(kStep, total - c0);
         __syncwarp();
         for (int r = 0; r < nrow; ++r) {
@@ -656,6 +658,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) lp_refine_kernel(RParams p) {
     __shared__ float sc_v[WARPS][32];
     __shared__ int sc_i[WARPS][32];
     __shared__ int s_cnt[kRChunk];
+    constexpr int kMaxOvf = 64;              // overflowed queries of a chunk that are rescanned by the whole CTA (more: inline, one warp each)
+    __shared__ int s_ovf[kMaxOvf], s_novf;
     int* s_kr = reinterpret_cast<int*>(rsm + (size_t)WARPS * kBufBytes);      // [SL][kRChunk]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, k = p.k;
@@ -673,6 +677,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) lp_refine_kernel(RParams p) {
     for (long long c0 = r_lo; c0 < r_hi; c0 += kRChunk) {
         const int nq = (int)min((long long)kRChunk, r_hi - c0);
         const long long c_s0 = prof ? clock64() : 0;
+        if (tid == 0) s_novf = 0;
         // ---- stage the chunk's metadata: every thread issues its loads back to back (independent, coalesced along the rows) ----
         const int rg0 = (int)(c0 / rows_launch);
         const int row0 = p.row_begin + (int)(c0 - (long long)rg0 * rows_launch);        // chunk row i: row0 + i, wrapping into the next radargram
@@ -769,19 +774,69 @@ __global__ void __launch_bounds__(WARPS * 32, 1) lp_refine_kernel(RParams p) {
                 x_finish_group(p, v, idv, grp_on && is_query && !rescan, min(c, k), rg, n, q, k, sub_base, s, es_all[warp][ql]);
                 if (prof) { const long long c_c3 = clock64(); XPROF(1, 1, c_c1 - c_c0); XPROF(1, 2, c_c2 - c_c1); XPROF(1, 3, c_c3 - c_c2); }
             }
-            // overflowed lists: full exact scan, one query at a time by the whole warp
+            // overflowed lists: queued for a rescan by the whole CTA after the chunk (inline by this warp when the queue is full)
             const long long c_r0 = prof ? clock64() : 0;
 #pragma unroll
             for (int grp = 0; grp < QPB; ++grp) {
                 const int need = __shfl_sync(0xffffffffu, (rescan && is_query) ? 1 : 0, grp * SL);
                 if (!need) continue;                                         // warp-uniform
+                const int g_i = __shfl_sync(0xffffffffu, i, grp * SL);
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_novf, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot < kMaxOvf) {
+                    if (lane == 0) s_ovf[slot] = g_i;
+                    continue;
+                }
                 const int g_n = __shfl_sync(0xffffffffu, n, grp * SL), g_q = __shfl_sync(0xffffffffu, q, grp * SL);
                 const int g_rg = __shfl_sync(0xffffffffu, rg, grp * SL);
                 float fv;
                 int fid;
-                x_full_scan<kCapRows>(p, p.xn + (size_t)g_rg * p.rows_rg * 128, buf, g_n, g_q, k, fv, fid);
+                x_full_scan<kCapRows>(p, p.xn + (size_t)g_rg * p.rows_rg * 128, buf, g_n, g_q, k, 0, 1, fv, fid);
                 const int g_live = __popc(__ballot_sync(0xffffffffu, fv > -INFINITY) & ((k >= 32) ? 0xffffffffu : ((1u << k) - 1u)));
                 x_finish_group(p, fv, fid, true, g_live, g_rg, g_n, g_q, k, 0, lane, es_all[warp][0]);
+            }
+            if (prof) XPROF(1, 4, clock64() - c_r0);
+        }
+        __syncthreads();
+        // ---- queued rescans: every warp scans its share of the candidate rounds, warp 0 merges the partial lists ----
+        {
+            const long long c_r0 = prof ? clock64() : 0;
+            const int novf = min(s_novf, kMaxOvf);
+            const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+            for (int e = 0; e < novf; ++e) {
+                const int i = s_ovf[e];
+                int rg = rg0, row = row0 + i;
+                while (row >= p.row_end) { row -= rows_launch; ++rg; }
+                const int n = row / N, q = row - n * N;
+                float pv;
+                int pi;
+                x_full_scan<kCapRows>(p, p.xn + (size_t)rg * p.rows_rg * 128, buf, n, q, k, warp, WARPS, pv, pi);
+                sc_v[warp][lane] = pv;
+                sc_i[warp][lane] = pi;
+                __syncthreads();
+                if (warp == 0) {
+                    float v = -INFINITY;
+                    int id = 0;
+                    for (int w2 = 0; w2 < WARPS; ++w2)
+                        for (int s2 = 0; s2 < k; ++s2) {
+                            const float c = sc_v[w2][s2];
+                            const int ci = sc_i[w2][s2];
+                            if (!(c > -INFINITY)) break;                                  // (warp-uniform) lists are sorted: the rest is empty
+                            // candidates arrive in no particular order: full comparator (logit desc, id asc)
+                            const int pos = __popc(__ballot_sync(0xffffffffu, v > c || (v == c && id < ci)) & kmask);
+                            if (pos < k) {
+                                const float vup = __shfl_up_sync(0xffffffffu, v, 1);
+                                const int iup = __shfl_up_sync(0xffffffffu, id, 1);
+                                if (lane > pos) { v = vup; id = iup; }
+                                else if (lane == pos) { v = c; id = ci; }
+                                if (lane >= k) v = -INFINITY;
+                            }
+                        }
+                    const int live = __popc(__ballot_sync(0xffffffffu, v > -INFINITY) & kmask);
+                    x_finish_group(p, v, id, true, live, rg, n, q, k, 0, lane, es_all[0][0]);
+                }
+                __syncthreads();
             }
             if (prof) XPROF(1, 4, clock64() - c_r0);
         }
