@@ -8,9 +8,18 @@
  *
  * Conventions
  *   - every pointer is a BORROWED DEVICE pointer (cudaMalloc'd / torch CUDA tensor
- *     storage); the library never allocates, frees or synchronises;
+ *     storage); the library never allocates or frees device memory for tensors and
+ *     never synchronises with the host (workspaces come from the caller, sized by the
+ *     crw_*_bytes functions);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
- *     default stream); calls are re-entrant per stream, there is no global state;
+ *     default stream) and is ordered after / before other work on that stream;
+ *   - process-wide state the library DOES keep, per device, created on first use and
+ *     never freed: a higher-priority side stream, a copy stream and a handful of
+ *     events (crw_labelprop_forward forks the early frames + the sequential label
+ *     gather onto the side stream and joins them back with events; the enqueue
+ *     sequence of a call is serialised by a mutex, so calls from several host threads
+ *     are safe but do not interleave), cached kernel attributes (opt-in shared-memory
+ *     sizes), and the environment switches listed in DESIGN.md, read once;
  *   - return value: CRW_OK, a negative CRW_ERR_* code, or -(1000 + cudaError_t) when
  *     a launch failed; no exceptions cross the boundary;
  *   - tensors are dense row-major fp32 unless said otherwise; shapes in brackets.
@@ -38,7 +47,7 @@ extern "C" {
 /* precision selectors */
 #define CRW_PREC_FP32 0        /* fp32 FMA, pinned order: bit-comparable with oracle/crw_oracle.c */
 #define CRW_PREC_BF16X3 1      /* tcgen05 kind::f16, error-compensated bf16 hi/lo (3 MMAs), fp32 accumulate */
-#define CRW_PREC_TF32 2        /* tcgen05 kind::tf32 (walk GEMMs), fp32 accumulate */
+/* (value 2 is unassigned: a kind::tf32 walk was declared in round 1 and never built; error-compensated bf16 covers that case) */
 #define CRW_PREC_TC_EXACT 3    /* label propagation only: one tcgen05 fp16 pass FILTERS the candidates with a proven margin, the
                                   survivors are re-scored in fp32 in the pinned order -- results bit-identical to CRW_PREC_FP32 */
 

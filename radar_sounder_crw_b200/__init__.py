@@ -8,8 +8,8 @@ Drop-in for the contrastive-random-walk hot path of jdalcorso/radar-sounder-crw:
 
 Everything after the encoder runs in hand-written CUDA kernels behind the C ABI declared in
 ``include/crw_b200.h`` (``lib/libcrw_b200.so``), exposed to PyTorch as ``torch.library`` custom ops
-in the ``crw_b200::`` namespace.  There is no CPU or PyTorch fallback: importing the ops without
-the built library raises.
+in the ``crw_b200::`` namespace.  There is no CPU or PyTorch fallback: the library is loaded on first
+use, and the first op call raises when it has not been built (``_lib.lib()``).
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcrw_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
-PREC_FP32, PREC_BF16X3, PREC_TF32, PREC_TC_EXACT = 0, 1, 2, 3
+PREC_FP32, PREC_BF16X3, PREC_TC_EXACT = 0, 1, 3
 LP_REF_EXACT, LP_FIXED = 0, 1
 
 _c_int, _c_f, _c_sz, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p

@@ -597,6 +597,7 @@ static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_
         if (dev >= 0 && dev < 64) opted[dev] = true;
     }
     if (batch <= 0) return CRW_OK;
+    if (batch > 65535) return CRW_ERR_UNSUPPORTED;       // the batch index rides in grid.z (the fp32 engine has no such limit)
     dim3 grid(ceil_div(Ncols, kWTile), ceil_div(Mrows, kWTile), batch);
     tc_tiles_kernel<P><<<grid, kTT, kWSmem, st>>>(p);
     CRW_LAUNCH_RET();

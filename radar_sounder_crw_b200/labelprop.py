@@ -11,7 +11,10 @@ from . import ops
 
 
 class LabelPropVOS_CRW(object):
-    def __init__(self, cfg, precision=ops.PREC_FP32, mode=ops.LP_REF_EXACT):
+    def __init__(self, cfg, precision=ops.PREC_AUTO, mode=ops.LP_REF_EXACT):
+        """cfg: the reference's dict (CXT_SIZE, RADIUS, TEMP, KNN; labelprop.py:44-48).  ``precision`` (not in the reference):
+        PREC_AUTO (default) = the exact tensor path where the shape allows, else the fp32 kernel -- identical results either
+        way; PREC_BF16X3 = the approximate error-compensated bf16 kernel (>= 99.8 % of the labels on near-collinear features)."""
         self.cxt_size = cfg["CXT_SIZE"]
         self.radius = cfg["RADIUS"]
         self.temperature = cfg["TEMP"]

@@ -20,7 +20,7 @@ class CRW(nn.Module):
     Extra keyword arguments (not in the reference, defaults keep its behaviour):
       need_A     return the affinities ``A [B,T-1,N,N]`` (model.py:46).  ``scripts/train.py:67``
                  discards them; pass False on the timed path to skip the N x N write.
-      precision  ops.PREC_FP32 (default) | ops.PREC_TF32 | ops.PREC_BF16X3
+      precision  ops.PREC_FP32 (default) | ops.PREC_BF16X3 (error-compensated bf16 pairs on the tensor cores)
     """
 
     def __init__(self, encoder, tau, pos_embed, only_a=False, need_A=True, precision=ops.PREC_FP32):

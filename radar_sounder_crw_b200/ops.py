@@ -6,13 +6,25 @@ raises ``RuntimeError`` on any non-zero return.  No op has a CPU implementation.
 """
 from __future__ import annotations
 
+import collections
 from typing import Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import PREC_FP32, PREC_BF16X3, PREC_TF32, PREC_TC_EXACT, LP_REF_EXACT, LP_FIXED  # noqa: F401
+from ._lib import PREC_FP32, PREC_BF16X3, PREC_TC_EXACT, LP_REF_EXACT, LP_FIXED  # noqa: F401
+
+
+PREC_AUTO = -1     # label propagation: the fastest path whose results are the fp32 path's (resolved by lp_precision())
+
+
+def lp_precision(precision: int, N: int, C: int, k: int) -> int:
+    """PREC_AUTO -> PREC_TC_EXACT where the exact tensor path serves the shape (C = 128, 8 <= N <= 128, k <= 24), else PREC_FP32.
+    Both give bit-identical results (same pinned fp32 arithmetic decides every id and weight); the choice is speed only."""
+    if int(precision) != PREC_AUTO:
+        return int(precision)
+    return PREC_TC_EXACT if (C == 128 and 8 <= N <= 128 and k <= 24) else PREC_FP32
 
 
 def _stream() -> int:
@@ -71,8 +83,9 @@ def walk_loss(x: Tensor, tau: float, need_A: bool, precision: int) -> Tuple[Tens
 @walk_loss.register_fake
 def _(x, tau, need_A, precision):
     B, T, N, C = x.shape
+    nbytes = _lib.lib().crw_walk_saved_bytes(B, T, N, C, int(precision))     # host-only arithmetic: safe under FakeTensor
     return (x.new_empty(()), x.new_empty((B, T - 1, N, N) if need_A else (0,)),
-            torch.empty(0, device=x.device, dtype=torch.uint8))
+            torch.empty(nbytes, device=x.device, dtype=torch.uint8))
 
 
 @torch.library.custom_op("crw_b200::walk_loss_backward", mutates_args=())
@@ -175,6 +188,7 @@ def labelprop(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: float
     feats, mask0 = _chk(feats, "feats"), _chk(mask0, "mask0")
     R, T, N, C = feats.shape
     M = mask0.shape[1]
+    precision = lp_precision(precision, N, C, k)
     L = _lib.lib()
     dev = feats.device
     labels = torch.empty((R, T, N), device=dev, dtype=torch.int32)
@@ -202,6 +216,21 @@ def _(feats, mask0, ctx, radius, temp, k, mode, precision, normalize, return_top
     tk = (R, T, k, N) if return_topk else (0,)
     return (torch.empty((R, T, N), device=dev, dtype=torch.int32), feats.new_empty((R, T, M, N)),
             feats.new_empty(tk), torch.empty(tk, device=dev, dtype=torch.int32))
+
+
+# labelprop_host returns while its H2D copies are still queued on the library's copy stream, which PyTorch's pinned-memory
+# allocator knows nothing about: a temporary such as ``x.pin_memory()`` would go back to the pool (and could be handed out and
+# overwritten) while the DMA is still reading it.  Every call therefore parks (event, source) here until the event -- recorded
+# on the caller's stream, which has waited for every copy -- has completed.
+_pinned_in_flight = collections.deque()
+
+
+def _park_pinned(feats: Tensor) -> None:
+    while _pinned_in_flight and _pinned_in_flight[0][0].query():
+        _pinned_in_flight.popleft()
+    ev = torch.cuda.Event()
+    ev.record()
+    _pinned_in_flight.append((ev, feats))
 
 
 @torch.library.custom_op("crw_b200::labelprop_host", mutates_args=())
@@ -233,6 +262,7 @@ def labelprop_host(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: 
         _lib.check(L.crw_labelprop_forward_host(feats.data_ptr(), _p(mask0), R, T, N, C, M, ctx, float(radius), float(temp), k,
                                                 int(mode), int(normalize), _p(labels), _p(masks), _p(W), _p(I),
                                                 _p(scratch), sbytes, _stream()), "crw_labelprop_forward_host")
+        _park_pinned(feats)
     return labels, masks, W, I
 
 

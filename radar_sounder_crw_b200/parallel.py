@@ -26,22 +26,30 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int, group=None) -> None:
-    """Average the gradients of ``params`` across ranks with ONE flat all-reduce (19.9 MB for the ResNet encoder).
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int, group=None, local_items: int = 1,
+                        total_items: int = 0) -> None:
+    """Combine the gradients of ``params`` across ranks with ONE flat all-reduce (19.9 MB for the ResNet encoder).
 
-    Equivalent to what DistributedDataParallel does with a single bucket; kept explicit because the encoder
-    is the only thing with parameters and the step is encoder-bound, so there is nothing to overlap with.
+    Every parameter that requires a gradient takes part on every rank, in parameter order (a parameter without a gradient on
+    this rank contributes zeros), so the flat buffers always line up.  Each rank's gradient is the gradient of ITS mean loss
+    over ``local_items`` batch elements; it is weighted by ``local_items / total_items`` so that uneven shards
+    (``shard_range`` with B % world != 0) still give the gradient of the full-batch mean loss.  With ``total_items = 0`` the
+    shards are taken to be equal (plain average).  Equivalent to DistributedDataParallel with a single bucket.
     """
     if world == 1:
         return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    ps = [p for p in params if p.requires_grad]
+    if not ps:
         return
-    flat = torch._utils._flatten_dense_tensors(grads)
+    weight = (float(local_items) / float(total_items)) if total_items else 1.0 / world
+    grads = [(p.grad if p.grad is not None else torch.zeros_like(p)) for p in ps]
+    flat = torch._utils._flatten_dense_tensors(grads).mul_(weight)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(world)
-    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(f)
+    for p, f in zip(ps, torch._utils._unflatten_dense_tensors(flat, grads)):
+        if p.grad is None:
+            p.grad = f.clone()
+        else:
+            p.grad.copy_(f)
 
 
 def gather_labels(local_labels: torch.Tensor, n_total: int, rank: int, world: int, group=None) -> torch.Tensor:

@@ -113,3 +113,20 @@ def test_pinned_expf_accuracy():
     assert (np.abs(e - ref) / ref).max() < 2.5e-7
     assert c_oracle.expf(np.array([0.0], np.float32))[0] == 1.0
     assert c_oracle.expf(np.array([-1e10 / 0.07], np.float32))[0] == 0.0
+
+
+@pytest.mark.parametrize("name", ["walk_small_f64.npz", "walk_cfg1_f32.npz", "walk_tau001_f32.npz", "walk_cfg4_f32.npz"])
+def test_torch_port_of_the_walk_matches_the_live_reference(name):
+    """oracle/walk_torch_port.crw_loss_reference_order (the restatement whose autograd the GPU tests compare against and the
+    port leg of bench.py's CPU arm) against the outputs of the LIVE reference: loss, returned affinities and d loss / d x."""
+    import torch
+    from oracle.walk_torch_port import crw_loss_reference_order
+    g = load_golden(name)
+    dt = torch.float64 if str(g["dtype"]) == "float64" else torch.float32
+    x = torch.tensor(g["x"].astype(np.float64 if dt == torch.float64 else np.float32), dtype=dt, requires_grad=True)
+    loss, A = crw_loss_reference_order(x, float(g["tau"]))
+    loss.backward()
+    tol = 1e-12 if dt == torch.float64 else 2e-6
+    assert abs(float(loss) - float(g["loss"])) <= tol * max(abs(float(g["loss"])), 1.0)
+    assert np.abs(A.detach().numpy() - g["A"]).max() <= tol * max(np.abs(g["A"]).max(), 1.0)
+    assert np.abs(x.grad.numpy() - g["dx"]).max() <= (1e-10 if dt == torch.float64 else 2e-6) * max(np.abs(g["dx"]).max(), 1e-30)
