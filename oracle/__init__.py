@@ -15,7 +15,7 @@ labelprop_oracle.py  numpy restatement of label propagation
                      (``src/utils.py:134-161``, ``src/imported/labelprop.py:67-116``,
                      ``src/imported/maskedatt.py:151-175,232-245``).
 crw_oracle.c         plain-C restatement of label propagation with a *pinned*
-                     fp32 operation order (sequential fmaf over channels, a
+                     fp32 operation order (one fmaf chain per float4 of channels + xor butterfly, a
                      fixed polynomial exp) so the CUDA fp32 path can be compared
                      bit for bit; also the multi-threaded CPU baseline.
 walk_torch_port.py   torch-CPU port of the reference train step used only to

@@ -14,7 +14,9 @@
  * The fp32 operation order is PINNED so that the CUDA fp32 path can be compared
  * bit for bit (the reference itself leaves GEMM summation order, exp and tie
  * order to the library):
- *   dot      acc = 0; for c = 0..C-1: acc = fmaf(key[c], query[c], acc)
+ *   dot      warp order: p[l] = fmaf chain over the channels 4l .. 4l+3 (one float4 per "lane", l = 0..31; channels
+ *            beyond 128 wrap onto the lanes again), then the xor butterfly 16, 8, 4, 2, 1 of plain adds -- see
+ *            crw_oracle_dot.  (One coalesced 16-byte load per lane and five shuffles on a GPU; no staging.)
  *   logit    in band (|j-q| < radius): dot * inv_temp,  inv_temp = 1.0f / temp
  *            (this is what ATen's CUDA `tensor /= python_float` computes);
  *            out of band: (-1e10f) * inv_temp   [dot + -1e10f == -1e10f in fp32]
@@ -57,6 +59,28 @@ float crw_oracle_expf(float x) {
     union { int32_t i; float f; } two_n;
     two_n.i = ((int32_t)n + 127) << 23;
     return y * two_n.f;
+}
+
+/* The pinned dot product (see the header): the order one warp computes it in.  "Lane" l (0..31) owns the channels c with
+ * (c mod 128) in [4l, 4l+4) -- one float4 of a 128-channel row -- and forms p[l] by sequential fmaf over them in ascending c;
+ * the 32 partials are then combined by the xor butterfly of the normalisation (offsets 16, 8, 4, 2, 1; plain adds), whose
+ * result is the same on every lane because fp addition is commutative. */
+float crw_oracle_dot(const float* a, const float* b, int C) {
+    float p[32], t[32];
+    for (int l = 0; l < 32; ++l) {
+        float acc = 0.0f;
+        for (int base = 0; base < C; base += 128)
+            for (int i = 0; i < 4; ++i) {
+                const int c = base + 4 * l + i;
+                if (c < C) acc = fmaf(a[c], b[c], acc);
+            }
+        p[l] = acc;
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int l = 0; l < 32; ++l) t[l] = p[l] + p[l ^ off];
+        for (int l = 0; l < 32; ++l) p[l] = t[l];
+    }
+    return p[0];
 }
 
 int crw_oracle_num_threads(void) {
@@ -126,9 +150,7 @@ int crw_oracle_lp_topk(const float* emb, int T, int N, int C, int ctx, float rad
                     int dj = j - q; if (dj < 0) dj = -dj;
                     if ((float)dj < radius) {
                         const float* kv = kf + (int64_t)j * C;
-                        float acc = 0.0f;
-                        for (int c = 0; c < C; ++c) acc = fmaf(kv[c], qv[c], acc);
-                        logit = acc * inv_temp;
+                        logit = crw_oracle_dot(kv, qv, C) * inv_temp;
                     } else {
                         logit = masked;
                     }

@@ -59,6 +59,51 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- the pinned dot product (oracle/crw_oracle.c::crw_oracle_dot) in its native form: one float4 of channels per lane ----
+// The oracle's dot product (crw_oracle_dot) of a key row with the query row, both held one float4 per lane: fmaf chain over the
+// lane's four channels, then the xor butterfly 16, 8, 4, 2, 1.  Every lane returns the same value.
+__device__ __forceinline__ float x_warp_dot(const float4& kv, const float4& qv) {
+    float acc = __fmaf_rn(kv.x, qv.x, 0.0f);
+    acc = __fmaf_rn(kv.y, qv.y, acc);
+    acc = __fmaf_rn(kv.z, qv.z, acc);
+    acc = __fmaf_rn(kv.w, qv.w, acc);
+    return warp_sum_butterfly_rn(acc);
+}
+
+// Sixteen warp dots at once.  p[v] = this lane's partial (fmaf chain over its four channels) of dot product v.  The xor butterfly
+// of x_warp_dot is run as a REDUCE-SCATTER: at the level with offset 16 a lane keeps the eight vectors whose index bit 3 equals
+// its lane bit 4 and hands the other eight to its partner, and so on (offsets 8, 4, 2), then the last level (offset 1) is a plain
+// exchange.  Every sum adds the same two operands as the butterfly does at that level (fp addition is commutative), so the
+// result is bit-identical to x_warp_dot -- with 16 shuffles instead of 80.  Returns the total of vector (lane >> 1).
+__device__ __forceinline__ float x_warp_dot16(const float (&p)[16], int lane) {
+    float q[8], r[4], s2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = b4 ? p[8 + i] : p[i], send = b4 ? p[i] : p[8 + i];
+        q[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b3 ? q[4 + i] : q[i], send = b3 ? q[i] : q[4 + i];
+        r[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b2 ? r[2 + i] : r[i], send = b2 ? r[i] : r[2 + i];
+        s2[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+    }
+    const float keep = b1 ? s2[1] : s2[0], send = b1 ? s2[0] : s2[1];
+    const float t = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+    return __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+}
+__device__ __forceinline__ float x_partial4(const float4& kv, const float4& qv) {
+    float acc = __fmaf_rn(kv.x, qv.x, 0.0f);
+    acc = __fmaf_rn(kv.y, qv.y, acc);
+    acc = __fmaf_rn(kv.z, qv.z, acc);
+    return __fmaf_rn(kv.w, qv.w, acc);
+}
+
 // trimmed key-frame rule of maskedatt.py:166-167
 __host__ __device__ inline int n_key_frames(int n, int ctx) { return n <= ctx + 1 ? n : ctx + 1; }
 __host__ __device__ inline int key_frame(int n, int ctx, int f) {

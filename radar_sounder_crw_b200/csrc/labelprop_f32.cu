@@ -8,8 +8,9 @@
 //   frame loop + argmax             src/utils.py:152-160
 //
 // Arithmetic order is pinned (see oracle/crw_oracle.c header) so results are bit-identical
-// to the C oracle: dot = sequential fmaf over channels, logit = dot * (1/temp), ties by
-// ascending candidate id, pinned polynomial exp, sequential softmax sum, mul-then-add gather.
+// to the C oracle: dot in WARP ORDER (lane l: fmaf chain over channels 4l .. 4l+3, then the xor butterfly 16, 8, 4, 2, 1 of
+// plain adds -- crw_oracle_dot), logit = dot * (1/temp), ties by ascending candidate id, pinned polynomial exp, sequential
+// softmax sum, mul-then-add gather.
 #include "common.cuh"
 
 namespace crw {
@@ -33,18 +34,18 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* x, int64
 // ------------------------------------------------------------------------------------------
 // Affinity + radius band + top-k + softmax, fp32.
 //
-// One CTA = one (query frame, chunk of 64 query nodes).  Frames are staged TRANSPOSED in
-// shared memory as [c][64 nodes] with the 16-byte node groups xor-swizzled by (c>>2), so
-// that (a) the transposing stores are bank-conflict free and (b) a thread computing a 4x4
-// (key x query) block reads one float4 of keys and one float4 of queries per channel.
-// Only 4x4 blocks that intersect the band |j - q| <= rb are computed (compact item list).
-// Scores go through shared memory to regroup them per query; each warp then keeps the
-// running top-k of its queries sorted across lanes (ballot + shuffle insertion).
+// One CTA = one (query frame, chunk of 64 query nodes).  Query rows and key rows are staged row-major in shared memory
+// ([64][128] floats, channels beyond C zero).  A (query, key) pair inside the band is one warp's work: every lane multiplies
+// its float4 of channels (fmaf chain over 4l .. 4l+3) and the 32 partials meet in the xor butterfly -- the pinned order of
+// crw_oracle_dot -- sixteen pairs at a time as a reduce-scatter (x_warp_dot16), which leaves each logit on a lane of its own;
+// each warp keeps the running top-k of its queries sorted across lanes (ballot + shuffle insertion).  This is the validation /
+// general-shape path (the exact tensor path of labelprop_x.cu is the fast one and gives the same bits).
 // ------------------------------------------------------------------------------------------
 constexpr int kChunk = 64;          // nodes per staged tile
 constexpr int kScoreLd = 68;        // padded row of the score tile (16-byte aligned rows)
 constexpr int kTopkThreads = 256;
 constexpr int kQPerWarp = kChunk / (kTopkThreads / 32);  // 8 queries per warp
+constexpr int kRowF = 128;          // floats per staged row (C <= 128)
 
 struct TopkParams {
     const float* keys;     // [n_keys, N, C]
@@ -55,39 +56,14 @@ struct TopkParams {
     float inv_temp;
 };
 
-__device__ __forceinline__ int swz(int c, int j) { return c * kChunk + ((((j >> 2) ^ (c >> 2)) & 15) << 2) + (j & 3); }
-
-// stage nodes [j_base, j_base+64) of `frame` ([N][C] row-major) into dst ([C][64] swizzled).
-// All global loads of a thread are issued before the first shared store so their latencies overlap.
-__device__ __forceinline__ void stage_frame_T(const float* __restrict__ frame, int N, int C, int j_base, float* dst) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int jl4 = lane & 3, c4 = lane >> 2;
-    constexpr int kRg = (kChunk / 4) / (kTopkThreads / 32);   // row groups per warp (2)
-    float4 v[kRg][4];                                          // C <= 128: at most 4 column blocks of 32
-#pragma unroll
-    for (int u = 0; u < kRg; ++u) {
-        const int jl = (warp + u * (kTopkThreads / 32)) * 4 + jl4;
-        const int j = j_base + jl;
-        const float4* src = reinterpret_cast<const float4*>(frame + (size_t)j * C);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int c = b * 32 + c4 * 4;
-            v[u][b] = (j < N && c < C) ? __ldg(src + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < kRg; ++u) {
-        const int jl = (warp + u * (kTopkThreads / 32)) * 4 + jl4;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int c = b * 32 + c4 * 4;
-            if (c < C) {
-                dst[swz(c + 0, jl)] = v[u][b].x;
-                dst[swz(c + 1, jl)] = v[u][b].y;
-                dst[swz(c + 2, jl)] = v[u][b].z;
-                dst[swz(c + 3, jl)] = v[u][b].w;
-            }
-        }
+// stage nodes [j_base, j_base+64) of `frame` ([N][C] row-major) into dst ([64][128], zero-padded)
+__device__ __forceinline__ void stage_frame_rows(const float* __restrict__ frame, int N, int C, int j_base, float* dst) {
+    const int c4n = C >> 2;
+    for (int i = threadIdx.x; i < kChunk * (kRowF / 4); i += kTopkThreads) {
+        const int jl = i >> 5, c4 = i & 31, j = j_base + jl;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < N && c4 < c4n) v = __ldg(reinterpret_cast<const float4*>(frame + (size_t)j * C) + c4);
+        reinterpret_cast<float4*>(dst)[i] = v;
     }
 }
 
@@ -95,11 +71,8 @@ template <int G>
 __global__ void __launch_bounds__(kTopkThreads, 1) lp_topk_f32_kernel(TopkParams p) {
     extern __shared__ __align__(16) float smem[];
     const int N = p.N, C = p.C, k = p.k, rb = p.rb;
-    float* Qt = smem;                              // [C][64]
-    float* Kt = Qt + C * kChunk;                   // [G][C][64]
-    float* score = Kt + G * C * kChunk;            // [G][64][kScoreLd]
-    unsigned short* items = reinterpret_cast<unsigned short*>(score + G * kChunk * kScoreLd);  // [G*256]
-    __shared__ int n_items;
+    float* Qr = smem;                              // [64][128]
+    float* Kr = Qr + kChunk * kRowF;               // [G][64][128]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_qchunks = ceil_div(N, kChunk);
@@ -113,7 +86,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1) lp_topk_f32_kernel(TopkParams
     const int njc = jc_hi - jc_lo + 1;
     const int n_tiles = F * njc;
 
-    stage_frame_T(p.queries + (size_t)job * N * C, N, C, q_base, Qt);
+    stage_frame_rows(p.queries + (size_t)job * N * C, N, C, q_base, Qr);
 
     // running top-k of this warp's queries: lane i holds the i-th best (value, id)
     float tv[kQPerWarp];
@@ -123,78 +96,39 @@ __global__ void __launch_bounds__(kTopkThreads, 1) lp_topk_f32_kernel(TopkParams
 
     for (int t0 = 0; t0 < n_tiles; t0 += G) {
         const int g_cnt = min(G, n_tiles - t0);
-        if (tid == 0) n_items = 0;
-        __syncthreads();   // previous scan done with `score`; previous FMA done with Kt
+        __syncthreads();   // previous products done with Kr
         for (int g = 0; g < g_cnt; ++g) {
             const int t = t0 + g, f = t / njc, jc = jc_lo + t % njc;
-            stage_frame_T(p.keys + (size_t)key_frame(n, p.ctx, f) * N * C, N, C, jc * kChunk, Kt + g * C * kChunk);
-            // in-band 4x4 blocks of this tile: thread <-> (qb, jb)
-            const int qb = tid >> 4, jb = tid & 15;
-            const int q0 = q_base + qb * 4, j0 = jc * kChunk + jb * 4;
-            if (q0 < N && j0 < N && (j0 - (q0 + 3)) <= rb && (q0 - (j0 + 3)) <= rb) {
-                const int slot = atomicAdd(&n_items, 1);
-                items[slot] = (unsigned short)((g << 8) | (qb << 4) | jb);
-            }
+            stage_frame_rows(p.keys + (size_t)key_frame(n, p.ctx, f) * N * C, N, C, jc * kChunk, Kr + g * kChunk * kRowF);
         }
         __syncthreads();
-        const int cnt = n_items;
-        for (int it = tid; it < cnt; it += kTopkThreads) {
-            const int code = items[it];
-            const int g = code >> 8, qb = (code >> 4) & 15, jb = code & 15;
-            const float* Kg = Kt + g * C * kChunk;
-            float acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
-#pragma unroll 2
-            for (int c4 = 0; c4 < (C >> 2); ++c4) {
-                const int sk = ((jb ^ c4) & 15) << 2, sq = ((qb ^ c4) & 15) << 2;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = c4 * 4 + i;
-                    const float4 kv = *reinterpret_cast<const float4*>(Kg + c * kChunk + sk);
-                    const float4 qv = *reinterpret_cast<const float4*>(Qt + c * kChunk + sq);
-                    const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
-                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = __fmaf_rn(kk[b], qq[a], acc[a][b]);
-                }
-            }
-            float* sc = score + (g * kChunk + qb * 4) * kScoreLd + jb * 4;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                float4 o;
-                o.x = __fmul_rn(acc[a][0], p.inv_temp);
-                o.y = __fmul_rn(acc[a][1], p.inv_temp);
-                o.z = __fmul_rn(acc[a][2], p.inv_temp);
-                o.w = __fmul_rn(acc[a][3], p.inv_temp);
-                *reinterpret_cast<float4*>(sc + a * kScoreLd) = o;
-            }
-        }
-        __syncthreads();
-        // scan: candidates in ascending id order (tile order = frame-major, then node)
+        // dot products of the in-band pairs of this warp's queries in warp order (crw_oracle_dot), sixteen keys at a time
+        // (x_warp_dot16: lane l ends up with the logit of key l >> 1), merged at once into the running top-k: candidates are
+        // visited in ascending id order (tile order = frame-major, then node), so a later id never displaces an equal logit
         const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-#pragma unroll
+#pragma unroll 1
         for (int qi = 0; qi < kQPerWarp; ++qi) {
             const int ql = warp + qi * (kTopkThreads / 32);
             const int q = q_base + ql;
-            if (q >= N) continue;                       // warp-uniform
+            if (q >= N) continue;                                     // warp-uniform
+            const float4 qv = reinterpret_cast<const float4*>(Qr + ql * kRowF)[lane];
             float v = tv[qi];
             int id = ti[qi];
             float thr = __shfl_sync(0xffffffffu, v, k - 1);
             for (int g = 0; g < g_cnt; ++g) {
                 const int t = t0 + g, f = t / njc, jc = jc_lo + t % njc;
-                const float* srow = score + (g * kChunk + ql) * kScoreLd;
+                const float* Kg = Kr + g * kChunk * kRowF;
+                const int j_lo = max(jc * kChunk, q - rb), j_hi = min(min(N - 1, jc * kChunk + kChunk - 1), q + rb);
+                for (int j0 = j_lo; j0 <= j_hi; j0 += 16) {
+                    float part[16];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int jl = half * 32 + lane;
-                    const int j = jc * kChunk + jl;
-                    const int dj = j - q;
-                    const bool ok = (j < N) && (dj <= rb) && (-dj <= rb);
-                    const float cand = ok ? srow[jl] : -INFINITY;
+                    for (int r = 0; r < 16; ++r) {
+                        const int jl = min(j0 + r, j_hi) - jc * kChunk;          // (rows past the band are recomputed and ignored)
+                        part[r] = x_partial4(reinterpret_cast<const float4*>(Kg + jl * kRowF)[lane], qv);
+                    }
+                    const float cand = __fmul_rn(x_warp_dot16(part, lane), p.inv_temp);
+                    const int j = j0 + (lane >> 1);
+                    const bool ok = !(lane & 1) && j <= j_hi;
                     const int cid = f * N + j;
                     unsigned m = __ballot_sync(0xffffffffu, ok && cand > thr);
                     while (m) {
@@ -563,8 +497,7 @@ extern "C" int crw_l2_normalize(const float* x, int64_t rows, int C, float* out,
 
 template <int G>
 static int launch_topk_f32(const TopkParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)(1 + G) * p.C * kChunk * sizeof(float) + (size_t)G * kChunk * kScoreLd * sizeof(float) +
-                        (size_t)G * 256 * sizeof(unsigned short);
+    const size_t smem = (size_t)(1 + G) * kRowF * kChunk * sizeof(float);
     CRW_CUDA_RET(cudaFuncSetAttribute(lp_topk_f32_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = p.n_q * ceil_div(p.N, kChunk);
     lp_topk_f32_kernel<G><<<grid, kTopkThreads, smem, st>>>(p);

@@ -18,7 +18,7 @@
 //                                      (20-bit fixed-point value | 12-bit stream column); a warp-wide flush merges them into a
 //                                      sorted register list of KL entries whose KT-th entry gives the bound
 //   lp_refine_kernel    per query: the fp32 rows of its survivors are fetched with cp.async.bulk (512 B each, mbarrier ring),
-//                       dot = the oracle's sequential fmaf chain, exact top-k (logit desc, id asc), masked fill, pinned
+//                       dot = the oracle's pinned four-chain fmaf order, exact top-k (logit desc, id asc), masked fill, pinned
 //                       softmax, W / I stores.  Queries whose survivor list overflowed (degenerate inputs: many exact ties)
 //                       are rescanned in full by a warp -- slower, same result.
 #include <cuda_fp16.h>
@@ -32,14 +32,21 @@ namespace crw {
 constexpr float kXScale = 256.0f;            // fp16 plane holds 256 * xn: keeps small components out of the subnormal range
 
 constexpr int kXStatSlots = 32;           // the per-call maxima are spread over 32 slots (fewer same-address atomics), reduced by the filter
+constexpr int kXStatVals = 4;             // per slot: max |xn|^2, max |xn - hq/256|^2, max |xn - mu|^2, max |(xn - mu) - hk/256|^2
+constexpr int kXStatBytes = kXStatSlots * kXStatVals * 4;
 
-__global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict__ x, int64_t rows, int do_normalize,
-                                                        float* __restrict__ xn, __half* __restrict__ h, unsigned* __restrict__ stats) {
+// pass 1: F.normalize in the pinned order -> xn (fp32), QUERY plane hq = fp16(256 xn), per-radargram column sums (for the mean
+// feature mu), maxima of |xn|^2 and of the rounding residual.  One warp per row; a CTA's 8 rows belong to one radargram.
+__global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict__ x, int rows_rg, int do_normalize, float* __restrict__ xn,
+                                                        __half* __restrict__ hq, float* __restrict__ musum, unsigned* __restrict__ stats) {
     __shared__ float s_n2[8], s_e2[8];
+    __shared__ float s_col[8][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
-    float n2 = 0.0f, e2 = 0.0f;
-    if (row < rows) {
+    const int rg = blockIdx.y;
+    float max_n2 = 0.0f, max_e2 = 0.0f;
+    float col[4] = {0.f, 0.f, 0.f, 0.f};          // this lane's column sums over the rows of this warp (few atomics per CTA)
+    for (int r = blockIdx.x * 8 + warp; r < rows_rg; r += gridDim.x * 8) {
+        const int64_t row = (int64_t)rg * rows_rg + r;
         const float* xr = x + row * 128;
         float v[4];
 #pragma unroll
@@ -53,29 +60,88 @@ __global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict_
 #pragma unroll
             for (int m = 0; m < 4; ++m) v[m] = __fdiv_rn(v[m], d);
         }
+        float n2 = 0.0f, e2 = 0.0f;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const __half hv = __float2half_rn(v[m] * kXScale);
-            const float r = v[m] - __half2float(hv) * (1.0f / kXScale);
+            const float res = v[m] - __half2float(hv) * (1.0f / kXScale);
             n2 = fmaf(v[m], v[m], n2);
-            e2 = fmaf(r, r, e2);
-            h[row * 128 + lane + 32 * m] = hv;
+            e2 = fmaf(res, res, e2);
+            col[m] += v[m];
+            hq[row * 128 + lane + 32 * m] = hv;
             if (xn) xn[row * 128 + lane + 32 * m] = v[m];
         }
-        // one butterfly for both sums: the pair travels together
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             n2 += __shfl_xor_sync(0xffffffffu, n2, off);
             e2 += __shfl_xor_sync(0xffffffffu, e2, off);
         }
+        max_n2 = fmaxf(max_n2, n2);
+        max_e2 = fmaxf(max_e2, e2);
     }
-    if (lane == 0) { s_n2[warp] = n2; s_e2[warp] = e2; }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) s_col[warp][lane + 32 * m] = col[m];
+    if (lane == 0) { s_n2[warp] = max_n2; s_e2[warp] = max_e2; }
     __syncthreads();
+    if (threadIdx.x < 128) {
+        float c = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) c += s_col[w][threadIdx.x];
+        atomicAdd(&musum[rg * 128 + threadIdx.x], c);
+    }
     if (threadIdx.x == 0) {          // non-negative floats order like their bit patterns
         float a = 0.0f, b2 = 0.0f;
         for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_n2[w]); b2 = fmaxf(b2, s_e2[w]); }
-        atomicMax(&stats[2 * (blockIdx.x % kXStatSlots)], __float_as_uint(a));
-        atomicMax(&stats[2 * (blockIdx.x % kXStatSlots) + 1], __float_as_uint(b2));
+        unsigned* st = stats + kXStatVals * (blockIdx.x % kXStatSlots);
+        atomicMax(&st[0], __float_as_uint(a));
+        atomicMax(&st[1], __float_as_uint(b2));
+    }
+}
+
+// pass 2: KEY plane hk = fp16(256 (xn - mu)), mu = the radargram's mean feature.  q . (k - mu) = q . k - q . mu ranks the keys of
+// a query exactly like q . k (the shift is the same for all of them), but its rounding error scales with |k - mu| instead of
+// |k|: on near-collinear embeddings (any encoder at initialisation) the filter margin shrinks with the spread of the
+// features, so the survivor lists stay short.  xn was written a moment ago: this pass reads it from L2.
+__global__ void __launch_bounds__(256) lp_center_x_kernel(const float* __restrict__ xn, int rows_rg, const float* __restrict__ musum,
+                                                          __half* __restrict__ hk, unsigned* __restrict__ stats) {
+    __shared__ float s_d2[8], s_e2[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rg = blockIdx.y;
+    const int r = blockIdx.x * 8 + warp;
+    const int64_t row = (int64_t)rg * rows_rg + r;
+    const float inv = 1.0f / (float)rows_rg;
+    float d2 = 0.0f, e2 = 0.0f;
+    if (r < rows_rg) {
+        // (no pinned order here: one float4 of channels per lane, one 8-byte store of four halves)
+        const float4 xv = reinterpret_cast<const float4*>(xn + row * 128)[lane];
+        const float4 mv = reinterpret_cast<const float4*>(musum + rg * 128)[lane];
+        const float d[4] = {xv.x - mv.x * inv, xv.y - mv.y * inv, xv.z - mv.z * inv, xv.w - mv.w * inv};
+        __half hv[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            hv[m] = __float2half_rn(d[m] * kXScale);
+            const float res = d[m] - __half2float(hv[m]) * (1.0f / kXScale);
+            d2 = fmaf(d[m], d[m], d2);
+            e2 = fmaf(res, res, e2);
+        }
+        uint2 packed;
+        packed.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
+        packed.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
+        reinterpret_cast<uint2*>(hk + row * 128)[lane] = packed;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        }
+    }
+    if (lane == 0) { s_d2[warp] = d2; s_e2[warp] = e2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.0f, b2 = 0.0f;
+        for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_d2[w]); b2 = fmaxf(b2, s_e2[w]); }
+        unsigned* st = stats + kXStatVals * (blockIdx.x % kXStatSlots);
+        atomicMax(&st[2], __float_as_uint(a));
+        atomicMax(&st[3], __float_as_uint(b2));
     }
 }
 
@@ -89,9 +155,10 @@ constexpr int kXStageBytes = 16384;          // key tile [kblock 0,1][64 rows][1
 constexpr int kXStages = 5;
 constexpr int kXEpi = 16;                    // epilogue warps
 constexpr int kXCap = 32;                    // appended-survivor slots per thread between two flushes
-constexpr int kXThreads = (kXEpi + 2) * 32;         // 16 epilogue warps, the TMA producer, the MMA issuer
+constexpr int kXThreads = (kXEpi + 4) * 32;         // 16 epilogue warps + one warp group: TMA producer, two MMA issuers, one idle
+constexpr int kXEpiRegs = 112, kXAuxRegs = 32;      // setmaxnreg: the epilogue warp groups take the registers the fifth one gives up
 constexpr int kXColBits = 12;                // packed key: value << 12 | stream column (key tile * 64 + column)
-constexpr float kXFixBias = 278528.0f;       // (dot + 1.0625) * 2^18 with a = 65536 dot:  fix = 4 a + 278528
+constexpr float kXFixHalf = 524280.0f;       // 2^19 - 8: fix = a * scale + kXFixHalf lies in [0, 2^20) for |a| <= the call's bound
 constexpr float kXFixMagic = 12582912.0f;    // 1.5 * 2^23: float -> integer in the low mantissa bits
 
 struct XParams {
@@ -102,7 +169,7 @@ struct XParams {
     unsigned magic_n;
     int debug;
     long long total_rows;
-    int32_t* surv;                           // [KL][total_rows] radargram-relative key rows of the survivors
+    int32_t* surv;                           // [total_rows][KL] radargram-relative key rows of the survivors (sorted prefix of the list)
     int32_t* cnt;                            // [total_rows]     number of survivors, bit 30 = list overflowed (rescan in full)
     const unsigned* stats;
     float inv_temp;
@@ -233,18 +300,18 @@ __device__ __forceinline__ void x_list_insert(uint32_t (&L)[KL], uint32_t P) {
 }
 
 // bound of the hot loop, in accumulator units (65536 * dot), from the packed KT-th best entry and the margin
-__device__ __forceinline__ float x_threshold(uint32_t theta, int m_fix) {
+__device__ __forceinline__ float x_threshold(uint32_t theta, int m_fix, float inv_scale) {
     if (theta == 0u) return -INFINITY;
-    const int X = (int)(theta >> kXColBits) - m_fix - 1;             // one fixed-point step of slack for the rounding of fix()
-    return ((float)max(X, 0) - kXFixBias) * 0.25f;
+    const int X = (int)(theta >> kXColBits) - m_fix - 2;             // fixed-point steps of slack for the rounding of fix() and of this product
+    return ((float)max(X, 0) - kXFixHalf) * inv_scale;
 }
 
 // 16 columns of a key tile: branch-free append of the values that beat the bound and are valid (window x band).
 // Per value: validity bit -> predicate, compare, column id, predicated 8-byte store (raw value, column), predicated slot advance.
 // Written as PTX so that the per-value work stays at these five instructions (the fixed-point packing happens at flush time).
-template <int I, int END>
+template <int I, int END, int OFF>
 struct XScan {
-    static __device__ __forceinline__ void run(const float (&val)[32], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
+    static __device__ __forceinline__ void run(const float (&val)[64], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
         asm volatile(
             "{\n\t.reg .pred p, v;\n\t.reg .b32 t, c;\n\t"
             "and.b32 t, %1, %2;\n\t"
@@ -254,24 +321,25 @@ struct XScan {
             "@p st.shared.v2.b32 [%0], {%7, c};\n\t"
             "@p add.u32 %0, %0, 256;\n\t}"
             : "+r"(ptr)
-            : "r"(vbits), "n"(1u << I), "f"(val[I]), "f"(thr), "r"(colbase), "n"(I), "r"(__float_as_uint(val[I]))
+            : "r"(vbits), "n"(1u << I), "f"(val[OFF + I]), "f"(thr), "r"(colbase), "n"(I), "r"(__float_as_uint(val[OFF + I]))
             : "memory");
-        XScan<I + 1, END>::run(val, vbits, colbase, thr, ptr);
+        XScan<I + 1, END, OFF>::run(val, vbits, colbase, thr, ptr);
     }
 };
-template <int END>
-struct XScan<END, END> {
-    static __device__ __forceinline__ void run(const float (&)[32], uint32_t, uint32_t, float, uint32_t&) {}
+template <int END, int OFF>
+struct XScan<END, END, OFF> {
+    static __device__ __forceinline__ void run(const float (&)[64], uint32_t, uint32_t, float, uint32_t&) {}
 };
-template <int I0>
-__device__ __forceinline__ void x_scan16(const float (&val)[32], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
-    XScan<I0, I0 + 16>::run(val, vbits, colbase, thr, ptr);
+// 16 columns I0 .. I0 + 15 of half H (columns 32 H ..) of a key tile; vbits = the validity bits of that half
+template <int H, int I0>
+__device__ __forceinline__ void x_scan16(const float (&val)[64], uint32_t vbits, uint32_t colbase, float thr, uint32_t& ptr) {
+    XScan<I0, I0 + 16, 32 * H>::run(val, vbits, colbase, thr, ptr);
 }
 
 template <int KT, int KL>
 __global__ void __launch_bounds__(kXThreads, 1)
 lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap, XParams p) {
-    constexpr int kProducerWarp = kXEpi, kMmaWarp = kXEpi + 1;
+    constexpr int kProducerWarp = kXEpi, kMmaWarp = kXEpi + 1;      // issuers: warps kMmaWarp (tiles 0, 1) and kMmaWarp + 1 (tiles 2, 3)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sK = smem;                                              // kXStages x 16 KB ring
@@ -284,7 +352,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 
     if (warp == kMmaWarp) tc::tmem_alloc<512>(&tmem_base_s);
     if (tid == 0) {
-        for (int s = 0; s < kXStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1); }
+        for (int s = 0; s < kXStages; ++s) { tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 2); }   // empty: one commit per issuer
         for (int g = 0; g < kXG; ++g) { tc::mbar_init(&acc_full[g], 1); tc::mbar_init(&acc_empty[g], 4); }
         tc::fence_barrier_init();
     }
@@ -293,7 +361,10 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;      // columns [0,256): four query tiles (64 each); [256,512): four accumulators
-
+    // register budget (setmaxnreg, first thing in every role): the epilogue keeps a whole 64-column key tile in registers so
+    // that it can free the accumulator at once; the auxiliary warp group gives up what it does not need
+    if (warp >= kXEpi) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kXAuxRegs));
     if (warp == kProducerWarp) {
         // ================= TMA producer =================
         const bool leader = tc::elect_one();
@@ -327,30 +398,35 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                 }
             }
         }
-    } else if (warp == kMmaWarp) {
-        // ================= MMA issuer =================
+    } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+        // ================= MMA issuers: warp kMmaWarp serves query tiles 0 and 1, warp kMmaWarp + 1 tiles 2 and 3 =================
+        // Both walk every ring slot (waiting until it is full, so that neither runs ahead of the producer) and commit to its
+        // `empty` barrier (count 2): the commit covers whatever the issuer queued for that slot -- the tcgen05.cp of one of its
+        // query tiles, the MMAs of the tiles that look at the key tile, or nothing.
+        const int iw = warp - kMmaWarp;
         const bool leader = tc::elect_one();
         const uint64_t kdesc0 = tc::umma_smem_desc_k128(tc::smem_u32(sK));
-        uint32_t scnt = 0, ucnt[kXG] = {0u, 0u, 0u, 0u};
+        uint32_t scnt = 0, ucnt[2] = {0u, 0u};
         for (int v = p.v_begin + blockIdx.x; v < p.v_end; v += gridDim.x) {
             const XItem t = x_item(p, v);
             if (t.n_kt == 0) continue;
-            XTile qt[kXG];
+            XTile qt[2];
 #pragma unroll
-            for (int g = 0; g < kXG; ++g) qt[g] = x_tile(p, t, g);
-            // query tiles: ring slots -> TMEM (tcgen05.cp executes in order with the MMAs issued before and after it)
-#pragma unroll
+            for (int gl = 0; gl < 2; ++gl) qt[gl] = x_tile(p, t, 2 * iw + gl);
+            // query tiles: ring slots -> TMEM (tcgen05.cp executes in order with the MMAs this thread issues before and after it)
             for (int g = 0; g < kXG; ++g) {
-                if (!qt[g].active) continue;
+                if (!x_tile(p, t, g).active) continue;
                 for (int kb = 0; kb < 2; ++kb, ++scnt) {
                     const int s = scnt % kXStages;
                     tc::mbar_wait(&k_full[s], (scnt / kXStages) & 1);
                     tc::tc_fence_after();
                     if (leader) {
-                        const uint64_t sd = kdesc0 + (uint64_t)((s * kXStageBytes) >> 4);
+                        if ((g >> 1) == iw) {
+                            const uint64_t sd = kdesc0 + (uint64_t)((s * kXStageBytes) >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            tc::tmem_cp_128x256b(tmem_base + (uint32_t)(g * 64 + kb * 32 + ks * 8), sd + (uint64_t)((ks * 32) >> 4));
+                            for (int ks = 0; ks < 4; ++ks)
+                                tc::tmem_cp_128x256b(tmem_base + (uint32_t)(g * 64 + kb * 32 + ks * 8), sd + (uint64_t)((ks * 32) >> 4));
+                        }
                         tc::umma_commit(&k_empty[s]);
                     }
                     __syncwarp();
@@ -365,9 +441,10 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                 const uint32_t idesc = umma_idesc_f16(kXBM, ncols);
                 const uint64_t kdesc = kdesc0 + (uint64_t)((s * kXStageBytes) >> 4);
 #pragma unroll
-                for (int g = 0; g < kXG; ++g) {
-                    if (!x_needs(p, qt[g], row0, nrows)) continue;
-                    tc::mbar_wait(&acc_empty[g], ((ucnt[g]) & 1) ^ 1);
+                for (int gl = 0; gl < 2; ++gl) {
+                    if (!x_needs(p, qt[gl], row0, nrows)) continue;
+                    const int g = 2 * iw + gl;
+                    tc::mbar_wait(&acc_empty[g], ((ucnt[gl]) & 1) ^ 1);
                     tc::tc_fence_after();
                     if (leader) {
                         const uint32_t d = tmem_base + 256u + (uint32_t)(g * kXBN);
@@ -381,24 +458,39 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                         tc::umma_commit(&acc_full[g]);
                     }
                     __syncwarp();
-                    ++ucnt[g];
+                    ++ucnt[gl];
                 }
                 if (leader) tc::umma_commit(&k_empty[s]);
                 __syncwarp();
             }
         }
+    }
+      // (the fourth warp of the auxiliary warp group is idle)
     } else {
         // ================= epilogue: thread = query row =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kXEpiRegs));
         const int g = warp >> 2, quarter = warp & 3;
         const int rb = p.rb, ctx = p.ctx;
         const uint32_t app = tc::smem_u32(sApp + (size_t)warp * kXCap * 32) + lane * 8;
-        // margin from the call's maxima (see header): E = 2 eps |x| + accumulation slack, survivors within 2 E of the bound
-        float n2 = 0.0f, e2 = 0.0f;
-        for (int i = 0; i < kXStatSlots; ++i) { n2 = fmaxf(n2, __uint_as_float(p.stats[2 * i])); e2 = fmaxf(e2, __uint_as_float(p.stats[2 * i + 1])); }
-        const float nrm = sqrtf(n2) * 1.00001f, eps = sqrtf(e2) * 1.0001f + 1e-9f;
-        const float E = (2.0f * eps * nrm + eps * eps + 2.5e-5f * nrm * nrm) * 1.02f;
-        const int m_fix = (int)ceilf(2.0f * E * 262144.0f) + 2;
-        const bool range_bad = !(n2 <= 1.002f);                    // un-normalised input: the fixed-point range does not hold
+        // margin from the call's maxima: a~ = tensor(hq . hk) / 65536 approximates q . (k - mu); with eq, ed the largest rounding
+        // residual norms of the query / centred key planes and nq, nd the largest norms,
+        //   |a~ - (chain(q, k) - q . mu)| <= E = eq nd + nq ed + eq ed + (tensor accumulation + chain rounding + the fp32 subtraction)
+        // so every candidate within 2 E of the KT-th best a~ survives (the true top-k is among them).
+        float nq2 = 0.0f, eq2 = 0.0f, nd2 = 0.0f, ed2 = 0.0f;
+        for (int i = 0; i < kXStatSlots; ++i) {
+            nq2 = fmaxf(nq2, __uint_as_float(p.stats[kXStatVals * i]));
+            eq2 = fmaxf(eq2, __uint_as_float(p.stats[kXStatVals * i + 1]));
+            nd2 = fmaxf(nd2, __uint_as_float(p.stats[kXStatVals * i + 2]));
+            ed2 = fmaxf(ed2, __uint_as_float(p.stats[kXStatVals * i + 3]));
+        }
+        const float nq = sqrtf(nq2) * 1.00001f, eq = sqrtf(eq2) * 1.0001f + 1e-9f;
+        const float nd = sqrtf(nd2) * 1.00001f + 1e-9f, ed = sqrtf(ed2) * 1.0001f + 1e-9f;
+        const float E = (eq * nd + nq * ed + eq * ed + 1.0e-5f * nq * nq + 2.0e-5f * nq * nd) * 1.02f;
+        // fixed point: a (accumulator units, 65536 x dot) lies within +-65536 A, A = 1.05 nq nd; 19 bits cover A
+        const float A = 1.05f * nq * nd + 1e-6f;
+        const float fix_scale = kXFixHalf / (A * 65536.0f), inv_scale = 1.0f / fix_scale;
+        const int m_fix = (int)ceilf(2.0f * E * 65536.0f * fix_scale) + 2;
+        const bool range_bad = !(nq2 <= 1.002f) || m_fix > 200000;   // un-normalised input / degenerate scale: rescan everything
         uint32_t ucnt = 0;
         for (int v = p.v_begin + blockIdx.x; v < p.v_end; v += gridDim.x) {
             const XItem t = x_item(p, v);
@@ -428,12 +520,12 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                 for (int i = 0; i < maxc; ++i) {
                     uint32_t vb, col;
                     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(vb), "=r"(col) : "r"(app + i * 256) : "memory");
-                    const float tf = __fmaf_rn(__uint_as_float(vb), 4.0f, kXFixBias + kXFixMagic);
+                    const float tf = __fmaf_rn(__uint_as_float(vb), fix_scale, kXFixHalf + kXFixMagic);
                     const uint32_t P = (__float_as_uint(tf) << kXColBits) | col;
                     x_list_insert<KL>(L, (i < cnt) ? P : 0u);
                 }
                 ptr = app;
-                thr = x_threshold(L[KT - 1], m_fix);
+                thr = x_threshold(L[KT - 1], m_fix, inv_scale);
             };
             auto maybe_flush = [&]() { if (__any_sync(0xffffffffu, ptr > app + (kXCap - 16) * 256)) flush(); };
             for (int kt = 0; kt < t.n_kt; ++kt) {
@@ -449,27 +541,28 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                 tc::tc_fence_after();
                 ++ucnt;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u + (uint32_t)(g * kXBN);
-                float val[32];
+                float val[64];
                 if (!(p.debug & 2)) {
-                    tc::tmem_ld_32x32b_x32(taddr, val);
-                    tc::tmem_ld_wait();
-                    x_scan16<0>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
-                    maybe_flush();
-                    x_scan16<16>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
-                    maybe_flush();
-                }
-                if (nrows > 32 && !(p.debug & 2)) {
-                    tc::tmem_ld_32x32b_x32(taddr + 32u, val);
+                    // both 32-column loads in flight before the one wait; once the values sit in registers the accumulator goes
+                    // straight back to the issuer, whose next MMAs then run under the whole scan of this key tile
+                    tc::tmem_ld_32x32b_x32(taddr, reinterpret_cast<float(&)[32]>(val[0]));
+                    if (nrows > 32) tc::tmem_ld_32x32b_x32(taddr + 32u, reinterpret_cast<float(&)[32]>(val[32]));
                     tc::tmem_ld_wait();
                 }
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&acc_empty[g]);
-                if (nrows > 32 && !(p.debug & 2)) {
-                    x_scan16<0>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
+                if (!(p.debug & 2)) {
+                    x_scan16<0, 0>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
                     maybe_flush();
-                    x_scan16<16>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
+                    x_scan16<0, 16>(val, (uint32_t)vm, (uint32_t)(kt * 64), thr, ptr);
                     maybe_flush();
+                    if (nrows > 32) {
+                        x_scan16<1, 0>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
+                        maybe_flush();
+                        x_scan16<1, 16>(val, (uint32_t)(vm >> 32), (uint32_t)(kt * 64 + 32), thr, ptr);
+                        maybe_flush();
+                    }
                 }
             }
             flush();
@@ -483,16 +576,19 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                     const uint32_t mP = (uint32_t)m_fix << kXColBits;
                     const uint32_t bound = (theta > mP) ? theta - mP : 0u;
                     if (theta != 0u && L[KL - 1] != 0u && L[KL - 1] >= bound) ovf = true;      // more may lie within the margin
+                    // the list is sorted: the survivors are a prefix of it.  All KL key rows are written (16-byte stores, row-major
+                    // [row][KL]); the count says how many of them matter
+                    int krs[KL];
 #pragma unroll
                     for (int s = 0; s < KL; ++s) {
-                        if (L[s] != 0u && L[s] >= bound) {
-                            const int col = (int)(L[s] & ((1u << kXColBits) - 1u));
-                            const int kt = col >> 6, i = col & 63;
-                            const int kr = (kt < t.has_f0) ? kt * kXBN + i : t.f_lo * N + (kt - t.has_f0) * kXBN + i;
-                            p.surv[(size_t)c * p.total_rows + grow] = kr;
-                            ++c;
-                        }
+                        const int col = (int)(L[s] & ((1u << kXColBits) - 1u));
+                        const int kt2 = col >> 6, i = col & 63;
+                        krs[s] = (kt2 < t.has_f0) ? kt2 * kXBN + i : t.f_lo * N + (kt2 - t.has_f0) * kXBN + i;
+                        c += (L[s] != 0u && L[s] >= bound) ? 1 : 0;
                     }
+                    int4* dst = reinterpret_cast<int4*>(p.surv + grow * KL);
+#pragma unroll
+                    for (int s = 0; s < KL; s += 4) dst[s >> 2] = make_int4(krs[s], krs[s + 1], krs[s + 2], krs[s + 3]);
                 }
                 p.cnt[grow] = qvalid ? (c | (ovf ? (1 << 30) : 0)) : 0;
             }
@@ -506,13 +602,13 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 // ------------------------------------------------------------------------------------------
 // refine
 // ------------------------------------------------------------------------------------------
-constexpr int kRRowBytes = 528;              // 128 floats + 16 B pad: float4 row reads of 32 lanes are conflict-free
-constexpr int kRChunk = 128;                 // queries per metadata chunk
-constexpr int kRMaxWarps = 16;
+constexpr int kRWarps = 8;                   // warps per CTA, one query at a time each
+constexpr int kRThreads = kRWarps * 32;
+constexpr int kRMaxOvf = 64;                 // overflowed queries a CTA rescans with all its warps (more: inline, one warp each)
 
 struct RParams {
     const float* xn;         // [total_rows, 128] normalised features
-    const int32_t* surv;     // [KL][total_rows]
+    const int32_t* surv;     // [total_rows][KL] key rows of the survivors, best approximate value first
     const int32_t* cnt;      // [total_rows]
     float* W;                // [R, T, k, N]
     int32_t* I;
@@ -521,14 +617,8 @@ struct RParams {
     long long total_rows;
     float inv_temp;
     unsigned magic_n;
-    int debug;               // timing aids (CRW_TC_DEBUG): 16 = no W / I stores, 32 = no row copies, 64 = no chains (results invalid)
+    int debug;               // timing aids (CRW_TC_DEBUG): 16 = no W / I stores, 32 = no row loads, 64 = no dot products (results invalid)
 };
-
-// one 512-byte feature row global -> shared by the whole warp (16 bytes per lane, asynchronous: cp.async / LDGSTS)
-__device__ __forceinline__ void warp_row_copy_async(uint32_t dst_row_smem, const float* src_row, int lane) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_row_smem + lane * 16), "l"(src_row + lane * 4) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
 // candidate id (slot in the trimmed key set * N + node) of key row kr for query frame n
 __device__ __forceinline__ int x_cand_id(int kr, int n, int N, int ctx, unsigned magic_n) {
@@ -537,84 +627,61 @@ __device__ __forceinline__ int x_cand_id(int kr, int n, int N, int ctx, unsigned
     return slot * N + j;
 }
 
-// the oracle's dot product: sequential fmaf chain over the 128 channels of two staged rows
-__device__ __forceinline__ float x_chain_dot(const uint8_t* krow_smem, const uint8_t* qrow_smem) {
-    const float4* krow = reinterpret_cast<const float4*>(krow_smem);
-    const float4* qrow = reinterpret_cast<const float4*>(qrow_smem);
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int c4 = 0; c4 < 32; ++c4) {
-        const float4 kv = krow[c4], qv = qrow[c4];
-        acc = __fmaf_rn(kv.x, qv.x, acc);
-        acc = __fmaf_rn(kv.y, qv.y, acc);
-        acc = __fmaf_rn(kv.z, qv.z, acc);
-        acc = __fmaf_rn(kv.w, qv.w, acc);
+// lanes [0, k) hold a sorted list (logit desc, id asc), one entry per lane; insert (c, ci) keeping that order.  Candidates may
+// arrive in any order (full comparator).
+__device__ __forceinline__ void x_list_insert_warp(float& v, int& id, float c, int ci, int k, unsigned kmask, int lane) {
+    const int pos = __popc(__ballot_sync(0xffffffffu, v > c || (v == c && id < ci)) & kmask);
+    if (pos < k) {
+        const float vup = __shfl_up_sync(0xffffffffu, v, 1);
+        const int iup = __shfl_up_sync(0xffffffffu, id, 1);
+        if (lane > pos) { v = vup; id = iup; }
+        else if (lane == pos) { v = c; id = ci; }
+        if (lane >= k) v = -INFINITY;
     }
-    return acc;
 }
 
-// Full exact scan of one query by one warp (its survivor list overflowed: many candidates tie within the filter margin).  The
-// in-band candidates are visited in ascending id order, 32 at a time through the warp's staging buffer; lane i keeps the i-th
-// best (the insertion of lp_topk_f32_kernel).  Returns this lane's (logit, id).
-// round_begin / round_stride: this warp visits rounds round_begin, round_begin + round_stride, ... (0, 1 = all of them)
-template <int CAP>
-__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, uint8_t* buf, int n, int q, int k, int round_begin, int round_stride,
+// Exact scan of the in-band candidates number c = round_begin * 16 + 16 j ... of one query by one warp (its survivor list
+// overflowed: many candidates tie within the filter margin): rounds of 16 candidates, their rows loaded together, one warp dot
+// each; lane i keeps the i-th best seen by this warp.  round_stride > 1: the rounds are dealt to several warps.
+__device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, int n, int q, int k, int round_begin, int round_stride,
                                             float& v_out, int& id_out) {
-    constexpr int kStep = CAP < 32 ? CAP : 32;      // candidates per round
     const int lane = threadIdx.x & 31;
     const int N = p.N, rb = p.rb;
     const int F = n_key_frames(n, p.ctx);
     const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     float v = -INFINITY;
     int id = 0;
-    float thr = -INFINITY;
     const int jlo = max(0, q - rb), jhi = min(N - 1, q + rb), bw = jhi - jlo + 1;
-    const uint32_t sbuf = tc::smem_u32(buf);
-    warp_row_copy_async(sbuf + CAP * kRRowBytes, xr + ((size_t)n * N + q) * 128, lane);
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)n * N + q) * 128) + lane);
     const int total = F * bw;                          // in-band candidates, ascending id = (frame slot, node)
-    for (int c0 = round_begin * kStep; c0 < total; c0 += round_stride * kStep) {
-        const int nrow = min(kStep, total - c0);
-        __syncwarp();
-        for (int r = 0; r < nrow; ++r) {
-            const int cc = c0 + r, f = cc / bw, jj = cc - f * bw;
-            warp_row_copy_async(sbuf + r * kRRowBytes, xr + ((size_t)key_frame(n, p.ctx, f) * N + jlo + jj) * 128, lane);
+    for (int c0 = round_begin * 16; c0 < total; c0 += round_stride * 16) {
+        const int nrow = min(16, total - c0);
+        // sixteen unconditional loads, issued back to back (indices past the end repeat the last candidate: ignored below)
+        float4 kv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int cc = min(c0 + r, total - 1), f = cc / bw, jj = cc - f * bw;
+            kv[r] = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)key_frame(n, p.ctx, f) * N + jlo + jj) * 128) + lane);
         }
-        cp_async_wait_all();
-        __syncwarp();
-        const bool ok = lane < nrow;
-        float cand = -INFINITY;
-        if (ok) cand = __fmul_rn(x_chain_dot(buf + lane * kRRowBytes, buf + CAP * kRRowBytes), p.inv_temp);
-        const int cc = c0 + lane, fl = cc / bw;
-        const int cid = fl * N + jlo + (cc - fl * bw);
-        unsigned m = __ballot_sync(0xffffffffu, ok && cand > thr);
-        while (m) {
-            const int s = __ffs(m) - 1;
-            m &= m - 1;
-            const float c = __shfl_sync(0xffffffffu, cand, s);
-            const int ci = __shfl_sync(0xffffffffu, cid, s);
-            if (c > thr) {
-                const int pos = __popc(__ballot_sync(0xffffffffu, v >= c) & kmask);
-                const float vup = __shfl_up_sync(0xffffffffu, v, 1);
-                const int iup = __shfl_up_sync(0xffffffffu, id, 1);
-                if (lane > pos) { v = vup; id = iup; }
-                else if (lane == pos) { v = c; id = ci; }
-                if (lane >= k) v = -INFINITY;
-                thr = __shfl_sync(0xffffffffu, v, k - 1);
-            }
+        float part[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) part[r] = x_partial4(kv[r], qv);
+        const float mine = __fmul_rn(x_warp_dot16(part, lane), p.inv_temp);           // candidate c0 + (lane >> 1)
+        for (int r = 0; r < nrow; ++r) {                                               // ascending id
+            const float cand = __shfl_sync(0xffffffffu, mine, 2 * r);
+            const int cc = c0 + r, f = cc / bw;
+            x_list_insert_warp(v, id, cand, f * N + jlo + (cc - f * bw), k, kmask, lane);
         }
     }
-    __syncwarp();
     v_out = v;
     id_out = id;
 }
 
-// Per lane group (sub_base .. sub_base + SL): lane sl holds the winner of rank sl, (logit desc, id asc), `live` of them real.
-// Masked fill, pinned softmax (sequential sum in rank order), W / I stores.  Every lane of the warp calls this; groups without a
-// query pass active = false.  es: k floats of scratch per group.
-__device__ __forceinline__ void x_finish_group(const RParams& p, float v, int id, bool active, int live, int rg, int n, int q, int k,
-                                               int sub_base, int sl, float* es) {
+// lane sl holds the winner of rank sl, (logit desc, id asc), `live` of them real: masked fill, pinned softmax (sequential sum
+// in rank order), W / I stores.  es: k floats of scratch of this warp.
+__device__ __forceinline__ void x_finish_query(const RParams& p, float v, int id, int live, int rg, int n, int q, int k, int sl, float* es) {
     const int N = p.N, rb = p.rb;
-    if (active && sl >= live && sl < k) {
+    if (sl >= live && sl < k) {
         // fewer than k in-band candidates: out-of-band ones share one logit and come in ascending id order
         const int lo_q = max(0, q - rb), w_q = min(N - 1, q + rb) - lo_q + 1, nob = max(N - w_q, 1);
         const int t = sl - live, f = t / nob, r = t - f * nob;
@@ -622,8 +689,8 @@ __device__ __forceinline__ void x_finish_group(const RParams& p, float v, int id
         v = __fmul_rn(kMaskBias, p.inv_temp);
         id = f * N + jj;
     }
-    const float v0 = __shfl_sync(0xffffffffu, v, sub_base);
-    const bool w = active && sl < k;
+    const float v0 = __shfl_sync(0xffffffffu, v, 0);
+    const bool w = sl < k;
     const float e = w ? pinned_expf(__fsub_rn(v, v0)) : 0.0f;
     if (w) es[sl] = e;
     __syncwarp();
@@ -640,208 +707,135 @@ __device__ __forceinline__ void x_finish_group(const RParams& p, float v, int id
     }
 }
 
-// SL = survivor slots per query handled by one lane group (16: two queries per pass; 32: one query per pass); WARPS autonomous
-// warps per CTA, each with a staging buffer of SROWS feature rows (the last 32 / SL of them hold the query rows).
-// A CTA owns a contiguous range of query rows and walks it in chunks of kRChunk queries: all threads first stage the chunk's
-// survivor lists (counts + key rows) in shared memory with coalesced loads.  Then every warp works on its own passes: the fp32
-// rows of the survivors (and the query rows) are copied into the warp's staging buffer with cp.async, one coalesced 512-byte
-// row per instruction, packed in survivor order; each lane then runs the sequential chain for its own survivor slot from
-// shared memory.  The bytes in flight per SM (what bounds this gather) are WARPS x ~11 rows x 512 B.
-template <int SL, int WARPS, int SROWS>
-__global__ void __launch_bounds__(WARPS * 32, 1) lp_refine_kernel(RParams p) {
-    constexpr int QPB = 32 / SL;             // queries per pass
-    constexpr int kCapRows = SROWS - QPB;    // survivor rows one pass can stage
-    constexpr int kBufBytes = SROWS * kRRowBytes;
-    constexpr int kThreads = WARPS * 32;
-    extern __shared__ __align__(128) uint8_t rsm[];
-    __shared__ float es_all[WARPS][2][32];
-    __shared__ float sc_v[WARPS][32];
-    __shared__ int sc_i[WARPS][32];
-    __shared__ int s_cnt[kRChunk];
-    constexpr int kMaxOvf = 64;              // overflowed queries of a chunk that are rescanned by the whole CTA (more: inline, one warp each)
-    __shared__ int s_ovf[kMaxOvf], s_novf;
-    int* s_kr = reinterpret_cast<int*>(rsm + (size_t)WARPS * kBufBytes);      // [SL][kRChunk]
+// KL = survivor slots per query (16 or 32).  One warp per query: the fp32 rows of the survivors come straight from L2 into
+// registers (one coalesced 512-byte row per load instruction, all of a query's loads in flight together), every dot product is
+// one warp dot in the oracle's order -- no shared-memory staging, so the kernel is bound by the row gather itself.
+template <int KL>
+__global__ void __launch_bounds__(kRThreads, 2) lp_refine_kernel(RParams p) {
+    __shared__ float es_all[kRWarps][32];
+    __shared__ float sc_v[kRWarps][32];
+    __shared__ int sc_i[kRWarps][32];
+    __shared__ int s_ovf[kRMaxOvf];
+    __shared__ int s_novf;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, k = p.k;
-    // this CTA's share of the launch: rows [r_lo, r_hi) of the flattened (radargram, row in [row_begin, row_end)) space
+    const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    if (tid == 0) s_novf = 0;
+    __syncthreads();
+    // this CTA's share of the launch: queries [r_lo, r_hi) of the flattened (radargram, row in [row_begin, row_end)) space
+    // (32-bit arithmetic: the host checks R * rows < 2^31; the radargram / row split is kept incrementally, no divisions)
     const int rows_launch = p.row_end - p.row_begin;
-    const long long total_q = (long long)p.R * rows_launch;
-    long long per = (total_q + gridDim.x - 1) / gridDim.x;
-    per = (per + QPB - 1) / QPB * QPB;
-    const long long r_lo = (long long)blockIdx.x * per, r_hi = min(total_q, r_lo + per);
-    const int ql = lane / SL, s = lane % SL, sub_base = ql * SL;
+    const int total_q = p.R * rows_launch;
+    const int per = (total_q + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int r_lo = (int)blockIdx.x * per, r_hi = min(total_q, r_lo + per);
     const bool prof = (p.debug & 8) != 0;
-    uint8_t* buf = rsm + (size_t)warp * kBufBytes;
-    const uint32_t sbuf = tc::smem_u32(buf);
 
-    for (long long c0 = r_lo; c0 < r_hi; c0 += kRChunk) {
-        const int nq = (int)min((long long)kRChunk, r_hi - c0);
-        const long long c_s0 = prof ? clock64() : 0;
-        if (tid == 0) s_novf = 0;
-        // ---- stage the chunk's metadata: every thread issues its loads back to back (independent, coalesced along the rows) ----
-        const int rg0 = (int)(c0 / rows_launch);
-        const int row0 = p.row_begin + (int)(c0 - (long long)rg0 * rows_launch);        // chunk row i: row0 + i, wrapping into the next radargram
-        {
-            constexpr int kPer = (SL * kRChunk + kThreads - 1) / kThreads;
-            int vals[kPer];
-#pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-                const int j = tid + u * kThreads, sl = j / kRChunk, i = j - sl * kRChunk;
-                int rg = rg0, row = row0 + i;
-                while (row >= p.row_end) { row -= rows_launch; ++rg; }
-                vals[u] = (sl < SL && i < nq) ? __ldg(p.surv + (size_t)sl * p.total_rows + (size_t)rg * p.rows_rg + row) : 0;
-            }
-            if (tid < nq) {
-                int rg = rg0, row = row0 + tid;
-                while (row >= p.row_end) { row -= rows_launch; ++rg; }
-                s_cnt[tid] = __ldg(p.cnt + (size_t)rg * p.rows_rg + row);
-            }
-#pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-                const int j = tid + u * kThreads;
-                if (j < SL * kRChunk) s_kr[j] = vals[u];
-            }
-        }
-        __syncthreads();
-        const long long c_s1 = prof ? clock64() : 0;
-        XPROF(1, 0, c_s1 - c_s0);
-        const int nbuf = (nq + QPB - 1) / QPB;
-        for (int b = warp; b < nbuf; b += WARPS) {
-            const int i = b * QPB + ql;
-            int rg = rg0, row = row0 + i;
-            while (row >= p.row_end) { row -= rows_launch; ++rg; }
-            const int n = row / N, q = row - n * N;
-            int c = (i < nq) ? s_cnt[i] : 0;
-            const bool rescan = (c >> 30) & 1;
-            c = rescan ? 0 : (c & 0xffff);
-            const bool valid = s < c;
-            const int kr = valid ? s_kr[s * kRChunk + i] : 0;
-            const bool is_query = i < nq && n >= 1 && n < p.T;
-            const unsigned vall = __ballot_sync(0xffffffffu, valid);
-            // the staging buffer holds kCapRows survivor rows: when the pass has more (two long lists), the lane groups go one by one
-            const int nsteps = (__popc(vall) > kCapRows) ? QPB : 1;
-            for (int step = 0; step < nsteps; ++step) {
-                const long long c_c0 = prof ? clock64() : 0;
-                const bool mine = valid && (nsteps == 1 || ql == step);
-                const unsigned vmask = __ballot_sync(0xffffffffu, mine);
-                const int srow = __popc(vmask & ((1u << lane) - 1u));          // this lane's row of the staging buffer
-                if (!(p.debug & 32)) {
-                    unsigned m = vmask;
-                    int r_stage = 0;
-                    while (m) {
-                        const int r = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int kr_r = __shfl_sync(0xffffffffu, kr, r);
-                        const int rg_r = __shfl_sync(0xffffffffu, rg, r);
-                        warp_row_copy_async(sbuf + r_stage * kRRowBytes, p.xn + ((size_t)rg_r * p.rows_rg + kr_r) * 128, lane);
-                        ++r_stage;
-                    }
-#pragma unroll
-                    for (int grp = 0; grp < QPB; ++grp) {
-                        if (nsteps > 1 && grp != step) continue;
-                        const int c_g = __shfl_sync(0xffffffffu, c, grp * SL);
-                        if (c_g > 0) {
-                            const int rg_g = __shfl_sync(0xffffffffu, rg, grp * SL), row_g = __shfl_sync(0xffffffffu, row, grp * SL);
-                            warp_row_copy_async(sbuf + (kCapRows + grp) * kRRowBytes, p.xn + ((size_t)rg_g * p.rows_rg + row_g) * 128, lane);
-                        }
-                    }
-                }
-                cp_async_wait_all();
-                __syncwarp();
-                const long long c_c1 = prof ? clock64() : 0;
-                float acc = 0.0f;
-                if (mine && !(p.debug & 64)) acc = x_chain_dot(buf + srow * kRRowBytes, buf + (kCapRows + ql) * kRRowBytes);
-                __syncwarp();                                                 // the staging buffer may be refilled
-                const long long c_c2 = prof ? clock64() : 0;
-                const float lg = mine ? __fmul_rn(acc, p.inv_temp) : -INFINITY;
-                const int id = mine ? x_cand_id(kr, n, N, p.ctx, p.magic_n) : 0x7fffffff;
-                // rank among the query's survivors: (logit desc, id asc)
-                int rank = 0;
-#pragma unroll
-                for (int o = 0; o < SL; ++o) {
-                    const float lo_ = __shfl_sync(0xffffffffu, lg, sub_base + o);
-                    const int io = __shfl_sync(0xffffffffu, id, sub_base + o);
-                    rank += (lo_ > lg || (lo_ == lg && io < id)) ? 1 : 0;
-                }
-                // move every survivor to the lane of its rank within the query's lane group (rank < c <= SL)
-                if (mine) { sc_v[warp][sub_base + rank] = lg; sc_i[warp][sub_base + rank] = id; }
-                __syncwarp();
-                float v = -INFINITY;
-                int idv = 0;
-                const bool grp_on = nsteps == 1 || ql == step;
-                if (grp_on && s < c) { v = sc_v[warp][lane]; idv = sc_i[warp][lane]; }
-                __syncwarp();
-                x_finish_group(p, v, idv, grp_on && is_query && !rescan, min(c, k), rg, n, q, k, sub_base, s, es_all[warp][ql]);
-                if (prof) { const long long c_c3 = clock64(); XPROF(1, 1, c_c1 - c_c0); XPROF(1, 2, c_c2 - c_c1); XPROF(1, 3, c_c3 - c_c2); }
-            }
-            // overflowed lists: queued for a rescan by the whole CTA after the chunk (inline by this warp when the queue is full)
-            const long long c_r0 = prof ? clock64() : 0;
-#pragma unroll
-            for (int grp = 0; grp < QPB; ++grp) {
-                const int need = __shfl_sync(0xffffffffu, (rescan && is_query) ? 1 : 0, grp * SL);
-                if (!need) continue;                                         // warp-uniform
-                const int g_i = __shfl_sync(0xffffffffu, i, grp * SL);
-                int slot = 0;
-                if (lane == 0) slot = atomicAdd(&s_novf, 1);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot < kMaxOvf) {
-                    if (lane == 0) s_ovf[slot] = g_i;
-                    continue;
-                }
-                const int g_n = __shfl_sync(0xffffffffu, n, grp * SL), g_q = __shfl_sync(0xffffffffu, q, grp * SL);
-                const int g_rg = __shfl_sync(0xffffffffu, rg, grp * SL);
+    // the survivor list of the NEXT query of this warp is fetched while the current one is worked on (two dependent global loads
+    // off the critical path)
+    auto fetch_meta = [&](int f, int rg, int row, int& cword, int& kr) {
+        cword = 0;
+        kr = 0;
+        if (f >= r_hi) return;
+        const size_t grow = (size_t)rg * p.rows_rg + row;
+        cword = __ldg(p.cnt + grow);
+        kr = (lane < KL) ? __ldg(p.surv + grow * KL + lane) : 0;                      // (slots beyond the count hold stale rows: unused)
+    };
+    int cword_n, kr_n;
+    int rg_n = (r_lo + warp) / rows_launch, row_n = p.row_begin + (r_lo + warp) - rg_n * rows_launch;       // (once per warp)
+    fetch_meta(r_lo + warp, rg_n, row_n, cword_n, kr_n);
+    for (int f = r_lo + warp; f < r_hi; f += kRWarps) {
+        const long long c_0 = prof ? clock64() : 0;
+        const int cword = cword_n, kr = kr_n, rg = rg_n, row = row_n;
+        row_n += kRWarps;
+        while (row_n >= p.row_end) { row_n -= rows_launch; ++rg_n; }
+        fetch_meta(f + kRWarps, rg_n, row_n, cword_n, kr_n);
+        const int n = (int)__umulhi((unsigned)row, p.magic_n), q = row - n * N;
+        if (n < 1 || n >= p.T) continue;                                  // warp-uniform
+        const bool rescan = (cword >> 30) & 1;
+        if (rescan) {                                                        // queued: rescanned by the whole CTA at the end
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(&s_novf, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < kRMaxOvf) {
+                if (lane == 0) s_ovf[slot] = f;
+            } else {
                 float fv;
                 int fid;
-                x_full_scan<kCapRows>(p, p.xn + (size_t)g_rg * p.rows_rg * 128, buf, g_n, g_q, k, 0, 1, fv, fid);
-                const int g_live = __popc(__ballot_sync(0xffffffffu, fv > -INFINITY) & ((k >= 32) ? 0xffffffffu : ((1u << k) - 1u)));
-                x_finish_group(p, fv, fid, true, g_live, g_rg, g_n, g_q, k, 0, lane, es_all[warp][0]);
+                x_full_scan(p, p.xn + (size_t)rg * p.rows_rg * 128, n, q, k, 0, 1, fv, fid);
+                const int live = __popc(__ballot_sync(0xffffffffu, fv > -INFINITY) & kmask);
+                x_finish_query(p, fv, fid, live, rg, n, q, k, lane, es_all[warp]);
             }
-            if (prof) XPROF(1, 4, clock64() - c_r0);
+            continue;
+        }
+        const int c = cword & 0xffff;
+        const float* xr = p.xn + (size_t)rg * p.rows_rg * 128;
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(xr + (size_t)row * 128) + lane);
+        float lg = -INFINITY;
+#pragma unroll
+        for (int sb = 0; sb < KL; sb += 16) {                            // (c <= KL: the slots beyond it are never touched)
+            if (sb >= c) break;                                              // warp-uniform
+            // all sixteen row loads are unconditional and issued back to back (slots past the count repeat the last survivor's
+            // row: same address, merged in L1, and their dots are ignored), so that they are in flight together
+            float4 kv[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                const int kr_s = __shfl_sync(0xffffffffu, kr, min(sb + s, c - 1));
+                kv[s] = __ldg(reinterpret_cast<const float4*>(xr + (size_t)kr_s * 128) + lane);
+            }
+            float part[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) part[s] = x_partial4(kv[s], qv);
+            const float mine = x_warp_dot16(part, lane);                     // dot of slot sb + (lane >> 1)
+            const float d = __shfl_sync(0xffffffffu, mine, (2 * (lane - sb)) & 31);
+            if (lane >= sb && lane < sb + 16 && lane < c) lg = __fmul_rn(d, p.inv_temp);
+        }
+        const long long c_1 = prof ? clock64() : 0;
+        const bool valid = lane < c;
+        const int id = valid ? x_cand_id(kr, n, N, p.ctx, p.magic_n) : 0x7fffffff;
+        // rank among the survivors: (logit desc, id asc)
+        int rank = 0;
+#pragma unroll 4
+        for (int o = 0; o < c; ++o) {
+            const float lo_ = __shfl_sync(0xffffffffu, lg, o);
+            const int io = __shfl_sync(0xffffffffu, id, o);
+            rank += (lo_ > lg || (lo_ == lg && io < id)) ? 1 : 0;
+        }
+        // every survivor moves to the lane of its rank
+        if (valid) { sc_v[warp][rank] = lg; sc_i[warp][rank] = id; }
+        __syncwarp();
+        float v = -INFINITY;
+        int idv = 0;
+        if (valid) { v = sc_v[warp][lane]; idv = sc_i[warp][lane]; }
+        __syncwarp();
+        x_finish_query(p, v, idv, min(c, k), rg, n, q, k, lane, es_all[warp]);
+        if (prof) { const long long c_2 = clock64(); XPROF(1, 1, c_1 - c_0); XPROF(1, 3, c_2 - c_1); }
+    }
+    __syncthreads();
+    // ---- queued rescans: every warp scans its share of the candidate rounds, warp 0 merges the partial lists ----
+    const int novf = min(s_novf, kRMaxOvf);
+    for (int e = 0; e < novf; ++e) {
+        const int f = s_ovf[e];
+        const int rg = f / rows_launch, row = p.row_begin + f - rg * rows_launch;
+        const int n = row / N, q = row - n * N;
+        float pv;
+        int pi;
+        x_full_scan(p, p.xn + (size_t)rg * p.rows_rg * 128, n, q, k, warp, kRWarps, pv, pi);
+        sc_v[warp][lane] = pv;
+        sc_i[warp][lane] = pi;
+        __syncthreads();
+        if (warp == 0) {
+            float v = -INFINITY;
+            int id = 0;
+            for (int w2 = 0; w2 < kRWarps; ++w2)
+                for (int s2 = 0; s2 < k; ++s2) {
+                    const float c = sc_v[w2][s2];
+                    if (!(c > -INFINITY)) break;                              // (warp-uniform) lists are sorted: the rest is empty
+                    x_list_insert_warp(v, id, c, sc_i[w2][s2], k, kmask, lane);
+                }
+            const int live = __popc(__ballot_sync(0xffffffffu, v > -INFINITY) & kmask);
+            x_finish_query(p, v, id, live, rg, n, q, k, lane, es_all[0]);
         }
         __syncthreads();
-        // ---- queued rescans: every warp scans its share of the candidate rounds, warp 0 merges the partial lists ----
-        {
-            const long long c_r0 = prof ? clock64() : 0;
-            const int novf = min(s_novf, kMaxOvf);
-            const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-            for (int e = 0; e < novf; ++e) {
-                const int i = s_ovf[e];
-                int rg = rg0, row = row0 + i;
-                while (row >= p.row_end) { row -= rows_launch; ++rg; }
-                const int n = row / N, q = row - n * N;
-                float pv;
-                int pi;
-                x_full_scan<kCapRows>(p, p.xn + (size_t)rg * p.rows_rg * 128, buf, n, q, k, warp, WARPS, pv, pi);
-                sc_v[warp][lane] = pv;
-                sc_i[warp][lane] = pi;
-                __syncthreads();
-                if (warp == 0) {
-                    float v = -INFINITY;
-                    int id = 0;
-                    for (int w2 = 0; w2 < WARPS; ++w2)
-                        for (int s2 = 0; s2 < k; ++s2) {
-                            const float c = sc_v[w2][s2];
-                            const int ci = sc_i[w2][s2];
-                            if (!(c > -INFINITY)) break;                                  // (warp-uniform) lists are sorted: the rest is empty
-                            // candidates arrive in no particular order: full comparator (logit desc, id asc)
-                            const int pos = __popc(__ballot_sync(0xffffffffu, v > c || (v == c && id < ci)) & kmask);
-                            if (pos < k) {
-                                const float vup = __shfl_up_sync(0xffffffffu, v, 1);
-                                const int iup = __shfl_up_sync(0xffffffffu, id, 1);
-                                if (lane > pos) { v = vup; id = iup; }
-                                else if (lane == pos) { v = c; id = ci; }
-                                if (lane >= k) v = -INFINITY;
-                            }
-                        }
-                    const int live = __popc(__ballot_sync(0xffffffffu, v > -INFINITY) & kmask);
-                    x_finish_group(p, v, id, true, live, rg, n, q, k, 0, lane, es_all[0][0]);
-                }
-                __syncthreads();
-            }
-            if (prof) XPROF(1, 4, clock64() - c_r0);
-        }
-        __syncthreads();                      // the metadata of this chunk is dead
-        if (prof) XPROF(1, 5, clock64() - c_s0);
     }
 }
 
@@ -862,13 +856,13 @@ static void x_kt_kl(int k, int& kt, int& kl) {
 }
 int lp_x_max_k() { return 24; }
 
-// scratch layout of the exact tensor path: stats | fp16 plane | xn (when normalising) | survivors | counts
+// scratch layout of the exact tensor path: stats + column sums | fp16 query plane | fp16 key plane | xn (when normalising) | survivors | counts
 size_t lp_x_scratch_bytes(int R, int T, int N, int C, int k, int do_normalize) {
     int kt, kl;
     x_kt_kl(k, kt, kl);
     const size_t rows = (size_t)R * T * N;
-    size_t b = 256;
-    b += align_up(rows * C * sizeof(__half), 256);
+    size_t b = align_up((size_t)kXStatBytes + (size_t)R * 128 * sizeof(float), 256);
+    b += 2 * align_up(rows * C * sizeof(__half), 256);
     if (do_normalize) b += align_up(rows * C * sizeof(float), 256);
     b += align_up(rows * kl * sizeof(int32_t), 256);
     b += align_up(rows * sizeof(int32_t), 256);
@@ -897,20 +891,15 @@ static int launch_filter(const LpXPlan& plan, const XParams& p, int max_ctas, cu
     return CRW_OK;
 }
 
-template <int SL, int WARPS, int SROWS>
+template <int KL>
 static int launch_refine(const RParams& r, int max_ctas, cudaStream_t st) {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const size_t smem = (size_t)WARPS * SROWS * kRRowBytes + (size_t)SL * kRChunk * sizeof(int);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        CRW_CUDA_RET(cudaFuncSetAttribute(lp_refine_kernel<SL, WARPS, SROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
-    const long long bufs = ((long long)r.R * (r.row_end - r.row_begin) + 32 / SL - 1) / (32 / SL);
-    if (bufs <= 0) return CRW_OK;
-    const int grid = (int)(bufs < max_ctas ? bufs : max_ctas);
-    lp_refine_kernel<SL, WARPS, SROWS><<<grid, WARPS * 32, smem, st>>>(r);
+    const long long total_q = (long long)r.R * (r.row_end - r.row_begin);
+    if (total_q <= 0) return CRW_OK;
+    if (total_q >= (1ll << 31) - 65536) return CRW_ERR_UNSUPPORTED;
+    // two CTAs of 8 warps per SM; a CTA's share is a contiguous range of queries (neighbouring queries share their key window)
+    long long ctas = (total_q + 4 * kRWarps - 1) / (4 * kRWarps);
+    if (ctas > 2LL * max_ctas) ctas = 2LL * max_ctas;
+    lp_refine_kernel<KL><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -927,8 +916,12 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
     char* sp = reinterpret_cast<char*>(scratch);
     unsigned* stats = reinterpret_cast<unsigned*>(sp);
-    sp += 256;
-    __half* h = reinterpret_cast<__half*>(sp);
+    float* musum = reinterpret_cast<float*>(sp + kXStatBytes);
+    const size_t head = align_up((size_t)kXStatBytes + (size_t)R * 128 * sizeof(float), 256);
+    sp += head;
+    __half* hq = reinterpret_cast<__half*>(sp);
+    sp += align_up(rows * C * sizeof(__half), 256);
+    __half* hk = reinterpret_cast<__half*>(sp);
     sp += align_up(rows * C * sizeof(__half), 256);
     float* xn = nullptr;
     if (do_normalize) { xn = reinterpret_cast<float*>(sp); sp += align_up(rows * C * sizeof(float), 256); }
@@ -936,11 +929,16 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     sp += align_up(rows * plan->kl * sizeof(int32_t), 256);
     int32_t* cnt = reinterpret_cast<int32_t*>(sp);
 
-    CRW_CUDA_RET(cudaMemsetAsync(stats, 0, 256, st));
-    {
-        const int64_t blocks = ((int64_t)rows + 7) / 8;
-        if (blocks > 0x7fffffffLL) return CRW_ERR_UNSUPPORTED;
-        lp_prep_x_kernel<<<(unsigned)blocks, 256, 0, st>>>(feats, (int64_t)rows, do_normalize, xn, h, stats);
+    CRW_CUDA_RET(cudaMemsetAsync(stats, 0, head, st));
+    if (rows > 0) {
+        const int rows_rg = T * N;
+        const dim3 grid((unsigned)((rows_rg + 7) / 8), (unsigned)R);
+        if (R > 65535) return CRW_ERR_UNSUPPORTED;
+        // pass 1 walks its rows with a bounded grid (each CTA ends with one atomicAdd per column): ~8 CTAs per SM over all radargrams
+        const unsigned per_rg = (unsigned)max(1, min((rows_rg + 7) / 8, (8 * max(sms, 1) + R - 1) / R));
+        lp_prep_x_kernel<<<dim3(per_rg, (unsigned)R), 256, 0, st>>>(feats, rows_rg, do_normalize, xn, hq, musum, stats);
+        CRW_LAUNCH_RET();
+        lp_center_x_kernel<<<grid, 256, 0, st>>>(do_normalize ? xn : feats, rows_rg, musum, hk, stats);
         CRW_LAUNCH_RET();
     }
     XParams& p = plan->p;
@@ -982,8 +980,8 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     r.total_rows = p.total_rows; r.inv_temp = p.inv_temp; r.magic_n = p.magic_n; r.debug = p.debug;
     if (T < 2) return CRW_OK;
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(plan->maps);
-    int rc = make_tmap_bf16_k64(&maps[0], h, (uint64_t)rows, 128, kXBM);      // 2-byte elements: the bf16 map type moves fp16 as well
-    if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[1], h, (uint64_t)rows, 128, kXBN);
+    int rc = make_tmap_bf16_k64(&maps[0], hq, (uint64_t)rows, 128, kXBM);     // 2-byte elements: the bf16 map type moves fp16 as well
+    if (rc == CRW_OK) rc = make_tmap_bf16_k64(&maps[1], hk, (uint64_t)rows, 128, kXBN);
     return rc;
 }
 int lp_x_total_slots(const void* plan) { const LpXPlan* pl = reinterpret_cast<const LpXPlan*>(plan); return pl->p.R * pl->p.items_per_rg; }
@@ -1011,7 +1009,9 @@ int lp_x_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, 
     const int early_slots = p.R * p.early_items_rg, early_rows = lp_x_early_rows(plan_storage);
     r.row_begin = (v_begin >= early_slots) ? early_rows : 0;
     r.row_end = (v_end <= early_slots) ? early_rows : p.rows_rg;
-    return plan.kl <= 16 ? launch_refine<16, 16, 24>(r, max_ctas, st) : launch_refine<32, 11, 33>(r, max_ctas, st);
+    if (plan.kl == 16) return launch_refine<16>(r, max_ctas, st);
+    if (plan.kl == 24) return launch_refine<24>(r, max_ctas, st);
+    return launch_refine<32>(r, max_ctas, st);
 }
 size_t lp_x_plan_bytes() { return sizeof(LpXPlan); }
 int lp_x_profile_read(unsigned long long* host_out, int reset) {

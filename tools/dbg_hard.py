@@ -24,7 +24,7 @@ for kind in ["white_noise", "layered"]:
     kl = 16 if k <= 10 else (24 if k <= 16 else 32)
     rows = R * T * N
     base = (-scratch.data_ptr()) % 256
-    off = base + 256 + align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
+    off = base + align(512 + R * 512) + 2 * align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
     cnt = scratch[off:off + rows * 4].view(torch.int32).view(T, N)
     ovf = (cnt >> 30) & 1
     badI = (I[0, 1:] != I32[0, 1:]).any(dim=1)   # [T-1, N]

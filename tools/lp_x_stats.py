@@ -31,13 +31,13 @@ def stats(name, feats, k, radius):
     kl = 16 if k <= 10 else (24 if k <= 16 else 32)
     rows = R * T * N
     base = (-scratch.data_ptr()) % 256
-    off = base + 256 + align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
+    off = base + align(512 + R * 512) + 2 * align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
     cnt = scratch[off:off + rows * 4].view(torch.int32).view(R, T, N)[:, 1:]
-    st = scratch[base:base + 8].view(torch.float32)
+    st = scratch[base:base + 512].view(torch.float32).view(32, 4).max(dim=0).values
     ovf = (cnt >> 30) & 1
     c = (cnt & 0xffff).float()
     print(f"{name:28s} k={k} r={radius}: survivors/query mean {c.mean():.2f} max {int(c.max())}  overflowed {int(ovf.sum())} of {cnt.numel()}"
-          f"  max|x|^2 {st[0]:.6f} max residual {st[1].sqrt():.2e}")
+          f"  max|x| {st[0].sqrt():.4f} res {st[1].sqrt():.2e}; centred keys: max|k - mu| {st[2].sqrt():.4f} res {st[3].sqrt():.2e}")
 
 
 torch.manual_seed(3)

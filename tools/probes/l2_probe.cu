@@ -56,6 +56,53 @@ __global__ void __launch_bounds__(256) k_lanerow(const float4* __restrict__ buf,
     if (acc == 123.456f) out[0] = acc;
 }
 
+// warp-per-row gather through cp.async (LDGSTS, 16 B per lane = one 512 B row per instruction) into a per-warp staging buffer
+// of `rows_per_pass` rows, wait, touch, repeat -- the refine kernel's first staging scheme
+__global__ void __launch_bounds__(512) k_ldgsts(const float4* __restrict__ buf, uint32_t rows, int passes, int rows_per_pass, float* out) {
+    extern __shared__ __align__(128) uint8_t st[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t* my = st + (size_t)warp * rows_per_pass * 528;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(my);
+    float acc = 0.f;
+    for (int pss = 0; pss < passes; ++pss) {
+        for (int r = 0; r < rows_per_pass; ++r) {
+            const uint32_t row = hash32(gw * 7919u + pss * 131u + r) % rows;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + r * 528 + lane * 16), "l"(buf + (size_t)row * 32 + lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        acc += reinterpret_cast<const float*>(my)[lane * 132 % (rows_per_pass * 132)];
+        __syncwarp();
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+// the same gather with LDG.128 into registers (8 rows in flight per batch) and STS.128 into the staging buffer
+__global__ void __launch_bounds__(512) k_ldg_sts(const float4* __restrict__ buf, uint32_t rows, int passes, int rows_per_pass, float* out) {
+    extern __shared__ __align__(128) uint8_t st[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t* my = st + (size_t)warp * rows_per_pass * 528;
+    float acc = 0.f;
+    for (int pss = 0; pss < passes; ++pss) {
+        for (int r0 = 0; r0 < rows_per_pass; r0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t row = hash32(gw * 7919u + pss * 131u + r0 + u) % rows;
+                v[u] = __ldcg(buf + (size_t)row * 32 + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (r0 + u < rows_per_pass) *reinterpret_cast<float4*>(my + (r0 + u) * 528 + lane * 16) = v[u];
+        }
+        __syncwarp();
+        acc += reinterpret_cast<const float*>(my)[lane * 132 % (rows_per_pass * 132)];
+        __syncwarp();
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __global__ void __launch_bounds__(128) k_bulk(const uint8_t* __restrict__ buf, size_t bytes, int chunks_per_cta, float* out) {
     extern __shared__ __align__(128) uint8_t sm[];
@@ -125,6 +172,18 @@ int main() {
         for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_bulk<<<sms, 128, 8 * 16384>>>(buf, bytes, chunks, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
         cudaEventElapsedTime(&ms, e0, e1);
         report("cp.async.bulk 16 KB x8 deep", (double)sms * chunks * 16384, ms);
+    }
+    for (int rpp : {8, 16, 24}) {
+        const int passes = 64, warps = 16;
+        const size_t smem = (size_t)warps * rpp * 528;
+        CK(cudaFuncSetAttribute(k_ldgsts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_ldg_sts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_ldgsts<<<sms, 512, smem>>>((const float4*)buf, rows, passes, rpp, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        char nm[64]; snprintf(nm, 64, "cp.async row gather %d rows/pass", rpp); report(nm, (double)sms * warps * passes * rpp * 512, ms);
+        for (int it = 0; it < 3; ++it) { cudaEventRecord(e0); k_ldg_sts<<<sms, 512, smem>>>((const float4*)buf, rows, passes, rpp, out); cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        snprintf(nm, 64, "LDG+STS row gather %d rows/pass", rpp); report(nm, (double)sms * warps * passes * rpp * 512, ms);
     }
     printf("done\n");
     return 0;
