@@ -34,114 +34,117 @@ constexpr float kXScale = 256.0f;            // fp16 plane holds 256 * xn: keeps
 constexpr int kXStatSlots = 32;           // the per-call maxima are spread over 32 slots (fewer same-address atomics), reduced by the filter
 constexpr int kXStatVals = 4;             // per slot: max |xn|^2, max |xn - hq/256|^2, max |xn - mu|^2, max |(xn - mu) - hk/256|^2
 constexpr int kXStatBytes = kXStatSlots * kXStatVals * 4;
+constexpr int kXCtrBytes = 64;             // overflow-list counters: [early | bulk launch][count, steal cursor]
 
-// pass 1: F.normalize in the pinned order -> xn (fp32), QUERY plane hq = fp16(256 xn), per-radargram column sums (for the mean
-// feature mu), maxima of |xn|^2 and of the rounding residual.  One warp per row; a CTA's 8 rows belong to one radargram.
-__global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict__ x, int rows_rg, int do_normalize, float* __restrict__ xn,
-                                                        __half* __restrict__ hq, float* __restrict__ musum, unsigned* __restrict__ stats) {
-    __shared__ float s_n2[8], s_e2[8];
+// F.normalize of one row held as v[m] = channel lane + 32 m, in the pinned order (identical to l2_normalize_kernel /
+// crw_oracle_l2_normalize)
+__device__ __forceinline__ void x_normalize_row(float (&v)[4]) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) ss = __fmaf_rn(v[m], v[m], ss);
+    ss = warp_sum_butterfly_rn(ss);
+    const float d = fmaxf(__fsqrt_rn(ss), kNormEps);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = __fdiv_rn(v[m], d);
+}
+
+// pass 0: the centre mu of a radargram's features, estimated from a strided SAMPLE of its rows (at most kXMuRows): ANY vector works as
+// the centre -- q . (k - mu) ranks the keys of a query exactly like q . k, and the filter margin is computed from the residuals and
+// norms actually measured against this mu in pass 1 -- the closer mu is to the mean, the shorter the survivor lists.  Sampling
+// makes it a sub-megabyte read, so that the planes are written by ONE pass over the features.
+constexpr int kXMuRows = 1024;      // one row per warp when the call holds few radargrams: the kernel is one HBM latency long
+__global__ void __launch_bounds__(256) lp_mu_x_kernel(const float* __restrict__ x, int rows_rg, int do_normalize, float* __restrict__ musum) {
     __shared__ float s_col[8][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rg = blockIdx.y;
-    float max_n2 = 0.0f, max_e2 = 0.0f;
-    float col[4] = {0.f, 0.f, 0.f, 0.f};          // this lane's column sums over the rows of this warp (few atomics per CTA)
-    for (int r = blockIdx.x * 8 + warp; r < rows_rg; r += gridDim.x * 8) {
-        const int64_t row = (int64_t)rg * rows_rg + r;
-        const float* xr = x + row * 128;
+    const int nsample = min(rows_rg, kXMuRows);
+    const int stride = rows_rg / nsample;                       // >= 1; sample i is row i * stride
+    float col[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = blockIdx.x * 8 + warp; i < nsample; i += gridDim.x * 8) {
+        const float* xr = x + ((int64_t)rg * rows_rg + (int64_t)i * stride) * 128;
         float v[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) v[m] = xr[lane + 32 * m];
-        if (do_normalize) {          // pinned order: identical to l2_normalize_kernel / crw_oracle_l2_normalize
-            float ss = 0.0f;
+        if (do_normalize) x_normalize_row(v);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) ss = __fmaf_rn(v[m], v[m], ss);
-            ss = warp_sum_butterfly_rn(ss);
-            const float d = fmaxf(__fsqrt_rn(ss), kNormEps);
-#pragma unroll
-            for (int m = 0; m < 4; ++m) v[m] = __fdiv_rn(v[m], d);
-        }
-        float n2 = 0.0f, e2 = 0.0f;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const __half hv = __float2half_rn(v[m] * kXScale);
-            const float res = v[m] - __half2float(hv) * (1.0f / kXScale);
-            n2 = fmaf(v[m], v[m], n2);
-            e2 = fmaf(res, res, e2);
-            col[m] += v[m];
-            hq[row * 128 + lane + 32 * m] = hv;
-            if (xn) xn[row * 128 + lane + 32 * m] = v[m];
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            n2 += __shfl_xor_sync(0xffffffffu, n2, off);
-            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
-        }
-        max_n2 = fmaxf(max_n2, n2);
-        max_e2 = fmaxf(max_e2, e2);
+        for (int m = 0; m < 4; ++m) col[m] += v[m];
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) s_col[warp][lane + 32 * m] = col[m];
-    if (lane == 0) { s_n2[warp] = max_n2; s_e2[warp] = max_e2; }
     __syncthreads();
     if (threadIdx.x < 128) {
         float c = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) c += s_col[w][threadIdx.x];
-        atomicAdd(&musum[rg * 128 + threadIdx.x], c);
-    }
-    if (threadIdx.x == 0) {          // non-negative floats order like their bit patterns
-        float a = 0.0f, b2 = 0.0f;
-        for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_n2[w]); b2 = fmaxf(b2, s_e2[w]); }
-        unsigned* st = stats + kXStatVals * (blockIdx.x % kXStatSlots);
-        atomicMax(&st[0], __float_as_uint(a));
-        atomicMax(&st[1], __float_as_uint(b2));
+        atomicAdd(&musum[rg * 128 + threadIdx.x], c * (1.0f / (float)nsample));
     }
 }
 
-// pass 2: KEY plane hk = fp16(256 (xn - mu)), mu = the radargram's mean feature.  q . (k - mu) = q . k - q . mu ranks the keys of
-// a query exactly like q . k (the shift is the same for all of them), but its rounding error scales with |k - mu| instead of
-// |k|: on near-collinear embeddings (any encoder at initialisation) the filter margin shrinks with the spread of the
-// features, so the survivor lists stay short.  xn was written a moment ago: this pass reads it from L2.
-__global__ void __launch_bounds__(256) lp_center_x_kernel(const float* __restrict__ xn, int rows_rg, const float* __restrict__ musum,
-                                                          __half* __restrict__ hk, unsigned* __restrict__ stats) {
-    __shared__ float s_d2[8], s_e2[8];
+// pass 1 (the only pass over all the features): F.normalize in the pinned order -> xn (fp32), QUERY plane hq = fp16(256 xn), KEY
+// plane hk = fp16(256 (xn - mu)), and the per-call maxima that size the filter margin: |xn|^2, |xn - hq/256|^2, |xn - mu|^2,
+// |(xn - mu) - hk/256|^2.  The rounding error of q . (k - mu) scales with |k - mu| instead of |k|: on near-collinear embeddings
+// (any encoder at initialisation) the margin shrinks with the spread of the features and the survivor lists stay short.
+// One warp per row, two rows per trip (eight independent loads in flight per lane); a CTA's rows belong to one radargram.
+__global__ void __launch_bounds__(256) lp_prep_x_kernel(const float* __restrict__ x, int rows_rg, int do_normalize, float* __restrict__ xn,
+                                                        __half* __restrict__ hq, __half* __restrict__ hk, const float* __restrict__ mu_all,
+                                                        unsigned* __restrict__ stats) {
+    __shared__ float s_st[8][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rg = blockIdx.y;
-    const int r = blockIdx.x * 8 + warp;
-    const int64_t row = (int64_t)rg * rows_rg + r;
-    const float inv = 1.0f / (float)rows_rg;
-    float d2 = 0.0f, e2 = 0.0f;
-    if (r < rows_rg) {
-        // (no pinned order here: one float4 of channels per lane, one 8-byte store of four halves)
-        const float4 xv = reinterpret_cast<const float4*>(xn + row * 128)[lane];
-        const float4 mv = reinterpret_cast<const float4*>(musum + rg * 128)[lane];
-        const float d[4] = {xv.x - mv.x * inv, xv.y - mv.y * inv, xv.z - mv.z * inv, xv.w - mv.w * inv};
-        __half hv[4];
+    float mu[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            hv[m] = __float2half_rn(d[m] * kXScale);
-            const float res = d[m] - __half2float(hv[m]) * (1.0f / kXScale);
-            d2 = fmaf(d[m], d[m], d2);
-            e2 = fmaf(res, res, e2);
-        }
-        uint2 packed;
-        packed.x = (uint32_t)__half_as_ushort(hv[0]) | ((uint32_t)__half_as_ushort(hv[1]) << 16);
-        packed.y = (uint32_t)__half_as_ushort(hv[2]) | ((uint32_t)__half_as_ushort(hv[3]) << 16);
-        reinterpret_cast<uint2*>(hk + row * 128)[lane] = packed;
+    for (int m = 0; m < 4; ++m) mu[m] = mu_all[rg * 128 + lane + 32 * m];
+    float mx[4] = {0.f, 0.f, 0.f, 0.f};
+    const int step = gridDim.x * 16;
+    for (int r0 = blockIdx.x * 16 + warp * 2; r0 < rows_rg; r0 += step) {
+        const int nr = min(2, rows_rg - r0);
+        float v[2][4];
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            d2 += __shfl_xor_sync(0xffffffffu, d2, off);
-            e2 += __shfl_xor_sync(0xffffffffu, e2, off);
+        for (int u = 0; u < 2; ++u) {
+            const float* xr = x + ((int64_t)rg * rows_rg + r0 + (u < nr ? u : 0)) * 128;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) v[u][m] = xr[lane + 32 * m];
         }
+        float acc[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (do_normalize) x_normalize_row(v[u]);
+            const int64_t row = (int64_t)rg * rows_rg + r0 + u;
+            float n2 = 0.0f, e2 = 0.0f, d2 = 0.0f, f2 = 0.0f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float val = v[u][m], dv = val - mu[m];
+                const __half hv = __float2half_rn(val * kXScale), kv = __float2half_rn(dv * kXScale);
+                const float res = val - __half2float(hv) * (1.0f / kXScale), rk = dv - __half2float(kv) * (1.0f / kXScale);
+                n2 = fmaf(val, val, n2);
+                e2 = fmaf(res, res, e2);
+                d2 = fmaf(dv, dv, d2);
+                f2 = fmaf(rk, rk, f2);
+                if (u < nr) {
+                    hq[row * 128 + lane + 32 * m] = hv;
+                    hk[row * 128 + lane + 32 * m] = kv;
+                    if (xn) xn[row * 128 + lane + 32 * m] = val;
+                }
+            }
+            acc[u][0] = n2; acc[u][1] = e2; acc[u][2] = d2; acc[u][3] = f2;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[u][j] += __shfl_xor_sync(0xffffffffu, acc[u][j], off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx[j] = fmaxf(mx[j], fmaxf(acc[0][j], nr > 1 ? acc[1][j] : 0.0f));
     }
-    if (lane == 0) { s_d2[warp] = d2; s_e2[warp] = e2; }
+    if (lane == 0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_st[warp][j] = mx[j];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.0f, b2 = 0.0f;
-        for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_d2[w]); b2 = fmaxf(b2, s_e2[w]); }
-        unsigned* st = stats + kXStatVals * (blockIdx.x % kXStatSlots);
-        atomicMax(&st[2], __float_as_uint(a));
-        atomicMax(&st[3], __float_as_uint(b2));
+    if (threadIdx.x < 4) {          // non-negative floats order like their bit patterns
+        float a = 0.0f;
+        for (int w = 0; w < 8; ++w) a = fmaxf(a, s_st[w][threadIdx.x]);
+        atomicMax(&stats[kXStatVals * (blockIdx.x % kXStatSlots) + threadIdx.x], __float_as_uint(a));
     }
 }
 
@@ -171,6 +174,8 @@ struct XParams {
     long long total_rows;
     int32_t* surv;                           // [total_rows][KL] radargram-relative key rows of the survivors (sorted prefix of the list)
     int32_t* cnt;                            // [total_rows]     number of survivors, bit 30 = list overflowed (rescan in full)
+    int32_t* ovf_list;                       // global rows of the overflowed queries of this launch, in arrival order
+    int* ovf_ctr;                            // [0] number of entries of ovf_list, [1] the refine kernel's steal cursor
     const unsigned* stats;
     float inv_temp;
 };
@@ -591,6 +596,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
                     for (int s = 0; s < KL; s += 4) dst[s >> 2] = make_int4(krs[s], krs[s + 1], krs[s + 2], krs[s + 3]);
                 }
                 p.cnt[grow] = qvalid ? (c | (ovf ? (1 << 30) : 0)) : 0;
+                if (qvalid && ovf) p.ovf_list[atomicAdd(p.ovf_ctr, 1)] = (int32_t)grow;
             }
         }
     }
@@ -604,7 +610,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 // ------------------------------------------------------------------------------------------
 constexpr int kRWarps = 8;                   // warps per CTA, one query at a time each
 constexpr int kRThreads = kRWarps * 32;
-constexpr int kRMaxOvf = 64;                 // overflowed queries a CTA rescans with all its warps (more: inline, one warp each)
+constexpr int kRRescCtas = 16;                // CTAs of the refine grid that only serve the overflow list
 
 struct RParams {
     const float* xn;         // [total_rows, 128] normalised features
@@ -617,6 +623,10 @@ struct RParams {
     long long total_rows;
     float inv_temp;
     unsigned magic_n;
+    int chunk_q;             // queries per warp chunk of the refine kernel (<= 32)
+    int resc_ctas;           // the first resc_ctas CTAs of the grid take no chunks: they start on the overflow list at once
+    const int32_t* ovf_list; // global rows of the overflowed queries of this launch (written by the filter)
+    int* ovf_ctr;            // [0] their number, [1] steal cursor
     int debug;               // timing aids (CRW_TC_DEBUG): 16 = no W / I stores, 32 = no row loads, 64 = no dot products (results invalid)
 };
 
@@ -650,8 +660,9 @@ __device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, i
     const int F = n_key_frames(n, p.ctx);
     const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     float v = -INFINITY;
-    int id = 0;
+    int id = 0x7fffffff;
     const int jlo = max(0, q - rb), jhi = min(N - 1, q + rb), bw = jhi - jlo + 1;
+    const unsigned magic_bw = (unsigned)((1ull << 32) / (unsigned)bw) + 1u;      // cc / bw for cc * bw < 2^32
     const float4 qv = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)n * N + q) * 128) + lane);
     const int total = F * bw;                          // in-band candidates, ascending id = (frame slot, node)
     for (int c0 = round_begin * 16; c0 < total; c0 += round_stride * 16) {
@@ -660,17 +671,24 @@ __device__ __forceinline__ void x_full_scan(const RParams& p, const float* xr, i
         float4 kv[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
-            const int cc = min(c0 + r, total - 1), f = cc / bw, jj = cc - f * bw;
+            const int cc = min(c0 + r, total - 1), f = (int)__umulhi((unsigned)cc, magic_bw), jj = cc - f * bw;
             kv[r] = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)key_frame(n, p.ctx, f) * N + jlo + jj) * 128) + lane);
         }
         float part[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) part[r] = x_partial4(kv[r], qv);
         const float mine = __fmul_rn(x_warp_dot16(part, lane), p.inv_temp);           // candidate c0 + (lane >> 1)
-        for (int r = 0; r < nrow; ++r) {                                               // ascending id
-            const float cand = __shfl_sync(0xffffffffu, mine, 2 * r);
-            const int cc = c0 + r, f = cc / bw;
-            x_list_insert_warp(v, id, cand, f * N + jlo + (cc - f * bw), k, kmask, lane);
+        const int cc_l = c0 + (lane >> 1), f_l = (int)__umulhi((unsigned)min(cc_l, total - 1), magic_bw);
+        const int id_l = f_l * N + jlo + (cc_l - f_l * bw);
+        // only the candidates that beat the k-th best so far are inserted (ascending lane = ascending id); after the first
+        // rounds that is a handful per round
+        const float vk = __shfl_sync(0xffffffffu, v, k - 1);
+        const int idk = __shfl_sync(0xffffffffu, id, k - 1);
+        unsigned m = __ballot_sync(0xffffffffu, !(lane & 1) && (lane >> 1) < nrow && (mine > vk || (mine == vk && id_l < idk)));
+        while (m) {                                                                    // warp-uniform
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            x_list_insert_warp(v, id, __shfl_sync(0xffffffffu, mine, src), __shfl_sync(0xffffffffu, id_l, src), k, kmask, lane);
         }
     }
     v_out = v;
@@ -707,115 +725,192 @@ __device__ __forceinline__ void x_finish_query(const RParams& p, float v, int id
     }
 }
 
-// KL = survivor slots per query (16 or 32).  One warp per query: the fp32 rows of the survivors come straight from L2 into
-// registers (one coalesced 512-byte row per load instruction, all of a query's loads in flight together), every dot product is
-// one warp dot in the oracle's order -- no shared-memory staging, so the kernel is bound by the row gather itself.
-template <int KL>
-__global__ void __launch_bounds__(kRThreads, 2) lp_refine_kernel(RParams p) {
+// ---- thread-per-query finish: sort the survivors of one query (logit desc, id asc) and write its softmax weights ----
+// 64-bit sort key: orderable logit bits in the upper word (larger = better), ~id in the lower word (smaller id = better); ids of
+// a query are distinct, so keys are distinct and the order is the oracle's total order.  (Dot products come out of fmaf chains
+// that start from +0 and butterfly sums: they are never -0, and neither is dot * (1 / temp).)
+__device__ __forceinline__ unsigned long long x_sort_key(float lg, int id) {
+    const uint32_t u = __float_as_uint(lg + 0.0f);
+    const uint32_t o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (uint32_t)id);
+}
+__device__ __forceinline__ float x_key_logit(unsigned long long key) {
+    const uint32_t o = (uint32_t)(key >> 32);
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ int x_key_id(unsigned long long key) { return (int)(0xffffffffu - (uint32_t)key); }
+// bitonic network over NS (power of two) register-resident keys, descending; every index is a compile-time constant
+template <int NS>
+__device__ __forceinline__ void x_sort_desc(unsigned long long (&key)[NS]) {
+#pragma unroll
+    for (int kk = 2; kk <= NS; kk <<= 1)
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & kk) == 0;
+                    const unsigned long long a = key[i], b2 = key[l];
+                    const bool sw = desc ? (a < b2) : (a > b2);
+                    key[i] = sw ? b2 : a;
+                    key[l] = sw ? a : b2;
+                }
+            }
+}
+
+// KL = survivor slots per query (16, 24 or 32).  Every WARP works on its own: it takes chunks of up to 32 consecutive queries and
+// runs two phases on each, with no CTA-wide barrier between them (warps of an SM are in different phases at any time, so the
+// latency-bound phase 2 of one runs under the loads of the others):
+//   phase 1, the warp on one query at a time: the fp32 rows of the survivors come straight from L2 into registers (one coalesced
+//            512-byte row per load instruction, all of a query's loads in flight together), every dot product is one warp dot in
+//            the oracle's order (sixteen per reduce-scatter); the dots go to the warp's slab of shared memory.
+//   phase 2, one LANE per query: exact order of the survivors (sorting network on registers), masked fill, pinned softmax
+//            (sequential sum in rank order), W / I stores (consecutive lanes = consecutive nodes) -- no shuffles.
+// Queries whose survivor list overflowed are queued and rescanned in full by the whole CTA at the end (rare).
+template <int KL, int RB, int MINB>
+__global__ void __launch_bounds__(kRThreads, MINB) lp_refine_kernel(RParams p) {
+    constexpr int NS = (KL <= 16) ? 16 : 32;
+    __shared__ float s_lg[kRWarps][KL][33];
     __shared__ float es_all[kRWarps][32];
     __shared__ float sc_v[kRWarps][32];
     __shared__ int sc_i[kRWarps][32];
-    __shared__ int s_ovf[kRMaxOvf];
-    __shared__ int s_novf;
+    __shared__ int s_steal;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, k = p.k;
     const unsigned kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-    if (tid == 0) s_novf = 0;
-    __syncthreads();
-    // this CTA's share of the launch: queries [r_lo, r_hi) of the flattened (radargram, row in [row_begin, row_end)) space
-    // (32-bit arithmetic: the host checks R * rows < 2^31; the radargram / row split is kept incrementally, no divisions)
     const int rows_launch = p.row_end - p.row_begin;
-    const int total_q = p.R * rows_launch;
-    const int per = (total_q + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int r_lo = (int)blockIdx.x * per, r_hi = min(total_q, r_lo + per);
+    const int total_q = p.R * rows_launch;          // (32-bit arithmetic: the host checks R * rows < 2^31)
+    const int qw = p.chunk_q;                       // queries per warp chunk (<= 32)
+    const int nchunks = (total_q + qw - 1) / qw;
     const bool prof = (p.debug & 8) != 0;
-
-    // the survivor list of the NEXT query of this warp is fetched while the current one is worked on (two dependent global loads
-    // off the critical path)
-    auto fetch_meta = [&](int f, int rg, int row, int& cword, int& kr) {
-        cword = 0;
-        kr = 0;
-        if (f >= r_hi) return;
-        const size_t grow = (size_t)rg * p.rows_rg + row;
-        cword = __ldg(p.cnt + grow);
-        kr = (lane < KL) ? __ldg(p.surv + grow * KL + lane) : 0;                      // (slots beyond the count hold stale rows: unused)
-    };
-    int cword_n, kr_n;
-    int rg_n = (r_lo + warp) / rows_launch, row_n = p.row_begin + (r_lo + warp) - rg_n * rows_launch;       // (once per warp)
-    fetch_meta(r_lo + warp, rg_n, row_n, cword_n, kr_n);
-    for (int f = r_lo + warp; f < r_hi; f += kRWarps) {
+    const int reg_ctas = (int)gridDim.x - p.resc_ctas;
+    for (int ch = ((int)blockIdx.x - p.resc_ctas) * kRWarps + warp; ch < nchunks && (int)blockIdx.x >= p.resc_ctas; ch += reg_ctas * kRWarps) {
         const long long c_0 = prof ? clock64() : 0;
-        const int cword = cword_n, kr = kr_n, rg = rg_n, row = row_n;
-        row_n += kRWarps;
-        while (row_n >= p.row_end) { row_n -= rows_launch; ++rg_n; }
-        fetch_meta(f + kRWarps, rg_n, row_n, cword_n, kr_n);
-        const int n = (int)__umulhi((unsigned)row, p.magic_n), q = row - n * N;
-        if (n < 1 || n >= p.T) continue;                                  // warp-uniform
-        const bool rescan = (cword >> 30) & 1;
-        if (rescan) {                                                        // queued: rescanned by the whole CTA at the end
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(&s_novf, 1);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            if (slot < kRMaxOvf) {
-                if (lane == 0) s_ovf[slot] = f;
-            } else {
-                float fv;
-                int fid;
-                x_full_scan(p, p.xn + (size_t)rg * p.rows_rg * 128, n, q, k, 0, 1, fv, fid);
-                const int live = __popc(__ballot_sync(0xffffffffu, fv > -INFINITY) & kmask);
-                x_finish_query(p, fv, fid, live, rg, n, q, k, lane, es_all[warp]);
+        const int r_lo = ch * qw, nq = min(total_q, r_lo + qw) - r_lo;
+        // lane j owns query r_lo + j in phase 2; its geometry and survivor count are fetched once (coalesced)
+        const int fj = r_lo + min(lane, nq - 1);
+        const int rg_j = fj / rows_launch, row_j = p.row_begin + fj - rg_j * rows_launch;
+        const int n_j = (int)__umulhi((unsigned)row_j, p.magic_n), q_j = row_j - n_j * N;
+        const size_t grow_j = (size_t)rg_j * p.rows_rg + row_j;
+        // count word: bit 31 = no query here (frame 0 / beyond the sequence / beyond the chunk), bit 30 = overflowed list
+        unsigned cword_j = 0x80000000u;
+        if (lane < nq && n_j >= 1 && n_j < p.T) cword_j = (unsigned)__ldg(p.cnt + grow_j);
+        // ---------------- phase 1 ----------------
+        // the survivor list of the NEXT query is fetched while the current one is worked on
+        const size_t grow0 = (size_t)__shfl_sync(0xffffffffu, rg_j, 0) * p.rows_rg + __shfl_sync(0xffffffffu, row_j, 0);
+        int kr_n = (lane < KL) ? __ldg(p.surv + grow0 * KL + lane) : 0;
+        for (int i = 0; i < nq; ++i) {
+            const unsigned cword = __shfl_sync(0xffffffffu, cword_j, i);
+            const int rg = __shfl_sync(0xffffffffu, rg_j, i), row = __shfl_sync(0xffffffffu, row_j, i);
+            const int kr = kr_n;
+            {
+                const int i1 = min(i + 1, nq - 1);
+                const size_t grow1 = (size_t)__shfl_sync(0xffffffffu, rg_j, i1) * p.rows_rg + __shfl_sync(0xffffffffu, row_j, i1);
+                kr_n = (lane < KL) ? __ldg(p.surv + grow1 * KL + lane) : 0;           // (slots beyond the count hold stale rows: unused)
             }
-            continue;
-        }
-        const int c = cword & 0xffff;
-        const float* xr = p.xn + (size_t)rg * p.rows_rg * 128;
-        const float4 qv = __ldg(reinterpret_cast<const float4*>(xr + (size_t)row * 128) + lane);
-        float lg = -INFINITY;
+            if (cword & 0x80000000u) continue;                                  // warp-uniform
+            if (cword & 0x40000000u) continue;                                  // overflowed list: on the launch's overflow list
+            const int c = (int)(cword & 0xffffu);
+            const float* xr = p.xn + (size_t)rg * p.rows_rg * 128;
+            const float4 qv = __ldg(reinterpret_cast<const float4*>(xr + (size_t)row * 128) + lane);
 #pragma unroll
-        for (int sb = 0; sb < KL; sb += 16) {                            // (c <= KL: the slots beyond it are never touched)
-            if (sb >= c) break;                                              // warp-uniform
-            // all sixteen row loads are unconditional and issued back to back (slots past the count repeat the last survivor's
-            // row: same address, merged in L1, and their dots are ignored), so that they are in flight together
-            float4 kv[16];
+            for (int sb = 0; sb < KL; sb += 16) {                            // (c <= KL: the slots beyond it are never touched)
+                if (sb >= c) break;                                              // warp-uniform
+                // the row loads of a batch (RB = 16: all of them, RB = 8: two batches) are unconditional and issued back to back
+                // (slots past the count repeat the last survivor's row: same address, merged in L1, and their dots are
+                // ignored), so that they are in flight together
+                float part[16];
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                const int kr_s = __shfl_sync(0xffffffffu, kr, min(sb + s, c - 1));
-                kv[s] = __ldg(reinterpret_cast<const float4*>(xr + (size_t)kr_s * 128) + lane);
+                for (int b0 = 0; b0 < 16; b0 += RB) {
+                    float4 kv[RB];
+#pragma unroll
+                    for (int s2 = 0; s2 < RB; ++s2) {
+                        int kr_s = __shfl_sync(0xffffffffu, kr, min(sb + b0 + s2, c - 1));
+                        if (p.debug & 32) kr_s = row;
+                        kv[s2] = __ldg(reinterpret_cast<const float4*>(xr + (size_t)kr_s * 128) + lane);
+                    }
+#pragma unroll
+                    for (int s2 = 0; s2 < RB; ++s2) part[b0 + s2] = x_partial4(kv[s2], qv);
+                }
+                const float mine = x_warp_dot16(part, lane);                     // dot of slot sb + (lane >> 1)
+                if (!(lane & 1) && sb + (lane >> 1) < KL) s_lg[warp][sb + (lane >> 1)][i] = mine;
             }
-            float part[16];
-#pragma unroll
-            for (int s = 0; s < 16; ++s) part[s] = x_partial4(kv[s], qv);
-            const float mine = x_warp_dot16(part, lane);                     // dot of slot sb + (lane >> 1)
-            const float d = __shfl_sync(0xffffffffu, mine, (2 * (lane - sb)) & 31);
-            if (lane >= sb && lane < sb + 16 && lane < c) lg = __fmul_rn(d, p.inv_temp);
         }
+        __syncwarp();
         const long long c_1 = prof ? clock64() : 0;
-        const bool valid = lane < c;
-        const int id = valid ? x_cand_id(kr, n, N, p.ctx, p.magic_n) : 0x7fffffff;
-        // rank among the survivors: (logit desc, id asc)
-        int rank = 0;
-#pragma unroll 4
-        for (int o = 0; o < c; ++o) {
-            const float lo_ = __shfl_sync(0xffffffffu, lg, o);
-            const int io = __shfl_sync(0xffffffffu, id, o);
-            rank += (lo_ > lg || (lo_ == lg && io < id)) ? 1 : 0;
+        // ---------------- phase 2 ----------------
+        if (!(cword_j & 0xc0000000u)) {
+            const int c = (int)(cword_j & 0xffffu), n = n_j, q = q_j, rg = rg_j;
+            unsigned long long key[NS];
+            const int4* sv = reinterpret_cast<const int4*>(p.surv + grow_j * KL);
+#pragma unroll
+            for (int s4 = 0; s4 < NS; s4 += 4) {
+                int krs[4] = {0, 0, 0, 0};
+                if (s4 < KL && s4 < c) { const int4 t4 = __ldg(sv + (s4 >> 2)); krs[0] = t4.x; krs[1] = t4.y; krs[2] = t4.z; krs[3] = t4.w; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s2 = s4 + u;
+                    unsigned long long kk = 0ull;
+                    if (s2 < KL && s2 < c)
+                        kk = x_sort_key(__fmul_rn(s_lg[warp][s2 < KL ? s2 : 0][lane], p.inv_temp), x_cand_id(krs[u], n, N, p.ctx, p.magic_n));
+                    key[s2] = kk;
+                }
+            }
+            x_sort_desc<NS>(key);
+            const int live = min(c, k);
+            // fewer than k in-band candidates: out-of-band ones share one logit and come in ascending id order
+            const int lo_q = max(0, q - p.rb), w_q = min(N - 1, q + p.rb) - lo_q + 1, nob = max(N - w_q, 1);
+            const float vfill = __fmul_rn(kMaskBias, p.inv_temp);
+            const float v0 = (live > 0) ? x_key_logit(key[0]) : vfill;
+            float e[KL];
+            float ssum = 0.0f;
+#pragma unroll
+            for (int s2 = 0; s2 < KL; ++s2) {
+                if (s2 < k) {
+                    const float v = (s2 < live) ? x_key_logit(key[s2]) : vfill;
+                    e[s2] = pinned_expf(__fsub_rn(v, v0));
+                    ssum = (s2 == 0) ? e[0] : __fadd_rn(ssum, e[s2]);
+                } else {
+                    e[s2] = 0.0f;
+                }
+            }
+            if (!(p.debug & 16)) {
+                const size_t o0 = ((size_t)(rg * p.T + n) * k) * N + q;
+#pragma unroll
+                for (int s2 = 0; s2 < KL; ++s2) {
+                    if (s2 < k) {
+                        int id;
+                        if (s2 < live) {
+                            id = x_key_id(key[s2]);
+                        } else {
+                            const int t = s2 - live, fo = t / nob, r = t - fo * nob;
+                            id = fo * N + ((r < lo_q) ? r : r + w_q);
+                        }
+                        p.W[o0 + (size_t)s2 * N] = __fdiv_rn(e[s2], ssum);
+                        p.I[o0 + (size_t)s2 * N] = id;
+                    }
+                }
+            }
         }
-        // every survivor moves to the lane of its rank
-        if (valid) { sc_v[warp][rank] = lg; sc_i[warp][rank] = id; }
         __syncwarp();
-        float v = -INFINITY;
-        int idv = 0;
-        if (valid) { v = sc_v[warp][lane]; idv = sc_i[warp][lane]; }
-        __syncwarp();
-        x_finish_query(p, v, idv, min(c, k), rg, n, q, k, lane, es_all[warp]);
         if (prof) { const long long c_2 = clock64(); XPROF(1, 1, c_1 - c_0); XPROF(1, 3, c_2 - c_1); }
     }
     __syncthreads();
-    // ---- queued rescans: every warp scans its share of the candidate rounds, warp 0 merges the partial lists ----
-    const int novf = min(s_novf, kRMaxOvf);
-    for (int e = 0; e < novf; ++e) {
-        const int f = s_ovf[e];
-        const int rg = f / rows_launch, row = p.row_begin + f - rg * rows_launch;
+    // ---------------- overflowed queries: rescanned in full, one at a time by the whole CTA (every warp scans its share of the
+    // candidate rounds, warp 0 merges the partial lists).  The list was completed by the filter launch; entries are handed out
+    // through a cursor: the first resc_ctas CTAs start here at once (a few overflows are absorbed while the others refine),
+    // everyone else joins when its chunks are done (degenerate inputs overflow everywhere). ----------------
+    const int novf = *reinterpret_cast<const volatile int*>(p.ovf_ctr);
+    if (novf == 0) return;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_steal = atomicAdd(p.ovf_ctr + 1, 1);
+        __syncthreads();
+        const int e2 = s_steal;
+        if (e2 >= novf) break;
+        const int grow = p.ovf_list[e2];
+        const int rg = grow / p.rows_rg, row = grow - rg * p.rows_rg;
         const int n = row / N, q = row - n * N;
         float pv;
         int pi;
@@ -825,17 +920,20 @@ __global__ void __launch_bounds__(kRThreads, 2) lp_refine_kernel(RParams p) {
         __syncthreads();
         if (warp == 0) {
             float v = -INFINITY;
-            int id = 0;
+            int id = 0x7fffffff;
             for (int w2 = 0; w2 < kRWarps; ++w2)
                 for (int s2 = 0; s2 < k; ++s2) {
                     const float c = sc_v[w2][s2];
+                    const int ci = sc_i[w2][s2];
                     if (!(c > -INFINITY)) break;                              // (warp-uniform) lists are sorted: the rest is empty
-                    x_list_insert_warp(v, id, c, sc_i[w2][s2], k, kmask, lane);
+                    const float vk = __shfl_sync(0xffffffffu, v, k - 1);
+                    const int idk = __shfl_sync(0xffffffffu, id, k - 1);
+                    if (!(c > vk || (c == vk && ci < idk))) break;           // ... or cannot enter the merged list any more
+                    x_list_insert_warp(v, id, c, ci, k, kmask, lane);
                 }
             const int live = __popc(__ballot_sync(0xffffffffu, v > -INFINITY) & kmask);
             x_finish_query(p, v, id, live, rg, n, q, k, lane, es_all[0]);
         }
-        __syncthreads();
     }
 }
 
@@ -861,8 +959,9 @@ size_t lp_x_scratch_bytes(int R, int T, int N, int C, int k, int do_normalize) {
     int kt, kl;
     x_kt_kl(k, kt, kl);
     const size_t rows = (size_t)R * T * N;
-    size_t b = align_up((size_t)kXStatBytes + (size_t)R * 128 * sizeof(float), 256);
+    size_t b = align_up((size_t)kXStatBytes + kXCtrBytes + (size_t)R * 128 * sizeof(float), 256);
     b += 2 * align_up(rows * C * sizeof(__half), 256);
+    b += align_up(rows * sizeof(int32_t), 256);          // overflow lists
     if (do_normalize) b += align_up(rows * C * sizeof(float), 256);
     b += align_up(rows * kl * sizeof(int32_t), 256);
     b += align_up(rows * sizeof(int32_t), 256);
@@ -892,14 +991,29 @@ static int launch_filter(const LpXPlan& plan, const XParams& p, int max_ctas, cu
 }
 
 template <int KL>
-static int launch_refine(const RParams& r, int max_ctas, cudaStream_t st) {
-    const long long total_q = (long long)r.R * (r.row_end - r.row_begin);
+static int launch_refine(const RParams& r_in, int max_ctas, cudaStream_t st) {
+    const RParams& r0 = r_in;
+    const long long total_q = (long long)r0.R * (r0.row_end - r0.row_begin);
     if (total_q <= 0) return CRW_OK;
     if (total_q >= (1ll << 31) - 65536) return CRW_ERR_UNSUPPORTED;
-    // two CTAs of 8 warps per SM; a CTA's share is a contiguous range of queries (neighbouring queries share their key window)
-    long long ctas = (total_q + 4 * kRWarps - 1) / (4 * kRWarps);
-    if (ctas > 2LL * max_ctas) ctas = 2LL * max_ctas;
-    lp_refine_kernel<KL><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
+    // two (three) CTAs of 8 warps per SM; a warp chunk is a contiguous range of at most 32 queries, sized so that one round of
+    // chunks fills every warp slot when the launch is small
+    static const int rb8s = [] { const char* e = getenv("CRW_LP_REFINE_RB8"); return e ? atoi(e) : 0; }();
+    const long long slots = (rb8s ? 3LL : 2LL) * max_ctas;
+    const long long resc = (slots >= 8 * kRRescCtas) ? kRRescCtas : 1;      // CTAs that only serve the overflow list
+    const long long wslots = (slots - resc) * kRWarps;
+    long long per = (total_q + wslots - 1) / wslots;
+    if (per > 32) per = 32;
+    if (per < 8) per = 8;
+    const long long nchunks = (total_q + per - 1) / per;
+    long long ctas = (nchunks + kRWarps - 1) / kRWarps;
+    if (ctas > slots - resc) ctas = slots - resc;
+    ctas += resc;
+    RParams r = r_in;
+    r.chunk_q = (int)per;
+    r.resc_ctas = (int)resc;
+    if (rb8s) lp_refine_kernel<KL, 8, 3><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
+    else lp_refine_kernel<KL, 16, 2><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -916,8 +1030,9 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     if ((uint64_t)T * N * N >= (1ull << 32)) return CRW_ERR_UNSUPPORTED;
     char* sp = reinterpret_cast<char*>(scratch);
     unsigned* stats = reinterpret_cast<unsigned*>(sp);
-    float* musum = reinterpret_cast<float*>(sp + kXStatBytes);
-    const size_t head = align_up((size_t)kXStatBytes + (size_t)R * 128 * sizeof(float), 256);
+    int* ovf_ctr = reinterpret_cast<int*>(sp + kXStatBytes);
+    float* musum = reinterpret_cast<float*>(sp + kXStatBytes + kXCtrBytes);
+    const size_t head = align_up((size_t)kXStatBytes + kXCtrBytes + (size_t)R * 128 * sizeof(float), 256);
     sp += head;
     __half* hq = reinterpret_cast<__half*>(sp);
     sp += align_up(rows * C * sizeof(__half), 256);
@@ -928,17 +1043,19 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     int32_t* surv = reinterpret_cast<int32_t*>(sp);
     sp += align_up(rows * plan->kl * sizeof(int32_t), 256);
     int32_t* cnt = reinterpret_cast<int32_t*>(sp);
+    sp += align_up(rows * sizeof(int32_t), 256);
+    int32_t* ovf_list = reinterpret_cast<int32_t*>(sp);
+    if (rows >= (1ull << 31)) return CRW_ERR_UNSUPPORTED;
 
     CRW_CUDA_RET(cudaMemsetAsync(stats, 0, head, st));
     if (rows > 0) {
         const int rows_rg = T * N;
-        const dim3 grid((unsigned)((rows_rg + 7) / 8), (unsigned)R);
         if (R > 65535) return CRW_ERR_UNSUPPORTED;
-        // pass 1 walks its rows with a bounded grid (each CTA ends with one atomicAdd per column): ~8 CTAs per SM over all radargrams
-        const unsigned per_rg = (unsigned)max(1, min((rows_rg + 7) / 8, (8 * max(sms, 1) + R - 1) / R));
-        lp_prep_x_kernel<<<dim3(per_rg, (unsigned)R), 256, 0, st>>>(feats, rows_rg, do_normalize, xn, hq, musum, stats);
+        // centre from a sample of the rows, then one pass over the features with a bounded grid (~8 CTAs per SM over all radargrams)
+        lp_mu_x_kernel<<<dim3(R <= 8 ? 128u : 16u, (unsigned)R), 256, 0, st>>>(feats, rows_rg, do_normalize, musum);
         CRW_LAUNCH_RET();
-        lp_center_x_kernel<<<grid, 256, 0, st>>>(do_normalize ? xn : feats, rows_rg, musum, hk, stats);
+        const unsigned per_rg = (unsigned)max(1, min((rows_rg + 15) / 16, (8 * max(sms, 1) + R - 1) / R));
+        lp_prep_x_kernel<<<dim3(per_rg, (unsigned)R), 256, 0, st>>>(feats, rows_rg, do_normalize, xn, hq, hk, musum, stats);
         CRW_LAUNCH_RET();
     }
     XParams& p = plan->p;
@@ -950,6 +1067,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     p.magic_n = (unsigned)((1ull << 32) / (unsigned)N) + 1u;
     p.total_rows = (long long)rows;
     p.surv = surv; p.cnt = cnt; p.stats = stats;
+    p.ovf_list = ovf_list; p.ovf_ctr = ovf_ctr;            // (lp_x_launch offsets both for the bulk launch)
     { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     // items: as many as fill whole rounds of the GPU, at most kXG * 128 rows each; the stream of one item must fit the 12-bit column
     const int max_rows = kXG * kXBM;
@@ -975,6 +1093,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     RParams& r = plan->r;
     r.xn = do_normalize ? xn : feats;
     r.surv = surv; r.cnt = cnt; r.W = W; r.I = I;
+    r.ovf_list = ovf_list; r.ovf_ctr = ovf_ctr; r.resc_ctas = 0;
     r.R = R; r.T = T; r.N = N; r.ctx = ctx; r.rb = p.rb; r.k = k;
     r.rows_rg = p.rows_rg; r.row_begin = 0; r.row_end = 0;
     r.total_rows = p.total_rows; r.inv_temp = p.inv_temp; r.magic_n = p.magic_n; r.debug = p.debug;
@@ -1000,12 +1119,20 @@ int lp_x_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, 
     XParams p = plan.p;
     p.v_begin = v_begin;
     p.v_end = v_end;
+    // overflow list of this launch: the early launch fills [0, R * early_rows), anything else the rest (a launch over everything
+    // starts at 0 as well: the two never run in one call)
+    const bool bulk_part = v_begin > 0;
+    const size_t list_off = bulk_part ? (size_t)plan.p.R * lp_x_early_rows(plan_storage) : 0;
+    p.ovf_list = plan.p.ovf_list + list_off;
+    p.ovf_ctr = plan.p.ovf_ctr + (bulk_part ? 2 : 0);
     int rc;
     if (plan.kt == 10) rc = launch_filter<10, 16>(plan, p, max_ctas, st);
     else if (plan.kt == 16) rc = launch_filter<16, 24>(plan, p, max_ctas, st);
     else rc = launch_filter<24, 32>(plan, p, max_ctas, st);
     if (rc != CRW_OK) return rc;
     RParams r = plan.r;
+    r.ovf_list = p.ovf_list;
+    r.ovf_ctr = p.ovf_ctr;
     const int early_slots = p.R * p.early_items_rg, early_rows = lp_x_early_rows(plan_storage);
     r.row_begin = (v_begin >= early_slots) ? early_rows : 0;
     r.row_end = (v_end <= early_slots) ? early_rows : p.rows_rg;

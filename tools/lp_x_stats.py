@@ -31,7 +31,7 @@ def stats(name, feats, k, radius):
     kl = 16 if k <= 10 else (24 if k <= 16 else 32)
     rows = R * T * N
     base = (-scratch.data_ptr()) % 256
-    off = base + align(512 + R * 512) + 2 * align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
+    off = base + align(512 + 64 + R * 512) + 2 * align(rows * C * 2) + align(rows * C * 4) + align(rows * kl * 4)
     cnt = scratch[off:off + rows * 4].view(torch.int32).view(R, T, N)[:, 1:]
     st = scratch[base:base + 512].view(torch.float32).view(32, 4).max(dim=0).values
     ovf = (cnt >> 30) & 1
