@@ -749,7 +749,9 @@ extern "C" int crw_labelprop_forward(const float* feats, const float* mask0, int
         }
         std::lock_guard<std::mutex> lock(sc->mu);
         CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));                       // prep done
-        if ((rc = lp_x_launch(plan.bytes, early, total, sms, st)) != CRW_OK) return rc;
+        // the bulk is the critical path: enqueue it first (it leaves the early items their SMs when they are few)
+        const int bulk_ctas = (early <= sms / 8) ? sms - early : sms;
+        if ((rc = lp_x_launch(plan.bytes, early, total, bulk_ctas, st)) != CRW_OK) return rc;
         CRW_CUDA_RET(cudaStreamWaitEvent(sc->s2, sc->ev_fork, 0));
         if ((rc = lp_x_launch(plan.bytes, 0, early, sms, sc->s2)) != CRW_OK) return rc;
         if ((rc = gather_launch_seq(gp, sc->s2)) != CRW_OK) return rc;

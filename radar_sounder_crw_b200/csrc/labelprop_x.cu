@@ -168,6 +168,7 @@ struct XParams {
     int R, T, N, ctx, rb, k;
     int rows_rg;                             // T * N
     int rows_per_item, items_per_rg, early_items_rg;
+    int early_rpi, early_rows;               // the first early_items_rg items of a radargram are small (early_rpi rows): rows [0, early_rows)
     int v_begin, v_end;                      // schedule slots walked by this launch
     unsigned magic_n;
     int debug;
@@ -199,8 +200,13 @@ __host__ __device__ __forceinline__ XItem x_item(const XParams& p, int v) {
     XItem t;
     int it;
     x_slot_to_item(p, v, t.rg, it);
-    t.ra = it * p.rows_per_item;
-    t.rb = min(t.ra + p.rows_per_item, p.rows_rg);
+    if (it < p.early_items_rg) {
+        t.ra = it * p.early_rpi;
+        t.rb = min(t.ra + p.early_rpi, p.early_rows);
+    } else {
+        t.ra = p.early_rows + (it - p.early_items_rg) * p.rows_per_item;
+        t.rb = min(t.ra + p.rows_per_item, p.rows_rg);
+    }
     const int n_lo = max(1, t.ra / p.N);
     t.n_hi = min(p.T - 1, (t.rb - 1) / p.N);
     t.f_lo = max(0, n_lo - p.ctx);
@@ -1069,14 +1075,27 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     p.surv = surv; p.cnt = cnt; p.stats = stats;
     p.ovf_list = ovf_list; p.ovf_ctr = ovf_ctr;            // (lp_x_launch offsets both for the bulk launch)
     { const char* e = getenv("CRW_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    // items: as many as fill whole rounds of the GPU, at most kXG * 128 rows each; the stream of one item must fit the 12-bit column
-    const int max_rows = kXG * kXBM;
-    long long items = ((long long)rows + max_rows - 1) / max_rows;
-    if (sms > 0) items = (items + sms - 1) / sms * sms;
-    int items_rg = (int)((items + R - 1) / R);
-    if (items_rg < 1) items_rg = 1;
-    int rpi = ceil_div(p.rows_rg, items_rg);
-    if (rpi < 1) rpi = 1;
+    // early items: the rows of frames 0 .. ctx+1 (the sequential gather waits for them) are cut into single query tiles, so that
+    // this side job takes a fraction of a bulk item's time
+    const int early_need = min((ctx + 2) * N, p.rows_rg);
+    p.early_rpi = kXBM;
+    p.early_items_rg = ceil_div(early_need, p.early_rpi);
+    p.early_rows = min(p.early_items_rg * p.early_rpi, p.rows_rg);
+    // bulk items: as many as fill whole rounds of the CTAs the bulk launch gets (all SMs but the ones the early items occupy
+    // when those are few), at most kXG * 128 rows each; the stream of one item must fit the 12-bit column
+    const int bulk_rows_rg = p.rows_rg - p.early_rows;
+    int rpi = kXG * kXBM;
+    if (bulk_rows_rg > 0) {
+        const int max_rows = kXG * kXBM;
+        const int early_ctas = R * p.early_items_rg;
+        const int nb = (sms > 0) ? ((early_ctas <= sms / 8) ? sms - early_ctas : sms) : 0;
+        long long items = ((long long)R * bulk_rows_rg + max_rows - 1) / max_rows;
+        if (nb > 0) items = (items + nb - 1) / nb * nb;
+        int items_rg = (int)((items + R - 1) / R);
+        if (items_rg < 1) items_rg = 1;
+        rpi = ceil_div(bulk_rows_rg, items_rg);
+        if (rpi < 1) rpi = 1;
+    }
     // stream length check: frame-0 tiles + (rows of the item + ctx + 1 frames) in 64-row tiles must stay below 2^12 / 64 tiles
     while (true) {
         const int frames = rpi / N + 2 + ctx;
@@ -1086,9 +1105,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
         rpi = rpi / 2;
     }
     p.rows_per_item = rpi;
-    p.items_per_rg = ceil_div(p.rows_rg, rpi);
-    const int early = ceil_div(min((ctx + 2) * N, p.rows_rg), rpi);
-    p.early_items_rg = early < p.items_per_rg ? early : p.items_per_rg;
+    p.items_per_rg = p.early_items_rg + ceil_div(bulk_rows_rg, rpi);
     p.v_begin = p.v_end = 0;
     RParams& r = plan->r;
     r.xn = do_normalize ? xn : feats;
@@ -1105,11 +1122,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
 }
 int lp_x_total_slots(const void* plan) { const LpXPlan* pl = reinterpret_cast<const LpXPlan*>(plan); return pl->p.R * pl->p.items_per_rg; }
 int lp_x_early_slots(const void* plan) { const LpXPlan* pl = reinterpret_cast<const LpXPlan*>(plan); return pl->p.R * pl->p.early_items_rg; }
-int lp_x_early_rows(const void* plan) {
-    const LpXPlan* pl = reinterpret_cast<const LpXPlan*>(plan);
-    const int r = pl->p.early_items_rg * pl->p.rows_per_item;
-    return r < pl->p.rows_rg ? r : pl->p.rows_rg;
-}
+int lp_x_early_rows(const void* plan) { return reinterpret_cast<const LpXPlan*>(plan)->p.early_rows; }
 
 // filter over schedule slots [v_begin, v_end), then refine over the rows those slots cover (early slots: rows [0, early_rows) of
 // every radargram; the rest: [early_rows, rows_rg)); v ranges must be exactly the early part, the rest, or everything
