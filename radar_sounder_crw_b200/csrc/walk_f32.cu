@@ -367,6 +367,11 @@ bool walk_small_supported(int N, int C);
 bool walk_small_mma_supported(int N, int C);
 int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
                        cudaStream_t st, bool mma);
+bool walk_fused_supported(int N, int C, int T);
+size_t walk_fused_saved_bytes(int B, int T);
+int walk_fused_backward(const float* x, const void* saved, const float* dloss, const float* dA_or_null, int B, int T, int N, int C, float tau,
+                        float* dx, cudaStream_t st);
+int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, void* saved, cudaStream_t st);
 int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
                         float tau, float* dx, float* sc, cudaStream_t st, bool mma);
 // walk_tc_tiles.cu: tile-parallel tcgen05 bf16x3 path
@@ -386,6 +391,7 @@ extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C, int precision
     if (B < 1 || T < 2 || N < 1 || C < 1) return 0;
     size_t b = WalkLayout(B, T, N, C).total * sizeof(float) + 256;
     if (precision == CRW_PREC_BF16X3) b += walk_tiles_saved_extra_bytes(B, T, N, C) + 256;
+    if (precision == CRW_PREC_BF16X3 && walk_fused_supported(N, C, T)) { const size_t f = walk_fused_saved_bytes(B, T); if (f > b) b = f; }
     return b;
 }
 
@@ -411,6 +417,8 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
     // BF16X3: tile-parallel tcgen05 GEMMs (any N).  FP32: shared-memory path for N <= 64, FMA tiles beyond.
     // BF16X3: one-tile sizes run the shared-memory kernels with warp-level MMAs; beyond that the tile-parallel tcgen05 path
     if (precision == CRW_PREC_BF16X3) {
+        if (getenv("CRW_WALK_FUSED") && walk_fused_supported(N, C, T) && aligned16p(x))
+            return walk_fused_forward(x, B, T, N, C, tau, loss, A_or_null, saved, st);
         if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
             return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st, true);
         return walk_tiles_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
@@ -444,6 +452,8 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
     if (precision == CRW_PREC_BF16X3) {
+        if (getenv("CRW_WALK_FUSED") && walk_fused_supported(N, C, T) && aligned16p(x))
+            return walk_fused_backward(x, saved, dloss, dA_or_null, B, T, N, C, tau, dx, st);
         if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
             return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st, true);
         return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);

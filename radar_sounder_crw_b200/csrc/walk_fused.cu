@@ -1,0 +1,730 @@
+// walk_fused.cu -- the training walk at the reference's own sizes (N <= 64 nodes, C = 128 channels) as ONE tcgen05 kernel per
+// direction, one CTA per batch element.
+//
+// Replaces src/model.py:22-46 (normalise, stride-1 affinities / tau, palindrome walk, cycle cross-entropy) and its autograd with
+//   walk_fused_fwd_kernel   frames arrive by TMA (cp.async.bulk.tensor, fp32, SWIZZLE_128B), are normalised and split into
+//                           bf16 hi / lo planes in the UMMA K-major layout; every product of the walk is a tcgen05.mma
+//                           (kind::f16 on the error-compensated pairs: hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) whose
+//                           epilogue -- temperature, the two row softmaxes, lse - diag -- works on the accumulator row a
+//                           thread owns and writes the NEXT product's operand straight back into shared memory.  No N x N
+//                           matrix goes through global memory between steps; what the reverse pass needs is saved as
+//                           ready-made operand tiles with bulk copies (cp.async.bulk shared -> global).
+//   walk_fused_bwd_kernel   the reverse pass over the same tiles (bulk copies global -> shared), one launch.
+// All 128 TMEM lanes are used by stacking two 64-row problems in one tile:
+//   affinity   rows = [E_a ; E_b] (the two frames in the two slots of the ring): lanes 0-63 x columns 0-63 hold E_a E_b^T,
+//              lanes 64-127 x columns 64-127 hold E_b E_a^T -- A_t and A_t^T, so that BOTH softmaxes of model.py:44 are row
+//              softmaxes of the thread that owns the row
+//   chain      X_k = [L_k ; R_k^T]:  [L_k | .] = X_{k-1} S'_{k-1} (B operand MN-major),  [. | R_k^T] = X_{k-1} S_{k-1}^T (K-major)
+//   cycle      M_k = L_k R_k = X_k[0:64] (X_k[64:128])^T, rows in lanes 0-63
+// (L_k = L_{k-1} S'_{k-1}, R_k = S_{k-1} R_{k-1}, M_k = L_k R_k.)
+#include <cuda_bf16.h>
+#include "tc_common.cuh"
+
+namespace crw {
+namespace wf {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kPlane128 = 128 * 128;                // [128 rows][128 B]
+constexpr uint32_t kTile64 = 64 * 128;                   // [64 rows][128 B]
+// ---- shared memory map of the forward kernel (bytes from a 1024-aligned base) ----
+constexpr uint32_t oE = 0;                               // E planes [hi, lo][k-block 0, 1][128 rows = slot 0, slot 1][128 B]
+constexpr uint32_t oX = oE + 4 * kPlane128;              // X = [L ; R^T]: hi, lo
+constexpr uint32_t oSS = oX + 2 * kPlane128;             // rows of S_t: hi, lo; rows of S'_t: hi, lo
+constexpr uint32_t oG = oSS + 4 * kTile64;               // rows of G_k = rowsoftmax(M_k) - I: hi, lo
+constexpr uint32_t oRaw = oG + 2 * kTile64;              // raw fp32 frame: 4 channel blocks x [64 rows][128 B] (SWIZZLE_128B)
+constexpr uint32_t oAst = oRaw + 4 * kTile64;            // fp32 A_t, dense [N][N] (staging for the coalesced copy-out)
+constexpr uint32_t oEnd = oAst + 64 * 64 * 4;
+constexpr uint32_t kSmemFwd = oEnd + 1024;
+
+// ---- saved workspace (bytes), per batch element: invn [T][64] fp32, then blocks j = 0 .. T-2 of operand tiles [X_j | S_j, S'_j | G_j]
+// (X_0, G_0 and S_{T-2} do not exist: those parts are never written and never read) ----
+constexpr size_t kSaveX = 2 * kPlane128, kSaveSS = 4 * kTile64, kSaveG = 2 * kTile64;
+constexpr size_t kSaveStep = kSaveX + kSaveSS + kSaveG;                   // 80 KB
+struct Layout {
+    size_t invn, tiles, part, ctr, total, per_b;
+    int T;
+    __host__ __device__ Layout(int B, int T_) : T(T_) {
+        const int K = T_ > 2 ? T_ - 2 : 0;
+        per_b = align_up((size_t)T_ * 64 * sizeof(float), 1024) + (size_t)(K + 1) * kSaveStep;
+        invn = 0;
+        tiles = align_up((size_t)T_ * 64 * sizeof(float), 1024);
+        part = (size_t)B * per_b;
+        ctr = part + align_up((size_t)B * sizeof(float), 256);
+        total = ctr + 256;
+    }
+    __host__ __device__ size_t step(int b, int j) const { return (size_t)b * per_b + tiles + (size_t)j * kSaveStep; }
+};
+
+struct FwdParams {
+    int B, T, N;
+    float inv_tau;
+    float* A;                 // [B, T-1, N, N] or null
+    float* loss;              // scalar
+    uint8_t* ws;              // saved workspace (1024-aligned)
+};
+
+// offset of 16-byte chunk `chunk` of row `row` inside a [rows][128 B] SWIZZLE_128B region
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(((row >> 3) << 10) + ((row & 7) << 7) + (((chunk ^ row) & 7) << 4)); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// two floats -> packed bf16 pair (hi) and the packed pair of the residuals (lo)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// one 64-element row (fp32, pads already zero) -> row `row` of a hi and a lo plane
+__device__ __forceinline__ void store_row64(uint32_t hi_base, uint32_t lo_base, int row, const float (&v)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], h[j], l[j]);
+        const uint32_t o = swz(row, c);
+        sts128(hi_base + o, h[0], h[1], h[2], h[3]);
+        sts128(lo_base + o, l[0], l[1], l[2], l[3]);
+    }
+}
+// row `row` of a hi / lo plane pair -> 64 floats (hi + lo)
+__device__ __forceinline__ void load_row64(uint32_t hi_base, uint32_t lo_base, int row, float (&v)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t o = swz(row, c);
+        const uint4 h = lds128u(hi_base + o), l = lds128u(lo_base + o);
+        const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&hh[j]), b2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
+            v[8 * c + 2 * j] = __low2float(a) + __low2float(b2);
+            v[8 * c + 2 * j + 1] = __high2float(a) + __high2float(b2);
+        }
+    }
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    tc::tmem_ld_32x32b_x32(taddr, reinterpret_cast<float(&)[32]>(v[0]));
+    tc::tmem_ld_32x32b_x32(taddr + 32u, reinterpret_cast<float(&)[32]>(v[32]));
+    tc::tmem_ld_wait();
+}
+// bulk copies shared <-> global (the TMA unit, no tensor map: whole operand tiles, layout unchanged)
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes),
+                 "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+// D[128 lanes x 64 columns at tmem_d] (+)= A (128 rows x 64 nkb) . B (64 rows x 64 nkb)^T on bf16 hi / lo pairs: hi.hi + hi.lo + lo.hi.
+// A_MN / B_MN: the operand is stored [k rows][64 (A: 128) elements] instead of [rows][64 k].  *_kbs = byte distance between the
+// operand's k-blocks of 64; a_lbo = byte distance between the two 64-row groups of an MN-major A.  One thread issues.
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void mma3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nkb, uint32_t a_kbs,
+                                     uint32_t b_kbs, uint32_t a_lbo, bool fresh) {
+    const uint32_t idesc = tc::umma_idesc_bf16_major(128, 64, A_MN, B_MN);
+    bool first = fresh;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t ap = (pass == 2) ? a_lo : a_hi, bp = (pass == 1) ? b_lo : b_hi;
+        for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + kb * a_kbs + ks * 2048, a_lbo, 1024) : tc::umma_smem_desc_k128(ap + kb * a_kbs + ks * 32);
+                const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + kb * b_kbs + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + kb * b_kbs + ks * 32);
+                tc::umma_bf16_ss(tmem_d, ad, bd, idesc, first ? 0u : 1u);
+                first = false;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar_tma, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_ss[128];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, N = p.N, T = p.T, K = T - 2;
+    const Layout lay(p.B, T);
+
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_tma, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&xmap);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t tA = tmem, tX = tmem + 128u, tM = tmem + 256u;       // accumulators: affinity (128 cols), chain (128), cycle (64)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t tma_phase = 0, mma_phase = 0;
+
+    const uint32_t sE = sb + oE, sX = sb + oX, sSS = sb + oSS, sG = sb + oG, sRaw = sb + oRaw, sAst = sb + oAst;
+    auto ePlane = [&](int pl, int kb) { return sE + (uint32_t)(pl * 2 + kb) * kPlane128; };
+
+    auto issue_frame = [&](int f) {          // thread 0: frame f of this batch element -> raw staging (four 32-channel blocks)
+        tc::mbar_arrive_expect_tx(&bar_tma, (uint32_t)N * 512u);
+        const int row0 = (b * T + f) * N;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+            tc::tma_load_2d(reinterpret_cast<void*>(smem_raw + (sRaw - tc::smem_u32(smem_raw)) + cb * kTile64), &xmap, cb * 32, row0, &bar_tma);
+    };
+    // raw staging -> normalised bf16 hi / lo rows of ring slot `slot`; thread = (channel half h, row r)
+    auto convert_frame = [&](int f, int slot) {
+        const int h = tid >> 6, r = tid & 63;
+        float v[64];
+        float ss = 0.0f;
+        if (r < N) {
+#pragma unroll
+            for (int cbl = 0; cbl < 2; ++cbl)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 q = lds128f(sRaw + (uint32_t)(2 * h + cbl) * kTile64 + swz(r, c));
+                    v[cbl * 32 + 4 * c + 0] = q.x; v[cbl * 32 + 4 * c + 1] = q.y; v[cbl * 32 + 4 * c + 2] = q.z; v[cbl * 32 + 4 * c + 3] = q.w;
+                    ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = 0.0f;
+        }
+        s_ss[tid] = ss;
+        __syncthreads();
+        const float inv = 1.0f / fmaxf(sqrtf(ss + s_ss[tid ^ 64]), kNormEps);
+        if (h == 0) reinterpret_cast<float*>(p.ws + (size_t)b * lay.per_b + lay.invn)[f * 64 + r] = (r < N) ? inv : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] *= inv;
+        store_row64(ePlane(0, h), ePlane(1, h), slot * 64 + r, v);
+    };
+
+    if (tid == 0) issue_frame(0);
+    tc::mbar_wait(&bar_tma, tma_phase & 1); ++tma_phase;
+    convert_frame(0, 0);
+    __syncthreads();                                                     // raw staging is free again
+    if (tid == 0) issue_frame(1);
+
+    float loss_acc = 0.0f;
+    for (int t = 0; t + 1 < T; ++t) {
+        if (t >= K && !p.A) break;                                       // the last affinity only feeds the returned A
+        tc::mbar_wait(&bar_tma, tma_phase & 1); ++tma_phase;
+        convert_frame(t + 1, (t + 1) & 1);
+        if (tid == 0) bulk_wait_read();                                  // the tiles saved at the end of the last step have left smem
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            if (t + 2 < T && (t + 1 < K || p.A)) issue_frame(t + 2);
+            // affinity: columns 0-63 <- rows . slot 1, columns 64-127 <- rows . slot 0
+            mma3<false, false>(tA, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0) + kTile64, ePlane(1, 0) + kTile64, 2, kPlane128, kPlane128, 0, true);
+            mma3<false, false>(tA + 64u, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
+            tc::umma_commit(&bar_mma);
+        }
+        tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
+        tc::tc_fence_after();
+        const int half = tid >> 6, r = tid & 63;
+        const bool isA = (half == 0) == ((t & 1) == 0);                  // this thread's accumulator row is a row of A_t (else of A_t^T)
+        {
+            float a[64];
+            tmem_ld64(tA + lane_base + (uint32_t)(half * 64), a);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                a[c] *= p.inv_tau;
+                if (c < N) mx = fmaxf(mx, a[c]);
+            }
+            if (p.A && isA && r < N) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c < N) tc::sts_f32(sAst + (uint32_t)(r * N + c) * 4u, a[c]);
+            }
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                a[c] = (c < N && r < N) ? exp2f((a[c] - mx) * 1.4426950408889634f) : 0.0f;
+                s += a[c];
+            }
+            const float is = (r < N) ? 1.0f / s : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) a[c] *= is;
+            if (t < K) {
+                // rows of S_t -> the K-major B operand of [. | R^T]; rows of S'_t -> the MN-major B operand of [L | .]
+                store_row64(sSS + (isA ? 0u : 2u * kTile64), sSS + (isA ? 1u : 3u) * kTile64, r, a);
+                if (t == 0) {
+                    // X_1 = [L_1 ; R_1^T] = [S'_0 ; I]
+                    if (!isA) {
+                        store_row64(sX, sX + kPlane128, r, a);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) a[c] = (c == r && r < N) ? 1.0f : 0.0f;
+                        store_row64(sX, sX + kPlane128, 64 + r, a);
+                    }
+                }
+            }
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        if (p.A) {
+            float* dst = p.A + ((size_t)b * (T - 1) + t) * N * N;
+            for (int i = tid; i < N * N; i += kThreads) dst[i] = tc::lds_f32(sAst + (uint32_t)i * 4u);
+        }
+        if (t >= K) continue;
+        const int k = t + 1;
+        if (k >= 2) {
+            if (tid == 0) {
+                tc::tc_fence_after();
+                mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);      // X . S'_{k-1}
+                mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);                  // X . S_{k-1}^T
+                tc::umma_commit(&bar_mma);
+            }
+            tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
+            tc::tc_fence_after();
+            {
+                float x[64];
+                tmem_ld64(tX + lane_base + (uint32_t)(half * 64), x);
+                store_row64(sX, sX + kPlane128, tid, x);
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            __syncthreads();
+        }
+        if (tid == 0) {
+            tc::tc_fence_after();
+            mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);        // M_k = L_k R_k
+            tc::umma_commit(&bar_mma);
+        }
+        tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
+        tc::tc_fence_after();
+        if (half == 0) {
+            float m[64];
+            tmem_ld64(tM + lane_base, m);
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+                if (c < N) mx = fmaxf(mx, m[c]);
+            float s = 0.0f, diag = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                if (c == r) diag = m[c];
+                m[c] = (c < N && r < N) ? exp2f((m[c] - mx) * 1.4426950408889634f) : 0.0f;
+                s += m[c];
+            }
+            if (r < N) loss_acc += logf(s) + mx - diag;
+            const float is = (r < N) ? 1.0f / s : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) m[c] = m[c] * is - ((c == r && r < N) ? 1.0f : 0.0f);
+            store_row64(sG, sG + kTile64, r, m);
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {          // what the reverse pass needs of step k, as ready-made operand tiles
+            uint8_t* dst = p.ws + lay.step(b, k);
+            bulk_store(dst, sX, (uint32_t)kSaveX);
+            bulk_store(p.ws + lay.step(b, k - 1) + kSaveX, sSS, (uint32_t)kSaveSS);
+            bulk_store(dst + kSaveX + kSaveSS, sG, (uint32_t)kSaveG);
+            bulk_commit();
+        }
+    }
+    // loss = sum over (b, k, d) of (lse - diag) / (B N N); the last CTA to finish adds the per-element sums in order
+    s_ss[tid] = loss_acc;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.0f;
+        for (int i = 0; i < 64; ++i) tot += s_ss[i];
+        float* part = reinterpret_cast<float*>(p.ws + lay.part);
+        part[b] = tot;
+        __threadfence();
+        const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(p.ws + lay.ctr), 1u);
+        if (done == (unsigned)p.B - 1u) {
+            __threadfence();
+            float sum = 0.0f;
+            for (int i = 0; i < p.B; ++i) sum += reinterpret_cast<volatile float*>(part)[i];
+            *p.loss = sum / ((float)p.B * (float)N * (float)N);
+        }
+        bulk_wait_all();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+    (void)lane; (void)s_last;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, one CTA per batch element, steps k = T-2 .. 1 (t = k - 1)
+//   state   Y_k = [dL_k ; dR_k^T], carried WITHOUT the factor dloss / (B N N) (everything up to the softmax backward is linear in it)
+//   (a)     [dS'_{k-1} | .] = L_{k-1}^T dL_k      (lanes 0-63),      [. | dS_{k-1}] = dR_k R_{k-1}^T   (lanes 64-127)
+//   (b)     T2 = coef S'_{k-1} o (dS' - rowsum) (rows of dA_{k-1}^T),  T1 = coef S_{k-1} o (dS - rowsum) + dA_in / tau (rows of dA_{k-1})
+//   (c)     dE_{k-1} += T1 E_k + T2^T E_k,   dE_k += T2 E_{k-1} + T1^T E_{k-1}     (frame j lives in lane half j & 1 of accumulator j & 1)
+//   (d)     Y_{k-1} = [G_{k-1} R_{k-1}^T ; G_{k-1}^T L_{k-1}] + Y_k [S'_{k-1}^T | S_{k-1}]
+//   (e)     dx_k = (dE_k - E_k (E_k . dE_k)) / |x_k|     (F.normalize backward), frame k is complete after step k
+// Every transposed operand is the SAME tile read through the other UMMA majorness; an MN-major A whose rows must land in lanes
+// 64-127 is addressed one 64-element group (8 KB) below its tile (the group that falls on lanes 0-63 multiplies junk into
+// accumulator rows nobody reads).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t bX = 0;                               // X_{k-1}: hi, lo                      } one 80 KB block of the saved
+constexpr uint32_t bSS = bX + 2 * kPlane128;             // rows of S_{k-1}: hi, lo; S'_{k-1}: hi, lo } workspace, loaded by one
+constexpr uint32_t bG = bSS + 4 * kTile64;               // rows of G_{k-1}: hi, lo               } bulk copy
+constexpr uint32_t bY = bG + 2 * kTile64;                // Y = [dL ; dR^T]: hi, lo
+constexpr uint32_t bT = bY + 2 * kPlane128;              // [T1 ; T2] (or [T2 ; T1]): hi, lo
+constexpr uint32_t bE = bT + 2 * kPlane128;              // E planes [hi, lo][k-block][128 rows = slot 0, slot 1][128 B]
+constexpr uint32_t bEnd = bE + 4 * kPlane128;
+constexpr uint32_t kSmemBwd = bEnd + 1024;
+static_assert(kSaveX == 2 * kPlane128 && kSaveSS == 4 * kTile64 && kSaveG == 2 * kTile64, "the saved block is the smem map bX .. bG");
+
+struct BwdParams {
+    int B, T, N;
+    float inv_tau;
+    const float* x;           // [B, T, N, 128] raw encoder output
+    const float* dloss;       // scalar
+    const float* dA;          // [B, T-1, N, N] gradient flowing into the returned A, or null
+    float* dx;                // [B, T, N, 128]
+    const uint8_t* ws;        // saved workspace of the forward kernel (1024-aligned)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar_ld, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.x, N = p.N, T = p.T, K = T - 2;
+    const Layout lay(p.B, T);
+    const float* invn = reinterpret_cast<const float*>(p.ws + (size_t)b * lay.per_b + lay.invn);
+
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_ld, 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t tDS = tmem, tY = tmem + 128u, tE0 = tmem + 256u;      // dE accumulators: tE0 + 128 (j & 1)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t ld_phase = 0, mma_phase = 0;
+    const int half = tid >> 6, r = tid & 63;
+
+    const uint32_t X_hi = sb + bX, X_lo = X_hi + kPlane128;
+    const uint32_t sST_hi = sb + bSS, sST_lo = sST_hi + kTile64, sSp_hi = sST_hi + 2 * kTile64, sSp_lo = sST_hi + 3 * kTile64;
+    const uint32_t G_hi = sb + bG, G_lo = G_hi + kTile64;
+    const uint32_t Y_hi = sb + bY, Y_lo = Y_hi + kPlane128;
+    const uint32_t T_hi = sb + bT, T_lo = T_hi + kPlane128;
+    auto ePlane = [&](int pl, int kb) { return sb + bE + (uint32_t)(pl * 2 + kb) * kPlane128; };
+    const float scale = __ldg(p.dloss) / ((float)p.B * (float)N * (float)N);
+    const float coef = scale * p.inv_tau;
+
+    auto load_block = [&](int j) {           // thread 0: [X_j | S_j, S'_j | G_j] -> bX .. bG
+        tc::mbar_arrive_expect_tx(&bar_ld, (uint32_t)kSaveStep);
+        bulk_load(sb + bX, p.ws + lay.step(b, j), (uint32_t)kSaveStep, &bar_ld);
+    };
+    // frame f: x * (1 / |x|) -> bf16 hi / lo rows of ring slot f & 1; thread = (channel half h, row r)
+    auto convert_frame = [&](int f) {
+        float v[64];
+        if (r < N) {
+            const float inv = invn[f * 64 + r];
+            const float4* src = reinterpret_cast<const float4*>(p.x + ((size_t)(b * T + f) * N + r) * 128 + 64 * half);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 q = __ldg(src + i);
+                v[4 * i] = q.x * inv; v[4 * i + 1] = q.y * inv; v[4 * i + 2] = q.z * inv; v[4 * i + 3] = q.w * inv;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = 0.0f;
+        }
+        store_row64(ePlane(0, half), ePlane(1, half), (f & 1) * 64 + r, v);
+    };
+    // dE_j (complete, in lane half j & 1 of accumulator j & 1) -> dx_j: F.normalize backward, row r of frame j
+    auto finish_frame = [&](int j) {
+        if (half != (j & 1)) return;                                     // (warp-uniform)
+        float g[128];
+        const uint32_t ta = tE0 + (uint32_t)((j & 1) * 128) + lane_base;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tc::tmem_ld_32x32b_x32(ta + (uint32_t)(c * 32), reinterpret_cast<float(&)[32]>(g[c * 32]));
+        tc::tmem_ld_wait();
+        if (r >= N) return;
+        const float inv = invn[j * 64 + r];
+        const float4* xr = reinterpret_cast<const float4*>(p.x + ((size_t)(b * T + j) * N + r) * 128);
+        float dot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float4 q = __ldg(xr + i);
+            dot = fmaf(q.x, g[4 * i], dot); dot = fmaf(q.y, g[4 * i + 1], dot); dot = fmaf(q.z, g[4 * i + 2], dot); dot = fmaf(q.w, g[4 * i + 3], dot);
+        }
+        dot *= inv * inv;                                                // E . dE = inv (x . dE); the factor E = inv x below takes the other inv
+        float4* dst = reinterpret_cast<float4*>(p.dx + ((size_t)(b * T + j) * N + r) * 128);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float4 q = __ldg(xr + i);
+            float4 o;
+            o.x = (g[4 * i] - q.x * dot) * inv; o.y = (g[4 * i + 1] - q.y * dot) * inv;
+            o.z = (g[4 * i + 2] - q.z * dot) * inv; o.w = (g[4 * i + 3] - q.w * dot) * inv;
+            dst[i] = o;
+        }
+    };
+    // (c): the two dE products of step k from the T tile (T1 rows in tile half (k-1) & 1, T2 rows in the other half)
+    auto issue_dE = [&](int k, bool fresh_k) {
+        const int p1 = (k - 1) & 1, p2 = k & 1;
+        const uint32_t T1o = (uint32_t)p1 * kTile64, T2o = (uint32_t)p2 * kTile64;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t Ek_hi = ePlane(0, kb) + (uint32_t)p2 * kTile64, Ek_lo = ePlane(1, kb) + (uint32_t)p2 * kTile64;
+            const uint32_t Em_hi = ePlane(0, kb) + (uint32_t)p1 * kTile64, Em_lo = ePlane(1, kb) + (uint32_t)p1 * kTile64;
+            const uint32_t acc1 = tE0 + (uint32_t)(p1 * 128 + kb * 64), acc2 = tE0 + (uint32_t)(p2 * 128 + kb * 64);
+            mma3<false, true>(acc1, T_hi, T_lo, Ek_hi, Ek_lo, 1, 0, 0, 0, true);                                                   // T1 E_k
+            mma3<true, true>(acc1, T_hi + T2o - (uint32_t)p1 * kTile64, T_lo + T2o - (uint32_t)p1 * kTile64, Ek_hi, Ek_lo, 1, 0, 0, kTile64, false);   // T2^T E_k
+            mma3<false, true>(acc2, T_hi, T_lo, Em_hi, Em_lo, 1, 0, 0, 0, fresh_k);                                                // T2 E_{k-1}
+            mma3<true, true>(acc2, T_hi + T1o - (uint32_t)p2 * kTile64, T_lo + T1o - (uint32_t)p2 * kTile64, Em_hi, Em_lo, 1, 0, 0, kTile64, false);   // T1^T E_{k-1}
+        }
+    };
+    auto mma_wait = [&]() {
+        tc::mbar_wait(&bar_mma, mma_phase & 1);
+        ++mma_phase;
+        tc::tc_fence_after();
+    };
+    auto publish = [&]() {                   // generic-proxy writes of operand tiles / TMEM reads done -> visible to the next MMAs
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+    };
+
+    const int k_first = p.dA ? K + 1 : K;
+    if (tid == 0) load_block(K);
+    convert_frame(k_first);
+    convert_frame(k_first - 1);
+    if (!p.dA) {                             // frame T-1 only enters the last affinity, which the loss does not see
+        float4* dst = reinterpret_cast<float4*>(p.dx + (size_t)(b * T + T - 1) * N * 128);
+        for (int i = tid; i < N * 32; i += kThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
+    publish();
+    // Y_K = [G_K R_K^T ; G_K^T L_K]
+    if (tid == 0) {
+        tc::tc_fence_after();
+        mma3<false, true>(tY, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
+        mma3<true, true>(tY + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
+        tc::umma_commit(&bar_mma);
+    }
+    mma_wait();
+    {
+        float y[64];
+        tmem_ld64(tY + lane_base + (uint32_t)(half * 64), y);
+        store_row64(Y_hi, Y_lo, tid, y);
+    }
+    publish();
+    if (tid == 0) load_block(K - 1);
+    if (p.dA) {
+        // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
+        float v[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) v[c] = 0.0f;
+        const int p1 = K & 1, p2 = (K + 1) & 1;
+        if (half == 1) {
+            if (r < N) {
+                const float* src = p.dA + (((size_t)b * (T - 1) + (T - 2)) * N + r) * N;
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c < N) v[c] = p.inv_tau * __ldg(src + c);
+            }
+            store_row64(T_hi, T_lo, p1 * 64 + r, v);
+        } else {
+            store_row64(T_hi, T_lo, p2 * 64 + r, v);
+        }
+        publish();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            issue_dE(K + 1, true);
+            tc::umma_commit(&bar_mma);
+        }
+        mma_wait();
+        finish_frame(K + 1);
+        tc::tc_fence_before();
+        __syncthreads();
+        convert_frame(K - 1);                // the ring now holds frames K and K - 1, as step K expects
+    }
+    tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
+    publish();
+
+    for (int k = K; k >= 1; --k) {
+        const int p1 = (k - 1) & 1, p2 = k & 1;
+        // ---- (a) ----
+        if (k >= 2) {
+            if (tid == 0) {
+                tc::tc_fence_after();
+                mma3<true, true>(tDS, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
+                mma3<true, true>(tDS + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
+                tc::umma_commit(&bar_mma);
+            }
+            mma_wait();
+        }
+        // ---- (b) ----
+        {
+            float d[64], P[64];
+            if (k >= 2) {
+                tmem_ld64(tDS + lane_base + (uint32_t)(half * 64), d);
+            } else if (half == 0) {
+                load_row64(Y_hi, Y_lo, r, d);                             // L_0 = I: dS'_0 = dL_1
+            } else {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) d[c] = 0.0f;                 // R_1 = I is not a product: dS_0 = 0
+            }
+            if (half == 0) load_row64(sSp_hi, sSp_lo, r, P);
+            else load_row64(sST_hi, sST_lo, r, P);
+            float s = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) s = fmaf(P[c], d[c], s);
+#pragma unroll
+            for (int c = 0; c < 64; ++c) d[c] = coef * P[c] * (d[c] - s);
+            if (half == 1 && p.dA && r < N) {
+                const float* src = p.dA + (((size_t)b * (T - 1) + (k - 1)) * N + r) * N;
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    if (c < N) d[c] = fmaf(p.inv_tau, __ldg(src + c), d[c]);
+            }
+            store_row64(T_hi, T_lo, (half == 1 ? p1 : p2) * 64 + r, d);
+        }
+        publish();
+        // ---- (c), (d) ----
+        if (tid == 0) {
+            tc::tc_fence_after();
+            issue_dE(k, k == k_first);
+            if (k >= 2) {
+                mma3<false, false>(tY, Y_hi, Y_lo, sSp_hi, sSp_lo, 1, 0, 0, 0, true);                                  // dL_k S'_{k-1}^T
+                mma3<false, true>(tY, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, false);                 // G_{k-1} R_{k-1}^T
+                mma3<false, true>(tY + 64u, Y_hi, Y_lo, sST_hi, sST_lo, 1, 0, 0, 0, true);                             // dR_k^T S_{k-1}
+                mma3<true, true>(tY + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, false);      // G_{k-1}^T L_{k-1}
+            }
+            tc::umma_commit(&bar_mma);
+        }
+        mma_wait();
+        // ---- (e) ----
+        if (k >= 2) {
+            float y[64];
+            tmem_ld64(tY + lane_base + (uint32_t)(half * 64), y);
+            store_row64(Y_hi, Y_lo, tid, y);
+        }
+        finish_frame(k);
+        if (k == 1) finish_frame(0);
+        publish();
+        // ---- next step's tiles and frame ----
+        if (k >= 2) {
+            if (tid == 0) load_block(k - 2);
+            convert_frame(k - 2);
+            tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
+            publish();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace wf
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnW wf_encode_fn() {
+    static EncodeTiledFnW fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFnW>(p);
+    }
+    return fn;
+}
+// fp32 [rows][128] row-major, box = [box_rows][32 floats = 128 B], SWIZZLE_128B
+static int make_tmap_f32_c32(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFnW fn = wf_encode_fn();
+    if (!fn) return CRW_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || box_rows < 1 || box_rows > 256) return CRW_ERR_ALIGN;
+    cuuint64_t gdim[2] = {128, rows};
+    cuuint64_t gstr[1] = {512};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
+}
+
+bool walk_fused_supported(int N, int C, int T) { return N >= 8 && N <= 64 && C == 128 && T >= 3; }
+size_t walk_fused_saved_bytes(int B, int T) { return wf::Layout(B, T).total + 1024; }
+
+static uint8_t* wf_align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023)); }
+
+int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, void* saved, cudaStream_t st) {
+    if (!walk_fused_supported(N, C, T)) return CRW_ERR_UNSUPPORTED;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemFwd));
+        attr_done[dev] = true;
+    }
+    CUtensorMap xmap;
+    int rc = make_tmap_f32_c32(&xmap, x, (uint64_t)B * T * N, (uint32_t)N);
+    if (rc != CRW_OK) return rc;
+    wf::FwdParams p;
+    p.B = B; p.T = T; p.N = N;
+    p.inv_tau = 1.0f / tau;
+    p.A = A_or_null;
+    p.loss = loss;
+    p.ws = wf_align1k(saved);
+    const wf::Layout lay(B, T);
+    CRW_CUDA_RET(cudaMemsetAsync(p.ws + lay.ctr, 0, 4, st));
+    wf::walk_fused_fwd_kernel<<<B, wf::kThreads, wf::kSmemFwd, st>>>(xmap, p);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+int walk_fused_backward(const float* x, const void* saved, const float* dloss, const float* dA_or_null, int B, int T, int N, int C, float tau,
+                        float* dx, cudaStream_t st) {
+    if (!walk_fused_supported(N, C, T)) return CRW_ERR_UNSUPPORTED;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemBwd));
+        attr_done[dev] = true;
+    }
+    wf::BwdParams p;
+    p.B = B; p.T = T; p.N = N;
+    p.inv_tau = 1.0f / tau;
+    p.x = x; p.dloss = dloss; p.dA = dA_or_null; p.dx = dx;
+    p.ws = wf_align1k(const_cast<void*>(saved));
+    wf::walk_fused_bwd_kernel<<<B, wf::kThreads, wf::kSmemBwd, st>>>(p);
+    CRW_LAUNCH_RET();
+    return CRW_OK;
+}
+
+}  // namespace crw
