@@ -230,6 +230,8 @@ int crw_debug_umma_pair_gemm(const void* A_bf16, const void* B_bf16, int BN, flo
 int crw_debug_lp_profile(unsigned long long* host_out, int reset);
 /* same for the exact tensor path (CRW_PREC_TC_EXACT): [2 kernels: filter, refine][160 CTAs][18 warps][8 phases] uint64 */
 int crw_debug_lp_x_profile(unsigned long long* host_out, int reset);
+/* profiling aid: per-phase cycle counters of the fused walk kernels, [forward, backward][16] uint64 (CRW_WALK_PROF=1) */
+int crw_debug_walk_fused_profile(unsigned long long* host_out, int reset);
 /* Test aid, host only (no GPU): the work items of a tensor-path top-k launch over n_tiles query tiles on `grid` CTAs -- whole tiles,
  * and, when the last round is partial, its tiles cut in two key-range halves scheduled first.  out[3 i .. 3 i + 2] = tile, half
  * (-1 whole, 0 / 1), index among the split tiles; returns the number of items (out may be null to query it), < 0 on error. */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "crw_debug_umma_pair_gemm": (_c_int, [_vp, _vp, _c_int, _vp, _vp]),
     "crw_debug_lp_profile": (_c_int, [_vp, _c_int]),
     "crw_debug_lp_x_profile": (_c_int, [_vp, _c_int]),
+    "crw_debug_walk_fused_profile": (_c_int, [_vp, _c_int]),
     "crw_debug_lp_schedule": (_c_int, [_c_int, _c_int, _c_int, _vp, _c_int]),
 }
 

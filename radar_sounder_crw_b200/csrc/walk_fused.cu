@@ -23,7 +23,8 @@
 namespace crw {
 namespace wf {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256 + 32;                       // forward: 8 epilogue warps (warps w and w + 4 share accumulator rows 32 (w & 3) .., 32 columns each) + the issuer warp
+constexpr int kBwdThreads = 128 + 32;                    // backward: 4 epilogue warps (thread = accumulator row) + the issuer warp
 constexpr uint32_t kPlane128 = 128 * 128;                // [128 rows][128 B]
 constexpr uint32_t kTile64 = 64 * 128;                   // [64 rows][128 B]
 // ---- shared memory map of the forward kernel (bytes from a 1024-aligned base) ----
@@ -36,27 +37,30 @@ constexpr uint32_t oAst = oRaw + 4 * kTile64;            // fp32 A_t, dense [N][
 constexpr uint32_t oEnd = oAst + 64 * 64 * 4;
 constexpr uint32_t kSmemFwd = oEnd + 1024;
 
-// ---- saved workspace (bytes), per batch element: invn [T][64] fp32, then blocks j = 0 .. T-2 of operand tiles [X_j | S_j, S'_j | G_j]
+// ---- saved workspace (bytes), per batch element: invn [T][64] fp32, the T normalised frames as operand rows, then blocks j = 0 .. T-2 of operand tiles [X_j | S_j, S'_j | G_j]
 // (X_0, G_0 and S_{T-2} do not exist: those parts are never written and never read) ----
 constexpr size_t kSaveX = 2 * kPlane128, kSaveSS = 4 * kTile64, kSaveG = 2 * kTile64;
 constexpr size_t kSaveStep = kSaveX + kSaveSS + kSaveG;                   // 80 KB
+constexpr size_t kSaveFrame = 4 * kTile64;                                // the normalised frame as bf16 hi / lo operand rows: 32 KB
 struct Layout {
-    size_t invn, tiles, part, ctr, total, per_b;
+    size_t invn, frames, tiles, part, ctr, total, per_b;
     int T;
     __host__ __device__ Layout(int B, int T_) : T(T_) {
         const int K = T_ > 2 ? T_ - 2 : 0;
-        per_b = align_up((size_t)T_ * 64 * sizeof(float), 1024) + (size_t)(K + 1) * kSaveStep;
         invn = 0;
-        tiles = align_up((size_t)T_ * 64 * sizeof(float), 1024);
+        frames = align_up((size_t)T_ * 64 * sizeof(float), 1024);
+        tiles = frames + (size_t)T_ * kSaveFrame;
+        per_b = tiles + (size_t)(K + 1) * kSaveStep;
         part = (size_t)B * per_b;
         ctr = part + align_up((size_t)B * sizeof(float), 256);
         total = ctr + 256;
     }
     __host__ __device__ size_t step(int b, int j) const { return (size_t)b * per_b + tiles + (size_t)j * kSaveStep; }
+    __host__ __device__ size_t frame(int b, int f) const { return (size_t)b * per_b + frames + (size_t)f * kSaveFrame; }   // [hi, lo][k-block][64 rows][128 B]
 };
 
 struct FwdParams {
-    int B, T, N;
+    int B, T, N, prof;
     float inv_tau;
     float* A;                 // [B, T-1, N, N] or null
     float* loss;              // scalar
@@ -123,6 +127,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t b
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes),
@@ -130,13 +135,15 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint3
                  : "memory");
 }
 
-// D[128 lanes x 64 columns at tmem_d] (+)= A (128 rows x 64 nkb) . B (64 rows x 64 nkb)^T on bf16 hi / lo pairs: hi.hi + hi.lo + lo.hi.
-// A_MN / B_MN: the operand is stored [k rows][64 (A: 128) elements] instead of [rows][64 k].  *_kbs = byte distance between the
-// operand's k-blocks of 64; a_lbo = byte distance between the two 64-row groups of an MN-major A.  One thread issues.
-template <bool A_MN, bool B_MN>
+// D[128 lanes x NN columns at tmem_d] (+)= A (128 rows x 64 nkb) . B (NN rows x 64 nkb)^T on bf16 hi / lo pairs: hi.hi + hi.lo + lo.hi.
+// A_MN / B_MN: the operand is stored [k rows][64-element groups] instead of [rows][64 k].  *_kbs = byte distance between the
+// operand's k-blocks of 64; a_lbo / b_lbo = byte distance between the 64-element groups of an MN-major operand.  One thread issues.
+// (An SS MMA reads its A and B slices from shared memory: at N = 64 that is 6 KB per 33 cycles of tensor time, more than the
+// 128 B / cycle the SM delivers -- measured ~55 cycles per MMA; N = 128 amortises the A slice.)
+template <bool A_MN, bool B_MN, int NN = 64>
 __device__ __forceinline__ void mma3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int nkb, uint32_t a_kbs,
-                                     uint32_t b_kbs, uint32_t a_lbo, bool fresh) {
-    const uint32_t idesc = tc::umma_idesc_bf16_major(128, 64, A_MN, B_MN);
+                                     uint32_t b_kbs, uint32_t a_lbo, bool fresh, uint32_t b_lbo = 8192) {
+    const uint32_t idesc = tc::umma_idesc_bf16_major(128, NN, A_MN, B_MN);
     bool first = fresh;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
@@ -145,13 +152,47 @@ __device__ __forceinline__ void mma3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + kb * a_kbs + ks * 2048, a_lbo, 1024) : tc::umma_smem_desc_k128(ap + kb * a_kbs + ks * 32);
-                const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + kb * b_kbs + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + kb * b_kbs + ks * 32);
+                const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + kb * b_kbs + ks * 2048, b_lbo, 1024) : tc::umma_smem_desc_k128(bp + kb * b_kbs + ks * 32);
                 tc::umma_bf16_ss(tmem_d, ad, bd, idesc, first ? 0u : 1u);
                 first = false;
             }
         }
     }
 }
+// 32 columns of a row (fp32, pads already zero) -> chunks 4 ch .. 4 ch + 3 of row `row` of a hi and a lo plane
+__device__ __forceinline__ void store_row32(uint32_t hi_base, uint32_t lo_base, int row, int ch, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split2(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], h[j], l[j]);
+        const uint32_t o = swz(row, 4 * ch + c);
+        sts128(hi_base + o, h[0], h[1], h[2], h[3]);
+        sts128(lo_base + o, l[0], l[1], l[2], l[3]);
+    }
+}
+__device__ __forceinline__ void load_row32(uint32_t hi_base, uint32_t lo_base, int row, int ch, float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t o = swz(row, 4 * ch + c);
+        const uint4 h = lds128u(hi_base + o), l = lds128u(lo_base + o);
+        const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&hh[j]), b2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[j]);
+            v[8 * c + 2 * j] = __low2float(a) + __low2float(b2);
+            v[8 * c + 2 * j + 1] = __high2float(a) + __high2float(b2);
+        }
+    }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    tc::tmem_ld_32x32b_x32(taddr, v);
+    tc::tmem_ld_wait();
+}
+
+// profiling aid (CRW_WALK_PROF=1): cycles per phase of CTA 0 as seen by thread 0, [kernel 0 = forward, 1 = backward][16 phases]
+__device__ unsigned long long g_wf_prof[2 * 16];
+#define WFPROF(kern, idx) do { if (p.prof && blockIdx.x == 0 && tid == 0) { const long long c_now = clock64(); g_wf_prof[(kern) * 16 + (idx)] += (unsigned long long)(c_now - c_last); c_last = c_now; } } while (0)
 
 // ------------------------------------------------------------------------------------------
 // forward
@@ -161,8 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ uint64_t bar_tma, bar_mma;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_ss[128];
-    __shared__ int s_last;
+    __shared__ float s_red[4][64];           // row reductions across the threads that share a row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x, N = p.N, T = p.T, K = T - 2;
     const Layout lay(p.B, T);
@@ -177,116 +217,154 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    // Warps 0-7 own the accumulator rows (epilogues): warp w works on TMEM lanes 32 (w & 3) .. and on column half w >> 2 of its
+    // row's 64-column window.  Warp 8 issues the TMA loads and the MMAs from ONE lane elected inside its own branch, so that the
+    // compiler emits straight-line issue code (inside an `if (tid == 0)` region every tcgen05.mma is wrapped in an elect + branch
+    // loop).  Both roles walk the same sequence of CTA barriers.
+    const bool is_epi = warp < 8, is_iss = warp == 8;
     const uint32_t tmem = tmem_base_s;
     const uint32_t tA = tmem, tX = tmem + 128u, tM = tmem + 256u;       // accumulators: affinity (128 cols), chain (128), cycle (64)
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int row = ((warp & 3) << 5) | lane;                            // accumulator row (TMEM lane)
+    const int half = row >> 6, r = row & 63, ch = (warp >> 2) & 1;       // which 64-row problem, row in it, column half
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t tma_phase = 0, mma_phase = 0;
 
     const uint32_t sE = sb + oE, sX = sb + oX, sSS = sb + oSS, sG = sb + oG, sRaw = sb + oRaw, sAst = sb + oAst;
     auto ePlane = [&](int pl, int kb) { return sE + (uint32_t)(pl * 2 + kb) * kPlane128; };
+    auto publish = [&]() {                   // operand tiles written / accumulators read -> visible to the MMAs issued after the barrier
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+    };
+    auto mma_wait = [&]() {
+        tc::mbar_wait(&bar_mma, mma_phase & 1);
+        ++mma_phase;
+        tc::tc_fence_after();
+    };
 
-    auto issue_frame = [&](int f) {          // thread 0: frame f of this batch element -> raw staging (four 32-channel blocks)
+    auto issue_frame = [&](int f) {          // issuer lane: frame f of this batch element -> raw staging (four 32-channel blocks)
         tc::mbar_arrive_expect_tx(&bar_tma, (uint32_t)N * 512u);
         const int row0 = (b * T + f) * N;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb)
             tc::tma_load_2d(reinterpret_cast<void*>(smem_raw + (sRaw - tc::smem_u32(smem_raw)) + cb * kTile64), &xmap, cb * 32, row0, &bar_tma);
     };
-    // raw staging -> normalised bf16 hi / lo rows of ring slot `slot`; thread = (channel half h, row r)
-    auto convert_frame = [&](int f, int slot) {
-        const int h = tid >> 6, r = tid & 63;
-        float v[64];
+    // raw staging -> normalised bf16 hi / lo rows of ring slot f & 1; thread = (32-channel block cq, row rr).  Holds one CTA barrier.
+    auto convert_frame = [&](int f) {
+        const int cq = (tid >> 6) & 3, rr = tid & 63;
+        float v[32];
         float ss = 0.0f;
-        if (r < N) {
+        if (is_epi && rr < N) {
 #pragma unroll
-            for (int cbl = 0; cbl < 2; ++cbl)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 q = lds128f(sRaw + (uint32_t)(2 * h + cbl) * kTile64 + swz(r, c));
-                    v[cbl * 32 + 4 * c + 0] = q.x; v[cbl * 32 + 4 * c + 1] = q.y; v[cbl * 32 + 4 * c + 2] = q.z; v[cbl * 32 + 4 * c + 3] = q.w;
-                    ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
-                }
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = lds128f(sRaw + (uint32_t)cq * kTile64 + swz(rr, c));
+                v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+                ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = 0.0f;
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
         }
-        s_ss[tid] = ss;
+        if (is_epi) s_red[cq][rr] = ss;
         __syncthreads();
-        const float inv = 1.0f / fmaxf(sqrtf(ss + s_ss[tid ^ 64]), kNormEps);
-        if (h == 0) reinterpret_cast<float*>(p.ws + (size_t)b * lay.per_b + lay.invn)[f * 64 + r] = (r < N) ? inv : 0.0f;
+        if (is_epi) {
+            const float inv = 1.0f / fmaxf(sqrtf((s_red[0][rr] + s_red[1][rr]) + (s_red[2][rr] + s_red[3][rr])), kNormEps);
+            if (cq == 0) reinterpret_cast<float*>(p.ws + (size_t)b * lay.per_b + lay.invn)[f * 64 + rr] = (rr < N) ? inv : 0.0f;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] *= inv;
-        store_row64(ePlane(0, h), ePlane(1, h), slot * 64 + r, v);
+            for (int i = 0; i < 32; ++i) v[i] *= inv;
+            store_row32(ePlane(0, cq >> 1), ePlane(1, cq >> 1), (f & 1) * 64 + rr, cq & 1, v);
+        }
+    };
+    auto save_frame = [&](int f) {           // issuer lane: the operand rows of frame f, for the reverse pass
+        uint8_t* dst = p.ws + lay.frame(b, f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bulk_store(dst + q * kTile64, sE + (uint32_t)q * kPlane128 + (uint32_t)(f & 1) * kTile64, kTile64);
+        bulk_commit();
     };
 
-    if (tid == 0) issue_frame(0);
+    if (is_iss && tc::elect_one()) issue_frame(0);
     tc::mbar_wait(&bar_tma, tma_phase & 1); ++tma_phase;
-    convert_frame(0, 0);
-    __syncthreads();                                                     // raw staging is free again
-    if (tid == 0) issue_frame(1);
+    convert_frame(0);
+    publish();                                                           // raw staging is free again
+    if (is_iss && tc::elect_one()) { issue_frame(1); save_frame(0); }
 
     float loss_acc = 0.0f;
+    long long c_last = clock64();
     for (int t = 0; t + 1 < T; ++t) {
         if (t >= K && !p.A) break;                                       // the last affinity only feeds the returned A
         tc::mbar_wait(&bar_tma, tma_phase & 1); ++tma_phase;
-        convert_frame(t + 1, (t + 1) & 1);
-        if (tid == 0) bulk_wait_read();                                  // the tiles saved at the end of the last step have left smem
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        WFPROF(0, 0);
+        convert_frame(t + 1);
+        WFPROF(0, 1);
+        publish();
+        if (is_iss && tc::elect_one()) {
             tc::tc_fence_after();
             if (t + 2 < T && (t + 1 < K || p.A)) issue_frame(t + 2);
-            // affinity: columns 0-63 <- rows . slot 1, columns 64-127 <- rows . slot 0
-            mma3<false, false>(tA, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0) + kTile64, ePlane(1, 0) + kTile64, 2, kPlane128, kPlane128, 0, true);
-            mma3<false, false>(tA + 64u, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
+            save_frame(t + 1);
+            // affinity: [rows . slot 0 | rows . slot 1] in one N = 128 product
+            mma3<false, false, 128>(tA, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
+            // everything saved before this step's frame has left shared memory before the epilogues below overwrite S / S' / X / G
+            // (and, one step on, the other ring slot): the wait runs under the MMAs
+            bulk_wait_read1();
             tc::umma_commit(&bar_mma);
         }
-        tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
-        tc::tc_fence_after();
-        const int half = tid >> 6, r = tid & 63;
+        WFPROF(0, 2);
+        mma_wait();
+        WFPROF(0, 3);
+        // lanes 0-63 are the rows of the frame in slot 0 and want the product with slot 1 (columns 64-127), and the other way round
         const bool isA = (half == 0) == ((t & 1) == 0);                  // this thread's accumulator row is a row of A_t (else of A_t^T)
-        {
-            float a[64];
-            tmem_ld64(tA + lane_base + (uint32_t)(half * 64), a);
-            float mx = -INFINITY;
+        float a[32];
+        float mx = -INFINITY;
+        if (is_epi) {
+            tmem_ld32(tA + lane_base + (uint32_t)((1 - half) * 64 + ch * 32), a);
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
+            for (int c = 0; c < 32; ++c) {
                 a[c] *= p.inv_tau;
-                if (c < N) mx = fmaxf(mx, a[c]);
+                if (32 * ch + c < N) mx = fmaxf(mx, a[c]);
             }
             if (p.A && isA && r < N) {
 #pragma unroll
-                for (int c = 0; c < 64; ++c)
-                    if (c < N) tc::sts_f32(sAst + (uint32_t)(r * N + c) * 4u, a[c]);
+                for (int c = 0; c < 32; ++c)
+                    if (32 * ch + c < N) tc::sts_f32(sAst + (uint32_t)(r * N + 32 * ch + c) * 4u, a[c]);
             }
-            float s = 0.0f;
+            s_red[half * 2 + ch][r] = mx;
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        float s = 0.0f;
+        if (is_epi) {
+            mx = fmaxf(mx, s_red[half * 2 + (1 - ch)][r]);
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                a[c] = (c < N && r < N) ? exp2f((a[c] - mx) * 1.4426950408889634f) : 0.0f;
+            for (int c = 0; c < 32; ++c) {
+                a[c] = (32 * ch + c < N && r < N) ? exp2f((a[c] - mx) * 1.4426950408889634f) : 0.0f;
                 s += a[c];
             }
+        }
+        __syncthreads();
+        if (is_epi) s_red[half * 2 + ch][r] = s;
+        __syncthreads();
+        if (is_epi) {
+            s += s_red[half * 2 + (1 - ch)][r];
             const float is = (r < N) ? 1.0f / s : 0.0f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) a[c] *= is;
+            for (int c = 0; c < 32; ++c) a[c] *= is;
             if (t < K) {
                 // rows of S_t -> the K-major B operand of [. | R^T]; rows of S'_t -> the MN-major B operand of [L | .]
-                store_row64(sSS + (isA ? 0u : 2u * kTile64), sSS + (isA ? 1u : 3u) * kTile64, r, a);
+                store_row32(sSS + (isA ? 0u : 2u * kTile64), sSS + (isA ? 1u : 3u) * kTile64, r, ch, a);
                 if (t == 0) {
                     // X_1 = [L_1 ; R_1^T] = [S'_0 ; I]
                     if (!isA) {
-                        store_row64(sX, sX + kPlane128, r, a);
+                        store_row32(sX, sX + kPlane128, r, ch, a);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 64; ++c) a[c] = (c == r && r < N) ? 1.0f : 0.0f;
-                        store_row64(sX, sX + kPlane128, 64 + r, a);
+                        for (int c = 0; c < 32; ++c) a[c] = (32 * ch + c == r && r < N) ? 1.0f : 0.0f;
+                        store_row32(sX, sX + kPlane128, 64 + r, ch, a);
                     }
                 }
             }
         }
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncthreads();
+        publish();
+        WFPROF(0, 4);
         if (p.A) {
             float* dst = p.A + ((size_t)b * (T - 1) + t) * N * N;
             for (int i = tid; i < N * N; i += kThreads) dst[i] = tc::lds_f32(sAst + (uint32_t)i * 4u);
@@ -294,67 +372,71 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
         if (t >= K) continue;
         const int k = t + 1;
         if (k >= 2) {
-            if (tid == 0) {
+            if (is_iss && tc::elect_one()) {
                 tc::tc_fence_after();
                 mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);      // X . S'_{k-1}
                 mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);                  // X . S_{k-1}^T
                 tc::umma_commit(&bar_mma);
             }
-            tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
-            tc::tc_fence_after();
-            {
-                float x[64];
-                tmem_ld64(tX + lane_base + (uint32_t)(half * 64), x);
-                store_row64(sX, sX + kPlane128, tid, x);
+            WFPROF(0, 5);
+            mma_wait();
+            WFPROF(0, 6);
+            if (is_epi) {
+                float x[32];
+                tmem_ld32(tX + lane_base + (uint32_t)(half * 64 + ch * 32), x);
+                store_row32(sX, sX + kPlane128, row, ch, x);
             }
-            tc::fence_proxy_async();
-            tc::tc_fence_before();
-            __syncthreads();
+            publish();
+            WFPROF(0, 7);
         }
-        if (tid == 0) {
+        if (is_iss && tc::elect_one()) {
             tc::tc_fence_after();
             mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);        // M_k = L_k R_k
             tc::umma_commit(&bar_mma);
         }
-        tc::mbar_wait(&bar_mma, mma_phase & 1); ++mma_phase;
-        tc::tc_fence_after();
-        if (half == 0) {
-            float m[64];
-            tmem_ld64(tM + lane_base, m);
-            float mx = -INFINITY;
+        WFPROF(0, 8);
+        mma_wait();
+        WFPROF(0, 9);
+        // rows of M_k (lanes 0-63): lse - diag and G_k = rowsoftmax(M_k) - I.  The entries of M_k lie in [0, 1]: exp(m - 1) needs no row max
+        float m[32];
+        float sm = 0.0f, diag = 0.0f;
+        if (is_epi && half == 0) {
+            tmem_ld32(tM + lane_base + (uint32_t)(ch * 32), m);
 #pragma unroll
-            for (int c = 0; c < 64; ++c)
-                if (c < N) mx = fmaxf(mx, m[c]);
-            float s = 0.0f, diag = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                if (c == r) diag = m[c];
-                m[c] = (c < N && r < N) ? exp2f((m[c] - mx) * 1.4426950408889634f) : 0.0f;
-                s += m[c];
+            for (int c = 0; c < 32; ++c) {
+                if (32 * ch + c == r) diag = m[c];
+                m[c] = (32 * ch + c < N && r < N) ? exp2f((m[c] - 1.0f) * 1.4426950408889634f) : 0.0f;
+                sm += m[c];
             }
-            if (r < N) loss_acc += logf(s) + mx - diag;
-            const float is = (r < N) ? 1.0f / s : 0.0f;
-#pragma unroll
-            for (int c = 0; c < 64; ++c) m[c] = m[c] * is - ((c == r && r < N) ? 1.0f : 0.0f);
-            store_row64(sG, sG + kTile64, r, m);
+            s_red[ch][r] = sm;
         }
-        tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
-        if (tid == 0) {          // what the reverse pass needs of step k, as ready-made operand tiles
+        if (is_epi && half == 0) {
+            sm += s_red[1 - ch][r];
+            if (r < N && (r >> 5) == ch) loss_acc += logf(sm) + 1.0f - diag;
+            const float is = (r < N) ? 1.0f / sm : 0.0f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) m[c] = m[c] * is - ((32 * ch + c == r && r < N) ? 1.0f : 0.0f);
+            store_row32(sG, sG + kTile64, r, ch, m);
+        }
+        publish();
+        if (is_iss && tc::elect_one()) {     // what the reverse pass needs of step k, as ready-made operand tiles
             uint8_t* dst = p.ws + lay.step(b, k);
             bulk_store(dst, sX, (uint32_t)kSaveX);
             bulk_store(p.ws + lay.step(b, k - 1) + kSaveX, sSS, (uint32_t)kSaveSS);
             bulk_store(dst + kSaveX + kSaveSS, sG, (uint32_t)kSaveG);
             bulk_commit();
         }
+        WFPROF(0, 10);
     }
     // loss = sum over (b, k, d) of (lse - diag) / (B N N); the last CTA to finish adds the per-element sums in order
-    s_ss[tid] = loss_acc;
+    __syncthreads();
+    if (is_epi && half == 0) s_red[ch][r] = loss_acc;
     __syncthreads();
     if (tid == 0) {
         float tot = 0.0f;
-        for (int i = 0; i < 64; ++i) tot += s_ss[i];
+        for (int i = 0; i < 64; ++i) tot += s_red[0][i] + s_red[1][i];
         float* part = reinterpret_cast<float*>(p.ws + lay.part);
         part[b] = tot;
         __threadfence();
@@ -365,12 +447,11 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
             for (int i = 0; i < p.B; ++i) sum += reinterpret_cast<volatile float*>(part)[i];
             *p.loss = sum / ((float)p.B * (float)N * (float)N);
         }
-        bulk_wait_all();
     }
+    if (is_iss && tc::elect_one()) bulk_wait_all();                      // (bulk groups belong to the thread that issued them)
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
-    (void)lane; (void)s_last;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -396,7 +477,7 @@ constexpr uint32_t kSmemBwd = bEnd + 1024;
 static_assert(kSaveX == 2 * kPlane128 && kSaveSS == 4 * kTile64 && kSaveG == 2 * kTile64, "the saved block is the smem map bX .. bG");
 
 struct BwdParams {
-    int B, T, N;
+    int B, T, N, prof;
     float inv_tau;
     const float* x;           // [B, T, N, 128] raw encoder output
     const float* dloss;       // scalar
@@ -405,7 +486,7 @@ struct BwdParams {
     const uint8_t* ws;        // saved workspace of the forward kernel (1024-aligned)
 };
 
-__global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) walk_fused_bwd_kernel(BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ uint64_t bar_ld, bar_mma;
@@ -424,9 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    const bool is_epi = warp < 4, is_iss = warp == 4;
     const uint32_t tmem = tmem_base_s;
     const uint32_t tDS = tmem, tY = tmem + 128u, tE0 = tmem + 256u;      // dE accumulators: tE0 + 128 (j & 1)
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ld_phase = 0, mma_phase = 0;
     const int half = tid >> 6, r = tid & 63;
 
@@ -445,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
     };
     // frame f: x * (1 / |x|) -> bf16 hi / lo rows of ring slot f & 1; thread = (channel half h, row r)
     auto convert_frame = [&](int f) {
+        if (!is_epi) return;
         float v[64];
         if (r < N) {
             const float inv = invn[f * 64 + r];
@@ -462,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
     };
     // dE_j (complete, in lane half j & 1 of accumulator j & 1) -> dx_j: F.normalize backward, row r of frame j
     auto finish_frame = [&](int j) {
-        if (half != (j & 1)) return;                                     // (warp-uniform)
+        if (!is_epi || half != (j & 1)) return;                          // (warp-uniform)
         float g[128];
         const uint32_t ta = tE0 + (uint32_t)((j & 1) * 128) + lane_base;
 #pragma unroll
@@ -515,37 +598,38 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
     };
 
     const int k_first = p.dA ? K + 1 : K;
-    if (tid == 0) load_block(K);
+    if (is_iss && tc::elect_one()) load_block(K);
     convert_frame(k_first);
     convert_frame(k_first - 1);
     if (!p.dA) {                             // frame T-1 only enters the last affinity, which the loss does not see
         float4* dst = reinterpret_cast<float4*>(p.dx + (size_t)(b * T + T - 1) * N * 128);
-        for (int i = tid; i < N * 32; i += kThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < N * 32; i += kBwdThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
     publish();
     // Y_K = [G_K R_K^T ; G_K^T L_K]
-    if (tid == 0) {
+    if (is_iss && tc::elect_one()) {
         tc::tc_fence_after();
         mma3<false, true>(tY, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
         mma3<true, true>(tY + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
         tc::umma_commit(&bar_mma);
     }
     mma_wait();
-    {
+    if (is_epi) {
         float y[64];
         tmem_ld64(tY + lane_base + (uint32_t)(half * 64), y);
         store_row64(Y_hi, Y_lo, tid, y);
     }
     publish();
-    if (tid == 0) load_block(K - 1);
+    if (is_iss && tc::elect_one()) load_block(K - 1);
     if (p.dA) {
         // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
         float v[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) v[c] = 0.0f;
         const int p1 = K & 1, p2 = (K + 1) & 1;
-        if (half == 1) {
+        if (!is_epi) {
+        } else if (half == 1) {
             if (r < N) {
                 const float* src = p.dA + (((size_t)b * (T - 1) + (T - 2)) * N + r) * N;
 #pragma unroll
@@ -557,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
             store_row64(T_hi, T_lo, p2 * 64 + r, v);
         }
         publish();
-        if (tid == 0) {
+        if (is_iss && tc::elect_one()) {
             tc::tc_fence_after();
             issue_dE(K + 1, true);
             tc::umma_commit(&bar_mma);
@@ -571,20 +655,23 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
     tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
     publish();
 
+    long long c_last = clock64();
     for (int k = K; k >= 1; --k) {
         const int p1 = (k - 1) & 1, p2 = k & 1;
         // ---- (a) ----
         if (k >= 2) {
-            if (tid == 0) {
+            if (is_iss && tc::elect_one()) {
                 tc::tc_fence_after();
                 mma3<true, true>(tDS, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
                 mma3<true, true>(tDS + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
                 tc::umma_commit(&bar_mma);
             }
+            WFPROF(1, 0);
             mma_wait();
+            WFPROF(1, 1);
         }
         // ---- (b) ----
-        {
+        if (is_epi) {
             float d[64], P[64];
             if (k >= 2) {
                 tmem_ld64(tDS + lane_base + (uint32_t)(half * 64), d);
@@ -610,8 +697,9 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
             store_row64(T_hi, T_lo, (half == 1 ? p1 : p2) * 64 + r, d);
         }
         publish();
+        WFPROF(1, 2);
         // ---- (c), (d) ----
-        if (tid == 0) {
+        if (is_iss && tc::elect_one()) {
             tc::tc_fence_after();
             issue_dE(k, k == k_first);
             if (k >= 2) {
@@ -622,9 +710,11 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
             }
             tc::umma_commit(&bar_mma);
         }
+        WFPROF(1, 3);
         mma_wait();
+        WFPROF(1, 4);
         // ---- (e) ----
-        if (k >= 2) {
+        if (k >= 2 && is_epi) {
             float y[64];
             tmem_ld64(tY + lane_base + (uint32_t)(half * 64), y);
             store_row64(Y_hi, Y_lo, tid, y);
@@ -632,12 +722,15 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_kernel(BwdParams p
         finish_frame(k);
         if (k == 1) finish_frame(0);
         publish();
+        WFPROF(1, 5);
         // ---- next step's tiles and frame ----
         if (k >= 2) {
-            if (tid == 0) load_block(k - 2);
+            if (is_iss && tc::elect_one()) load_block(k - 2);
             convert_frame(k - 2);
+            WFPROF(1, 6);
             tc::mbar_wait(&bar_ld, ld_phase & 1); ++ld_phase;
             publish();
+            WFPROF(1, 7);
         }
     }
     tc::tc_fence_before();
@@ -696,6 +789,7 @@ int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, fl
     if (rc != CRW_OK) return rc;
     wf::FwdParams p;
     p.B = B; p.T = T; p.N = N;
+    p.prof = getenv("CRW_WALK_PROF") ? 1 : 0;
     p.inv_tau = 1.0f / tau;
     p.A = A_or_null;
     p.loss = loss;
@@ -719,12 +813,26 @@ int walk_fused_backward(const float* x, const void* saved, const float* dloss, c
     }
     wf::BwdParams p;
     p.B = B; p.T = T; p.N = N;
+    p.prof = getenv("CRW_WALK_PROF") ? 1 : 0;
     p.inv_tau = 1.0f / tau;
     p.x = x; p.dloss = dloss; p.dA = dA_or_null; p.dx = dx;
     p.ws = wf_align1k(const_cast<void*>(saved));
-    wf::walk_fused_bwd_kernel<<<B, wf::kThreads, wf::kSmemBwd, st>>>(p);
+    wf::walk_fused_bwd_kernel<<<B, wf::kBwdThreads, wf::kSmemBwd, st>>>(p);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
 
+int walk_fused_profile_read(unsigned long long* host_out, int reset) {
+    if (host_out) CRW_CUDA_RET(cudaMemcpyFromSymbol(host_out, wf::g_wf_prof, sizeof(wf::g_wf_prof)));
+    if (reset) {
+        void* ptr = nullptr;
+        CRW_CUDA_RET(cudaGetSymbolAddress(&ptr, wf::g_wf_prof));
+        CRW_CUDA_RET(cudaMemset(ptr, 0, sizeof(wf::g_wf_prof)));
+    }
+    return CRW_OK;
+}
+
 }  // namespace crw
+
+// profiling aid: per-phase cycle counters of the fused walk kernels ([2 kernels][16] uint64) to host memory (synchronising)
+extern "C" int crw_debug_walk_fused_profile(unsigned long long* host_out, int reset) { return crw::walk_fused_profile_read(host_out, reset); }
