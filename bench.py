@@ -538,6 +538,21 @@ def run_b200(args):
     # the same fwd+bwd with precision = BF16X3 (warp-level MMAs on split bf16 pairs at this size); reported beside the fp32 kernels
     wk_tc = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3,
                        kernel_note="walk fwd+bwd kernels (BF16X3: mma.sync on bf16 hi/lo pairs), 8 launches") if only in ("all", "walk") else None
+    # the same again on the fused tcgen05 kernels (walk_fused.cu: one kernel per direction, one CTA per batch element; opt-in), at the
+    # config-2 batch and at a batch that fills the SMs, each beside the default BF16X3 engine
+    wk_fused = None
+    if only in ("all", "walk"):
+        wk_fused = {}
+        for Bf in (TRAIN["B"], 4 * TRAIN["B"]):
+            os.environ["CRW_WALK_FUSED"] = "1"
+            try:
+                rf = bench_walk(crw, args, world, pk, B=Bf, precision=crw.ops.PREC_BF16X3,
+                                kernel_note="walk_fused_fwd_kernel + walk_fused_bwd_kernel (tcgen05 bf16x3, TMA-fed, one CTA per batch element), 2 launches")
+            finally:
+                del os.environ["CRW_WALK_FUSED"]
+            rd = wk_tc if Bf == TRAIN["B"] else bench_walk(crw, args, world, pk, B=Bf, precision=crw.ops.PREC_BF16X3)
+            wk_fused[f"B{Bf}"] = dict(ms=rf["ms"], ms_eager_dispatch=rf["ms_eager"], launches=2, tflops=rf["roofline"]["achieved"],
+                                      frac=rf["roofline"]["frac"], default_engine_ms=rd["ms"], default_engine_ms_eager=rd["ms_eager"])
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
     # the multi-GPU configurations BASELINE names (config 4: T=20 + UNet-as-encoder, data parallel; config 5: 64 radargrams of
     # 50k columns sharded over the ranks, strong scaling) ride in the same line as objects of their own
@@ -576,6 +591,12 @@ def run_b200(args):
                        bf16x3=dict(ms=wk_tc["ms"], tflops=wk_tc["roofline"]["achieved"], frac=wk_tc["roofline"]["frac"],
                                    note="precision=BF16X3 (error-compensated bf16 pairs, fp32 accumulate; gradients within 1e-4 "
                                         "of fp64); the train step above runs the fp32 kernels"))
+            hot["fused_tcgen05"] = dict(
+                what="opt-in (CRW_WALK_FUSED=1, precision=BF16X3): ONE tcgen05 kernel per direction, one CTA per batch element, frames by TMA, "
+                     "softmax / lse-diag / softmax-backward in the MMA epilogues, no N x N matrix through global memory between steps; "
+                     "loss 1e-7 / dx 1e-5 of the fp64 oracle (tests/test_gpu_walk_fused.py).  Latency bound by the per-element chain: it "
+                     "uses B of the 148 SMs, so it wins once the per-GPU batch fills them",
+                **wk_fused)
             line = dict(
                 metric="crw_train_radargrams_per_sec", value=tr["value"], unit="radargrams/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=tr["ms_per_step"], higher_is_better=True,

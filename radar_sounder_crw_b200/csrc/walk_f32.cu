@@ -385,6 +385,18 @@ size_t walk_tiles_scratch_extra_bytes(int B, int T, int N, int C);
 
 using namespace crw;
 
+// BF16X3 at the reference's sizes: the fused tcgen05 kernels (walk_fused.cu) put ONE CTA on each batch element, so their time does
+// not grow with the batch until it exceeds the SM count, while the eight shared-memory kernels spread every stage over B x T CTAs.
+// Measured at T = 10, N = 47 (CUDA-graph replay): B = 32: 0.190 vs 0.114 ms, B = 128: 0.220 vs 0.284 ms.  CRW_WALK_FUSED=1 / 0
+// forces the choice; unset, the fused kernels take batches of 96 and more.  (Forward and backward see the same B, T, N, C and
+// environment, hence the same `saved` layout.)
+static bool walk_use_fused(int B, int T, int N, int C) {
+    if (!walk_fused_supported(N, C, T)) return false;
+    const char* e = getenv("CRW_WALK_FUSED");
+    if (e) return atoi(e) != 0;
+    return B >= 96;
+}
+
 static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" size_t crw_walk_saved_bytes(int B, int T, int N, int C, int precision) {
@@ -417,8 +429,7 @@ extern "C" int crw_walk_forward(const float* x, int B, int T, int N, int C, floa
     // BF16X3: tile-parallel tcgen05 GEMMs (any N).  FP32: shared-memory path for N <= 64, FMA tiles beyond.
     // BF16X3: one-tile sizes run the shared-memory kernels with warp-level MMAs; beyond that the tile-parallel tcgen05 path
     if (precision == CRW_PREC_BF16X3) {
-        if (getenv("CRW_WALK_FUSED") && walk_fused_supported(N, C, T) && aligned16p(x))
-            return walk_fused_forward(x, B, T, N, C, tau, loss, A_or_null, saved, st);
+        if (walk_use_fused(B, T, N, C) && aligned16p(x)) return walk_fused_forward(x, B, T, N, C, tau, loss, A_or_null, saved, st);
         if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
             return walk_small_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st, true);
         return walk_tiles_forward(x, B, T, N, C, tau, loss, A_or_null, ws, st);
@@ -452,8 +463,7 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
     if (precision == CRW_PREC_BF16X3) {
-        if (getenv("CRW_WALK_FUSED") && walk_fused_supported(N, C, T) && aligned16p(x))
-            return walk_fused_backward(x, saved, dloss, dA_or_null, B, T, N, C, tau, dx, st);
+        if (walk_use_fused(B, T, N, C) && aligned16p(x)) return walk_fused_backward(x, saved, dloss, dA_or_null, B, T, N, C, tau, dx, st);
         if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
             return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st, true);
         return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);
