@@ -4,23 +4,26 @@
 // mask of :232-245) and produces BIT-IDENTICAL W / I (hence masks and labels) to the pinned-order fp32 path and to
 // oracle/crw_oracle.c, at tensor-core speed (precision = CRW_PREC_TC_EXACT):
 //
-//   lp_prep_x_kernel    F.normalize in the pinned order -> xn (fp32) and one fp16 plane h = fp16(256 xn); per-call maxima of
-//                       |xn|^2 and |xn - h/256|^2 (they size the filter margin)
+//   lp_mu_x_kernel      the centre mu of each radargram's features from a strided sample of its rows (sub-megabyte read)
+//   lp_prep_x_kernel    ONE pass over the features: F.normalize in the pinned order -> xn (fp32), the query plane fp16(256 xn), the
+//                       key plane fp16(256 (xn - mu)) (q . (k - mu) ranks the keys like q . k, with a rounding error that scales
+//                       with the spread of the features), per-call maxima of the norms and rounding residuals (they size the margin)
 //   lp_filter_kernel    ONE tcgen05 pass (kind::f16, fp16 operands, fp32 accumulate in TMEM) over the dense (query tile x key
 //                       tile) blocks.  The approximate dot a~ differs from the pinned fp32 chain dot by at most E (Cauchy-
 //                       Schwarz on the rounding residuals + accumulation slack), so every candidate whose a~ is within 2E of
 //                       the k-th best a~ survives: the true top-k is a subset of the survivors.  Four 128-row query tiles
 //                       share every 64-row key stage (the L2 -> SM key stream is a quarter of one tile per stage).
 //                         warp 16      TMA producer: ring of 16 KB stages (query half-tiles, then key tiles), SWIZZLE_128B
-//                         warp 17      MMA issuer: query tiles copied smem -> TMEM (tcgen05.cp), TS-form MMAs, 4 accumulators
+//                         warps 17-18  MMA issuers: query tiles copied smem -> TMEM (tcgen05.cp), TS-form MMAs, 4 accumulators
 //                         warps 0-15   epilogue: thread = query row; branch-free "beats the bound and lies in the window/band"
-//                                      test per value, survivors appended to a per-thread smem column as packed 32-bit keys
-//                                      (20-bit fixed-point value | 12-bit stream column); a warp-wide flush merges them into a
-//                                      sorted register list of KL entries whose KT-th entry gives the bound
-//   lp_refine_kernel    per query: the fp32 rows of its survivors are fetched with cp.async.bulk (512 B each, mbarrier ring),
-//                       dot = the oracle's pinned four-chain fmaf order, exact top-k (logit desc, id asc), masked fill, pinned
-//                       softmax, W / I stores.  Queries whose survivor list overflowed (degenerate inputs: many exact ties)
-//                       are rescanned in full by a warp -- slower, same result.
+//                                      test per value, survivors appended to a per-thread smem column; a warp-wide flush merges
+//                                      them into a sorted register list of KL entries whose KT-th entry gives the bound.
+//                                      Queries whose list overflowed go to the launch's overflow list in global memory
+//   lp_refine_kernel    every warp on its own, chunks of up to 32 queries: phase 1 (warp per query) loads the fp32 rows of the
+//                       survivors straight from L2 and forms the dots in the oracle's pinned order; phase 2 (lane per query)
+//                       sorts them (logit desc, id asc), masked fill, pinned softmax, W / I stores.  Overflowed queries are
+//                       rescanned in full, one per CTA at a time: a few dedicated CTAs start on the overflow list at once,
+//                       the others join when their chunks are done -- slower, same result.
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
 
@@ -1002,10 +1005,9 @@ static int launch_refine(const RParams& r_in, int max_ctas, cudaStream_t st) {
     const long long total_q = (long long)r0.R * (r0.row_end - r0.row_begin);
     if (total_q <= 0) return CRW_OK;
     if (total_q >= (1ll << 31) - 65536) return CRW_ERR_UNSUPPORTED;
-    // two (three) CTAs of 8 warps per SM; a warp chunk is a contiguous range of at most 32 queries, sized so that one round of
+    // two CTAs of 8 warps per SM; a warp chunk is a contiguous range of at most 32 queries, sized so that one round of
     // chunks fills every warp slot when the launch is small
-    static const int rb8s = [] { const char* e = getenv("CRW_LP_REFINE_RB8"); return e ? atoi(e) : 0; }();
-    const long long slots = (rb8s ? 3LL : 2LL) * max_ctas;
+    const long long slots = 2LL * max_ctas;
     const long long resc = (slots >= 8 * kRRescCtas) ? kRRescCtas : 1;      // CTAs that only serve the overflow list
     const long long wslots = (slots - resc) * kRWarps;
     long long per = (total_q + wslots - 1) / wslots;
@@ -1018,8 +1020,8 @@ static int launch_refine(const RParams& r_in, int max_ctas, cudaStream_t st) {
     RParams r = r_in;
     r.chunk_q = (int)per;
     r.resc_ctas = (int)resc;
-    if (rb8s) lp_refine_kernel<KL, 8, 3><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
-    else lp_refine_kernel<KL, 16, 2><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
+    // (RB = 8 with three CTAs per SM was measured: 80 vs 76 us, the 80-register budget spills)
+    lp_refine_kernel<KL, 16, 2><<<(unsigned)ctas, kRThreads, 0, st>>>(r);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
