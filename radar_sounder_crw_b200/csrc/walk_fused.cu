@@ -43,7 +43,7 @@ constexpr size_t kSaveX = 2 * kPlane128, kSaveSS = 4 * kTile64, kSaveG = 2 * kTi
 constexpr size_t kSaveStep = kSaveX + kSaveSS + kSaveG;                   // 80 KB
 constexpr size_t kSaveFrame = 4 * kTile64;                                // the normalised frame as bf16 hi / lo operand rows: 32 KB
 struct Layout {
-    size_t invn, frames, tiles, part, ctr, total, per_b;
+    size_t invn, frames, tiles, part, ctr, flags, total, per_b;
     int T;
     __host__ __device__ Layout(int B, int T_) : T(T_) {
         const int K = T_ > 2 ? T_ - 2 : 0;
@@ -53,8 +53,11 @@ struct Layout {
         per_b = tiles + (size_t)(K + 1) * kSaveStep;
         part = (size_t)B * per_b;
         ctr = part + align_up((size_t)B * sizeof(float), 256);
-        total = ctr + 256;
+        flags = ctr + 256;
+        total = flags + align_up((size_t)B * 4 * T_ * sizeof(int), 256);
     }
+    // hand-over flags of the role-split kernels, per batch element [ss_ready | x_ready | y_ready | t_ready][T] (ctr + 4: error flag)
+    __host__ __device__ size_t flag(int b, int which, int i) const { return flags + ((size_t)(b * 4 + which) * T + i) * sizeof(int); }
     __host__ __device__ size_t step(int b, int j) const { return (size_t)b * per_b + tiles + (size_t)j * kSaveStep; }
     __host__ __device__ size_t frame(int b, int f) const { return (size_t)b * per_b + frames + (size_t)f * kSaveFrame; }   // [hi, lo][k-block][64 rows][128 B]
 };
@@ -133,6 +136,29 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes),
                  "r"(tc::smem_u32(bar))
                  : "memory");
+}
+
+// ---- hand-over between the CTAs of the role-split kernels: operand tiles travel through global memory (L2) by bulk copies, a
+// flag per tile says it is complete.  Writer (one lane): bulk stores -> wait for their completion -> fence -> release store.
+// Reader (one lane): acquire load (spin) -> fence -> bulk load.  A reader only ever waits for CTAs with a SMALLER block index
+// (dispatched earlier), and a writer never waits for a reader.  The spin is bounded: a lost flag ends in an error code, not a hang.
+__device__ __forceinline__ void flag_set(int* f) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+}
+__device__ __forceinline__ bool flag_wait(const int* f, int* err) {
+    int v = 0;
+    for (long long it = 0; it < (1ll << 24); ++it) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v != 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            return true;
+        }
+        __nanosleep(64);
+    }
+    atomicExch(err, 1);
+    return false;
 }
 
 // D[128 lanes x NN columns at tmem_d] (+)= A (128 rows x 64 nkb) . B (NN rows x 64 nkb)^T on bf16 hi / lo pairs: hi.hi + hi.lo + lo.hi.
@@ -455,6 +481,313 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, role-split: FOUR CTAs per batch element (grid = 4 B, role = blockIdx.x / B), for batches that leave SMs idle.
+//   roles 0, 1  producers: affinities t = role, role + 2, ...: frames by TMA -> normalise -> one N = 128 product -> both softmaxes ->
+//               rows of S_t / S'_t as operand tiles -> global (block t of the saved workspace, where the reverse pass wants them
+//               anyway) + flag; also A_t, invn and the frames' operand rows for the reverse pass
+//   role 2      chain: X_1 = [S'_0 ; I], X_k = X_{k-1} [S'_{k-1} | S_{k-1}^T]: waits for S tiles, saves X_k + flag
+//   role 3      cycle: M_k = L_k R_k from the saved X_k: lse - diag, G_k, the loss
+// The only serial part left on one SM is the chain (one product + one 32-column epilogue per step).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t rE = 0;                               // producer: E planes (64 KB) | chain: S tiles, two buffers | cycle: X, two buffers
+constexpr uint32_t rRaw = rE + 4 * kPlane128;            // producer: raw frames, two buffers (64 KB) | chain: X (32 KB) | cycle: G (16 KB)
+constexpr uint32_t rSS = rRaw + 8 * kTile64;             // producer: S tiles out (32 KB)
+constexpr uint32_t rAst = rSS + 4 * kTile64;             // producer: fp32 A_t staging (16 KB)
+constexpr uint32_t rEnd = rAst + 64 * 64 * 4;
+constexpr uint32_t kSmemRoles = rEnd + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sb - tc::smem_u32(smem_raw));            // generic pointer to the aligned base
+    __shared__ uint64_t bar_ld[2], bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_red[4][64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int role = blockIdx.x / p.B, b = blockIdx.x % p.B, N = p.N, T = p.T, K = T - 2;
+    const Layout lay(p.B, T);
+    int* err = reinterpret_cast<int*>(p.ws + lay.ctr + 4);
+    auto flagp = [&](int which, int i) { return reinterpret_cast<int*>(p.ws + lay.flag(b, which, i)); };
+
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_ld[0], 1);
+        tc::mbar_init(&bar_ld[1], 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&xmap);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const bool is_epi = warp < 8, is_iss = warp == 8;
+    const uint32_t tmem = tmem_base_s;
+    const int row = ((warp & 3) << 5) | lane;
+    const int half = row >> 6, r = row & 63, ch = (warp >> 2) & 1;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ld_phase[2] = {0u, 0u}, mma_phase = 0;
+    auto publish = [&]() {
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+    };
+    auto mma_wait = [&]() {
+        tc::mbar_wait(&bar_mma, mma_phase & 1);
+        ++mma_phase;
+        tc::tc_fence_after();
+    };
+    auto ld_wait = [&](int i) {
+        tc::mbar_wait(&bar_ld[i], ld_phase[i] & 1);
+        ++ld_phase[i];
+    };
+
+    if (role < 2) {
+        // ================= producer =================
+        const int Tlast = p.A ? T - 1 : K;                               // affinities 0 .. Tlast - 1 are wanted
+        const uint32_t sE = sb + rE, sSS = sb + rSS, sAst = sb + rAst;
+        auto ePlane = [&](int pl, int kb) { return sE + (uint32_t)(pl * 2 + kb) * kPlane128; };
+        auto issue_frame = [&](int f, int buf) {     // issuer lane
+            tc::mbar_arrive_expect_tx(&bar_ld[buf], (uint32_t)N * 512u);
+            const int row0 = (b * T + f) * N;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) tc::tma_load_2d(sgen + rRaw + (buf * 4 + cb) * kTile64, &xmap, cb * 32, row0, &bar_ld[buf]);
+        };
+        auto convert_frame = [&](int f, int buf) {   // raw buffer `buf` -> ring slot f & 1; one CTA barrier inside
+            const int cq = (tid >> 6) & 3, rr = tid & 63;
+            float v[32];
+            float ss = 0.0f;
+            if (is_epi && rr < N) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 q = lds128f(sb + rRaw + (uint32_t)(buf * 4 + cq) * kTile64 + swz(rr, c));
+                    v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+                    ss = fmaf(q.x, q.x, ss); ss = fmaf(q.y, q.y, ss); ss = fmaf(q.z, q.z, ss); ss = fmaf(q.w, q.w, ss);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (is_epi) s_red[cq][rr] = ss;
+            __syncthreads();
+            if (is_epi) {
+                const float inv = 1.0f / fmaxf(sqrtf((s_red[0][rr] + s_red[1][rr]) + (s_red[2][rr] + s_red[3][rr])), kNormEps);
+                if (cq == 0) reinterpret_cast<float*>(p.ws + (size_t)b * lay.per_b + lay.invn)[f * 64 + rr] = (rr < N) ? inv : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= inv;
+                store_row32(ePlane(0, cq >> 1), ePlane(1, cq >> 1), (f & 1) * 64 + rr, cq & 1, v);
+            }
+        };
+        auto save_frame = [&](int f) {               // issuer lane
+            uint8_t* dst = p.ws + lay.frame(b, f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bulk_store(dst + q * kTile64, sE + (uint32_t)q * kPlane128 + (uint32_t)(f & 1) * kTile64, kTile64);
+        };
+        if (role < Tlast && is_iss && tc::elect_one()) { issue_frame(role, 0); issue_frame(role + 1, 1); }
+        for (int t = role; t < Tlast; t += 2) {
+            ld_wait(0);
+            convert_frame(t, 0);
+            ld_wait(1);
+            convert_frame(t + 1, 1);
+            if (is_iss && tc::elect_one()) bulk_wait_read();             // (the S tiles of the last affinity have left shared memory)
+            publish();
+            if (is_iss && tc::elect_one()) {
+                tc::tc_fence_after();
+                if (t + 2 < Tlast) { issue_frame(t + 2, 0); issue_frame(t + 3, 1); }
+                save_frame(t);
+                save_frame(t + 1);
+                bulk_commit();
+                mma3<false, false, 128>(tmem, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
+                tc::umma_commit(&bar_mma);
+            }
+            mma_wait();
+            const bool isA = (half == 0) == ((t & 1) == 0);
+            float a[32];
+            float mx = -INFINITY;
+            if (is_epi) {
+                tmem_ld32(tmem + lane_base + (uint32_t)((1 - half) * 64 + ch * 32), a);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    a[c] *= p.inv_tau;
+                    if (32 * ch + c < N) mx = fmaxf(mx, a[c]);
+                }
+                if (p.A && isA && r < N) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (32 * ch + c < N) tc::sts_f32(sAst + (uint32_t)(r * N + 32 * ch + c) * 4u, a[c]);
+                }
+                s_red[half * 2 + ch][r] = mx;
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            float s = 0.0f;
+            if (is_epi) {
+                mx = fmaxf(mx, s_red[half * 2 + (1 - ch)][r]);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    a[c] = (32 * ch + c < N && r < N) ? exp2f((a[c] - mx) * 1.4426950408889634f) : 0.0f;
+                    s += a[c];
+                }
+            }
+            __syncthreads();
+            if (is_epi) s_red[half * 2 + ch][r] = s;
+            __syncthreads();
+            if (is_epi && t < K) {
+                s += s_red[half * 2 + (1 - ch)][r];
+                const float is = (r < N) ? 1.0f / s : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) a[c] *= is;
+                store_row32(sSS + (isA ? 0u : 2u * kTile64), sSS + (isA ? 1u : 3u) * kTile64, r, ch, a);
+            }
+            publish();
+            if (t < K && is_iss && tc::elect_one()) {
+                bulk_store(p.ws + lay.step(b, t) + kSaveX, sSS, (uint32_t)kSaveSS);
+                bulk_commit();
+                bulk_wait_all();
+                flag_set(flagp(0, t));
+            }
+            if (p.A) {
+                float* dst = p.A + ((size_t)b * (T - 1) + t) * N * N;
+                for (int i = tid; i < N * N; i += kThreads) dst[i] = tc::lds_f32(sAst + (uint32_t)i * 4u);
+            }
+        }
+        if (is_iss && tc::elect_one()) bulk_wait_all();
+    } else if (role == 2) {
+        // ================= chain =================
+        const uint32_t sSSb = sb + rE, sX = sb + rRaw;                   // S tiles: two 32 KB buffers; X: hi, lo
+        const uint32_t tX = tmem;
+        auto load_ss = [&](int t, int buf) {         // issuer lane
+            flag_wait(flagp(0, t), err);
+            tc::mbar_arrive_expect_tx(&bar_ld[buf], (uint32_t)kSaveSS);
+            bulk_load(sSSb + (uint32_t)buf * (uint32_t)kSaveSS, p.ws + lay.step(b, t) + kSaveX, (uint32_t)kSaveSS, &bar_ld[buf]);
+        };
+        if (is_iss && tc::elect_one()) load_ss(0, 0);
+        for (int k = 1; k <= K; ++k) {
+            const int buf = (k - 1) & 1;
+            const uint32_t sSS = sSSb + (uint32_t)buf * (uint32_t)kSaveSS;
+            ld_wait(buf);
+            if (k == 1) {
+                // X_1 = [L_1 ; R_1^T] = [S'_0 ; I]: the rows of S'_0 are already operand rows (same swizzle): copy them
+                if (is_epi) {
+                    for (int i = tid; i < 2 * 512; i += 256) {           // 2 planes x 512 chunks of 16 bytes
+                        const int pl = i >> 9, cidx = i & 511;
+                        const uint4 q = lds128u(sSS + (uint32_t)(2 + pl) * kTile64 + (uint32_t)cidx * 16u);
+                        sts128(sX + (uint32_t)pl * kPlane128 + (uint32_t)cidx * 16u, q.x, q.y, q.z, q.w);
+                    }
+                    if (half == 1) {
+                        float e[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) e[c] = (32 * ch + c == r && r < N) ? 1.0f : 0.0f;
+                        store_row32(sX, sX + kPlane128, 64 + r, ch, e);
+                    }
+                }
+                publish();
+            } else {
+                if (is_iss && tc::elect_one()) {
+                    tc::tc_fence_after();
+                    mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);   // X . S'_{k-1}
+                    mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);               // X . S_{k-1}^T
+                    bulk_wait_read();                                    // the copy of X_{k-1} has left shared memory before anybody is told the product is done
+                    tc::umma_commit(&bar_mma);
+                    // under the MMAs: X_{k-1} has been copied out completely -> hand it to the cycle CTA; fetch the next S tiles
+                    bulk_wait_all();
+                    flag_set(flagp(1, k - 1));
+                    if (k < K) load_ss(k, k & 1);
+                }
+                mma_wait();
+                if (is_epi) {
+                    float x[32];
+                    tmem_ld32(tX + lane_base + (uint32_t)(half * 64 + ch * 32), x);
+                    store_row32(sX, sX + kPlane128, row, ch, x);
+                }
+                publish();
+            }
+            if (is_iss && tc::elect_one()) {
+                bulk_store(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX);
+                bulk_commit();
+                if (k == 1 && K > 1) load_ss(1, 1);
+            }
+        }
+        if (is_iss && tc::elect_one()) {
+            bulk_wait_all();
+            flag_set(flagp(1, K));
+        }
+    } else {
+        // ================= cycle =================
+        const uint32_t sXb = sb + rE, sG = sb + rRaw;                    // X: two 32 KB buffers; G: hi, lo
+        const uint32_t tM = tmem;
+        auto load_x = [&](int k, int buf) {          // issuer lane
+            flag_wait(flagp(1, k), err);
+            tc::mbar_arrive_expect_tx(&bar_ld[buf], (uint32_t)kSaveX);
+            bulk_load(sXb + (uint32_t)buf * (uint32_t)kSaveX, p.ws + lay.step(b, k), (uint32_t)kSaveX, &bar_ld[buf]);
+        };
+        float loss_acc = 0.0f;
+        if (is_iss && tc::elect_one()) load_x(1, 1);
+        for (int k = 1; k <= K; ++k) {
+            const int buf = k & 1;
+            const uint32_t sX = sXb + (uint32_t)buf * (uint32_t)kSaveX;
+            ld_wait(buf);
+            if (is_iss && tc::elect_one()) {
+                tc::tc_fence_after();
+                mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);    // M_k = L_k R_k
+                bulk_wait_read();                                        // G_{k-1} has left shared memory before the epilogue is let go
+                tc::umma_commit(&bar_mma);
+                if (k < K) load_x(k + 1, (k + 1) & 1);                   // (its buffer was read by the product before last: complete)
+            }
+            mma_wait();
+            float m[32];
+            float sm = 0.0f, diag = 0.0f;
+            if (is_epi && half == 0) {
+                tmem_ld32(tM + lane_base + (uint32_t)(ch * 32), m);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (32 * ch + c == r) diag = m[c];
+                    m[c] = (32 * ch + c < N && r < N) ? exp2f((m[c] - 1.0f) * 1.4426950408889634f) : 0.0f;
+                    sm += m[c];
+                }
+                s_red[ch][r] = sm;
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            if (is_epi && half == 0) {
+                sm += s_red[1 - ch][r];
+                if (r < N && (r >> 5) == ch) loss_acc += logf(sm) + 1.0f - diag;
+                const float is = (r < N) ? 1.0f / sm : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) m[c] = m[c] * is - ((32 * ch + c == r && r < N) ? 1.0f : 0.0f);
+                store_row32(sG, sG + kTile64, r, ch, m);
+            }
+            publish();
+            if (is_iss && tc::elect_one()) {
+                bulk_store(p.ws + lay.step(b, k) + kSaveX + kSaveSS, sG, (uint32_t)kSaveG);
+                bulk_commit();
+            }
+        }
+        __syncthreads();
+        if (is_epi && half == 0) s_red[ch][r] = loss_acc;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.0f;
+            for (int i = 0; i < 64; ++i) tot += s_red[0][i] + s_red[1][i];
+            float* part = reinterpret_cast<float*>(p.ws + lay.part);
+            part[b] = tot;
+            __threadfence();
+            const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(p.ws + lay.ctr), 1u);
+            if (done == (unsigned)p.B - 1u) {
+                __threadfence();
+                float sum = 0.0f;
+                for (int i = 0; i < p.B; ++i) sum += reinterpret_cast<volatile float*>(part)[i];
+                if (*reinterpret_cast<volatile int*>(err)) sum = __int_as_float(0x7fc00000);      // a hand-over flag never arrived: NaN, not a wrong number
+                *p.loss = sum / ((float)p.B * (float)N * (float)N);
+            }
+        }
+        if (is_iss && tc::elect_one()) bulk_wait_all();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
 // backward, one CTA per batch element, steps k = T-2 .. 1 (t = k - 1)
 //   state   Y_k = [dL_k ; dR_k^T], carried WITHOUT the factor dloss / (B N N) (everything up to the softmax backward is linear in it)
 //   (a)     [dS'_{k-1} | .] = L_{k-1}^T dL_k      (lanes 0-63),      [. | dS_{k-1}] = dR_k R_{k-1}^T   (lanes 64-127)
@@ -773,11 +1106,19 @@ static int make_tmap_f32_c32(CUtensorMap* out, const void* base, uint64_t rows, 
 bool walk_fused_supported(int N, int C, int T) { return N >= 8 && N <= 64 && C == 128 && T >= 3; }
 size_t walk_fused_saved_bytes(int B, int T) { return wf::Layout(B, T).total + 1024; }
 
+// Role-split kernels (several CTAs per batch element, hand-over through L2) while every CTA of the launch can be resident at once
+// (no CTA then waits for one that is not running); one CTA per element beyond.  CRW_WALK_ROLES=0 / 1 forces.
+static bool walk_fused_roles(int B, int sms) {
+    const char* e = getenv("CRW_WALK_ROLES");
+    if (e) return atoi(e) != 0;
+    return 4 * B <= sms;
+}
+
 static uint8_t* wf_align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023)); }
 
 int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, void* saved, cudaStream_t st) {
     if (!walk_fused_supported(N, C, T)) return CRW_ERR_UNSUPPORTED;
-    static bool attr_done[64] = {};
+    static bool attr_done[64] = {}, attr_done_roles[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
@@ -795,8 +1136,18 @@ int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, fl
     p.loss = loss;
     p.ws = wf_align1k(saved);
     const wf::Layout lay(B, T);
-    CRW_CUDA_RET(cudaMemsetAsync(p.ws + lay.ctr, 0, 4, st));
-    wf::walk_fused_fwd_kernel<<<B, wf::kThreads, wf::kSmemFwd, st>>>(xmap, p);
+    CRW_CUDA_RET(cudaMemsetAsync(p.ws + lay.ctr, 0, lay.total - lay.ctr, st));          // loss counter, error flag, hand-over flags
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (walk_fused_roles(B, sms)) {
+        if (dev >= 0 && dev < 64 && !attr_done_roles[dev]) {
+            CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_fwd_roles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemRoles));
+            attr_done_roles[dev] = true;
+        }
+        wf::walk_fused_fwd_roles_kernel<<<4 * B, wf::kThreads, wf::kSmemRoles, st>>>(xmap, p);
+    } else {
+        wf::walk_fused_fwd_kernel<<<B, wf::kThreads, wf::kSmemFwd, st>>>(xmap, p);
+    }
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
