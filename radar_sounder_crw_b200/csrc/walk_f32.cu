@@ -370,7 +370,8 @@ int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, fl
 bool walk_fused_supported(int N, int C, int T);
 size_t walk_fused_saved_bytes(int B, int T);
 int walk_fused_backward(const float* x, const void* saved, const float* dloss, const float* dA_or_null, int B, int T, int N, int C, float tau,
-                        float* dx, cudaStream_t st);
+                        float* dx, void* scratch, cudaStream_t st);
+size_t walk_fused_bwd_scratch_bytes(int B, int T);
 int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, void* saved, cudaStream_t st);
 int walk_small_backward(const float* x, const float* ws, const float* dloss, const float* dA_or_null, int B, int T, int N, int C,
                         float tau, float* dx, float* sc, cudaStream_t st, bool mma);
@@ -411,6 +412,7 @@ extern "C" size_t crw_walk_backward_scratch_bytes(int B, int T, int N, int C, in
     if (B < 1 || T < 2 || N < 1) return 0;
     size_t b = BwdLayout(B, T, N).total * sizeof(float) + 256;
     if (precision == CRW_PREC_BF16X3) b += walk_tiles_scratch_extra_bytes(B, T, N, C) + 256;
+    if (precision == CRW_PREC_BF16X3 && walk_fused_supported(N, C, T)) { const size_t f = walk_fused_bwd_scratch_bytes(B, T); if (f > b) b = f; }
     return b;
 }
 
@@ -463,7 +465,7 @@ extern "C" int crw_walk_backward(const float* x, const void* saved, size_t saved
     float* sc = align256(scratch);
     const float inv_tau = 1.0f / tau;
     if (precision == CRW_PREC_BF16X3) {
-        if (walk_use_fused(B, T, N, C) && aligned16p(x)) return walk_fused_backward(x, saved, dloss, dA_or_null, B, T, N, C, tau, dx, st);
+        if (walk_use_fused(B, T, N, C) && aligned16p(x)) return walk_fused_backward(x, saved, dloss, dA_or_null, B, T, N, C, tau, dx, scratch, st);
         if (walk_small_mma_supported(N, C) && aligned16p(x) && !getenv("CRW_WALK_FORCE_TILES"))
             return walk_small_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st, true);
         return walk_tiles_backward(x, ws, dloss, dA_or_null, B, T, N, C, tau, dx, sc, st);

@@ -64,6 +64,7 @@ struct Layout {
 
 struct FwdParams {
     int B, T, N, prof;
+    int P;                    // role-split kernel: affinity producers per batch element
     float inv_tau;
     float* A;                 // [B, T-1, N, N] or null
     float* loss;              // scalar
@@ -481,12 +482,12 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------
-// forward, role-split: FOUR CTAs per batch element (grid = 4 B, role = blockIdx.x / B), for batches that leave SMs idle.
-//   roles 0, 1  producers: affinities t = role, role + 2, ...: frames by TMA -> normalise -> one N = 128 product -> both softmaxes ->
+// forward, role-split: P + 2 CTAs per batch element (grid = (P + 2) B, role = blockIdx.x / B), for batches that leave SMs idle.
+//   roles < P   producers: affinities t = role, role + P, ...: frames by TMA -> normalise -> one N = 128 product -> both softmaxes ->
 //               rows of S_t / S'_t as operand tiles -> global (block t of the saved workspace, where the reverse pass wants them
 //               anyway) + flag; also A_t, invn and the frames' operand rows for the reverse pass
-//   role 2      chain: X_1 = [S'_0 ; I], X_k = X_{k-1} [S'_{k-1} | S_{k-1}^T]: waits for S tiles, saves X_k + flag
-//   role 3      cycle: M_k = L_k R_k from the saved X_k: lse - diag, G_k, the loss
+//   role P      chain: X_1 = [S'_0 ; I], X_k = X_{k-1} [S'_{k-1} | S_{k-1}^T]: waits for S tiles, saves X_k + flag
+//   role P + 1  cycle: M_k = L_k R_k from the saved X_k: lse - diag, G_k, the loss
 // The only serial part left on one SM is the chain (one product + one 32-column epilogue per step).
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t rE = 0;                               // producer: E planes (64 KB) | chain: S tiles, two buffers | cycle: X, two buffers
@@ -531,17 +532,29 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
         tc::tc_fence_before();
         __syncthreads();
     };
-    auto mma_wait = [&]() {
+    auto mma_wait_raw = [&]() {
         tc::mbar_wait(&bar_mma, mma_phase & 1);
         ++mma_phase;
         tc::tc_fence_after();
     };
+    // profiling aid (CRW_WALK_PROF=1): per role of element 0, cycles [total, waiting for loads (hand-over + TMA), waiting for MMAs]
+    const bool rprof = p.prof && b == 0 && tid == 0;
+    const long long c_begin = clock64();
+    long long c_ld = 0, c_mma = 0;
     auto ld_wait = [&](int i) {
+        const long long c0 = rprof ? clock64() : 0;
         tc::mbar_wait(&bar_ld[i], ld_phase[i] & 1);
         ++ld_phase[i];
+        if (rprof) c_ld += clock64() - c0;
+    };
+    auto mma_wait = [&]() {
+        const long long c0 = rprof ? clock64() : 0;
+        mma_wait_raw();
+        if (rprof) c_mma += clock64() - c0;
     };
 
-    if (role < 2) {
+    const int P = p.P;
+    if (role < P) {
         // ================= producer =================
         const int Tlast = p.A ? T - 1 : K;                               // affinities 0 .. Tlast - 1 are wanted
         const uint32_t sE = sb + rE, sSS = sb + rSS, sAst = sb + rAst;
@@ -583,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             for (int q = 0; q < 4; ++q) bulk_store(dst + q * kTile64, sE + (uint32_t)q * kPlane128 + (uint32_t)(f & 1) * kTile64, kTile64);
         };
         if (role < Tlast && is_iss && tc::elect_one()) { issue_frame(role, 0); issue_frame(role + 1, 1); }
-        for (int t = role; t < Tlast; t += 2) {
+        for (int t = role; t < Tlast; t += P) {
             ld_wait(0);
             convert_frame(t, 0);
             ld_wait(1);
@@ -592,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             publish();
             if (is_iss && tc::elect_one()) {
                 tc::tc_fence_after();
-                if (t + 2 < Tlast) { issue_frame(t + 2, 0); issue_frame(t + 3, 1); }
+                if (t + P < Tlast) { issue_frame(t + P, 0); issue_frame(t + P + 1, 1); }
                 save_frame(t);
                 save_frame(t + 1);
                 bulk_commit();
@@ -651,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             }
         }
         if (is_iss && tc::elect_one()) bulk_wait_all();
-    } else if (role == 2) {
+    } else if (role == P) {
         // ================= chain =================
         const uint32_t sSSb = sb + rE, sX = sb + rRaw;                   // S tiles: two 32 KB buffers; X: hi, lo
         const uint32_t tX = tmem;
@@ -781,6 +794,12 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             }
         }
         if (is_iss && tc::elect_one()) bulk_wait_all();
+    }
+    if (rprof && (role < 2 || role >= P)) {
+        const int pr = role < P ? (role < 2 ? role : 1) : (role == P ? 2 : 3);
+        g_wf_prof[pr * 4 + 0] += (unsigned long long)(clock64() - c_begin);
+        g_wf_prof[pr * 4 + 1] += (unsigned long long)c_ld;
+        g_wf_prof[pr * 4 + 2] += (unsigned long long)c_mma;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1071,6 +1090,320 @@ __global__ void __launch_bounds__(kBwdThreads, 1) walk_fused_bwd_kernel(BwdParam
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------
+// backward, role-split: 2 + PE CTAs per batch element (grid = (2 + PE) B, role = blockIdx.x / B), hand-over through L2 as in the
+// forward.  Same algebra as walk_fused_bwd_kernel:
+//   role 0        chain: Y_K = own_K, Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]; saves every Y_k + flag (one product pair and one
+//                 32-column epilogue per step: the only serial part)
+//   role 1        dA: per step (a) [dS' | dS] from Y_k and X_{k-1}, (b) softmax backward -> the tile [T1 ; T2] (rows of dA_{k-1} and of
+//                 its transpose, scaled by dloss / (B N N tau), plus the gradient arriving through the returned A) + flag
+//   roles 2 ..    dE: per FRAME j: dE_j = T1_{j+1} E_{j+1} + T2_{j+1}^T E_{j+1} + T2_j E_{j-1} + T1_j^T E_{j-1} (four N = 128 products on the
+//                 frames' operand rows the forward saved), F.normalize backward, dx_j.  Frames are dealt round-robin, last frame first.
+// ------------------------------------------------------------------------------------------
+struct BScratch {            // backward scratch (bytes): per batch element Y_k (k = 1 .. K) and T_k (k = 1 .. K + 1) tiles, then the flags
+    size_t per_b, flags, total;
+    int T, K;
+    __host__ __device__ BScratch(int B, int T_) : T(T_), K(T_ - 2) {
+        per_b = (size_t)(2 * K + 1) * kSaveX;
+        flags = (size_t)B * per_b;
+        total = flags + align_up((size_t)(B * 2 * T_ + 1) * sizeof(int), 256);
+    }
+    __host__ __device__ size_t Y(int b, int k) const { return (size_t)b * per_b + (size_t)(k - 1) * kSaveX; }
+    __host__ __device__ size_t Tt(int b, int k) const { return (size_t)b * per_b + (size_t)(K + k - 1) * kSaveX; }
+    __host__ __device__ size_t flag(int b, int which, int i) const { return flags + ((size_t)(b * 2 + which) * T + i + 1) * sizeof(int); }   // [0] = error flag
+};
+
+struct BwdRolesParams {
+    BwdParams q;
+    uint8_t* scratch;         // BScratch (1024-aligned)
+    int PE;                   // dE CTAs per batch element
+};
+
+constexpr uint32_t kSmemBwdRoles = 7 * 2 * kPlane128 + 1024;             // 224 KB (the dA role's map) + alignment slack
+
+__global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRolesParams pp) {
+    const BwdParams& p = pp.q;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ uint64_t bar_ld[2], bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_red[4][64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int role = blockIdx.x / p.B, b = blockIdx.x % p.B, N = p.N, T = p.T, K = T - 2;
+    const Layout lay(p.B, T);
+    const BScratch sc(p.B, T);
+    int* err = reinterpret_cast<int*>(pp.scratch + sc.flags);
+    auto flagp = [&](int which, int i) { return reinterpret_cast<int*>(pp.scratch + sc.flag(b, which, i)); };
+    const float* invn = reinterpret_cast<const float*>(p.ws + (size_t)b * lay.per_b + lay.invn);
+
+    if (warp == 0) tc::tmem_alloc<128>(&tmem_base_s);
+    if (tid == 0) {
+        tc::mbar_init(&bar_ld[0], 1);
+        tc::mbar_init(&bar_ld[1], 1);
+        tc::mbar_init(&bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const bool is_epi = warp < 8, is_iss = warp == 8;
+    const uint32_t tmem = tmem_base_s;
+    const int row = ((warp & 3) << 5) | lane;
+    const int half = row >> 6, r = row & 63, ch = (warp >> 2) & 1;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ld_phase[2] = {0u, 0u}, mma_phase = 0;
+    auto publish = [&]() {
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncthreads();
+    };
+    auto mma_wait = [&]() {
+        tc::mbar_wait(&bar_mma, mma_phase & 1);
+        ++mma_phase;
+        tc::tc_fence_after();
+    };
+    auto ld_wait = [&](int i) {
+        tc::mbar_wait(&bar_ld[i], ld_phase[i] & 1);
+        ++ld_phase[i];
+    };
+    const int k_first = p.dA ? K + 1 : K;
+
+    if (role == 0) {
+        // ================= chain =================
+        const uint32_t sY = sb + 2 * (uint32_t)kSaveStep;                // blocks: two 80 KB buffers at 0; Y: hi, lo
+        const uint32_t Y_hi = sY, Y_lo = sY + kPlane128;
+        auto blk = [&](int j) { return sb + (uint32_t)(j & 1) * (uint32_t)kSaveStep; };
+        auto load_block = [&](int j) {               // issuer lane: [X_j | S_j, S'_j | G_j] of the forward's workspace
+            tc::mbar_arrive_expect_tx(&bar_ld[j & 1], (uint32_t)kSaveStep);
+            bulk_load(blk(j), p.ws + lay.step(b, j), (uint32_t)kSaveStep, &bar_ld[j & 1]);
+        };
+        if (is_iss && tc::elect_one()) { load_block(K); if (K >= 2) load_block(K - 1); }
+        ld_wait(K & 1);
+        if (is_iss && tc::elect_one()) {             // Y_K = [G_K R_K^T ; G_K^T L_K]
+            const uint32_t X_hi = blk(K), X_lo = X_hi + kPlane128, G_hi = X_hi + (uint32_t)(kSaveX + kSaveSS), G_lo = G_hi + kTile64;
+            tc::tc_fence_after();
+            mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
+            mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
+            tc::umma_commit(&bar_mma);
+        }
+        mma_wait();
+        if (is_epi) {
+            float y[32];
+            tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
+            store_row32(Y_hi, Y_lo, row, ch, y);
+        }
+        publish();
+        if (is_iss && tc::elect_one()) {
+            bulk_store(pp.scratch + sc.Y(b, K), sY, (uint32_t)kSaveX);
+            bulk_commit();
+        }
+        for (int k = K; k >= 2; --k) {
+            ld_wait((k - 1) & 1);
+            if (is_iss && tc::elect_one()) {         // Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]
+                const uint32_t X_hi = blk(k - 1), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX, G_hi = S_hi + (uint32_t)kSaveSS, G_lo = G_hi + kTile64;
+                tc::tc_fence_after();
+                mma3<false, false>(tmem, Y_hi, Y_lo, S_hi + 2 * kTile64, S_hi + 3 * kTile64, 1, 0, 0, 0, true);             // dL_k S'_{k-1}^T
+                mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, false);                    // G_{k-1} R_{k-1}^T
+                mma3<false, true>(tmem + 64u, Y_hi, Y_lo, S_hi, S_hi + kTile64, 1, 0, 0, 0, true);                          // dR_k^T S_{k-1}
+                mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, false);         // G_{k-1}^T L_{k-1}
+                bulk_wait_read();                    // the copy of Y_k has left shared memory before the epilogue is let go
+                tc::umma_commit(&bar_mma);
+                bulk_wait_all();
+                flag_set(flagp(0, k));
+                if (k >= 3) load_block(k - 2);       // (its buffer was read by the products of the step before: complete)
+            }
+            mma_wait();
+            if (is_epi) {
+                float y[32];
+                tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
+                store_row32(Y_hi, Y_lo, row, ch, y);
+            }
+            publish();
+            if (is_iss && tc::elect_one()) {
+                bulk_store(pp.scratch + sc.Y(b, k - 1), sY, (uint32_t)kSaveX);
+                bulk_commit();
+            }
+        }
+        if (is_iss && tc::elect_one()) {
+            bulk_wait_all();
+            flag_set(flagp(0, 1));
+        }
+    } else if (role == 1) {
+        // ================= dA =================
+        const uint32_t sYb = sb, sXS = sb + 2 * (uint32_t)kSaveX, sT = sXS + 2 * (uint32_t)(kSaveX + kSaveSS);   // Y x 2 | (X, S) x 2 | T
+        const uint32_t T_hi = sT, T_lo = sT + kPlane128;
+        const float scale = __ldg(p.dloss) / ((float)p.B * (float)N * (float)N);
+        const float coef = scale * p.inv_tau;
+        auto load_y = [&](int k) {                   // issuer lane; Y_k -> buffer k & 1 (barrier 0)
+            flag_wait(flagp(0, k), err);
+            tc::mbar_arrive_expect_tx(&bar_ld[0], (uint32_t)kSaveX);
+            bulk_load(sYb + (uint32_t)(k & 1) * (uint32_t)kSaveX, pp.scratch + sc.Y(b, k), (uint32_t)kSaveX, &bar_ld[0]);
+        };
+        auto load_xs = [&](int j) {                  // issuer lane; [X_j | S_j, S'_j] -> buffer j & 1 (barrier 1)
+            tc::mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(kSaveX + kSaveSS));
+            bulk_load(sXS + (uint32_t)(j & 1) * (uint32_t)(kSaveX + kSaveSS), p.ws + lay.step(b, j), (uint32_t)(kSaveX + kSaveSS), &bar_ld[1]);
+        };
+        if (is_iss && tc::elect_one()) { load_xs(K - 1); load_y(K); }
+        if (p.dA) {
+            // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
+            if (is_epi) {
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = 0.0f;
+                if (half == 1 && r < N) {
+                    const float* src = p.dA + (((size_t)b * (T - 1) + (T - 2)) * N + r) * N;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (32 * ch + c < N) v[c] = p.inv_tau * __ldg(src + 32 * ch + c);
+                }
+                store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, v);
+            }
+            publish();
+            if (is_iss && tc::elect_one()) {
+                bulk_store(pp.scratch + sc.Tt(b, K + 1), sT, (uint32_t)kSaveX);
+                bulk_commit();
+                bulk_wait_all();
+                flag_set(flagp(1, K + 1));
+            }
+            __syncthreads();
+        }
+        for (int k = K; k >= 1; --k) {
+            const uint32_t Y_hi = sYb + (uint32_t)(k & 1) * (uint32_t)kSaveX, Y_lo = Y_hi + kPlane128;
+            const uint32_t X_hi = sXS + (uint32_t)((k - 1) & 1) * (uint32_t)(kSaveX + kSaveSS), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX;
+            ld_wait(0);
+            ld_wait(1);
+            if (is_iss && tc::elect_one()) {
+                tc::tc_fence_after();
+                if (k >= 2) {
+                    mma3<true, true>(tmem, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
+                    mma3<true, true>(tmem + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
+                }
+                bulk_wait_read();                    // the copy of T_{k+1} has left shared memory
+                tc::umma_commit(&bar_mma);
+                if (k < K) { bulk_wait_all(); flag_set(flagp(1, k + 1)); }
+                if (k >= 2) { load_xs(k - 2); load_y(k - 1); }
+            }
+            mma_wait();
+            float d[32], P[32];
+            float s = 0.0f;
+            if (is_epi) {
+                if (k >= 2) {
+                    tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), d);
+                } else if (half == 0) {
+                    load_row32(Y_hi, Y_lo, r, ch, d);                     // L_0 = I: dS'_0 = dL_1
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) d[c] = 0.0f;             // R_1 = I is not a product: dS_0 = 0
+                }
+                if (half == 0) load_row32(S_hi + 2 * kTile64, S_hi + 3 * kTile64, r, ch, P);
+                else load_row32(S_hi, S_hi + kTile64, r, ch, P);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) s = fmaf(P[c], d[c], s);
+                s_red[half * 2 + ch][r] = s;
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            if (is_epi) {
+                s += s_red[half * 2 + (1 - ch)][r];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) d[c] = coef * P[c] * (d[c] - s);
+                if (half == 1 && p.dA && r < N) {
+                    const float* src = p.dA + (((size_t)b * (T - 1) + (k - 1)) * N + r) * N;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (32 * ch + c < N) d[c] = fmaf(p.inv_tau, __ldg(src + 32 * ch + c), d[c]);
+                }
+                store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, d);   // T1 (rows of dA) on top, T2 (rows of dA^T) below
+            }
+            publish();
+            if (is_iss && tc::elect_one()) {
+                bulk_store(pp.scratch + sc.Tt(b, k), sT, (uint32_t)kSaveX);
+                bulk_commit();
+            }
+        }
+        if (is_iss && tc::elect_one()) {
+            bulk_wait_all();
+            flag_set(flagp(1, 1));
+        }
+    } else {
+        // ================= dE (frames) =================
+        const int e = role - 2;
+        const uint32_t sTa = sb, sTb = sb + (uint32_t)kSaveX, sEa = sb + 2 * (uint32_t)kSaveX, sEb = sb + 3 * (uint32_t)kSaveX;
+        if (e == 0 && !p.dA) {                       // frame T-1 only enters the last affinity, which the loss does not see
+            float4* dst = reinterpret_cast<float4*>(p.dx + (size_t)(b * T + T - 1) * N * 128);
+            for (int i = tid; i < N * 32; i += kThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int j = k_first - e; j >= 0; j -= pp.PE) {
+            const bool has1 = j + 1 <= k_first, has2 = j >= 1;
+            if (is_iss && tc::elect_one()) {
+                const uint32_t bytes = (uint32_t)((has1 ? 1 : 0) + (has2 ? 1 : 0)) * (uint32_t)(kSaveX + kSaveFrame);
+                if (has1) flag_wait(flagp(1, j + 1), err);
+                if (has2) flag_wait(flagp(1, j), err);
+                tc::mbar_arrive_expect_tx(&bar_ld[0], bytes);
+                if (has1) {
+                    bulk_load(sTa, pp.scratch + sc.Tt(b, j + 1), (uint32_t)kSaveX, &bar_ld[0]);
+                    bulk_load(sEa, p.ws + lay.frame(b, j + 1), (uint32_t)kSaveFrame, &bar_ld[0]);
+                }
+                if (has2) {
+                    bulk_load(sTb, pp.scratch + sc.Tt(b, j), (uint32_t)kSaveX, &bar_ld[0]);
+                    bulk_load(sEb, p.ws + lay.frame(b, j - 1), (uint32_t)kSaveFrame, &bar_ld[0]);
+                }
+            }
+            ld_wait(0);
+            if (is_iss && tc::elect_one()) {
+                tc::tc_fence_after();
+                // frame tiles: [hi, lo][k-block][64 rows][128 B] -> MN-major B with two 64-channel groups 8 KB apart
+                if (has1) {
+                    mma3<false, true, 128>(tmem, sTa, sTa + kPlane128, sEa, sEa + 2 * kTile64, 1, 0, 0, 0, true, kTile64);                       // T1 E_{j+1}
+                    mma3<true, true, 128>(tmem, sTa + kTile64, sTa + kPlane128 + kTile64, sEa, sEa + 2 * kTile64, 1, 0, 0, kTile64, false, kTile64); // T2^T E_{j+1}
+                }
+                if (has2) {
+                    mma3<false, true, 128>(tmem, sTb + kTile64, sTb + kPlane128 + kTile64, sEb, sEb + 2 * kTile64, 1, 0, 0, 0, !has1, kTile64);  // T2 E_{j-1}
+                    mma3<true, true, 128>(tmem, sTb, sTb + kPlane128, sEb, sEb + 2 * kTile64, 1, 0, 0, kTile64, false, kTile64);                  // T1^T E_{j-1}
+                }
+                tc::umma_commit(&bar_mma);
+            }
+            mma_wait();
+            // F.normalize backward on the rows in lanes 0-63; thread = (row r, 64 channels)
+            float g[64];
+            float dot = 0.0f;
+            const bool mine = is_epi && half == 0;
+            const float inv = (mine && r < N) ? invn[j * 64 + r] : 0.0f;
+            const float4* xr = reinterpret_cast<const float4*>(p.x + ((size_t)(b * T + j) * N + (r < N ? r : 0)) * 128 + 64 * ch);
+            if (mine) {
+                tmem_ld64(tmem + lane_base + (uint32_t)(ch * 64), g);
+                if (r < N) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 q = __ldg(xr + i);
+                        dot = fmaf(q.x, g[4 * i], dot); dot = fmaf(q.y, g[4 * i + 1], dot); dot = fmaf(q.z, g[4 * i + 2], dot); dot = fmaf(q.w, g[4 * i + 3], dot);
+                    }
+                }
+                s_red[ch][r] = dot;
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+            if (mine && r < N) {
+                dot = (dot + s_red[1 - ch][r]) * inv * inv;
+                float4* dst = reinterpret_cast<float4*>(p.dx + ((size_t)(b * T + j) * N + r) * 128 + 64 * ch);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 q = __ldg(xr + i);
+                    float4 o;
+                    o.x = (g[4 * i] - q.x * dot) * inv; o.y = (g[4 * i + 1] - q.y * dot) * inv;
+                    o.z = (g[4 * i + 2] - q.z * dot) * inv; o.w = (g[4 * i + 3] - q.w * dot) * inv;
+                    dst[i] = o;
+                }
+            }
+            tc::tc_fence_before();
+            __syncthreads();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(tmem);
+}
+
 }  // namespace wf
 
 // ------------------------------------------------------------------------------------------
@@ -1106,12 +1439,15 @@ static int make_tmap_f32_c32(CUtensorMap* out, const void* base, uint64_t rows, 
 bool walk_fused_supported(int N, int C, int T) { return N >= 8 && N <= 64 && C == 128 && T >= 3; }
 size_t walk_fused_saved_bytes(int B, int T) { return wf::Layout(B, T).total + 1024; }
 
-// Role-split kernels (several CTAs per batch element, hand-over through L2) while every CTA of the launch can be resident at once
-// (no CTA then waits for one that is not running); one CTA per element beyond.  CRW_WALK_ROLES=0 / 1 forces.
-static bool walk_fused_roles(int B, int sms) {
+// Role-split kernels (several CTAs per batch element, hand-over through L2): number of affinity producers per element, 0 = one CTA
+// per element.  A CTA only waits for CTAs with a smaller block index (dispatched before it) and producers wait for nobody, so the
+// launch may exceed one wave; beyond ~1.5 waves the extra CTAs buy nothing.  CRW_WALK_ROLES=<P> forces (0 = off).
+static int walk_fused_roles(int B, int sms) {
     const char* e = getenv("CRW_WALK_ROLES");
-    if (e) return atoi(e) != 0;
-    return 4 * B <= sms;
+    if (e) { const int v = atoi(e); return v < 0 ? 0 : (v > 8 ? 8 : v); }
+    if (6 * B <= sms + sms / 2) return 4;
+    if (4 * B <= sms) return 2;
+    return 0;
 }
 
 static uint8_t* wf_align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023)); }
@@ -1139,12 +1475,13 @@ int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, fl
     CRW_CUDA_RET(cudaMemsetAsync(p.ws + lay.ctr, 0, lay.total - lay.ctr, st));          // loss counter, error flag, hand-over flags
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (walk_fused_roles(B, sms)) {
+    p.P = walk_fused_roles(B, sms);
+    if (p.P > 0) {
         if (dev >= 0 && dev < 64 && !attr_done_roles[dev]) {
             CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_fwd_roles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemRoles));
             attr_done_roles[dev] = true;
         }
-        wf::walk_fused_fwd_roles_kernel<<<4 * B, wf::kThreads, wf::kSmemRoles, st>>>(xmap, p);
+        wf::walk_fused_fwd_roles_kernel<<<(p.P + 2) * B, wf::kThreads, wf::kSmemRoles, st>>>(xmap, p);
     } else {
         wf::walk_fused_fwd_kernel<<<B, wf::kThreads, wf::kSmemFwd, st>>>(xmap, p);
     }
@@ -1152,14 +1489,17 @@ int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, fl
     return CRW_OK;
 }
 
+size_t walk_fused_bwd_scratch_bytes(int B, int T) { return wf::BScratch(B, T).total + 1024; }
+
 int walk_fused_backward(const float* x, const void* saved, const float* dloss, const float* dA_or_null, int B, int T, int N, int C, float tau,
-                        float* dx, cudaStream_t st) {
+                        float* dx, void* scratch, cudaStream_t st) {
     if (!walk_fused_supported(N, C, T)) return CRW_ERR_UNSUPPORTED;
     static bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemBwd));
+        CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_bwd_roles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemBwdRoles));
         attr_done[dev] = true;
     }
     wf::BwdParams p;
@@ -1168,7 +1508,19 @@ int walk_fused_backward(const float* x, const void* saved, const float* dloss, c
     p.inv_tau = 1.0f / tau;
     p.x = x; p.dloss = dloss; p.dA = dA_or_null; p.dx = dx;
     p.ws = wf_align1k(const_cast<void*>(saved));
-    wf::walk_fused_bwd_kernel<<<B, wf::kBwdThreads, wf::kSmemBwd, st>>>(p);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (walk_fused_roles(B, sms) > 0 && scratch) {
+        wf::BwdRolesParams pp;
+        pp.q = p;
+        pp.scratch = wf_align1k(scratch);
+        pp.PE = 2;
+        const wf::BScratch sc(B, T);
+        CRW_CUDA_RET(cudaMemsetAsync(pp.scratch + sc.flags, 0, sc.total - sc.flags, st));
+        wf::walk_fused_bwd_roles_kernel<<<(2 + pp.PE) * B, wf::kThreads, wf::kSmemBwdRoles, st>>>(pp);
+    } else {
+        wf::walk_fused_bwd_kernel<<<B, wf::kBwdThreads, wf::kSmemBwd, st>>>(p);
+    }
     CRW_LAUNCH_RET();
     return CRW_OK;
 }

@@ -1,5 +1,4 @@
-"""Fused tcgen05 walk (walk_fused.cu: one kernel per direction, one CTA per batch element; opt-in through CRW_WALK_FUSED=1 with
-precision=BF16X3) against the fp64 oracle and the live-reference goldens -- reference: src/model.py:22-46 and its autograd.
+"""Fused tcgen05 walk (walk_fused.cu: one kernel per direction; CRW_WALK_FUSED=1 with precision=BF16X3 forces it at any batch) against the fp64 oracle and the live-reference goldens -- reference: src/model.py:22-46 and its autograd.
 Bars: loss / A 1e-4, gradients 1e-3 relative (BASELINE north_star: "within 1e-3 relative, bf16 operands stated")."""
 import numpy as np
 import pytest
@@ -17,9 +16,18 @@ def pkg():
     return p
 
 
-@pytest.fixture()
-def fused(monkeypatch):
+@pytest.fixture(params=["roles", "roles2", "one_cta"])
+def fused(request, monkeypatch):
+    """The fused engine in its three shapes: role-split kernels (several CTAs per batch element handing operand tiles over through
+    L2; four or two affinity producers) and one CTA per batch element."""
     monkeypatch.setenv("CRW_WALK_FUSED", "1")
+    if request.param == "one_cta":
+        monkeypatch.setenv("CRW_WALK_ROLES", "0")
+    elif request.param == "roles2":
+        monkeypatch.setenv("CRW_WALK_ROLES", "2")
+    else:
+        monkeypatch.delenv("CRW_WALK_ROLES", raising=False)
+    return request.param
 
 
 def _dev(a):

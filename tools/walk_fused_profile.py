@@ -26,6 +26,10 @@ torch.cuda.synchronize()
 L.crw_debug_walk_fused_profile(buf.ctypes.data_as(ctypes.c_void_p), 1)
 fw = ["wait frame", "convert", "issue A", "wait A", "epilogue A (+pub)", "issue X", "wait X", "epilogue X (+pub)", "issue M", "wait M", "epilogue M + save"]
 bw = ["issue (a)", "wait (a)", "epilogue (b)", "issue (c,d)", "wait (c,d)", "epilogue (e)", "convert next", "wait block"]
+if os.environ.get("CRW_WALK_ROLES", "") != "0":
+    print("forward, role-split kernel, element 0: cycles [total, waiting for loads / hand-over, waiting for MMAs]")
+    for i, n in enumerate(["producer 0", "producer 1", "chain", "cycle"]):
+        print(f"  {n:12s} {int(buf[4 * i]):8d} {int(buf[4 * i + 1]):8d} {int(buf[4 * i + 2]):8d}")
 print("forward, cycles over the kernel (thread 0 of CTA 0; 1 us ~ 1900 cycles):")
 for i, n in enumerate(fw):
     print(f"  {n:20s} {int(buf[i]):8d}")
