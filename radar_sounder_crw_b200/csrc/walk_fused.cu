@@ -24,6 +24,7 @@ namespace crw {
 namespace wf {
 
 constexpr int kThreads = 256 + 32;                       // forward: 8 epilogue warps (warps w and w + 4 share accumulator rows 32 (w & 3) .., 32 columns each) + the issuer warp
+constexpr int kRoleThreads = 256 + 64;                   // role-split kernels: 8 epilogue warps + the issuer warp + the store warp
 constexpr int kBwdThreads = 128 + 32;                    // backward: 4 epilogue warps (thread = accumulator row) + the issuer warp
 constexpr uint32_t kPlane128 = 128 * 128;                // [128 rows][128 B]
 constexpr uint32_t kTile64 = 64 * 128;                   // [64 rows][128 B]
@@ -147,6 +148,11 @@ __device__ __forceinline__ void flag_set(int* f) {
     asm volatile("fence.proxy.async;" ::: "memory");
     __threadfence();
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+}
+__device__ __forceinline__ bool flag_peek(const int* f) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    return v != 0;
 }
 __device__ __forceinline__ bool flag_wait(const int* f, int* err) {
     int v = 0;
@@ -497,11 +503,11 @@ constexpr uint32_t rAst = rSS + 4 * kTile64;             // producer: fp32 A_t s
 constexpr uint32_t rEnd = rAst + 64 * 64 * 4;
 constexpr uint32_t kSmemRoles = rEnd + 1024;
 
-__global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams p) {
+__global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(const __grid_constant__ CUtensorMap xmap, FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sb - tc::smem_u32(smem_raw));            // generic pointer to the aligned base
-    __shared__ uint64_t bar_ld[2], bar_mma;
+    __shared__ uint64_t bar_ld[2], bar_mma, bar_st;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_red[4][64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -515,18 +521,37 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
         tc::mbar_init(&bar_ld[0], 1);
         tc::mbar_init(&bar_ld[1], 1);
         tc::mbar_init(&bar_mma, 1);
+        tc::mbar_init(&bar_st, 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&xmap);
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const bool is_epi = warp < 8, is_iss = warp == 8;
+    // warp 8 issues loads and MMAs; warp 9 issues the bulk stores, waits for their completion and raises the flags -- it is back at the
+    // next CTA barrier before anybody overwrites what it copied, and its waits stay off the issuer's path
+    const bool is_epi = warp < 8, is_iss = warp == 8, is_st = warp == 9;
     const uint32_t tmem = tmem_base_s;
     const int row = ((warp & 3) << 5) | lane;
     const int half = row >> 6, r = row & 63, ch = (warp >> 2) & 1;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ld_phase[2] = {0u, 0u}, mma_phase = 0;
+    // the store warp's copy of a tile has LEFT shared memory (arrives on bar_st): waited for by everybody right before the tile is
+    // overwritten in place; its completion in global memory and the flag follow on the store lane alone
+    uint32_t st_phase = 0;
+    auto st_wait = [&]() {
+        if (is_st) return;                   // (the store warp is the one that arrives; see ld_wait)
+        tc::mbar_wait(&bar_st, st_phase & 1);
+        ++st_phase;
+    };
+    auto store_tile = [&](void* gdst, uint32_t ssrc, uint32_t bytes, int* flag) {     // store lane
+        bulk_store(gdst, ssrc, bytes);
+        bulk_commit();
+        bulk_wait_read();
+        tc::mbar_arrive(&bar_st);
+        bulk_wait_all();
+        if (flag) flag_set(flag);
+    };
     auto publish = [&]() {
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -541,13 +566,17 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
     const bool rprof = p.prof && b == 0 && tid == 0;
     const long long c_begin = clock64();
     long long c_ld = 0, c_mma = 0;
+    // (The store warp skips the waits on load / MMA barriers: it needs none of that data, and, coming late from a copy it completed,
+    // it could find a barrier re-armed and completed AGAIN -- same parity -- and wait for ever.)
     auto ld_wait = [&](int i) {
+        if (is_st) return;
         const long long c0 = rprof ? clock64() : 0;
         tc::mbar_wait(&bar_ld[i], ld_phase[i] & 1);
         ++ld_phase[i];
         if (rprof) c_ld += clock64() - c0;
     };
     auto mma_wait = [&]() {
+        if (is_st) return;
         const long long c0 = rprof ? clock64() : 0;
         mma_wait_raw();
         if (rprof) c_mma += clock64() - c0;
@@ -595,23 +624,24 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
 #pragma unroll
             for (int q = 0; q < 4; ++q) bulk_store(dst + q * kTile64, sE + (uint32_t)q * kPlane128 + (uint32_t)(f & 1) * kTile64, kTile64);
         };
-        if (role < Tlast && is_iss && tc::elect_one()) { issue_frame(role, 0); issue_frame(role + 1, 1); }
+        if (role < Tlast && is_iss) { if (tc::elect_one()) { issue_frame(role, 0); issue_frame(role + 1, 1); } __syncwarp(); }
         for (int t = role; t < Tlast; t += P) {
             ld_wait(0);
             convert_frame(t, 0);
             ld_wait(1);
             convert_frame(t + 1, 1);
-            if (is_iss && tc::elect_one()) bulk_wait_read();             // (the S tiles of the last affinity have left shared memory)
             publish();
-            if (is_iss && tc::elect_one()) {
-                tc::tc_fence_after();
-                if (t + P < Tlast) { issue_frame(t + P, 0); issue_frame(t + P + 1, 1); }
+            if (is_st) { if (tc::elect_one()) {          // (waited for together with the S tiles at the end of this affinity, before the ring is rewritten)
                 save_frame(t);
                 save_frame(t + 1);
                 bulk_commit();
+            } __syncwarp(); }
+            if (is_iss) { if (tc::elect_one()) {
+                tc::tc_fence_after();
+                if (t + P < Tlast) { issue_frame(t + P, 0); issue_frame(t + P + 1, 1); }
                 mma3<false, false, 128>(tmem, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
                 tc::umma_commit(&bar_mma);
-            }
+            } __syncwarp(); }
             mma_wait();
             const bool isA = (half == 0) == ((t & 1) == 0);
             float a[32];
@@ -652,18 +682,19 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
                 store_row32(sSS + (isA ? 0u : 2u * kTile64), sSS + (isA ? 1u : 3u) * kTile64, r, ch, a);
             }
             publish();
-            if (t < K && is_iss && tc::elect_one()) {
-                bulk_store(p.ws + lay.step(b, t) + kSaveX, sSS, (uint32_t)kSaveSS);
-                bulk_commit();
+            if (is_st) { if (tc::elect_one()) {
+                if (t < K) {
+                    bulk_store(p.ws + lay.step(b, t) + kSaveX, sSS, (uint32_t)kSaveSS);
+                    bulk_commit();
+                }
                 bulk_wait_all();
-                flag_set(flagp(0, t));
-            }
+                if (t < K) flag_set(flagp(0, t));
+            } __syncwarp(); }
             if (p.A) {
                 float* dst = p.A + ((size_t)b * (T - 1) + t) * N * N;
-                for (int i = tid; i < N * N; i += kThreads) dst[i] = tc::lds_f32(sAst + (uint32_t)i * 4u);
+                for (int i = tid; i < N * N; i += kRoleThreads) dst[i] = tc::lds_f32(sAst + (uint32_t)i * 4u);
             }
         }
-        if (is_iss && tc::elect_one()) bulk_wait_all();
     } else if (role == P) {
         // ================= chain =================
         const uint32_t sSSb = sb + rE, sX = sb + rRaw;                   // S tiles: two 32 KB buffers; X: hi, lo
@@ -673,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             tc::mbar_arrive_expect_tx(&bar_ld[buf], (uint32_t)kSaveSS);
             bulk_load(sSSb + (uint32_t)buf * (uint32_t)kSaveSS, p.ws + lay.step(b, t) + kSaveX, (uint32_t)kSaveSS, &bar_ld[buf]);
         };
-        if (is_iss && tc::elect_one()) load_ss(0, 0);
+        if (is_iss) { if (tc::elect_one()) load_ss(0, 0); __syncwarp(); }
         for (int k = 1; k <= K; ++k) {
             const int buf = (k - 1) & 1;
             const uint32_t sSS = sSSb + (uint32_t)buf * (uint32_t)kSaveSS;
@@ -695,18 +726,15 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
                 }
                 publish();
             } else {
-                if (is_iss && tc::elect_one()) {
+                if (is_iss) { if (tc::elect_one()) {
                     tc::tc_fence_after();
                     mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);   // X . S'_{k-1}
                     mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);               // X . S_{k-1}^T
-                    bulk_wait_read();                                    // the copy of X_{k-1} has left shared memory before anybody is told the product is done
                     tc::umma_commit(&bar_mma);
-                    // under the MMAs: X_{k-1} has been copied out completely -> hand it to the cycle CTA; fetch the next S tiles
-                    bulk_wait_all();
-                    flag_set(flagp(1, k - 1));
-                    if (k < K) load_ss(k, k & 1);
-                }
+                    if (k < K) load_ss(k, k & 1);                        // under the MMAs: fetch the next S tiles
+                } __syncwarp(); }
                 mma_wait();
+                st_wait();                                               // the copy of X_{k-1} has left shared memory
                 if (is_epi) {
                     float x[32];
                     tmem_ld32(tX + lane_base + (uint32_t)(half * 64 + ch * 32), x);
@@ -714,15 +742,8 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
                 }
                 publish();
             }
-            if (is_iss && tc::elect_one()) {
-                bulk_store(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX);
-                bulk_commit();
-                if (k == 1 && K > 1) load_ss(1, 1);
-            }
-        }
-        if (is_iss && tc::elect_one()) {
-            bulk_wait_all();
-            flag_set(flagp(1, K));
+            if (k == 1 && K > 1 && is_iss) { if (tc::elect_one()) load_ss(1, 1); __syncwarp(); }
+            if (is_st) { if (tc::elect_one()) store_tile(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX, flagp(1, k)); __syncwarp(); }   // the cycle CTA is waiting for X_k
         }
     } else {
         // ================= cycle =================
@@ -734,19 +755,19 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
             bulk_load(sXb + (uint32_t)buf * (uint32_t)kSaveX, p.ws + lay.step(b, k), (uint32_t)kSaveX, &bar_ld[buf]);
         };
         float loss_acc = 0.0f;
-        if (is_iss && tc::elect_one()) load_x(1, 1);
+        if (is_iss) { if (tc::elect_one()) load_x(1, 1); __syncwarp(); }
         for (int k = 1; k <= K; ++k) {
             const int buf = k & 1;
             const uint32_t sX = sXb + (uint32_t)buf * (uint32_t)kSaveX;
             ld_wait(buf);
-            if (is_iss && tc::elect_one()) {
+            if (is_iss) { if (tc::elect_one()) {
                 tc::tc_fence_after();
                 mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);    // M_k = L_k R_k
-                bulk_wait_read();                                        // G_{k-1} has left shared memory before the epilogue is let go
                 tc::umma_commit(&bar_mma);
                 if (k < K) load_x(k + 1, (k + 1) & 1);                   // (its buffer was read by the product before last: complete)
-            }
+            } __syncwarp(); }
             mma_wait();
+            if (k >= 2) st_wait();                                       // the copy of G_{k-1} has left shared memory
             float m[32];
             float sm = 0.0f, diag = 0.0f;
             if (is_epi && half == 0) {
@@ -770,10 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
                 store_row32(sG, sG + kTile64, r, ch, m);
             }
             publish();
-            if (is_iss && tc::elect_one()) {
-                bulk_store(p.ws + lay.step(b, k) + kSaveX + kSaveSS, sG, (uint32_t)kSaveG);
-                bulk_commit();
-            }
+            if (is_st) { if (tc::elect_one()) store_tile(p.ws + lay.step(b, k) + kSaveX + kSaveSS, sG, (uint32_t)kSaveG, nullptr); __syncwarp(); }
         }
         __syncthreads();
         if (is_epi && half == 0) s_red[ch][r] = loss_acc;
@@ -793,7 +811,6 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_roles_kernel(const
                 *p.loss = sum / ((float)p.B * (float)N * (float)N);
             }
         }
-        if (is_iss && tc::elect_one()) bulk_wait_all();
     }
     if (rprof && (role < 2 || role >= P)) {
         const int pr = role < P ? (role < 2 ? role : 1) : (role == P ? 2 : 3);
@@ -1117,17 +1134,19 @@ struct BwdRolesParams {
     BwdParams q;
     uint8_t* scratch;         // BScratch (1024-aligned)
     int PE;                   // dE CTAs per batch element
+    int dbg;                  // development switches (CRW_WALK_DBG)
 };
 
 constexpr uint32_t kSmemBwdRoles = 7 * 2 * kPlane128 + 1024;             // 224 KB (the dA role's map) + alignment slack
 
-__global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRolesParams pp) {
+__global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(BwdRolesParams pp) {
     const BwdParams& p = pp.q;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ uint64_t bar_ld[2], bar_mma;
+    __shared__ uint64_t bar_ld[2], bar_mma, bar_st;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_red[4][64];
+    __shared__ int s_next;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = blockIdx.x / p.B, b = blockIdx.x % p.B, N = p.N, T = p.T, K = T - 2;
     const Layout lay(p.B, T);
@@ -1141,34 +1160,65 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
         tc::mbar_init(&bar_ld[0], 1);
         tc::mbar_init(&bar_ld[1], 1);
         tc::mbar_init(&bar_mma, 1);
+        tc::mbar_init(&bar_st, 1);
         tc::fence_barrier_init();
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const bool is_epi = warp < 8, is_iss = warp == 8;
+    const bool is_epi = warp < 8, is_iss = warp == 8, is_st = warp == 9;      // (warp 9: bulk stores, their completion, the flags)
     const uint32_t tmem = tmem_base_s;
     const int row = ((warp & 3) << 5) | lane;
     const int half = row >> 6, r = row & 63, ch = (warp >> 2) & 1;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ld_phase[2] = {0u, 0u}, mma_phase = 0;
+    // the store warp's copy of a tile has LEFT shared memory (arrives on bar_st): waited for by everybody right before the tile is
+    // overwritten in place; its completion in global memory and the flag follow on the store lane alone
+    uint32_t st_phase = 0;
+    auto st_wait = [&]() {
+        if (is_st) return;                   // (the store warp is the one that arrives; see ld_wait)
+        tc::mbar_wait(&bar_st, st_phase & 1);
+        ++st_phase;
+    };
+    auto store_tile = [&](void* gdst, uint32_t ssrc, uint32_t bytes, int* flag) {     // store lane
+        bulk_store(gdst, ssrc, bytes);
+        bulk_commit();
+        bulk_wait_read();
+        tc::mbar_arrive(&bar_st);
+        bulk_wait_all();
+        if (flag) flag_set(flag);
+    };
     auto publish = [&]() {
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
     };
+    // profiling aid (CRW_WALK_PROF=1): per role of element 0, cycles [total, waiting for loads / hand-over, waiting for MMAs]
+    const bool rprof = p.prof && b == 0 && tid == 0;
+    const long long c_begin = clock64();
+    long long c_ld = 0, c_mma = 0;
     auto mma_wait = [&]() {
+        if (is_st) return;
+        const long long c0 = rprof ? clock64() : 0;
         tc::mbar_wait(&bar_mma, mma_phase & 1);
         ++mma_phase;
         tc::tc_fence_after();
+        if (rprof) c_mma += clock64() - c0;
     };
+    // (The store warp skips the waits on load / MMA barriers: it needs none of that data, and, coming late from a copy it completed,
+    // it could find a barrier re-armed and completed AGAIN -- same parity -- and wait for ever.)
     auto ld_wait = [&](int i) {
+        if (is_st) return;
+        const long long c0 = rprof ? clock64() : 0;
         tc::mbar_wait(&bar_ld[i], ld_phase[i] & 1);
         ++ld_phase[i];
+        if (rprof) c_ld += clock64() - c0;
     };
     const int k_first = p.dA ? K + 1 : K;
 
-    if (role == 0) {
+    if (((pp.dbg & 2) && role >= 1) || ((pp.dbg & 4) && role >= 2)) {
+        // (development: role switched off)
+    } else if (role == 0) {
         // ================= chain =================
         const uint32_t sY = sb + 2 * (uint32_t)kSaveStep;                // blocks: two 80 KB buffers at 0; Y: hi, lo
         const uint32_t Y_hi = sY, Y_lo = sY + kPlane128;
@@ -1177,15 +1227,15 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             tc::mbar_arrive_expect_tx(&bar_ld[j & 1], (uint32_t)kSaveStep);
             bulk_load(blk(j), p.ws + lay.step(b, j), (uint32_t)kSaveStep, &bar_ld[j & 1]);
         };
-        if (is_iss && tc::elect_one()) { load_block(K); if (K >= 2) load_block(K - 1); }
+        if (is_iss) { if (tc::elect_one()) { load_block(K); if (K >= 2) load_block(K - 1); } __syncwarp(); }
         ld_wait(K & 1);
-        if (is_iss && tc::elect_one()) {             // Y_K = [G_K R_K^T ; G_K^T L_K]
+        if (is_iss) { if (tc::elect_one()) {             // Y_K = [G_K R_K^T ; G_K^T L_K]
             const uint32_t X_hi = blk(K), X_lo = X_hi + kPlane128, G_hi = X_hi + (uint32_t)(kSaveX + kSaveSS), G_lo = G_hi + kTile64;
             tc::tc_fence_after();
             mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
             mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
             tc::umma_commit(&bar_mma);
-        }
+        } __syncwarp(); }
         mma_wait();
         if (is_epi) {
             float y[32];
@@ -1193,40 +1243,28 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             store_row32(Y_hi, Y_lo, row, ch, y);
         }
         publish();
-        if (is_iss && tc::elect_one()) {
-            bulk_store(pp.scratch + sc.Y(b, K), sY, (uint32_t)kSaveX);
-            bulk_commit();
-        }
+        if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Y(b, K), sY, (uint32_t)kSaveX, flagp(0, K)); __syncwarp(); }
         for (int k = K; k >= 2; --k) {
             ld_wait((k - 1) & 1);
-            if (is_iss && tc::elect_one()) {         // Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]
+            if (is_iss) { if (tc::elect_one()) {         // Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]
                 const uint32_t X_hi = blk(k - 1), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX, G_hi = S_hi + (uint32_t)kSaveSS, G_lo = G_hi + kTile64;
                 tc::tc_fence_after();
                 mma3<false, false>(tmem, Y_hi, Y_lo, S_hi + 2 * kTile64, S_hi + 3 * kTile64, 1, 0, 0, 0, true);             // dL_k S'_{k-1}^T
                 mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, false);                    // G_{k-1} R_{k-1}^T
                 mma3<false, true>(tmem + 64u, Y_hi, Y_lo, S_hi, S_hi + kTile64, 1, 0, 0, 0, true);                          // dR_k^T S_{k-1}
                 mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, false);         // G_{k-1}^T L_{k-1}
-                bulk_wait_read();                    // the copy of Y_k has left shared memory before the epilogue is let go
                 tc::umma_commit(&bar_mma);
-                bulk_wait_all();
-                flag_set(flagp(0, k));
                 if (k >= 3) load_block(k - 2);       // (its buffer was read by the products of the step before: complete)
-            }
+            } __syncwarp(); }
             mma_wait();
+            st_wait();                                                   // the copy of Y_k has left shared memory
             if (is_epi) {
                 float y[32];
                 tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
                 store_row32(Y_hi, Y_lo, row, ch, y);
             }
             publish();
-            if (is_iss && tc::elect_one()) {
-                bulk_store(pp.scratch + sc.Y(b, k - 1), sY, (uint32_t)kSaveX);
-                bulk_commit();
-            }
-        }
-        if (is_iss && tc::elect_one()) {
-            bulk_wait_all();
-            flag_set(flagp(0, 1));
+            if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Y(b, k - 1), sY, (uint32_t)kSaveX, flagp(0, k - 1)); __syncwarp(); }
         }
     } else if (role == 1) {
         // ================= dA =================
@@ -1243,7 +1281,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             tc::mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(kSaveX + kSaveSS));
             bulk_load(sXS + (uint32_t)(j & 1) * (uint32_t)(kSaveX + kSaveSS), p.ws + lay.step(b, j), (uint32_t)(kSaveX + kSaveSS), &bar_ld[1]);
         };
-        if (is_iss && tc::elect_one()) { load_xs(K - 1); load_y(K); }
+        if (is_iss) { if (tc::elect_one()) { load_xs(K - 1); load_y(K); } __syncwarp(); }
         if (p.dA) {
             // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
             if (is_epi) {
@@ -1259,12 +1297,12 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
                 store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, v);
             }
             publish();
-            if (is_iss && tc::elect_one()) {
+            if (is_st) { if (tc::elect_one()) {
                 bulk_store(pp.scratch + sc.Tt(b, K + 1), sT, (uint32_t)kSaveX);
                 bulk_commit();
                 bulk_wait_all();
                 flag_set(flagp(1, K + 1));
-            }
+            } __syncwarp(); }
             __syncthreads();
         }
         for (int k = K; k >= 1; --k) {
@@ -1272,17 +1310,15 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             const uint32_t X_hi = sXS + (uint32_t)((k - 1) & 1) * (uint32_t)(kSaveX + kSaveSS), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX;
             ld_wait(0);
             ld_wait(1);
-            if (is_iss && tc::elect_one()) {
+            if (is_iss) { if (tc::elect_one()) {
                 tc::tc_fence_after();
                 if (k >= 2) {
                     mma3<true, true>(tmem, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
                     mma3<true, true>(tmem + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
                 }
-                bulk_wait_read();                    // the copy of T_{k+1} has left shared memory
                 tc::umma_commit(&bar_mma);
-                if (k < K) { bulk_wait_all(); flag_set(flagp(1, k + 1)); }
                 if (k >= 2) { load_xs(k - 2); load_y(k - 1); }
-            }
+            } __syncwarp(); }
             mma_wait();
             float d[32], P[32];
             float s = 0.0f;
@@ -1303,6 +1339,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             }
             tc::tc_fence_before();
             __syncthreads();
+            if (k < K) st_wait();                                        // the copy of T_{k+1} has left shared memory
             if (is_epi) {
                 s += s_red[half * 2 + (1 - ch)][r];
 #pragma unroll
@@ -1316,14 +1353,7 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
                 store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, d);   // T1 (rows of dA) on top, T2 (rows of dA^T) below
             }
             publish();
-            if (is_iss && tc::elect_one()) {
-                bulk_store(pp.scratch + sc.Tt(b, k), sT, (uint32_t)kSaveX);
-                bulk_commit();
-            }
-        }
-        if (is_iss && tc::elect_one()) {
-            bulk_wait_all();
-            flag_set(flagp(1, 1));
+            if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Tt(b, k), sT, (uint32_t)kSaveX, flagp(1, k)); __syncwarp(); }   // the dE CTAs are waiting for T_k
         }
     } else {
         // ================= dE (frames) =================
@@ -1331,26 +1361,29 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
         const uint32_t sTa = sb, sTb = sb + (uint32_t)kSaveX, sEa = sb + 2 * (uint32_t)kSaveX, sEb = sb + 3 * (uint32_t)kSaveX;
         if (e == 0 && !p.dA) {                       // frame T-1 only enters the last affinity, which the loss does not see
             float4* dst = reinterpret_cast<float4*>(p.dx + (size_t)(b * T + T - 1) * N * 128);
-            for (int i = tid; i < N * 32; i += kThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < N * 32; i += kRoleThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        auto load_frame_tiles = [&](int j) {         // issuer lane: T_{j+1}, E_{j+1}, T_j, E_{j-1} (those that exist)
+            const bool has1 = j + 1 <= k_first, has2 = j >= 1;
+            const uint32_t bytes = (uint32_t)((has1 ? 1 : 0) + (has2 ? 1 : 0)) * (uint32_t)(kSaveX + kSaveFrame);
+            if (has1) flag_wait(flagp(1, j + 1), err);
+            if (has2) flag_wait(flagp(1, j), err);
+            tc::mbar_arrive_expect_tx(&bar_ld[0], bytes);
+            if (has1) {
+                bulk_load(sTa, pp.scratch + sc.Tt(b, j + 1), (uint32_t)kSaveX, &bar_ld[0]);
+                bulk_load(sEa, p.ws + lay.frame(b, j + 1), (uint32_t)kSaveFrame, &bar_ld[0]);
+            }
+            if (has2) {
+                bulk_load(sTb, pp.scratch + sc.Tt(b, j), (uint32_t)kSaveX, &bar_ld[0]);
+                bulk_load(sEb, p.ws + lay.frame(b, j - 1), (uint32_t)kSaveFrame, &bar_ld[0]);
+            }
+        };
+        bool have_next = false;                      // this frame's tiles were fetched under the previous frame's epilogue
         for (int j = k_first - e; j >= 0; j -= pp.PE) {
             const bool has1 = j + 1 <= k_first, has2 = j >= 1;
-            if (is_iss && tc::elect_one()) {
-                const uint32_t bytes = (uint32_t)((has1 ? 1 : 0) + (has2 ? 1 : 0)) * (uint32_t)(kSaveX + kSaveFrame);
-                if (has1) flag_wait(flagp(1, j + 1), err);
-                if (has2) flag_wait(flagp(1, j), err);
-                tc::mbar_arrive_expect_tx(&bar_ld[0], bytes);
-                if (has1) {
-                    bulk_load(sTa, pp.scratch + sc.Tt(b, j + 1), (uint32_t)kSaveX, &bar_ld[0]);
-                    bulk_load(sEa, p.ws + lay.frame(b, j + 1), (uint32_t)kSaveFrame, &bar_ld[0]);
-                }
-                if (has2) {
-                    bulk_load(sTb, pp.scratch + sc.Tt(b, j), (uint32_t)kSaveX, &bar_ld[0]);
-                    bulk_load(sEb, p.ws + lay.frame(b, j - 1), (uint32_t)kSaveFrame, &bar_ld[0]);
-                }
-            }
+            if (!have_next && is_iss) { if (tc::elect_one()) load_frame_tiles(j); __syncwarp(); }
             ld_wait(0);
-            if (is_iss && tc::elect_one()) {
+            if (is_iss) { if (tc::elect_one()) {
                 tc::tc_fence_after();
                 // frame tiles: [hi, lo][k-block][64 rows][128 B] -> MN-major B with two 64-channel groups 8 KB apart
                 if (has1) {
@@ -1362,8 +1395,24 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
                     mma3<true, true, 128>(tmem, sTb, sTb + kPlane128, sEb, sEb + 2 * kTile64, 1, 0, 0, kTile64, false, kTile64);                  // T1^T E_{j-1}
                 }
                 tc::umma_commit(&bar_mma);
-            }
+            } __syncwarp(); }
             mma_wait();
+            // the operand buffers are free: fetch the next frame's tiles under this frame's epilogue
+            // (only when they are already there: the issuer must not sit in a flag wait while this frame's epilogue needs it at a barrier)
+            bool fetched = false;
+            if (j - pp.PE >= 0) {
+                const int jn = j - pp.PE;
+                int ok = 0;
+                if (is_iss) {
+                    if (tc::elect_one()) {
+                        ok = (jn + 1 > k_first || flag_peek(flagp(1, jn + 1))) && (jn < 1 || flag_peek(flagp(1, jn)));
+                        if (ok) load_frame_tiles(jn);
+                    }
+                    ok = __shfl_sync(0xffffffffu, ok, 0) | __any_sync(0xffffffffu, ok);
+                    if (lane == 0) s_next = ok;
+                }
+                fetched = true;
+            }
             // F.normalize backward on the rows in lanes 0-63; thread = (row r, 64 channels)
             float g[64];
             float dot = 0.0f;
@@ -1397,7 +1446,13 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_bwd_roles_kernel(BwdRo
             }
             tc::tc_fence_before();
             __syncthreads();
+            have_next = fetched && s_next != 0;
         }
+    }
+    if (rprof && role < 4) {
+        g_wf_prof[16 + role * 4 + 0] += (unsigned long long)(clock64() - c_begin);
+        g_wf_prof[16 + role * 4 + 1] += (unsigned long long)c_ld;
+        g_wf_prof[16 + role * 4 + 2] += (unsigned long long)c_mma;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -1481,7 +1536,7 @@ int walk_fused_forward(const float* x, int B, int T, int N, int C, float tau, fl
             CRW_CUDA_RET(cudaFuncSetAttribute(wf::walk_fused_fwd_roles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf::kSmemRoles));
             attr_done_roles[dev] = true;
         }
-        wf::walk_fused_fwd_roles_kernel<<<(p.P + 2) * B, wf::kThreads, wf::kSmemRoles, st>>>(xmap, p);
+        wf::walk_fused_fwd_roles_kernel<<<(p.P + 2) * B, wf::kRoleThreads, wf::kSmemRoles, st>>>(xmap, p);
     } else {
         wf::walk_fused_fwd_kernel<<<B, wf::kThreads, wf::kSmemFwd, st>>>(xmap, p);
     }
@@ -1515,9 +1570,10 @@ int walk_fused_backward(const float* x, const void* saved, const float* dloss, c
         pp.q = p;
         pp.scratch = wf_align1k(scratch);
         pp.PE = 2;
+        { const char* e = getenv("CRW_WALK_DBG"); pp.dbg = e ? atoi(e) : 0; }
         const wf::BScratch sc(B, T);
         CRW_CUDA_RET(cudaMemsetAsync(pp.scratch + sc.flags, 0, sc.total - sc.flags, st));
-        wf::walk_fused_bwd_roles_kernel<<<(2 + pp.PE) * B, wf::kThreads, wf::kSmemBwdRoles, st>>>(pp);
+        wf::walk_fused_bwd_roles_kernel<<<(2 + pp.PE) * B, wf::kRoleThreads, wf::kSmemBwdRoles, st>>>(pp);
     } else {
         wf::walk_fused_bwd_kernel<<<B, wf::kBwdThreads, wf::kSmemBwd, st>>>(p);
     }

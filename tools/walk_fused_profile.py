@@ -34,6 +34,10 @@ print("forward, cycles over the kernel (thread 0 of CTA 0; 1 us ~ 1900 cycles):"
 for i, n in enumerate(fw):
     print(f"  {n:20s} {int(buf[i]):8d}")
 print("  total", int(buf[:16].sum()))
+if os.environ.get("CRW_WALK_ROLES", "") != "0":
+    print("backward, role-split kernel, element 0: cycles [total, waiting for loads / hand-over, waiting for MMAs]")
+    for i, n in enumerate(["chain", "dA", "dE 0", "dE 1"]):
+        print(f"  {n:12s} {int(buf[16 + 4 * i]):8d} {int(buf[16 + 4 * i + 1]):8d} {int(buf[16 + 4 * i + 2]):8d}")
 print("backward:")
 for i, n in enumerate(bw):
     print(f"  {n:20s} {int(buf[16 + i]):8d}")
