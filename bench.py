@@ -280,7 +280,9 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         encoder = crw.UNetEncoder(pos_embed=False, chunk=2048).cuda().train().to(memory_format=torch.channels_last)
     else:
         encoder = crw.Resnet(pos_embed=False).cuda().train().to(memory_format=torch.channels_last)
-    model = crw.CRW(encoder, tau, False, need_A=False)
+    # the walk runs on the fused tcgen05 kernels (precision=BF16X3: error-compensated bf16 pairs, fp32 accumulate -- BASELINE config 2's
+    # "bf16 walk"; loss 1e-7 / gradients 1e-5 of the fp64 oracle)
+    model = crw.CRW(encoder, tau, False, need_A=False, precision=crw.ops.PREC_BF16X3)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=5)          # ~4 buckets of the 19.9 MB of gradients: the all-reduce overlaps backward
@@ -343,7 +345,7 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
                          h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
 
 
-def bench_walk(crw, args, world, pk, N=47, T=None, B=None, precision=None, kernel_note=None):
+def bench_walk(crw, args, world, pk, N=47, T=None, B=None, precision=None, kernel_note=None, launches=8):
     """The hot path alone: fused walk fwd + bwd on resident embeddings (config-2 shape by default)."""
     B = TRAIN["B"] if B is None else B
     T = TRAIN["T"] if T is None else T
@@ -374,7 +376,7 @@ def bench_walk(crw, args, world, pk, N=47, T=None, B=None, precision=None, kerne
     tf = fl / (ms * 1e-3) / 1e12
     kernel = kernel_note or ("walk fwd+bwd kernels (fp32, shared-memory-resident small-N path), 8 launches" if N <= 64 else
                              "walk fwd+bwd kernels (fp32 FMA tiles), 8 launches")
-    return dict(ms=ms, ms_eager=ms_eager, launches=8, shape=dict(B=B, T=T, N=N, C=128),
+    return dict(ms=ms, ms_eager=ms_eager, launches=launches, shape=dict(B=B, T=T, N=N, C=128),
                 roofline=dict(bound="tensor", achieved=tf, peak=pk["bf16"], unit="TFLOP/s", frac=tf / pk["bf16"],
                               traffic=None, kernel=kernel, algorithmic_flops=fl, peak_source=pk["src"] + " bf16 burst",
                               note=("N=47: launch/latency bound; tensor-pipe ceiling at this N is <= ~36% (SURVEY 7.3.1)"
@@ -534,25 +536,28 @@ def run_b200(args):
     torch.manual_seed(11 + rank)
     only = args.only
     tr = bench_train(crw, args, rank, world, local, pk) if only in ("all", "train") else None
-    wk = bench_walk(crw, args, world, pk) if only in ("all", "walk") else None
-    # the same fwd+bwd with precision = BF16X3 (warp-level MMAs on split bf16 pairs at this size); reported beside the fp32 kernels
-    wk_tc = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3,
-                       kernel_note="walk fwd+bwd kernels (BF16X3: mma.sync on bf16 hi/lo pairs), 8 launches") if only in ("all", "walk") else None
-    # the same again on the fused tcgen05 kernels (walk_fused.cu: one kernel per direction, one CTA per batch element; opt-in), at the
-    # config-2 batch and at a batch that fills the SMs, each beside the default BF16X3 engine
-    wk_fused = None
+    # the hot path alone.  Primary = what the train step runs: precision=BF16X3, which at this size takes the fused tcgen05 kernels
+    # (walk_fused.cu, role-split: one launch per direction); beside it the fp32 shared-memory kernels, the eight-kernel BF16X3 engine
+    # (CRW_WALK_FUSED=0), and both BF16X3 engines at a batch that fills the SMs (one CTA per batch element there)
+    wk = wk_f32 = wk_tc = wk_fused = None
     if only in ("all", "walk"):
-        wk_fused = {}
-        for Bf in (TRAIN["B"], 4 * TRAIN["B"]):
-            os.environ["CRW_WALK_FUSED"] = "1"
-            try:
-                rf = bench_walk(crw, args, world, pk, B=Bf, precision=crw.ops.PREC_BF16X3,
-                                kernel_note="walk_fused_fwd_kernel + walk_fused_bwd_kernel (tcgen05 bf16x3, TMA-fed, one CTA per batch element), 2 launches")
-            finally:
-                del os.environ["CRW_WALK_FUSED"]
-            rd = wk_tc if Bf == TRAIN["B"] else bench_walk(crw, args, world, pk, B=Bf, precision=crw.ops.PREC_BF16X3)
-            wk_fused[f"B{Bf}"] = dict(ms=rf["ms"], ms_eager_dispatch=rf["ms_eager"], launches=2, tflops=rf["roofline"]["achieved"],
-                                      frac=rf["roofline"]["frac"], default_engine_ms=rd["ms"], default_engine_ms_eager=rd["ms_eager"])
+        fused_note = "walk_fused_fwd_roles_kernel + walk_fused_bwd_roles_kernel (tcgen05 kind::f16 on bf16 hi/lo pairs, frames by TMA, tiles by bulk copies), 2 launches"
+        wk = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3, kernel_note=fused_note, launches=2)
+        wk_f32 = bench_walk(crw, args, world, pk)
+        os.environ["CRW_WALK_FUSED"] = "0"
+        try:
+            wk_tc = bench_walk(crw, args, world, pk, precision=crw.ops.PREC_BF16X3,
+                               kernel_note="walk fwd+bwd kernels (BF16X3: mma.sync on bf16 hi/lo pairs), 8 launches")
+            rd128 = bench_walk(crw, args, world, pk, B=4 * TRAIN["B"], precision=crw.ops.PREC_BF16X3)
+        finally:
+            del os.environ["CRW_WALK_FUSED"]
+        rf128 = bench_walk(crw, args, world, pk, B=4 * TRAIN["B"], precision=crw.ops.PREC_BF16X3,
+                           kernel_note="walk_fused_fwd_kernel + walk_fused_bwd_kernel (one CTA per batch element), 2 launches", launches=2)
+        wk_fused = {f"B{TRAIN['B']}": dict(ms=wk["ms"], ms_eager_dispatch=wk["ms_eager"], launches=2, kernels="role-split (4 CTAs per batch element)",
+                                          eight_kernel_engine_ms=wk_tc["ms"], eight_kernel_engine_ms_eager=wk_tc["ms_eager"]),
+                    f"B{4 * TRAIN['B']}": dict(ms=rf128["ms"], ms_eager_dispatch=rf128["ms_eager"], launches=2, kernels="one CTA per batch element",
+                                              tflops=rf128["roofline"]["achieved"], eight_kernel_engine_ms=rd128["ms"],
+                                              eight_kernel_engine_ms_eager=rd128["ms_eager"])}
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
     # the multi-GPU configurations BASELINE names (config 4: T=20 + UNet-as-encoder, data parallel; config 5: 64 radargrams of
     # 50k columns sharded over the ranks, strong scaling) ride in the same line as objects of their own
@@ -585,25 +590,24 @@ def run_b200(args):
             emit(dict(only=only, train=tr, walk=wk, labelprop=lp, train_cfg4=tr4, labelprop_cfg5=lp5))
         else:
             B, T = TRAIN["B"], TRAIN["T"]
-            hot = dict(what="fused walk fwd+bwd (crw_b200::walk_loss + backward), embeddings resident, CUDA-graph replay",
+            hot = dict(what="walk fwd+bwd (crw_b200::walk_loss + backward) as the train step runs it: precision=BF16X3 on the fused tcgen05 kernels "
+                            "(one launch per direction, role-split CTAs handing operand tiles over through L2; frames by TMA; softmax / lse-diag / "
+                            "softmax backward in the MMA epilogues; no N x N matrix through global memory between steps); embeddings resident, "
+                            "CUDA-graph replay; loss 1e-7 / dx 1e-5 of the fp64 oracle (tests/test_gpu_walk_fused.py)",
                        ms=wk["ms"], ms_eager_dispatch=wk["ms_eager"],
                        launches=wk["launches"], share_of_step=wk["ms"] / tr["ms_per_step"],
-                       bf16x3=dict(ms=wk_tc["ms"], tflops=wk_tc["roofline"]["achieved"], frac=wk_tc["roofline"]["frac"],
-                                   note="precision=BF16X3 (error-compensated bf16 pairs, fp32 accumulate; gradients within 1e-4 "
-                                        "of fp64); the train step above runs the fp32 kernels"))
-            hot["fused_tcgen05"] = dict(
-                what="opt-in (CRW_WALK_FUSED=1, precision=BF16X3): ONE tcgen05 kernel per direction, one CTA per batch element, frames by TMA, "
-                     "softmax / lse-diag / softmax-backward in the MMA epilogues, no N x N matrix through global memory between steps; "
-                     "loss 1e-7 / dx 1e-5 of the fp64 oracle (tests/test_gpu_walk_fused.py).  Latency bound by the per-element chain: it "
-                     "uses B of the 148 SMs, so it wins once the per-GPU batch fills them",
-                **wk_fused)
+                       fp32=dict(ms=wk_f32["ms"], ms_eager_dispatch=wk_f32["ms_eager"], launches=8,
+                                 note="precision=FP32: shared-memory-resident fp32 FMA kernels (round 1's train-step path)"),
+                       bf16x3_eight_kernels=dict(ms=wk_tc["ms"], ms_eager_dispatch=wk_tc["ms_eager"], launches=8,
+                                                 note="precision=BF16X3 with CRW_WALK_FUSED=0: shared-memory kernels, warp-level mma.sync"),
+                       fused_by_batch=wk_fused)
             line = dict(
                 metric="crw_train_radargrams_per_sec", value=tr["value"], unit="radargrams/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=tr["ms_per_step"], higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                scaling="weak", vs_baseline=None, dtype="bf16x3 walk (tcgen05, fp32 accumulate); encoder fp32", data="synthetic",
                 config=dict(workload="BASELINE config 2: CRW train step, B=32 per GPU, T=10 frames, 400-row radargram, "
                                      "32x32 patches overlap (24,0) -> N=47 nodes, ResNet[1,1,1,1] encoder (PyTorch fp32), "
-                                     "fused CUDA walk fwd+bwd (fp32), Adam; random-init weights",
+                                     "fused tcgen05 walk fwd+bwd (bf16x3, two launches), Adam; random-init weights",
                             global_batch=B * world, frames=T, nodes=tr["N"], tau=TRAIN["tau"],
                             parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of encoder grads)" if world > 1 else ""),
                             l2="4 rotating input batches (246 MB) > L2"),
@@ -620,8 +624,8 @@ def run_b200(args):
                     steps=tr4["steps"], warmup=tr4["warmup"], scaling="weak", e2e=tr4["e2e"], loss=tr4["loss"], clocks=tr4["clocks"],
                     config=dict(workload="BASELINE config 4: data-parallel CRW train step, B=32 per GPU, T=20 frames, N=47 nodes, "
                                          "UNet-as-encoder adapter (UNet(1,128) + global average pool, 2048-patch chunks under activation "
-                                         "checkpointing; NOT reference behaviour: the reference never feeds CRW from its UNet), fused CUDA "
-                                         "walk fwd+bwd (fp32), Adam",
+                                         "checkpointing; NOT reference behaviour: the reference never feeds CRW from its UNet), fused tcgen05 "
+                                         "walk fwd+bwd (bf16x3), Adam",
                                 global_batch=B * world, frames=20, nodes=tr4["N"],
                                 parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of 17.2 MB of encoder grads, 5 MB buckets)" if world > 1 else "")))
             if lp5 is not None:
@@ -829,7 +833,7 @@ def run_reference(args):
               f"autograd, Adam: scripts/train.py:56-72 verbatim) on the host cores, {threads} threads; s/step by threads: {every}")
     line = dict(impl="reference", metric="crw_train_radargrams_per_sec", value=value, unit="radargrams/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                scaling="weak", vs_baseline=None, dtype="bf16x3 walk (tcgen05, fp32 accumulate); encoder fp32", data="synthetic",
                 config=dict(workload="BASELINE config 2 (bounded CPU sample): " + sample),
                 cpu_baseline=dict(value=value, unit="radargrams/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="radargrams/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),

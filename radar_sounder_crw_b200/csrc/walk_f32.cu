@@ -368,6 +368,7 @@ bool walk_small_mma_supported(int N, int C);
 int walk_small_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
                        cudaStream_t st, bool mma);
 bool walk_fused_supported(int N, int C, int T);
+bool walk_fused_roles_apply(int B);
 size_t walk_fused_saved_bytes(int B, int T);
 int walk_fused_backward(const float* x, const void* saved, const float* dloss, const float* dA_or_null, int B, int T, int N, int C, float tau,
                         float* dx, void* scratch, cudaStream_t st);
@@ -386,16 +387,20 @@ size_t walk_tiles_scratch_extra_bytes(int B, int T, int N, int C);
 
 using namespace crw;
 
-// BF16X3 at the reference's sizes: the fused tcgen05 kernels (walk_fused.cu) put ONE CTA on each batch element, so their time does
-// not grow with the batch until it exceeds the SM count, while the eight shared-memory kernels spread every stage over B x T CTAs.
-// Measured at T = 10, N = 47 (CUDA-graph replay): B = 32: 0.190 vs 0.114 ms, B = 128: 0.220 vs 0.284 ms.  CRW_WALK_FUSED=1 / 0
-// forces the choice; unset, the fused kernels take batches of 96 and more.  (Forward and backward see the same B, T, N, C and
-// environment, hence the same `saved` layout.)
+// BF16X3 at the reference's sizes (N <= 64, C = 128): the fused tcgen05 kernels (walk_fused.cu), one launch per direction.
+//   4 B <= #SMs   role-split kernels: four CTAs per batch element (affinity producers / chain / cycle; chain / dA / per-frame dE) that
+//                 hand operand tiles over through L2 -- measured at B = 32, T = 10, N = 47 (CUDA-graph replay): 0.097 ms against
+//                 0.114 ms for the eight shared-memory kernels (0.132 ms fp32)
+//   B >= 96       one CTA per batch element: its time does not grow with the batch until it exceeds the SM count (B = 128: 0.220
+//                 vs 0.284 ms)
+//   in between    the eight shared-memory kernels with warp-level MMAs (walk_small.cu), which spread every stage over B x T CTAs
+// CRW_WALK_FUSED=1 / 0 forces the choice.  (Forward and backward see the same B, T, N, C and environment, hence the same layout
+// of `saved`.)
 static bool walk_use_fused(int B, int T, int N, int C) {
     if (!walk_fused_supported(N, C, T)) return false;
     const char* e = getenv("CRW_WALK_FUSED");
     if (e) return atoi(e) != 0;
-    return B >= 96;
+    return B >= 96 || walk_fused_roles_apply(B);
 }
 
 static inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

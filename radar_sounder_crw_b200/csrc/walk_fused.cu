@@ -1495,14 +1495,19 @@ bool walk_fused_supported(int N, int C, int T) { return N >= 8 && N <= 64 && C =
 size_t walk_fused_saved_bytes(int B, int T) { return wf::Layout(B, T).total + 1024; }
 
 // Role-split kernels (several CTAs per batch element, hand-over through L2): number of affinity producers per element, 0 = one CTA
-// per element.  A CTA only waits for CTAs with a smaller block index (dispatched before it) and producers wait for nobody, so the
-// launch may exceed one wave; beyond ~1.5 waves the extra CTAs buy nothing.  CRW_WALK_ROLES=<P> forces (0 = off).
+// per element.  Used while every CTA of the launch can be resident at once (four per element); a CTA only ever waits for CTAs with
+// a smaller block index and producers wait for nobody, so larger launches would not deadlock either, but they gain nothing (measured:
+// four producers per element, 192 CTAs at B = 32, 49.7 vs 42 us).  CRW_WALK_ROLES=<P> forces (0 = off).
 static int walk_fused_roles(int B, int sms) {
     const char* e = getenv("CRW_WALK_ROLES");
     if (e) { const int v = atoi(e); return v < 0 ? 0 : (v > 8 ? 8 : v); }
-    if (6 * B <= sms + sms / 2) return 4;
-    if (4 * B <= sms) return 2;
-    return 0;
+    return 4 * B <= sms ? 2 : 0;
+}
+bool walk_fused_roles_apply(int B) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return walk_fused_roles(B, sms) > 0;
 }
 
 static uint8_t* wf_align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023)); }
