@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(kThreads, 1) walk_fused_fwd_kernel(const __gri
 //   role P + 1  cycle: M_k = L_k R_k from the saved X_k: lse - diag, G_k, the loss
 // The only serial part left on one SM is the chain (one product + one 32-column epilogue per step).
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t rE = 0;                               // producer: E planes (64 KB) | chain: S tiles, two buffers | cycle: X, two buffers
-constexpr uint32_t rRaw = rE + 4 * kPlane128;            // producer: raw frames, two buffers (64 KB) | chain: X (32 KB) | cycle: G (16 KB)
+constexpr uint32_t rE = 0;                               // producer: E planes (64 KB) | chain: S tiles, three buffers, then X | cycle: X, two buffers
+constexpr uint32_t rRaw = rE + 4 * kPlane128;            // producer: raw frames, two buffers (64 KB) | cycle: G (16 KB)
 constexpr uint32_t rSS = rRaw + 8 * kTile64;             // producer: S tiles out (32 KB)
 constexpr uint32_t rAst = rSS + 4 * kTile64;             // producer: fp32 A_t staging (16 KB)
 constexpr uint32_t rEnd = rAst + 64 * 64 * 4;
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sb - tc::smem_u32(smem_raw));            // generic pointer to the aligned base
-    __shared__ uint64_t bar_ld[2], bar_mma, bar_st;
+    __shared__ uint64_t bar_ld[2], bar_mma, bar_st, bar_tile, bar_ld3[3];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_red[4][64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -522,6 +522,8 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         tc::mbar_init(&bar_ld[1], 1);
         tc::mbar_init(&bar_mma, 1);
         tc::mbar_init(&bar_st, 1);
+        tc::mbar_init(&bar_tile, 1);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(&bar_ld3[i], 1);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&xmap);
     }
@@ -624,21 +626,26 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
 #pragma unroll
             for (int q = 0; q < 4; ++q) bulk_store(dst + q * kTile64, sE + (uint32_t)q * kPlane128 + (uint32_t)(f & 1) * kTile64, kTile64);
         };
-        if (role < Tlast && is_iss) { if (tc::elect_one()) { issue_frame(role, 0); issue_frame(role + 1, 1); } __syncwarp(); }
-        for (int t = role; t < Tlast; t += P) {
-            ld_wait(0);
-            convert_frame(t, 0);
-            ld_wait(1);
-            convert_frame(t + 1, 1);
+        // a CONTIGUOUS range of affinities per producer: consecutive affinities share a frame, so only the range's first one converts two
+        // frames.  Raw buffer = frame parity; the next frame is fetched by TMA while this affinity's product and epilogue run.
+        const int per = (Tlast + P - 1) / P, t0 = role * per, t1 = min(Tlast, t0 + per);
+        if (t0 < t1 && is_iss) { if (tc::elect_one()) { issue_frame(t0, t0 & 1); issue_frame(t0 + 1, (t0 + 1) & 1); } __syncwarp(); }
+        for (int t = t0; t < t1; ++t) {
+            if (t == t0) {
+                ld_wait(t & 1);
+                convert_frame(t, t & 1);
+            }
+            ld_wait((t + 1) & 1);
+            convert_frame(t + 1, (t + 1) & 1);
             publish();
             if (is_st) { if (tc::elect_one()) {          // (waited for together with the S tiles at the end of this affinity, before the ring is rewritten)
-                save_frame(t);
+                if (t == t0) save_frame(t);
                 save_frame(t + 1);
                 bulk_commit();
             } __syncwarp(); }
             if (is_iss) { if (tc::elect_one()) {
                 tc::tc_fence_after();
-                if (t + P < Tlast) { issue_frame(t + P, 0); issue_frame(t + P + 1, 1); }
+                if (t + 1 < t1) issue_frame(t + 2, t & 1);               // (raw buffer t & 1 held frame t: converted)
                 mma3<false, false, 128>(tmem, ePlane(0, 0), ePlane(1, 0), ePlane(0, 0), ePlane(1, 0), 2, kPlane128, kPlane128, 0, true);
                 tc::umma_commit(&bar_mma);
             } __syncwarp(); }
@@ -697,53 +704,83 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         }
     } else if (role == P) {
         // ================= chain =================
-        const uint32_t sSSb = sb + rE, sX = sb + rRaw;                   // S tiles: two 32 KB buffers; X: hi, lo
+        // The serial role: per step one product pair and one 32-column epilogue.  Everything else is kept off its path: the S tiles are
+        // fetched up to two steps ahead (three buffers, only when already flagged), and the store warp runs on its own -- it waits for
+        // "X_k is written" (bar_tile), copies, says "the copy has left shared memory" (bar_st), completes, flags; the other nine warps
+        // synchronise among themselves on a named barrier.
+        const uint32_t sSSb = sb + rE, sX = sb + rE + 3 * (uint32_t)kSaveSS;      // S tiles: three 32 KB buffers; X: hi, lo
         const uint32_t tX = tmem;
-        auto load_ss = [&](int t, int buf) {         // issuer lane
-            flag_wait(flagp(0, t), err);
-            tc::mbar_arrive_expect_tx(&bar_ld[buf], (uint32_t)kSaveSS);
-            bulk_load(sSSb + (uint32_t)buf * (uint32_t)kSaveSS, p.ws + lay.step(b, t) + kSaveX, (uint32_t)kSaveSS, &bar_ld[buf]);
-        };
-        if (is_iss) { if (tc::elect_one()) load_ss(0, 0); __syncwarp(); }
-        for (int k = 1; k <= K; ++k) {
-            const int buf = (k - 1) & 1;
-            const uint32_t sSS = sSSb + (uint32_t)buf * (uint32_t)kSaveSS;
-            ld_wait(buf);
-            if (k == 1) {
-                // X_1 = [L_1 ; R_1^T] = [S'_0 ; I]: the rows of S'_0 are already operand rows (same swizzle): copy them
-                if (is_epi) {
-                    for (int i = tid; i < 2 * 512; i += 256) {           // 2 planes x 512 chunks of 16 bytes
-                        const int pl = i >> 9, cidx = i & 511;
-                        const uint4 q = lds128u(sSS + (uint32_t)(2 + pl) * kTile64 + (uint32_t)cidx * 16u);
-                        sts128(sX + (uint32_t)pl * kPlane128 + (uint32_t)cidx * 16u, q.x, q.y, q.z, q.w);
-                    }
-                    if (half == 1) {
-                        float e[32];
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) e[c] = (32 * ch + c == r && r < N) ? 1.0f : 0.0f;
-                        store_row32(sX, sX + kPlane128, 64 + r, ch, e);
-                    }
-                }
-                publish();
-            } else {
-                if (is_iss) { if (tc::elect_one()) {
-                    tc::tc_fence_after();
-                    mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);   // X . S'_{k-1}
-                    mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);               // X . S_{k-1}^T
-                    tc::umma_commit(&bar_mma);
-                    if (k < K) load_ss(k, k & 1);                        // under the MMAs: fetch the next S tiles
-                } __syncwarp(); }
-                mma_wait();
-                st_wait();                                               // the copy of X_{k-1} has left shared memory
-                if (is_epi) {
-                    float x[32];
-                    tmem_ld32(tX + lane_base + (uint32_t)(half * 64 + ch * 32), x);
-                    store_row32(sX, sX + kPlane128, row, ch, x);
-                }
-                publish();
+        if (is_st) {
+            for (int k = 1; k <= K; ++k) {
+                tc::mbar_wait(&bar_tile, (k - 1) & 1);
+                if (tc::elect_one()) store_tile(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX, flagp(1, k));      // the cycle CTA is waiting for X_k
+                __syncwarp();
             }
-            if (k == 1 && K > 1 && is_iss) { if (tc::elect_one()) load_ss(1, 1); __syncwarp(); }
-            if (is_st) { if (tc::elect_one()) store_tile(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX, flagp(1, k)); __syncwarp(); }   // the cycle CTA is waiting for X_k
+        } else {
+            auto sync9 = [&]() {                     // operand tiles written / accumulators read -> visible; the nine working warps only
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+            };
+            int next_load = 0;                       // S tiles 0 .. next_load - 1 are in flight or loaded (issuer lane's view)
+            auto try_loads = [&](int upto, bool must) {      // issuer lane: fetch S_t for t < upto in order; `must`: wait for the flags
+                while (next_load < upto && next_load < K) {
+                    if (!must && !flag_peek(flagp(0, next_load))) break;
+                    flag_wait(flagp(0, next_load), err);
+                    const int buf = next_load % 3;
+                    tc::mbar_arrive_expect_tx(&bar_ld3[buf], (uint32_t)kSaveSS);
+                    bulk_load(sSSb + (uint32_t)buf * (uint32_t)kSaveSS, p.ws + lay.step(b, next_load) + kSaveX, (uint32_t)kSaveSS, &bar_ld3[buf]);
+                    ++next_load;
+                }
+            };
+            uint32_t ld3_phase[3] = {0u, 0u, 0u};
+            auto ld3_wait = [&](int buf) {
+                tc::mbar_wait(&bar_ld3[buf], ld3_phase[buf] & 1);
+                ++ld3_phase[buf];
+            };
+            if (is_iss) { if (tc::elect_one()) { try_loads(1, true); try_loads(3, false); } __syncwarp(); }
+            for (int k = 1; k <= K; ++k) {
+                const int buf = (k - 1) % 3;
+                const uint32_t sSS = sSSb + (uint32_t)buf * (uint32_t)kSaveSS;
+                if (is_iss) { if (tc::elect_one()) try_loads(k, true); __syncwarp(); }      // (S_{k-1}: waited for here, where nothing else is held up)
+                ld3_wait(buf);
+                if (k == 1) {
+                    // X_1 = [L_1 ; R_1^T] = [S'_0 ; I]: the rows of S'_0 are already operand rows (same swizzle): copy them
+                    if (is_epi) {
+                        for (int i = tid; i < 2 * 512; i += 256) {           // 2 planes x 512 chunks of 16 bytes
+                            const int pl = i >> 9, cidx = i & 511;
+                            const uint4 q = lds128u(sSS + (uint32_t)(2 + pl) * kTile64 + (uint32_t)cidx * 16u);
+                            sts128(sX + (uint32_t)pl * kPlane128 + (uint32_t)cidx * 16u, q.x, q.y, q.z, q.w);
+                        }
+                        if (half == 1) {
+                            float e[32];
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) e[c] = (32 * ch + c == r && r < N) ? 1.0f : 0.0f;
+                            store_row32(sX, sX + kPlane128, 64 + r, ch, e);
+                        }
+                    }
+                    sync9();
+                    if (is_iss) { if (tc::elect_one()) { tc::mbar_arrive(&bar_tile); try_loads(4, false); } __syncwarp(); }
+                } else {
+                    if (is_iss) { if (tc::elect_one()) {
+                        tc::tc_fence_after();
+                        mma3<false, true>(tX, sX, sX + kPlane128, sSS + 2 * kTile64, sSS + 3 * kTile64, 1, 0, 0, 0, true);   // X . S'_{k-1}
+                        mma3<false, false>(tX + 64u, sX, sX + kPlane128, sSS, sSS + kTile64, 1, 0, 0, 0, true);               // X . S_{k-1}^T
+                        tc::umma_commit(&bar_mma);
+                        try_loads(k + 2, false);         // under the MMAs: later S tiles whose producers are already done (never the
+                                                         // buffer these MMAs read); no waiting here -- the epilogue needs this warp
+                    } __syncwarp(); }
+                    mma_wait();
+                    st_wait();                                               // the copy of X_{k-1} has left shared memory
+                    if (is_epi) {
+                        float x[32];
+                        tmem_ld32(tX + lane_base + (uint32_t)(half * 64 + ch * 32), x);
+                        store_row32(sX, sX + kPlane128, row, ch, x);
+                    }
+                    sync9();
+                    if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
+                }
+            }
         }
     } else {
         // ================= cycle =================
@@ -755,16 +792,18 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
             bulk_load(sXb + (uint32_t)buf * (uint32_t)kSaveX, p.ws + lay.step(b, k), (uint32_t)kSaveX, &bar_ld[buf]);
         };
         float loss_acc = 0.0f;
-        if (is_iss) { if (tc::elect_one()) load_x(1, 1); __syncwarp(); }
+        int x_issued = 0;                            // (issuer lane) X_k has been fetched for k <= x_issued
         for (int k = 1; k <= K; ++k) {
             const int buf = k & 1;
             const uint32_t sX = sXb + (uint32_t)buf * (uint32_t)kSaveX;
+            if (is_iss) { if (tc::elect_one()) { if (x_issued < k) { load_x(k, buf); x_issued = k; } } __syncwarp(); }      // (waits for the flag here)
             ld_wait(buf);
             if (is_iss) { if (tc::elect_one()) {
                 tc::tc_fence_after();
                 mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);    // M_k = L_k R_k
                 tc::umma_commit(&bar_mma);
-                if (k < K) load_x(k + 1, (k + 1) & 1);                   // (its buffer was read by the product before last: complete)
+                // the next X under this step's epilogue -- only if it is already there: the epilogue needs this warp at its barriers
+                if (k < K && flag_peek(flagp(1, k + 1))) { load_x(k + 1, (k + 1) & 1); x_issued = k + 1; }
             } __syncwarp(); }
             mma_wait();
             if (k >= 2) st_wait();                                       // the copy of G_{k-1} has left shared memory
@@ -791,8 +830,14 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
                 store_row32(sG, sG + kTile64, r, ch, m);
             }
             publish();
-            if (is_st) { if (tc::elect_one()) store_tile(p.ws + lay.step(b, k) + kSaveX + kSaveSS, sG, (uint32_t)kSaveG, nullptr); __syncwarp(); }
+            if (is_st) { if (tc::elect_one()) {      // nobody waits for G_k in this launch: only "the copy has left shared memory" matters per step
+                bulk_store(p.ws + lay.step(b, k) + kSaveX + kSaveSS, sG, (uint32_t)kSaveG);
+                bulk_commit();
+                bulk_wait_read();
+                tc::mbar_arrive(&bar_st);
+            } __syncwarp(); }
         }
+        if (is_st) { if (tc::elect_one()) bulk_wait_all(); __syncwarp(); }
         __syncthreads();
         if (is_epi && half == 0) s_red[ch][r] = loss_acc;
         __syncthreads();
@@ -1143,7 +1188,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(B
     const BwdParams& p = pp.q;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sb = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-    __shared__ uint64_t bar_ld[2], bar_mma, bar_st;
+    __shared__ uint64_t bar_ld[2], bar_mma, bar_st, bar_tile;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_red[4][64];
     __shared__ int s_next;
@@ -1161,6 +1206,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(B
         tc::mbar_init(&bar_ld[1], 1);
         tc::mbar_init(&bar_mma, 1);
         tc::mbar_init(&bar_st, 1);
+        tc::mbar_init(&bar_tile, 1);
         tc::fence_barrier_init();
     }
     tc::tc_fence_before();
@@ -1220,51 +1266,66 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(B
         // (development: role switched off)
     } else if (role == 0) {
         // ================= chain =================
+        // (the serial role; the store warp runs on its own as in the forward's chain: bar_tile "Y is written" -> copy -> bar_st "the copy
+        // has left shared memory" -> completion -> flag)
         const uint32_t sY = sb + 2 * (uint32_t)kSaveStep;                // blocks: two 80 KB buffers at 0; Y: hi, lo
         const uint32_t Y_hi = sY, Y_lo = sY + kPlane128;
-        auto blk = [&](int j) { return sb + (uint32_t)(j & 1) * (uint32_t)kSaveStep; };
-        auto load_block = [&](int j) {               // issuer lane: [X_j | S_j, S'_j | G_j] of the forward's workspace
-            tc::mbar_arrive_expect_tx(&bar_ld[j & 1], (uint32_t)kSaveStep);
-            bulk_load(blk(j), p.ws + lay.step(b, j), (uint32_t)kSaveStep, &bar_ld[j & 1]);
-        };
-        if (is_iss) { if (tc::elect_one()) { load_block(K); if (K >= 2) load_block(K - 1); } __syncwarp(); }
-        ld_wait(K & 1);
-        if (is_iss) { if (tc::elect_one()) {             // Y_K = [G_K R_K^T ; G_K^T L_K]
-            const uint32_t X_hi = blk(K), X_lo = X_hi + kPlane128, G_hi = X_hi + (uint32_t)(kSaveX + kSaveSS), G_lo = G_hi + kTile64;
-            tc::tc_fence_after();
-            mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
-            mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
-            tc::umma_commit(&bar_mma);
-        } __syncwarp(); }
-        mma_wait();
-        if (is_epi) {
-            float y[32];
-            tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
-            store_row32(Y_hi, Y_lo, row, ch, y);
-        }
-        publish();
-        if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Y(b, K), sY, (uint32_t)kSaveX, flagp(0, K)); __syncwarp(); }
-        for (int k = K; k >= 2; --k) {
-            ld_wait((k - 1) & 1);
-            if (is_iss) { if (tc::elect_one()) {         // Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]
-                const uint32_t X_hi = blk(k - 1), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX, G_hi = S_hi + (uint32_t)kSaveSS, G_lo = G_hi + kTile64;
+        if (is_st) {
+            for (int k = K; k >= 1; --k) {
+                tc::mbar_wait(&bar_tile, (K - k) & 1);
+                if (tc::elect_one()) store_tile(pp.scratch + sc.Y(b, k), sY, (uint32_t)kSaveX, flagp(0, k));
+                __syncwarp();
+            }
+        } else {
+            auto sync9 = [&]() {
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+            };
+            auto blk = [&](int j) { return sb + (uint32_t)(j & 1) * (uint32_t)kSaveStep; };
+            auto load_block = [&](int j) {               // issuer lane: [X_j | S_j, S'_j | G_j] of the forward's workspace
+                tc::mbar_arrive_expect_tx(&bar_ld[j & 1], (uint32_t)kSaveStep);
+                bulk_load(blk(j), p.ws + lay.step(b, j), (uint32_t)kSaveStep, &bar_ld[j & 1]);
+            };
+            if (is_iss) { if (tc::elect_one()) { load_block(K); if (K >= 2) load_block(K - 1); } __syncwarp(); }
+            ld_wait(K & 1);
+            if (is_iss) { if (tc::elect_one()) {             // Y_K = [G_K R_K^T ; G_K^T L_K]
+                const uint32_t X_hi = blk(K), X_lo = X_hi + kPlane128, G_hi = X_hi + (uint32_t)(kSaveX + kSaveSS), G_lo = G_hi + kTile64;
                 tc::tc_fence_after();
-                mma3<false, false>(tmem, Y_hi, Y_lo, S_hi + 2 * kTile64, S_hi + 3 * kTile64, 1, 0, 0, 0, true);             // dL_k S'_{k-1}^T
-                mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, false);                    // G_{k-1} R_{k-1}^T
-                mma3<false, true>(tmem + 64u, Y_hi, Y_lo, S_hi, S_hi + kTile64, 1, 0, 0, 0, true);                          // dR_k^T S_{k-1}
-                mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, false);         // G_{k-1}^T L_{k-1}
+                mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, true);
+                mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, true);
                 tc::umma_commit(&bar_mma);
-                if (k >= 3) load_block(k - 2);       // (its buffer was read by the products of the step before: complete)
             } __syncwarp(); }
             mma_wait();
-            st_wait();                                                   // the copy of Y_k has left shared memory
             if (is_epi) {
                 float y[32];
                 tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
                 store_row32(Y_hi, Y_lo, row, ch, y);
             }
-            publish();
-            if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Y(b, k - 1), sY, (uint32_t)kSaveX, flagp(0, k - 1)); __syncwarp(); }
+            sync9();
+            if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
+            for (int k = K; k >= 2; --k) {
+                ld_wait((k - 1) & 1);
+                if (is_iss) { if (tc::elect_one()) {         // Y_{k-1} = own_{k-1} + Y_k [S'_{k-1}^T | S_{k-1}]
+                    const uint32_t X_hi = blk(k - 1), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX, G_hi = S_hi + (uint32_t)kSaveSS, G_lo = G_hi + kTile64;
+                    tc::tc_fence_after();
+                    mma3<false, false>(tmem, Y_hi, Y_lo, S_hi + 2 * kTile64, S_hi + 3 * kTile64, 1, 0, 0, 0, true);             // dL_k S'_{k-1}^T
+                    mma3<false, true>(tmem, G_hi, G_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, 0, false);                    // G_{k-1} R_{k-1}^T
+                    mma3<false, true>(tmem + 64u, Y_hi, Y_lo, S_hi, S_hi + kTile64, 1, 0, 0, 0, true);                          // dR_k^T S_{k-1}
+                    mma3<true, true>(tmem + 64u, G_hi - kTile64, G_lo - kTile64, X_hi, X_lo, 1, 0, 0, kTile64, false);         // G_{k-1}^T L_{k-1}
+                    tc::umma_commit(&bar_mma);
+                    if (k >= 3) load_block(k - 2);       // (its buffer was read by the products of the step before: complete)
+                } __syncwarp(); }
+                mma_wait();
+                st_wait();                                                   // the copy of Y_k has left shared memory
+                if (is_epi) {
+                    float y[32];
+                    tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), y);
+                    store_row32(Y_hi, Y_lo, row, ch, y);
+                }
+                sync9();
+                if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
+            }
         }
     } else if (role == 1) {
         // ================= dA =================
@@ -1281,79 +1342,93 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(B
             tc::mbar_arrive_expect_tx(&bar_ld[1], (uint32_t)(kSaveX + kSaveSS));
             bulk_load(sXS + (uint32_t)(j & 1) * (uint32_t)(kSaveX + kSaveSS), p.ws + lay.step(b, j), (uint32_t)(kSaveX + kSaveSS), &bar_ld[1]);
         };
-        if (is_iss) { if (tc::elect_one()) { load_xs(K - 1); load_y(K); } __syncwarp(); }
-        if (p.dA) {
-            // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
-            if (is_epi) {
-                float v[32];
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = 0.0f;
-                if (half == 1 && r < N) {
-                    const float* src = p.dA + (((size_t)b * (T - 1) + (T - 2)) * N + r) * N;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (32 * ch + c < N) v[c] = p.inv_tau * __ldg(src + 32 * ch + c);
-                }
-                store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, v);
+        if (is_st) {
+            // the store warp on its own: "T_k is written" (bar_tile) -> copy -> "the copy has left shared memory" (bar_st) -> completion -> flag
+            int n = 0;
+            for (int k = k_first; k >= 1; --k, ++n) {
+                tc::mbar_wait(&bar_tile, n & 1);
+                if (tc::elect_one()) store_tile(pp.scratch + sc.Tt(b, k), sT, (uint32_t)kSaveX, flagp(1, k));       // the dE CTAs are waiting for T_k
+                __syncwarp();
             }
-            publish();
-            if (is_st) { if (tc::elect_one()) {
-                bulk_store(pp.scratch + sc.Tt(b, K + 1), sT, (uint32_t)kSaveX);
-                bulk_commit();
-                bulk_wait_all();
-                flag_set(flagp(1, K + 1));
-            } __syncwarp(); }
-            __syncthreads();
-        }
-        for (int k = K; k >= 1; --k) {
-            const uint32_t Y_hi = sYb + (uint32_t)(k & 1) * (uint32_t)kSaveX, Y_lo = Y_hi + kPlane128;
-            const uint32_t X_hi = sXS + (uint32_t)((k - 1) & 1) * (uint32_t)(kSaveX + kSaveSS), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX;
-            ld_wait(0);
-            ld_wait(1);
-            if (is_iss) { if (tc::elect_one()) {
-                tc::tc_fence_after();
-                if (k >= 2) {
-                    mma3<true, true>(tmem, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
-                    mma3<true, true>(tmem + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
-                }
-                tc::umma_commit(&bar_mma);
-                if (k >= 2) { load_xs(k - 2); load_y(k - 1); }
-            } __syncwarp(); }
-            mma_wait();
-            float d[32], P[32];
-            float s = 0.0f;
-            if (is_epi) {
-                if (k >= 2) {
-                    tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), d);
-                } else if (half == 0) {
-                    load_row32(Y_hi, Y_lo, r, ch, d);                     // L_0 = I: dS'_0 = dL_1
-                } else {
+        } else {
+            auto sync9 = [&]() {
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+            };
+            int y_low = K + 1;                       // (issuer lane) Y_k has been fetched for k >= y_low
+            if (is_iss) { if (tc::elect_one()) load_xs(K - 1); __syncwarp(); }
+            if (p.dA) {
+                // pseudo-step k = K + 1 (t = T - 2): only the gradient that arrives through the returned A
+                if (is_epi) {
+                    float v[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) d[c] = 0.0f;             // R_1 = I is not a product: dS_0 = 0
-                }
-                if (half == 0) load_row32(S_hi + 2 * kTile64, S_hi + 3 * kTile64, r, ch, P);
-                else load_row32(S_hi, S_hi + kTile64, r, ch, P);
+                    for (int c = 0; c < 32; ++c) v[c] = 0.0f;
+                    if (half == 1 && r < N) {
+                        const float* src = p.dA + (((size_t)b * (T - 1) + (T - 2)) * N + r) * N;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) s = fmaf(P[c], d[c], s);
-                s_red[half * 2 + ch][r] = s;
+                        for (int c = 0; c < 32; ++c)
+                            if (32 * ch + c < N) v[c] = p.inv_tau * __ldg(src + 32 * ch + c);
+                    }
+                    store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, v);
+                }
+                sync9();
+                if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
             }
-            tc::tc_fence_before();
-            __syncthreads();
-            if (k < K) st_wait();                                        // the copy of T_{k+1} has left shared memory
-            if (is_epi) {
-                s += s_red[half * 2 + (1 - ch)][r];
+            for (int k = K; k >= 1; --k) {
+                const uint32_t Y_hi = sYb + (uint32_t)(k & 1) * (uint32_t)kSaveX, Y_lo = Y_hi + kPlane128;
+                const uint32_t X_hi = sXS + (uint32_t)((k - 1) & 1) * (uint32_t)(kSaveX + kSaveSS), X_lo = X_hi + kPlane128, S_hi = X_hi + (uint32_t)kSaveX;
+                if (is_iss) { if (tc::elect_one()) { if (y_low > k) { load_y(k); y_low = k; } } __syncwarp(); }       // (waits for the flag here)
+                ld_wait(0);
+                ld_wait(1);
+                if (is_iss) { if (tc::elect_one()) {
+                    tc::tc_fence_after();
+                    if (k >= 2) {
+                        mma3<true, true>(tmem, X_hi, X_lo, Y_hi, Y_lo, 1, 0, 0, kTile64, true);                              // L_{k-1}^T dL_k
+                        mma3<true, true>(tmem + 64u, Y_hi, Y_lo, X_hi + kTile64, X_lo + kTile64, 1, 0, 0, kTile64, true);    // dR_k R_{k-1}^T
+                    }
+                    tc::umma_commit(&bar_mma);
+                    if (k >= 2) {
+                        load_xs(k - 2);
+                        if (flag_peek(flagp(0, k - 1))) { load_y(k - 1); y_low = k - 1; }    // (only if it is already there)
+                    }
+                } __syncwarp(); }
+                mma_wait();
+                float d[32], P[32];
+                float s = 0.0f;
+                if (is_epi) {
+                    if (k >= 2) {
+                        tmem_ld32(tmem + lane_base + (uint32_t)(half * 64 + ch * 32), d);
+                    } else if (half == 0) {
+                        load_row32(Y_hi, Y_lo, r, ch, d);                     // L_0 = I: dS'_0 = dL_1
+                    } else {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) d[c] = coef * P[c] * (d[c] - s);
-                if (half == 1 && p.dA && r < N) {
-                    const float* src = p.dA + (((size_t)b * (T - 1) + (k - 1)) * N + r) * N;
+                        for (int c = 0; c < 32; ++c) d[c] = 0.0f;             // R_1 = I is not a product: dS_0 = 0
+                    }
+                    if (half == 0) load_row32(S_hi + 2 * kTile64, S_hi + 3 * kTile64, r, ch, P);
+                    else load_row32(S_hi, S_hi + kTile64, r, ch, P);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (32 * ch + c < N) d[c] = fmaf(p.inv_tau, __ldg(src + 32 * ch + c), d[c]);
+                    for (int c = 0; c < 32; ++c) s = fmaf(P[c], d[c], s);
+                    s_red[half * 2 + ch][r] = s;
                 }
-                store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, d);   // T1 (rows of dA) on top, T2 (rows of dA^T) below
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 288;" ::: "memory");
+                if (k < K || p.dA) st_wait();                                // the copy of T_{k+1} has left shared memory
+                if (is_epi) {
+                    s += s_red[half * 2 + (1 - ch)][r];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) d[c] = coef * P[c] * (d[c] - s);
+                    if (half == 1 && p.dA && r < N) {
+                        const float* src = p.dA + (((size_t)b * (T - 1) + (k - 1)) * N + r) * N;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (32 * ch + c < N) d[c] = fmaf(p.inv_tau, __ldg(src + 32 * ch + c), d[c]);
+                    }
+                    store_row32(T_hi, T_lo, (half == 1 ? 0 : 64) + r, ch, d);   // T1 (rows of dA) on top, T2 (rows of dA^T) below
+                }
+                sync9();
+                if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
             }
-            publish();
-            if (is_st) { if (tc::elect_one()) store_tile(pp.scratch + sc.Tt(b, k), sT, (uint32_t)kSaveX, flagp(1, k)); __syncwarp(); }   // the dE CTAs are waiting for T_k
         }
     } else {
         // ================= dE (frames) =================
