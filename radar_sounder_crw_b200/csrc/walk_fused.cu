@@ -1,15 +1,22 @@
-// walk_fused.cu -- the training walk at the reference's own sizes (N <= 64 nodes, C = 128 channels) as ONE tcgen05 kernel per
-// direction, one CTA per batch element.
+// walk_fused.cu -- the training walk at the reference's own sizes (N <= 64 nodes, C = 128 channels) on tcgen05: ONE launch per
+// direction.
 //
-// Replaces src/model.py:22-46 (normalise, stride-1 affinities / tau, palindrome walk, cycle cross-entropy) and its autograd with
-//   walk_fused_fwd_kernel   frames arrive by TMA (cp.async.bulk.tensor, fp32, SWIZZLE_128B), are normalised and split into
-//                           bf16 hi / lo planes in the UMMA K-major layout; every product of the walk is a tcgen05.mma
-//                           (kind::f16 on the error-compensated pairs: hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) whose
-//                           epilogue -- temperature, the two row softmaxes, lse - diag -- works on the accumulator row a
-//                           thread owns and writes the NEXT product's operand straight back into shared memory.  No N x N
-//                           matrix goes through global memory between steps; what the reverse pass needs is saved as
-//                           ready-made operand tiles with bulk copies (cp.async.bulk shared -> global).
-//   walk_fused_bwd_kernel   the reverse pass over the same tiles (bulk copies global -> shared), one launch.
+// Replaces src/model.py:22-46 (normalise, stride-1 affinities / tau, palindrome walk, cycle cross-entropy) and its autograd.
+// Common to all kernels: frames arrive by TMA (cp.async.bulk.tensor, fp32, SWIZZLE_128B), are normalised and split into bf16
+// hi / lo rows in the UMMA K-major layout; every product of the walk is a tcgen05.mma (kind::f16 on the error-compensated pairs:
+// hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM) whose epilogue -- temperature, the two row softmaxes, lse - diag, softmax
+// backward, F.normalize backward -- works on the accumulator row a thread owns and writes the NEXT product's operand straight back
+// into shared memory.  No N x N matrix is re-laid-out or re-read by a later launch: what another CTA or the reverse pass needs
+// travels as ready-made operand tiles by bulk copies (cp.async.bulk shared <-> global, L2-resident).
+//   walk_fused_fwd_kernel / walk_fused_bwd_kernel              one CTA per batch element (batches that fill the SMs: B >= 96)
+//   walk_fused_fwd_roles_kernel / walk_fused_bwd_roles_kernel  four CTAs per batch element, each with one ROLE, for batches that would
+//        leave SMs idle (4 B <= #SMs; BASELINE config 2: B = 32).  Forward: two affinity producers (contiguous ranges of t) -> chain
+//        (X_k) -> cycle (M_k, loss, G_k).  Backward: chain (Y_k) -> dA (softmax backward, the tile [T1 ; T2]) -> two dE CTAs (per
+//        frame: four N = 128 products, F.normalize backward, dx).  A consumer waits for a producer's tile with an acquire spin on a
+//        flag the producer releases after its bulk store completed; a CTA only ever waits for CTAs with a smaller block index, and
+//        producers wait for nobody.  Only the chains are serial: one product pair and one 32-column epilogue per step.
+//        Warps: 0-7 epilogues (warps w and w + 4 share accumulator rows 32 (w & 3) .., 32 columns each), 8 issues TMA / bulk loads
+//        and MMAs, 9 issues the bulk stores, waits for their completion and raises the flags.
 // All 128 TMEM lanes are used by stacking two 64-row problems in one tile:
 //   affinity   rows = [E_a ; E_b] (the two frames in the two slots of the ring): lanes 0-63 x columns 0-63 hold E_a E_b^T,
 //              lanes 64-127 x columns 64-127 hold E_b E_a^T -- A_t and A_t^T, so that BOTH softmaxes of model.py:44 are row
