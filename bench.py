@@ -472,6 +472,9 @@ def bench_labelprop(crw, args, rank, world, pk, lp_config=None):
     if bf16x3_path is not None:
         bf16x3_path["label_agreement_with_primary"] = float((labels_b == res[0]).float().mean().item())
     ms_e2e = timed_loop(lp_step_e2e, steps, 3, world, flush=flush)
+    pipeline = None
+    if not cfg5 and args.lp_precision != "fp32":
+        pipeline = bench_lp_pipeline(crw, args, world, flush, Tl, Nl, M)
     LP = lp_saved
     cols = R * Tl * COLS_PER_FRAME
     if cfg5:
@@ -498,7 +501,7 @@ def bench_labelprop(crw, args, rank, world, pk, lp_config=None):
         roofline_tensor=dict(bound="tensor", achieved=dense / (ms * 1e-3) / 1e12, peak=pk["bf16"], unit="TFLOP/s",
                              frac=dense / (ms * 1e-3) / 1e12 / pk["bf16"], algorithmic_flops=dense,
                              note="dense (ctx+1) N^2 C 2 per query frame; 41 % of it lies inside the radius band; executed once (fp16 filter)"),
-        gpu_launches=7 * steps, steps=steps, bf16x3_path=bf16x3_path, bit_exact=True,
+        gpu_launches=7 * steps, steps=steps, bf16x3_path=bf16x3_path, bit_exact=True, pipeline_e2e=pipeline,
         dtype="fp16 tensor-core filter + fp32 refine (results = fp32 pinned order)" if args.lp_precision != "fp32" else "f32",
         frames=Tl, fp32_path=fp32_path,
         scaling="strong" if cfg5 else "weak",
@@ -507,6 +510,48 @@ def bench_labelprop(crw, args, rank, world, pk, lp_config=None):
                               "BASELINE config 3: 400x20000-column radargram per GPU -> T=1250 frames x N=49 nodes x C=128, "
                               "M=4, ctx=20, k=10, radius=12, temp=0.07, mode=ref_exact"),
                     l2="flushed between iterations (256 MB write)"))
+
+
+def bench_lp_pipeline(crw, args, world, flush, Tl, Nl, M):
+    """The reference's real call pattern for one radargram (scripts/test/test_all.py:91-96): host radargram + host segmentation ->
+    RGDataset (HBM) -> frames -> encoder (PyTorch Resnet, eval) -> propagate -> nearest upsample -> label map back on the host.
+    The encoder is out of scope as a kernel and dominates; reported so that the hot path's end-to-end weight is on record."""
+    H, Wc = LP["rows"], LP["cols"]
+    g = torch.Generator().manual_seed(5)
+    rg_host = torch.randn(H, Wc, generator=g).pin_memory()
+    seg_host = torch.randint(0, M, (H, Wc), generator=g).float().pin_memory()
+    enc = crw.Resnet(pos_embed=False).cuda().eval()
+    lp = crw.LabelPropVOS_CRW({"CXT_SIZE": LP["ctx"], "RADIUS": LP["radius"], "TEMP": LP["temp"], "KNN": LP["k"]})
+    out = [None]
+    t_enc = [0.0]
+
+    def step(i):
+        rg = rg_host.cuda(non_blocking=True)
+        seg = seg_host.cuda(non_blocking=True)
+        ds = crw.RGDataset(rg, length=Tl, dim=LP["patch"], overlap=LP["overlap"])
+        seq = ds[0]                                                        # [T,N,h,w], one item = the whole radargram
+        pred, _, _ = crw.propagate(seq, seg[:, :LP["patch"][1]], enc, lp, M, False, False)
+        up = crw.ops.labels_upsample(pred.t().contiguous().to(torch.int32)[None], H, Wc)
+        out[0] = up.cpu()                                                  # D2H of the label map
+
+    ms = timed_loop(step, max(2, min(args.steps, 5)), 2, world, flush=flush)
+
+    # the encoder's share, timed alone on the same frames
+    ds = crw.RGDataset(rg_host.cuda(), length=Tl, dim=LP["patch"], overlap=LP["overlap"])
+    seq = ds[0]
+    x = seq.reshape(-1, LP["patch"][0], LP["patch"][1]).unsqueeze(1)
+
+    def enc_step(i):
+        with torch.no_grad():
+            enc(x)
+
+    ms_enc = timed_loop(enc_step, max(2, min(args.steps, 5)), 2, world)
+    cols = Wc * world
+    return dict(value=cols / (ms * 1e-3), unit="columns/s", ms_per_step=ms, encoder_ms=ms_enc,
+                h2d_bytes_per_step=int(rg_host.numel() * 4 + seg_host.numel() * 4), d2h_bytes_per_step=int(H * Wc * 4),
+                what="host radargram + segmentation -> RGDataset -> frames -> Resnet encoder (PyTorch, eval, fp32) -> propagate (exact tensor "
+                     "path) -> nearest upsample -> label map on the host; reference call pattern scripts/test/test_all.py:91-96, one item = the "
+                     "whole radargram; includes the horizontality metric's D2H and (no ruptures here) no change-point search")
 
 
 def lp_call_traffic(cfg5, lp_precision):
