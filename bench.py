@@ -264,7 +264,7 @@ def walk_flops(B, T, N, C):
 def bench_train(crw, args, rank, world, local, pk, cfg4=False):
     """BASELINE config 2: full train step (PyTorch encoder + fused CUDA walk fwd/bwd + Adam).
     cfg4: BASELINE config 4 -- T=20 frames and the UNet-as-encoder adapter (UNet(1,128) + global average pool; NOT reference
-    behaviour, see encoder.UNetEncoder), B=32 per GPU, DDP all-reduce of the 17.2 MB of gradients."""
+    behaviour, see encoder.UNetEncoder), B=32 per GPU, all-reduce of the 17.2 MB of gradients."""
     import torch.distributed as dist  # noqa: F401
     B, T, tau = TRAIN["B"], (20 if cfg4 else TRAIN["T"]), TRAIN["tau"]
     steps = max(2, min(args.steps, 4)) if cfg4 else args.steps
@@ -283,9 +283,16 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
     # the walk runs on the fused tcgen05 kernels (precision=BF16X3: error-compensated bf16 pairs, fp32 accumulate -- BASELINE config 2's
     # "bf16 walk"; loss 1e-7 / gradients 1e-5 of the fp64 oracle)
     model = crw.CRW(encoder, tau, False, need_A=False, precision=crw.ops.PREC_BF16X3)
-    if world > 1:
+    fg = None
+    if world > 1 and os.environ.get("CRW_BENCH_DDP"):
+        # DistributedDataParallel, ~4 buckets of the 19.9 MB of gradients; no per-step broadcast of the batch-norm running statistics
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                          bucket_cap_mb=5)          # ~4 buckets of the 19.9 MB of gradients: the all-reduce overlaps backward
+                                                          bucket_cap_mb=int(os.environ.get("CRW_BENCH_BUCKET_MB", "5")),
+                                                          broadcast_buffers=bool(int(os.environ.get("CRW_BENCH_DDP_BCAST", "0"))))
+    elif world > 1:
+        # default: the parameters' gradients are views of ONE flat buffer, averaged by one NCCL all-reduce after backward
+        # (parallel.FlatGradients): no hooks, no buckets, no copies -- measured against DDP in DESIGN.md section 5
+        fg = crw.parallel.FlatGradients(model.parameters(), world)
     opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"], fused=True)   # train-loop glue
     last_loss = [None]
 
@@ -294,8 +301,13 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         if not seq.is_cuda:
             seq = seq.cuda(non_blocking=True)
         loss, _ = model(seq)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
+        if fg is not None:
+            fg.zero()
+            loss.backward()
+            fg.reduce()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
         opt.step()
         last_loss[0] = loss
 
@@ -326,9 +338,15 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         enqueue_copy(i + 1)                                        # next step's input, overlapped with this step
         torch.cuda.current_stream().wait_event(ready[slot])
         loss, _ = model(dev_buf[slot])
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        consumed[slot].record()
+        if fg is not None:
+            fg.zero()
+            loss.backward()
+            consumed[slot].record()
+            fg.reduce()
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            consumed[slot].record()
         opt.step()
         last_loss[0] = loss.item()                                 # D2H read of the step's result
 
@@ -654,7 +672,7 @@ def run_b200(args):
                                      "32x32 patches overlap (24,0) -> N=47 nodes, ResNet[1,1,1,1] encoder (PyTorch fp32), "
                                      "fused tcgen05 walk fwd+bwd (bf16x3, two launches), Adam; random-init weights",
                             global_batch=B * world, frames=T, nodes=tr["N"], tau=TRAIN["tau"],
-                            parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of encoder grads)" if world > 1 else ""),
+                            parallelism=f"dp{world}" + (" (one process per GPU, ONE NCCL all-reduce of the 19.9 MB of encoder gradients per step: parallel.FlatGradients)" if world > 1 else ""),
                             l2="4 rotating input batches (246 MB) > L2"),
                 clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=wk["launches"] * args.steps,
                 roofline=wk["roofline"], hot_path=hot, loss=tr["loss"],
@@ -672,7 +690,7 @@ def run_b200(args):
                                          "checkpointing; NOT reference behaviour: the reference never feeds CRW from its UNet), fused tcgen05 "
                                          "walk fwd+bwd (bf16x3), Adam",
                                 global_batch=B * world, frames=20, nodes=tr4["N"],
-                                parallelism=f"dp{world}" + (" (DDP, NCCL allreduce of 17.2 MB of encoder grads, 5 MB buckets)" if world > 1 else "")))
+                                parallelism=f"dp{world}" + (" (one process per GPU, ONE NCCL all-reduce of the 17.2 MB of encoder gradients per step: parallel.FlatGradients)" if world > 1 else "")))
             if lp5 is not None:
                 line["labelprop_cfg5"] = lp5
             emit(line)

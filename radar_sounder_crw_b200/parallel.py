@@ -52,6 +52,39 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int, group=
             p.grad.copy_(f)
 
 
+class FlatGradients:
+    """Gradient all-reduce without a wrapper module: every parameter's ``.grad`` becomes a VIEW (same sizes and strides as the
+    parameter, so fused optimizers see matching layouts) of ONE flat buffer that lives as long as this object; after
+    ``loss.backward()`` a single ``reduce()`` averages the whole buffer across ranks in place -- no per-parameter hooks, no
+    bucket bookkeeping, no copies.  ``zero()`` replaces ``optimizer.zero_grad()`` (one memset; ``set_to_none`` would drop the views).
+
+    Measured against DistributedDataParallel on 2 B200s (config 2, 19.9 MB of gradients): see DESIGN.md section 5.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], world: int, group=None):
+        self.ps = [p for p in params if p.requires_grad]
+        self.world, self.group = world, group
+        n = sum(p.numel() for p in self.ps)
+        ref = self.ps[0]
+        self.flat = torch.zeros(n, device=ref.device, dtype=ref.dtype)
+        off = 0
+        for p in self.ps:
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            if dense:
+                p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
+            else:
+                p.grad = self.flat[off:off + p.numel()].view(p.size())
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def reduce(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
+
+
 def gather_labels(local_labels: torch.Tensor, n_total: int, rank: int, world: int, group=None) -> torch.Tensor:
     """Convenience (NOT on the data path): assemble per-rank label blocks [R_local, ...] into [n_total, ...] on every rank."""
     if world == 1:

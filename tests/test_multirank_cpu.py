@@ -26,7 +26,7 @@ def _enc():
     return torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(16, 8))
 
 
-def _worker(rank, world, port, ret, B=4, weighted=False):
+def _worker(rank, world, port, ret, B=4, weighted=False, flat=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.walk_torch_port import crw_loss_reference_order
@@ -42,8 +42,20 @@ def _worker(rank, world, port, ret, B=4, weighted=False):
     if rank == 0:
         emb = emb * extra
     loss, _ = crw_loss_reference_order(emb, 0.07)
-    loss.backward()
-    if weighted:
+    if flat:
+        from radar_sounder_crw_b200.parallel import FlatGradients
+        fg = FlatGradients(list(enc.parameters()) + [extra], world)
+        fg.zero()
+        loss.backward()
+        fg.reduce()
+        views_kept = all(p.grad.untyped_storage().data_ptr() == fg.flat.untyped_storage().data_ptr() for p in enc.parameters())
+        if rank == 0:
+            ret["views_kept"] = views_kept
+    else:
+        loss.backward()
+    if flat:
+        pass
+    elif weighted:
         allreduce_gradients(list(enc.parameters()) + [extra], world, local_items=b1 - b0, total_items=B)
     else:
         allreduce_gradients(list(enc.parameters()) + [extra], world)
@@ -102,6 +114,24 @@ def test_two_rank_uneven_shards_weighted_allreduce_equals_full_batch():
     emb = torch.cat([emb[:3] * extra, emb[3:]])              # rank 0 (items 0..2) multiplies by the extra parameter (= 1)
     # the loss is a mean over batch elements of per-element terms, so the full-batch gradient is the item-weighted mean
     loss, _ = crw_loss_reference_order(emb, 0.07)
+    loss.backward()
+    for g, p in zip(ret["grad"], enc.parameters()):
+        assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_two_rank_flat_gradients_equal_full_batch():
+    """FlatGradients: the parameters' .grad are views of one buffer, autograd accumulates into them in place, ONE all-reduce."""
+    from oracle.walk_torch_port import crw_loss_reference_order
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret, 4, False, True), nprocs=2, join=True)
+    assert ret["views_kept"]
+    torch.manual_seed(11)
+    B, T, N = 4, 5, 6
+    seq = torch.randn(B, T, N, 4, 4)
+    enc = _enc()
+    loss, _ = crw_loss_reference_order(enc(seq.reshape(-1, 1, 4, 4)).reshape(B, T, N, -1), 0.07)
     loss.backward()
     for g, p in zip(ret["grad"], enc.parameters()):
         assert torch.allclose(g, p.grad, rtol=1e-5, atol=1e-8)
