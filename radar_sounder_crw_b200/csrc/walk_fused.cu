@@ -1530,6 +1530,8 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_bwd_roles_kernel(B
             __syncthreads();
             have_next = fetched && s_next != 0;
         }
+        // a hand-over flag that never arrived (this launch or the forward's) must not pass for a gradient: poison the element
+        if (e == 0 && tid == 0 && *reinterpret_cast<volatile int*>(err)) p.dx[(size_t)b * T * N * 128] = __int_as_float(0x7fc00000);
     }
     if (rprof && role < 4) {
         g_wf_prof[16 + role * 4 + 0] += (unsigned long long)(clock64() - c_begin);
