@@ -140,3 +140,25 @@ def test_fused_walk_train_step_through_crw_module(pkg, fused):
     g = [p.grad for p in enc.parameters() if p.grad is not None]
     assert len(g) > 0 and all(torch.isfinite(t).all() for t in g)
     assert torch.isfinite(loss) and A.shape == (2, 4, 47, 47)
+
+
+@pytest.mark.parametrize("B", [1, 36, 37, 38, 96, 150])
+def test_bf16x3_dispatch_across_batch_sizes(pkg, monkeypatch, B):
+    """precision=BF16X3 with no switches: role-split kernels while 4 B <= #SMs (B = 37 fills all 148), the eight shared-memory
+    kernels in between, one CTA per element from B = 96 (B = 150: more CTAs than SMs).  Same results as the fp32 kernels, with the
+    gradient that arrives through the returned A."""
+    monkeypatch.delenv("CRW_WALK_FUSED", raising=False)
+    monkeypatch.delenv("CRW_WALK_ROLES", raising=False)
+    torch.manual_seed(B)
+    for T, N in [(3, 8), (7, 47)]:
+        x = torch.randn(B, T, N, 128, device="cuda")
+        outs = []
+        for prec in (pkg.ops.PREC_BF16X3, pkg.ops.PREC_FP32):
+            xr = x.clone().requires_grad_(True)
+            loss, A, _ = pkg.ops.walk_loss(xr, 0.07, True, prec)
+            (loss + 0.01 * (A * A).mean()).backward()
+            outs.append((loss.item(), A.detach(), xr.grad))
+        assert torch.isfinite(outs[0][2]).all()
+        assert abs(outs[0][0] - outs[1][0]) <= 1e-5 * abs(outs[1][0])
+        assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < 1e-4
+        assert rel_err(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy()) < 1e-3
