@@ -455,11 +455,12 @@ def bench_labelprop(crw, args, rank, world, pk, lp_config=None):
     total_cols = (LP5["R_total"] if cfg5 else R * world) * Tl * COLS_PER_FRAME
 
     def lp_step_e2e(i):
-        # from pinned HOST features to labels on the host.  bf16x3: the public host-buffer call streams the features in chunks,
-        # the copy of chunk c+1 overlapping the top-k of chunk c (crw_labelprop_forward_host); the other paths copy first
-        if prec[0] == crw.ops.PREC_BF16X3:
+        # from pinned HOST features to labels on the host.  The public host-buffer calls stream the features in pieces, the copy of piece
+        # c+1 overlapping the search of piece c: chunks of query tiles for the bf16x3 kernel, whole radargrams for the exact path (one
+        # radargram alone is copied first: a segment's search lasts one filter item however short it is); fp32 copies first
+        if prec[0] == crw.ops.PREC_BF16X3 or (prec[0] == crw.ops.PREC_TC_EXACT and R > 1):
             labels, _, _, _ = crw.ops.labelprop_host(feats_host, mask0, LP["ctx"], float(LP["radius"]), LP["temp"], LP["k"],
-                                                     crw.ops.LP_REF_EXACT, True, False)
+                                                     crw.ops.LP_REF_EXACT, True, False, prec[0])
             res[0] = labels
         else:
             lp_step(i, feats_host)

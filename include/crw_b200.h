@@ -159,6 +159,15 @@ int crw_labelprop_forward_host(const float* feats_host, const float* mask0, int 
                                int ctx, float radius, float temp, int k, int mode, int do_normalize,
                                int32_t* labels, float* masks, float* W_or_null, int32_t* I_or_null, void* scratch,
                                size_t scratch_bytes, void* stream);
+/* The same for the EXACT tensor path (CRW_PREC_TC_EXACT): each radargram is cut into up to four segments of frames, segment s + 1
+ * is copied while segment s runs prep -> filter -> refine; a later segment is the sub-sequence [frame 0 | its ctx context frames |
+ * its frames], whose windows and candidate numbering are those of the whole radargram -- results bit-identical to
+ * crw_labelprop_forward(..., CRW_PREC_TC_EXACT, ...). */
+size_t crw_labelprop_host_exact_scratch_bytes(int R, int T, int N, int C, int k, int have_topk_out);
+int crw_labelprop_forward_host_exact(const float* feats_host, const float* mask0, int R, int T, int N, int C, int M,
+                               int ctx, float radius, float temp, int k, int mode, int do_normalize,
+                               int32_t* labels, float* masks, float* W_or_null, int32_t* I_or_null, void* scratch,
+                               size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * "Horizontality" metric -- replaces src/utils.py:118-123 (channel-shifted intra-frame

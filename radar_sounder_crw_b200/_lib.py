@@ -37,6 +37,9 @@ SIGNATURES = {
     "crw_labelprop_host_scratch_bytes": (_c_sz, [_c_int] * 6),
     "crw_labelprop_forward_host": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_int,
                                             _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_sz, _vp]),
+    "crw_labelprop_host_exact_scratch_bytes": (_c_sz, [_c_int] * 6),
+    "crw_labelprop_forward_host_exact": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_f, _c_int,
+                                            _c_int, _c_int, _vp, _vp, _vp, _vp, _vp, _c_sz, _vp]),
     "crw_horizontality_xent": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_labels_upsample": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_patch_unfold": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

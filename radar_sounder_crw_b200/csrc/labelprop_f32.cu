@@ -611,7 +611,7 @@ size_t lp_x_plan_bytes();
 size_t lp_x_scratch_bytes(int R, int T, int N, int C, int k, int do_normalize);
 int lp_x_max_k();
 int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize, float* W,
-                 int32_t* I, void* scratch, int sms, cudaStream_t st, void* plan_storage, size_t plan_bytes);
+                 int32_t* I, void* scratch, int sms, cudaStream_t st, void* plan_storage, size_t plan_bytes, int n_min = 1);
 int lp_x_launch(const void* plan_storage, int v_begin, int v_end, int max_ctas, cudaStream_t st);
 int lp_x_total_slots(const void* plan_storage);
 int lp_x_early_slots(const void* plan_storage);
@@ -902,4 +902,119 @@ extern "C" int crw_horizontality_xent(const float* emb, int T, int N, int C, flo
     xent_kernel<<<T - 1, 256, smem, (cudaStream_t)stream>>>(emb, T, N, C, xent);
     CRW_LAUNCH_RET();
     return CRW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-streamed EXACT tensor path: `feats` lives in PINNED HOST memory.  Each radargram is cut into up to four segments of frames;
+// segment s + 1 is copied into a staging double buffer on the copy stream while segment s runs prep -> filter -> refine.  A query
+// frame only needs frame 0 and the ctx frames before it, so a later segment [a, b) is the SUB-SEQUENCE [frame 0 | frames a - ctx .. b):
+// its queries sit at sub-sequence frames >= ctx + 1, where window, trimmed candidate numbering and hence W / I are exactly those of
+// the whole radargram; the context frames are not emitted (n_min).  Results are bit-identical to crw_labelprop_forward with
+// CRW_PREC_TC_EXACT.  The gathers run once over the whole call.
+// ------------------------------------------------------------------------------------------
+// Segments per radargram: ONE by default -- the pipeline then overlaps the copy of radargram r + 1 with the search of radargram r,
+// which is what pays (config 5: 77 MB per radargram against 4.4 ms of search).  Cutting one radargram into segments does not: a
+// segment's search lasts one filter item (~65 us at config 3) however short it is, so four segments cost 4 x 110 us against 160 us
+// for the whole radargram and the tail after the last copy is as long as before (measured: 0.82 against 0.79 ms for copy-then-search).
+// CRW_LP_HOST_SEGS=<n> cuts into up to n segments (used by the tests of the sub-sequence logic).
+static void host_exact_segments(int T, int ctx, int& nseg, int& seg) {
+    int maxseg = 1;
+    { const char* e = getenv("CRW_LP_HOST_SEGS"); if (e && atoi(e) > 0) maxseg = atoi(e); }
+    nseg = T / 128;
+    if (nseg > maxseg) nseg = maxseg;
+    if (nseg < 1) nseg = 1;
+    seg = ceil_div(T, nseg);
+    if (seg < ctx + 2) { seg = T; nseg = 1; }
+    nseg = ceil_div(T, seg);
+}
+extern "C" size_t crw_labelprop_host_exact_scratch_bytes(int R, int T, int N, int C, int k, int have_topk_out) {
+    if (T < 1 || N < 1) return 0;
+    int nseg, seg;
+    host_exact_segments(T, 20, nseg, seg);                       // (upper bound over ctx: segments only get shorter with larger ctx... sized below with slack)
+    const size_t tsub = (size_t)T;                              // a segment never exceeds the radargram
+    size_t b = 2 * align_up(tsub * N * C * sizeof(float), 256);                                  // staging double buffer
+    b += align_up(crw::lp_x_scratch_bytes(1, (int)tsub, N, C, k, 1), 256);
+    if (!have_topk_out) b += 2 * align_up((size_t)R * T * k * N * sizeof(float), 256);
+    return b + 512;
+}
+extern "C" int crw_labelprop_forward_host_exact(const float* feats_host, const float* mask0, int R, int T, int N, int C, int M, int ctx,
+                                                float radius, float temp, int k, int mode, int do_normalize, int32_t* labels,
+                                                float* masks, float* W_or_null, int32_t* I_or_null, void* scratch,
+                                                size_t scratch_bytes, void* stream) {
+    if (!feats_host || !mask0 || !labels || !masks) return CRW_ERR_INVALID;
+    if (R < 0 || T < 1 || N < 1 || C < 1 || M < 1) return CRW_ERR_INVALID;
+    if ((W_or_null == nullptr) != (I_or_null == nullptr)) return CRW_ERR_INVALID;
+    if (ctx < 1 || k < 1 || !(radius > 0.0f) || !(temp > 0.0f) || (int64_t)N < k) return CRW_ERR_INVALID;
+    if (R == 0) return CRW_OK;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, feats_host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return CRW_ERR_INVALID;                                   // pageable memory would serialise the copies silently
+    }
+    const size_t need = crw_labelprop_host_exact_scratch_bytes(R, T, N, C, k, W_or_null != nullptr);
+    if (!scratch || scratch_bytes < need) return CRW_ERR_WORKSPACE;
+    SideCtx* sc = side_ctx();
+    if (!sc) return CRW_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+    const size_t stage_bytes = align_up((size_t)T * N * C * sizeof(float), 256);
+    float* stage[2] = {reinterpret_cast<float*>(sp), reinterpret_cast<float*>(sp + stage_bytes)};
+    sp += 2 * stage_bytes;
+    void* xs = sp;
+    sp += align_up(lp_x_scratch_bytes(1, T, N, C, k, 1), 256);
+    float* Wt = W_or_null;
+    int32_t* It = I_or_null;
+    if (!Wt) {
+        Wt = reinterpret_cast<float*>(sp);
+        sp += align_up((size_t)R * T * k * N * sizeof(float), 256);
+        It = reinterpret_cast<int32_t*>(sp);
+    }
+    GatherParams gp;
+    int rc = gather_params(gp, Wt, It, mask0, R, T, N, M, ctx, k, mode, labels, masks);
+    if (rc != CRW_OK) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int nseg, seg;
+    host_exact_segments(T, ctx, nseg, seg);
+    const size_t frame = (size_t)N * C;
+
+    std::lock_guard<std::mutex> lock(sc->mu);
+    CRW_CUDA_RET(cudaEventRecord(sc->ev_fork, st));               // earlier work on `st` may still use the scratch
+    CRW_CUDA_RET(cudaStreamWaitEvent(sc->s_copy, sc->ev_fork, 0));
+    int g = 0;
+    for (int rg = 0; rg < R; ++rg) {
+        const float* src = feats_host + (size_t)rg * T * frame;
+        for (int s = 0; s < nseg; ++s, ++g) {
+            const int slot = g & 1;
+            const int a = s * seg, b = (a + seg < T) ? a + seg : T;
+            if (g >= 2) CRW_CUDA_RET(cudaStreamWaitEvent(sc->s_copy, sc->ev_free[slot], 0));
+            int tsub, n_min, out_off;
+            if (s == 0) {
+                tsub = b; n_min = 1; out_off = 0;
+                CRW_CUDA_RET(cudaMemcpyAsync(stage[slot], src, (size_t)b * frame * sizeof(float), cudaMemcpyHostToDevice, sc->s_copy));
+            } else {
+                tsub = 1 + ctx + (b - a); n_min = ctx + 1; out_off = a - ctx - 1;
+                CRW_CUDA_RET(cudaMemcpyAsync(stage[slot], src, frame * sizeof(float), cudaMemcpyHostToDevice, sc->s_copy));
+                CRW_CUDA_RET(cudaMemcpyAsync(stage[slot] + frame, src + (size_t)(a - ctx) * frame, (size_t)(b - a + ctx) * frame * sizeof(float),
+                                             cudaMemcpyHostToDevice, sc->s_copy));
+            }
+            CRW_CUDA_RET(cudaEventRecord(sc->ev_copied[slot], sc->s_copy));
+            CRW_CUDA_RET(cudaStreamWaitEvent(st, sc->ev_copied[slot], 0));
+            if (tsub >= 2) {
+                LpXPlanStorage plan;
+                const size_t o = ((size_t)rg * T + out_off) * k * N;
+                // full-size items (four query tiles each, all sixteen epilogue warps busy) on as many SMs as that takes: a segment's
+                // search then lasts one item's time and hides behind the next segment's copy
+                int sms_seg = ceil_div(tsub * N, 512);
+                if (sms_seg > sms) sms_seg = sms;
+                if ((rc = lp_x_prepare(stage[slot], 1, tsub, N, C, ctx, radius, temp, k, do_normalize, Wt + o, It + o, xs, sms_seg, st, plan.bytes,
+                                       sizeof(plan.bytes), n_min)) != CRW_OK) return rc;
+                if ((rc = lp_x_launch(plan.bytes, 0, lp_x_total_slots(plan.bytes), sms, st)) != CRW_OK) return rc;
+            }
+            CRW_CUDA_RET(cudaEventRecord(sc->ev_free[slot], st));
+        }
+    }
+    if ((rc = gather_launch_seq(gp, st)) != CRW_OK) return rc;
+    return gather_launch_par(gp, st);
 }

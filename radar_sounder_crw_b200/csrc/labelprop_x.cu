@@ -169,6 +169,7 @@ constexpr float kXFixMagic = 12582912.0f;    // 1.5 * 2^23: float -> integer in 
 
 struct XParams {
     int R, T, N, ctx, rb, k;
+    int n_min;                               // first query frame whose results are wanted (1; ctx + 1 for a streamed sub-sequence)
     int rows_rg;                             // T * N
     int rows_per_item, items_per_rg, early_items_rg;
     int early_rpi, early_rows;               // the first early_items_rg items of a radargram are small (early_rpi rows): rows [0, early_rows)
@@ -517,7 +518,7 @@ lp_filter_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
             const int row = qt.r_lo + quarter * 32 + lane;
             const int n = row / N, q = row - n * N;
             const bool in_item = row < t.rb;
-            const bool qvalid = qt.active && in_item && (n >= 1) && (n < p.T);
+            const bool qvalid = qt.active && in_item && (n >= p.n_min) && (n < p.T);
             const int win_lo = (n > ctx + 1) ? n - ctx : 1;
             const int lo_q = max(0, q - rb), w_q = min(N - 1, q + rb) - lo_q + 1;
             const unsigned long long mq = (w_q >= 64) ? ~0ull : ((1ull << w_q) - 1ull);
@@ -628,6 +629,7 @@ struct RParams {
     float* W;                // [R, T, k, N]
     int32_t* I;
     int R, T, N, ctx, rb, k;
+    int n_min;               // first query frame whose results are wanted
     int rows_rg, row_begin, row_end;   // radargram-relative row range handled by this launch (every radargram)
     long long total_rows;
     float inv_temp;
@@ -804,7 +806,7 @@ __global__ void __launch_bounds__(kRThreads, MINB) lp_refine_kernel(RParams p) {
         const size_t grow_j = (size_t)rg_j * p.rows_rg + row_j;
         // count word: bit 31 = no query here (frame 0 / beyond the sequence / beyond the chunk), bit 30 = overflowed list
         unsigned cword_j = 0x80000000u;
-        if (lane < nq && n_j >= 1 && n_j < p.T) cword_j = (unsigned)__ldg(p.cnt + grow_j);
+        if (lane < nq && n_j >= p.n_min && n_j < p.T) cword_j = (unsigned)__ldg(p.cnt + grow_j);
         // ---------------- phase 1 ----------------
         // the survivor list of the NEXT query is fetched while the current one is worked on
         const size_t grow0 = (size_t)__shfl_sync(0xffffffffu, rg_j, 0) * p.rows_rg + __shfl_sync(0xffffffffu, row_j, 0);
@@ -1028,7 +1030,7 @@ static int launch_refine(const RParams& r_in, int max_ctas, cudaStream_t st) {
 
 // prep + plan.  feats [R,T,N,128] fp32 -> plan (tensor maps, schedule).  `sms` sizes the items so that one round fills the GPU.
 int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float radius, float temp, int k, int do_normalize, float* W,
-                 int32_t* I, void* scratch, int sms, cudaStream_t st, void* plan_storage, size_t plan_bytes) {
+                 int32_t* I, void* scratch, int sms, cudaStream_t st, void* plan_storage, size_t plan_bytes, int n_min) {
     if (plan_bytes < sizeof(LpXPlan)) return CRW_ERR_WORKSPACE;
     LpXPlan* plan = reinterpret_cast<LpXPlan*>(plan_storage);
     if (C != 128 || N > 128 || N < 8 || k > lp_x_max_k()) return CRW_ERR_UNSUPPORTED;
@@ -1068,6 +1070,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     }
     XParams& p = plan->p;
     p.R = R; p.T = T; p.N = N; p.ctx = ctx; p.k = k;
+    p.n_min = n_min < 1 ? 1 : n_min;
     p.rows_rg = T * N;
     const float rc_ = ceilf(radius);
     p.rb = (rc_ - 1.0f >= (float)N) ? N : (int)rc_ - 1;
@@ -1114,6 +1117,7 @@ int lp_x_prepare(const float* feats, int R, int T, int N, int C, int ctx, float 
     r.surv = surv; r.cnt = cnt; r.W = W; r.I = I;
     r.ovf_list = ovf_list; r.ovf_ctr = ovf_ctr; r.resc_ctas = 0;
     r.R = R; r.T = T; r.N = N; r.ctx = ctx; r.rb = p.rb; r.k = k;
+    r.n_min = p.n_min;
     r.rows_rg = p.rows_rg; r.row_begin = 0; r.row_end = 0;
     r.total_rows = p.total_rows; r.inv_temp = p.inv_temp; r.magic_n = p.magic_n; r.debug = p.debug;
     if (T < 2) return CRW_OK;

@@ -235,9 +235,11 @@ def _park_pinned(feats: Tensor) -> None:
 
 @torch.library.custom_op("crw_b200::labelprop_host", mutates_args=())
 def labelprop_host(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: float, k: int, mode: int,
-                   normalize: bool, return_topk: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """``labelprop`` (tensor path) for features in PINNED HOST memory: the H2D copy is chunked and overlapped with the
-    top-k of the previous chunk.  ``feats`` must not be modified until the current stream has caught up."""
+                   normalize: bool, return_topk: bool, precision: int = PREC_BF16X3) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``labelprop`` (tensor paths) for features in PINNED HOST memory: the H2D copy is cut into pieces and overlapped with the
+    search of the previous piece.  ``precision``: PREC_BF16X3 (the approximate kernel; chunks of query tiles) or PREC_TC_EXACT /
+    PREC_AUTO (the exact tensor path; segments of frames -- results bit-identical to ``labelprop`` with PREC_TC_EXACT).
+    ``feats`` must not be modified until the current stream has caught up."""
     if feats.is_cuda or not feats.is_pinned():
         raise RuntimeError("crw_b200::labelprop_host: `feats` must be a pinned host tensor (use labelprop for CUDA tensors)")
     if feats.dtype != torch.float32:
@@ -248,6 +250,9 @@ def labelprop_host(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: 
     M = mask0.shape[1]
     L = _lib.lib()
     dev = mask0.device
+    prec = lp_precision(precision, N, C, k) if int(precision) == PREC_AUTO else int(precision)
+    if prec not in (PREC_BF16X3, PREC_TC_EXACT):
+        raise RuntimeError("crw_b200::labelprop_host: precision must be PREC_BF16X3 or PREC_TC_EXACT (the fp32 kernel has no host-streamed entry)")
     labels = torch.empty((R, T, N), device=dev, dtype=torch.int32)
     masks = torch.empty((R, T, M, N), device=dev, dtype=torch.float32)
     if return_topk:
@@ -256,18 +261,20 @@ def labelprop_host(feats: Tensor, mask0: Tensor, ctx: int, radius: float, temp: 
     else:
         W = torch.empty(0, device=dev, dtype=torch.float32)
         I = torch.empty(0, device=dev, dtype=torch.int32)
-    sbytes = L.crw_labelprop_host_scratch_bytes(R, T, N, C, k, int(return_topk))
+    exact = prec == PREC_TC_EXACT
+    sbytes = (L.crw_labelprop_host_exact_scratch_bytes if exact else L.crw_labelprop_host_scratch_bytes)(R, T, N, C, k, int(return_topk))
     scratch = torch.empty(sbytes, device=dev, dtype=torch.uint8)
+    fn, name = ((L.crw_labelprop_forward_host_exact, "crw_labelprop_forward_host_exact") if exact
+                else (L.crw_labelprop_forward_host, "crw_labelprop_forward_host"))
     with torch.cuda.device(dev):
-        _lib.check(L.crw_labelprop_forward_host(feats.data_ptr(), _p(mask0), R, T, N, C, M, ctx, float(radius), float(temp), k,
-                                                int(mode), int(normalize), _p(labels), _p(masks), _p(W), _p(I),
-                                                _p(scratch), sbytes, _stream()), "crw_labelprop_forward_host")
+        _lib.check(fn(feats.data_ptr(), _p(mask0), R, T, N, C, M, ctx, float(radius), float(temp), k, int(mode), int(normalize),
+                      _p(labels), _p(masks), _p(W), _p(I), _p(scratch), sbytes, _stream()), name)
         _park_pinned(feats)
     return labels, masks, W, I
 
 
 @labelprop_host.register_fake
-def _(feats, mask0, ctx, radius, temp, k, mode, normalize, return_topk):
+def _(feats, mask0, ctx, radius, temp, k, mode, normalize, return_topk, precision=PREC_BF16X3):
     R, T, N, _ = feats.shape
     M = mask0.shape[1]
     dev = mask0.device
