@@ -60,7 +60,7 @@ struct Layout {
         tiles = frames + (size_t)T_ * kSaveFrame;
         per_b = tiles + (size_t)(K + 1) * kSaveStep;
         part = (size_t)B * per_b;
-        ctr = part + align_up((size_t)B * sizeof(float), 256);
+        ctr = part + align_up((size_t)2 * B * sizeof(float), 256);      // (role-split forward: chain and cycle CTA of an element each add one)
         flags = ctr + 256;
         total = flags + align_up((size_t)B * 4 * T_ * sizeof(int), 256);
     }
@@ -591,6 +591,21 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         if (rprof) c_mma += clock64() - c0;
     };
 
+    // loss = sum over (b, k, d) of (lse - diag) / (B N N): the chain CTA (last cycle step) and the cycle CTA of every element each
+    // deposit one partial sum; the last of the 2 B depositors adds them in order
+    auto deposit_loss = [&](float tot, int slot) {       // one thread
+        float* part = reinterpret_cast<float*>(p.ws + lay.part);
+        part[slot] = tot;
+        __threadfence();
+        const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(p.ws + lay.ctr), 1u);
+        if (done == 2u * (unsigned)p.B - 1u) {
+            __threadfence();
+            float sum = 0.0f;
+            for (int i = 0; i < 2 * p.B; ++i) sum += reinterpret_cast<volatile float*>(part)[i];
+            if (*reinterpret_cast<volatile int*>(err)) sum = __int_as_float(0x7fc00000);      // a hand-over flag never arrived: NaN, not a wrong number
+            *p.loss = sum / ((float)p.B * (float)N * (float)N);
+        }
+    };
     const int P = p.P;
     if (role < P) {
         // ================= producer =================
@@ -717,12 +732,16 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         // synchronise among themselves on a named barrier.
         const uint32_t sSSb = sb + rE, sX = sb + rE + 3 * (uint32_t)kSaveSS;      // S tiles: three 32 KB buffers; X: hi, lo
         const uint32_t tX = tmem;
+        const uint32_t sGc = sSSb + (uint32_t)(K % 3) * (uint32_t)kSaveSS;       // G_K: the S buffer the last product did not read
         if (is_st) {
             for (int k = 1; k <= K; ++k) {
                 tc::mbar_wait(&bar_tile, (k - 1) & 1);
                 if (tc::elect_one()) store_tile(p.ws + lay.step(b, k), sX, (uint32_t)kSaveX, flagp(1, k));      // the cycle CTA is waiting for X_k
                 __syncwarp();
             }
+            tc::mbar_wait(&bar_tile, K & 1);
+            if (tc::elect_one()) store_tile(p.ws + lay.step(b, K) + kSaveX + kSaveSS, sGc, (uint32_t)kSaveG, nullptr);
+            __syncwarp();
         } else {
             auto sync9 = [&]() {                     // operand tiles written / accumulators read -> visible; the nine working warps only
                 tc::fence_proxy_async();
@@ -788,6 +807,46 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
                     if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
                 }
             }
+            // the LAST cycle step here, where X_K already is: M_K = L_K R_K, lse - diag, G_K (the cycle CTA does steps 1 .. K - 1; handing
+            // X_K over would put a flag, a 32 KB load and a product latency at the very end of the launch)
+            const uint32_t tM = tmem + 128u;
+            if (is_iss) { if (tc::elect_one()) {
+                tc::tc_fence_after();
+                mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);
+                tc::umma_commit(&bar_mma);
+            } __syncwarp(); }
+            mma_wait();
+            float m[32];
+            float sm = 0.0f, diag = 0.0f, lsum = 0.0f;
+            if (is_epi && half == 0) {
+                tmem_ld32(tM + lane_base + (uint32_t)(ch * 32), m);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if (32 * ch + c == r) diag = m[c];
+                    m[c] = (32 * ch + c < N && r < N) ? exp2f((m[c] - 1.0f) * 1.4426950408889634f) : 0.0f;
+                    sm += m[c];
+                }
+                s_red[ch][r] = sm;
+            }
+            tc::tc_fence_before();
+            asm volatile("bar.sync 1, 288;" ::: "memory");
+            if (is_epi && half == 0) {
+                sm += s_red[1 - ch][r];
+                if (r < N && (r >> 5) == ch) lsum = logf(sm) + 1.0f - diag;
+                const float is = (r < N) ? 1.0f / sm : 0.0f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) m[c] = m[c] * is - ((32 * ch + c == r && r < N) ? 1.0f : 0.0f);
+                store_row32(sGc, sGc + kTile64, r, ch, m);
+            }
+            sync9();
+            if (is_iss) { if (tc::elect_one()) tc::mbar_arrive(&bar_tile); __syncwarp(); }
+            if (is_epi && half == 0) s_red[2 + ch][r] = lsum;
+            asm volatile("bar.sync 1, 288;" ::: "memory");
+            if (tid == 0) {
+                float tot = 0.0f;
+                for (int i = 0; i < 64; ++i) tot += s_red[2][i] + s_red[3][i];
+                deposit_loss(tot, p.B + b);
+            }
         }
     } else {
         // ================= cycle =================
@@ -800,7 +859,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         };
         float loss_acc = 0.0f;
         int x_issued = 0;                            // (issuer lane) X_k has been fetched for k <= x_issued
-        for (int k = 1; k <= K; ++k) {
+        for (int k = 1; k < K; ++k) {                // (the chain CTA does step K itself)
             const int buf = k & 1;
             const uint32_t sX = sXb + (uint32_t)buf * (uint32_t)kSaveX;
             if (is_iss) { if (tc::elect_one()) { if (x_issued < k) { load_x(k, buf); x_issued = k; } } __syncwarp(); }      // (waits for the flag here)
@@ -810,7 +869,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
                 mma3<false, false>(tM, sX, sX + kPlane128, sX + kTile64, sX + kPlane128 + kTile64, 1, 0, 0, 0, true);    // M_k = L_k R_k
                 tc::umma_commit(&bar_mma);
                 // the next X under this step's epilogue -- only if it is already there: the epilogue needs this warp at its barriers
-                if (k < K && flag_peek(flagp(1, k + 1))) { load_x(k + 1, (k + 1) & 1); x_issued = k + 1; }
+                if (k + 1 < K && flag_peek(flagp(1, k + 1))) { load_x(k + 1, (k + 1) & 1); x_issued = k + 1; }
             } __syncwarp(); }
             mma_wait();
             if (k >= 2) st_wait();                                       // the copy of G_{k-1} has left shared memory
@@ -851,17 +910,7 @@ __global__ void __launch_bounds__(kRoleThreads, 1) walk_fused_fwd_roles_kernel(c
         if (tid == 0) {
             float tot = 0.0f;
             for (int i = 0; i < 64; ++i) tot += s_red[0][i] + s_red[1][i];
-            float* part = reinterpret_cast<float*>(p.ws + lay.part);
-            part[b] = tot;
-            __threadfence();
-            const unsigned done = atomicAdd(reinterpret_cast<unsigned*>(p.ws + lay.ctr), 1u);
-            if (done == (unsigned)p.B - 1u) {
-                __threadfence();
-                float sum = 0.0f;
-                for (int i = 0; i < p.B; ++i) sum += reinterpret_cast<volatile float*>(part)[i];
-                if (*reinterpret_cast<volatile int*>(err)) sum = __int_as_float(0x7fc00000);      // a hand-over flag never arrived: NaN, not a wrong number
-                *p.loss = sum / ((float)p.B * (float)N * (float)N);
-            }
+            deposit_loss(tot, b);
         }
     }
     if (rprof && (role < 2 || role >= P)) {
