@@ -18,8 +18,10 @@
  *     events (crw_labelprop_forward forks the early frames + the sequential label
  *     gather onto the side stream and joins them back with events; the enqueue
  *     sequence of a call is serialised by a mutex, so calls from several host threads
- *     are safe but do not interleave), cached kernel attributes (opt-in shared-memory
- *     sizes), and the environment switches listed in DESIGN.md, read once;
+ *     are safe but do not interleave) and cached kernel attributes (opt-in shared-memory
+ *     sizes).  The environment switches listed in DESIGN.md (engine selection for tests,
+ *     profiling aids) are looked up with getenv at every call -- none is needed in
+ *     production and none changes results except the documented debug flags;
  *   - return value: CRW_OK, a negative CRW_ERR_* code, or -(1000 + cudaError_t) when
  *     a launch failed; no exceptions cross the boundary;
  *   - tensors are dense row-major fp32 unless said otherwise; shapes in brackets.
