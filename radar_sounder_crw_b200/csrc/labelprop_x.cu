@@ -830,7 +830,8 @@ __global__ void __launch_bounds__(kRThreads, MINB) lp_refine_kernel(RParams p) {
                 if (sb >= c) break;                                              // warp-uniform
                 // the row loads of a batch (RB = 16: all of them, RB = 8: two batches) are unconditional and issued back to back
                 // (slots past the count repeat the last survivor's row: same address, merged in L1, and their dots are
-                // ignored), so that they are in flight together
+                // ignored), so that they are in flight together (measured: loads predicated on `slot < count` instead -- no duplicate
+                // L1 traffic -- are issued one by one by the compiler: 73 us instead of 43)
                 float part[16];
 #pragma unroll
                 for (int b0 = 0; b0 < 16; b0 += RB) {
