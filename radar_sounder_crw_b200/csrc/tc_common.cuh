@@ -94,6 +94,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// 3-D tiled load: (c0 = innermost element index, c1 = row index, c2 = matrix index)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // whole warp
@@ -266,5 +274,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 // ---------------------------------------------------------------- host: tensor-map encoding
 // 2-D bf16 row-major matrix [rows][cols], box = [box_rows][64 elements], SWIZZLE_128B.  Returns CRW_OK or an error.
 int make_tmap_bf16_k64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+// a stack of `mats` bf16 matrices [rows][cols valid of `pitch`], box = 64 x 64 elements of one matrix, SWIZZLE_128B, zero fill
+int make_tmap_bf16_mats(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t mats, uint64_t pitch);
 
 }  // namespace crw

@@ -51,6 +51,22 @@ int make_tmap_bf16_box(CUtensorMap* out, const void* base, uint64_t rows, uint64
     return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
 }
 
+// a stack of `mats` bf16 row-major matrices [rows][cols valid of `pitch` elements], one after the other (matrix stride =
+// rows * pitch); box = 64 x 64 elements of ONE matrix, SWIZZLE_128B.  Rows / columns past the matrix read as zero.
+int make_tmap_bf16_mats(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t mats, uint64_t pitch) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return CRW_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (pitch * 2) % 16 || cols > pitch || !cols || !rows || !mats) return CRW_ERR_ALIGN;
+    cuuint64_t gdim[3] = {cols, rows, mats};
+    cuuint64_t gstr[2] = {pitch * 2, rows * pitch * 2};
+    cuuint32_t box[3] = {64, 64, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? CRW_OK : CRW_ERR_INVALID;
+}
+
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int BN, float* out) {
     extern __shared__ uint8_t smem_raw[];

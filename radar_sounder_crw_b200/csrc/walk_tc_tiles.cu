@@ -7,8 +7,11 @@
 //     row pitch padded to 8 elements, pads zero), written by the epilogue that produces it with 16-byte stores;
 //   * an operand used as stored is a K-major tile, an operand used transposed is an MN-major tile of the SAME plane
 //     (UMMA majorness bits + LBO/SBO descriptors, pinned by crw_debug_umma_mn_gemm) -- no transposed copies;
-//   * staging is sixteen 16-byte cp.async per thread per 64-wide k-chunk straight into the SWIZZLE_128B layout, three
-//     stages deep; the MMAs of chunk c are queued before the CTA waits for the stage of chunk c-1 to drain;
+//   * staging is TMA: three tensor maps (the E planes, the saved families, the backward families) describe every plane
+//     as a stack of matrices, one 64 x 64-element SWIZZLE_128B box is the unit (a K-major tile = two boxes along the rows,
+//     an MN-major tile = two boxes along the columns; rows / columns / k past the matrix are zero-filled by the TMA), one
+//     elected lane of warp 0 produces three stages ahead (full / empty mbarriers), one elected lane of warp 1 issues the
+//     MMAs, the other warps sleep on the accumulator barrier until the epilogue;
 //   * S'_t = softmax(A_t^T) is never materialised: the path keeps Q_t = S'_t^T = column-softmax(A_t) (same orientation
 //     as A_t, so softmax forward / backward are transposition-free and coalesced) and uses it through the other majorness;
 //   * the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in small kernels;
@@ -75,37 +78,22 @@ __device__ __forceinline__ void zero_row_pad(const Mat2& mt, int r, int N, int l
 }
 
 // ---- one 128 x 128 tile from bf16 planes -----------------------------------------------------------------
-// K-major use: logical X(r,k) = plane[r*pitch + k]; MN-major use: X(r,k) = plane[k*pitch + r].  `rows` = valid r extent.
-struct OpSrc { const bf16 *hi, *lo; int pitch, rows; };
+// K-major use: logical X(r,k) = plane[r*pitch + k]; MN-major use: X(r,k) = plane[k*pitch + r].  An operand is the hi / lo
+// matrix pair `zhi`, `zlo` (indices along the third dimension) of one tensor map.
+struct OpSrc { const CUtensorMap* map; int zhi, zlo; };
+struct TMaps { CUtensorMap E, W, S; };      // E planes [2*B*T][N][C]; saved families [5*2*B*(T-1)][N][N]; backward families [3*2*B*(T-1)][N][N]
 
-struct TcCtx3 { uint8_t* buf; uint64_t* bar; uint32_t tmem; uint32_t uses[kWStages]; int last_stage; };
+struct TcCtx3 { uint8_t* buf; uint64_t* full; uint64_t* empty; uint64_t* acc; uint32_t tmem; uint32_t g, tiles; const TMaps* maps; };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-    const int n = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
-}
+// one operand plane of one stage: 16 KB = two 64 x 64 boxes
 template <bool MN>
-__device__ __forceinline__ void stage_operand_async(uint32_t dst_hi, uint32_t dst_lo, const OpSrc& S, int r0, int k0, int K) {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int id = threadIdx.x + it * kTT;          // 1024 chunks of 8 elements
-        size_t so;
-        uint32_t off;
-        bool valid;
-        if (!MN) {
-            const int r = id >> 3, c = id & 7, kk = k0 + c * 8;
-            valid = (r0 + r) < S.rows && kk < K;
-            so = (size_t)(r0 + r) * S.pitch + kk;
-            off = (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ (r & 7)) & 7) << 4));
-        } else {
-            const int g = id >> 9, kk = (id >> 3) & 63, c = id & 7, r = r0 + g * 64 + c * 8;
-            valid = (k0 + kk) < K && r < ((S.rows + 7) & ~7);
-            so = (size_t)(k0 + kk) * S.pitch + r;
-            off = (uint32_t)((g << 13) + (kk << 7) + (((c ^ (kk & 7)) & 7) << 4));
-        }
-        if (!valid) so = 0;
-        cp_async16_zfill(dst_hi + off, S.hi + so, valid);
-        cp_async16_zfill(dst_lo + off, S.lo + so, valid);
+__device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* map, int z, int r0, int k0, uint64_t* bar) {
+    if (!MN) {
+        tc::tma_load_3d(dst, map, k0, r0, z, bar);
+        tc::tma_load_3d(dst + 8192, map, k0, r0 + 64, z, bar);
+    } else {
+        tc::tma_load_3d(dst, map, r0, k0, z, bar);
+        tc::tma_load_3d(dst + 8192, map, r0 + 64, k0, z, bar);
     }
 }
 
@@ -113,51 +101,61 @@ __device__ __forceinline__ void stage_operand_async(uint32_t dst_hi, uint32_t ds
 // against its own extents and pitch).  The accumulator goes TMEM -> registers (thread = row) -> shared memory ->
 // registers (warp = row, lane = column) so that every global access of the epilogue is coalesced.
 constexpr int kEpPitch = 132;      // floats; 528-byte rows: 16-byte aligned, conflict-free for the v4 stores of phase 1
-// acc (TMEM) = (fresh ? 0 : acc) + A B over the whole K extent; several calls may accumulate into one tile
+// acc (TMEM) = (fresh ? 0 : acc) + A B over the whole K extent; several calls may accumulate into one tile.  cx.g counts
+// the k-chunks this CTA has ever staged: chunk g lives in stage g % 3, its barriers are in phase (g / 3) & 1.
 template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void bf_gemm_accumulate(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, TcCtx3& cx, bool fresh) {
     const uint32_t idesc = tc::umma_idesc_bf16_major(kWTile, kWTile, A_MN, B_MN);
-    const int nchunks = (K + kWChunk - 1) / kWChunk;
-    auto issue = [&](int c) {
-        const int s = c % kWStages;
-        if (cx.uses[s] > 0) tc::mbar_wait(&cx.bar[s], (cx.uses[s] - 1) & 1);      // MMAs that read this stage retired
-        const uint32_t base = tc::smem_u32(cx.buf + s * kWStage);
-        stage_operand_async<A_MN>(base, base + kWOperand, A, m0, c * kWChunk, K);
-        stage_operand_async<B_MN>(base + 2 * kWOperand, base + 3 * kWOperand, B, n0, c * kWChunk, K);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    issue(0);
-    if (nchunks > 1) issue(1);
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kWStages;
-        if (c + 1 < nchunks) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        tc::fence_proxy_async();       // cp.async (generic proxy) writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tc::tc_fence_after();
-            const uint32_t a0 = tc::smem_u32(cx.buf + s * kWStage), b0 = a0 + 2 * kWOperand;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t ap = a0 + ((pass == 2) ? kWOperand : 0), bp = b0 + ((pass == 1) ? kWOperand : 0);
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
-                    const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
-                    tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (!fresh || (c | pass | ks)) ? 1u : 0u);
-                }
+    const int nchunks = (K + kWChunk - 1) / kWChunk, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            for (int c = 0; c < nchunks; ++c) {
+                const uint32_t g = cx.g + c, s = g % kWStages;
+                if (g >= kWStages) tc::mbar_wait(&cx.empty[s], (g / kWStages - 1) & 1);      // MMAs that read this stage retired
+                tc::mbar_arrive_expect_tx(&cx.full[s], kWStage);
+                const uint32_t base = tc::smem_u32(cx.buf + s * kWStage);
+                tma_operand<A_MN>(base, A.map, A.zhi, m0, c * kWChunk, &cx.full[s]);
+                tma_operand<A_MN>(base + kWOperand, A.map, A.zlo, m0, c * kWChunk, &cx.full[s]);
+                tma_operand<B_MN>(base + 2 * kWOperand, B.map, B.zhi, n0, c * kWChunk, &cx.full[s]);
+                tma_operand<B_MN>(base + 3 * kWOperand, B.map, B.zlo, n0, c * kWChunk, &cx.full[s]);
             }
-            tc::umma_commit(&cx.bar[s]);
         }
-        cx.uses[s]++;
-        cx.last_stage = s;
-        if (c + 2 < nchunks) issue(c + 2);     // its stage held chunk c-1: the wait overlaps the MMAs just queued
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            for (int c = 0; c < nchunks; ++c) {
+                const uint32_t g = cx.g + c, s = g % kWStages;
+                tc::mbar_wait(&cx.full[s], (g / kWStages) & 1);
+                tc::tc_fence_after();
+                const uint32_t a0 = tc::smem_u32(cx.buf + s * kWStage), b0 = a0 + 2 * kWOperand;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t ap = a0 + ((pass == 2) ? kWOperand : 0), bp = b0 + ((pass == 1) ? kWOperand : 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
+                        const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
+                        tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (!fresh || (c | pass | ks)) ? 1u : 0u);
+                    }
+                }
+                tc::umma_commit(&cx.empty[s]);
+            }
+        }
+        __syncwarp();
     }
+    cx.g += nchunks;
 }
 template <class Epi>
 __device__ __forceinline__ void bf_gemm_epilogue(int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc::mbar_wait(&cx.bar[cx.last_stage], (cx.uses[cx.last_stage] - 1) & 1);   // commit tracks every earlier MMA too: all stages idle
+    // one commit per tile on a barrier of its own: the warps that took no part in the staging arrive here at once, and a
+    // parity wait on a STAGE barrier would alias with that stage's previous use still in flight
+    if (warp == 1) {
+        if (tc::elect_one()) tc::umma_commit(cx.acc);      // tracks every MMA of this tile: all stages idle when it fires
+        __syncwarp();
+    }
+    tc::mbar_wait(cx.acc, cx.tiles & 1);
+    cx.tiles++;
     tc::tc_fence_after();
     float* ep = reinterpret_cast<float*>(cx.buf);
     {
@@ -179,7 +177,8 @@ __device__ __forceinline__ void bf_gemm_epilogue(int m0, int n0, int Mvalid, TcC
 #pragma unroll
         for (int q = 0; q < 4; ++q) epi(m0 + r, n0 + lane + 32 * q, ep[r * kEpPitch + lane + 32 * q]);
     }
-    __syncthreads();     // the staging buffer and TMEM are reused by the next tile
+    tc::fence_proxy_async();   // this tile's generic-proxy use of the staging buffer is ordered before the next tile's TMA writes
+    __syncthreads();           // the staging buffer and TMEM are reused by the next tile
 }
 template <bool A_MN, bool B_MN, class Epi>
 __device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
@@ -188,20 +187,25 @@ __device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int
 }
 
 template <class P>
-__global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(P p) {
+__global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(const __grid_constant__ P p, const __grid_constant__ TMaps maps) {
     extern __shared__ uint8_t tc_raw[];
-    __shared__ uint64_t bars[kWStages];
+    __shared__ uint64_t bars[2 * kWStages + 1];
     __shared__ uint32_t slot;
     TcCtx3 cx;
     cx.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-    cx.bar = bars;
-    cx.last_stage = 0;
-#pragma unroll
-    for (int s = 0; s < kWStages; ++s) cx.uses[s] = 0;
+    cx.full = bars;
+    cx.empty = bars + kWStages;
+    cx.acc = bars + 2 * kWStages;
+    cx.g = 0;
+    cx.tiles = 0;
+    cx.maps = &maps;
     if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<128>(&slot);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWStages; ++s) tc::mbar_init(&bars[s], 1);
+        for (int s = 0; s < 2 * kWStages + 1; ++s) tc::mbar_init(&bars[s], 1);
         tc::fence_barrier_init();
+        tc::prefetch_tmap(&maps.E);
+        tc::prefetch_tmap(&maps.W);
+        tc::prefetch_tmap(&maps.S);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -221,7 +225,19 @@ struct Ctx {
     float* sc;        // fp32 backward scratch (BwdLayout)
     bf16* sa;         // bf16 backward arena
 };
-__device__ __forceinline__ OpSrc src_of(const Mat2& m, int rows) { return OpSrc{m.hi, m.lo, m.P, rows}; }
+// matrix (fam, b, t) of the saved / backward families, frame (b, t) of the E planes: indices along the maps' third dimension
+__device__ __forceinline__ OpSrc op_saved(const TcCtx3& cx, const Dims& d, int fam, int b, int t) {
+    const int nm = d.B * (d.T - 1), z = fam * 2 * nm + b * (d.T - 1) + t;
+    return OpSrc{&cx.maps->W, z, z + nm};
+}
+__device__ __forceinline__ OpSrc op_bwd(const TcCtx3& cx, const Dims& d, int fam, int b, int t) {
+    const int nm = d.B * (d.T - 1), z = fam * 2 * nm + b * (d.T - 1) + t;
+    return OpSrc{&cx.maps->S, z, z + nm};
+}
+__device__ __forceinline__ OpSrc op_frame(const TcCtx3& cx, const Dims& d, int b, int t) {
+    const int z = b * d.T + t;
+    return OpSrc{&cx.maps->E, z, z + d.B * d.T};
+}
 
 // ---- forward problems -----------------------------------------------------------------------------------
 struct AffinityProb {       // batch = b*(T-1) + t :  A_t = E_t E_{t+1}^T / tau
@@ -231,10 +247,7 @@ struct AffinityProb {       // batch = b*(T-1) + t :  A_t = E_t E_{t+1}^T / tau
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const TcArena ar(d, kNumSavedFam, true);
         const int b = z / (d.T - 1), t = z % (d.T - 1), N = d.N;
-        const size_t rows = (size_t)d.B * d.T * N, r0 = ((size_t)b * d.T + t) * N;
-        const bf16* Ehi = c.wa + ar.E;
-        const bf16* Elo = Ehi + rows * ar.CP;
-        const OpSrc A{Ehi + r0 * ar.CP, Elo + r0 * ar.CP, ar.CP, N}, Bm{Ehi + (r0 + N) * ar.CP, Elo + (r0 + N) * ar.CP, ar.CP, N};
+        const OpSrc A = op_frame(cx, d, b, t), Bm = op_frame(cx, d, b, t + 1);
         float* At = c.ws + lay.mat(lay.A, b, t);
         float* Ao = A_out ? A_out + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
         const float it = inv_tau;
@@ -254,8 +267,8 @@ struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} = L_{
         const TcArena ar(d, kNumSavedFam, true);
         const int role = z / d.B, b = z % d.B, N = d.N;
         if (role == 1 && k < 2) return;
-        const OpSrc A = src_of(mat2(c.wa, ar, d, role == 0 ? kFamL : kFamS, b, k - 1), N);      // as stored (K-major)
-        const OpSrc Bm = src_of(mat2(c.wa, ar, d, role == 0 ? kFamQ : kFamR, b, k - 1), N);
+        const OpSrc A = op_saved(cx, d, role == 0 ? kFamL : kFamS, b, k - 1);      // as stored (K-major)
+        const OpSrc Bm = op_saved(cx, d, role == 0 ? kFamQ : kFamR, b, k - 1);
         float* out = c.ws + lay.mat(role == 0 ? lay.L : lay.R, b, k);
         const Mat2 om = mat2(c.wa, ar, d, role == 0 ? kFamL : kFamR, b, k);
         auto epi = [&](int m, int n, float v) {
@@ -275,7 +288,7 @@ struct CycleProb {          // batch = b*K + (k-1) :  M_k = L_k R_k  (raw, into 
         const TcArena ar(d, kNumSavedFam, true);
         const int K = d.T - 2, b = z / K, k = z % K + 1, N = d.N;
         float* G = c.ws + lay.mat(lay.G, b, k);
-        bf_gemm_tile<false, true>(src_of(mat2(c.wa, ar, d, kFamL, b, k), N), src_of(mat2(c.wa, ar, d, kFamR, b, k), N), N, m0, n0, N, cx,
+        bf_gemm_tile<false, true>(op_saved(cx, d, kFamL, b, k), op_saved(cx, d, kFamR, b, k), N, m0, n0, N, cx,
                                   [&](int m, int n, float v) { if (n < N) G[(size_t)m * N + n] = v; });
     }
 };
@@ -291,16 +304,16 @@ struct BwdChainProb {       // batch = role*B + b ; dL~_j = G_j R_j^T + dL~_{j+1
         const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int role = z / d.B, b = z % d.B, N = d.N, K = d.T - 2;
         if (role == 1 && j < 2) return;
-        const OpSrc G = src_of(mat2(c.wa, ar, d, kFamG, b, j), N);
+        const OpSrc G = op_saved(cx, d, kFamG, b, j);
         const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j);
         if (role == 0) {
-            bf_gemm_accumulate<false, false>(G, src_of(mat2(c.wa, ar, d, kFamR, b, j), N), N, m0, n0, cx, true);      // B^T(n,k) = R[n][k]
+            bf_gemm_accumulate<false, false>(G, op_saved(cx, d, kFamR, b, j), N, m0, n0, cx, true);      // B^T(n,k) = R[n][k]
             if (j < K)
-                bf_gemm_accumulate<false, true>(src_of(mat2(c.sa, ab, d, kFamDL, b, j + 1), N), src_of(mat2(c.wa, ar, d, kFamQ, b, j), N), N, m0, n0, cx, false);
+                bf_gemm_accumulate<false, true>(op_bwd(cx, d, kFamDL, b, j + 1), op_saved(cx, d, kFamQ, b, j), N, m0, n0, cx, false);
         } else {
-            bf_gemm_accumulate<true, true>(src_of(mat2(c.wa, ar, d, kFamL, b, j), N), G, N, m0, n0, cx, true);        // A(m,k) = L[k][m]
+            bf_gemm_accumulate<true, true>(op_saved(cx, d, kFamL, b, j), G, N, m0, n0, cx, true);        // A(m,k) = L[k][m]
             if (j < K)
-                bf_gemm_accumulate<true, true>(src_of(mat2(c.wa, ar, d, kFamS, b, j), N), src_of(mat2(c.sa, ab, d, kFamDR, b, j + 1), N), N, m0, n0, cx, false);
+                bf_gemm_accumulate<true, true>(op_saved(cx, d, kFamS, b, j), op_bwd(cx, d, kFamDR, b, j + 1), N, m0, n0, cx, false);
         }
         bf_gemm_epilogue(m0, n0, N, cx, [&](int m, int n, float v) { emit_pad(om, m, n, v, N); });
     }
@@ -318,12 +331,12 @@ struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; dQ_t = s dL~
         if (role == 0) {
             if (t + 1 > K) return;
             float* o = c.sc + lay.mat(bl.dSp, b, t);
-            bf_gemm_tile<true, true>(src_of(mat2(c.sa, ab, d, kFamDL, b, t + 1), N), src_of(mat2(c.wa, ar, d, kFamL, b, t), N), N, m0, n0, N, cx,
+            bf_gemm_tile<true, true>(op_bwd(cx, d, kFamDL, b, t + 1), op_saved(cx, d, kFamL, b, t), N, m0, n0, N, cx,
                                      [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
         } else {
             if (t < 1 || t + 1 > K) return;
             float* o = c.sc + lay.mat(bl.dS, b, t);
-            bf_gemm_tile<false, false>(src_of(mat2(c.sa, ab, d, kFamDR, b, t + 1), N), src_of(mat2(c.wa, ar, d, kFamR, b, t), N), N, m0, n0, N, cx,
+            bf_gemm_tile<false, false>(op_bwd(cx, d, kFamDR, b, t + 1), op_saved(cx, d, kFamR, b, t), N, m0, n0, N, cx,
                                        [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
         }
     }
@@ -336,13 +349,10 @@ struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}
         const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int b = z / d.T, t = z % d.T, N = d.N, C = d.C;
         float* o = dx + ((size_t)b * d.T + t) * N * C;
-        const size_t rows = (size_t)d.B * d.T * N;
-        const bf16* Ehi = c.wa + ar.E;
-        const bf16* Elo = Ehi + rows * ar.CP;
         const float it = inv_tau;
         if (t <= d.T - 2) {
-            const size_t eo = ((size_t)b * d.T + t + 1) * N * ar.CP;      // B(k=j, n=ch) = E_{t+1}[j][ch]: MN-major, MN extent C
-            bf_gemm_tile<false, true>(src_of(mat2(c.sa, ab, d, kFamDA, b, t), N), OpSrc{Ehi + eo, Elo + eo, ar.CP, C}, N, m0, n0, N, cx,
+            // B(k=j, n=ch) = E_{t+1}[j][ch]: MN-major, MN extent C
+            bf_gemm_tile<false, true>(op_bwd(cx, d, kFamDA, b, t), op_frame(cx, d, b, t + 1), N, m0, n0, N, cx,
                                       [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] = v * it; });
         } else {
             for (int e = threadIdx.x; e < kWTile * kWTile; e += kTT) {
@@ -352,8 +362,7 @@ struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}
             __syncthreads();
         }
         if (t >= 1) {
-            const size_t eo = ((size_t)b * d.T + t - 1) * N * ar.CP;
-            bf_gemm_tile<true, true>(src_of(mat2(c.sa, ab, d, kFamDA, b, t - 1), N), OpSrc{Ehi + eo, Elo + eo, ar.CP, C}, N, m0, n0, N, cx,
+            bf_gemm_tile<true, true>(op_bwd(cx, d, kFamDA, b, t - 1), op_frame(cx, d, b, t - 1), N, m0, n0, N, cx,
                                      [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] += v * it; });
         }
     }
@@ -588,7 +597,7 @@ __global__ void __launch_bounds__(256) t_dx_epi_kernel(const float* __restrict__
 
 // ---- host orchestration -----------------------------------------------------------------------------------
 template <class P>
-static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_t st) {
+static int launch_tiles(const P& p, const TMaps& maps, int Mrows, int Ncols, int batch, cudaStream_t st) {
     static bool opted[64] = {};   // per instantiation and device; the attribute is a per-device property of the function
     int dev = 0;
     cudaGetDevice(&dev);
@@ -599,7 +608,7 @@ static int launch_tiles(const P& p, int Mrows, int Ncols, int batch, cudaStream_
     if (batch <= 0) return CRW_OK;
     if (batch > 65535) return CRW_ERR_UNSUPPORTED;       // the batch index rides in grid.z (the fp32 engine has no such limit)
     dim3 grid(ceil_div(Ncols, kWTile), ceil_div(Mrows, kWTile), batch);
-    tc_tiles_kernel<P><<<grid, kTT, kWSmem, st>>>(p);
+    tc_tiles_kernel<P><<<grid, kTT, kWSmem, st>>>(p, maps);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -623,6 +632,19 @@ size_t walk_tiles_scratch_extra_bytes(int B, int T, int N, int C) {
 static bf16* arena_after(float* f32_base, size_t f32_floats) {
     return reinterpret_cast<bf16*>((reinterpret_cast<uintptr_t>(f32_base + f32_floats) + 255) & ~uintptr_t(255));
 }
+// tensor maps over the bf16 arenas (sa = nullptr: forward, no backward families yet)
+static int make_tile_maps(TMaps* m, const Dims& d, bf16* wa, bf16* sa) {
+    const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
+    const uint64_t nm = (uint64_t)d.B * (d.T - 1);
+    memset(m, 0, sizeof(*m));
+    int rc = make_tmap_bf16_mats(&m->E, wa + ar.E, d.C, d.N, 2 * (uint64_t)d.B * d.T, ar.CP);
+    if (rc == CRW_OK) rc = make_tmap_bf16_mats(&m->W, wa + ar.fam0, d.N, d.N, kNumSavedFam * 2 * nm, ar.P);
+    if (rc == CRW_OK) {
+        if (sa) rc = make_tmap_bf16_mats(&m->S, sa + ab.fam0, d.N, d.N, kNumBwdFam * 2 * nm, ab.P);
+        else m->S = m->W;
+    }
+    return rc;
+}
 
 int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, float* loss, float* A_or_null, float* ws,
                        cudaStream_t st) {
@@ -630,10 +652,12 @@ int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, fl
     const WalkLayout lay(B, T, N, C);
     Ctx c{d, ws, arena_after(ws, lay.total), nullptr, nullptr};
     int rc;
+    TMaps maps;
+    if ((rc = make_tile_maps(&maps, d, c.wa, nullptr))) return rc;
     const long long rows = (long long)B * T * N;
     t_rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, c);
     CRW_LAUNCH_RET();
-    if ((rc = launch_tiles(AffinityProb{c, A_or_null, 1.0f / tau}, N, N, B * (T - 1), st))) return rc;
+    if ((rc = launch_tiles(AffinityProb{c, A_or_null, 1.0f / tau}, maps, N, N, B * (T - 1), st))) return rc;
     if (T < 3) {
         t_zero_loss_kernel<<<1, 1, 0, st>>>(loss);
         CRW_LAUNCH_RET();
@@ -646,8 +670,8 @@ int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, fl
     CRW_LAUNCH_RET();
     const int K = T - 2;
     for (int k = 1; k <= K; ++k)
-        if ((rc = launch_tiles(ChainProb{c, k}, N, N, k >= 2 ? 2 * B : B, st))) return rc;
-    if ((rc = launch_tiles(CycleProb{c}, N, N, B * K, st))) return rc;
+        if ((rc = launch_tiles(ChainProb{c, k}, maps, N, N, k >= 2 ? 2 * B : B, st))) return rc;
+    if ((rc = launch_tiles(CycleProb{c}, maps, N, N, B * K, st))) return rc;
     t_cycle_epi_kernel<<<dim3(K, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
     t_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, d);
@@ -663,16 +687,18 @@ int walk_tiles_backward(const float* x, const float* ws_c, const float* dloss, c
     float* ws = const_cast<float*>(ws_c);
     Ctx c{d, ws, arena_after(ws, lay.total), sc, arena_after(sc, bl.total)};
     int rc;
+    TMaps maps;
+    if ((rc = make_tile_maps(&maps, d, c.wa, c.sa))) return rc;
     const int K = T - 2;
     if (T >= 3) {
         for (int j = K; j >= 1; --j)
-            if ((rc = launch_tiles(BwdChainProb{c, j}, N, N, j >= 2 ? 2 * B : B, st))) return rc;
-        if ((rc = launch_tiles(DsProb{c, dloss}, N, N, 2 * B * (T - 1), st))) return rc;
+            if ((rc = launch_tiles(BwdChainProb{c, j}, maps, N, N, j >= 2 ? 2 * B : B, st))) return rc;
+        if ((rc = launch_tiles(DsProb{c, dloss}, maps, N, N, 2 * B * (T - 1), st))) return rc;
     }
     if ((rc = opt_in_rowwise_smem(t_dA_epi_kernel, N))) return rc;
     t_dA_epi_kernel<<<dim3(T - 1, B), 256, 10 * N * sizeof(float), st>>>(c, dA_or_null);
     CRW_LAUNCH_RET();
-    if ((rc = launch_tiles(DxProb{c, dx, 1.0f / tau}, N, C, B * T, st))) return rc;
+    if ((rc = launch_tiles(DxProb{c, dx, 1.0f / tau}, maps, N, C, B * T, st))) return rc;
     t_dx_epi_kernel<<<dim3(T, B), 256, 0, st>>>(x, ws, dx, d);
     CRW_LAUNCH_RET();
     return CRW_OK;
