@@ -20,10 +20,11 @@
 #include "common.cuh"
 #include "walk_layout.cuh"
 #include "tc_common.cuh"
+#include <algorithm>
+#include <cstring>
 
 namespace crw {
 
-constexpr int kTT = 256;
 typedef __nv_bfloat16 bf16;
 
 constexpr int kWTile = 128;                       // output tile
@@ -31,7 +32,6 @@ constexpr int kWChunk = 64;                       // k elements per stage
 constexpr int kWOperand = kWTile * 128;           // one operand plane of one stage: 16 KB (K-major and MN-major alike)
 constexpr int kWStage = 4 * kWOperand;            // A_hi, A_lo, B_hi, B_lo
 constexpr int kWStages = 3;
-constexpr int kWSmem = kWStages * kWStage + 1024;
 
 struct Dims { int B, T, N, C; };
 
@@ -40,13 +40,13 @@ enum { kFamS = 0, kFamQ, kFamL, kFamR, kFamG, kNumSavedFam };       // saved are
 enum { kFamDL = 0, kFamDR, kFamDA, kNumBwdFam };                    // scratch arena (backward state)
 
 struct TcArena {
-    int P;                       // row pitch of N x N planes (N rounded up to 8 elements = 16 bytes)
+    int P;                       // row pitch of N x N planes (N rounded up to 64 elements = 128 bytes)
     int CP;                      // row pitch of the E planes (C rounded up likewise)
     size_t plane;                // B*(T-1)*N*P elements: one plane of one family
     size_t E, fam0, total;       // offsets in bf16 elements
     __host__ __device__ TcArena(const Dims& d, int nfam, bool with_E) {
-        P = (d.N + 7) & ~7;
-        CP = (d.C + 7) & ~7;
+        P = (d.N + 63) & ~63;        // 128-byte rows: every row of a 64 x 64 TMA box is exactly one aligned L2 line
+        CP = (d.C + 63) & ~63;
         plane = (size_t)d.B * (d.T - 1) * d.N * P;
         size_t o = 0;
         E = o; if (with_E) o += 2 * (size_t)d.B * d.T * d.N * CP;            // hi, lo   [B*T*N][CP]
@@ -77,13 +77,19 @@ __device__ __forceinline__ void zero_row_pad(const Mat2& mt, int r, int N, int l
     for (int c = N + lane; c < mt.P; c += 32) { mt.hi[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); }
 }
 
-// ---- one 128 x 128 tile from bf16 planes -----------------------------------------------------------------
+// ---- persistent tile engine ------------------------------------------------------------------------------
 // K-major use: logical X(r,k) = plane[r*pitch + k]; MN-major use: X(r,k) = plane[k*pitch + r].  An operand is the hi / lo
 // matrix pair `zhi`, `zlo` (indices along the third dimension) of one tensor map.
 struct OpSrc { const CUtensorMap* map; int zhi, zlo; };
 struct TMaps { CUtensorMap E, W, S; };      // E planes [2*B*T][N][C]; saved families [5*2*B*(T-1)][N][N]; backward families [3*2*B*(T-1)][N][N]
 
-struct TcCtx3 { uint8_t* buf; uint64_t* full; uint64_t* empty; uint64_t* acc; uint32_t tmem; uint32_t g, tiles; const TMaps* maps; };
+struct Pipe {
+    uint8_t* buf;                       // kWStages stages of [A_hi | A_lo | B_hi | B_lo]
+    uint64_t *full, *empty;             // per stage: TMA bytes landed / the MMAs that read it retired
+    uint64_t *tfull, *tempty;           // per accumulator (two of 128 TMEM columns): tile accumulated / tile drained
+    uint32_t tmem;
+    const TMaps* maps;
+};
 
 // one operand plane of one stage: 16 KB = two 64 x 64 boxes
 template <bool MN>
@@ -97,111 +103,167 @@ __device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* map
     }
 }
 
-// epi(m, n, value) is called for every row m < Mvalid of the tile and every column n of the tile (the caller clips n
-// against its own extents and pitch).  The accumulator goes TMEM -> registers (thread = row) -> shared memory ->
-// registers (warp = row, lane = column) so that every global access of the epilogue is coalesced.
-constexpr int kEpPitch = 132;      // floats; 528-byte rows: 16-byte aligned, conflict-free for the v4 stores of phase 1
-// acc (TMEM) = (fresh ? 0 : acc) + A B over the whole K extent; several calls may accumulate into one tile.  cx.g counts
-// the k-chunks this CTA has ever staged: chunk g lives in stage g % 3, its barriers are in phase (g / 3) & 1.
-template <bool A_MN, bool B_MN>
-__device__ __forceinline__ void bf_gemm_accumulate(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, TcCtx3& cx, bool fresh) {
-    const uint32_t idesc = tc::umma_idesc_bf16_major(kWTile, kWTile, A_MN, B_MN);
-    const int nchunks = (K + kWChunk - 1) / kWChunk, warp = threadIdx.x >> 5;
-    if (warp == 0) {
-        if (tc::elect_one()) {
-            for (int c = 0; c < nchunks; ++c) {
-                const uint32_t g = cx.g + c, s = g % kWStages;
-                if (g >= kWStages) tc::mbar_wait(&cx.empty[s], (g / kWStages - 1) & 1);      // MMAs that read this stage retired
-                tc::mbar_arrive_expect_tx(&cx.full[s], kWStage);
-                const uint32_t base = tc::smem_u32(cx.buf + s * kWStage);
-                tma_operand<A_MN>(base, A.map, A.zhi, m0, c * kWChunk, &cx.full[s]);
-                tma_operand<A_MN>(base + kWOperand, A.map, A.zlo, m0, c * kWChunk, &cx.full[s]);
-                tma_operand<B_MN>(base + 2 * kWOperand, B.map, B.zhi, n0, c * kWChunk, &cx.full[s]);
-                tma_operand<B_MN>(base + 3 * kWOperand, B.map, B.zlo, n0, c * kWChunk, &cx.full[s]);
-            }
+// A problem describes a tile's products once (`mainloop`); the producer lane runs it with a Loader, the MMA lane with an
+// Issuer.  g counts the k-chunks this CTA has ever staged: chunk g lives in stage g % 3, its barriers are in phase (g / 3) & 1.
+struct Loader {
+    const Pipe& pp; const TMaps* maps; uint32_t g;
+    template <bool A_MN, bool B_MN>
+    __device__ __forceinline__ void mm(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, bool) {
+        const int nchunks = (K + kWChunk - 1) / kWChunk;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+            const uint32_t s = g % kWStages;
+            if (g >= kWStages) tc::mbar_wait(&pp.empty[s], (g / kWStages - 1) & 1);
+            tc::mbar_arrive_expect_tx(&pp.full[s], kWStage);
+            const uint32_t base = tc::smem_u32(pp.buf + s * kWStage);
+            tma_operand<A_MN>(base, A.map, A.zhi, m0, c * kWChunk, &pp.full[s]);
+            tma_operand<A_MN>(base + kWOperand, A.map, A.zlo, m0, c * kWChunk, &pp.full[s]);
+            tma_operand<B_MN>(base + 2 * kWOperand, B.map, B.zhi, n0, c * kWChunk, &pp.full[s]);
+            tma_operand<B_MN>(base + 3 * kWOperand, B.map, B.zlo, n0, c * kWChunk, &pp.full[s]);
         }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (tc::elect_one()) {
-            for (int c = 0; c < nchunks; ++c) {
-                const uint32_t g = cx.g + c, s = g % kWStages;
-                tc::mbar_wait(&cx.full[s], (g / kWStages) & 1);
-                tc::tc_fence_after();
-                const uint32_t a0 = tc::smem_u32(cx.buf + s * kWStage), b0 = a0 + 2 * kWOperand;
+    }
+};
+struct Issuer {
+    const Pipe& pp; const TMaps* maps; uint32_t g; uint32_t acc;     // acc = TMEM address of this tile's accumulator
+    template <bool A_MN, bool B_MN>
+    __device__ __forceinline__ void mm(const OpSrc&, const OpSrc&, int K, int, int, bool fresh) {
+        const uint32_t idesc = tc::umma_idesc_bf16_major(kWTile, kWTile, A_MN, B_MN);
+        const int nchunks = (K + kWChunk - 1) / kWChunk;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+            const uint32_t s = g % kWStages;
+            tc::mbar_wait(&pp.full[s], (g / kWStages) & 1);
+            tc::tc_fence_after();
+            const uint32_t a0 = tc::smem_u32(pp.buf + s * kWStage), b0 = a0 + 2 * kWOperand;
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t ap = a0 + ((pass == 2) ? kWOperand : 0), bp = b0 + ((pass == 1) ? kWOperand : 0);
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t ap = a0 + ((pass == 2) ? kWOperand : 0), bp = b0 + ((pass == 1) ? kWOperand : 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
-                        const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
-                        tc::umma_bf16_ss(cx.tmem, ad, bd, idesc, (!fresh || (c | pass | ks)) ? 1u : 0u);
-                    }
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = A_MN ? tc::umma_smem_desc_mn128(ap + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(ap + ks * 32);
+                    const uint64_t bd = B_MN ? tc::umma_smem_desc_mn128(bp + ks * 2048, 8192, 1024) : tc::umma_smem_desc_k128(bp + ks * 32);
+                    tc::umma_bf16_ss(acc, ad, bd, idesc, (!fresh || (c | pass | ks)) ? 1u : 0u);
                 }
-                tc::umma_commit(&cx.empty[s]);
+            }
+            tc::umma_commit(&pp.empty[s]);
+        }
+    }
+};
+// Eight epilogue warps: warp w owns the 32 accumulator rows of TMEM lane quarter w & 3 and two of the tile's four
+// 32-column chunks; no CTA-wide barrier is involved.  Two ways out of the accumulator:
+//   planes()  bf16 hi / lo operand planes straight from the registers: thread = row holds 32 consecutive columns = 64
+//             bytes of each plane, 64-byte aligned (pitch and chunk are multiples of 64 / 32 elements): packed converts
+//             and four 16-byte stores per plane -- ~4 instructions per element pair;
+//   f32()     a row-major fp32 matrix of ANY pitch (N is odd in general, rows are only 4-byte aligned): TMEM -> registers
+//             (thread = row) -> the warp's own XOR-swizzled staging block -> registers (lane = column), so every store
+//             instruction writes 128 contiguous bytes.
+constexpr int kEpWarps = 8;
+constexpr int kEpStage = 32 * 32 * 4;               // bytes per epilogue warp
+__device__ __forceinline__ uint32_t bf162_bits(const __nv_bfloat162& h) { return *reinterpret_cast<const uint32_t*>(&h); }
+struct Drainer {
+    const TMaps* maps; uint32_t acc; float* stg;
+    // pads: columns N <= n < pitch are written as zero, rows >= Mvalid not at all
+    __device__ __forceinline__ void planes(int m0, int n0, int Mvalid, const Mat2& om, int N) {
+        const int w = (threadIdx.x >> 5) - 2, q = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+        if (m0 + q * 32 >= Mvalid) return;
+        const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int ch = 2 * (w >> 2); ch < 2 * (w >> 2) + 2; ++ch) {
+            const int nb = n0 + ch * 32;
+            if (nb >= om.P) break;
+            float v[32];
+            tc::tmem_ld_32x32b_x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+            tc::tmem_ld_wait();
+            if (nb + 32 > N) {
+#pragma unroll
+                for (int cc = 0; cc < 32; ++cc)
+                    if (nb + cc >= N) v[cc] = 0.0f;
+            }
+            if (m < Mvalid) {
+                uint4* ph = reinterpret_cast<uint4*>(om.hi + (size_t)m * om.P + nb);
+                uint4* pl = reinterpret_cast<uint4*>(om.lo + (size_t)m * om.P + nb);
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x = v[g4 * 8 + 2 * j], y = v[g4 * 8 + 2 * j + 1];
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
+                        h[j] = bf162_bits(hh);
+                        l[j] = bf162_bits(__floats2bfloat162_rn(x - __low2float(hh), y - __high2float(hh)));
+                    }
+                    ph[g4] = make_uint4(h[0], h[1], h[2], h[3]);
+                    pl[g4] = make_uint4(l[0], l[1], l[2], l[3]);
+                }
             }
         }
-        __syncwarp();
     }
-    cx.g += nchunks;
-}
-template <class Epi>
-__device__ __forceinline__ void bf_gemm_epilogue(int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // one commit per tile on a barrier of its own: the warps that took no part in the staging arrive here at once, and a
-    // parity wait on a STAGE barrier would alias with that stage's previous use still in flight
-    if (warp == 1) {
-        if (tc::elect_one()) tc::umma_commit(cx.acc);      // tracks every MMA of this tile: all stages idle when it fires
-        __syncwarp();
-    }
-    tc::mbar_wait(cx.acc, cx.tiles & 1);
-    cx.tiles++;
-    tc::tc_fence_after();
-    float* ep = reinterpret_cast<float*>(cx.buf);
-    {
-        const int g = warp & 3, half = warp >> 2;
-        float* row = ep + (g * 32 + lane) * kEpPitch + half * 64;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+    // out[m * pitch + n] = acc * scale for m < Mvalid, n < Nvalid (and the same into out2 when given)
+    __device__ __forceinline__ void f32(int m0, int n0, int Mvalid, int Nvalid, float* out, int pitch, float scale, float* out2 = nullptr) {
+        const int w = (threadIdx.x >> 5) - 2, q = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+        const int rows = min(32, Mvalid - (m0 + q * 32));
+        if (rows <= 0) return;
+#pragma unroll 1
+        for (int ch = 2 * (w >> 2); ch < 2 * (w >> 2) + 2; ++ch) {
+            const int nb = n0 + ch * 32;
+            if (nb >= Nvalid) break;
             float v[32];
-            tc::tmem_ld_32x32b_x32(cx.tmem + ((uint32_t)(g * 32) << 16) + (uint32_t)(half * 64 + ch * 32), v);
+            tc::tmem_ld_32x32b_x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(row + ch * 32 + q * 4) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            for (int cc = 0; cc < 32; ++cc) stg[lane * 32 + (cc ^ lane)] = v[cc] * scale;
+            __syncwarp();
+            const bool cok = nb + lane < Nvalid;
+            const size_t off = (size_t)(m0 + q * 32) * pitch + nb + lane;
+            float* o = out + off;
+            if (rows == 32) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const float x = stg[r * 32 + (lane ^ r)];
+                    if (cok) o[(size_t)r * pitch] = x;
+                }
+                if (out2) {
+                    float* o2 = out2 + off;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const float x = stg[r * 32 + (lane ^ r)];
+                        if (cok) o2[(size_t)r * pitch] = x;
+                    }
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float x = stg[r * 32 + (lane ^ r)];
+                    if (cok) {
+                        o[(size_t)r * pitch] = x;
+                        if (out2) out2[off + (size_t)r * pitch] = x;
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
-    tc::tc_fence_before();
-    __syncthreads();
-    for (int r = warp; r < kWTile && m0 + r < Mvalid; r += 8) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) epi(m0 + r, n0 + lane + 32 * q, ep[r * kEpPitch + lane + 32 * q]);
-    }
-    tc::fence_proxy_async();   // this tile's generic-proxy use of the staging buffer is ordered before the next tile's TMA writes
-    __syncthreads();           // the staging buffer and TMEM are reused by the next tile
-}
-template <bool A_MN, bool B_MN, class Epi>
-__device__ __forceinline__ void bf_gemm_tile(const OpSrc& A, const OpSrc& B, int K, int m0, int n0, int Mvalid, TcCtx3& cx, Epi epi) {
-    bf_gemm_accumulate<A_MN, B_MN>(A, B, K, m0, n0, cx, true);
-    bf_gemm_epilogue(m0, n0, Mvalid, cx, epi);
-}
+};
+
+constexpr int kTT = 32 * (2 + kEpWarps);          // warp 0: TMA lane, warp 1: MMA lane (owns TMEM), warps 2-9: epilogue
+constexpr int kWSmem = kWStages * kWStage + kEpWarps * kEpStage + 1024;
+struct TileGrid { int tiles_m, tiles_n, batch; };
 
 template <class P>
-__global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(const __grid_constant__ P p, const __grid_constant__ TMaps maps) {
+__global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(const __grid_constant__ P p, const __grid_constant__ TMaps maps, TileGrid tg) {
     extern __shared__ uint8_t tc_raw[];
-    __shared__ uint64_t bars[2 * kWStages + 1];
+    __shared__ uint64_t bars[2 * kWStages + 4];
     __shared__ uint32_t slot;
-    TcCtx3 cx;
-    cx.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
-    cx.full = bars;
-    cx.empty = bars + kWStages;
-    cx.acc = bars + 2 * kWStages;
-    cx.g = 0;
-    cx.tiles = 0;
-    cx.maps = &maps;
-    if ((threadIdx.x >> 5) == 0) tc::tmem_alloc<128>(&slot);
+    Pipe pp;
+    pp.buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
+    pp.full = bars;
+    pp.empty = bars + kWStages;
+    pp.tfull = bars + 2 * kWStages;
+    pp.tempty = bars + 2 * kWStages + 2;
+    pp.maps = &maps;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 1) tc::tmem_alloc<256>(&slot);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2 * kWStages + 1; ++s) tc::mbar_init(&bars[s], 1);
+        for (int s = 0; s < 2 * kWStages + 2; ++s) tc::mbar_init(&bars[s], 1);
+        tc::mbar_init(&pp.tempty[0], kEpWarps);
+        tc::mbar_init(&pp.tempty[1], kEpWarps);
         tc::fence_barrier_init();
         tc::prefetch_tmap(&maps.E);
         tc::prefetch_tmap(&maps.W);
@@ -210,11 +272,57 @@ __global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(const __grid_constant_
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    cx.tmem = slot;
-    p.run((int)blockIdx.z, (int)blockIdx.y * kWTile, (int)blockIdx.x * kWTile, cx);
+    pp.tmem = slot;
+    const int per_z = tg.tiles_m * tg.tiles_n, total = per_z * tg.batch;
+    // every role walks the same tile sequence; n counts the tiles this CTA actually works on: accumulator n & 1, use n >> 1
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            Loader ld{pp, &maps, 0};
+            for (int i = blockIdx.x; i < total; i += gridDim.x) {
+                const int z = i / per_z, r = i % per_z;
+                if (p.active(z)) p.mainloop(z, (r / tg.tiles_n) * kWTile, (r % tg.tiles_n) * kWTile, ld);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            Issuer is{pp, &maps, 0, 0};
+            uint32_t n = 0;
+            for (int i = blockIdx.x; i < total; i += gridDim.x) {
+                const int z = i / per_z, r = i % per_z;
+                if (!p.active(z)) continue;
+                const uint32_t a = n & 1, u = n >> 1;
+                if (u >= 1) {
+                    tc::mbar_wait(&pp.tempty[a], (u - 1) & 1);       // the tile two back has left this accumulator
+                    tc::tc_fence_after();
+                }
+                is.acc = pp.tmem + a * kWTile;
+                p.mainloop(z, (r / tg.tiles_n) * kWTile, (r % tg.tiles_n) * kWTile, is);
+                tc::umma_commit(&pp.tfull[a]);                        // tracks every MMA of the tile
+                ++n;
+            }
+        }
+        __syncwarp();
+    } else {
+        Drainer dr{&maps, 0, reinterpret_cast<float*>(pp.buf + kWStages * kWStage + (warp - 2) * kEpStage)};
+        uint32_t n = 0;
+        for (int i = blockIdx.x; i < total; i += gridDim.x) {
+            const int z = i / per_z, r = i % per_z;
+            if (!p.active(z)) continue;
+            const uint32_t a = n & 1, u = n >> 1;
+            tc::mbar_wait(&pp.tfull[a], u & 1);
+            tc::tc_fence_after();
+            dr.acc = pp.tmem + a * kWTile;
+            p.epilogue(z, (r / tg.tiles_n) * kWTile, (r % tg.tiles_n) * kWTile, dr);
+            tc::tc_fence_before();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&pp.tempty[a]);
+            ++n;
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc<128>(cx.tmem);
+    if (warp == 1) tc::tmem_dealloc<256>(pp.tmem);
 }
 
 // pointers every problem needs
@@ -226,70 +334,74 @@ struct Ctx {
     bf16* sa;         // bf16 backward arena
 };
 // matrix (fam, b, t) of the saved / backward families, frame (b, t) of the E planes: indices along the maps' third dimension
-__device__ __forceinline__ OpSrc op_saved(const TcCtx3& cx, const Dims& d, int fam, int b, int t) {
+__device__ __forceinline__ OpSrc op_saved(const TMaps* m, const Dims& d, int fam, int b, int t) {
     const int nm = d.B * (d.T - 1), z = fam * 2 * nm + b * (d.T - 1) + t;
-    return OpSrc{&cx.maps->W, z, z + nm};
+    return OpSrc{&m->W, z, z + nm};
 }
-__device__ __forceinline__ OpSrc op_bwd(const TcCtx3& cx, const Dims& d, int fam, int b, int t) {
+__device__ __forceinline__ OpSrc op_bwd(const TMaps* m, const Dims& d, int fam, int b, int t) {
     const int nm = d.B * (d.T - 1), z = fam * 2 * nm + b * (d.T - 1) + t;
-    return OpSrc{&cx.maps->S, z, z + nm};
+    return OpSrc{&m->S, z, z + nm};
 }
-__device__ __forceinline__ OpSrc op_frame(const TcCtx3& cx, const Dims& d, int b, int t) {
+__device__ __forceinline__ OpSrc op_frame(const TMaps* m, const Dims& d, int b, int t) {
     const int z = b * d.T + t;
-    return OpSrc{&cx.maps->E, z, z + d.B * d.T};
+    return OpSrc{&m->E, z, z + d.B * d.T};
 }
 
 // ---- forward problems -----------------------------------------------------------------------------------
 struct AffinityProb {       // batch = b*(T-1) + t :  A_t = E_t E_{t+1}^T / tau
     Ctx c; float* A_out; float inv_tau;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int) const { return true; }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
+        const Dims& d = c.d;
+        const int b = z / (d.T - 1), t = z % (d.T - 1);
+        g.template mm<false, false>(op_frame(g.maps, d, b, t), op_frame(g.maps, d, b, t + 1), d.C, m0, n0, true);
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
         const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
-        const TcArena ar(d, kNumSavedFam, true);
         const int b = z / (d.T - 1), t = z % (d.T - 1), N = d.N;
-        const OpSrc A = op_frame(cx, d, b, t), Bm = op_frame(cx, d, b, t + 1);
         float* At = c.ws + lay.mat(lay.A, b, t);
         float* Ao = A_out ? A_out + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
-        const float it = inv_tau;
-        bf_gemm_tile<false, false>(A, Bm, d.C, m0, n0, N, cx, [&](int m, int n, float v) {
-            if (n >= N) return;
-            At[(size_t)m * N + n] = v * it;
-            if (Ao) Ao[(size_t)m * N + n] = v * it;
-        });
+        dr.f32(m0, n0, N, N, At, N, inv_tau, Ao);
     }
 };
 
 struct ChainProb {          // batch = role*B + b ; L_k = L_{k-1} S'_{k-1} = L_{k-1} Q_{k-1}^T ;  R_k = S_{k-1} R_{k-1}
     Ctx c; int k;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int z) const { return !(z / c.d.B == 1 && k < 2); }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
         const Dims& d = c.d;
-        const WalkLayout lay(d.B, d.T, d.N, d.C);
+        const int role = z / d.B, b = z % d.B, N = d.N;
+        const OpSrc A = op_saved(g.maps, d, role == 0 ? kFamL : kFamS, b, k - 1);      // as stored (K-major)
+        const OpSrc Bm = op_saved(g.maps, d, role == 0 ? kFamQ : kFamR, b, k - 1);
+        if (role == 0) g.template mm<false, false>(A, Bm, N, m0, n0, true);             // B(k,n) = Q[n][k]: K-major
+        else g.template mm<false, true>(A, Bm, N, m0, n0, true);                        // B(k,n) = R[k][n]: MN-major
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
+        const Dims& d = c.d;
         const TcArena ar(d, kNumSavedFam, true);
         const int role = z / d.B, b = z % d.B, N = d.N;
-        if (role == 1 && k < 2) return;
-        const OpSrc A = op_saved(cx, d, role == 0 ? kFamL : kFamS, b, k - 1);      // as stored (K-major)
-        const OpSrc Bm = op_saved(cx, d, role == 0 ? kFamQ : kFamR, b, k - 1);
-        float* out = c.ws + lay.mat(role == 0 ? lay.L : lay.R, b, k);
-        const Mat2 om = mat2(c.wa, ar, d, role == 0 ? kFamL : kFamR, b, k);
-        auto epi = [&](int m, int n, float v) {
-            if (n < N) out[(size_t)m * N + n] = v;
-            emit_pad(om, m, n, v, N);
-        };
-        if (role == 0) bf_gemm_tile<false, false>(A, Bm, N, m0, n0, N, cx, epi);    // B(k,n) = Q[n][k]: K-major
-        else bf_gemm_tile<false, true>(A, Bm, N, m0, n0, N, cx, epi);               // B(k,n) = R[k][n]: MN-major
+        dr.planes(m0, n0, N, mat2(c.wa, ar, d, role == 0 ? kFamL : kFamR, b, k), N);      // only ever used as operands: no fp32 copy
     }
 };
 
 struct CycleProb {          // batch = b*K + (k-1) :  M_k = L_k R_k  (raw, into the G slot)
     Ctx c;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int) const { return true; }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
+        const Dims& d = c.d;
+        const int K = d.T - 2, b = z / K, k = z % K + 1;
+        g.template mm<false, true>(op_saved(g.maps, d, kFamL, b, k), op_saved(g.maps, d, kFamR, b, k), d.N, m0, n0, true);
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
         const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
-        const TcArena ar(d, kNumSavedFam, true);
         const int K = d.T - 2, b = z / K, k = z % K + 1, N = d.N;
         float* G = c.ws + lay.mat(lay.G, b, k);
-        bf_gemm_tile<false, true>(op_saved(cx, d, kFamL, b, k), op_saved(cx, d, kFamR, b, k), N, m0, n0, N, cx,
-                                  [&](int m, int n, float v) { if (n < N) G[(size_t)m * N + n] = v; });
+        dr.f32(m0, n0, N, N, G, N, 1.0f);
     }
 };
 
@@ -299,72 +411,70 @@ struct CycleProb {          // batch = b*K + (k-1) :  M_k = L_k R_k  (raw, into 
 // term and the propagated term, and only the bf16 planes of dL~ / dR~ are ever written.
 struct BwdChainProb {       // batch = role*B + b ; dL~_j = G_j R_j^T + dL~_{j+1} Q_j ;  dR~_j = L_j^T G_j + S_j^T dR~_{j+1}
     Ctx c; int j;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int z) const { return !(z / c.d.B == 1 && j < 2); }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
         const Dims& d = c.d;
-        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
         const int role = z / d.B, b = z % d.B, N = d.N, K = d.T - 2;
-        if (role == 1 && j < 2) return;
-        const OpSrc G = op_saved(cx, d, kFamG, b, j);
-        const Mat2 om = mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j);
+        const OpSrc Gj = op_saved(g.maps, d, kFamG, b, j);
         if (role == 0) {
-            bf_gemm_accumulate<false, false>(G, op_saved(cx, d, kFamR, b, j), N, m0, n0, cx, true);      // B^T(n,k) = R[n][k]
-            if (j < K)
-                bf_gemm_accumulate<false, true>(op_bwd(cx, d, kFamDL, b, j + 1), op_saved(cx, d, kFamQ, b, j), N, m0, n0, cx, false);
+            g.template mm<false, false>(Gj, op_saved(g.maps, d, kFamR, b, j), N, m0, n0, true);      // B^T(n,k) = R[n][k]
+            if (j < K) g.template mm<false, true>(op_bwd(g.maps, d, kFamDL, b, j + 1), op_saved(g.maps, d, kFamQ, b, j), N, m0, n0, false);
         } else {
-            bf_gemm_accumulate<true, true>(op_saved(cx, d, kFamL, b, j), G, N, m0, n0, cx, true);        // A(m,k) = L[k][m]
-            if (j < K)
-                bf_gemm_accumulate<true, true>(op_saved(cx, d, kFamS, b, j), op_bwd(cx, d, kFamDR, b, j + 1), N, m0, n0, cx, false);
+            g.template mm<true, true>(op_saved(g.maps, d, kFamL, b, j), Gj, N, m0, n0, true);        // A(m,k) = L[k][m]
+            if (j < K) g.template mm<true, true>(op_saved(g.maps, d, kFamS, b, j), op_bwd(g.maps, d, kFamDR, b, j + 1), N, m0, n0, false);
         }
-        bf_gemm_epilogue(m0, n0, N, cx, [&](int m, int n, float v) { emit_pad(om, m, n, v, N); });
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
+        const Dims& d = c.d;
+        const TcArena ab(d, kNumBwdFam, false);
+        const int role = z / d.B, b = z % d.B, N = d.N;
+        dr.planes(m0, n0, N, mat2(c.sa, ab, d, role == 0 ? kFamDL : kFamDR, b, j), N);
     }
 };
 
 struct DsProb {             // batch = role*B*(T-1) + b*(T-1) + t ; dQ_t = s dL~_{t+1}^T L_t  (= (L_t^T dL_{t+1})^T) ; dS_t = s dR~_{t+1} R_t^T
     Ctx c; const float* dloss;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int z) const {
+        const Dims& d = c.d;
+        const int K = d.T - 2, nt = d.T - 1, role = z / (d.B * nt), t = (z % (d.B * nt)) % nt;
+        return role == 0 ? (t + 1 <= K) : (t >= 1 && t + 1 <= K);
+    }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
+        const Dims& d = c.d;
+        const int N = d.N, nt = d.T - 1, role = z / (d.B * nt), r = z % (d.B * nt), b = r / nt, t = r % nt;
+        if (role == 0) g.template mm<true, true>(op_bwd(g.maps, d, kFamDL, b, t + 1), op_saved(g.maps, d, kFamL, b, t), N, m0, n0, true);
+        else g.template mm<false, false>(op_bwd(g.maps, d, kFamDR, b, t + 1), op_saved(g.maps, d, kFamR, b, t), N, m0, n0, true);
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
         const Dims& d = c.d;
         const WalkLayout lay(d.B, d.T, d.N, d.C);
         const BwdLayout bl(d.B, d.T, d.N);
-        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
-        const int K = d.T - 2, N = d.N, nt = d.T - 1, role = z / (d.B * nt), r = z % (d.B * nt), b = r / nt, t = r % nt;
+        const int N = d.N, nt = d.T - 1, role = z / (d.B * nt), r = z % (d.B * nt), b = r / nt, t = r % nt;
         const float s = *dloss / ((float)d.B * (float)N * (float)N);
-        if (role == 0) {
-            if (t + 1 > K) return;
-            float* o = c.sc + lay.mat(bl.dSp, b, t);
-            bf_gemm_tile<true, true>(op_bwd(cx, d, kFamDL, b, t + 1), op_saved(cx, d, kFamL, b, t), N, m0, n0, N, cx,
-                                     [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
-        } else {
-            if (t < 1 || t + 1 > K) return;
-            float* o = c.sc + lay.mat(bl.dS, b, t);
-            bf_gemm_tile<false, false>(op_bwd(cx, d, kFamDR, b, t + 1), op_saved(cx, d, kFamR, b, t), N, m0, n0, N, cx,
-                                       [&](int m, int n, float v) { if (n < N) o[(size_t)m * N + n] = v * s; });
-        }
+        float* o = c.sc + lay.mat(role == 0 ? bl.dSp : bl.dS, b, t);
+        dr.f32(m0, n0, N, N, o, N, s);
     }
 };
 
-struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau
+struct DxProb {             // batch = b*T + t ; dE_t = (dA_t E_{t+1} + dA_{t-1}^T E_{t-1}) / tau, both products in one accumulator
     Ctx c; float* dx; float inv_tau;
-    __device__ void run(int z, int m0, int n0, TcCtx3& cx) const {
+    __device__ bool active(int) const { return true; }
+    template <class G>
+    __device__ void mainloop(int z, int m0, int n0, G& g) const {
         const Dims& d = c.d;
-        const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
+        const int b = z / d.T, t = z % d.T, N = d.N;
+        const bool first = t <= d.T - 2;
+        if (first)      // B(k=j, n=ch) = E_{t+1}[j][ch]: MN-major, MN extent C
+            g.template mm<false, true>(op_bwd(g.maps, d, kFamDA, b, t), op_frame(g.maps, d, b, t + 1), N, m0, n0, true);
+        if (t >= 1) g.template mm<true, true>(op_bwd(g.maps, d, kFamDA, b, t - 1), op_frame(g.maps, d, b, t - 1), N, m0, n0, !first);
+    }
+    __device__ void epilogue(int z, int m0, int n0, Drainer& dr) const {
+        const Dims& d = c.d;
         const int b = z / d.T, t = z % d.T, N = d.N, C = d.C;
         float* o = dx + ((size_t)b * d.T + t) * N * C;
-        const float it = inv_tau;
-        if (t <= d.T - 2) {
-            // B(k=j, n=ch) = E_{t+1}[j][ch]: MN-major, MN extent C
-            bf_gemm_tile<false, true>(op_bwd(cx, d, kFamDA, b, t), op_frame(cx, d, b, t + 1), N, m0, n0, N, cx,
-                                      [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] = v * it; });
-        } else {
-            for (int e = threadIdx.x; e < kWTile * kWTile; e += kTT) {
-                const int m = m0 + e / kWTile, ch = n0 + e % kWTile;
-                if (m < N && ch < C) o[(size_t)m * C + ch] = 0.0f;
-            }
-            __syncthreads();
-        }
-        if (t >= 1) {
-            bf_gemm_tile<true, true>(op_bwd(cx, d, kFamDA, b, t - 1), op_frame(cx, d, b, t - 1), N, m0, n0, N, cx,
-                                     [&](int m, int n, float v) { if (n < C) o[(size_t)m * C + n] += v * it; });
-        }
+        dr.f32(m0, n0, N, C, o, C, inv_tau);
     }
 };
 
@@ -393,184 +503,215 @@ __global__ void __launch_bounds__(256) t_rownorm_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) t_identity_kernel(Ctx c) {   // L_0 = I, R_1 = I
+// L_0 = I, R_1 = I as operand planes (the fp32 L / R slots of the workspace hold no matrices on this path: the chain
+// products are only ever operands -- the slots carry the column statistics and the loss partials instead).
+// grid (ceil(N * P / 8 / 256), B): one 16-byte store per thread and plane
+__global__ void __launch_bounds__(256) t_identity_kernel(Ctx c) {
     const Dims& d = c.d;
-    const WalkLayout lay(d.B, d.T, d.N, d.C);
     const TcArena ar(d, kNumSavedFam, true);
-    const int b = blockIdx.x, N = d.N;
-    float* L0 = c.ws + lay.mat(lay.L, b, 0);
-    float* R1 = c.ws + lay.mat(lay.R, b, 1);
+    const int b = blockIdx.y, N = d.N, P8 = ar.P / 8, idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= N * P8) return;
+    const int r = idx / P8, dd = r - (idx % P8) * 8;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (dd >= 0 && dd < 8) w[dd >> 1] = 0x3F80u << ((dd & 1) * 16);       // bf16(1.0) on the diagonal
+    const uint4 h = make_uint4(w[0], w[1], w[2], w[3]), z = make_uint4(0u, 0u, 0u, 0u);
     const Mat2 l0 = mat2(c.wa, ar, d, kFamL, b, 0), r1 = mat2(c.wa, ar, d, kFamR, b, 1);
-    for (size_t i = threadIdx.x; i < (size_t)N * l0.P; i += blockDim.x) {
-        const int r = (int)(i / l0.P), cc = (int)(i % l0.P);
-        const float v = (r == cc) ? 1.0f : 0.0f;
-        if (cc < N) { L0[(size_t)r * N + cc] = v; R1[(size_t)r * N + cc] = v; }
-        const bf16 h = __float2bfloat16_rn(v), zz = __float2bfloat16_rn(0.0f);
-        l0.hi[i] = h; l0.lo[i] = zz;
-        r1.hi[i] = h; r1.lo[i] = zz;
+    reinterpret_cast<uint4*>(l0.hi)[idx] = h;
+    reinterpret_cast<uint4*>(l0.lo)[idx] = z;
+    reinterpret_cast<uint4*>(r1.hi)[idx] = h;
+    reinterpret_cast<uint4*>(r1.lo)[idx] = z;
+}
+
+// Small per-matrix vectors that live in workspace slots this path has no matrices for:
+//   column max / 1 / column sum of A_t   -> fp32 L slot, 2 N floats per (b, t)
+//   loss partials per block of 8 rows     -> fp32 R slot, ceil(N / 8) floats per (b, k)
+//   column sums of Q . dQ                 -> fp32 dL slot of the backward scratch, N floats per (b, t)
+__device__ __forceinline__ float* colstat_slot(const Ctx& c, const WalkLayout& lay, int b, int t) {
+    return c.ws + lay.L + ((size_t)b * (c.d.T - 1) + t) * 2 * c.d.N;
+}
+__device__ __forceinline__ size_t loss_slot(const WalkLayout& lay, int T, int nblk, int b, int k) {
+    return lay.R + ((size_t)b * (T - 1) + k) * nblk;
+}
+
+// column statistics for Q_t = colsoftmax(A_t): grid (ceil(N / 32), T-1, B); lanes on 32 consecutive columns (coalesced),
+// warps on rows i = warp, warp + 8, ...; the eight partials per column meet in shared memory in a fixed order
+__global__ void __launch_bounds__(256) t_colstats_kernel(Ctx c) {
+    __shared__ float part[8][32];
+    __shared__ float cm[32];
+    const Dims& d = c.d;
+    const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane, t = blockIdx.y, b = blockIdx.z, N = d.N;
+    const float* col = c.ws + lay.mat(lay.A, b, t) + (j < N ? j : 0);
+    float m = -INFINITY;
+#pragma unroll 4
+    for (int i = warp; i < N; i += 8) m = fmaxf(m, col[(size_t)i * N]);
+    part[warp][lane] = m;
+    __syncthreads();
+    if (warp == 0) {
+        float mm = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) mm = fmaxf(mm, part[w][lane]);
+        cm[lane] = mm;
+    }
+    __syncthreads();
+    const float cmx = cm[lane];
+    float a = 0.0f;
+#pragma unroll 4
+    for (int i = warp; i < N; i += 8) a += __expf(col[(size_t)i * N] - cmx);
+    part[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0 && j < N) {
+        float ss = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) ss += part[w][lane];
+        float* st = colstat_slot(c, lay, b, t);
+        st[j] = cmx;
+        st[N + j] = 1.0f / ss;
     }
 }
 
-// column statistics helper: every warp scans its rows (warp, warp+8, ...) with lanes on consecutive columns (coalesced),
-// the 8 partials per column meet in shared memory.  f(i, j) is the value at row i, column j.
-template <class F>
-__device__ __forceinline__ void column_max(float* out, float* part, int N, F f) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = lane; j < N; j += 32) {
-        float m = -INFINITY;
-        for (int i = warp; i < N; i += 8) m = fmaxf(m, f(i, j));
-        part[warp * N + j] = m;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        float m = part[j];
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, part[w * N + j]);
-        out[j] = m;
-    }
-    __syncthreads();
-}
-template <class F>
-__device__ __forceinline__ void column_sum(float* out, float* part, int N, F f) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int j = lane; j < N; j += 32) {
-        float a = 0.0f;
-        for (int i = warp; i < N; i += 8) a += f(i, j);
-        part[warp * N + j] = a;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        float a = part[j];
-        for (int w = 1; w < 8; ++w) a += part[w * N + j];
-        out[j] = a;
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) t_softmax_kernel(Ctx c) {    // grid (T-1, B): S_t = rowsoftmax(A_t), Q_t = colsoftmax(A_t)
-    extern __shared__ float sm_soft[];      // part[8][N], cmax[N], cinv[N]
+// grid (ceil(N / 8), T-1, B), one warp per row: S_t = rowsoftmax(A_t), Q_t = colsoftmax(A_t), fp32 (for the backward) and planes
+__global__ void __launch_bounds__(256) t_softmax_rows_kernel(Ctx c) {
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const TcArena ar(d, kNumSavedFam, true);
-    const int t = blockIdx.x, b = blockIdx.y, N = d.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* At = c.ws + lay.mat(lay.A, b, t);
-    float* S = c.ws + lay.mat(lay.S, b, t);
-    float* Q = c.ws + lay.mat(lay.Sp, b, t);
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y, b = blockIdx.z, N = d.N;
+    if (i >= N) return;
+    const float* row = c.ws + lay.mat(lay.A, b, t) + (size_t)i * N;
+    float* S = c.ws + lay.mat(lay.S, b, t) + (size_t)i * N;
+    float* Q = c.ws + lay.mat(lay.Sp, b, t) + (size_t)i * N;
     const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mq = mat2(c.wa, ar, d, kFamQ, b, t);
-    float* part = sm_soft;
-    float* cmax = part + 8 * N;
-    float* cinv = cmax + N;
-    column_max(cmax, part, N, [&](int i, int j) { return At[(size_t)i * N + j]; });
-    column_sum(cinv, part, N, [&](int i, int j) { return __expf(At[(size_t)i * N + j] - cmax[j]); });
-    for (int j = threadIdx.x; j < N; j += blockDim.x) cinv[j] = 1.0f / cinv[j];
-    __syncthreads();
-    for (int i = warp; i < N; i += 8) {
-        const float* row = At + (size_t)i * N;
-        float mx = -INFINITY;
-        for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
-        mx = warp_max(mx);
-        float se = 0.0f;
-        for (int j = lane; j < N; j += 32) se += __expf(row[j] - mx);
-        se = warp_sum(se);
-        const float inv = 1.0f / se;
-        for (int j = lane; j < N; j += 32) {
-            const float a = row[j];
-            const float sv = __expf(a - mx) * inv, qv = __expf(a - cmax[j]) * cinv[j];
-            S[(size_t)i * N + j] = sv;
-            Q[(size_t)i * N + j] = qv;
-            emit_one(ms, i, j, sv);
-            emit_one(mq, i, j, qv);
-        }
-        zero_row_pad(ms, i, N, lane);
-        zero_row_pad(mq, i, N, lane);
+    const float* cmax = colstat_slot(c, lay, b, t);
+    const float* cinv = cmax + N;
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float se = 0.0f;
+    for (int j = lane; j < N; j += 32) se += __expf(row[j] - mx);
+    se = warp_sum(se);
+    const float inv = 1.0f / se;
+#pragma unroll 2
+    for (int j = lane; j < N; j += 32) {
+        const float a = row[j];
+        const float sv = __expf(a - mx) * inv, qv = __expf(a - cmax[j]) * cinv[j];
+        S[j] = sv;
+        Q[j] = qv;
+        emit_one(ms, i, j, sv);
+        emit_one(mq, i, j, qv);
     }
+    zero_row_pad(ms, i, N, lane);
+    zero_row_pad(mq, i, N, lane);
 }
 
-__global__ void __launch_bounds__(256) t_cycle_epi_kernel(Ctx c) {  // grid (T-2, B): G_k = softmax(M_k) - I, loss partial
+// grid (ceil(N / 8), T-2, B), one warp per row: G_k = softmax(M_k) - I as planes, loss partial of the block of 8 rows
+__global__ void __launch_bounds__(256) t_cycle_rows_kernel(Ctx c) {
     __shared__ float red[8];
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const TcArena ar(d, kNumSavedFam, true);
-    const int k = blockIdx.x + 1, b = blockIdx.y, N = d.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* Gk = c.ws + lay.mat(lay.G, b, k);
-    const Mat2 mg = mat2(c.wa, ar, d, kFamG, b, k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r = blockIdx.x * 8 + warp, k = blockIdx.y + 1, b = blockIdx.z, N = d.N;
     float part = 0.0f;
-    for (int r = warp; r < N; r += 8) {
-        float* row = Gk + (size_t)r * N;
+    if (r < N) {
+        const float* row = c.ws + lay.mat(lay.G, b, k) + (size_t)r * N;       // raw M_k
+        const Mat2 mg = mat2(c.wa, ar, d, kFamG, b, k);
         float mx = -INFINITY;
         for (int cc = lane; cc < N; cc += 32) mx = fmaxf(mx, row[cc]);
         mx = warp_max(mx);
         float se = 0.0f;
         for (int cc = lane; cc < N; cc += 32) se += __expf(row[cc] - mx);
         se = warp_sum(se);
-        const float diag = row[r];
-        __syncwarp();
         const float inv = 1.0f / se;
-        for (int cc = lane; cc < N; cc += 32) {
-            const float v = __expf(row[cc] - mx) * inv - (cc == r ? 1.0f : 0.0f);
-            row[cc] = v;
-            emit_one(mg, r, cc, v);
-        }
+#pragma unroll 2
+        for (int cc = lane; cc < N; cc += 32) emit_one(mg, r, cc, __expf(row[cc] - mx) * inv - (cc == r ? 1.0f : 0.0f));
         zero_row_pad(mg, r, N, lane);
-        part += (logf(se) + mx) - diag;
+        part = (logf(se) + mx) - row[r];
     }
     if (lane == 0) red[warp] = part;
     __syncthreads();
     if (threadIdx.x == 0) {
         float s = 0.0f;
+#pragma unroll
         for (int w = 0; w < 8; ++w) s += red[w];
-        c.ws[lay.part + (size_t)b * (d.T - 1) + k] = s;
+        c.ws[loss_slot(lay, d.T, gridDim.x, b, k) + blockIdx.x] = s;
     }
 }
 
-__global__ void t_loss_reduce_kernel(const float* ws, float* loss, Dims d) {
+// one CTA, fixed summation order
+__global__ void __launch_bounds__(1024) t_loss_reduce_kernel(const float* ws, float* loss, Dims d, int nblk) {
+    __shared__ float red[32];
     const WalkLayout lay(d.B, d.T, d.N, d.C);
-    const int lane = threadIdx.x;
+    const int K = d.T - 2, total = d.B * K * nblk;
     float s = 0.0f;
-    for (int i = lane; i < d.B * (d.T - 2); i += 32) s += ws[lay.part + (size_t)(i / (d.T - 2)) * (d.T - 1) + i % (d.T - 2) + 1];
+    for (int idx = threadIdx.x; idx < total; idx += 1024) {
+        const int e = idx / nblk;
+        s += ws[loss_slot(lay, d.T, nblk, e / K, e % K + 1) + idx % nblk];
+    }
     s = warp_sum(s);
-    if (lane == 0) *loss = s / ((float)d.B * (float)d.N) / (float)d.N;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < 32; ++w) tot += red[w];
+        *loss = tot / ((float)d.B * (float)d.N) / (float)d.N;
+    }
 }
 __global__ void t_zero_loss_kernel(float* loss) { *loss = 0.0f; }
 
-__global__ void __launch_bounds__(256) t_dA_epi_kernel(Ctx c, const float* dA_ext) {   // grid (T-1, B)
-    extern __shared__ float sm_da[];   // part[8][N], rS[N], rQ[N]
+// rQ[j] = sum_i Q_t[i][j] dQ_t[i][j]: grid (ceil(N / 32), T-1, B), same shape as t_colstats_kernel
+__global__ void __launch_bounds__(256) t_dq_colsum_kernel(Ctx c) {
+    __shared__ float part[8][32];
+    const Dims& d = c.d;
+    const WalkLayout lay(d.B, d.T, d.N, d.C);
+    const BwdLayout bl(d.B, d.T, d.N);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane, t = blockIdx.y, b = blockIdx.z, N = d.N;
+    if (t + 1 > d.T - 2) return;
+    const size_t jo = (j < N ? j : 0);
+    const float* Q = c.ws + lay.mat(lay.Sp, b, t) + jo;
+    const float* dQ = c.sc + lay.mat(bl.dSp, b, t) + jo;
+    float a = 0.0f;
+#pragma unroll 4
+    for (int i = warp; i < N; i += 8) a += Q[(size_t)i * N] * dQ[(size_t)i * N];
+    part[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0 && j < N) {
+        float ss = part[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) ss += part[w][lane];
+        c.sc[bl.dL + ((size_t)b * (d.T - 1) + t) * N + j] = ss;
+    }
+}
+
+// grid (ceil(N / 8), T-1, B), one warp per row: dA_t = dA_ext + S.(dS - rowsum(S.dS)) + Q.(dQ - colsum(Q.dQ)) as planes
+__global__ void __launch_bounds__(256) t_dA_rows_kernel(Ctx c, const float* dA_ext) {
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const BwdLayout bl(d.B, d.T, d.N);
     const TcArena ab(d, kNumBwdFam, false);
-    const int t = blockIdx.x, b = blockIdx.y, N = d.N, K = d.T - 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y, b = blockIdx.z, N = d.N, K = d.T - 2;
+    if (i >= N) return;
     const bool hasQ = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
-    const float* S = c.ws + lay.mat(lay.S, b, t);
-    const float* Q = c.ws + lay.mat(lay.Sp, b, t);
-    const float* dS = c.sc + lay.mat(bl.dS, b, t);
-    const float* dQ = c.sc + lay.mat(bl.dSp, b, t);
+    const size_t ro = (size_t)i * N;
+    const float* S = c.ws + lay.mat(lay.S, b, t) + ro;
+    const float* Q = c.ws + lay.mat(lay.Sp, b, t) + ro;
+    const float* dS = c.sc + lay.mat(bl.dS, b, t) + ro;
+    const float* dQ = c.sc + lay.mat(bl.dSp, b, t) + ro;
+    const float* rQ = c.sc + bl.dL + ((size_t)b * (d.T - 1) + t) * N;
+    const float* ext = dA_ext ? dA_ext + ((size_t)b * (d.T - 1) + t) * N * N + ro : nullptr;
     const Mat2 ma = mat2(c.sa, ab, d, kFamDA, b, t);
-    const float* ext = dA_ext ? dA_ext + ((size_t)b * (d.T - 1) + t) * N * N : nullptr;
-    float* part = sm_da;
-    float* rS = part + 8 * N;
-    float* rQ = rS + N;
-    if (hasQ) column_sum(rQ, part, N, [&](int i, int j) { return Q[(size_t)i * N + j] * dQ[(size_t)i * N + j]; });
-    for (int i = warp; i < N; i += 8) {
-        float a = 0.0f;
-        if (hasS) {
-            for (int j = lane; j < N; j += 32) a = fmaf(S[(size_t)i * N + j], dS[(size_t)i * N + j], a);
-            a = warp_sum(a);
-        }
-        if (lane == 0) rS[i] = a;
+    float ri = 0.0f;
+    if (hasS) {
+        for (int j = lane; j < N; j += 32) ri = fmaf(S[j], dS[j], ri);
+        ri = warp_sum(ri);
     }
-    __syncthreads();
-    for (int i = warp; i < N; i += 8) {
-        const float ri = rS[i];
-        for (int j = lane; j < ma.P; j += 32) {
-            float g = 0.0f;
-            if (j < N) {
-                const size_t e = (size_t)i * N + j;
-                g = ext ? ext[e] : 0.0f;
-                if (hasS) g += S[e] * (dS[e] - ri);
-                if (hasQ) g += Q[e] * (dQ[e] - rQ[j]);
-            }
-            emit_one(ma, i, j, g);
+#pragma unroll 2
+    for (int j = lane; j < ma.P; j += 32) {
+        float g = 0.0f;
+        if (j < N) {
+            g = ext ? ext[j] : 0.0f;
+            if (hasS) g += S[j] * (dS[j] - ri);
+            if (hasQ) g += Q[j] * (dQ[j] - rQ[j]);
         }
+        emit_one(ma, i, j, g);
     }
 }
 
@@ -596,6 +737,12 @@ __global__ void __launch_bounds__(256) t_dx_epi_kernel(const float* __restrict__
 }
 
 // ---- host orchestration -----------------------------------------------------------------------------------
+static int device_sms() {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
 template <class P>
 static int launch_tiles(const P& p, const TMaps& maps, int Mrows, int Ncols, int batch, cudaStream_t st) {
     static bool opted[64] = {};   // per instantiation and device; the attribute is a per-device property of the function
@@ -606,19 +753,11 @@ static int launch_tiles(const P& p, const TMaps& maps, int Mrows, int Ncols, int
         if (dev >= 0 && dev < 64) opted[dev] = true;
     }
     if (batch <= 0) return CRW_OK;
-    if (batch > 65535) return CRW_ERR_UNSUPPORTED;       // the batch index rides in grid.z (the fp32 engine has no such limit)
-    dim3 grid(ceil_div(Ncols, kWTile), ceil_div(Mrows, kWTile), batch);
-    tc_tiles_kernel<P><<<grid, kTT, kWSmem, st>>>(p, maps);
+    const TileGrid tg{ceil_div(Mrows, kWTile), ceil_div(Ncols, kWTile), batch};
+    const long long total = (long long)tg.tiles_m * tg.tiles_n * batch;
+    if (total > (1ll << 30)) return CRW_ERR_UNSUPPORTED;
+    tc_tiles_kernel<P><<<(unsigned)std::min<long long>(total, device_sms()), kTT, kWSmem, st>>>(p, maps, tg);
     CRW_LAUNCH_RET();
-    return CRW_OK;
-}
-
-// the column-statistics kernels keep 10 N floats in shared memory
-template <class Kern>
-static int opt_in_rowwise_smem(Kern kern, int N) {
-    const size_t need = 10 * (size_t)N * sizeof(float);
-    if (need > 227 * 1024) return CRW_ERR_UNSUPPORTED;
-    if (need > 48 * 1024) CRW_CUDA_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     return CRW_OK;
 }
 
@@ -663,18 +802,23 @@ int walk_tiles_forward(const float* x, int B, int T, int N, int C, float tau, fl
         CRW_LAUNCH_RET();
         return CRW_OK;
     }
-    if ((rc = opt_in_rowwise_smem(t_softmax_kernel, N))) return rc;
-    t_softmax_kernel<<<dim3(T - 1, B), 256, 10 * N * sizeof(float), st>>>(c);
+    const int nblk = ceil_div(N, 8), ncb = ceil_div(N, 32);
+    t_colstats_kernel<<<dim3(ncb, T - 1, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
-    t_identity_kernel<<<B, 256, 0, st>>>(c);
+    t_softmax_rows_kernel<<<dim3(nblk, T - 1, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
+    {
+        const TcArena ar(d, kNumSavedFam, true);
+        t_identity_kernel<<<dim3(ceil_div(N * (ar.P / 8), 256), B), 256, 0, st>>>(c);
+        CRW_LAUNCH_RET();
+    }
     const int K = T - 2;
     for (int k = 1; k <= K; ++k)
         if ((rc = launch_tiles(ChainProb{c, k}, maps, N, N, k >= 2 ? 2 * B : B, st))) return rc;
     if ((rc = launch_tiles(CycleProb{c}, maps, N, N, B * K, st))) return rc;
-    t_cycle_epi_kernel<<<dim3(K, B), 256, 0, st>>>(c);
+    t_cycle_rows_kernel<<<dim3(nblk, K, B), 256, 0, st>>>(c);
     CRW_LAUNCH_RET();
-    t_loss_reduce_kernel<<<1, 32, 0, st>>>(ws, loss, d);
+    t_loss_reduce_kernel<<<1, 1024, 0, st>>>(ws, loss, d, nblk);
     CRW_LAUNCH_RET();
     return CRW_OK;
 }
@@ -695,8 +839,11 @@ int walk_tiles_backward(const float* x, const float* ws_c, const float* dloss, c
             if ((rc = launch_tiles(BwdChainProb{c, j}, maps, N, N, j >= 2 ? 2 * B : B, st))) return rc;
         if ((rc = launch_tiles(DsProb{c, dloss}, maps, N, N, 2 * B * (T - 1), st))) return rc;
     }
-    if ((rc = opt_in_rowwise_smem(t_dA_epi_kernel, N))) return rc;
-    t_dA_epi_kernel<<<dim3(T - 1, B), 256, 10 * N * sizeof(float), st>>>(c, dA_or_null);
+    if (T >= 3) {
+        t_dq_colsum_kernel<<<dim3(ceil_div(N, 32), T - 1, B), 256, 0, st>>>(c);
+        CRW_LAUNCH_RET();
+    }
+    t_dA_rows_kernel<<<dim3(ceil_div(N, 8), T - 1, B), 256, 0, st>>>(c, dA_or_null);
     CRW_LAUNCH_RET();
     if ((rc = launch_tiles(DxProb{c, dx, 1.0f / tau}, maps, N, C, B * T, st))) return rc;
     t_dx_epi_kernel<<<dim3(T, B), 256, 0, st>>>(x, ws, dx, d);
