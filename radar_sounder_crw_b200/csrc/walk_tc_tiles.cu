@@ -69,6 +69,21 @@ __device__ __forceinline__ void emit_one(const Mat2& mt, int r, int c, float v) 
     mt.hi[(size_t)r * mt.P + c] = h;
     mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+// two adjacent columns (c even) as one 4-byte store per plane / one 4-byte load per plane
+__device__ __forceinline__ void emit_pair(const Mat2& mt, int r, int c, float v0, float v1) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
+    *reinterpret_cast<__nv_bfloat162*>(mt.hi + (size_t)r * mt.P + c) = h;
+    *reinterpret_cast<__nv_bfloat162*>(mt.lo + (size_t)r * mt.P + c) = l;
+}
+__device__ __forceinline__ float2 read_pair(const Mat2& mt, int r, int c) {
+    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mt.hi + (size_t)r * mt.P + c));
+    const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mt.lo + (size_t)r * mt.P + c));
+    return make_float2(h.x + l.x, h.y + l.y);
+}
+__device__ __forceinline__ float read_one(const Mat2& mt, int r, int c) {
+    return __bfloat162float(mt.hi[(size_t)r * mt.P + c]) + __bfloat162float(mt.lo[(size_t)r * mt.P + c]);
+}
 // value for n < N, zero for the pad columns N <= n < pitch
 __device__ __forceinline__ void emit_pad(const Mat2& mt, int r, int n, float v, int N) {
     if (n < mt.P) emit_one(mt, r, n, n < N ? v : 0.0f);
@@ -570,7 +585,8 @@ __global__ void __launch_bounds__(256) t_colstats_kernel(Ctx c) {
     }
 }
 
-// grid (ceil(N / 8), T-1, B), one warp per row: S_t = rowsoftmax(A_t), Q_t = colsoftmax(A_t), fp32 (for the backward) and planes
+// grid (ceil(N / 8), T-1, B), one warp per row: S_t = rowsoftmax(A_t), Q_t = colsoftmax(A_t) as operand planes only (the
+// backward reads them back as hi + lo: 16 mantissa bits, far inside the 1e-3 gate); lanes on column PAIRS, pads written as zero
 __global__ void __launch_bounds__(256) t_softmax_rows_kernel(Ctx c) {
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
@@ -578,8 +594,6 @@ __global__ void __launch_bounds__(256) t_softmax_rows_kernel(Ctx c) {
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y, b = blockIdx.z, N = d.N;
     if (i >= N) return;
     const float* row = c.ws + lay.mat(lay.A, b, t) + (size_t)i * N;
-    float* S = c.ws + lay.mat(lay.S, b, t) + (size_t)i * N;
-    float* Q = c.ws + lay.mat(lay.Sp, b, t) + (size_t)i * N;
     const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mq = mat2(c.wa, ar, d, kFamQ, b, t);
     const float* cmax = colstat_slot(c, lay, b, t);
     const float* cinv = cmax + N;
@@ -591,16 +605,18 @@ __global__ void __launch_bounds__(256) t_softmax_rows_kernel(Ctx c) {
     se = warp_sum(se);
     const float inv = 1.0f / se;
 #pragma unroll 2
-    for (int j = lane; j < N; j += 32) {
-        const float a = row[j];
-        const float sv = __expf(a - mx) * inv, qv = __expf(a - cmax[j]) * cinv[j];
-        S[j] = sv;
-        Q[j] = qv;
-        emit_one(ms, i, j, sv);
-        emit_one(mq, i, j, qv);
+    for (int j = 2 * lane; j < ar.P; j += 64) {
+        float sv[2] = {0.0f, 0.0f}, qv[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            if (j + e < N) {
+                const float a = row[j + e];
+                sv[e] = __expf(a - mx) * inv;
+                qv[e] = __expf(a - cmax[j + e]) * cinv[j + e];
+            }
+        emit_pair(ms, i, j, sv[0], sv[1]);
+        emit_pair(mq, i, j, qv[0], qv[1]);
     }
-    zero_row_pad(ms, i, N, lane);
-    zero_row_pad(mq, i, N, lane);
 }
 
 // grid (ceil(N / 8), T-2, B), one warp per row: G_k = softmax(M_k) - I as planes, loss partial of the block of 8 rows
@@ -622,8 +638,13 @@ __global__ void __launch_bounds__(256) t_cycle_rows_kernel(Ctx c) {
         se = warp_sum(se);
         const float inv = 1.0f / se;
 #pragma unroll 2
-        for (int cc = lane; cc < N; cc += 32) emit_one(mg, r, cc, __expf(row[cc] - mx) * inv - (cc == r ? 1.0f : 0.0f));
-        zero_row_pad(mg, r, N, lane);
+        for (int cc = 2 * lane; cc < mg.P; cc += 64) {
+            float v[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (cc + e < N) v[e] = __expf(row[cc + e] - mx) * inv - (cc + e == r ? 1.0f : 0.0f);
+            emit_pair(mg, r, cc, v[0], v[1]);
+        }
         part = (logf(se) + mx) - row[r];
     }
     if (lane == 0) red[warp] = part;
@@ -665,12 +686,13 @@ __global__ void __launch_bounds__(256) t_dq_colsum_kernel(Ctx c) {
     const BwdLayout bl(d.B, d.T, d.N);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane, t = blockIdx.y, b = blockIdx.z, N = d.N;
     if (t + 1 > d.T - 2) return;
-    const size_t jo = (j < N ? j : 0);
-    const float* Q = c.ws + lay.mat(lay.Sp, b, t) + jo;
+    const int jo = (j < N ? j : 0);
+    const TcArena ar(d, kNumSavedFam, true);
+    const Mat2 mq = mat2(c.wa, ar, d, kFamQ, b, t);
     const float* dQ = c.sc + lay.mat(bl.dSp, b, t) + jo;
     float a = 0.0f;
 #pragma unroll 4
-    for (int i = warp; i < N; i += 8) a += Q[(size_t)i * N] * dQ[(size_t)i * N];
+    for (int i = warp; i < N; i += 8) a += read_one(mq, i, jo) * dQ[(size_t)i * N];
     part[warp][lane] = a;
     __syncthreads();
     if (warp == 0 && j < N) {
@@ -681,18 +703,18 @@ __global__ void __launch_bounds__(256) t_dq_colsum_kernel(Ctx c) {
     }
 }
 
-// grid (ceil(N / 8), T-1, B), one warp per row: dA_t = dA_ext + S.(dS - rowsum(S.dS)) + Q.(dQ - colsum(Q.dQ)) as planes
+// grid (ceil(N / 8), T-1, B), one warp per row: dA_t = dA_ext + S.(dS - rowsum(S.dS)) + Q.(dQ - colsum(Q.dQ)) as planes;
+// S and Q come back from their planes (hi + lo), lanes on column pairs
 __global__ void __launch_bounds__(256) t_dA_rows_kernel(Ctx c, const float* dA_ext) {
     const Dims& d = c.d;
     const WalkLayout lay(d.B, d.T, d.N, d.C);
     const BwdLayout bl(d.B, d.T, d.N);
-    const TcArena ab(d, kNumBwdFam, false);
+    const TcArena ar(d, kNumSavedFam, true), ab(d, kNumBwdFam, false);
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5), t = blockIdx.y, b = blockIdx.z, N = d.N, K = d.T - 2;
     if (i >= N) return;
     const bool hasQ = (t + 1 <= K), hasS = (t >= 1 && t + 1 <= K);
     const size_t ro = (size_t)i * N;
-    const float* S = c.ws + lay.mat(lay.S, b, t) + ro;
-    const float* Q = c.ws + lay.mat(lay.Sp, b, t) + ro;
+    const Mat2 ms = mat2(c.wa, ar, d, kFamS, b, t), mq = mat2(c.wa, ar, d, kFamQ, b, t);
     const float* dS = c.sc + lay.mat(bl.dS, b, t) + ro;
     const float* dQ = c.sc + lay.mat(bl.dSp, b, t) + ro;
     const float* rQ = c.sc + bl.dL + ((size_t)b * (d.T - 1) + t) * N;
@@ -700,18 +722,30 @@ __global__ void __launch_bounds__(256) t_dA_rows_kernel(Ctx c, const float* dA_e
     const Mat2 ma = mat2(c.sa, ab, d, kFamDA, b, t);
     float ri = 0.0f;
     if (hasS) {
-        for (int j = lane; j < N; j += 32) ri = fmaf(S[j], dS[j], ri);
+        for (int j = 2 * lane; j < N; j += 64) {
+            const float2 sv = read_pair(ms, i, j);       // pads are zero
+            ri = fmaf(sv.x, dS[j], ri);
+            if (j + 1 < N) ri = fmaf(sv.y, dS[j + 1], ri);
+        }
         ri = warp_sum(ri);
     }
 #pragma unroll 2
-    for (int j = lane; j < ma.P; j += 32) {
-        float g = 0.0f;
+    for (int j = 2 * lane; j < ma.P; j += 64) {
+        float g[2] = {0.0f, 0.0f};
         if (j < N) {
-            g = ext ? ext[j] : 0.0f;
-            if (hasS) g += S[j] * (dS[j] - ri);
-            if (hasQ) g += Q[j] * (dQ[j] - rQ[j]);
+            const float2 sv = hasS ? read_pair(ms, i, j) : make_float2(0.f, 0.f);
+            const float2 qv = hasQ ? read_pair(mq, i, j) : make_float2(0.f, 0.f);
+            const float s2[2] = {sv.x, sv.y}, q2[2] = {qv.x, qv.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (j + e < N) {
+                    float v = ext ? ext[j + e] : 0.0f;
+                    if (hasS) v += s2[e] * (dS[j + e] - ri);
+                    if (hasQ) v += q2[e] * (dQ[j + e] - rQ[j + e]);
+                    g[e] = v;
+                }
         }
-        emit_one(ma, i, j, g);
+        emit_pair(ma, i, j, g[0], g[1]);
     }
 }
 
