@@ -622,6 +622,16 @@ def run_b200(args):
                     f"B{4 * TRAIN['B']}": dict(ms=rf128["ms"], ms_eager_dispatch=rf128["ms_eager"], launches=2, kernels="one CTA per batch element",
                                               tflops=rf128["roofline"]["achieved"], eight_kernel_engine_ms=rd128["ms"],
                                               eight_kernel_engine_ms_eager=rd128["ms_eager"])}
+    # the large-N tile engine (walk_tc_tiles.cu) at the scaled geometries of SURVEY appendix D -- never reference-size figures
+    wk_scaled = None
+    if only == "all" and world == 1:
+        wk_scaled = []
+        for n in (185, 369):
+            r = bench_walk(crw, args, world, pk, N=n, T=20, B=32, precision=crw.ops.PREC_BF16X3, launches=51,
+                           kernel_note="persistent tcgen05 tile engine (TMA-fed bf16 hi/lo planes, 3 MMA passes; algorithmic FLOPs counted once)")
+            wk_scaled.append(dict(shape=r["shape"], ms=r["ms"], launches=51, tflops_algorithmic=r["roofline"]["achieved"],
+                                  frac_of_bf16_peak=r["roofline"]["frac"], note="scaled geometry (SURVEY appendix D), not a reference-size figure"))
+        torch.cuda.empty_cache()
     lp = bench_labelprop(crw, args, rank, world, pk) if only in ("all", "labelprop") else None
     # the multi-GPU configurations BASELINE names (config 4: T=20 + UNet-as-encoder, data parallel; config 5: 64 radargrams of
     # 50k columns sharded over the ranks, strong scaling) ride in the same line as objects of their own
@@ -664,7 +674,7 @@ def run_b200(args):
                                  note="precision=FP32: shared-memory-resident fp32 FMA kernels (round 1's train-step path)"),
                        bf16x3_eight_kernels=dict(ms=wk_tc["ms"], ms_eager_dispatch=wk_tc["ms_eager"], launches=8,
                                                  note="precision=BF16X3 with CRW_WALK_FUSED=0: shared-memory kernels, warp-level mma.sync"),
-                       fused_by_batch=wk_fused)
+                       fused_by_batch=wk_fused, scaled_geometry_tile_engine=wk_scaled)
             line = dict(
                 metric="crw_train_radargrams_per_sec", value=tr["value"], unit="radargrams/s", n_gpus=world,
                 steps=args.steps, warmup=args.warmup, ms_per_step=tr["ms_per_step"], higher_is_better=True,
