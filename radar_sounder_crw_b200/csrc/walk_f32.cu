@@ -397,7 +397,7 @@ using namespace crw;
 // CRW_WALK_FUSED=1 / 0 forces the choice.  (Forward and backward see the same B, T, N, C and environment, hence the same layout
 // of `saved`.)
 static bool walk_use_fused(int B, int T, int N, int C) {
-    if (!walk_fused_supported(N, C, T)) return false;
+    if (!walk_fused_supported(N, C, T) || getenv("CRW_WALK_FORCE_TILES")) return false;      // the test switch for the tile engine wins
     const char* e = getenv("CRW_WALK_FUSED");
     if (e) return atoi(e) != 0;
     return B >= 96 || walk_fused_roles_apply(B);

@@ -319,6 +319,8 @@ WALK_TC_CASES = [
     (2, 4, 12, 32, 0.07),      # K = 32 (half a chunk), K = 12
     (2, 3, 9, 16, 0.05),       # T = 3
     (2, 7, 24, 128, 0.01),     # the reference's train default tau
+    (1, 4, 300, 128, 0.07),    # 3 x 3 output tiles, five k-chunks with a 44-wide tail, a third tile row of 44 rows
+    (3, 4, 130, 96, 0.07),     # tiles that are almost empty (2 rows / 2 columns), C = 96: E boxes zero-filled past the channels
 ]
 
 
@@ -347,6 +349,40 @@ def test_walk_tensorcore_vs_f64_oracle(pkg, case, walk_engine):
     assert rel_err(A.detach().cpu().numpy(), wo.affinities(wo.l2_normalize(x.astype(np.float64)), tau)) < 1e-4
     err = rel_err(xt.grad.cpu().numpy(), dx64)
     assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("N,T", [(21, 3), (100, 4), (150, 5)])
+def test_walk_tile_engine_grad_through_returned_A(pkg, monkeypatch, N, T):
+    """The reference returns A as a differentiable tensor (model.py:46): on the tile engine an incoming dA joins the softmax
+    backward in t_dA_rows_kernel and reaches x through both dE products, also through the last affinity (which the loss never sees)."""
+    monkeypatch.setenv("CRW_WALK_FORCE_TILES", "1")
+    rs = np.random.RandomState(N + T)
+    B = 2
+    x = rs.randn(B, T, N, 128).astype(np.float32)
+    Gext = rs.randn(B, T - 1, N, N).astype(np.float32)
+    xt = _dev(x).requires_grad_(True)
+    loss, A, _ = pkg.ops.walk_loss(xt, 0.07, True, pkg.ops.PREC_BF16X3)
+    (loss + (A * _dev(Gext)).sum()).backward()
+    xr = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    E = torch.nn.functional.normalize(xr, dim=-1)
+    Ar = torch.einsum("btnc,btmc->btnm", E[:, :-1], E[:, 1:]) / 0.07
+    (Ar * torch.tensor(Gext, dtype=torch.float64)).sum().backward()
+    _, _, _, dx_loss = wo.walk_backward_chain(x.astype(np.float64), 0.07)
+    assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy() + dx_loss) < 1e-3
+
+
+def test_walk_tile_engine_is_deterministic(pkg, monkeypatch):
+    """Every reduction of the tile engine has a fixed order (per-block loss partials, column statistics): two runs agree bit for bit."""
+    monkeypatch.setenv("CRW_WALK_FORCE_TILES", "1")
+    x = torch.randn(2, 5, 140, 128, device="cuda")
+    outs = []
+    for _ in range(2):
+        xt = x.clone().requires_grad_(True)
+        loss, A, _ = pkg.ops.walk_loss(xt, 0.07, True, pkg.ops.PREC_BF16X3)
+        loss.backward()
+        outs.append((loss.detach().clone(), A.detach().clone(), xt.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
 
 
 def test_walk_tensorcore_golden_reference(pkg, walk_engine):
