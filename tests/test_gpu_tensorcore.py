@@ -371,6 +371,27 @@ def test_walk_tile_engine_grad_through_returned_A(pkg, monkeypatch, N, T):
     assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy() + dx_loss) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(8, 20, 185), (24, 6, 47), (2, 8, 369)])
+def test_walk_tile_engine_many_tiles_per_cta_matches_fp32_engine(pkg, monkeypatch, shape):
+    """More tiles than SMs: every persistent CTA walks several tiles, so the two TMEM accumulators, the stage ring and their
+    barrier phases wrap around many times (the oracle cases above give each CTA at most one tile).  Checked against the fp32
+    FMA engine (itself pinned to the fp64 oracle) at sizes the numpy oracle would take minutes for."""
+    B, T, N = shape
+    monkeypatch.setenv("CRW_WALK_FORCE_TILES", "1")
+    torch.manual_seed(B + T + N)
+    x = torch.randn(B, T, N, 128, device="cuda") + torch.randn(B, 1, 1, 128, device="cuda")
+    Gext = torch.randn(B, T - 1, N, N, device="cuda") * 0.01
+    out = {}
+    for name, prec in [("tiles", pkg.ops.PREC_BF16X3), ("fp32", pkg.ops.PREC_FP32)]:
+        xt = x.clone().requires_grad_(True)
+        loss, A, _ = pkg.ops.walk_loss(xt, 0.07, True, prec)
+        (loss + (A * Gext).sum()).backward()
+        out[name] = (loss.item(), A.detach().cpu().numpy(), xt.grad.cpu().numpy())
+    assert abs(out["tiles"][0] - out["fp32"][0]) <= 1e-4 * abs(out["fp32"][0])
+    assert rel_err(out["tiles"][1], out["fp32"][1]) < 1e-4
+    assert rel_err(out["tiles"][2], out["fp32"][2]) < 1e-3
+
+
 def test_walk_tile_engine_is_deterministic(pkg, monkeypatch):
     """Every reduction of the tile engine has a fixed order (per-block loss partials, column statistics): two runs agree bit for bit."""
     monkeypatch.setenv("CRW_WALK_FORCE_TILES", "1")
