@@ -1,22 +1,29 @@
 // walk_tc_tiles.cu -- tile-parallel tensor-core walk (precision = CRW_PREC_BF16X3), any N.
 //
 // Same algorithm and reference mapping as walk_f32.cu (src/model.py:22-46 and its autograd).  Here
-//   * every GEMM is a grid of independent 128 x 128 output tiles, one CTA each: tcgen05.mma kind::f16 on
-//     error-compensated bf16 pairs (x = hi + lo; passes hi.hi, hi.lo, lo.hi), fp32 accumulator in TMEM;
-//   * every matrix that is ever a GEMM operand is kept, next to its fp32 copy, as two ROW-MAJOR bf16 planes (hi, lo;
-//     row pitch padded to 8 elements, pads zero), written by the epilogue that produces it with 16-byte stores;
+//   * every GEMM is a list of 128 x 128 output tiles walked by a PERSISTENT grid (one CTA per SM): tcgen05.mma kind::f16 on
+//     error-compensated bf16 pairs (x = hi + lo; passes hi.hi, hi.lo, lo.hi), fp32 accumulators in TMEM -- two of 128
+//     columns, so a tile drains while the next one accumulates;
+//   * every matrix that is ever a GEMM operand lives as two ROW-MAJOR bf16 planes (hi, lo; row pitch padded to 64 elements
+//     = 128-byte rows, pads zero), written by the epilogue that produces it with 16-byte stores straight from the registers;
+//     S, Q, L, R, G and the chain adjoints exist only as planes (the backward reads S, Q back as hi + lo);
 //   * an operand used as stored is a K-major tile, an operand used transposed is an MN-major tile of the SAME plane
 //     (UMMA majorness bits + LBO/SBO descriptors, pinned by crw_debug_umma_mn_gemm) -- no transposed copies;
 //   * staging is TMA: three tensor maps (the E planes, the saved families, the backward families) describe every plane
 //     as a stack of matrices, one 64 x 64-element SWIZZLE_128B box is the unit (a K-major tile = two boxes along the rows,
-//     an MN-major tile = two boxes along the columns; rows / columns / k past the matrix are zero-filled by the TMA), one
-//     elected lane of warp 0 produces three stages ahead (full / empty mbarriers), one elected lane of warp 1 issues the
-//     MMAs, the other warps sleep on the accumulator barrier until the epilogue;
+//     an MN-major tile = two boxes along the columns; rows / columns / k past the matrix are zero-filled by the TMA), three
+//     stages of 64 KB with full / empty mbarriers;
+//   * roles: warp 0 = one TMA lane, warp 1 = one MMA lane (owns the tensor memory), warps 2-9 = epilogue (TMEM lane quarter x
+//     column half).  A problem describes the products of a tile ONCE (`mainloop`); the TMA lane runs that description with a
+//     Loader, the MMA lane with an Issuer, so the two cannot disagree about the order of the k-chunks;
 //   * S'_t = softmax(A_t^T) is never materialised: the path keeps Q_t = S'_t^T = column-softmax(A_t) (same orientation
 //     as A_t, so softmax forward / backward are transposition-free and coalesced) and uses it through the other majorness;
-//   * the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in small kernels;
+//   * the row-wise work (softmax, cycle cross-entropy, softmax backward, normalise backward) lives in small kernels on
+//     (block of 8 rows, t, b) grids, one warp per row, lanes on column pairs; column statistics in kernels of their own;
 //   * the L / R chains and their adjoints are one launch per step (both chains in one grid): the only serialisation
 //     left is the algorithm's own 2(T-3) dependent products forward and backward.
+// What bounds the tile kernels (last part): the shared-memory port -- an SS-form M128 x N128 x K16 MMA
+// reads 8 KB of operands in its 64 cycles and the TMA writes the next stage through the same 128 B/clk.
 #include "common.cuh"
 #include "walk_layout.cuh"
 #include "tc_common.cuh"
