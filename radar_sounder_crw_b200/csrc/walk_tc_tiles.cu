@@ -67,15 +67,6 @@ __device__ __forceinline__ Mat2 mat2(bf16* arena, const TcArena& a, const Dims& 
     bf16* base = arena + a.fam0 + (size_t)fam * 2 * a.plane + ((size_t)b * (d.T - 1) + t) * d.N * a.P;
     return Mat2{base, base + a.plane, a.P};
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void emit_one(const Mat2& mt, int r, int c, float v) {
-    const bf16 h = __float2bfloat16_rn(v);
-    mt.hi[(size_t)r * mt.P + c] = h;
-    mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(v - __bfloat162float(h));
-}
 // two adjacent columns (c even) as one 4-byte store per plane / one 4-byte load per plane
 __device__ __forceinline__ void emit_pair(const Mat2& mt, int r, int c, float v0, float v1) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
@@ -90,13 +81,6 @@ __device__ __forceinline__ float2 read_pair(const Mat2& mt, int r, int c) {
 }
 __device__ __forceinline__ float read_one(const Mat2& mt, int r, int c) {
     return __bfloat162float(mt.hi[(size_t)r * mt.P + c]) + __bfloat162float(mt.lo[(size_t)r * mt.P + c]);
-}
-// value for n < N, zero for the pad columns N <= n < pitch
-__device__ __forceinline__ void emit_pad(const Mat2& mt, int r, int n, float v, int N) {
-    if (n < mt.P) emit_one(mt, r, n, n < N ? v : 0.0f);
-}
-__device__ __forceinline__ void zero_row_pad(const Mat2& mt, int r, int N, int lane) {
-    for (int c = N + lane; c < mt.P; c += 32) { mt.hi[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); mt.lo[(size_t)r * mt.P + c] = __float2bfloat16_rn(0.f); }
 }
 
 // ---- persistent tile engine ------------------------------------------------------------------------------
