@@ -165,7 +165,7 @@ constexpr int kEpWarps = 8;
 constexpr int kEpStage = 32 * 32 * 4;               // bytes per epilogue warp
 __device__ __forceinline__ uint32_t bf162_bits(const __nv_bfloat162& h) { return *reinterpret_cast<const uint32_t*>(&h); }
 struct Drainer {
-    const TMaps* maps; uint32_t acc; float* stg;
+    const TMaps* maps; uint32_t acc; uint32_t stg;      // stg: shared-space address of this warp's staging block (explicit st/ld.shared)
     // pads: columns N <= n < pitch are written as zero, rows >= Mvalid not at all
     __device__ __forceinline__ void planes(int m0, int n0, int Mvalid, const Mat2& om, int N) {
         const int w = (threadIdx.x >> 5) - 2, q = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
@@ -215,28 +215,30 @@ struct Drainer {
             tc::tmem_ld_32x32b_x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int cc = 0; cc < 32; ++cc) stg[lane * 32 + (cc ^ lane)] = v[cc] * scale;
+            for (int cc = 0; cc < 32; ++cc) tc::sts_f32(stg + (uint32_t)(lane * 128) + (uint32_t)((cc ^ lane) << 2), v[cc] * scale);
             __syncwarp();
             const bool cok = nb + lane < Nvalid;
             const size_t off = (size_t)(m0 + q * 32) * pitch + nb + lane;
             float* o = out + off;
             if (rows == 32) {
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const float x = stg[r * 32 + (lane ^ r)];
-                    if (cok) o[(size_t)r * pitch] = x;
-                }
-                if (out2) {
-                    float* o2 = out2 + off;
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const float x = stg[r * 32 + (lane ^ r)];
-                        if (cok) o2[(size_t)r * pitch] = x;
+                // eight staged rows in registers before their stores go out (the shared-space loads are explicit and ordered)
+#pragma unroll 1
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = tc::lds_f32(stg + (uint32_t)((r0 + i) * 128) + (uint32_t)((lane ^ (r0 + i)) << 2));
+                    if (cok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[(size_t)(r0 + i) * pitch] = x[i];
+                        if (out2) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) out2[off + (size_t)(r0 + i) * pitch] = x[i];
+                        }
                     }
                 }
             } else {
                 for (int r = 0; r < rows; ++r) {
-                    const float x = stg[r * 32 + (lane ^ r)];
+                    const float x = tc::lds_f32(stg + (uint32_t)(r * 128) + (uint32_t)((lane ^ r) << 2));
                     if (cok) {
                         o[(size_t)r * pitch] = x;
                         if (out2) out2[off + (size_t)r * pitch] = x;
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(kTT, 1) tc_tiles_kernel(const __grid_constant_
         }
         __syncwarp();
     } else {
-        Drainer dr{&maps, 0, reinterpret_cast<float*>(pp.buf + kWStages * kWStage + (warp - 2) * kEpStage)};
+        Drainer dr{&maps, 0, tc::smem_u32(pp.buf + kWStages * kWStage + (warp - 2) * kEpStage)};
         uint32_t n = 0;
         for (int i = blockIdx.x; i < total; i += gridDim.x) {
             const int z = i / per_z, r = i % per_z;
