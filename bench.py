@@ -289,11 +289,23 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=int(os.environ.get("CRW_BENCH_BUCKET_MB", "5")),
                                                           broadcast_buffers=bool(int(os.environ.get("CRW_BENCH_DDP_BCAST", "0"))))
-    elif world > 1:
-        # default: the parameters' gradients are views of ONE flat buffer, averaged by one NCCL all-reduce after backward
-        # (parallel.FlatGradients): no hooks, no buckets, no copies -- measured against DDP in DESIGN.md section 5
-        fg = crw.parallel.FlatGradients(model.parameters(), world)
-    opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"], fused=True)   # train-loop glue
+    # train-loop glue (scripts/train.py:56,70-72).  optim.FlatAdam: parameters, gradients and moments as views of flat
+    # buffers, zero_grad = one memset, step = one SUM all-reduce of the gradient buffer + ONE launch of crw_b200::adam_step over all
+    # parameters (the 1 / world rides in the kernel).  Default for N > 1: 34.71 ms per step on 2 B200s against 34.82 ms for
+    # parallel.FlatGradients + torch.optim.Adam(fused=True).  At N = 1 torch's optimizer on fresh gradients stays the default
+    # (34.53 against 34.66 ms: autograd ACCUMULATES into gradient views that already exist, one add per parameter, where
+    # zero_grad(set_to_none) lets it hand the fresh gradient over).  CRW_BENCH_FLAT_ADAM=0 / 1 forces one or the other.
+    use_flat = (world > 1) if os.environ.get("CRW_BENCH_FLAT_ADAM") is None else bool(int(os.environ["CRW_BENCH_FLAT_ADAM"]))
+    use_flat = use_flat and not os.environ.get("CRW_BENCH_DDP")
+    flat = None
+    if use_flat:
+        opt = flat = crw.optim.FlatAdam(model.parameters(), lr=TRAIN["lr"], world=world)
+    else:
+        if world > 1 and not os.environ.get("CRW_BENCH_DDP"):
+            # the parameters' gradients are views of ONE flat buffer, averaged by one NCCL all-reduce after backward
+            # (parallel.FlatGradients): no hooks, no buckets, no copies -- measured against DDP in DESIGN.md section 5
+            fg = crw.parallel.FlatGradients(model.parameters(), world)
+        opt = torch.optim.Adam(model.parameters(), lr=TRAIN["lr"], fused=True)
     last_loss = [None]
 
     def train_step(i, src=batches_dev):
@@ -301,7 +313,10 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         if not seq.is_cuda:
             seq = seq.cuda(non_blocking=True)
         loss, _ = model(seq)
-        if fg is not None:
+        if flat is not None:
+            flat.zero_grad()
+            loss.backward()
+        elif fg is not None:
             fg.zero()
             loss.backward()
             fg.reduce()
@@ -338,7 +353,11 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
         enqueue_copy(i + 1)                                        # next step's input, overlapped with this step
         torch.cuda.current_stream().wait_event(ready[slot])
         loss, _ = model(dev_buf[slot])
-        if fg is not None:
+        if flat is not None:
+            flat.zero_grad()
+            loss.backward()
+            consumed[slot].record()
+        elif fg is not None:
             fg.zero()
             loss.backward()
             consumed[slot].record()
@@ -359,6 +378,7 @@ def bench_train(crw, args, rank, world, local, pk, cfg4=False):
 
     ms_e2e = timed_loop(train_step_e2e_seq, steps, 2 if cfg4 else 3, world)
     return dict(steps=steps, warmup=warm, frames=T, ms_per_step=ms, value=B * world / (ms * 1e-3), N=N, clocks=sampler.summary(), loss=float(last_loss[0]),
+                optimizer=("optim.FlatAdam (crw_b200::adam_step, one launch over all parameters)" if flat is not None else "torch.optim.Adam(fused=True)"),
                 e2e=dict(value=B * world / (ms_e2e * 1e-3), unit="radargrams/s",
                          h2d_bytes_per_step=int(batches_host[0].numel() * 4), d2h_bytes_per_step=4))
 
@@ -685,7 +705,7 @@ def run_b200(args):
                             global_batch=B * world, frames=T, nodes=tr["N"], tau=TRAIN["tau"],
                             parallelism=f"dp{world}" + (" (one process per GPU, ONE NCCL all-reduce of the 19.9 MB of encoder gradients per step: parallel.FlatGradients)" if world > 1 else ""),
                             l2="4 rotating input batches (246 MB) > L2"),
-                clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=wk["launches"] * args.steps,
+                clocks=tr["clocks"], e2e=tr["e2e"], gpu_launches=(wk["launches"] + (1 if tr["optimizer"].startswith("optim.FlatAdam") else 0)) * args.steps,
                 roofline=wk["roofline"], hot_path=hot, loss=tr["loss"],
                 cpu_baseline=(cpu["train"] if cpu else None), labelprop=lp)
             line["host_link"] = dict(h2d_gbs_per_rank_all_ranks_copying=h2d, rank0_numa=numa,

@@ -220,6 +220,18 @@ int crw_fuse_reversed(const float* fwd, const float* rev, int H, int64_t W, int 
                       void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Optimizer step of the train loop -- replaces `optimizer.step()` of scripts/train.py:56,72 (torch.optim.Adam(lr), amsgrad
+ * and maximize off) for ALL parameters at once: params / grads / exp_avg / exp_avg_sq are flat f32 device buffers of n
+ * elements (16-byte aligned; radar_sounder_crw_b200.optim.FlatAdam lays every parameter and its gradient out as views of
+ * such buffers), one elementwise launch.  `step` = 1 for the first call (bias corrections 1 - beta^step are computed in
+ * double on the host from the double hyper-parameters, as torch does with its python floats); the gradient is read as grad_scale * grads (1 / world after a SUM all-reduce).
+ *   g' = grad_scale g + weight_decay p;  m += (g' - m)(1 - beta1);  v = beta2 v + (1 - beta2) g'^2;
+ *   p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * ---------------------------------------------------------------------------------- */
+int crw_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Self-test of the tensor-core plumbing (TMA SWIZZLE_128B tiles -> tcgen05.mma -> TMEM -> tcgen05.ld):
  *   out[128,BN] = A[128,128] * B[BN,128]^T, A/B bf16 row-major, out fp32; BN multiple of 16, <= 256.
  * No reference counterpart; it pins the descriptor encodings the tensor-core kernels rely on.

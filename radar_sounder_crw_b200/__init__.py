@@ -14,6 +14,7 @@ use, and the first op call raises when it has not been built (``_lib.lib()``).
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401
 from . import parallel  # noqa: F401
+from . import optim  # noqa: F401
 from .model import CRW  # noqa: F401
 from .labelprop import LabelPropVOS_CRW  # noqa: F401
 from .maskedatt import MaskedAttention, batched_affinity  # noqa: F401

@@ -44,6 +44,7 @@ SIGNATURES = {
     "crw_labels_upsample": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "crw_patch_unfold": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   _c_int, _c_int, _vp, _vp]),
+    "crw_adam_step": (_c_int, [_vp, _vp, _vp, _vp, _c_i64] + [ctypes.c_double] * 5 + [_c_i64, ctypes.c_double, _vp]),
     "crw_seed_labels": (_c_int, [_vp, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "crw_fuse_reversed_scratch_bytes": (_c_sz, [_c_i64]),
     "crw_fuse_reversed": (_c_int, [_vp, _vp, _c_int, _c_i64, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),

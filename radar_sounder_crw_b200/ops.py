@@ -389,3 +389,23 @@ def fuse_reversed(fwd: Tensor, rev: Tensor, rg_len: int, rule: int) -> Tensor:
 @fuse_reversed.register_fake
 def _(fwd, rev, rg_len, rule):
     return torch.empty_like(fwd)
+
+
+# ------------------------------------------------------------------------------------------------
+# adam_step  (scripts/train.py:56,72: torch.optim.Adam over flat buffers, one launch)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("crw_b200::adam_step", mutates_args=("params", "exp_avg", "exp_avg_sq"))
+def adam_step(params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, beta1: float, beta2: float,
+              eps: float, weight_decay: float, step: int, grad_scale: float) -> None:
+    """In place: one torch.optim.Adam update of the flat f32 buffer ``params`` from ``grad_scale * grads``; ``step`` counts from 1."""
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 1 or t.numel() != params.numel():
+            raise RuntimeError(f"crw_b200::adam_step: `{name}` must be a contiguous 1-D f32 CUDA tensor of the parameters' length")
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.lib().crw_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
+                                            weight_decay, step, grad_scale, _stream()), "crw_adam_step")
+
+
+@adam_step.register_fake
+def _(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale):
+    return None

@@ -64,7 +64,10 @@ class FlatGradients:
     def __init__(self, params: Iterable[torch.nn.Parameter], world: int, group=None):
         self.ps = [p for p in params if p.requires_grad]
         self.world, self.group = world, group
-        n = sum(p.numel() for p in self.ps)
+        # every view starts on a 256-byte boundary so that the backward's accumulate kernels keep their vector accesses (with
+        # optim.FlatAdam, where the PARAMETERS are such views too, unaligned views cost 0.35 ms of the 34.5 ms step); pads stay zero
+        pad = lambda k: (k + 63) // 64 * 64      # noqa: E731
+        n = sum(pad(p.numel()) for p in self.ps)
         ref = self.ps[0]
         self.flat = torch.zeros(n, device=ref.device, dtype=ref.dtype)
         off = 0
@@ -74,7 +77,7 @@ class FlatGradients:
                 p.grad = torch.as_strided(self.flat, p.size(), p.stride(), off)
             else:
                 p.grad = self.flat[off:off + p.numel()].view(p.size())
-            off += p.numel()
+            off += pad(p.numel())
 
     def zero(self) -> None:
         self.flat.zero_()
